@@ -1,0 +1,250 @@
+/*
+ * oracle/ref_harness.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Thin glue that is compiled TOGETHER WITH the reference's own, unmodified source files
+ * (taken where they lie under /root/reference; see oracle/Makefile) into
+ * oracle/_ref/libsrslte_ref.so.  It adds nothing to the arithmetic: every function here
+ * only allocates reference objects and calls the reference's public API, so that the
+ * tests and the CPU-baseline leg of bench.py can drive the real srslte_tdec_* /
+ * srslte_dlsch_* code through ctypes without knowing struct layouts.
+ *
+ * Reference API used: turbodecoder.h:97-135, turbocoder.h:54-61, rm_turbo.h:45-93,
+ * crc.h:48-83, sch.h:76-115, softbuffer.h:52-76 (all under lib/include/srslte/phy).
+ */
+#define _GNU_SOURCE
+#include <pthread.h>
+#include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "srslte/srslte.h"
+
+/* ---- sizes, so that python can cross-check the ABI mirror in include/ ---- */
+size_t refh_sizeof_tdec(void) { return sizeof(srslte_tdec_t); }
+size_t refh_sizeof_sch(void) { return sizeof(srslte_sch_t); }
+size_t refh_sizeof_crc(void) { return sizeof(srslte_crc_t); }
+size_t refh_sizeof_softbuffer_rx(void) { return sizeof(srslte_softbuffer_rx_t); }
+size_t refh_sizeof_cbsegm(void) { return sizeof(srslte_cbsegm_t); }
+size_t refh_offsetof_tdec_n_iter(void) { return offsetof(srslte_tdec_t, n_iter); }
+size_t refh_offsetof_sch_decoder(void) { return offsetof(srslte_sch_t, decoder); }
+
+/* ---- decoder handle ---- */
+srslte_tdec_t* refh_tdec_new(uint32_t max_k, int impl /* 0 = AUTO */)
+{
+  srslte_tdec_t* h = (srslte_tdec_t*)srslte_vec_malloc(sizeof(srslte_tdec_t));
+  if (!h) return NULL;
+  if (srslte_tdec_init_manual(h, max_k, (srslte_tdec_impl_type_t)impl)) {
+    free(h);
+    return NULL;
+  }
+  return h;
+}
+
+void refh_tdec_free(srslte_tdec_t* h)
+{
+  if (h) {
+    srslte_tdec_free(h);
+    free(h);
+  }
+}
+
+/* soft values the decision was taken from (SB storage order for window decoders) */
+const int16_t* refh_tdec_llr_ptr(srslte_tdec_t* h)
+{
+  return (h->n_iter % 2) == 0 ? (const int16_t*)h->app1 : (const int16_t*)h->ext1;
+}
+
+/* ---- batch of srslte_tdec_run_all, `threads` pthreads, one handle per thread ---- */
+typedef struct {
+  const int16_t* in;
+  uint8_t*       out;
+  uint32_t       in_stride, out_stride, first, last, K, nit;
+  int            natural, rc;
+} job_t;
+
+static void* worker(void* arg)
+{
+  job_t*         j = (job_t*)arg;
+  srslte_tdec_t* h = refh_tdec_new(6144, 0);
+  if (!h) {
+    j->rc = -1;
+    return NULL;
+  }
+  if (j->natural) srslte_tdec_force_not_sb(h);
+  /* run_all re-reads `input` in SB mode and writes the tail copies into its pads: give it
+   * a private aligned copy, as the reference requires SIMD-aligned input anyway.        */
+  uint32_t len = j->natural ? 3 * j->K + 12 : 3 * (j->K + 32) + 12;
+  int16_t* buf = (int16_t*)srslte_vec_malloc(sizeof(int16_t) * (len + 64));
+  for (uint32_t i = j->first; i < j->last; i++) {
+    memcpy(buf, j->in + (size_t)i * j->in_stride, sizeof(int16_t) * len);
+    if (srslte_tdec_run_all(h, buf, j->out + (size_t)i * j->out_stride, j->nit, j->K)) j->rc = -1;
+  }
+  free(buf);
+  refh_tdec_free(h);
+  return NULL;
+}
+
+int refh_batch_run_all(const int16_t* in, uint32_t in_stride, int natural, uint8_t* out,
+                       uint32_t out_stride, uint32_t n, uint32_t K, uint32_t nof_iterations,
+                       uint32_t threads)
+{
+  if (threads == 0) threads = 1;
+  if (threads > n) threads = n ? n : 1;
+  pthread_t* th   = (pthread_t*)calloc(threads, sizeof(pthread_t));
+  job_t*     jobs = (job_t*)calloc(threads, sizeof(job_t));
+  int        rc   = 0;
+  for (uint32_t t = 0; t < threads; t++) {
+    jobs[t] = (job_t){in, out, in_stride, out_stride, (uint32_t)((uint64_t)n * t / threads),
+                      (uint32_t)((uint64_t)n * (t + 1) / threads), K, nof_iterations, natural, 0};
+    pthread_create(&th[t], NULL, worker, &jobs[t]);
+  }
+  for (uint32_t t = 0; t < threads; t++) {
+    pthread_join(th[t], NULL);
+    if (jobs[t].rc) rc = -1;
+  }
+  free(th);
+  free(jobs);
+  return rc;
+}
+
+/* ---- per-iteration trace of one block, the way sch.c drives the decoder ---- */
+int refh_tdec_trace(const int16_t* in, int natural, uint32_t K, uint32_t nof_iterations,
+                    uint8_t* out_bytes /* nit * K/8 */, int16_t* out_llr /* nit * K, nullable */)
+{
+  srslte_tdec_t* h = refh_tdec_new(6144, 0);
+  if (!h) return -1;
+  if (natural) srslte_tdec_force_not_sb(h);
+  uint32_t len = natural ? 3 * K + 12 : 3 * (K + 32) + 12;
+  int16_t* buf = (int16_t*)srslte_vec_malloc(sizeof(int16_t) * (len + 64));
+  memcpy(buf, in, sizeof(int16_t) * len);
+  int rc = srslte_tdec_new_cb(h, K);
+  for (uint32_t it = 0; it < nof_iterations && !rc; it++) {
+    srslte_tdec_iteration(h, buf, out_bytes + (size_t)it * (K / 8));
+    if (out_llr) memcpy(out_llr + (size_t)it * K, refh_tdec_llr_ptr(h), sizeof(int16_t) * K);
+  }
+  free(buf);
+  refh_tdec_free(h);
+  return rc;
+}
+
+/* ---- encoder side (vector generation only) ---- */
+int refh_tcod_encode(const uint8_t* bits, uint8_t* coded /* 3K+12 */, uint32_t K)
+{
+  srslte_tcod_t tc;
+  if (srslte_tcod_init(&tc, 6144)) return -1;
+  int rc = srslte_tcod_encode(&tc, (uint8_t*)bits, coded, K);
+  srslte_tcod_free(&tc);
+  return rc;
+}
+
+int refh_rm_turbo_tx(const uint8_t* coded, uint32_t K, uint8_t* e, uint32_t E, uint32_t rv)
+{
+  uint8_t* w  = (uint8_t*)calloc(3 * 6176 + 64, 1);
+  /* the circular buffer w is only (re)built by an rv 0 call: rm_turbo.c:950 */
+  int rc = srslte_rm_turbo_tx(w, 3 * 6176, (uint8_t*)coded, 3 * K + 12, e, E, 0);
+  if (!rc && rv) rc = srslte_rm_turbo_tx(w, 3 * 6176, (uint8_t*)coded, 3 * K + 12, e, E, rv);
+  free(w);
+  return rc;
+}
+
+/* ---- transport-block level: srslte_dlsch_encode2 / srslte_dlsch_decode2 ---- */
+typedef struct {
+  srslte_sch_t           sch;
+  srslte_softbuffer_tx_t sb_tx;
+  srslte_softbuffer_rx_t sb_rx;
+  srslte_pdsch_cfg_t     cfg;
+} refh_tb_t;
+
+refh_tb_t* refh_tb_new(void)
+{
+  refh_tb_t* t = (refh_tb_t*)srslte_vec_malloc(sizeof(refh_tb_t));
+  if (!t) return NULL;
+  memset(t, 0, sizeof(*t));
+  if (srslte_sch_init(&t->sch) || srslte_softbuffer_tx_init(&t->sb_tx, 110) ||
+      srslte_softbuffer_rx_init(&t->sb_rx, 110)) {
+    free(t);
+    return NULL;
+  }
+  return t;
+}
+
+void refh_tb_free(refh_tb_t* t)
+{
+  if (!t) return;
+  srslte_sch_free(&t->sch);
+  srslte_softbuffer_tx_free(&t->sb_tx);
+  srslte_softbuffer_rx_free(&t->sb_rx);
+  free(t);
+}
+
+static void fill_cfg(refh_tb_t* t, uint32_t tbs, uint32_t qm, uint32_t rv, uint32_t G, int tx)
+{
+  memset(&t->cfg, 0, sizeof(t->cfg));
+  t->cfg.grant.nof_tb     = 1;
+  t->cfg.grant.nof_layers = 1;
+  t->cfg.grant.tb[0].mod  = qm == 2 ? SRSLTE_MOD_QPSK : qm == 4 ? SRSLTE_MOD_16QAM
+                          : qm == 6 ? SRSLTE_MOD_64QAM : SRSLTE_MOD_256QAM;
+  t->cfg.grant.tb[0].tbs      = (int)tbs;
+  t->cfg.grant.tb[0].rv       = (int)rv;
+  t->cfg.grant.tb[0].nof_bits = G;
+  t->cfg.grant.tb[0].enabled  = true;
+  if (tx)
+    t->cfg.softbuffers.tx[0] = &t->sb_tx;
+  else
+    t->cfg.softbuffers.rx[0] = &t->sb_rx;
+}
+
+/* data: tbs/8 bytes in; e_bits: G unpacked bits (one per byte) out */
+int refh_tb_encode(refh_tb_t* t, uint32_t tbs, uint32_t qm, uint32_t rv, uint32_t G,
+                   const uint8_t* data, uint8_t* e_bits)
+{
+  uint8_t* packed = (uint8_t*)calloc(G / 8 + 64, 1);
+  uint8_t* d      = (uint8_t*)calloc(tbs / 8 + 64, 1);
+  memcpy(d, data, tbs / 8);
+  fill_cfg(t, tbs, qm, rv, G, 1);
+  if (rv == 0) srslte_softbuffer_tx_reset_tbs(&t->sb_tx, tbs);
+  int rc = srslte_dlsch_encode2(&t->sch, &t->cfg, d, packed, 0, 1);
+  if (!rc) srslte_bit_unpack_vector(packed, e_bits, (int)G);
+  free(packed);
+  free(d);
+  return rc;
+}
+
+void refh_tb_rx_reset(refh_tb_t* t, uint32_t tbs) { srslte_softbuffer_rx_reset_tbs(&t->sb_rx, tbs); }
+
+/* out: tbs/8 + 8 bytes.  Returns srslte_dlsch_decode2's value; *avg_it = srslte_sch_last_noi */
+int refh_tb_decode(refh_tb_t* t, uint32_t tbs, uint32_t qm, uint32_t rv, uint32_t G,
+                   const int16_t* llr, uint8_t* out, uint32_t max_it, float* avg_it,
+                   uint8_t* cb_crc /* nullable, C entries */)
+{
+  int16_t* e = (int16_t*)srslte_vec_malloc(sizeof(int16_t) * (G + 64));
+  memcpy(e, llr, sizeof(int16_t) * G);
+  fill_cfg(t, tbs, qm, rv, G, 0);
+  srslte_sch_set_max_noi(&t->sch, max_it);
+  int rc = srslte_dlsch_decode2(&t->sch, &t->cfg, e, out, 0, 1);
+  if (avg_it) *avg_it = srslte_sch_last_noi(&t->sch);
+  if (cb_crc) {
+    srslte_cbsegm_t s;
+    srslte_cbsegm(&s, tbs);
+    for (uint32_t i = 0; i < s.C; i++) cb_crc[i] = t->sb_rx.cb_crc[i];
+  }
+  free(e);
+  return rc;
+}
+
+const int16_t* refh_tb_softbuffer(refh_tb_t* t, uint32_t cb) { return t->sb_rx.buffer_f[cb]; }
+
+/* ---- CRC through the reference's table implementation ---- */
+uint32_t refh_crc_bytes(uint32_t poly, const uint8_t* data, uint32_t nbits)
+{
+  srslte_crc_t c;
+  srslte_crc_init(&c, poly, 24);
+  return srslte_crc_checksum_byte(&c, (uint8_t*)data, (int)nbits);
+}
+
+uint32_t refh_crc_bits(uint32_t poly, const uint8_t* bits, uint32_t nbits)
+{
+  srslte_crc_t c;
+  srslte_crc_init(&c, poly, 24);
+  return srslte_crc_checksum(&c, (uint8_t*)bits, (int)nbits);
+}

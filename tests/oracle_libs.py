@@ -1,0 +1,195 @@
+"""ctypes loaders for the CPU checkers (TEST INFRASTRUCTURE).
+
+  port()  -> oracle/libtdec_port.so          this repo's scalar restatement (oracle/tdec_port.c)
+  ref()   -> oracle/_ref/libsrslte_ref.so    the reference's own sources compiled by oracle/Makefile
+             (None when it has not been built; it is built in the dev container where
+             /root/reference exists and travels to the GPU box as a prebuilt file)
+
+Nothing under srslte-emane_b200/ imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE = os.path.join(ROOT, "oracle")
+PORT_SO = os.path.join(ORACLE, "libtdec_port.so")
+REF_SO = os.path.join(ORACLE, "_ref", "libsrslte_ref.so")
+
+CRC24A = 0x1864CFB
+CRC24B = 0x1800063
+
+_i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+
+_port = None
+_ref = None
+
+
+def build_port():
+    if (not os.path.exists(PORT_SO)
+            or os.path.getmtime(PORT_SO) < os.path.getmtime(os.path.join(ORACLE, "tdec_port.c"))):
+        subprocess.check_call(["make", "-s", "-C", ORACLE, "port"])
+
+
+def build_ref():
+    """(Re)build oracle/_ref when the reference tree is present; no-op otherwise."""
+    if os.path.isdir("/root/reference/lib/src/phy/fec"):
+        subprocess.check_call(["make", "-s", "-C", ORACLE, "ref"])
+    return os.path.exists(REF_SO)
+
+
+class PortSoftbuffer(C.Structure):
+    _fields_ = [("max_cb", C.c_uint32), ("buffer_f", C.POINTER(C.c_int16)),
+                ("data", C.POINTER(C.c_uint8)), ("cb_crc", C.POINTER(C.c_uint8)),
+                ("tb_crc", C.c_uint8)]
+
+
+class PortCbsegm(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("F", "C", "K1", "K2", "K1_idx", "K2_idx", "C1", "C2", "tbs")]
+
+
+def port():
+    global _port
+    if _port is not None:
+        return _port
+    build_port()
+    L = C.CDLL(PORT_SO)
+    L.port_cb_size.argtypes = [C.c_uint32]
+    L.port_cb_index.argtypes = [C.c_uint32]
+    L.port_nof_subblocks.argtypes = [C.c_uint32]
+    L.port_qpp.argtypes = [C.c_uint32, C.c_uint32]
+    L.port_qpp.restype = C.c_uint32
+    L.port_crc_bytes.argtypes = [C.c_uint32, _u8p, C.c_uint32]
+    L.port_crc_bytes.restype = C.c_uint32
+    L.port_crc_bits.argtypes = [C.c_uint32, _u8p, C.c_uint32]
+    L.port_crc_bits.restype = C.c_uint32
+    L.port_cbsegm.argtypes = [C.POINTER(PortCbsegm), C.c_uint32]
+    L.port_rm_rx_table.argtypes = [C.c_uint32, C.c_uint32, C.c_int, _u16p]
+    L.port_rm_turbo_rx.argtypes = [_i16p, C.c_uint32, _i16p, C.c_uint32, C.c_uint32, C.c_int]
+    L.port_tdec_new.restype = C.c_void_p
+    L.port_tdec_free.argtypes = [C.c_void_p]
+    L.port_tdec_new_cb.argtypes = [C.c_void_p, C.c_uint32]
+    L.port_tdec_iteration.argtypes = [C.c_void_p, _i16p, C.c_int, _u8p]
+    L.port_tdec_run_all.argtypes = [C.c_void_p, _i16p, C.c_int, _u8p, C.c_uint32, C.c_uint32]
+    L.port_tdec_get_nof_iterations.argtypes = [C.c_void_p]
+    L.port_tdec_clamp_count.argtypes = [C.c_void_p]
+    L.port_tdec_clamp_count.restype = C.c_uint64
+    L.port_tdec_last_llr.argtypes = [C.c_void_p]
+    L.port_tdec_last_llr.restype = C.POINTER(C.c_int16)
+    L.port_softbuffer_init.argtypes = [C.POINTER(PortSoftbuffer), C.c_uint32]
+    L.port_softbuffer_reset.argtypes = [C.POINTER(PortSoftbuffer)]
+    L.port_softbuffer_free.argtypes = [C.POINTER(PortSoftbuffer)]
+    L.port_decode_tb.argtypes = [C.c_void_p, C.POINTER(PortSoftbuffer), C.c_uint32, C.c_uint32,
+                                 C.c_uint32, C.c_uint32, _i16p, _u8p, C.c_uint32,
+                                 C.POINTER(C.c_float), _u32p]
+    L.port_batch_run_all.argtypes = [_i16p, C.c_uint32, C.c_int, _u8p, C.c_uint32, C.c_uint32,
+                                     C.c_uint32, C.c_uint32, C.c_uint32]
+    _port = L
+    return L
+
+
+def ref():
+    global _ref
+    if _ref is not None:
+        return _ref
+    if not os.path.exists(REF_SO):
+        if not build_ref():
+            return None
+    L = C.CDLL(REF_SO)
+    for n in ("refh_sizeof_tdec", "refh_sizeof_sch", "refh_sizeof_crc", "refh_sizeof_softbuffer_rx",
+              "refh_sizeof_cbsegm", "refh_offsetof_tdec_n_iter", "refh_offsetof_sch_decoder"):
+        getattr(L, n).restype = C.c_size_t
+    L.refh_batch_run_all.argtypes = [_i16p, C.c_uint32, C.c_int, _u8p, C.c_uint32, C.c_uint32,
+                                     C.c_uint32, C.c_uint32, C.c_uint32]
+    L.refh_tdec_trace.argtypes = [_i16p, C.c_int, C.c_uint32, C.c_uint32, _u8p, C.c_void_p]
+    L.refh_tcod_encode.argtypes = [_u8p, _u8p, C.c_uint32]
+    L.refh_rm_turbo_tx.argtypes = [_u8p, C.c_uint32, _u8p, C.c_uint32, C.c_uint32]
+    L.refh_tb_new.restype = C.c_void_p
+    L.refh_tb_free.argtypes = [C.c_void_p]
+    L.refh_tb_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, _u8p]
+    L.refh_tb_rx_reset.argtypes = [C.c_void_p, C.c_uint32]
+    L.refh_tb_decode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _i16p,
+                                 _u8p, C.c_uint32, C.POINTER(C.c_float), C.c_void_p]
+    L.refh_tb_softbuffer.argtypes = [C.c_void_p, C.c_uint32]
+    L.refh_tb_softbuffer.restype = C.POINTER(C.c_int16)
+    L.refh_crc_bytes.argtypes = [C.c_uint32, _u8p, C.c_uint32]
+    L.refh_crc_bytes.restype = C.c_uint32
+    L.refh_crc_bits.argtypes = [C.c_uint32, _u8p, C.c_uint32]
+    L.refh_crc_bits.restype = C.c_uint32
+    L.srslte_rm_turbo_gentables.argtypes = []
+    L.srslte_rm_turbo_rx_lut.argtypes = [_i16p, _i16p, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.srslte_rm_turbo_rx_lut_.argtypes = [_i16p, _i16p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_bool]
+    L.srslte_cbsegm.argtypes = [C.POINTER(PortCbsegm), C.c_uint32]  # identical 9 x uint32 layout
+    L.srslte_cbsegm_cbindex.argtypes = [C.c_uint32]
+    L.srslte_tdec_autoimp_get_subblocks.argtypes = [C.c_uint32]
+    L.srslte_tdec_autoimp_get_subblocks.restype = C.c_uint32
+    L.srslte_rm_turbo_gentables()
+    _ref = L
+    return L
+
+
+ALL_K = (list(range(40, 513, 8)) + list(range(528, 1025, 16)) + list(range(1056, 2049, 32))
+         + list(range(2112, 6145, 64)))
+
+
+# ------------------------------------------------------------------------------------------
+# convenience wrappers
+# ------------------------------------------------------------------------------------------
+def port_run_all(llr, K, nit, natural=True):
+    """llr: [n, len] int16 -> bytes [n, K/8] through the scalar port."""
+    P = port()
+    llr = np.ascontiguousarray(llr, dtype=np.int16)
+    n = llr.shape[0]
+    out = np.zeros((n, K // 8), np.uint8)
+    rc = P.port_batch_run_all(llr.reshape(-1), llr.shape[1], int(natural), out.reshape(-1), K // 8, n, K, nit,
+                              min(n, os.cpu_count() or 1))
+    assert rc == 0
+    return out
+
+
+def ref_run_all(llr, K, nit, natural=True, threads=None):
+    R = ref()
+    llr = np.ascontiguousarray(llr, dtype=np.int16)
+    n = llr.shape[0]
+    out = np.zeros((n, K // 8), np.uint8)
+    rc = R.refh_batch_run_all(llr.reshape(-1), llr.shape[1], int(natural), out.reshape(-1), K // 8, n, K, nit,
+                              threads or min(n, os.cpu_count() or 1))
+    assert rc == 0
+    return out
+
+
+def port_trace(llr1, K, nit, natural=True):
+    """per-half-iteration decisions [nit, K/8] and soft outputs [nit, K] (natural order)."""
+    P = port()
+    h = P.port_tdec_new()
+    try:
+        assert P.port_tdec_new_cb(h, K) == 0
+        llr1 = np.ascontiguousarray(llr1, np.int16)
+        by = np.zeros((nit, K // 8), np.uint8)
+        so = np.zeros((nit, K), np.int16)
+        for it in range(nit):
+            P.port_tdec_iteration(h, llr1, int(natural), by[it])
+            so[it] = np.ctypeslib.as_array(P.port_tdec_last_llr(h), (K,))
+        return by, so, int(P.port_tdec_clamp_count(h))
+    finally:
+        P.port_tdec_free(h)
+
+
+def ref_trace(llr1, K, nit, natural=True):
+    """same through the compiled reference; soft outputs are de-permuted to natural order."""
+    R = ref()
+    llr1 = np.ascontiguousarray(llr1, np.int16)
+    by = np.zeros((nit, K // 8), np.uint8)
+    so = np.zeros((nit, K), np.int16)
+    assert R.refh_tdec_trace(llr1, int(natural), K, nit, by.reshape(-1), so.ctypes.data) == 0
+    W = int(R.srslte_tdec_autoimp_get_subblocks(K))
+    if W:
+        L = K // W
+        n = np.arange(K)
+        so = so[:, (n % L) * W + n // L]
+    return by, so
