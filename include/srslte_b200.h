@@ -1,0 +1,125 @@
+/*
+ * srslte_b200.h -- C ABI of the B200-native LTE turbo-decode path.
+ *
+ * This is the ONE added, batched entry of the drop-in: the reference's
+ * per-code-block calls are replaced by calls over arrays of independent code blocks.  The
+ * unchanged legacy entry points (srslte_tdec_*, srslte_rm_turbo_rx_lut*, ...) are declared in
+ * srslte_b200_compat.h and are thin batch-of-one wrappers over the functions below.
+ *
+ * Plain C types only; every pointer is either a host pointer or a CUDA device pointer as stated.
+ * All functions return 0 on success, SRSLTE_B200_ERROR (-1) on a runtime/CUDA failure and
+ * SRSLTE_B200_ERROR_INVALID_INPUTS (-2) on bad arguments -- the reference's convention
+ * (lib/include/srslte/config.h:56-63).  There is no CPU fallback: without a CUDA device the
+ * context cannot be created and every entry fails.
+ *
+ * Reference interfaces replaced (paths under the reference tree):
+ *   srslte_tdec_run_all / srslte_tdec_iteration      lib/include/srslte/phy/fec/turbodecoder.h:121-135
+ *                                                    lib/src/phy/fec/turbodecoder.c:539-562
+ *   srslte_rm_turbo_rx_lut                           lib/include/srslte/phy/fec/rm_turbo.h:76-80
+ *                                                    lib/src/phy/fec/rm_turbo.c:374-426
+ *   decode_tb_cb / decode_tb (per-CB loop, CRC early stop)   lib/src/phy/phch/sch.c:299-500
+ *   srslte_crc_checksum_byte                         lib/src/phy/fec/crc.c:139-153
+ */
+#ifndef SRSLTE_B200_H
+#define SRSLTE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRSLTE_B200_SUCCESS 0
+#define SRSLTE_B200_ERROR (-1)
+#define SRSLTE_B200_ERROR_INVALID_INPUTS (-2)
+
+#define SRSLTE_B200_API __attribute__((visibility("default")))
+
+typedef struct srslte_b200_ctx srslte_b200_ctx_t;
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* One context per host thread / GPU (the reference's handles are single-threaded too:
+ * one srslte_sch_t per worker, SURVEY.md 8b "Threading").                                       */
+SRSLTE_B200_API int  srslte_b200_ctx_create(srslte_b200_ctx_t** ctx, int cuda_device);
+SRSLTE_B200_API void srslte_b200_ctx_destroy(srslte_b200_ctx_t* ctx);
+/* Kernels of the *_dev entries are enqueued on this CUDA stream (cudaStream_t passed as void*;
+ * NULL = the context's own stream).                                                             */
+SRSLTE_B200_API int  srslte_b200_ctx_set_stream(srslte_b200_ctx_t* ctx, void* cuda_stream);
+SRSLTE_B200_API int  srslte_b200_ctx_synchronize(srslte_b200_ctx_t* ctx);
+SRSLTE_B200_API const char* srslte_b200_last_error(const srslte_b200_ctx_t* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches).                 */
+SRSLTE_B200_API uint64_t srslte_b200_launch_count(const srslte_b200_ctx_t* ctx);
+
+/* Pinned host memory for the *_host entries (plain cudaHostAlloc; any host pointer is accepted,
+ * pinned ones are copied without staging).                                                      */
+SRSLTE_B200_API void* srslte_b200_host_alloc(size_t bytes);
+SRSLTE_B200_API void  srslte_b200_host_free(void* p);
+
+/* ---- tables (host, no GPU needed) ---------------------------------------------------------- */
+/* srslte_cbsegm_cbindex / _cbsize (cbsegm.c:109-135)                                            */
+SRSLTE_B200_API int srslte_b200_cb_index(uint32_t long_cb);
+SRSLTE_B200_API int srslte_b200_cb_size(uint32_t index);
+/* srslte_tdec_autoimp_get_subblocks (turbodecoder.c:394-406): 16, 8 or 0                        */
+SRSLTE_B200_API uint32_t srslte_b200_nof_windows(uint32_t long_cb);
+/* int16 elements of one code block in the decoder's working layout (= what
+ * srslte_rm_turbo_rx_lut writes): 3*(K+32)+12 for window decoders, 3*K+12 for K <= 400.         */
+SRSLTE_B200_API uint32_t srslte_b200_working_len(uint32_t long_cb);
+/* The receive index table of (K, rv): table[i] = working-layout (sb_layout != 0) or natural
+ * (sb_layout == 0) index accumulating rate-matched sample i, i < 3K+12 (rm_turbo.c:160-260).    */
+SRSLTE_B200_API int srslte_b200_rm_rx_table(uint32_t long_cb, uint32_t rv, int sb_layout, uint16_t* table);
+
+/* ---- batched turbo decode ------------------------------------------------------------------ */
+#define SRSLTE_B200_INPUT_NATURAL 0 /* in[3i+j], tails last: srslte_tdec_force_not_sb semantics   */
+#define SRSLTE_B200_INPUT_WORKING 1 /* sub-block soft-buffer layout written by rate de-matching   */
+
+#define SRSLTE_B200_CRC_NONE 0 /* exactly max(1, nof_iterations) half iterations: srslte_tdec_run_all */
+#define SRSLTE_B200_CRC_24B 1  /* stop a block when CRC24B over its K bits is 0: sch.c:365-378, C > 1 */
+#define SRSLTE_B200_CRC_24A 2  /* same with CRC24A: single-code-block transport block              */
+
+typedef struct {
+  uint32_t        n_cb;           /* number of independent code blocks                            */
+  const uint32_t* long_cb;        /* host array [n_cb] of K, or NULL when all blocks have uniform_long_cb */
+  uint32_t        uniform_long_cb;
+  uint32_t        input_format;   /* SRSLTE_B200_INPUT_*                                           */
+  uint32_t        in_stride;      /* int16 elements between consecutive blocks' inputs (even)      */
+  uint32_t        out_stride;     /* bytes between consecutive blocks' outputs (>= K/8)            */
+  uint32_t        nof_iterations; /* cap, in srsLTE HALF iterations (enb.conf.example:184)         */
+  uint32_t        crc_mode;       /* SRSLTE_B200_CRC_*                                             */
+} srslte_b200_tdec_batch_t;
+
+/* Device-resident variant: llr, out, n_iter, crc_ok are CUDA device pointers; work is enqueued on
+ * the context's stream and the call returns without waiting.
+ *   llr    [n_cb * in_stride] int16
+ *   out    [n_cb * out_stride] decoded bytes, MSB first (K/8 per block)
+ *   n_iter [n_cb] half iterations actually run per block (nullable)
+ *   crc_ok [n_cb] 1 if the block's CRC check passed (nullable; 0 in CRC_NONE mode)               */
+SRSLTE_B200_API int srslte_b200_tdec_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_tdec_batch_t* batch,
+                                               const int16_t* llr, uint8_t* out, uint8_t* n_iter,
+                                               uint8_t* crc_ok);
+
+/* Host variant: same arguments as host pointers; copies are pipelined with the kernels; returns
+ * when the results are in host memory (the reference's calls are synchronous).                  */
+SRSLTE_B200_API int srslte_b200_tdec_batch_host(srslte_b200_ctx_t* ctx, const srslte_b200_tdec_batch_t* batch,
+                                                const int16_t* llr, uint8_t* out, uint8_t* n_iter,
+                                                uint8_t* crc_ok);
+
+/* ---- batched rate de-matching -------------------------------------------------------------- */
+typedef struct {
+  uint32_t long_cb;   /* K                                                                         */
+  uint32_t rv;        /* redundancy version 0..3                                                   */
+  uint32_t e_offset;  /* first sample of this block in e (int16 elements)                          */
+  uint32_t e_len;     /* number of rate-matched samples E (may exceed 3K+12: wraps)                */
+  uint32_t work_offset; /* start of the block's working/soft buffer (int16 elements, even)         */
+} srslte_b200_rm_block_t;
+
+/* work[table[i mod (3K+12)]] += e[i] (wrapping int16) for every block: HARQ combining happens in
+ * place, the caller zeroes `work` for a new transmission (srslte_softbuffer_rx_reset).
+ * e and work are device pointers; blocks is a host array.                                        */
+SRSLTE_B200_API int srslte_b200_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_rm_block_t* blocks,
+                                                uint32_t n_blocks, const int16_t* e, int16_t* work);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRSLTE_B200_H */

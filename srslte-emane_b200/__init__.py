@@ -1,0 +1,213 @@
+"""srslte-emane_b200: B200-native LTE turbo-decode receive tail (host-side Python binding).
+
+The product is the C-ABI shared library ``libsrslte_b200.so`` (include/srslte_b200.h).  This module is
+only a ctypes mirror of that ABI for the tests and bench.py; it contains no decoding logic and never
+touches oracle/.  It fails loudly when the library is missing or no CUDA device is usable -- there is
+no CPU fallback.
+
+Because the directory name contains a hyphen, import it through ``__graft_entry__.load_package()``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import vectors  # noqa: F401  (synthetic vector generation; no decoder inside)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsrslte_b200.so")
+
+INPUT_NATURAL, INPUT_WORKING = 0, 1
+CRC_NONE, CRC_24B, CRC_24A = 0, 1, 2
+SUCCESS, ERROR, ERROR_INVALID_INPUTS = 0, -1, -2
+
+
+class TdecBatch(C.Structure):
+    _fields_ = [("n_cb", C.c_uint32), ("long_cb", C.POINTER(C.c_uint32)), ("uniform_long_cb", C.c_uint32),
+                ("input_format", C.c_uint32), ("in_stride", C.c_uint32), ("out_stride", C.c_uint32),
+                ("nof_iterations", C.c_uint32), ("crc_mode", C.c_uint32)]
+
+
+class RmBlock(C.Structure):
+    _fields_ = [("long_cb", C.c_uint32), ("rv", C.c_uint32), ("e_offset", C.c_uint32), ("e_len", C.c_uint32),
+                ("work_offset", C.c_uint32)]
+
+
+EXPORTS = [
+    "srslte_b200_ctx_create", "srslte_b200_ctx_destroy", "srslte_b200_ctx_set_stream",
+    "srslte_b200_ctx_synchronize", "srslte_b200_last_error", "srslte_b200_launch_count",
+    "srslte_b200_host_alloc", "srslte_b200_host_free", "srslte_b200_cb_index", "srslte_b200_cb_size",
+    "srslte_b200_nof_windows", "srslte_b200_working_len", "srslte_b200_rm_rx_table",
+    "srslte_b200_tdec_batch_dev", "srslte_b200_tdec_batch_host", "srslte_b200_rm_rx_batch_dev",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libsrslte_b200.so (raises if it has not been built: run __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+                           " -- this package has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, u32, i32 = C.c_void_p, C.c_uint32, C.c_int
+    L.srslte_b200_ctx_create.argtypes = [C.POINTER(vp), i32]
+    L.srslte_b200_ctx_destroy.argtypes = [vp]
+    L.srslte_b200_ctx_destroy.restype = None
+    L.srslte_b200_ctx_set_stream.argtypes = [vp, vp]
+    L.srslte_b200_ctx_synchronize.argtypes = [vp]
+    L.srslte_b200_last_error.argtypes = [vp]
+    L.srslte_b200_last_error.restype = C.c_char_p
+    L.srslte_b200_launch_count.argtypes = [vp]
+    L.srslte_b200_launch_count.restype = C.c_uint64
+    L.srslte_b200_host_alloc.argtypes = [C.c_size_t]
+    L.srslte_b200_host_alloc.restype = vp
+    L.srslte_b200_host_free.argtypes = [vp]
+    L.srslte_b200_host_free.restype = None
+    L.srslte_b200_cb_index.argtypes = [u32]
+    L.srslte_b200_cb_size.argtypes = [u32]
+    L.srslte_b200_nof_windows.argtypes = [u32]
+    L.srslte_b200_nof_windows.restype = u32
+    L.srslte_b200_working_len.argtypes = [u32]
+    L.srslte_b200_working_len.restype = u32
+    L.srslte_b200_rm_rx_table.argtypes = [u32, u32, i32, vp]
+    L.srslte_b200_tdec_batch_dev.argtypes = [vp, C.POINTER(TdecBatch), vp, vp, vp, vp]
+    L.srslte_b200_tdec_batch_host.argtypes = [vp, C.POINTER(TdecBatch), vp, vp, vp, vp]
+    L.srslte_b200_rm_rx_batch_dev.argtypes = [vp, C.POINTER(RmBlock), u32, vp, vp]
+    _lib = L
+    return L
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def rm_rx_table(K, rv, sb_layout=True):
+    t = np.zeros(3 * K + 12, np.uint16)
+    rc = lib().srslte_b200_rm_rx_table(K, rv, int(sb_layout), t.ctypes.data)
+    if rc:
+        raise B200Error(f"srslte_b200_rm_rx_table({K},{rv}) -> {rc}")
+    return t
+
+
+def working_len(K):
+    return int(lib().srslte_b200_working_len(K))
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc memory (inputs of the *_host entry that need no staging)."""
+
+    def __init__(self, shape, dtype):
+        self.shape = tuple(shape)
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self._p = lib().srslte_b200_host_alloc(max(nbytes, 1))
+        if not self._p:
+            raise B200Error("cudaHostAlloc failed")
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            lib().srslte_b200_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One decoder context on one GPU (srslte_b200_ctx_t)."""
+
+    def __init__(self, device=0):
+        self._L = lib()
+        self._h = C.c_void_p()
+        rc = self._L.srslte_b200_ctx_create(C.byref(self._h), device)
+        if rc:
+            raise B200Error(f"srslte_b200_ctx_create(device={device}) failed ({rc}): no usable CUDA device; "
+                            "there is no CPU fallback")
+
+    def close(self):
+        if self._h:
+            self._L.srslte_b200_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc:
+            raise B200Error(f"{what} -> {rc}: {self._L.srslte_b200_last_error(self._h).decode()}")
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self._L.srslte_b200_ctx_set_stream(self._h, C.c_void_p(cuda_stream_ptr)), "set_stream")
+
+    def synchronize(self):
+        self._check(self._L.srslte_b200_ctx_synchronize(self._h), "synchronize")
+
+    @property
+    def launch_count(self):
+        return int(self._L.srslte_b200_launch_count(self._h))
+
+    @staticmethod
+    def _batch(n, K, natural, in_stride, out_stride, nof_iterations, crc_mode):
+        b = TdecBatch()
+        b.n_cb = n
+        keep = None
+        if np.isscalar(K):
+            b.long_cb = None
+            b.uniform_long_cb = int(K)
+        else:
+            keep = np.ascontiguousarray(K, dtype=np.uint32)
+            assert keep.shape == (n,)
+            b.long_cb = keep.ctypes.data_as(C.POINTER(C.c_uint32))
+            b.uniform_long_cb = 0
+        b.input_format = INPUT_NATURAL if natural else INPUT_WORKING
+        b.in_stride = in_stride
+        b.out_stride = out_stride
+        b.nof_iterations = nof_iterations
+        b.crc_mode = crc_mode
+        return b, keep
+
+    # ---- host-pointer entry: the call a user of the reference's API makes -------------------------
+    def tdec_batch_host(self, llr, K, nof_iterations, crc_mode=CRC_NONE, natural=True, out=None):
+        """llr: int16 [n, in_stride] (numpy, host).  Returns (bytes [n, out_stride], n_iter [n], crc_ok [n])."""
+        assert llr.dtype == np.int16 and llr.ndim == 2 and llr.flags.c_contiguous
+        n, in_stride = llr.shape
+        kmax = int(K) if np.isscalar(K) else int(np.max(K)) if n else 0
+        out_stride = kmax // 8
+        if out is None:
+            out = np.zeros((n, out_stride), np.uint8)
+        nit = np.zeros(n, np.uint8)
+        ok = np.zeros(n, np.uint8)
+        b, keep = self._batch(n, K, natural, in_stride, out_stride, nof_iterations, crc_mode)
+        rc = self._L.srslte_b200_tdec_batch_host(self._h, C.byref(b), llr.ctypes.data, out.ctypes.data,
+                                                 nit.ctypes.data, ok.ctypes.data)
+        self._check(rc, "srslte_b200_tdec_batch_host")
+        return out, nit, ok
+
+    # ---- device-pointer entry: raw CUDA pointers (e.g. torch tensors' data_ptr()) -----------------
+    def tdec_batch_dev(self, llr_ptr, n, in_stride, K, nof_iterations, out_ptr, out_stride, nit_ptr=0, crc_ptr=0,
+                       crc_mode=CRC_NONE, natural=True):
+        b, keep = self._batch(n, K, natural, in_stride, out_stride, nof_iterations, crc_mode)
+        rc = self._L.srslte_b200_tdec_batch_dev(self._h, C.byref(b), C.c_void_p(llr_ptr), C.c_void_p(out_ptr),
+                                                C.c_void_p(nit_ptr), C.c_void_p(crc_ptr))
+        self._check(rc, "srslte_b200_tdec_batch_dev")
+
+    def rm_rx_batch_dev(self, blocks, e_ptr, work_ptr):
+        """blocks: list of (K, rv, e_offset, e_len, work_offset)."""
+        arr = (RmBlock * len(blocks))()
+        for i, (K, rv, eo, el, wo) in enumerate(blocks):
+            arr[i] = RmBlock(K, rv, eo, el, wo)
+        rc = self._L.srslte_b200_rm_rx_batch_dev(self._h, arr, len(blocks), C.c_void_p(e_ptr), C.c_void_p(work_ptr))
+        self._check(rc, "srslte_b200_rm_rx_batch_dev")

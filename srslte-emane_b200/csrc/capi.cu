@@ -1,0 +1,532 @@
+// capi.cu -- the C ABI of include/srslte_b200.h: context, scheduling of code blocks onto warps,
+// copy/compute pipelining for host buffers.  No decoding arithmetic lives here.
+#include "../../include/srslte_b200.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "lte_tables.h"
+#include "tdec_kernels.h"
+
+using namespace b200;
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+  T*     p   = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t reserve(size_t n)
+  {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p   = nullptr;
+    cap = 0;
+    const size_t want = n + n / 8 + 64;
+    cudaError_t  e    = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release()
+  {
+    if (p) cudaFree(p);
+    p   = nullptr;
+    cap = 0;
+  }
+};
+
+template <typename T>
+struct PinBuf {
+  T*     p   = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n)
+  {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p   = nullptr;
+    cap = 0;
+    const size_t want = n + n / 8 + 64;
+    cudaError_t  e    = cudaHostAlloc(&p, want * sizeof(T), cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release()
+  {
+    if (p) cudaFreeHost(p);
+    p   = nullptr;
+    cap = 0;
+  }
+};
+
+struct Regime {  // one per decoder kind: index 0 -> W=16, 1 -> W=8, 2 -> generic
+  int               W = 0;
+  bool              ready = false;
+  TdecGeometry      geo{};
+  DevBuf<uint8_t>   ws_ae, ws_chk;
+};
+
+struct Schedule {  // how the code blocks of one launch map onto warps
+  std::vector<uint32_t> order;
+  std::vector<WorkItem> items[3];
+  uint32_t              item_base[3] = {0, 0, 0};
+};
+
+}  // namespace
+
+struct srslte_b200_ctx {
+  int          device      = 0;
+  cudaStream_t own_stream  = nullptr;
+  cudaStream_t stream      = nullptr;  // where *_dev work goes
+  cudaStream_t h2d_stream  = nullptr;
+  cudaStream_t d2h_stream  = nullptr;
+  Regime       regime[3];
+  DevBuf<uint32_t> counters;           // 3 work counters
+  // schedule cache
+  DevBuf<uint32_t> d_order;
+  DevBuf<WorkItem> d_items;
+  DevBuf<uint32_t> d_cbK;
+  PinBuf<uint32_t> h_order;
+  PinBuf<WorkItem> h_items;
+  PinBuf<uint32_t> h_cbK;
+  Schedule     sched;
+  bool         sched_valid = false;
+  uint32_t     sched_n = 0, sched_uniform_K = 0;
+  std::vector<uint32_t> sched_K;       // per-block K of the cached schedule when not uniform
+  // working-layout staging for natural-order input
+  DevBuf<int16_t> d_work;
+  // host-pipeline buffers (double buffered)
+  DevBuf<int16_t> d_in[2];
+  DevBuf<uint8_t> d_out[2], d_nit[2], d_crc[2];
+  cudaEvent_t  ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  // rate-dematching tables
+  std::map<uint32_t, uint32_t> rm_tab_off;  // key = K*4+rv -> offset in the pool
+  std::vector<uint16_t>        rm_pool_host;
+  DevBuf<uint16_t>             rm_pool_dev;
+  size_t                       rm_pool_uploaded = 0;
+  DevBuf<RmItem>               d_rm_items;
+  PinBuf<RmItem>               h_rm_items;
+  uint64_t     launches = 0;
+  std::string  err;
+};
+
+namespace {
+
+int fail(srslte_b200_ctx* c, int code, const char* fmt, ...)
+{
+  char    buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess)                                                                            \
+      return fail(ctx, SRSLTE_B200_ERROR, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),     \
+                  __FILE__, __LINE__);                                                                 \
+  } while (0)
+
+int regime_index(int W) { return W == 16 ? 0 : W == 8 ? 1 : 2; }
+
+int ensure_regime(srslte_b200_ctx* ctx, int ri)
+{
+  Regime& r = ctx->regime[ri];
+  if (r.ready) return 0;
+  r.W = ri == 0 ? 16 : ri == 1 ? 8 : 0;
+  CU(tdec_geometry(r.W, ctx->device, &r.geo));
+  CU(r.ws_ae.reserve(r.geo.ws_ae_bytes));
+  CU(r.ws_chk.reserve(r.geo.ws_chk_bytes));
+  r.ready = true;
+  return 0;
+}
+
+// Group the blocks [0, n) by K (largest first, so the longest work starts first) and cut each
+// group into warp-sized items.
+int build_schedule(srslte_b200_ctx* ctx, const uint32_t* K, uint32_t uniform_K, uint32_t n, Schedule& s)
+{
+  s.order.resize(n);
+  for (auto& v : s.items) v.clear();
+  auto emit = [&](uint32_t Kv, uint32_t first, uint32_t count) {
+    const int idx = cb_index_exact(Kv);
+    const int W   = nof_windows(Kv);
+    const int ri  = regime_index(W);
+    const uint32_t per = (uint32_t)tdec_blocks_per_warp(W);
+    for (uint32_t o = 0; o < count; o += per) {
+      WorkItem wi;
+      wi.first = first + o;
+      wi.count = (uint16_t)std::min(per, count - o);
+      wi.K     = (uint16_t)Kv;
+      wi.f1    = kQpp[idx].f1;
+      wi.f2    = kQpp[idx].f2;
+      s.items[ri].push_back(wi);
+    }
+  };
+  if (!K) {
+    if (cb_index_exact(uniform_K) < 0)
+      return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "invalid code block size %u", uniform_K);
+    for (uint32_t i = 0; i < n; i++) s.order[i] = i;
+    emit(uniform_K, 0, n);
+    return 0;
+  }
+  std::vector<uint32_t> cnt(kNofCbSizes + 1, 0);
+  std::vector<int>      idx(n);
+  for (uint32_t i = 0; i < n; i++) {
+    idx[i] = cb_index_exact(K[i]);
+    if (idx[i] < 0) return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "invalid code block size %u (block %u)", K[i], i);
+    cnt[kNofCbSizes - 1 - idx[i]]++;  // bucket 0 = largest K
+  }
+  std::vector<uint32_t> start(kNofCbSizes + 1, 0);
+  for (int b = 0; b < kNofCbSizes; b++) start[b + 1] = start[b] + cnt[b];
+  std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+  for (uint32_t i = 0; i < n; i++) s.order[fill[kNofCbSizes - 1 - idx[i]]++] = i;
+  for (int b = 0; b < kNofCbSizes; b++)
+    if (cnt[b]) emit(kQpp[kNofCbSizes - 1 - b].K, start[b], cnt[b]);
+  return 0;
+}
+
+// Make sure the device holds the schedule for this (K list, n).  Returns with ctx->sched valid.
+int ensure_schedule(srslte_b200_ctx* ctx, const uint32_t* K, uint32_t uniform_K, uint32_t n, cudaStream_t st)
+{
+  bool same = ctx->sched_valid && ctx->sched_n == n;
+  if (same) {
+    if (!K)
+      same = ctx->sched_K.empty() && ctx->sched_uniform_K == uniform_K;
+    else
+      same = ctx->sched_K.size() == n && std::memcmp(ctx->sched_K.data(), K, n * sizeof(uint32_t)) == 0;
+  }
+  if (same) return 0;
+  ctx->sched_valid = false;
+  int rc = build_schedule(ctx, K, uniform_K, n, ctx->sched);
+  if (rc) return rc;
+  Schedule& s = ctx->sched;
+  size_t n_items = 0;
+  for (int r = 0; r < 3; r++) {
+    s.item_base[r] = (uint32_t)n_items;
+    n_items += s.items[r].size();
+  }
+  // the pinned staging may still be in flight from a previous upload
+  CU(cudaStreamSynchronize(st));
+  CU(ctx->h_order.reserve(n));
+  CU(ctx->h_items.reserve(n_items));
+  CU(ctx->d_order.reserve(n));
+  CU(ctx->d_items.reserve(n_items));
+  std::memcpy(ctx->h_order.p, s.order.data(), n * sizeof(uint32_t));
+  for (int r = 0; r < 3; r++)
+    if (!s.items[r].empty())
+      std::memcpy(ctx->h_items.p + s.item_base[r], s.items[r].data(), s.items[r].size() * sizeof(WorkItem));
+  CU(cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.p, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_items.p, ctx->h_items.p, n_items * sizeof(WorkItem), cudaMemcpyHostToDevice, st));
+  if (K) {
+    CU(ctx->h_cbK.reserve(n));
+    CU(ctx->d_cbK.reserve(n));
+    std::memcpy(ctx->h_cbK.p, K, n * sizeof(uint32_t));
+    CU(cudaMemcpyAsync(ctx->d_cbK.p, ctx->h_cbK.p, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    ctx->sched_K.assign(K, K + n);
+  } else {
+    ctx->sched_K.clear();
+  }
+  ctx->sched_n         = n;
+  ctx->sched_uniform_K = uniform_K;
+  ctx->sched_valid     = true;
+  return 0;
+}
+
+int check_batch(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint32_t* max_work_len)
+{
+  if (!ctx) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  if (!b) return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "batch descriptor is NULL");
+  if (b->input_format > SRSLTE_B200_INPUT_WORKING) return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "bad input_format");
+  if (b->crc_mode > SRSLTE_B200_CRC_24A) return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "bad crc_mode");
+  if (b->in_stride & 1) return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "in_stride must be even");
+  if (b->nof_iterations > 255) return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "nof_iterations > 255");
+  uint32_t wl = 0;
+  for (uint32_t i = 0; i < (b->long_cb ? b->n_cb : 1u); i++) {
+    const uint32_t K = b->long_cb ? b->long_cb[i] : b->uniform_long_cb;
+    if (cb_index_exact(K) < 0) return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "invalid code block size %u", K);
+    const uint32_t need = b->input_format == SRSLTE_B200_INPUT_NATURAL ? 3 * K + 12 : working_len(K);
+    if (b->in_stride < need) return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "in_stride %u < %u needed for K=%u", b->in_stride, need, K);
+    if (b->out_stride < K / 8) return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "out_stride %u < K/8 for K=%u", b->out_stride, K);
+    wl = std::max(wl, working_len(K));
+  }
+  *max_work_len = (wl + 63u) & ~63u;
+  return 0;
+}
+
+// enqueue conversion (if needed) + the decode kernels for blocks described by `b` on stream st
+int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint32_t work_len, const int16_t* d_llr,
+                   uint8_t* d_out, uint8_t* d_nit, uint8_t* d_crc, cudaStream_t st)
+{
+  int rc = ensure_schedule(ctx, b->long_cb, b->uniform_long_cb, b->n_cb, st);
+  if (rc) return rc;
+  const int16_t* win    = d_llr;
+  uint32_t       stride = b->in_stride;
+  if (b->input_format == SRSLTE_B200_INPUT_NATURAL) {
+    CU(ctx->d_work.reserve((size_t)b->n_cb * work_len));
+    CU(natural_to_working_launch(d_llr, b->in_stride, ctx->d_work.p, work_len, b->long_cb ? ctx->d_cbK.p : nullptr,
+                                 b->uniform_long_cb, b->n_cb, st));
+    ctx->launches++;
+    win    = ctx->d_work.p;
+    stride = work_len;
+  }
+  CU(ctx->counters.reserve(4));
+  for (int r = 0; r < 3; r++) {
+    const auto& items = ctx->sched.items[r];
+    if (items.empty()) continue;
+    rc = ensure_regime(ctx, r);
+    if (rc) return rc;
+    Regime&    R = ctx->regime[r];
+    TdecLaunch a{};
+    a.in         = win;
+    a.in_stride  = stride;
+    a.out        = d_out;
+    a.out_stride = b->out_stride;
+    a.n_iter     = d_nit;
+    a.crc_ok     = d_crc;
+    a.order      = ctx->d_order.p;
+    a.items      = ctx->d_items.p + ctx->sched.item_base[r];
+    a.n_items    = (uint32_t)items.size();
+    a.counter    = ctx->counters.p + r;
+    a.max_iter   = b->nof_iterations;
+    a.crc_mode   = b->crc_mode;
+    a.ws_ae      = reinterpret_cast<int16_t*>(R.ws_ae.p);
+    a.ws_chk     = reinterpret_cast<uint32_t*>(R.ws_chk.p);
+    CU(tdec_launch(R.W, R.geo, a, st));
+    ctx->launches++;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int srslte_b200_ctx_create(srslte_b200_ctx_t** out, int cuda_device)
+{
+  if (!out) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || cuda_device < 0 || cuda_device >= n) {
+    fprintf(stderr, "srslte_b200: no usable CUDA device %d (found %d); this library has no CPU path\n", cuda_device, n);
+    return SRSLTE_B200_ERROR;
+  }
+  srslte_b200_ctx* ctx = new srslte_b200_ctx();
+  ctx->device          = cuda_device;
+  if (cudaSetDevice(cuda_device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    fprintf(stderr, "srslte_b200: CUDA stream creation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+    delete ctx;
+    return SRSLTE_B200_ERROR;
+  }
+  for (int i = 0; i < 2; i++) {
+    cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming);
+  }
+  ctx->stream = ctx->own_stream;
+  upload_crc_tables();
+  *out = ctx;
+  return SRSLTE_B200_SUCCESS;
+}
+
+void srslte_b200_ctx_destroy(srslte_b200_ctx_t* ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto& r : ctx->regime) {
+    r.ws_ae.release();
+    r.ws_chk.release();
+  }
+  ctx->counters.release();
+  ctx->d_order.release();
+  ctx->d_items.release();
+  ctx->d_cbK.release();
+  ctx->h_order.release();
+  ctx->h_items.release();
+  ctx->h_cbK.release();
+  ctx->d_work.release();
+  for (int i = 0; i < 2; i++) {
+    ctx->d_in[i].release();
+    ctx->d_out[i].release();
+    ctx->d_nit[i].release();
+    ctx->d_crc[i].release();
+    if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+    if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
+    if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
+  }
+  ctx->rm_pool_dev.release();
+  ctx->d_rm_items.release();
+  ctx->h_rm_items.release();
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+  delete ctx;
+}
+
+int srslte_b200_ctx_set_stream(srslte_b200_ctx_t* ctx, void* cuda_stream)
+{
+  if (!ctx) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return SRSLTE_B200_SUCCESS;
+}
+
+int srslte_b200_ctx_synchronize(srslte_b200_ctx_t* ctx)
+{
+  if (!ctx) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SRSLTE_B200_SUCCESS;
+}
+
+const char* srslte_b200_last_error(const srslte_b200_ctx_t* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+uint64_t    srslte_b200_launch_count(const srslte_b200_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
+
+void* srslte_b200_host_alloc(size_t bytes)
+{
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void srslte_b200_host_free(void* p)
+{
+  if (p) cudaFreeHost(p);
+}
+
+int srslte_b200_cb_index(uint32_t long_cb) { return cb_index_ceil(long_cb); }
+int srslte_b200_cb_size(uint32_t index) { return cb_size(index); }
+uint32_t srslte_b200_nof_windows(uint32_t long_cb) { return (uint32_t)nof_windows(long_cb); }
+uint32_t srslte_b200_working_len(uint32_t long_cb) { return working_len(long_cb); }
+
+int srslte_b200_rm_rx_table(uint32_t long_cb, uint32_t rv, int sb_layout, uint16_t* table)
+{
+  if (!table || rv > 3 || cb_index_exact(long_cb) < 0) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  std::vector<uint16_t> t;
+  rm_rx_table(long_cb, rv, sb_layout != 0, t);
+  std::memcpy(table, t.data(), t.size() * sizeof(uint16_t));
+  return SRSLTE_B200_SUCCESS;
+}
+
+int srslte_b200_tdec_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_tdec_batch_t* b, const int16_t* llr,
+                               uint8_t* out, uint8_t* n_iter, uint8_t* crc_ok)
+{
+  uint32_t work_len = 0;
+  int      rc       = check_batch(ctx, b, &work_len);
+  if (rc) return rc;
+  if (b->n_cb == 0) return SRSLTE_B200_SUCCESS;
+  if (!llr || !out) return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "llr/out is NULL");
+  CU(cudaSetDevice(ctx->device));
+  return enqueue_decode(ctx, b, work_len, llr, out, n_iter, crc_ok, ctx->stream);
+}
+
+int srslte_b200_tdec_batch_host(srslte_b200_ctx_t* ctx, const srslte_b200_tdec_batch_t* b, const int16_t* llr,
+                                uint8_t* out, uint8_t* n_iter, uint8_t* crc_ok)
+{
+  uint32_t work_len = 0;
+  int      rc       = check_batch(ctx, b, &work_len);
+  if (rc) return rc;
+  if (b->n_cb == 0) return SRSLTE_B200_SUCCESS;
+  if (!llr || !out) return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "llr/out is NULL");
+  CU(cudaSetDevice(ctx->device));
+
+  // Pieces of up to `piece` blocks: H2D of piece p+1 overlaps the kernels of piece p and the D2H of
+  // piece p-1.  Uniform-K batches reuse one cached schedule for every full piece.
+  const uint32_t piece = 8192;
+  cudaStream_t   cs    = ctx->stream;
+  const uint32_t n_pieces = (b->n_cb + piece - 1) / piece;
+  for (uint32_t p = 0; p < n_pieces; p++) {
+    const int      s     = (int)(p & 1);
+    const uint32_t first = p * piece;
+    const uint32_t n     = std::min(piece, b->n_cb - first);
+    const size_t   in_elems = (size_t)n * b->in_stride;
+    CU(ctx->d_in[s].reserve((size_t)piece * b->in_stride));
+    CU(ctx->d_out[s].reserve((size_t)piece * b->out_stride));
+    CU(ctx->d_nit[s].reserve(piece));
+    CU(ctx->d_crc[s].reserve(piece));
+    // the buffers of slot s were last used by piece p-2
+    if (p >= 2) {
+      CU(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_comp[s], 0));
+      CU(cudaStreamWaitEvent(cs, ctx->ev_d2h[s], 0));
+    }
+    CU(cudaMemcpyAsync(ctx->d_in[s].p, llr + (size_t)first * b->in_stride, in_elems * sizeof(int16_t),
+                       cudaMemcpyHostToDevice, ctx->h2d_stream));
+    CU(cudaEventRecord(ctx->ev_h2d[s], ctx->h2d_stream));
+    CU(cudaStreamWaitEvent(cs, ctx->ev_h2d[s], 0));
+    srslte_b200_tdec_batch_t pb = *b;
+    pb.n_cb                     = n;
+    pb.long_cb                  = b->long_cb ? b->long_cb + first : nullptr;
+    rc = enqueue_decode(ctx, &pb, work_len, ctx->d_in[s].p, ctx->d_out[s].p, ctx->d_nit[s].p, ctx->d_crc[s].p, cs);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev_comp[s], cs));
+    CU(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_comp[s], 0));
+    CU(cudaMemcpyAsync(out + (size_t)first * b->out_stride, ctx->d_out[s].p, (size_t)n * b->out_stride,
+                       cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    if (n_iter) CU(cudaMemcpyAsync(n_iter + first, ctx->d_nit[s].p, n, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    if (crc_ok) CU(cudaMemcpyAsync(crc_ok + first, ctx->d_crc[s].p, n, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    CU(cudaEventRecord(ctx->ev_d2h[s], ctx->d2h_stream));
+  }
+  CU(cudaStreamSynchronize(ctx->d2h_stream));
+  CU(cudaStreamSynchronize(cs));
+  return SRSLTE_B200_SUCCESS;
+}
+
+int srslte_b200_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_rm_block_t* blocks, uint32_t n_blocks,
+                                const int16_t* e, int16_t* work)
+{
+  if (!ctx) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  if (n_blocks == 0) return SRSLTE_B200_SUCCESS;
+  if (!blocks || !e || !work) return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "NULL argument");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CU(cudaStreamSynchronize(st));  // pinned staging reuse
+  CU(ctx->h_rm_items.reserve(n_blocks));
+  CU(ctx->d_rm_items.reserve(n_blocks));
+  for (uint32_t i = 0; i < n_blocks; i++) {
+    const srslte_b200_rm_block_t& bl = blocks[i];
+    if (bl.rv > 3 || cb_index_exact(bl.long_cb) < 0)
+      return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "block %u: invalid K=%u or rv=%u", i, bl.long_cb, bl.rv);
+    const uint32_t key = bl.long_cb * 4 + bl.rv;
+    auto           it  = ctx->rm_tab_off.find(key);
+    if (it == ctx->rm_tab_off.end()) {
+      std::vector<uint16_t> t;
+      rm_rx_table(bl.long_cb, bl.rv, true, t);
+      const uint32_t off = (uint32_t)ctx->rm_pool_host.size();
+      ctx->rm_pool_host.insert(ctx->rm_pool_host.end(), t.begin(), t.end());
+      it = ctx->rm_tab_off.emplace(key, off).first;
+    }
+    RmItem ri;
+    ri.e_off    = bl.e_offset;
+    ri.E        = bl.e_len;
+    ri.work_off = bl.work_offset;
+    ri.tab_off  = it->second;
+    ri.N        = 3 * bl.long_cb + 12;
+    ctx->h_rm_items.p[i] = ri;
+  }
+  if (ctx->rm_pool_uploaded != ctx->rm_pool_host.size()) {
+    if (ctx->rm_pool_host.size() > ctx->rm_pool_dev.cap) {
+      // grow: the whole pool is re-uploaded (tables are small and cached for the context lifetime)
+      CU(ctx->rm_pool_dev.reserve(ctx->rm_pool_host.size() * 2));
+      ctx->rm_pool_uploaded = 0;
+    }
+    CU(cudaMemcpyAsync(ctx->rm_pool_dev.p + ctx->rm_pool_uploaded, ctx->rm_pool_host.data() + ctx->rm_pool_uploaded,
+                       (ctx->rm_pool_host.size() - ctx->rm_pool_uploaded) * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));  // the source is pageable std::vector memory
+    ctx->rm_pool_uploaded = ctx->rm_pool_host.size();
+  }
+  CU(cudaMemcpyAsync(ctx->d_rm_items.p, ctx->h_rm_items.p, n_blocks * sizeof(RmItem), cudaMemcpyHostToDevice, st));
+  CU(rm_rx_launch(e, work, ctx->rm_pool_dev.p, ctx->d_rm_items.p, n_blocks, st));
+  ctx->launches++;
+  return SRSLTE_B200_SUCCESS;
+}
+
+}  // extern "C"

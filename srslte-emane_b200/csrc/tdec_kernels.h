@@ -1,0 +1,70 @@
+// tdec_kernels.h -- launch interface of the sm_100a turbo-decode kernels (internal to the library).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200 {
+
+// One warp-load of code blocks that share K (and therefore window count, window length and QPP).
+struct WorkItem {
+  uint32_t first;   // index of the first code block of this item in `order`
+  uint16_t count;   // code blocks in this item (<= blocks-per-warp of the kernel that runs it)
+  uint16_t K;
+  uint16_t f1, f2;  // QPP coefficients of K
+};
+
+enum CrcMode : uint32_t {
+  CRC_NONE = 0,  // run exactly max(1, nof_iterations) half iterations (srslte_tdec_run_all)
+  CRC_24B  = 1,  // stop a block when CRC24B over its K decoded bits is 0 (sch.c, C > 1)
+  CRC_24A  = 2,  // same with CRC24A (sch.c, single-block transport block)
+};
+
+struct TdecLaunch {
+  const int16_t*  in;          // working-layout input of every code block (device)
+  uint32_t        in_stride;   // int16 elements between code blocks (even)
+  uint8_t*        out;         // decoded bytes (device)
+  uint32_t        out_stride;  // bytes between code blocks
+  uint8_t*        n_iter;      // [n_cb] half iterations run (device, nullable)
+  uint8_t*        crc_ok;      // [n_cb] 1 when the block's CRC was 0 (device, nullable)
+  const uint32_t* order;       // code-block indices grouped by K (device)
+  const WorkItem* items;       // device
+  uint32_t        n_items;
+  uint32_t*       counter;     // device work counter, zeroed by the launcher
+  uint32_t        max_iter;    // half-iteration cap
+  uint32_t        crc_mode;
+  int16_t*        ws_ae;       // extrinsic work arrays, sized by tdec_workspace_bytes()
+  uint32_t*       ws_chk;      // beta checkpoints, sized by tdec_workspace_bytes()
+};
+
+struct TdecGeometry {
+  int      blocks;          // grid size
+  int      threads;         // block size
+  size_t   smem;            // dynamic shared memory per block
+  size_t   ws_ae_bytes;     // workspace for the a-priori / extrinsic arrays
+  size_t   ws_chk_bytes;    // workspace for the beta checkpoints
+};
+
+// W = 16 or 8 (window decoders) or 0 (generic decoder, K <= 400)
+cudaError_t tdec_geometry(int W, int device, TdecGeometry* g);
+cudaError_t tdec_launch(int W, const TdecGeometry& g, const TdecLaunch& a, cudaStream_t s);
+int         tdec_blocks_per_warp(int W);
+
+// natural (3i+j, tails last) -> working layout, one code block per CTA.
+cudaError_t natural_to_working_launch(const int16_t* nat, uint32_t nat_stride, int16_t* work, uint32_t work_stride,
+                                      const uint32_t* cb_K /* device, nullable */, uint32_t uniform_K, uint32_t n_cb,
+                                      cudaStream_t s);
+
+// rate de-matching: work[tab[i mod N]] += e[i], i < E, wrapping int16.
+struct RmItem {
+  uint32_t e_off;     // offset of this block's samples in the e buffer (int16 elements)
+  uint32_t E;         // samples
+  uint32_t work_off;  // offset of the block's working buffer (int16 elements)
+  uint32_t tab_off;   // offset of its (K, rv) index table in the table pool (uint16 elements)
+  uint32_t N;         // 3K+12
+};
+cudaError_t rm_rx_launch(const int16_t* e, int16_t* work, const uint16_t* tab_pool, const RmItem* items,
+                         uint32_t n_items, cudaStream_t s);
+
+void upload_crc_tables();  // fills the __constant__ CRC tables (once per process/device)
+
+}  // namespace b200
