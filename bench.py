@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- batched LTE turbo decode on B200: information Gbit/s (K=6144, nof_iterations=4).
+
+One "step" = one pass of the hot path over one batch of synthetic code blocks:
+natural-order int16 LLRs -> working layout -> 4 half iterations of int16 max-log-MAP -> hard decision
+(srslte_tdec_run_all semantics, the reference's turbodecoder_test config scaled to a batch).
+
+  value        device-resident throughput (inputs already in HBM), CUDA events, max over ranks
+  e2e          same metric through the host-pointer C-ABI call (pinned host input, H2D + D2H inside)
+  roofline     dominant kernel (16-window decoder) against the measured integer-pipe peak
+               (+ roofline_hbm: its algorithmic bytes against the measured HBM copy bandwidth)
+  cpu_baseline the reference's own AVX2 decoder (oracle/_ref) on the box's host cores, bounded sample
+
+`--impl reference` times the reference's CPU implementation alone on all host cores.
+Multi-GPU: one process per GPU under torchrun, code blocks sharded, no data-path collective
+(torch.distributed is only used for the barrier and the max-over-ranks of the timing).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 6144
+NOF_ITERATIONS = 4          # srsLTE HALF iterations
+EBNO_HARNESS = 1.5          # turbodecoder_test "-e 1.5" (sigma = 1.457 on +-1; never converges, F7)
+LLR_SCALE = 100.0
+IN_LEN = 3 * K + 12
+INT_PEAK_THREAD_INSTR_PER_CLK_SM = 64.0   # measured: profiles/r01_int_peak*.txt (VIADD.16x2 / VIMNMX.S16x2)
+
+
+def int_ops_per_block(k=K, w=16, nit=NOF_ITERATIONS):
+    """int16 lane-ops per MAP call = 80*K + 1960*W."""
+    return nit * (80 * k + 1960 * w)
+
+
+def algo_bytes_per_block(k=K):
+    """(3K+12)*2 B read + K/8 B + 2 B written."""
+    return (3 * k + 12) * 2 + k // 8 + 2
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.stop_flag = False
+        self.gpu = gpu_index
+        self.t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.t:
+            self.t.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_llr_device(n, device, seed):
+    """Synthetic natural-order int16 LLRs [n, 3K+12] on the GPU: random payloads -> LTE turbo encoder ->
+    BPSK +-1 -> AWGN (harness -e 1.5) -> (int16)(100*rx).  A pool of 512 distinct code words is tiled over
+    the batch; the noise is independent per block."""
+    import torch
+    import __graft_entry__ as ge
+    vec = ge.load_package().vectors
+    pool = 512
+    rng = np.random.default_rng(seed)
+    bits = rng.integers(0, 2, (pool, K), dtype=np.uint8)
+    coded = torch.from_numpy(vec.turbo_encode(bits)).to(device)          # [pool, 3K+12] 0/1
+    sigma = vec.harness_sigma(EBNO_HARNESS)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty((n, IN_LEN), dtype=torch.int16, device=device)
+    step = 4096
+    for i in range(0, n, step):
+        m = min(step, n - i)
+        idx = (torch.arange(i, i + m, device=device) % pool)
+        tx = coded[idx].to(torch.float32) * 2.0 - 1.0
+        rx = tx + sigma * torch.randn((m, IN_LEN), device=device, generator=g)
+        out[i:i + m] = torch.trunc(LLR_SCALE * rx).clamp_(-32768, 32767).to(torch.int16)
+    return out
+
+
+def cpu_reference_rate(sample_blocks, threads, llr_np, min_wall=1.5):
+    """Gbit/s of the reference's AVX2 decoder (oracle/_ref) over `sample_blocks` blocks on `threads` cores."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_libs as ol
+    R = ol.ref()
+    kind = "reference"
+    run = ol.ref_run_all
+    if R is None:
+        kind = "port"
+        run = lambda llr, k, nit, natural=True, threads=None: ol.port_run_all(llr, k, nit, natural)  # noqa: E731
+    x = llr_np[:sample_blocks]
+    run(x[:min(len(x), 4 * threads)], K, NOF_ITERATIONS, True, threads=threads)   # warm the tables / caches
+    t0 = time.perf_counter()
+    passes = 0
+    while True:                      # repeat the sample until ~min_wall seconds of wall time have been spent
+        run(x, K, NOF_ITERATIONS, True, threads=threads)
+        passes += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_wall:
+            break
+    return passes * len(x) * K / dt / 1e9, dt, kind, passes
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import __graft_entry__ as ge
+    vec = ge.load_package().vectors
+    cores = os.cpu_count() or 1
+    n = max(cores * 512, 4096)      # ~0.5 s of all-core work per step
+    bits, llr = vec.make_blocks(n, K, vec.harness_sigma(EBNO_HARNESS), LLR_SCALE, seed=7, crc=False)
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_rate(min(n, cores * 8), cores, llr, min_wall=0.0)
+    times = []
+    kind = "reference"
+    for _ in range(args.steps):
+        rate, dt, kind, _ = cpu_reference_rate(n, cores, llr, min_wall=0.0)
+        times.append(dt)
+    dt = float(np.mean(times))
+    value = n * K / dt / 1e9
+    line = {
+        "impl": "reference", "metric": "turbo_decode_info_gbps_k6144_4it", "value": value, "unit": "Gbit/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "config": {"workload": f"srslte_tdec_run_all K={K} nof_iterations={NOF_ITERATIONS} (half iterations), "
+                               f"AWGN harness -e {EBNO_HARNESS}, scale {LLR_SCALE:g}; reference CPU arm: {n} blocks per step"},
+        "cpu_baseline": {"value": value, "unit": "Gbit/s", "cores": cores, "kind": kind,
+                         "sample": f"{n} K={K} blocks per step, {cores} pthreads, one srslte_tdec_t each"},
+        "e2e": {"value": value, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--blocks", type=int, default=65536, help="code blocks per GPU per step")
+    ap.add_argument("--e2e-blocks", type=int, default=16384, help="code blocks per GPU for the host-pointer leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=dev)
+        dist = dist_mod
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.blocks
+    ctx = pkg.Context(local)
+    stream = torch.cuda.Stream(device=dev)   # an explicit stream: the kernels and the timing events share it
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+
+    llr = make_llr_device(n, dev, seed=1234 + rank)
+    out = torch.zeros((n, K // 8), dtype=torch.uint8, device=dev)
+    nit = torch.zeros(n, dtype=torch.uint8, device=dev)
+    crc = torch.zeros(n, dtype=torch.uint8, device=dev)
+
+    def step():
+        ctx.tdec_batch_dev(llr.data_ptr(), n, IN_LEN, K, NOF_ITERATIONS, out.data_ptr(), K // 8, nit.data_ptr(),
+                           crc.data_ptr(), crc_mode=pkg.CRC_NONE, natural=True)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.enable_timing(True)
+    launches0 = ctx.launch_count
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launch_count - launches0
+    dec_ms, dec_n = ctx.kernel_time(0)
+    lay_ms, lay_n = ctx.kernel_time(3)
+    ctx.enable_timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * n * K / (ms_step * 1e-3) / 1e9
+
+    # sanity: the decoder must have produced something that depends on the input
+    chk = int(out[: min(n, 64)].to(torch.int32).sum().item())
+
+    # ---- end to end through the host-pointer entry (pinned host memory, H2D + D2H inside) -------------
+    ne = min(args.e2e_blocks, n)
+    pin_in = pkg.PinnedArray((ne, IN_LEN), np.int16)
+    pin_out = pkg.PinnedArray((ne, K // 8), np.uint8)
+    pin_in.array[:] = llr[:ne].cpu().numpy()
+    ctx.set_stream(0)  # the host entry uses the context's own streams
+    for _ in range(2):
+        ctx.tdec_batch_host(pin_in.array, K, NOF_ITERATIONS, out=pin_out.array)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        got, got_nit, _ = ctx.tdec_batch_host(pin_in.array, K, NOF_ITERATIONS, out=pin_out.array)
+    e2e_dt = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * ne * K / float(t.item()) / 1e9
+    same = bool(np.array_equal(pin_out.array[:64], out[:64].cpu().numpy()))
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured" if "hbm_gbs" in peaks else "fallback"
+    sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    sm_max = (clocks or {}).get("sm_max_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
+    dec_ms_per_launch = dec_ms / max(dec_n, 1)
+    ops_launch = n * int_ops_per_block()
+    achieved_tops = ops_launch / (dec_ms_per_launch * 1e-3) / 1e12
+    peak_tops = INT_PEAK_THREAD_INSTR_PER_CLK_SM * 2 * sms * sm_max * 1e6 / 1e12      # int16 lane-ops/s at max clock
+    bytes_launch = n * algo_bytes_per_block()
+    hbm_achieved = bytes_launch / (dec_ms_per_launch * 1e-3) / 1e9
+
+    line = {
+        "metric": "turbo_decode_info_gbps_k6144_4it", "value": value, "unit": "Gbit/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "config": {
+            "workload": f"batched srslte_tdec_run_all: {n} code blocks per GPU, K={K}, nof_iterations={NOF_ITERATIONS} "
+                        f"(srsLTE half iterations), natural-order int16 LLR, AWGN harness -e {EBNO_HARNESS} "
+                        f"(sigma 1.457), LLR scale {LLR_SCALE:g}, 16-window int16 max-log-MAP, no CRC",
+            "blocks_per_gpu": n, "K": K, "nof_iterations": NOF_ITERATIONS,
+            "l2": f"inputs {n * IN_LEN * 2 / 1e6:.0f} MB per step > 126 MB L2, no flush needed",
+            "parallelism": f"code blocks sharded over {world} GPU(s), no collective",
+        },
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "Gbit/s", "h2d_bytes_per_step": ne * IN_LEN * 2,
+                "d2h_bytes_per_step": ne * (K // 8 + 2), "blocks_per_gpu": ne, "ms_per_step": e2e_dt * 1e3,
+                "matches_device_path": same},
+        "gpu_launches": launches,
+        "roofline": {
+            "bound": "int_alu", "kernel": "tdec_win_kernel<16>", "achieved": achieved_tops, "peak": peak_tops,
+            "unit": "Tops/s (int16 lane-ops)", "frac": achieved_tops / peak_tops,
+            "ops_per_block": int_ops_per_block(), "ms_per_launch": dec_ms_per_launch,
+            "peak_source": f"measured {INT_PEAK_THREAD_INSTR_PER_CLK_SM:g} packed-int16x2 thread-instr/clk/SM "
+                           f"(tools/int_peak.cu, profiles/r01_int_peak*.txt) x 2 lanes x {sms} SMs x {sm_max:g} MHz",
+            "sm_mhz_during_run": sm_mhz, "traffic": None,
+        },
+        "roofline_hbm": {
+            "bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+            "bytes_per_block": algo_bytes_per_block(), "peak_source": f"MEASURED_PEAKS.json ({hbm_src})", "traffic": None,
+        },
+        "kernel_share": {"decode_ms_per_step": dec_ms / args.steps, "layout_ms_per_step": lay_ms / args.steps,
+                         "decode_launches": dec_n, "layout_launches": lay_n},
+        "checksum": chk,
+    }
+
+    if not args.no_cpu:
+        cores = os.cpu_count() or 1
+        sample = min(ne, max(1024, cores * 256))
+        llr_np = pin_in.array[:sample].copy()
+        rate, dt, kind, passes = cpu_reference_rate(sample, cores, llr_np, min_wall=1.5)
+        line["cpu_baseline"] = {"value": rate, "unit": "Gbit/s", "cores": cores, "kind": kind,
+                                "sample": f"{passes} passes over {sample} of the same K={K} blocks, "
+                                          f"nof_iterations={NOF_ITERATIONS}, {cores} pthreads (one srslte_tdec_t "
+                                          f"each), {dt:.2f} s wall = {dt * cores:.0f} core-seconds"}
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -51,6 +51,15 @@ SRSLTE_B200_API const char* srslte_b200_last_error(const srslte_b200_ctx_t* ctx)
 /* Number of kernels this context has launched so far (bench.py's gpu_launches).                 */
 SRSLTE_B200_API uint64_t srslte_b200_launch_count(const srslte_b200_ctx_t* ctx);
 
+/* Optional per-kernel timing for measurement (bench.py): when enabled, every kernel launch of the
+ * context is bracketed by CUDA events on its own stream.  kind: 0 = 16-window decoder, 1 = 8-window
+ * decoder, 2 = generic decoder, 3 = natural->working layout, 4 = rate de-matching.
+ * _kernel_time synchronizes the device and returns the summed duration and the launch count since
+ * timing was (re-)enabled.                                                                       */
+SRSLTE_B200_API int srslte_b200_ctx_enable_timing(srslte_b200_ctx_t* ctx, int enable);
+SRSLTE_B200_API int srslte_b200_ctx_kernel_time(srslte_b200_ctx_t* ctx, int kind, double* total_ms,
+                                                uint32_t* launches);
+
 /* Pinned host memory for the *_host entries (plain cudaHostAlloc; any host pointer is accepted,
  * pinned ones are copied without staging).                                                      */
 SRSLTE_B200_API void* srslte_b200_host_alloc(size_t bytes);

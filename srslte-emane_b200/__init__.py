@@ -12,6 +12,7 @@ import os
 
 import numpy as np
 
+from . import sharding  # noqa: F401
 from . import vectors  # noqa: F401  (synthetic vector generation; no decoder inside)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -36,7 +37,7 @@ class RmBlock(C.Structure):
 EXPORTS = [
     "srslte_b200_ctx_create", "srslte_b200_ctx_destroy", "srslte_b200_ctx_set_stream",
     "srslte_b200_ctx_synchronize", "srslte_b200_last_error", "srslte_b200_launch_count",
-    "srslte_b200_host_alloc", "srslte_b200_host_free", "srslte_b200_cb_index", "srslte_b200_cb_size",
+    "srslte_b200_ctx_enable_timing", "srslte_b200_ctx_kernel_time", "srslte_b200_host_alloc", "srslte_b200_host_free", "srslte_b200_cb_index", "srslte_b200_cb_size",
     "srslte_b200_nof_windows", "srslte_b200_working_len", "srslte_b200_rm_rx_table",
     "srslte_b200_tdec_batch_dev", "srslte_b200_tdec_batch_host", "srslte_b200_rm_rx_batch_dev",
 ]
@@ -63,6 +64,8 @@ def lib():
     L.srslte_b200_last_error.restype = C.c_char_p
     L.srslte_b200_launch_count.argtypes = [vp]
     L.srslte_b200_launch_count.restype = C.c_uint64
+    L.srslte_b200_ctx_enable_timing.argtypes = [vp, i32]
+    L.srslte_b200_ctx_kernel_time.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u32)]
     L.srslte_b200_host_alloc.argtypes = [C.c_size_t]
     L.srslte_b200_host_alloc.restype = vp
     L.srslte_b200_host_free.argtypes = [vp]
@@ -154,6 +157,15 @@ class Context:
 
     def synchronize(self):
         self._check(self._L.srslte_b200_ctx_synchronize(self._h), "synchronize")
+
+    def enable_timing(self, on=True):
+        self._check(self._L.srslte_b200_ctx_enable_timing(self._h, int(on)), "enable_timing")
+
+    def kernel_time(self, kind):
+        """(total ms, launches) of kernel kind 0..4 since timing was enabled (synchronizes)."""
+        ms, n = C.c_double(), C.c_uint32()
+        self._check(self._L.srslte_b200_ctx_kernel_time(self._h, kind, C.byref(ms), C.byref(n)), "kernel_time")
+        return ms.value, n.value
 
     @property
     def launch_count(self):

@@ -111,6 +111,10 @@ struct srslte_b200_ctx {
   DevBuf<RmItem>               d_rm_items;
   PinBuf<RmItem>               h_rm_items;
   uint64_t     launches = 0;
+  // optional per-kernel event timing (bench.py's roofline): kind 0..4 = W16, W8, generic, layout, rate-dematch
+  bool         timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev[5];
+  size_t       tev_used[5] = {0, 0, 0, 0, 0};
   std::string  err;
 };
 
@@ -136,6 +140,30 @@ int fail(srslte_b200_ctx* c, int code, const char* fmt, ...)
   } while (0)
 
 int regime_index(int W) { return W == 16 ? 0 : W == 8 ? 1 : 2; }
+
+// event pair around one kernel launch when timing is enabled
+struct KernelTimer {
+  srslte_b200_ctx* c;
+  int              kind;
+  cudaStream_t     st;
+  cudaEvent_t      stop = nullptr;
+  KernelTimer(srslte_b200_ctx* ctx, int k, cudaStream_t s) : c(ctx), kind(k), st(s)
+  {
+    if (!c->timing || c->tev_used[kind] >= 4096) return;
+    if (c->tev_used[kind] == c->tev[kind].size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+      c->tev[kind].emplace_back(a, b);
+    }
+    auto& pr = c->tev[kind][c->tev_used[kind]++];
+    cudaEventRecord(pr.first, st);
+    stop = pr.second;
+  }
+  ~KernelTimer()
+  {
+    if (stop) cudaEventRecord(stop, st);
+  }
+};
 
 int ensure_regime(srslte_b200_ctx* ctx, int ri)
 {
@@ -271,8 +299,11 @@ int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint
   uint32_t       stride = b->in_stride;
   if (b->input_format == SRSLTE_B200_INPUT_NATURAL) {
     CU(ctx->d_work.reserve((size_t)b->n_cb * work_len));
-    CU(natural_to_working_launch(d_llr, b->in_stride, ctx->d_work.p, work_len, b->long_cb ? ctx->d_cbK.p : nullptr,
-                                 b->uniform_long_cb, b->n_cb, st));
+    {
+      KernelTimer kt(ctx, 3, st);
+      CU(natural_to_working_launch(d_llr, b->in_stride, ctx->d_work.p, work_len, b->long_cb ? ctx->d_cbK.p : nullptr,
+                                   b->uniform_long_cb, b->n_cb, st));
+    }
     ctx->launches++;
     win    = ctx->d_work.p;
     stride = work_len;
@@ -299,7 +330,10 @@ int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint
     a.crc_mode   = b->crc_mode;
     a.ws_ae      = reinterpret_cast<int16_t*>(R.ws_ae.p);
     a.ws_chk     = reinterpret_cast<uint32_t*>(R.ws_chk.p);
-    CU(tdec_launch(R.W, R.geo, a, st));
+    {
+      KernelTimer kt(ctx, r, st);
+      CU(tdec_launch(R.W, R.geo, a, st));
+    }
     ctx->launches++;
   }
   return 0;
@@ -366,6 +400,11 @@ void srslte_b200_ctx_destroy(srslte_b200_ctx_t* ctx)
     if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
     if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
   }
+  for (auto& v : ctx->tev)
+    for (auto& pr : v) {
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
   ctx->rm_pool_dev.release();
   ctx->d_rm_items.release();
   ctx->h_rm_items.release();
@@ -391,6 +430,30 @@ int srslte_b200_ctx_synchronize(srslte_b200_ctx_t* ctx)
 
 const char* srslte_b200_last_error(const srslte_b200_ctx_t* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 uint64_t    srslte_b200_launch_count(const srslte_b200_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
+
+int srslte_b200_ctx_enable_timing(srslte_b200_ctx_t* ctx, int enable)
+{
+  if (!ctx) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  ctx->timing = enable != 0;
+  for (auto& u : ctx->tev_used) u = 0;
+  return SRSLTE_B200_SUCCESS;
+}
+
+int srslte_b200_ctx_kernel_time(srslte_b200_ctx_t* ctx, int kind, double* total_ms, uint32_t* launches)
+{
+  if (!ctx || kind < 0 || kind > 4 || !total_ms || !launches) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaDeviceSynchronize());
+  double sum = 0;
+  for (size_t i = 0; i < ctx->tev_used[kind]; i++) {
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->tev[kind][i].first, ctx->tev[kind][i].second));
+    sum += ms;
+  }
+  *total_ms = sum;
+  *launches = (uint32_t)ctx->tev_used[kind];
+  return SRSLTE_B200_SUCCESS;
+}
 
 void* srslte_b200_host_alloc(size_t bytes)
 {
@@ -524,7 +587,10 @@ int srslte_b200_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_rm_blo
     ctx->rm_pool_uploaded = ctx->rm_pool_host.size();
   }
   CU(cudaMemcpyAsync(ctx->d_rm_items.p, ctx->h_rm_items.p, n_blocks * sizeof(RmItem), cudaMemcpyHostToDevice, st));
-  CU(rm_rx_launch(e, work, ctx->rm_pool_dev.p, ctx->d_rm_items.p, n_blocks, st));
+  {
+    KernelTimer kt(ctx, 4, st);
+    CU(rm_rx_launch(e, work, ctx->rm_pool_dev.p, ctx->d_rm_items.p, n_blocks, st));
+  }
   ctx->launches++;
   return SRSLTE_B200_SUCCESS;
 }
