@@ -231,6 +231,7 @@ def main():
         sampler.start()
     ctx.enable_timing(True)
     launches0 = ctx.launch_count
+    fallbacks0 = ctx.fallback_count
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     barrier()
@@ -241,6 +242,7 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
+    fallbacks = ctx.fallback_count - fallbacks0
     dec_ms, dec_n = ctx.kernel_time(0)
     lay_ms, lay_n = ctx.kernel_time(3)
     ctx.enable_timing(False)
@@ -329,6 +331,8 @@ def main():
         },
         "kernel_share": {"decode_ms_per_step": dec_ms / args.steps, "layout_ms_per_step": lay_ms / args.steps,
                          "decode_launches": dec_n, "layout_launches": lay_n},
+        "exact_fallbacks": {"count": fallbacks, "of": args.steps * ((n + 3) // 4) * NOF_ITERATIONS,
+                            "unit": "(warp, half iteration) pairs re-run with exact saturating arithmetic"},
         "checksum": chk,
     }
 

@@ -60,6 +60,14 @@ SRSLTE_B200_API int srslte_b200_ctx_enable_timing(srslte_b200_ctx_t* ctx, int en
 SRSLTE_B200_API int srslte_b200_ctx_kernel_time(srslte_b200_ctx_t* ctx, int kind, double* total_ms,
                                                 uint32_t* launches);
 
+/* The window decoders run every half iteration first with wrapping int16x2 arithmetic plus a proof
+ * that none of the reference's saturating operations could have clamped, and re-run it with exact
+ * saturating arithmetic when the proof fails (both on the GPU, results identical by construction).
+ * _set_exact(1) forces the exact variant (tests); _fallback_count returns how many (warp, half
+ * iteration) pairs have taken the exact re-run so far (synchronizes the device).                 */
+SRSLTE_B200_API int srslte_b200_ctx_set_exact(srslte_b200_ctx_t* ctx, int force_exact);
+SRSLTE_B200_API int srslte_b200_ctx_fallback_count(srslte_b200_ctx_t* ctx, uint64_t* count);
+
 /* Pinned host memory for the *_host entries (plain cudaHostAlloc; any host pointer is accepted,
  * pinned ones are copied without staging).                                                      */
 SRSLTE_B200_API void* srslte_b200_host_alloc(size_t bytes);

@@ -37,7 +37,8 @@ class RmBlock(C.Structure):
 EXPORTS = [
     "srslte_b200_ctx_create", "srslte_b200_ctx_destroy", "srslte_b200_ctx_set_stream",
     "srslte_b200_ctx_synchronize", "srslte_b200_last_error", "srslte_b200_launch_count",
-    "srslte_b200_ctx_enable_timing", "srslte_b200_ctx_kernel_time", "srslte_b200_host_alloc", "srslte_b200_host_free", "srslte_b200_cb_index", "srslte_b200_cb_size",
+    "srslte_b200_ctx_enable_timing", "srslte_b200_ctx_kernel_time", "srslte_b200_ctx_set_exact",
+    "srslte_b200_ctx_fallback_count", "srslte_b200_host_alloc", "srslte_b200_host_free", "srslte_b200_cb_index", "srslte_b200_cb_size",
     "srslte_b200_nof_windows", "srslte_b200_working_len", "srslte_b200_rm_rx_table",
     "srslte_b200_tdec_batch_dev", "srslte_b200_tdec_batch_host", "srslte_b200_rm_rx_batch_dev",
 ]
@@ -66,6 +67,8 @@ def lib():
     L.srslte_b200_launch_count.restype = C.c_uint64
     L.srslte_b200_ctx_enable_timing.argtypes = [vp, i32]
     L.srslte_b200_ctx_kernel_time.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u32)]
+    L.srslte_b200_ctx_set_exact.argtypes = [vp, i32]
+    L.srslte_b200_ctx_fallback_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.srslte_b200_host_alloc.argtypes = [C.c_size_t]
     L.srslte_b200_host_alloc.restype = vp
     L.srslte_b200_host_free.argtypes = [vp]
@@ -166,6 +169,16 @@ class Context:
         ms, n = C.c_double(), C.c_uint32()
         self._check(self._L.srslte_b200_ctx_kernel_time(self._h, kind, C.byref(ms), C.byref(n)), "kernel_time")
         return ms.value, n.value
+
+    def set_exact(self, on=True):
+        """force the exact saturating variant of the window decoders (the fast variant is the default)."""
+        self._check(self._L.srslte_b200_ctx_set_exact(self._h, int(on)), "set_exact")
+
+    @property
+    def fallback_count(self):
+        v = C.c_uint64()
+        self._check(self._L.srslte_b200_ctx_fallback_count(self._h, C.byref(v)), "fallback_count")
+        return int(v.value)
 
     @property
     def launch_count(self):

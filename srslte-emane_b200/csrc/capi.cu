@@ -85,7 +85,8 @@ struct srslte_b200_ctx {
   cudaStream_t h2d_stream  = nullptr;
   cudaStream_t d2h_stream  = nullptr;
   Regime       regime[3];
-  DevBuf<uint32_t> counters;           // 3 work counters
+  DevBuf<uint32_t> counters;           // 3 work counters + 1 fallback counter
+  bool         force_exact = false;
   // schedule cache
   DevBuf<uint32_t> d_order;
   DevBuf<WorkItem> d_items;
@@ -285,7 +286,11 @@ int check_batch(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint32_
     if (b->out_stride < K / 8) return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "out_stride %u < K/8 for K=%u", b->out_stride, K);
     wl = std::max(wl, working_len(K));
   }
-  *max_work_len = (wl + 63u) & ~63u;
+  (void)wl;
+  uint32_t il = 0;
+  for (uint32_t i = 0; i < (b->long_cb ? b->n_cb : 1u); i++)
+    il = std::max(il, internal_len(b->long_cb ? b->long_cb[i] : b->uniform_long_cb));
+  *max_work_len = (il + 63u) & ~63u;
   return 0;
 }
 
@@ -295,20 +300,20 @@ int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint
 {
   int rc = ensure_schedule(ctx, b->long_cb, b->uniform_long_cb, b->n_cb, st);
   if (rc) return rc;
-  const int16_t* win    = d_llr;
-  uint32_t       stride = b->in_stride;
-  if (b->input_format == SRSLTE_B200_INPUT_NATURAL) {
-    CU(ctx->d_work.reserve((size_t)b->n_cb * work_len));
-    {
-      KernelTimer kt(ctx, 3, st);
-      CU(natural_to_working_launch(d_llr, b->in_stride, ctx->d_work.p, work_len, b->long_cb ? ctx->d_cbK.p : nullptr,
-                                   b->uniform_long_cb, b->n_cb, st));
-    }
-    ctx->launches++;
-    win    = ctx->d_work.p;
-    stride = work_len;
+  // every input format is first brought into the decoder's internal layout
+  CU(ctx->d_work.reserve((size_t)b->n_cb * work_len));
+  {
+    KernelTimer kt(ctx, 3, st);
+    CU(to_internal_launch(d_llr, b->in_stride, b->input_format == SRSLTE_B200_INPUT_NATURAL ? 0 : 1, ctx->d_work.p,
+                          work_len, b->long_cb ? ctx->d_cbK.p : nullptr, b->uniform_long_cb, b->n_cb, st));
   }
-  CU(ctx->counters.reserve(4));
+  ctx->launches++;
+  const int16_t* win    = ctx->d_work.p;
+  const uint32_t stride = work_len;
+  if (ctx->counters.cap == 0) {
+    CU(ctx->counters.reserve(4));
+    CU(cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(uint32_t), st));
+  }
   for (int r = 0; r < 3; r++) {
     const auto& items = ctx->sched.items[r];
     if (items.empty()) continue;
@@ -330,6 +335,8 @@ int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint
     a.crc_mode   = b->crc_mode;
     a.ws_ae      = reinterpret_cast<int16_t*>(R.ws_ae.p);
     a.ws_chk     = reinterpret_cast<uint32_t*>(R.ws_chk.p);
+    a.force_exact = ctx->force_exact ? 1u : 0u;
+    a.stats      = ctx->counters.p + 3;
     {
       KernelTimer kt(ctx, r, st);
       CU(tdec_launch(R.W, R.geo, a, st));
@@ -452,6 +459,26 @@ int srslte_b200_ctx_kernel_time(srslte_b200_ctx_t* ctx, int kind, double* total_
   }
   *total_ms = sum;
   *launches = (uint32_t)ctx->tev_used[kind];
+  return SRSLTE_B200_SUCCESS;
+}
+
+int srslte_b200_ctx_set_exact(srslte_b200_ctx_t* ctx, int force_exact)
+{
+  if (!ctx) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  ctx->force_exact = force_exact != 0;
+  return SRSLTE_B200_SUCCESS;
+}
+
+int srslte_b200_ctx_fallback_count(srslte_b200_ctx_t* ctx, uint64_t* count)
+{
+  if (!ctx || !count) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  *count = 0;
+  if (ctx->counters.cap == 0) return SRSLTE_B200_SUCCESS;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaDeviceSynchronize());
+  uint32_t v = 0;
+  CU(cudaMemcpy(&v, ctx->counters.p + 3, sizeof(v), cudaMemcpyDeviceToHost));
+  *count = v;
   return SRSLTE_B200_SUCCESS;
 }
 

@@ -11,18 +11,25 @@
 //
 // How (B200 mapping):
 //   * a code block is W independent trellis windows; one thread owns TWO adjacent windows as the
-//     two int16 halves of every 32-bit register (the reference's storage layout puts windows
-//     d, d+1 of trellis row k next to each other, so one 32-bit load feeds both).  W/2 threads per
-//     block, 4 (W=16) or 8 (W=8) code blocks per warp, the 8 state metrics live in registers.
+//     two int16 halves of every 32-bit register.  W/2 threads per block, 4 (W=16) or 8 (W=8) code
+//     blocks per warp, the 8 state metrics live in registers.
+//   * inputs are held in a "pair-major" layout: the words a thread needs for 4 consecutive trellis
+//     rows are contiguous, so one 128-bit load feeds 4 steps.
 //   * the reference keeps all beta metrics of a half iteration (98 KB per K=6144 block).  Here the
 //     backward pass keeps one checkpoint per 16 trellis rows; the forward pass rebuilds the 16 rows
-//     of beta it needs in shared memory (the recursion and its normalisation points depend only
-//     on the row index, so the rebuilt values are identical).
+//     of beta it needs in shared memory (the recursion and its normalisation points depend only on
+//     the row index, so the rebuilt values are identical).
 //   * the two extrinsic arrays are stored already differenced (what the reference computes with
 //     srslte_vec_sub_sss at the start of the next half iteration), so the a-posteriori value of
 //     every bit is always A + E (wrapping) and no third array is needed.
-//   * QPP addresses are computed on the fly from (f1, f2): pi(d*L + k) shares its row
+//   * QPP addresses are computed in the kernel from (f1, f2): pi(d*L + k) shares its row
 //     pi(k) mod L across all windows (contention-free property), only the window index differs.
+//   * saturating int16x2 adds are 6 instructions on sm_100a, wrapping adds and fused add-max are 1.
+//     Every half iteration first runs a FAST variant (wrapping VIADD.16x2 on the FMA pipe, fused
+//     VIADDMNMX.S16x2 / VIMNMX.S16x2 on the ALU pipe) that also records the extremes of its state
+//     metrics; from them it PROVES that no saturating operation of the reference could have
+//     clamped (then wrapping == saturating, bit for bit).  If the proof fails, the half iteration
+//     is re-run with the EXACT saturating variant.  Both run on the GPU; there is no CPU path.
 #include "tdec_kernels.h"
 
 #include <cstdio>
@@ -31,124 +38,303 @@ namespace b200 {
 
 namespace {
 
-constexpr int      kWarm    = 40;  // win_overlap_len
-constexpr int      kChunk   = 16;  // rows of beta rebuilt at a time (must be even)
-constexpr int      kThreads = 128;
+constexpr int      kWarm      = 40;  // win_overlap_len
+constexpr int      kChunk     = 16;  // rows of beta rebuilt at a time (multiple of 4)
+constexpr int      kThreads   = 128;
 constexpr int      kMaxChunks = 24;  // ceil(384 / 16)
-constexpr int      kNegInf  = -10000;
-constexpr uint32_t kNegInf2 = 0xD8F0D8F0u;  // (-10000, -10000)
+constexpr int      kMaxL      = 384;
+constexpr int      kExactRows = 4;   // rows next to a known-state boundary always use exact arithmetic
+constexpr int      kMaxFastG  = 5461; // largest per-step metric change the fast variant accepts (6 * G <= 32767)
+constexpr int      kNegInf    = -10000;
+constexpr uint32_t kNegInf2   = 0xD8F0D8F0u;  // (-10000, -10000)
+constexpr uint32_t kMax2      = 0x7FFF7FFFu;
+constexpr uint32_t kMin2      = 0x80008000u;
 
 __constant__ uint32_t c_crc_tab[2][256];
 
 // ---- packed int16x2 arithmetic -------------------------------------------------------------------
 __device__ __forceinline__ uint32_t sadd2(uint32_t a, uint32_t b) { return __vaddss2(a, b); }
 __device__ __forceinline__ uint32_t ssub2(uint32_t a, uint32_t b) { return __vsubss2(a, b); }
+__device__ __forceinline__ uint32_t wadd2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
 __device__ __forceinline__ uint32_t wsub2(uint32_t a, uint32_t b) { return __vsub2(a, b); }
+__device__ __forceinline__ uint32_t wneg2(uint32_t a) { return __vneg2(a); }
 __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+__device__ __forceinline__ uint32_t min2(uint32_t a, uint32_t b) { return __vmins2(a, b); }
+__device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
+__device__ __forceinline__ uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
+// max(a + b, c) with a wrapping add: only used where a + b is proven not to overflow
+__device__ __forceinline__ uint32_t addmax2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
 __device__ __forceinline__ uint32_t sra1_2(uint32_t v) { return ((v >> 1) & 0x7FFF7FFFu) | (v & 0x80008000u); }
 
+// extremes of the values a thread has seen, per int16 lane
+struct Range {
+  uint32_t hi, lo;
+  __device__ __forceinline__ void reset() { hi = 0; lo = 0; }
+  __device__ __forceinline__ void add8(const uint32_t s[8])
+  {  // s[0] is 0 after a normalisation and hi/lo already straddle 0
+    const uint32_t h1 = max3(s[1], s[2], s[3]), h2 = max3(s[4], s[5], s[6]);
+    const uint32_t l1 = min3(s[1], s[2], s[3]), l2 = min3(s[4], s[5], s[6]);
+    hi = max3(hi, h1, h2);
+    lo = min3(lo, l1, l2);
+    hi = max2(hi, s[7]);
+    lo = min2(lo, s[7]);
+  }
+  __device__ __forceinline__ void add2v(uint32_t a, uint32_t b)
+  {
+    hi = max3(hi, a, b);
+    lo = min3(lo, a, b);
+  }
+  __device__ __forceinline__ void add1(uint32_t a)
+  {
+    hi = max2(hi, a);
+    lo = min2(lo, a);
+  }
+};
+
+__device__ __forceinline__ int lo16(uint32_t v) { return (int)(int16_t)(v & 0xFFFFu); }
+__device__ __forceinline__ int hi16(uint32_t v) { return (int)(int16_t)(v >> 16); }
+
+// ---- trellis steps ---------------------------------------------------------------------------------
+// FAST = wrapping adds fused with the max; !FAST = saturating adds exactly as the reference.
+template <bool FAST>
 __device__ __forceinline__ void beta_step(uint32_t b[8], uint32_t x, uint32_t y, uint32_t xy)
 {
-  const uint32_t n0 = max2(sadd2(b[4], xy), b[0]);
-  const uint32_t n1 = max2(b[4], sadd2(b[0], xy));
-  const uint32_t n2 = max2(sadd2(b[5], y), sadd2(b[1], x));
-  const uint32_t n3 = max2(sadd2(b[5], x), sadd2(b[1], y));
-  const uint32_t n4 = max2(sadd2(b[6], x), sadd2(b[2], y));
-  const uint32_t n5 = max2(sadd2(b[6], y), sadd2(b[2], x));
-  const uint32_t n6 = max2(b[7], sadd2(b[3], xy));
-  const uint32_t n7 = max2(sadd2(b[7], xy), b[3]);
+  uint32_t n0, n1, n2, n3, n4, n5, n6, n7;
+  if (FAST) {
+    n0 = addmax2(b[4], xy, b[0]);
+    n1 = addmax2(b[0], xy, b[4]);
+    n2 = addmax2(b[5], y, wadd2(b[1], x));
+    n3 = addmax2(b[5], x, wadd2(b[1], y));
+    n4 = addmax2(b[6], x, wadd2(b[2], y));
+    n5 = addmax2(b[6], y, wadd2(b[2], x));
+    n6 = addmax2(b[3], xy, b[7]);
+    n7 = addmax2(b[7], xy, b[3]);
+  } else {
+    n0 = max2(sadd2(b[4], xy), b[0]);
+    n1 = max2(b[4], sadd2(b[0], xy));
+    n2 = max2(sadd2(b[5], y), sadd2(b[1], x));
+    n3 = max2(sadd2(b[5], x), sadd2(b[1], y));
+    n4 = max2(sadd2(b[6], x), sadd2(b[2], y));
+    n5 = max2(sadd2(b[6], y), sadd2(b[2], x));
+    n6 = max2(b[7], sadd2(b[3], xy));
+    n7 = max2(sadd2(b[7], xy), b[3]);
+  }
   b[0] = n0; b[1] = n1; b[2] = n2; b[3] = n3; b[4] = n4; b[5] = n5; b[6] = n6; b[7] = n7;
 }
 
-// branch metrics into each state: m = bit-0 branches, n = bit-1 branches
-__device__ __forceinline__ void alpha_branches(const uint32_t a[8], uint32_t x, uint32_t y, uint32_t xy,
-                                               uint32_t m[8], uint32_t n[8])
+// alpha recursion without output (warm-up rows)
+template <bool FAST>
+__device__ __forceinline__ void alpha_step(uint32_t a[8], uint32_t x, uint32_t y, uint32_t xy)
 {
-  m[0] = a[0];            m[1] = sadd2(a[3], y);  m[2] = sadd2(a[4], y);  m[3] = a[7];
-  m[4] = a[1];            m[5] = sadd2(a[2], y);  m[6] = sadd2(a[5], y);  m[7] = a[6];
-  n[0] = sadd2(a[1], xy); n[1] = sadd2(a[2], x);  n[2] = sadd2(a[5], x);  n[3] = sadd2(a[6], xy);
-  n[4] = sadd2(a[0], xy); n[5] = sadd2(a[3], x);  n[6] = sadd2(a[4], x);  n[7] = sadd2(a[7], xy);
+  uint32_t n0, n1, n2, n3, n4, n5, n6, n7;
+  if (FAST) {
+    n0 = addmax2(a[1], xy, a[0]);
+    n1 = addmax2(a[2], x, wadd2(a[3], y));
+    n2 = addmax2(a[5], x, wadd2(a[4], y));
+    n3 = addmax2(a[6], xy, a[7]);
+    n4 = addmax2(a[0], xy, a[1]);
+    n5 = addmax2(a[3], x, wadd2(a[2], y));
+    n6 = addmax2(a[4], x, wadd2(a[5], y));
+    n7 = addmax2(a[7], xy, a[6]);
+  } else {
+    n0 = max2(a[0], sadd2(a[1], xy));
+    n1 = max2(sadd2(a[3], y), sadd2(a[2], x));
+    n2 = max2(sadd2(a[4], y), sadd2(a[5], x));
+    n3 = max2(a[7], sadd2(a[6], xy));
+    n4 = max2(a[1], sadd2(a[0], xy));
+    n5 = max2(sadd2(a[2], y), sadd2(a[3], x));
+    n6 = max2(sadd2(a[5], y), sadd2(a[4], x));
+    n7 = max2(a[6], sadd2(a[7], xy));
+  }
+  a[0] = n0; a[1] = n1; a[2] = n2; a[3] = n3; a[4] = n4; a[5] = n5; a[6] = n6; a[7] = n7;
 }
 
+// alpha recursion + a-posteriori output (max over bit-1 branches minus max over bit-0 branches)
+template <bool FAST>
+__device__ __forceinline__ uint32_t alpha_out_step(uint32_t a[8], const uint32_t bb[8], uint32_t x, uint32_t y,
+                                                   uint32_t xy, Range& rm)
+{
+  uint32_t m[8], n[8], M0, M1, o;
+  if (FAST) {
+    m[0] = a[0];            m[1] = wadd2(a[3], y);  m[2] = wadd2(a[4], y);  m[3] = a[7];
+    m[4] = a[1];            m[5] = wadd2(a[2], y);  m[6] = wadd2(a[5], y);  m[7] = a[6];
+    n[0] = wadd2(a[1], xy); n[1] = wadd2(a[2], x);  n[2] = wadd2(a[5], x);  n[3] = wadd2(a[6], xy);
+    n[4] = wadd2(a[0], xy); n[5] = wadd2(a[3], x);  n[6] = wadd2(a[4], x);  n[7] = wadd2(a[7], xy);
+    M0 = wadd2(bb[0], m[0]);
+    M1 = wadd2(bb[0], n[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+      M0 = addmax2(bb[i], m[i], M0);
+      M1 = addmax2(bb[i], n[i], M1);
+    }
+    rm.add2v(M0, M1);
+    o = wsub2(M1, M0);
+  } else {
+    m[0] = a[0];            m[1] = sadd2(a[3], y);  m[2] = sadd2(a[4], y);  m[3] = a[7];
+    m[4] = a[1];            m[5] = sadd2(a[2], y);  m[6] = sadd2(a[5], y);  m[7] = a[6];
+    n[0] = sadd2(a[1], xy); n[1] = sadd2(a[2], x);  n[2] = sadd2(a[5], x);  n[3] = sadd2(a[6], xy);
+    n[4] = sadd2(a[0], xy); n[5] = sadd2(a[3], x);  n[6] = sadd2(a[4], x);  n[7] = sadd2(a[7], xy);
+    M0 = sadd2(bb[0], m[0]);
+    M1 = sadd2(bb[0], n[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+      M0 = max2(M0, sadd2(bb[i], m[i]));
+      M1 = max2(M1, sadd2(bb[i], n[i]));
+    }
+    o = ssub2(M1, M0);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = max2(m[i], n[i]);
+  return o;
+}
+
+template <bool FAST>
 __device__ __forceinline__ void normalize(uint32_t s[8])
 {
+  if (FAST) {
+    const uint32_t neg = wneg2(s[0]);
 #pragma unroll
-  for (int i = 1; i < 8; i++) s[i] = ssub2(s[i], s[0]);
+    for (int i = 1; i < 8; i++) s[i] = wadd2(s[i], neg);
+  } else {
+#pragma unroll
+    for (int i = 1; i < 8; i++) s[i] = ssub2(s[i], s[0]);
+  }
   s[0] = 0;
 }
 
-// ---- per-warp decode state -----------------------------------------------------------------------
+// ---- per-thread decode context ---------------------------------------------------------------------
 template <int W>
 struct WinCtx {
-  static constexpr int WH = W / 2;
-  // geometry of this code-block size
-  uint32_t K, L, f1, f2, mK, mL;
-  // thread position
-  int t;  // 0..WH-1: owns windows 2t (low half) and 2t+1 (high half)
-  // QPP window offsets of the two windows (mod W)
-  uint32_t base_lo, base_hi, inc_lo, inc_hi;
-  // data
-  const uint32_t* sys;   // [L][WH]
-  const uint32_t* par0;  // [L][WH]
-  const uint32_t* par1;  // [L][WH]
-  const int16_t*  tail;  // 12 tail samples
-  uint32_t*       A32;   // [L][WH]  extrinsic of DEC2 minus E (a-priori of DEC1)
-  uint32_t*       E32;   // [L][WH]  a-posteriori of DEC1 minus A
-  uint32_t*       chk;   // checkpoints: [(c*8 + i)*32], already offset by lane
-  uint4*          sm;    // chunk of beta: [(s*2 + h)*kThreads], already offset by tid
+  uint32_t K, L;
+  int      t;  // 0..W/2-1: owns windows 2t (low half) and 2t+1 (high half)
+  uint32_t base_lo, base_hi, inc_lo, inc_hi;  // QPP window offsets of the two windows (mod W)
+  const uint4*    sys4;   // pair-major: [row/4][W/2] uint4 = 4 rows of this thread's window pair
+  const uint4*    par04;
+  const uint4*    par14;
+  const int16_t*  tail;   // 12 tail samples
+  uint4*          A4;     // pair-major   extrinsic of DEC2 minus E (= a-priori of DEC1)
+  uint4*          E4;     // pair-major   a-posteriori of DEC1 minus A (= systematic of DEC2)
+  uint32_t*       chk;    // checkpoints: [(c*8 + i)*32], already offset by lane
+  uint4*          sm;     // chunk of beta: [(s*2 + h)*kThreads], already offset by tid
+  const uint32_t* qtab;   // per-warp table in shared memory: pi(k) as row | window << 16, k < L
 };
 
+// pair-major layout: int16 index of (row k, window d) and 32-bit word index of (row k, thread t)
 template <int W>
-__device__ __forceinline__ void qpp_at(const WinCtx<W>& c, uint32_t k, uint32_t& row, uint32_t& w_lo, uint32_t& w_hi)
+__device__ __forceinline__ uint32_t pm_index(uint32_t k, uint32_t d)
 {
-  const uint32_t v = (c.f1 + c.f2 * k) * k;  // pi(k) before reduction; k < L <= 384 keeps it below 2^32
-  uint32_t       p = v - __umulhi(v, c.mK) * c.K;
-  if (p >= c.K) p -= c.K;
-  if (p >= c.K) p -= c.K;
-  const uint32_t w0 = __umulhi(p, c.mL);
-  row               = p - w0 * c.L;
-  w_lo              = (w0 + c.base_lo + c.inc_lo * k) & (W - 1);
-  w_hi              = (w0 + c.base_hi + c.inc_hi * k) & (W - 1);
+  return (((k >> 2) * (W / 2) + (d >> 1)) << 3) + ((k & 3) << 1) + (d & 1);
+}
+template <int W>
+__device__ __forceinline__ uint32_t pm_word(uint32_t k, uint32_t t)
+{
+  return (((k >> 2) * (W / 2) + t) << 2) + (k & 3);
 }
 
-// systematic (+ a-priori) and parity of trellis row k for this thread's two windows.
-// aux returns what the output stage has to subtract: the a-priori (DEC1) or x itself (DEC2).
+// where row k of DEC2's trellis reads its systematic input / writes its extrinsic (QPP on the fly)
 template <int W>
-__device__ __forceinline__ void load_xy(const WinCtx<W>& c, bool dec2, bool apriori, uint32_t k, uint32_t& x,
-                                        uint32_t& y, uint32_t& aux)
+__device__ __forceinline__ void qpp_pair(const WinCtx<W>& c, uint32_t k, uint32_t& i_lo, uint32_t& i_hi)
+{
+  const uint32_t q = c.qtab[k], row = q & 0xFFFFu, w0 = q >> 16;
+  i_lo = pm_index<W>(row, (w0 + c.base_lo + c.inc_lo * k) & (W - 1));
+  i_hi = pm_index<W>(row, (w0 + c.base_hi + c.inc_hi * k) & (W - 1));
+}
+
+// the inputs of 4 consecutive trellis rows (one row group) for this thread's window pair
+struct Group {
+  uint32_t x[4], y[4], aux[4];
+};
+
+// the loads of one row group, issued one group ahead of their use (software prefetch)
+struct RawGroup {
+  uint4 a, b, c;  // DEC1: sys, parity, a-priori.  DEC2: b = parity, a / c = gathered low / high halves
+};
+
+template <int W, bool DEC2>
+__device__ __forceinline__ void issue_group(const WinCtx<W>& c, bool apriori, int kg, RawGroup& q)
 {
   constexpr int WH = W / 2;
+  if (!DEC2) {
+    q.a = __ldg(c.sys4 + kg * WH + c.t);
+    q.b = __ldg(c.par04 + kg * WH + c.t);
+    if (apriori) q.c = c.A4[kg * WH + c.t];
+  } else {
+    q.b = __ldg(c.par14 + kg * WH + c.t);
+    const uint16_t* E16 = reinterpret_cast<const uint16_t*>(c.E4);
+    uint32_t        lo[4], hi[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      uint32_t i_lo, i_hi;
+      qpp_pair<W>(c, (uint32_t)(kg * 4 + r), i_lo, i_hi);  // only called for groups that are entirely < L
+      lo[r] = E16[i_lo];
+      hi[r] = E16[i_hi];
+    }
+    q.a = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    q.c = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  }
+}
+
+// FAST rows only: x = sys + a-priori with a wrapping add
+template <bool DEC2>
+__device__ __forceinline__ void finish_group(bool apriori, const RawGroup& q, Group& g)
+{
+  g.y[0] = q.b.x; g.y[1] = q.b.y; g.y[2] = q.b.z; g.y[3] = q.b.w;
+  if (!DEC2) {
+    g.x[0] = q.a.x; g.x[1] = q.a.y; g.x[2] = q.a.z; g.x[3] = q.a.w;
+    if (apriori) {
+      g.aux[0] = q.c.x; g.aux[1] = q.c.y; g.aux[2] = q.c.z; g.aux[3] = q.c.w;
+#pragma unroll
+      for (int r = 0; r < 4; r++) g.x[r] = wadd2(g.aux[r], g.x[r]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; r++) g.aux[r] = 0;
+    }
+  } else {
+    g.x[0] = q.a.x | (q.c.x << 16); g.x[1] = q.a.y | (q.c.y << 16);
+    g.x[2] = q.a.z | (q.c.z << 16); g.x[3] = q.a.w | (q.c.w << 16);
+#pragma unroll
+    for (int r = 0; r < 4; r++) g.aux[r] = g.x[r];
+  }
+}
+
+// one row with the reference's saturating a-priori add (exact rows)
+template <int W>
+__device__ __forceinline__ void load_row_exact(const WinCtx<W>& c, bool dec2, bool apriori, uint32_t k, uint32_t& x,
+                                               uint32_t& y, uint32_t& aux)
+{
+  const uint32_t w = pm_word<W>(k, (uint32_t)c.t);
   if (!dec2) {
-    x   = __ldg(c.sys + k * WH + c.t);
-    y   = __ldg(c.par0 + k * WH + c.t);
+    x   = __ldg(reinterpret_cast<const uint32_t*>(c.sys4) + w);
+    y   = __ldg(reinterpret_cast<const uint32_t*>(c.par04) + w);
     aux = 0;
     if (apriori) {
-      aux = c.A32[k * WH + c.t];
+      aux = reinterpret_cast<const uint32_t*>(c.A4)[w];
       x   = sadd2(aux, x);
     }
   } else {
-    uint32_t row, w_lo, w_hi;
-    qpp_at<W>(c, k, row, w_lo, w_hi);
-    const uint16_t* E16 = reinterpret_cast<const uint16_t*>(c.E32);
-    x   = (uint32_t)E16[row * W + w_lo] | ((uint32_t)E16[row * W + w_hi] << 16);
-    y   = __ldg(c.par1 + k * WH + c.t);
+    uint32_t i_lo, i_hi;
+    qpp_pair<W>(c, k, i_lo, i_hi);
+    const uint16_t* E16 = reinterpret_cast<const uint16_t*>(c.E4);
+    x   = (uint32_t)E16[i_lo] | ((uint32_t)E16[i_hi] << 16);
+    y   = __ldg(reinterpret_cast<const uint32_t*>(c.par14) + w);
     aux = x;
   }
 }
 
-template <int W>
-__device__ __forceinline__ void store_out(const WinCtx<W>& c, bool dec2, uint32_t k, uint32_t o, uint32_t aux)
+// store the differenced output of row k (see file header) and remember its extremes
+template <int W, bool DEC2>
+__device__ __forceinline__ void store_out(const WinCtx<W>& c, uint32_t k, uint32_t o, uint32_t aux, Range& rd)
 {
-  constexpr int  WH = W / 2;
-  const uint32_t d  = wsub2(o, aux);
-  if (!dec2) {
-    c.E32[k * WH + c.t] = d;
+  const uint32_t d = wsub2(o, aux);
+  rd.add1(d);
+  if (!DEC2) {
+    reinterpret_cast<uint32_t*>(c.E4)[pm_word<W>(k, (uint32_t)c.t)] = d;
   } else {
-    uint32_t row, w_lo, w_hi;
-    qpp_at<W>(c, k, row, w_lo, w_hi);
-    uint16_t* A16       = reinterpret_cast<uint16_t*>(c.A32);
-    A16[row * W + w_lo] = (uint16_t)(d & 0xFFFFu);
-    A16[row * W + w_hi] = (uint16_t)(d >> 16);
+    uint32_t i_lo, i_hi;
+    qpp_pair<W>(c, k, i_lo, i_hi);
+    uint16_t* A16 = reinterpret_cast<uint16_t*>(c.A4);
+    A16[i_lo]     = (uint16_t)(d & 0xFFFFu);
+    A16[i_hi]     = (uint16_t)(d >> 16);
   }
 }
 
@@ -171,131 +357,459 @@ __device__ __forceinline__ void tail_beta(const int16_t* tl, int16_t b[8])
   }
 }
 
-// One constituent MAP decoder run (one srsLTE "iteration") for this thread's two windows.
-template <int W>
-__device__ void half_iteration(const WinCtx<W>& c, bool dec2, bool apriori)
-{
-  constexpr int  WH = W / 2;
-  const uint32_t L  = c.L;
-  const int      nchunks = (int)((L + kChunk - 1) / kChunk);
-  uint32_t       s[8], x, y, aux;
+// state of one half iteration that the out-of-line exact helpers update (kept in local memory only
+// around the helper calls; the fast loops work on register copies)
+struct RowState {
+  uint32_t s[8];       // beta or alpha metrics
+  Range    trk;        // post-normalisation extremes
+  Range    rd;         // extremes of the stored outputs
+};
 
-  // ---------------- backward pass: boundary metrics, then checkpoints ----------------
+// ---- exact rows (reference arithmetic), one row at a time, shared by the exact variant and by the
+// ---- rows of the fast variant that sit next to a known-state boundary -------------------------------
+// beta recursion over rows k_hi .. k_lo (descending).  mode 0: warm-up (nothing stored), 1: main pass
+// (checkpoint when k % kChunk == 0), 2: rebuild (B[k] -> shared memory slot k - sm_lo - 1).
+template <int W>
+__device__ __noinline__ void beta_rows_exact(const WinCtx<W> c, uint32_t flags, int k_hi, int k_lo, int mode, int sm_lo,
+                                             RowState* st)
+{
+  const bool dec2 = flags & 1, apriori = (flags & 2) != 0;
+  uint32_t   s[8];
 #pragma unroll
-  for (int i = 0; i < 8; i++) s[i] = kNegInf2;
-  for (int k = kWarm - 1; k >= 0; k--) {
-    load_xy<W>(c, dec2, apriori, (uint32_t)k, x, y, aux);
-    beta_step(s, x, y, sadd2(x, y));
-    if ((k & 1) == 0 && k != 0) normalize(s);
-  }
-  {
-    // window d starts from what window d+1 estimated; the last window from the tail
-    int16_t tb[8];
-    tail_beta(c.tail + (dec2 ? 6 : 0), tb);
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const uint32_t nxt = __shfl_down_sync(0xFFFFFFFFu, s[i], 1, WH);
-      uint32_t       v   = __byte_perm(s[i], nxt, 0x5432);
-      if (c.t == WH - 1) v = (v & 0xFFFFu) | ((uint32_t)(uint16_t)tb[i] << 16);
-      s[i] = v;
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; i++) c.chk[((nchunks - 1) * 8 + i) * 32] = s[i];
-  for (int k = (int)L - 1; k >= 0; k--) {
-    load_xy<W>(c, dec2, apriori, (uint32_t)k, x, y, aux);
-    beta_step(s, x, y, sadd2(x, y));
-    if ((k % kChunk) == 0 && k != 0) {
+  for (int i = 0; i < 8; i++) s[i] = st->s[i];
+  Range trk = st->trk;
+#pragma unroll 1
+  for (int k = k_hi; k >= k_lo; k--) {
+    uint32_t x, y, aux;
+    load_row_exact<W>(c, dec2, apriori, (uint32_t)k, x, y, aux);
+    beta_step<false>(s, x, y, sadd2(x, y));
+    if (mode == 1 && (k % kChunk) == 0 && k != 0) {
 #pragma unroll
       for (int i = 0; i < 8; i++) c.chk[((k / kChunk - 1) * 8 + i) * 32] = s[i];
     }
-    if ((k & 1) == 0 && k != 0) normalize(s);
+    if (mode == 2) {
+      c.sm[((k - sm_lo - 1) * 2 + 0) * kThreads] = make_uint4(s[0], s[1], s[2], s[3]);
+      c.sm[((k - sm_lo - 1) * 2 + 1) * kThreads] = make_uint4(s[4], s[5], s[6], s[7]);
+    }
+    if ((k & 1) == 0 && k != 0) {
+      normalize<false>(s);
+      trk.add8(s);
+    }
   }
+#pragma unroll
+  for (int i = 0; i < 8; i++) st->s[i] = s[i];
+  st->trk = trk;
+}
 
-  // ---------------- forward pass ----------------
-  uint32_t a[8];
+// alpha recursion over rows k_lo .. k_hi (ascending).  mode 0: warm-up (normalisation counter starts at
+// k_norm0 for row k_lo, no output), 1: with a-posteriori output from the beta chunk whose base row is sm_lo.
+template <int W>
+__device__ __noinline__ void alpha_rows_exact(const WinCtx<W> c, uint32_t flags, int k_lo, int k_hi, int mode, int sm_lo,
+                                              int k_norm0, RowState* st)
+{
+  const bool dec2 = flags & 1, apriori = (flags & 2) != 0;
+  uint32_t   a[8];
 #pragma unroll
-  for (int i = 0; i < 8; i++) a[i] = kNegInf2;
-  for (int k = 0; k < kWarm; k++) {
-    uint32_t m[8], n[8];
-    load_xy<W>(c, dec2, apriori, L - kWarm + (uint32_t)k, x, y, aux);
-    alpha_branches(a, x, y, sadd2(x, y), m, n);
-#pragma unroll
-    for (int i = 0; i < 8; i++) a[i] = max2(m[i], n[i]);
-    if ((k & 1) == 0 && k != 0) normalize(a);
+  for (int i = 0; i < 8; i++) a[i] = st->s[i];
+  Range trk = st->trk, rd = st->rd, unused;
+  unused.reset();
+#pragma unroll 1
+  for (int k = k_lo; k <= k_hi; k++) {
+    uint32_t x, y, aux;
+    load_row_exact<W>(c, dec2, apriori, (uint32_t)k, x, y, aux);
+    const int j = mode == 0 ? k_norm0 + (k - k_lo) : k;
+    if (mode == 0) {
+      alpha_step<false>(a, x, y, sadd2(x, y));
+    } else {
+      const uint4    b0 = c.sm[((k - sm_lo) * 2 + 0) * kThreads];
+      const uint4    b1 = c.sm[((k - sm_lo) * 2 + 1) * kThreads];
+      const uint32_t bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint32_t       o = alpha_out_step<false>(a, bb, x, y, sadd2(x, y), unused);
+      if (W == 8) o = sra1_2(o);  // the 8-window (sse16) decoder halves its output
+      if (dec2)
+        store_out<W, true>(c, (uint32_t)k, o, aux, rd);
+      else
+        store_out<W, false>(c, (uint32_t)k, o, aux, rd);
+    }
+    if ((j & 1) == 0 && j != 0) {
+      normalize<false>(a);
+      trk.add8(a);
+    }
   }
+#pragma unroll
+  for (int i = 0; i < 8; i++) st->s[i] = a[i];
+  st->trk = trk;
+  st->rd  = rd;
+}
+
+// what one half iteration reports back
+struct HalfResult {
+  bool     proven;  // fast variant only: no saturating op of the reference can have clamped
+  uint32_t dmax;    // max |stored differenced output| over this thread's rows and lanes
+};
+
+template <int WH>
+__device__ __forceinline__ void exchange_beta_boundary(uint32_t s[8], int t, const int16_t* tail)
+{
+  // window d starts from what window d+1 estimated; the last window from the terminated tail
+  int16_t tb[8];
+  tail_beta(tail, tb);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t nxt = __shfl_down_sync(0xFFFFFFFFu, s[i], 1, WH);
+    uint32_t       v   = __byte_perm(s[i], nxt, 0x5432);
+    if (t == WH - 1) v = (v & 0xFFFFu) | ((uint32_t)(uint16_t)tb[i] << 16);
+    s[i] = v;
+  }
+}
+
+template <int WH>
+__device__ __forceinline__ void exchange_alpha_boundary(uint32_t a[8], int t)
+{
+  // window d starts from what window d-1 estimated; window 0 from the known all-zero state
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     const uint32_t prv = __shfl_up_sync(0xFFFFFFFFu, a[i], 1, WH);
     uint32_t       v   = __byte_perm(a[i], prv, 0x1076);
-    if (c.t == 0) v = (v & 0xFFFF0000u) | (i == 0 ? 0u : (uint32_t)(uint16_t)kNegInf);
+    if (t == 0) v = (v & 0xFFFF0000u) | (i == 0 ? 0u : (uint32_t)(uint16_t)kNegInf);
     a[i] = v;
   }
+}
 
+__device__ __forceinline__ uint32_t range_absmax(const Range& r)
+{
+  const int d0 = max(abs(lo16(r.hi)), abs(lo16(r.lo))), d1 = max(abs(hi16(r.hi)), abs(hi16(r.lo)));
+  return (uint32_t)max(d0, d1);
+}
+
+// ---- EXACT variant of one half iteration: the reference's saturating arithmetic on every row -------
+template <int W>
+__device__ __noinline__ HalfResult half_iteration_exact(const WinCtx<W> c, bool dec2, bool apriori)
+{
+  constexpr int  WH = W / 2;
+  const int      L  = (int)c.L;
+  const int      nchunks = (L + kChunk - 1) / kChunk;
+  const uint32_t flags = (dec2 ? 1u : 0u) | (apriori ? 2u : 0u);
+  RowState       st;
+  st.trk.reset();
+  st.rd.reset();
+#pragma unroll
+  for (int i = 0; i < 8; i++) st.s[i] = kNegInf2;
+  beta_rows_exact<W>(c, flags, kWarm - 1, 0, 0, 0, &st);
+  exchange_beta_boundary<WH>(st.s, c.t, c.tail + (dec2 ? 6 : 0));
+#pragma unroll
+  for (int i = 0; i < 8; i++) c.chk[((nchunks - 1) * 8 + i) * 32] = st.s[i];
+  beta_rows_exact<W>(c, flags, L - 1, 0, 1, 0, &st);
+
+  RowState al;
+  al.trk.reset();
+  al.rd.reset();
+#pragma unroll
+  for (int i = 0; i < 8; i++) al.s[i] = kNegInf2;
+  alpha_rows_exact<W>(c, flags, L - kWarm, L - 1, 0, 0, 0, &al);
+  exchange_alpha_boundary<WH>(al.s, c.t);
+  for (int ch = 0; ch < nchunks; ch++) {
+    const int lo = ch * kChunk, hi = min(lo + kChunk, L);
+#pragma unroll
+    for (int i = 0; i < 8; i++) st.s[i] = c.chk[(ch * 8 + i) * 32];
+    c.sm[((hi - lo - 1) * 2 + 0) * kThreads] = make_uint4(st.s[0], st.s[1], st.s[2], st.s[3]);
+    c.sm[((hi - lo - 1) * 2 + 1) * kThreads] = make_uint4(st.s[4], st.s[5], st.s[6], st.s[7]);
+    if (hi != L) normalize<false>(st.s);  // hi is even and non-zero: the backward pass normalised after storing
+    beta_rows_exact<W>(c, flags, hi - 1, lo + 1, 2, lo, &st);
+    alpha_rows_exact<W>(c, flags, lo, hi - 1, 1, lo, 0, &al);
+  }
+  __syncwarp();
+  HalfResult res;
+  res.proven = true;
+  res.dmax   = range_absmax(al.rd);
+  return res;
+}
+
+// ---- FAST variant: wrapping adds fused with max, plus the bookkeeping that proves it equals the exact one
+// G bounds |x|, |y| and |x + y| of every row of this code block in this half iteration.
+template <int W, bool DEC2>
+__device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bool apriori, int G)
+{
+  constexpr int  WH = W / 2;
+  const int      L  = (int)c.L;
+  const int      nchunks = (L + kChunk - 1) / kChunk;
+  const uint32_t flags = (DEC2 ? 1u : 0u) | (apriori ? 2u : 0u);
+  // rows [4, kf] are covered by full row groups of fast arithmetic; rows above kf (next to the terminated
+  // tail) and rows 0..3 of the forward pass (next to the known start state) always use exact arithmetic
+  const int gtop = (L - kExactRows) / 4 - 1;  // last fully fast group
+  const int kf   = gtop * 4 + 3;              // last fast row (kf <= L - kExactRows - 1)
+  uint32_t  s[8];
+  Group     g;
+  RawGroup  q;
+  Range     rb, ra, rm, rd;
+  rb.reset(); ra.reset(); rd.reset();
+  rm.hi = kMin2; rm.lo = kMax2;
+  RowState st;
+
+  // ---------------- backward pass: boundary metrics from the next window's first 40 rows ----------------
+#pragma unroll
+  for (int i = 0; i < 8; i++) s[i] = kNegInf2;
+  issue_group<W, DEC2>(c, apriori, kWarm / 4 - 1, q);
+#pragma unroll 1
+  for (int kg = kWarm / 4 - 1; kg >= 0; kg--) {
+    finish_group<DEC2>(apriori, q, g);
+    issue_group<W, DEC2>(c, apriori, kg > 0 ? kg - 1 : gtop, q);  // last: top fast group of the main pass
+#pragma unroll
+    for (int r = 3; r >= 0; r--) {
+      beta_step<true>(s, g.x[r], g.y[r], wadd2(g.x[r], g.y[r]));
+      if ((r & 1) == 0 && (kg | r) != 0) {
+        normalize<true>(s);
+        rb.add8(s);
+      }
+    }
+  }
+  exchange_beta_boundary<WH>(s, c.t, c.tail + (DEC2 ? 6 : 0));
+#pragma unroll
+  for (int i = 0; i < 8; i++) c.chk[((nchunks - 1) * 8 + i) * 32] = s[i];
+
+  // ---------------- backward pass over the window: checkpoints every kChunk rows ----------------
+#pragma unroll
+  for (int i = 0; i < 8; i++) st.s[i] = s[i];
+  st.trk = rb;
+  beta_rows_exact<W>(c, flags, L - 1, kf + 1, 1, 0, &st);
+#pragma unroll
+  for (int i = 0; i < 8; i++) s[i] = st.s[i];
+  rb = st.trk;
+#pragma unroll 1
+  for (int kg = gtop; kg >= 0; kg--) {
+    finish_group<DEC2>(apriori, q, g);
+    if (kg > 0) issue_group<W, DEC2>(c, apriori, kg - 1, q);
+#pragma unroll
+    for (int r = 3; r >= 0; r--) {
+      beta_step<true>(s, g.x[r], g.y[r], wadd2(g.x[r], g.y[r]));
+      if (r == 0 && (kg & (kChunk / 4 - 1)) == 0 && kg != 0) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) c.chk[((kg / (kChunk / 4) - 1) * 8 + i) * 32] = s[i];
+      }
+      if ((r & 1) == 0 && (kg | r) != 0) {
+        normalize<true>(s);
+        rb.add8(s);
+      }
+    }
+  }
+
+  // ---------------- forward pass: boundary metrics from the previous window's last 40 rows ----------------
+  uint32_t a[8];
+  {
+    const int a0 = L - kWarm;                 // first warm-up row
+    const int ga = (a0 + 3) >> 2;             // first full group
+    const int gb = (L >> 2) - 1;              // last full group
+    issue_group<W, DEC2>(c, apriori, ga, q);
+#pragma unroll
+    for (int i = 0; i < 8; i++) st.s[i] = kNegInf2;
+    st.trk = ra;
+    if (ga * 4 > a0) alpha_rows_exact<W>(c, flags, a0, ga * 4 - 1, 0, 0, 0, &st);
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = st.s[i];
+    ra = st.trk;
+#pragma unroll 1
+    for (int kg = ga; kg <= gb; kg++) {
+      finish_group<DEC2>(apriori, q, g);
+      if (kg < gb) issue_group<W, DEC2>(c, apriori, kg + 1, q);
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int j = kg * 4 + r - a0;  // the reference normalises on the warm-up counter
+        alpha_step<true>(a, g.x[r], g.y[r], wadd2(g.x[r], g.y[r]));
+        if ((j & 1) == 0 && j != 0) {
+          normalize<true>(a);
+          ra.add8(a);
+        }
+      }
+    }
+    if ((gb + 1) * 4 < L) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) st.s[i] = a[i];
+      st.trk = ra;
+      alpha_rows_exact<W>(c, flags, (gb + 1) * 4, L - 1, 0, 0, (gb + 1) * 4 - a0, &st);
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] = st.s[i];
+      ra = st.trk;
+    }
+  }
+  exchange_alpha_boundary<WH>(a, c.t);
+
+  // ---------------- forward pass over the window, chunk by chunk ----------------
+  issue_group<W, DEC2>(c, apriori, min((kChunk - 1) >> 2, gtop), q);  // top fast group of chunk 0
+#pragma unroll 1
   for (int ch = 0; ch < nchunks; ch++) {
     const int lo = ch * kChunk;
-    const int hi = min(lo + kChunk, (int)L);
+    const int hi = min(lo + kChunk, L);
+    const int g_lo = lo >> 2, g_hi = min((hi - 1) >> 2, gtop);  // fast groups of this chunk (may be empty)
     // rebuild B[lo+1 .. hi] into shared memory, slot (k - lo - 1) holds B[k]
 #pragma unroll
     for (int i = 0; i < 8; i++) s[i] = c.chk[(ch * 8 + i) * 32];
     c.sm[((hi - lo - 1) * 2 + 0) * kThreads] = make_uint4(s[0], s[1], s[2], s[3]);
     c.sm[((hi - lo - 1) * 2 + 1) * kThreads] = make_uint4(s[4], s[5], s[6], s[7]);
-    if (hi != (int)L) normalize(s);  // hi is even and non-zero: the backward pass normalised after storing
-    for (int k = hi - 1; k > lo; k--) {
-      load_xy<W>(c, dec2, apriori, (uint32_t)k, x, y, aux);
-      beta_step(s, x, y, sadd2(x, y));
-      c.sm[((k - lo - 1) * 2 + 0) * kThreads] = make_uint4(s[0], s[1], s[2], s[3]);
-      c.sm[((k - lo - 1) * 2 + 1) * kThreads] = make_uint4(s[4], s[5], s[6], s[7]);
-      if ((k & 1) == 0) normalize(s);
+    if (hi != L) {  // hi is even and non-zero: the backward pass normalised after storing
+      if (hi <= kf)
+        normalize<true>(s);
+      else
+        normalize<false>(s);
+    }
+    if (hi - 1 > kf) {  // rows next to the tail: exact
+#pragma unroll
+      for (int i = 0; i < 8; i++) st.s[i] = s[i];
+      st.trk.reset();
+      beta_rows_exact<W>(c, flags, hi - 1, max(kf, lo) + 1, 2, lo, &st);
+#pragma unroll
+      for (int i = 0; i < 8; i++) s[i] = st.s[i];
+    }
+#pragma unroll 1
+    for (int kg = g_hi; kg >= g_lo; kg--) {
+      finish_group<DEC2>(apriori, q, g);
+      // next: the group below, or (when done) the first fast group of the alpha rows of this chunk
+      issue_group<W, DEC2>(c, apriori, kg > g_lo ? kg - 1 : max(g_lo, 1), q);
+#pragma unroll
+      for (int r = 3; r >= 0; r--) {
+        const int k = kg * 4 + r;
+        if (r == 0 && kg == g_lo) continue;  // B[lo] belongs to the chunk below
+        beta_step<true>(s, g.x[r], g.y[r], wadd2(g.x[r], g.y[r]));
+        c.sm[((k - lo - 1) * 2 + 0) * kThreads] = make_uint4(s[0], s[1], s[2], s[3]);
+        c.sm[((k - lo - 1) * 2 + 1) * kThreads] = make_uint4(s[4], s[5], s[6], s[7]);
+        if ((r & 1) == 0) normalize<true>(s);
+      }
     }
     // alpha recursion + a-posteriori output over the chunk
-    for (int k = lo; k < hi; k++) {
-      uint32_t m[8], n[8];
-      load_xy<W>(c, dec2, apriori, (uint32_t)k, x, y, aux);
-      alpha_branches(a, x, y, sadd2(x, y), m, n);
-      const uint4 b0 = c.sm[((k - lo) * 2 + 0) * kThreads];
-      const uint4 b1 = c.sm[((k - lo) * 2 + 1) * kThreads];
-      const uint32_t bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      uint32_t       M0 = sadd2(bb[0], m[0]), M1 = sadd2(bb[0], n[0]);
+    int ga = g_lo;
+    if (ch == 0) {  // rows 0..3 next to the known start state: exact
 #pragma unroll
-      for (int i = 1; i < 8; i++) {
-        M0 = max2(M0, sadd2(bb[i], m[i]));
-        M1 = max2(M1, sadd2(bb[i], n[i]));
+      for (int i = 0; i < 8; i++) st.s[i] = a[i];
+      st.trk = ra;
+      st.rd  = rd;
+      alpha_rows_exact<W>(c, flags, 0, min(kExactRows, hi) - 1, 1, lo, 0, &st);
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] = st.s[i];
+      ra = st.trk;
+      rd = st.rd;
+      ga = 1;
+    }
+#pragma unroll 1
+    for (int kg = ga; kg <= g_hi; kg++) {
+      finish_group<DEC2>(apriori, q, g);
+      if (kg < g_hi)
+        issue_group<W, DEC2>(c, apriori, kg + 1, q);
+      else if (ch + 1 < nchunks)
+        issue_group<W, DEC2>(c, apriori, min((min(hi + kChunk, L) - 1) >> 2, gtop), q);  // top fast group of the next chunk
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int      k  = kg * 4 + r;
+        const uint4    b0 = c.sm[((k - lo) * 2 + 0) * kThreads];
+        const uint4    b1 = c.sm[((k - lo) * 2 + 1) * kThreads];
+        const uint32_t bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        uint32_t       o = alpha_out_step<true>(a, bb, g.x[r], g.y[r], wadd2(g.x[r], g.y[r]), rm);
+        if (W == 8) o = sra1_2(o);  // the 8-window (sse16) decoder halves its output
+        store_out<W, DEC2>(c, (uint32_t)k, o, g.aux[r], rd);
+        if ((r & 1) == 0) {
+          normalize<true>(a);
+          ra.add8(a);
+        }
       }
-      uint32_t o = ssub2(M1, M0);
-      if (W == 8) o = sra1_2(o);  // the 8-window (sse16) decoder halves its output
-      store_out<W>(c, dec2, (uint32_t)k, o, aux);
+    }
+    if (hi - 1 > kf) {  // rows next to the tail: exact
 #pragma unroll
-      for (int i = 0; i < 8; i++) a[i] = max2(m[i], n[i]);
-      if ((k & 1) == 0 && k != 0) normalize(a);
+      for (int i = 0; i < 8; i++) st.s[i] = a[i];
+      st.trk = ra;
+      st.rd  = rd;
+      alpha_rows_exact<W>(c, flags, max(max(kf, lo - 1) + 1, ch == 0 ? kExactRows : 0), hi - 1, 1, lo, 0, &st);
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] = st.s[i];
+      ra = st.trk;
+      rd = st.rd;
     }
   }
   __syncwarp();
+
+  HalfResult res;
+  res.dmax = range_absmax(rd);
+  // Proof obligations, per int16 lane (see DESIGN.md "fast path"): every fast row is at most 2 steps
+  // away from a normalisation point whose post-normalisation metrics lie in [lo, hi]; one step moves a
+  // metric by at most G.
+  bool ok = true;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int bh = h ? hi16(rb.hi) : lo16(rb.hi), bl = h ? hi16(rb.lo) : lo16(rb.lo);
+    const int ah = h ? hi16(ra.hi) : lo16(ra.hi), al = h ? hi16(ra.lo) : lo16(ra.lo);
+    const int mh = h ? hi16(rm.hi) : lo16(rm.hi), ml = h ? hi16(rm.lo) : lo16(rm.lo);
+    ok = ok && (bh + 2 * G <= 32767) && (bl - 2 * G >= -32768) && (bh - bl + 4 * G <= 32767);
+    ok = ok && (ah + 2 * G <= 32767) && (al - 2 * G >= -32768) && (ah - al + 4 * G <= 32767);
+    ok = ok && (bh + ah + 5 * G <= 32767) && (bl + al - 5 * G >= -32768);
+    ok = ok && (mh < ml || mh - ml <= 32767);
+  }
+  // warm-up starts from 8 equal metrics of -10000 and runs at most 3 steps before normalising
+  ok         = ok && (G <= kMaxFastG);
+  res.proven = ok;
+  return res;
 }
 
 // hard decision of this code block: bit n = (A[n] + E[n] > 0), MSB first.
+// Phase 1: every thread turns its two windows into bit strings (32 rows per word) in shared memory;
+// phase 2: bytes are cut out of the concatenated window strings.  `bits` is per-warp scratch (the beta
+// chunk area, free between half iterations): [group][window][word].
 template <int W>
-__device__ void decide(const WinCtx<W>& c, uint8_t* out)
+__device__ void decide(const WinCtx<W>& c, uint8_t* out, bool write)
 {
-  constexpr int   WH  = W / 2;
-  const uint16_t* A16 = reinterpret_cast<const uint16_t*>(c.A32);
-  const uint16_t* E16 = reinterpret_cast<const uint16_t*>(c.E32);
-  for (uint32_t j = (uint32_t)c.t; j < c.K / 8; j += WH) {
-    uint32_t n = 8 * j;
-    uint32_t d = __umulhi(n, c.mL);
-    uint32_t k = n - d * c.L;
-    uint32_t byte = 0;
+  constexpr int  WH = W / 2;
+  constexpr int  NW = (kMaxL + 31) / 32;  // words per window
+  const uint32_t L  = c.L;
+  // bit-string word f (= window * NW + word) of this code block lives in the .x component of beta-chunk
+  // slot f / WH of the group's thread f % WH: only this group's own shared-memory slots are touched
+  uint32_t* grp_base = reinterpret_cast<uint32_t*>(c.sm - c.t);
+  auto      word     = [&](uint32_t f) -> uint32_t& { return grp_base[((f / WH) * kThreads + (f % WH)) * 4]; };
+  uint32_t  acc_lo = 0, acc_hi = 0;
+  for (uint32_t kg = 0; kg * 4 < L; kg++) {
+    const uint4    av = c.A4[kg * WH + c.t], ev = c.E4[kg * WH + c.t];
+    const uint32_t v[4] = {wadd2(av.x, ev.x), wadd2(av.y, ev.y), wadd2(av.z, ev.z), wadd2(av.w, ev.w)};
 #pragma unroll
-    for (int b = 0; b < 8; b++) {
-      const int16_t v = (int16_t)(uint16_t)(A16[k * W + d] + E16[k * W + d]);
-      byte            = (byte << 1) | (v > 0 ? 1u : 0u);
-      if (++k == c.L) {
-        k = 0;
-        d++;
+    for (int r = 0; r < 4; r++) {
+      const uint32_t k = kg * 4 + r;
+      if (k < L) {
+        // sign bit of -(max(v, -1)) is set exactly when v > 0 (no overflow: max(v,-1) >= -1)
+        const uint32_t m = wneg2(max2(v[r], 0xFFFFFFFFu));
+        acc_lo = (acc_lo << 1) | ((m >> 15) & 1u);
+        acc_hi = (acc_hi << 1) | (m >> 31);
+        if ((k & 31) == 31 || k == L - 1) {
+          const uint32_t sh = 31 - (k & 31);  // left-align a partial last word
+          word((2 * c.t) * NW + (k >> 5))     = acc_lo << sh;
+          word((2 * c.t + 1) * NW + (k >> 5)) = acc_hi << sh;
+          acc_lo = 0;
+          acc_hi = 0;
+        }
       }
     }
-    out[j] = (uint8_t)byte;
   }
+  __syncwarp();
+  if (write) {
+    const uint32_t mL = (uint32_t)((0x100000000ull + L - 1) / L);
+    for (uint32_t j = (uint32_t)c.t; j < c.K / 8; j += WH) {
+      const uint32_t n = 8 * j;
+      uint32_t       d = __umulhi(n, mL);
+      uint32_t       off = n - d * L;
+      uint32_t       byte;
+      if (off + 8 <= L) {
+        const uint32_t f  = d * NW + (off >> 5);
+        const uint32_t bo = off & 31;
+        const uint32_t w0 = word(f), w1 = (bo > 24) ? word(f + 1) : 0u;  // only when the byte straddles two words
+        byte = (__funnelshift_l(w1, w0, bo) >> 24) & 0xFFu;
+      } else {  // the byte straddles two windows (L not a multiple of 8)
+        byte = 0;
+        for (int b = 0; b < 8; b++) {
+          if (off == L) {
+            off = 0;
+            d++;
+          }
+          byte = (byte << 1) | ((word(d * NW + (off >> 5)) >> (31 - (off & 31))) & 1u);
+          off++;
+        }
+      }
+      out[j] = (uint8_t)byte;
+    }
+  }
+  __syncwarp();
 }
 
 __device__ __forceinline__ uint32_t crc24_bytes_dev(int which, const uint8_t* p, uint32_t nbytes)
@@ -305,6 +819,15 @@ __device__ __forceinline__ uint32_t crc24_bytes_dev(int which, const uint8_t* p,
   return crc;
 }
 
+// max over the W/2 threads of a code block
+template <int WH>
+__device__ __forceinline__ uint32_t group_max(uint32_t v)
+{
+#pragma unroll
+  for (int o = WH / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+  return v;
+}
+
 template <int W>
 __global__ void __launch_bounds__(kThreads, 3) tdec_win_kernel(const TdecLaunch a)
 {
@@ -312,10 +835,13 @@ __global__ void __launch_bounds__(kThreads, 3) tdec_win_kernel(const TdecLaunch 
   constexpr int CBW = 32 / WH;
   constexpr uint32_t KMAX = (W == 16) ? 6144u : 800u;
   extern __shared__ uint4 smem[];
+  uint32_t* qtab_all = reinterpret_cast<uint32_t*>(smem + kChunk * 2 * kThreads);
 
   const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int      grp = lane / WH, t = lane % WH;
   const uint32_t slot = blockIdx.x * (kThreads / 32) + warp;
+  uint32_t*      qtab = qtab_all + warp * kMaxL;
+  uint32_t       fallbacks = 0;
 
   for (;;) {
     uint32_t it = 0;
@@ -327,44 +853,77 @@ __global__ void __launch_bounds__(kThreads, 3) tdec_win_kernel(const TdecLaunch 
     const uint32_t cb     = a.order[wi.first + (active ? grp : 0)];
 
     WinCtx<W> c;
-    c.K  = wi.K;
-    c.L  = c.K / W;
-    c.f1 = wi.f1;
-    c.f2 = wi.f2;
-    c.mK = (uint32_t)(0x100000000ull / c.K);
-    c.mL = (uint32_t)((0x100000000ull + c.L - 1) / c.L);
-    c.t  = t;
+    c.K = wi.K;
+    c.L = c.K / W;
+    c.t = t;
+    const uint32_t f1 = wi.f1, f2 = wi.f2;
     {
       const uint32_t d0 = 2 * (uint32_t)t, d1 = d0 + 1;
-      c.base_lo = (d0 * (c.f1 + c.f2 * d0 * c.L)) & (W - 1);
-      c.base_hi = (d1 * (c.f1 + c.f2 * d1 * c.L)) & (W - 1);
-      c.inc_lo  = (2 * c.f2 * d0) & (W - 1);
-      c.inc_hi  = (2 * c.f2 * d1) & (W - 1);
+      c.base_lo = (d0 * (f1 + f2 * d0 * c.L)) & (W - 1);
+      c.base_hi = (d1 * (f1 + f2 * d1 * c.L)) & (W - 1);
+      c.inc_lo  = (2 * f2 * d0) & (W - 1);
+      c.inc_hi  = (2 * f2 * d1) & (W - 1);
     }
+    // pi(k) for k < L, computed here from (f1, f2): row = pi(k) mod L, window = pi(k) / L
+    {
+      const uint32_t mK = (uint32_t)(0x100000000ull / c.K);
+      const uint32_t mL = (uint32_t)((0x100000000ull + c.L - 1) / c.L);
+      __syncwarp();
+      for (uint32_t k = (uint32_t)lane; k < c.L; k += 32) {
+        const uint32_t v = (f1 + f2 * k) * k;  // k < L <= 384 keeps it below 2^32
+        uint32_t       p = v - __umulhi(v, mK) * c.K;
+        if (p >= c.K) p -= c.K;
+        if (p >= c.K) p -= c.K;
+        const uint32_t w0 = __umulhi(p, mL);
+        qtab[k]           = (p - w0 * c.L) | (w0 << 16);
+      }
+      __syncwarp();
+    }
+    c.qtab = qtab;
+    const uint32_t Lp = (c.L + 3) & ~3u;
+    const uint32_t S  = Lp * W;  // int16 per stream
     const int16_t* in = a.in + (size_t)cb * a.in_stride;
-    c.sys  = reinterpret_cast<const uint32_t*>(in);
-    c.par0 = reinterpret_cast<const uint32_t*>(in + (c.K + 32));
-    c.par1 = reinterpret_cast<const uint32_t*>(in + 2 * (c.K + 32));
-    c.tail = in + 3 * (c.K + 32);
+    c.sys4  = reinterpret_cast<const uint4*>(in);
+    c.par04 = reinterpret_cast<const uint4*>(in + S);
+    c.par14 = reinterpret_cast<const uint4*>(in + 2 * S);
+    c.tail  = in + 3 * S;
+    const uint16_t* meta = reinterpret_cast<const uint16_t*>(in + 3 * S + 16);
+    const int smax = meta[0], p0max = meta[1], p1max = meta[2];
     int16_t* ae = a.ws_ae + ((size_t)slot * CBW + grp) * 2 * KMAX;
-    c.A32 = reinterpret_cast<uint32_t*>(ae);
-    c.E32 = reinterpret_cast<uint32_t*>(ae + KMAX);
+    c.A4  = reinterpret_cast<uint4*>(ae);
+    c.E4  = reinterpret_cast<uint4*>(ae + KMAX);
     c.chk = a.ws_chk + (size_t)slot * kMaxChunks * 8 * 32 + lane;
     c.sm  = smem + tid;
 
-    for (uint32_t k = 0; k < c.L; k++) c.A32[k * WH + t] = 0;
+    for (uint32_t kg = 0; kg < Lp / 4; kg++) c.A4[kg * WH + t] = make_uint4(0, 0, 0, 0);
     __syncwarp();
 
     uint8_t* out  = a.out + (size_t)cb * a.out_stride;
     uint32_t n    = 0, iters = 0;
     bool     done = false, ok = false;
+    int      amax = 0, emax = 0;  // max |A|, max |E| over the code block
     const int which = a.crc_mode == CRC_24A ? 0 : 1;
     do {
-      half_iteration<W>(c, (n & 1) != 0, n > 0);
+      const bool dec2 = (n & 1) != 0, apriori = n > 0;
+      // bound on |x|, |y|, |x + y| of this half iteration
+      const int Gx = dec2 ? emax : (apriori ? smax + amax : smax);
+      const int G  = Gx + (dec2 ? p1max : p0max);
+      HalfResult r;
+      bool       fast_ok = false;
+      // the decision must be warp-uniform: the passes below use full-warp shuffles and votes
+      if (__all_sync(0xFFFFFFFFu, a.force_exact == 0 && G <= kMaxFastG)) {
+        r       = dec2 ? half_iteration_fast<W, true>(c, apriori, G) : half_iteration_fast<W, false>(c, apriori, G);
+        fast_ok = __all_sync(0xFFFFFFFFu, r.proven);
+      }
+      if (!fast_ok) {
+        r = half_iteration_exact<W>(c, dec2, apriori);
+        fallbacks++;
+      }
+      const int dm = (int)group_max<WH>(r.dmax);
+      if (dec2) amax = dm; else emax = dm;
       n++;
       if (a.crc_mode != CRC_NONE) {
-        if (!done && active) decide<W>(c, out);
-        __syncwarp();
+        decide<W>(c, out, !done && active);
         uint32_t crc = 1;
         if (!done && active && t == 0) crc = crc24_bytes_dev(which, out, c.K / 8);
         crc = __shfl_sync(0xFFFFFFFFu, crc, grp * WH);
@@ -378,7 +937,7 @@ __global__ void __launch_bounds__(kThreads, 3) tdec_win_kernel(const TdecLaunch 
       }
     } while (n < a.max_iter && !__all_sync(0xFFFFFFFFu, done || !active));
     if (a.crc_mode == CRC_NONE) {
-      if (active) decide<W>(c, out);
+      decide<W>(c, out, active);
       iters = n;
     }
     if (active && t == 0) {
@@ -387,6 +946,7 @@ __global__ void __launch_bounds__(kThreads, 3) tdec_win_kernel(const TdecLaunch 
     }
     __syncwarp();
   }
+  if (lane == 0 && fallbacks && a.stats) atomicAdd(a.stats, fallbacks);
 }
 
 // ---- generic decoder (K <= 400): one thread per code block, natural order, wrapping arithmetic ----
@@ -546,27 +1106,79 @@ __global__ void __launch_bounds__(kThreads) tdec_gen_kernel(const TdecLaunch a)
   }
 }
 
-// ---- layout conversion: natural 3i+j -> working layout -----------------------------------------
-__global__ void natural_to_working_kernel(const int16_t* __restrict__ nat, uint32_t nat_stride,
-                                          int16_t* __restrict__ work, uint32_t work_stride,
-                                          const uint32_t* __restrict__ cb_K, uint32_t uniform_K)
+// ---- layout conversion into the decoder's internal layout -----------------------------------------
+// window decoders: [sys | par0 | par1] pair-major streams of Lp*W int16 each (Lp = L rounded up to 4),
+//                  then 16 int16 holding the 12 tail samples, then 16 int16 of meta data:
+//                  max |sys|, max |par0|, max |par1| (uint16) -- the inputs of the fast-path proof.
+// generic decoder: the natural 3i+j order unchanged.
+__device__ __forceinline__ uint32_t windows_of(uint32_t K)
 {
+  return (K % 16 == 0 && K > 800) ? 16u : (K % 8 == 0 && K > 400) ? 8u : 0u;
+}
+
+// src_format 0: natural 3i+j (tails at 3K).  1: the reference's sub-block soft-buffer layout.
+__global__ void __launch_bounds__(256) to_internal_kernel(const int16_t* __restrict__ src_all, uint32_t src_stride,
+                                                          int16_t* __restrict__ dst_all, uint32_t dst_stride,
+                                                          const uint32_t* __restrict__ cb_K, uint32_t uniform_K,
+                                                          uint32_t src_format)
+{
+  extern __shared__ int16_t stage[];  // natural input of one code block (format 0 only)
+  __shared__ uint32_t s_max[3];
   const uint32_t cb = blockIdx.x;
   const uint32_t K  = cb_K ? cb_K[cb] : uniform_K;
-  const int16_t* src = nat + (size_t)cb * nat_stride;
-  int16_t*       dst = work + (size_t)cb * work_stride;
-  const uint32_t W = (K % 16 == 0 && K > 800) ? 16u : (K % 8 == 0 && K > 400) ? 8u : 0u;
+  const int16_t* src = src_all + (size_t)cb * src_stride;
+  int16_t*       dst = dst_all + (size_t)cb * dst_stride;
+  const uint32_t W = windows_of(K);
   if (W == 0) {
     for (uint32_t i = threadIdx.x; i < 3 * K + 12; i += blockDim.x) dst[i] = src[i];
     return;
   }
-  const uint32_t L = K / W;
-  for (uint32_t o = threadIdx.x; o < 3 * K; o += blockDim.x) {
-    const uint32_t j = o / K, s = o - j * K;
-    const uint32_t k = s / W, d = s - k * W;
-    dst[j * (K + 32) + s] = src[3 * (d * L + k) + j];
+  const uint32_t L = K / W, Lp = (L + 3) & ~3u, WH = W / 2, S = Lp * W;
+  if (threadIdx.x < 3) s_max[threadIdx.x] = 0;
+  if (src_format == 0) {
+    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+    uint32_t*       t32 = reinterpret_cast<uint32_t*>(stage);
+    for (uint32_t i = threadIdx.x; i < (3 * K + 12) / 2; i += blockDim.x) t32[i] = s32[i];
   }
-  for (uint32_t i = threadIdx.x; i < 12; i += blockDim.x) dst[3 * (K + 32) + i] = src[3 * K + i];
+  __syncthreads();
+  const uint32_t groups = Lp / 4;
+  uint32_t       mx[3]  = {0, 0, 0};
+  for (uint32_t o = threadIdx.x; o < 3 * groups * WH; o += blockDim.x) {
+    const uint32_t j = o / (groups * WH), rem = o - j * groups * WH;
+    const uint32_t kg = rem / WH, t = rem - kg * WH;
+    uint32_t       w[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const uint32_t k = kg * 4 + r;
+      int            lo = 0, hi = 0;
+      if (k < L) {
+        if (src_format == 0) {
+          lo = stage[3 * ((2 * t) * L + k) + j];
+          hi = stage[3 * ((2 * t + 1) * L + k) + j];
+        } else {
+          const uint32_t v = reinterpret_cast<const uint32_t*>(src + j * (K + 32))[k * WH + t];
+          lo = (int16_t)(v & 0xFFFFu);
+          hi = (int16_t)(v >> 16);
+        }
+      }
+      mx[j] = max(mx[j], (uint32_t)max(abs(lo), abs(hi)));
+      w[r]  = (uint32_t)(uint16_t)lo | ((uint32_t)(uint16_t)hi << 16);
+    }
+    reinterpret_cast<uint4*>(dst + j * S)[kg * WH + t] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  const int16_t* tl = src_format == 0 ? stage + 3 * K : src + 3 * (K + 32);
+  if (threadIdx.x < 16) dst[3 * S + threadIdx.x] = threadIdx.x < 12 ? tl[threadIdx.x] : (int16_t)0;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    uint32_t v = mx[j];
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(&s_max[j], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    uint16_t* meta = reinterpret_cast<uint16_t*>(dst + 3 * S + 16);
+    meta[threadIdx.x] = threadIdx.x < 3 ? (uint16_t)s_max[threadIdx.x] : (uint16_t)0;
+  }
 }
 
 // ---- rate de-matching ----------------------------------------------------------------------------
@@ -603,6 +1215,14 @@ void upload_crc_tables()
 
 int tdec_blocks_per_warp(int W) { return W == 16 ? 4 : W == 8 ? 8 : 32; }
 
+uint32_t internal_len(uint32_t K)
+{
+  const uint32_t W = (K % 16 == 0 && K > 800) ? 16u : (K % 8 == 0 && K > 400) ? 8u : 0u;
+  if (W == 0) return 3 * K + 12;
+  const uint32_t L = K / W, Lp = (L + 3) & ~3u;
+  return 3 * Lp * W + 32;
+}
+
 cudaError_t tdec_geometry(int W, int device, TdecGeometry* g)
 {
   int sms = 0;
@@ -618,7 +1238,7 @@ cudaError_t tdec_geometry(int W, int device, TdecGeometry* g)
     g->ws_chk_bytes = slots * (400 + 4) * 32 * sizeof(uint4);
     return cudaSuccess;
   }
-  g->smem = (size_t)kChunk * 2 * kThreads * sizeof(uint4);
+  g->smem = (size_t)kChunk * 2 * kThreads * sizeof(uint4) + warps_per_block * kMaxL * sizeof(uint32_t);
   int per_sm = 0;
   if (W == 16) {
     e = cudaFuncSetAttribute(tdec_win_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
@@ -642,9 +1262,8 @@ cudaError_t tdec_launch(int W, const TdecGeometry& g, const TdecLaunch& a, cudaS
   if (a.n_items == 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
-  const int blocks = (int)((a.n_items + (kThreads / 32) - 1) / (kThreads / 32)) < g.blocks
-                         ? (int)((a.n_items + (kThreads / 32) - 1) / (kThreads / 32))
-                         : g.blocks;
+  const int want   = (int)((a.n_items + (kThreads / 32) - 1) / (kThreads / 32));
+  const int blocks = want < g.blocks ? want : g.blocks;
   if (W == 16)
     tdec_win_kernel<16><<<blocks, g.threads, g.smem, s>>>(a);
   else if (W == 8)
@@ -654,11 +1273,20 @@ cudaError_t tdec_launch(int W, const TdecGeometry& g, const TdecLaunch& a, cudaS
   return cudaGetLastError();
 }
 
-cudaError_t natural_to_working_launch(const int16_t* nat, uint32_t nat_stride, int16_t* work, uint32_t work_stride,
-                                      const uint32_t* cb_K, uint32_t uniform_K, uint32_t n_cb, cudaStream_t s)
+cudaError_t to_internal_launch(const int16_t* src, uint32_t src_stride, int src_format, int16_t* dst,
+                               uint32_t dst_stride, const uint32_t* cb_K, uint32_t uniform_K, uint32_t n_cb,
+                               cudaStream_t s)
 {
   if (n_cb == 0) return cudaSuccess;
-  natural_to_working_kernel<<<n_cb, 256, 0, s>>>(nat, nat_stride, work, work_stride, cb_K, uniform_K);
+  static bool attr_set = false;
+  const size_t smem = src_format == 0 ? (3 * 6144 + 12) * sizeof(int16_t) : 0;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(to_internal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)((3 * 6144 + 12) * sizeof(int16_t)));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  to_internal_kernel<<<n_cb, 256, smem, s>>>(src, src_stride, dst, dst_stride, cb_K, uniform_K, (uint32_t)src_format);
   return cudaGetLastError();
 }
 

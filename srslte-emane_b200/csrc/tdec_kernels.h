@@ -20,7 +20,7 @@ enum CrcMode : uint32_t {
 };
 
 struct TdecLaunch {
-  const int16_t*  in;          // working-layout input of every code block (device)
+  const int16_t*  in;          // internal-layout input of every code block (device), see to_internal_launch
   uint32_t        in_stride;   // int16 elements between code blocks (even)
   uint8_t*        out;         // decoded bytes (device)
   uint32_t        out_stride;  // bytes between code blocks
@@ -32,8 +32,10 @@ struct TdecLaunch {
   uint32_t*       counter;     // device work counter, zeroed by the launcher
   uint32_t        max_iter;    // half-iteration cap
   uint32_t        crc_mode;
-  int16_t*        ws_ae;       // extrinsic work arrays, sized by tdec_workspace_bytes()
-  uint32_t*       ws_chk;      // beta checkpoints, sized by tdec_workspace_bytes()
+  int16_t*        ws_ae;       // extrinsic work arrays, sized by tdec_geometry()
+  uint32_t*       ws_chk;      // beta checkpoints, sized by tdec_geometry()
+  uint32_t        force_exact; // 1: always run the exact saturating variant (tests)
+  uint32_t*       stats;       // device counter: half iterations (per warp) that fell back to the exact variant
 };
 
 struct TdecGeometry {
@@ -49,10 +51,15 @@ cudaError_t tdec_geometry(int W, int device, TdecGeometry* g);
 cudaError_t tdec_launch(int W, const TdecGeometry& g, const TdecLaunch& a, cudaStream_t s);
 int         tdec_blocks_per_warp(int W);
 
-// natural (3i+j, tails last) -> working layout, one code block per CTA.
-cudaError_t natural_to_working_launch(const int16_t* nat, uint32_t nat_stride, int16_t* work, uint32_t work_stride,
-                                      const uint32_t* cb_K /* device, nullable */, uint32_t uniform_K, uint32_t n_cb,
-                                      cudaStream_t s);
+// int16 elements of one code block in the decoder's internal layout (pair-major streams + tail + meta
+// for window decoders, natural order for the generic decoder).
+uint32_t internal_len(uint32_t K);
+
+// src_format 0: natural (3i+j, tails last); 1: the reference's sub-block soft-buffer layout.
+// One code block per CTA; also records max |sys|, |par0|, |par1| per block for the fast-path proof.
+cudaError_t to_internal_launch(const int16_t* src, uint32_t src_stride, int src_format, int16_t* dst,
+                               uint32_t dst_stride, const uint32_t* cb_K /* device, nullable */, uint32_t uniform_K,
+                               uint32_t n_cb, cudaStream_t s);
 
 // rate de-matching: work[tab[i mod N]] += e[i], i < E, wrapping int16.
 struct RmItem {

@@ -44,3 +44,4 @@ for K in Ks:
                 print(f"K={K} CRC mode block {i}: n_iter {n_iter[i]} vs {stop}, ok {ok[i]} vs {exp_ok}, bytes eq {np.array_equal(got[i], by[stop-1])}")
     print(f"K={K} done, cumulative mismatches {bad_total}", flush=True)
 print("TOTAL MISMATCHES", bad_total)
+print("fallbacks (warp x half-iteration) so far:", ctx.fallback_count)
