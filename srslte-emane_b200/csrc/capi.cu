@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -309,7 +310,9 @@ int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint
   }
   ctx->launches++;
   const int16_t* win    = ctx->d_work.p;
-  const uint32_t stride = work_len;
+  // development probe: B200_ALIAS_INPUT=1 makes every block read block 0's input (memory-stall experiment)
+  static const bool alias_input = getenv("B200_ALIAS_INPUT") != nullptr;
+  const uint32_t stride = alias_input ? 0u : work_len;
   if (ctx->counters.cap == 0) {
     CU(ctx->counters.reserve(4));
     CU(cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(uint32_t), st));

@@ -33,6 +33,7 @@
 #include "tdec_kernels.h"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace b200 {
 
@@ -42,7 +43,12 @@ constexpr int      kWarm      = 40;  // win_overlap_len
 constexpr int      kChunk     = 16;  // rows of beta rebuilt at a time (multiple of 4)
 constexpr int      kThreads   = 128;
 constexpr int      kMaxChunks = 24;  // ceil(384 / 16)
+// per-warp-slot strides are odd multiples of 128 bytes: warps run in near lock step, and power-of-two
+// strides would send all of them to the same L2 slices / HBM channels at once
+constexpr int      kChkSlotWords = kMaxChunks * 8 * 32 + 32;
+constexpr uint32_t kAeStride16 = 6144 + 64, kAeStride8 = 800 + 32;  // int16 per A or E array
 constexpr int      kMaxL      = 384;
+constexpr int      kPrefetchGroups = 4;  // L2 prefetch distance in row groups
 constexpr int      kExactRows = 4;   // rows next to a known-state boundary always use exact arithmetic
 constexpr int      kMaxFastG  = 5461; // largest per-step metric change the fast variant accepts (6 * G <= 32767)
 constexpr int      kNegInf    = -10000;
@@ -212,8 +218,10 @@ struct WinCtx {
   const uint4*    par04;
   const uint4*    par14;
   const int16_t*  tail;   // 12 tail samples
-  uint4*          A4;     // pair-major   extrinsic of DEC2 minus E (= a-priori of DEC1)
-  uint4*          E4;     // pair-major   a-posteriori of DEC1 minus A (= systematic of DEC2)
+  uint32_t*       A32;    // row-major [L][W/2]: extrinsic of DEC2 minus E (= a-priori of DEC1)
+  uint32_t*       E32;    // row-major [L][W/2]: a-posteriori of DEC1 minus A (= systematic of DEC2)
+                          // (row-major keeps the 16 windows of a row in one 32-byte sector for the QPP
+                          //  gather / scatter of DEC2)
   uint32_t*       chk;    // checkpoints: [(c*8 + i)*32], already offset by lane
   uint4*          sm;     // chunk of beta: [(s*2 + h)*kThreads], already offset by tid
   const uint32_t* qtab;   // per-warp table in shared memory: pi(k) as row | window << 16, k < L
@@ -231,13 +239,14 @@ __device__ __forceinline__ uint32_t pm_word(uint32_t k, uint32_t t)
   return (((k >> 2) * (W / 2) + t) << 2) + (k & 3);
 }
 
-// where row k of DEC2's trellis reads its systematic input / writes its extrinsic (QPP on the fly)
+// where row k of DEC2's trellis reads its systematic input / writes its extrinsic (QPP on the fly):
+// int16 indices into the row-major A / E arrays
 template <int W>
 __device__ __forceinline__ void qpp_pair(const WinCtx<W>& c, uint32_t k, uint32_t& i_lo, uint32_t& i_hi)
 {
   const uint32_t q = c.qtab[k], row = q & 0xFFFFu, w0 = q >> 16;
-  i_lo = pm_index<W>(row, (w0 + c.base_lo + c.inc_lo * k) & (W - 1));
-  i_hi = pm_index<W>(row, (w0 + c.base_hi + c.inc_hi * k) & (W - 1));
+  i_lo = row * W + ((w0 + c.base_lo + c.inc_lo * k) & (W - 1));
+  i_hi = row * W + ((w0 + c.base_hi + c.inc_hi * k) & (W - 1));
 }
 
 // the inputs of 4 consecutive trellis rows (one row group) for this thread's window pair
@@ -250,6 +259,24 @@ struct RawGroup {
   uint4 a, b, c;  // DEC1: sys, parity, a-priori.  DEC2: b = parity, a / c = gathered low / high halves
 };
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// pull the streaming inputs of row group kg (one 128-byte line per stream and code block) into L2 well
+// ahead of the register prefetch; one lane per code block issues it
+template <int W, bool DEC2>
+__device__ __forceinline__ void prefetch_group_l2(const WinCtx<W>& c, bool apriori, int kg)
+{
+  constexpr int WH = W / 2;
+  if (c.t != 0 || kg < 0 || kg * 4 >= (int)c.L) return;
+  if (!DEC2) {
+    prefetch_l2(c.sys4 + kg * WH);
+    prefetch_l2(c.par04 + kg * WH);
+    if (apriori) prefetch_l2(c.A32 + (kg * 4) * WH);
+  } else {
+    prefetch_l2(c.par14 + kg * WH);
+  }
+}
+
 template <int W, bool DEC2>
 __device__ __forceinline__ void issue_group(const WinCtx<W>& c, bool apriori, int kg, RawGroup& q)
 {
@@ -257,10 +284,13 @@ __device__ __forceinline__ void issue_group(const WinCtx<W>& c, bool apriori, in
   if (!DEC2) {
     q.a = __ldg(c.sys4 + kg * WH + c.t);
     q.b = __ldg(c.par04 + kg * WH + c.t);
-    if (apriori) q.c = c.A4[kg * WH + c.t];
+    if (apriori) {
+      const uint32_t* ap = c.A32 + (kg * 4) * WH + c.t;
+      q.c = make_uint4(ap[0], ap[WH], ap[2 * WH], ap[3 * WH]);
+    }
   } else {
     q.b = __ldg(c.par14 + kg * WH + c.t);
-    const uint16_t* E16 = reinterpret_cast<const uint16_t*>(c.E4);
+    const uint16_t* E16 = reinterpret_cast<const uint16_t*>(c.E32);
     uint32_t        lo[4], hi[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
@@ -308,13 +338,13 @@ __device__ __forceinline__ void load_row_exact(const WinCtx<W>& c, bool dec2, bo
     y   = __ldg(reinterpret_cast<const uint32_t*>(c.par04) + w);
     aux = 0;
     if (apriori) {
-      aux = reinterpret_cast<const uint32_t*>(c.A4)[w];
+      aux = c.A32[k * (W / 2) + c.t];
       x   = sadd2(aux, x);
     }
   } else {
     uint32_t i_lo, i_hi;
     qpp_pair<W>(c, k, i_lo, i_hi);
-    const uint16_t* E16 = reinterpret_cast<const uint16_t*>(c.E4);
+    const uint16_t* E16 = reinterpret_cast<const uint16_t*>(c.E32);
     x   = (uint32_t)E16[i_lo] | ((uint32_t)E16[i_hi] << 16);
     y   = __ldg(reinterpret_cast<const uint32_t*>(c.par14) + w);
     aux = x;
@@ -328,11 +358,11 @@ __device__ __forceinline__ void store_out(const WinCtx<W>& c, uint32_t k, uint32
   const uint32_t d = wsub2(o, aux);
   rd.add1(d);
   if (!DEC2) {
-    reinterpret_cast<uint32_t*>(c.E4)[pm_word<W>(k, (uint32_t)c.t)] = d;
+    c.E32[k * (W / 2) + c.t] = d;
   } else {
     uint32_t i_lo, i_hi;
     qpp_pair<W>(c, k, i_lo, i_hi);
-    uint16_t* A16 = reinterpret_cast<uint16_t*>(c.A4);
+    uint16_t* A16 = reinterpret_cast<uint16_t*>(c.A32);
     A16[i_lo]     = (uint16_t)(d & 0xFFFFu);
     A16[i_hi]     = (uint16_t)(d >> 16);
   }
@@ -579,6 +609,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
   for (int kg = gtop; kg >= 0; kg--) {
     finish_group<DEC2>(apriori, q, g);
     if (kg > 0) issue_group<W, DEC2>(c, apriori, kg - 1, q);
+    prefetch_group_l2<W, DEC2>(c, apriori, kg - kPrefetchGroups);
 #pragma unroll
     for (int r = 3; r >= 0; r--) {
       beta_step<true>(s, g.x[r], g.y[r], wadd2(g.x[r], g.y[r]));
@@ -695,6 +726,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
         issue_group<W, DEC2>(c, apriori, kg + 1, q);
       else if (ch + 1 < nchunks)
         issue_group<W, DEC2>(c, apriori, min((min(hi + kChunk, L) - 1) >> 2, gtop), q);  // top fast group of the next chunk
+      prefetch_group_l2<W, DEC2>(c, apriori, kg + kChunk / 4 + kPrefetchGroups);  // rows of the chunks ahead
 #pragma unroll
       for (int r = 0; r < 4; r++) {
         const int      k  = kg * 4 + r;
@@ -761,9 +793,14 @@ __device__ void decide(const WinCtx<W>& c, uint8_t* out, bool write)
   uint32_t* grp_base = reinterpret_cast<uint32_t*>(c.sm - c.t);
   auto      word     = [&](uint32_t f) -> uint32_t& { return grp_base[((f / WH) * kThreads + (f % WH)) * 4]; };
   uint32_t  acc_lo = 0, acc_hi = 0;
+#pragma unroll 2
   for (uint32_t kg = 0; kg * 4 < L; kg++) {
-    const uint4    av = c.A4[kg * WH + c.t], ev = c.E4[kg * WH + c.t];
-    const uint32_t v[4] = {wadd2(av.x, ev.x), wadd2(av.y, ev.y), wadd2(av.z, ev.z), wadd2(av.w, ev.w)};
+    uint32_t v[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const uint32_t k = min(kg * 4 + r, L - 1);
+      v[r] = wadd2(c.A32[k * WH + c.t], c.E32[k * WH + c.t]);
+    }
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       const uint32_t k = kg * 4 + r;
@@ -833,7 +870,7 @@ __global__ void __launch_bounds__(kThreads, 3) tdec_win_kernel(const TdecLaunch 
 {
   constexpr int WH  = W / 2;
   constexpr int CBW = 32 / WH;
-  constexpr uint32_t KMAX = (W == 16) ? 6144u : 800u;
+  constexpr uint32_t KMAX = (W == 16) ? kAeStride16 : kAeStride8;
   extern __shared__ uint4 smem[];
   uint32_t* qtab_all = reinterpret_cast<uint32_t*>(smem + kChunk * 2 * kThreads);
 
@@ -890,12 +927,12 @@ __global__ void __launch_bounds__(kThreads, 3) tdec_win_kernel(const TdecLaunch 
     const uint16_t* meta = reinterpret_cast<const uint16_t*>(in + 3 * S + 16);
     const int smax = meta[0], p0max = meta[1], p1max = meta[2];
     int16_t* ae = a.ws_ae + ((size_t)slot * CBW + grp) * 2 * KMAX;
-    c.A4  = reinterpret_cast<uint4*>(ae);
-    c.E4  = reinterpret_cast<uint4*>(ae + KMAX);
-    c.chk = a.ws_chk + (size_t)slot * kMaxChunks * 8 * 32 + lane;
+    c.A32 = reinterpret_cast<uint32_t*>(ae);
+    c.E32 = reinterpret_cast<uint32_t*>(ae + KMAX);
+    c.chk = a.ws_chk + (size_t)slot * kChkSlotWords + lane;
     c.sm  = smem + tid;
 
-    for (uint32_t kg = 0; kg < Lp / 4; kg++) c.A4[kg * WH + t] = make_uint4(0, 0, 0, 0);
+    for (uint32_t k = 0; k < c.L; k++) c.A32[k * WH + t] = 0;
     __syncwarp();
 
     uint8_t* out  = a.out + (size_t)cb * a.out_stride;
@@ -1249,11 +1286,15 @@ cudaError_t tdec_geometry(int W, int device, TdecGeometry* g)
   }
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
+  if (const char* e = getenv("B200_BLOCKS_PER_SM")) {  // development probe
+    const int v = atoi(e);
+    if (v >= 1 && v < per_sm) per_sm = v;
+  }
   g->blocks = sms * per_sm;
   const size_t slots = (size_t)g->blocks * warps_per_block;
-  const size_t kmax  = W == 16 ? 6144 : 800;
+  const size_t kmax  = W == 16 ? kAeStride16 : kAeStride8;
   g->ws_ae_bytes  = slots * (size_t)tdec_blocks_per_warp(W) * 2 * kmax * sizeof(int16_t);
-  g->ws_chk_bytes = slots * kMaxChunks * 8 * 32 * sizeof(uint32_t);
+  g->ws_chk_bytes = slots * kChkSlotWords * sizeof(uint32_t);
   return cudaSuccess;
 }
 

@@ -211,3 +211,38 @@ def test_rate_dematch_vs_oracle(ctx, vec, pkg):
     ctx.synchronize()
     got, n_iter, ok = ctx.tdec_batch_host(work.cpu().numpy(), K, 8, crc_mode=pkg.CRC_24B, natural=False)
     assert np.array_equal(got, np.packbits(bits, axis=1)) and (ok == 1).all()
+
+
+def test_fast_and_exact_variants_agree(ctx, vec, pkg):
+    """The fast (wrapping, proven) and the exact (saturating) variants of the window decoders give the
+    same bytes; benign inputs stay on the fast variant, saturating inputs fall back to the exact one."""
+    for K in (408, 1024, 6144):
+        for sigma, scale in ((1.092, 100), (0.9, 700), (0.6, 4000)):
+            bits, llr = vec.make_blocks(8, K, sigma, scale, seed=K + scale)
+            want = ol.port_run_all(llr, K, 6)
+            f0 = ctx.fallback_count
+            fast, _, _ = ctx.tdec_batch_host(llr, K, 6)
+            f1 = ctx.fallback_count
+            ctx.set_exact(True)
+            exact, _, _ = ctx.tdec_batch_host(llr, K, 6)
+            ctx.set_exact(False)
+            assert np.array_equal(fast, want) and np.array_equal(exact, want), (K, sigma, scale)
+            if scale == 4000:
+                assert f1 > f0, "inputs that saturate must take the exact re-run"
+    # the benchmark operating point never needs the exact re-run
+    bits, llr = vec.make_blocks(64, 6144, vec.harness_sigma(1.5), 100, seed=77, crc=False)
+    f0 = ctx.fallback_count
+    got, _, _ = ctx.tdec_batch_host(llr, 6144, 4)
+    assert ctx.fallback_count == f0
+    assert np.array_equal(got, ol.port_run_all(llr, 6144, 4))
+
+
+def test_near_saturation_boundary(ctx, vec):
+    """LLR scales swept across the point where the reference's saturating adds start to clamp: the
+    proof-or-fallback logic must stay bit-exact on both sides of it."""
+    K = 2048
+    for scale in (150, 300, 450, 600, 900, 1300, 2000):
+        bits, llr = vec.make_blocks(4, K, 0.8, scale, seed=scale)
+        for nit in (2, 5, 9):
+            got, _, _ = ctx.tdec_batch_host(llr, K, nit)
+            assert np.array_equal(got, ol.port_run_all(llr, K, nit)), (scale, nit)
