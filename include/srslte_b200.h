@@ -136,6 +136,37 @@ typedef struct {
 SRSLTE_B200_API int srslte_b200_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_rm_block_t* blocks,
                                                 uint32_t n_blocks, const int16_t* e, int16_t* work);
 
+/* ---- batched transport-block decode (the sch.c decode_tb loop over many TBs) ----------------- */
+/* HARQ state lives on the device: one "soft buffer" = max_cb code-block LLR buffers + CRC flags +
+ * saved payloads, the counterpart of srslte_softbuffer_rx_t (softbuffer.h:37-43, softbuffer.c:41-150). */
+typedef struct srslte_b200_harq_pool srslte_b200_harq_pool_t;
+SRSLTE_B200_API int  srslte_b200_harq_pool_create(srslte_b200_ctx_t* ctx, uint32_t n_softbuffers, uint32_t max_cb,
+                                                  srslte_b200_harq_pool_t** pool);
+SRSLTE_B200_API void srslte_b200_harq_pool_destroy(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool);
+/* srslte_softbuffer_rx_reset: zero the LLRs, clear cb_crc / tb_crc and the saved payloads of one soft buffer */
+SRSLTE_B200_API int  srslte_b200_harq_reset(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool, uint32_t softbuffer);
+/* copy of softbuffer->cb_crc[0..n) */
+SRSLTE_B200_API int  srslte_b200_harq_cb_crc(srslte_b200_harq_pool_t* pool, uint32_t softbuffer, uint8_t* cb_crc,
+                                             uint32_t n);
+
+typedef struct {
+  uint32_t       tbs;            /* transport block size in bits (without its CRC24A)                  */
+  uint32_t       qm;             /* bits per symbol x layers, as decode_tb receives it (sch.c:528)     */
+  uint32_t       rv;             /* redundancy version                                                 */
+  uint32_t       nof_e_bits;     /* G: rate-matched soft bits of this TB                               */
+  uint32_t       softbuffer;     /* soft buffer of the pool (HARQ process) to combine into             */
+  const int16_t* e_bits;         /* host: nof_e_bits int16 LLRs                                        */
+  uint8_t*       data;           /* host: decoded TB, at least tbs/8 + 6 bytes                         */
+  int32_t        ret;            /* out: 0 ok, -1 CRC failure, -2 invalid arguments (decode_tb's value) */
+  float          avg_iterations; /* out: srslte_sch_last_noi                                           */
+} srslte_b200_tb_t;
+
+/* decode_tb (sch.c:429-500) for n_tb independent transport blocks in one call: rate de-matching into the
+ * soft buffers, all code blocks of all TBs decoded in one batch with CRC24B/24A early termination,
+ * block -> TB assembly, TB CRC24A, HARQ bookkeeping.  Returns 0 when the batch ran; per-TB results in tbs[]. */
+SRSLTE_B200_API int srslte_b200_decode_tb_batch(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
+                                                srslte_b200_tb_t* tbs, uint32_t n_tb, uint32_t max_iterations);
+
 #ifdef __cplusplus
 }
 #endif

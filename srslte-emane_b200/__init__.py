@@ -34,6 +34,12 @@ class RmBlock(C.Structure):
                 ("work_offset", C.c_uint32)]
 
 
+class TbDesc(C.Structure):
+    _fields_ = [("tbs", C.c_uint32), ("qm", C.c_uint32), ("rv", C.c_uint32), ("nof_e_bits", C.c_uint32),
+                ("softbuffer", C.c_uint32), ("e_bits", C.c_void_p), ("data", C.c_void_p), ("ret", C.c_int32),
+                ("avg_iterations", C.c_float)]
+
+
 EXPORTS = [
     "srslte_b200_ctx_create", "srslte_b200_ctx_destroy", "srslte_b200_ctx_set_stream",
     "srslte_b200_ctx_synchronize", "srslte_b200_last_error", "srslte_b200_launch_count",
@@ -41,6 +47,8 @@ EXPORTS = [
     "srslte_b200_ctx_fallback_count", "srslte_b200_host_alloc", "srslte_b200_host_free", "srslte_b200_cb_index", "srslte_b200_cb_size",
     "srslte_b200_nof_windows", "srslte_b200_working_len", "srslte_b200_rm_rx_table",
     "srslte_b200_tdec_batch_dev", "srslte_b200_tdec_batch_host", "srslte_b200_rm_rx_batch_dev",
+    "srslte_b200_harq_pool_create", "srslte_b200_harq_pool_destroy", "srslte_b200_harq_reset",
+    "srslte_b200_harq_cb_crc", "srslte_b200_decode_tb_batch",
 ]
 
 _lib = None
@@ -83,6 +91,12 @@ def lib():
     L.srslte_b200_tdec_batch_dev.argtypes = [vp, C.POINTER(TdecBatch), vp, vp, vp, vp]
     L.srslte_b200_tdec_batch_host.argtypes = [vp, C.POINTER(TdecBatch), vp, vp, vp, vp]
     L.srslte_b200_rm_rx_batch_dev.argtypes = [vp, C.POINTER(RmBlock), u32, vp, vp]
+    L.srslte_b200_harq_pool_create.argtypes = [vp, u32, u32, C.POINTER(vp)]
+    L.srslte_b200_harq_pool_destroy.argtypes = [vp, vp]
+    L.srslte_b200_harq_pool_destroy.restype = None
+    L.srslte_b200_harq_reset.argtypes = [vp, vp, u32]
+    L.srslte_b200_harq_cb_crc.argtypes = [vp, u32, vp, u32]
+    L.srslte_b200_decode_tb_batch.argtypes = [vp, vp, C.POINTER(TbDesc), u32, u32]
     _lib = L
     return L
 
@@ -229,6 +243,26 @@ class Context:
                                                 C.c_void_p(nit_ptr), C.c_void_p(crc_ptr))
         self._check(rc, "srslte_b200_tdec_batch_dev")
 
+    # ---- transport blocks (sch.c decode_tb semantics, device-resident HARQ soft buffers) ----------
+    def harq_pool(self, n_softbuffers, max_cb):
+        return HarqPool(self, n_softbuffers, max_cb)
+
+    def decode_tb_batch(self, pool, tbs, max_iterations):
+        """tbs: list of dicts {tbs, qm, rv, e_bits (int16 ndarray), softbuffer}.
+        Returns list of (ret, data bytes [tbs/8 + 6], avg_iterations)."""
+        n = len(tbs)
+        arr = (TbDesc * n)()
+        outs, keep = [], []
+        for i, t in enumerate(tbs):
+            e = np.ascontiguousarray(t["e_bits"], dtype=np.int16)
+            o = np.zeros(t["tbs"] // 8 + 8, np.uint8)
+            keep.append(e)
+            outs.append(o)
+            arr[i] = TbDesc(t["tbs"], t["qm"], t["rv"], e.size, t["softbuffer"], e.ctypes.data, o.ctypes.data, 0, 0.0)
+        rc = self._L.srslte_b200_decode_tb_batch(self._h, pool._p, arr, n, max_iterations)
+        self._check(rc, "srslte_b200_decode_tb_batch")
+        return [(int(arr[i].ret), outs[i], float(arr[i].avg_iterations)) for i in range(n)]
+
     def rm_rx_batch_dev(self, blocks, e_ptr, work_ptr):
         """blocks: list of (K, rv, e_offset, e_len, work_offset)."""
         arr = (RmBlock * len(blocks))()
@@ -236,3 +270,34 @@ class Context:
             arr[i] = RmBlock(K, rv, eo, el, wo)
         rc = self._L.srslte_b200_rm_rx_batch_dev(self._h, arr, len(blocks), C.c_void_p(e_ptr), C.c_void_p(work_ptr))
         self._check(rc, "srslte_b200_rm_rx_batch_dev")
+
+
+class HarqPool:
+    """Device-resident HARQ soft buffers (srslte_b200_harq_pool_t)."""
+
+    def __init__(self, ctx, n_softbuffers, max_cb):
+        self._ctx = ctx
+        self._p = C.c_void_p()
+        self.max_cb = max_cb
+        rc = ctx._L.srslte_b200_harq_pool_create(ctx._h, n_softbuffers, max_cb, C.byref(self._p))
+        ctx._check(rc, "srslte_b200_harq_pool_create")
+
+    def reset(self, softbuffer):
+        self._ctx._check(self._ctx._L.srslte_b200_harq_reset(self._ctx._h, self._p, softbuffer), "harq_reset")
+
+    def cb_crc(self, softbuffer, n):
+        out = np.zeros(n, np.uint8)
+        rc = self._ctx._L.srslte_b200_harq_cb_crc(self._p, softbuffer, out.ctypes.data, n)
+        self._ctx._check(rc, "harq_cb_crc")
+        return out
+
+    def close(self):
+        if self._p:
+            self._ctx._L.srslte_b200_harq_pool_destroy(self._ctx._h, self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -297,7 +297,8 @@ int check_batch(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint32_
 
 // enqueue conversion (if needed) + the decode kernels for blocks described by `b` on stream st
 int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint32_t work_len, const int16_t* d_llr,
-                   uint8_t* d_out, uint8_t* d_nit, uint8_t* d_crc, cudaStream_t st)
+                   uint8_t* d_out, uint8_t* d_nit, uint8_t* d_crc, cudaStream_t st,
+                   const uint64_t* d_src_off = nullptr, const uint8_t* d_crc_mode_cb = nullptr)
 {
   int rc = ensure_schedule(ctx, b->long_cb, b->uniform_long_cb, b->n_cb, st);
   if (rc) return rc;
@@ -305,8 +306,9 @@ int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint
   CU(ctx->d_work.reserve((size_t)b->n_cb * work_len));
   {
     KernelTimer kt(ctx, 3, st);
-    CU(to_internal_launch(d_llr, b->in_stride, b->input_format == SRSLTE_B200_INPUT_NATURAL ? 0 : 1, ctx->d_work.p,
-                          work_len, b->long_cb ? ctx->d_cbK.p : nullptr, b->uniform_long_cb, b->n_cb, st));
+    CU(to_internal_launch(d_llr, b->in_stride, d_src_off, b->input_format == SRSLTE_B200_INPUT_NATURAL ? 0 : 1,
+                          ctx->d_work.p, work_len, b->long_cb ? ctx->d_cbK.p : nullptr, b->uniform_long_cb, b->n_cb,
+                          st));
   }
   ctx->launches++;
   const int16_t* win    = ctx->d_work.p;
@@ -336,6 +338,7 @@ int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint
     a.counter    = ctx->counters.p + r;
     a.max_iter   = b->nof_iterations;
     a.crc_mode   = b->crc_mode;
+    a.crc_mode_cb = d_crc_mode_cb;
     a.ws_ae      = reinterpret_cast<int16_t*>(R.ws_ae.p);
     a.ws_chk     = reinterpret_cast<uint32_t*>(R.ws_chk.p);
     a.force_exact = ctx->force_exact ? 1u : 0u;
@@ -622,6 +625,264 @@ int srslte_b200_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_rm_blo
     CU(rm_rx_launch(e, work, ctx->rm_pool_dev.p, ctx->d_rm_items.p, n_blocks, st));
   }
   ctx->launches++;
+  return SRSLTE_B200_SUCCESS;
+}
+
+}  // extern "C"
+
+// =====================================================================================================
+// transport blocks: rate de-matching into device-resident HARQ soft buffers, decode with CRC early
+// termination, code-block -> transport-block assembly, TB CRC24A  (reference: sch.c:299-500)
+// =====================================================================================================
+struct srslte_b200_harq_pool {
+  uint32_t n_sb = 0, max_cb = 0;
+  static constexpr uint32_t kStride = 18624;  // int16 per code block (>= SOFTBUFFER_SIZE 18600, multiple of 64)
+  DevBuf<int16_t>      llr;                   // [n_sb][max_cb][kStride]
+  std::vector<uint8_t> cb_crc;                // [n_sb][max_cb]
+  std::vector<uint8_t> tb_crc;                // [n_sb]
+  std::vector<uint8_t> saved;                 // [n_sb][max_cb][768] payloads of good blocks of a failed TB
+  // staging of the batch entry
+  PinBuf<int16_t>  h_e;
+  DevBuf<int16_t>  d_e;
+  PinBuf<uint64_t> h_off;
+  DevBuf<uint64_t> d_off;
+  PinBuf<uint8_t>  h_mode, h_out, h_nit, h_ok;
+  DevBuf<uint8_t>  d_mode, d_out, d_nit, d_ok;
+};
+
+namespace {
+struct CbJob {
+  uint32_t tb, cb, K, E, rp;
+};
+}  // namespace
+
+extern "C" {
+
+int srslte_b200_harq_pool_create(srslte_b200_ctx_t* ctx, uint32_t n_softbuffers, uint32_t max_cb,
+                                 srslte_b200_harq_pool_t** pool)
+{
+  if (!ctx || !pool || n_softbuffers == 0 || max_cb == 0) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  *pool = nullptr;
+  CU(cudaSetDevice(ctx->device));
+  auto* p   = new srslte_b200_harq_pool();
+  p->n_sb   = n_softbuffers;
+  p->max_cb = max_cb;
+  const size_t n = (size_t)n_softbuffers * max_cb;
+  cudaError_t  e = p->llr.reserve(n * srslte_b200_harq_pool::kStride);
+  if (e == cudaSuccess) e = cudaMemsetAsync(p->llr.p, 0, p->llr.cap * sizeof(int16_t), ctx->stream);
+  if (e != cudaSuccess) {
+    p->llr.release();
+    delete p;
+    return fail(ctx, SRSLTE_B200_ERROR, "HARQ pool allocation failed: %s", cudaGetErrorString(e));
+  }
+  p->cb_crc.assign(n, 0);
+  p->tb_crc.assign(n_softbuffers, 0);
+  p->saved.assign(n * 768, 0);
+  *pool = p;
+  return SRSLTE_B200_SUCCESS;
+}
+
+void srslte_b200_harq_pool_destroy(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* p)
+{
+  if (!p) return;
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+  }
+  p->llr.release();
+  p->d_e.release();
+  p->h_e.release();
+  p->h_off.release();
+  p->d_off.release();
+  p->h_mode.release();
+  p->h_out.release();
+  p->h_nit.release();
+  p->h_ok.release();
+  p->d_mode.release();
+  p->d_out.release();
+  p->d_nit.release();
+  p->d_ok.release();
+  delete p;
+}
+
+int srslte_b200_harq_reset(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* p, uint32_t softbuffer)
+{
+  if (!ctx || !p || softbuffer >= p->n_sb) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  CU(cudaSetDevice(ctx->device));
+  const size_t per = (size_t)p->max_cb * srslte_b200_harq_pool::kStride;
+  CU(cudaMemsetAsync(p->llr.p + softbuffer * per, 0, per * sizeof(int16_t), ctx->stream));
+  std::fill(p->cb_crc.begin() + (size_t)softbuffer * p->max_cb, p->cb_crc.begin() + (size_t)(softbuffer + 1) * p->max_cb, 0);
+  std::fill(p->saved.begin() + (size_t)softbuffer * p->max_cb * 768, p->saved.begin() + (size_t)(softbuffer + 1) * p->max_cb * 768, 0);
+  p->tb_crc[softbuffer] = 0;
+  return SRSLTE_B200_SUCCESS;
+}
+
+int srslte_b200_harq_cb_crc(srslte_b200_harq_pool_t* p, uint32_t softbuffer, uint8_t* cb_crc, uint32_t n)
+{
+  if (!p || !cb_crc || softbuffer >= p->n_sb || n > p->max_cb) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  std::memcpy(cb_crc, p->cb_crc.data() + (size_t)softbuffer * p->max_cb, n);
+  return SRSLTE_B200_SUCCESS;
+}
+
+int srslte_b200_decode_tb_batch(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool, srslte_b200_tb_t* tbs,
+                                uint32_t n_tb, uint32_t max_iterations)
+{
+  if (!ctx) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  if (n_tb == 0) return SRSLTE_B200_SUCCESS;
+  if (!pool || !tbs) return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "NULL argument");
+  if (max_iterations > 255) return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "max_iterations > 255");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  constexpr uint32_t kStride = srslte_b200_harq_pool::kStride;
+
+  // ---- plan: segmentation, per-block rate-matching sizes (sch.c:315-334), blocks to skip ----
+  std::vector<CbSegm>   seg(n_tb);
+  std::vector<uint8_t>  run(n_tb, 0);
+  std::vector<size_t>   e_base(n_tb, 0);
+  std::vector<CbJob>    jobs;
+  std::vector<uint32_t> Ks;
+  size_t                e_total = 0;
+  for (uint32_t i = 0; i < n_tb; i++) {
+    srslte_b200_tb_t& t = tbs[i];
+    t.ret            = SRSLTE_B200_ERROR_INVALID_INPUTS;
+    t.avg_iterations = 0;
+    if (!t.e_bits || !t.data || t.softbuffer >= pool->n_sb || t.rv > 3 || t.qm == 0) continue;
+    if (cbsegm(&seg[i], t.tbs)) {
+      t.ret = SRSLTE_B200_ERROR;  // srslte_dlsch_decode2: "Error computing Codeword segmentation"
+      continue;
+    }
+    if (seg[i].tbs == 0 || seg[i].C == 0) {
+      t.ret = SRSLTE_B200_SUCCESS;
+      continue;
+    }
+    if (seg[i].F || seg[i].C > pool->max_cb) continue;  // filler bits unsupported / soft buffer too small: -2
+    run[i] = 1;
+    t.data[t.tbs / 8 + 0] = 0;
+    t.data[t.tbs / 8 + 1] = 0;
+    t.data[t.tbs / 8 + 2] = 0;
+    e_base[i] = e_total;
+    e_total += (t.nof_e_bits + 1u) & ~1u;
+    const CbSegm& s   = seg[i];
+    uint8_t*      crc = pool->cb_crc.data() + (size_t)t.softbuffer * pool->max_cb;
+    for (uint32_t cb = 0; cb < s.C; cb++) {
+      const uint32_t K    = cb < s.C1 ? s.K1 : s.K2;
+      const uint32_t rlen = s.C == 1 ? K : K - 24;
+      if (crc[cb]) {  // decoded in an earlier transmission: copy what was saved then
+        std::memcpy(&t.data[cb * rlen / 8], &pool->saved[((size_t)t.softbuffer * pool->max_cb + cb) * 768], rlen / 8);
+        continue;
+      }
+      const uint32_t Gp = t.nof_e_bits / t.qm, gamma = Gp % s.C, n_e = t.qm * (Gp / s.C);
+      uint32_t       rp = cb * n_e, n_e2 = n_e;
+      if (cb > s.C - gamma) {  // the reference's `>` (not `>=`) is kept on purpose
+        n_e2 = n_e + t.qm;
+        rp   = (s.C - gamma) * n_e + (cb - (s.C - gamma)) * n_e2;
+      }
+      jobs.push_back({i, cb, K, n_e2, rp});
+      Ks.push_back(K);
+    }
+  }
+
+  const uint32_t n_cb = (uint32_t)jobs.size();
+  std::vector<uint32_t> noi(n_cb, 0);
+  if (n_cb) {
+    // ---- upload the rate-matched LLRs of every TB that has work ----
+    CU(cudaStreamSynchronize(st));  // staging reuse
+    CU(pool->h_e.reserve(e_total));
+    CU(pool->d_e.reserve(e_total));
+    for (uint32_t i = 0; i < n_tb; i++)
+      if (run[i]) std::memcpy(pool->h_e.p + e_base[i], tbs[i].e_bits, (size_t)tbs[i].nof_e_bits * sizeof(int16_t));
+    CU(cudaMemcpyAsync(pool->d_e.p, pool->h_e.p, e_total * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+
+    // ---- rate de-matching with HARQ combining, in place in the pool ----
+    std::vector<srslte_b200_rm_block_t> rm(n_cb);
+    CU(pool->h_off.reserve(n_cb));
+    CU(pool->d_off.reserve(n_cb));
+    CU(pool->h_mode.reserve(n_cb));
+    CU(pool->d_mode.reserve(n_cb));
+    for (uint32_t j = 0; j < n_cb; j++) {
+      const CbJob&  jb  = jobs[j];
+      const size_t  off = ((size_t)tbs[jb.tb].softbuffer * pool->max_cb + jb.cb) * kStride;
+      if (off > 0xFFFFFFFFull || e_base[jb.tb] + jb.rp > 0xFFFFFFFFull)
+        return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "HARQ pool or batch too large for 32-bit block offsets");
+      rm[j].long_cb     = jb.K;
+      rm[j].rv          = tbs[jb.tb].rv;
+      rm[j].e_offset    = (uint32_t)(e_base[jb.tb] + jb.rp);
+      rm[j].e_len       = jb.E;
+      rm[j].work_offset = (uint32_t)off;
+      pool->h_off.p[j]  = off;
+      pool->h_mode.p[j] = seg[jb.tb].C > 1 ? (uint8_t)CRC_24B : (uint8_t)CRC_24A;
+    }
+    int rc = srslte_b200_rm_rx_batch_dev(ctx, rm.data(), n_cb, pool->d_e.p, pool->llr.p);
+    if (rc) return rc;
+
+    // ---- decode all blocks of all TBs in one batch, CRC after every half iteration ----
+    CU(cudaMemcpyAsync(pool->d_off.p, pool->h_off.p, n_cb * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(pool->d_mode.p, pool->h_mode.p, n_cb, cudaMemcpyHostToDevice, st));
+    CU(pool->d_out.reserve((size_t)n_cb * 768));
+    CU(pool->d_nit.reserve(n_cb));
+    CU(pool->d_ok.reserve(n_cb));
+    CU(pool->h_out.reserve((size_t)n_cb * 768));
+    CU(pool->h_nit.reserve(n_cb));
+    CU(pool->h_ok.reserve(n_cb));
+    srslte_b200_tdec_batch_t b{};
+    b.n_cb           = n_cb;
+    b.long_cb        = Ks.data();
+    b.input_format   = SRSLTE_B200_INPUT_WORKING;
+    b.in_stride      = kStride;
+    b.out_stride     = 768;
+    b.nof_iterations = max_iterations;
+    b.crc_mode       = SRSLTE_B200_CRC_24B;
+    uint32_t work_len = 0;
+    rc = check_batch(ctx, &b, &work_len);
+    if (rc) return rc;
+    rc = enqueue_decode(ctx, &b, work_len, pool->llr.p, pool->d_out.p, pool->d_nit.p, pool->d_ok.p, st, pool->d_off.p,
+                        pool->d_mode.p);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(pool->h_out.p, pool->d_out.p, (size_t)n_cb * 768, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(pool->h_nit.p, pool->d_nit.p, n_cb, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(pool->h_ok.p, pool->d_ok.p, n_cb, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+
+    // ---- code blocks -> transport blocks.  Like the reference, every block writes its full K/8 bytes at
+    // cb*rlen/8, so a block's CRC bytes are overwritten by the next block and the last block's survive. ----
+    for (uint32_t j = 0; j < n_cb; j++) {
+      const CbJob&      jb = jobs[j];
+      srslte_b200_tb_t& t  = tbs[jb.tb];
+      const uint32_t    rlen = seg[jb.tb].C == 1 ? jb.K : jb.K - 24;
+      std::memcpy(&t.data[jb.cb * rlen / 8], pool->h_out.p + (size_t)j * 768, jb.K / 8);
+      noi[j] = pool->h_nit.p[j];
+      if (pool->h_ok.p[j]) pool->cb_crc[(size_t)t.softbuffer * pool->max_cb + jb.cb] = 1;
+    }
+  }
+
+  // ---- per-TB bookkeeping (sch.c:391-412, 470-488) ----
+  std::vector<float> total_it(n_tb, 0.f);
+  for (uint32_t j = 0; j < n_cb; j++) total_it[jobs[j].tb] += (float)noi[j];
+  for (uint32_t i = 0; i < n_tb; i++) {
+    if (!run[i]) continue;
+    srslte_b200_tb_t& t   = tbs[i];
+    const CbSegm&     s   = seg[i];
+    uint8_t*          crc = pool->cb_crc.data() + (size_t)t.softbuffer * pool->max_cb;
+    bool              all = true;
+    for (uint32_t cb = 0; cb < s.C && all; cb++) all = crc[cb] != 0;
+    pool->tb_crc[t.softbuffer] = all ? 1 : 0;
+    if (!all) {
+      for (uint32_t cb = 0; cb < s.C; cb++)
+        if (crc[cb]) {
+          const uint32_t K = cb < s.C1 ? s.K1 : s.K2, rlen = s.C == 1 ? K : K - 24;
+          std::memcpy(&pool->saved[((size_t)t.softbuffer * pool->max_cb + cb) * 768], &t.data[cb * rlen / 8], rlen / 8);
+        }
+    }
+    t.avg_iterations = total_it[i] / (float)s.C;
+    if (!all) {
+      t.ret = SRSLTE_B200_ERROR;
+      continue;
+    }
+    const uint32_t par_rx = crc24_bytes(kCrc24A, t.data, t.tbs / 8);
+    const uint32_t par_tx = ((uint32_t)t.data[t.tbs / 8] << 16) | ((uint32_t)t.data[t.tbs / 8 + 1] << 8) |
+                            (uint32_t)t.data[t.tbs / 8 + 2];
+    t.ret = (par_rx == par_tx && par_rx) ? SRSLTE_B200_SUCCESS : SRSLTE_B200_ERROR;  // `&& par_rx`: sch.c:481
+  }
   return SRSLTE_B200_SUCCESS;
 }
 

@@ -939,7 +939,9 @@ __global__ void __launch_bounds__(kThreads, 3) tdec_win_kernel(const TdecLaunch 
     uint32_t n    = 0, iters = 0;
     bool     done = false, ok = false;
     int      amax = 0, emax = 0;  // max |A|, max |E| over the code block
-    const int which = a.crc_mode == CRC_24A ? 0 : 1;
+    const uint32_t crc_mode = a.crc_mode_cb ? a.crc_mode_cb[cb] : a.crc_mode;
+    const int      which    = crc_mode == CRC_24A ? 0 : 1;
+    const bool     any_crc  = __any_sync(0xFFFFFFFFu, crc_mode != CRC_NONE);
     do {
       const bool dec2 = (n & 1) != 0, apriori = n > 0;
       // bound on |x|, |y|, |x + y| of this half iteration
@@ -959,12 +961,13 @@ __global__ void __launch_bounds__(kThreads, 3) tdec_win_kernel(const TdecLaunch 
       const int dm = (int)group_max<WH>(r.dmax);
       if (dec2) amax = dm; else emax = dm;
       n++;
-      if (a.crc_mode != CRC_NONE) {
-        decide<W>(c, out, !done && active);
+      if (any_crc) {
+        const bool check = crc_mode != CRC_NONE && !done && active;
+        decide<W>(c, out, check);
         uint32_t crc = 1;
-        if (!done && active && t == 0) crc = crc24_bytes_dev(which, out, c.K / 8);
+        if (check && t == 0) crc = crc24_bytes_dev(which, out, c.K / 8);
         crc = __shfl_sync(0xFFFFFFFFu, crc, grp * WH);
-        if (!done) {
+        if (check) {
           iters = n;
           if (crc == 0) {
             ok   = true;
@@ -973,8 +976,10 @@ __global__ void __launch_bounds__(kThreads, 3) tdec_win_kernel(const TdecLaunch 
         }
       }
     } while (n < a.max_iter && !__all_sync(0xFFFFFFFFu, done || !active));
-    if (a.crc_mode == CRC_NONE) {
+    if (crc_mode == CRC_NONE) {
       decide<W>(c, out, active);
+      iters = n;
+    } else if (!any_crc) {
       iters = n;
     }
     if (active && t == 0) {
@@ -1111,7 +1116,8 @@ __global__ void __launch_bounds__(kThreads) tdec_gen_kernel(const TdecLaunch a)
     uint8_t* out  = a.out + (size_t)cb * a.out_stride;
     uint32_t n    = 0, iters = 0;
     bool     done = false, ok = false;
-    const int which = a.crc_mode == CRC_24A ? 0 : 1;
+    const uint32_t crc_mode = a.crc_mode_cb ? a.crc_mode_cb[cb] : a.crc_mode;
+    const int      which    = crc_mode == CRC_24A ? 0 : 1;
     auto decide_gen = [&]() {
       for (uint32_t j = 0; j < c.K / 8; j++) {
         uint32_t byte = 0;
@@ -1122,7 +1128,7 @@ __global__ void __launch_bounds__(kThreads) tdec_gen_kernel(const TdecLaunch a)
     do {
       gen_half_iteration(c, (n & 1) != 0, n > 0);
       n++;
-      if (a.crc_mode != CRC_NONE && !done && active) {
+      if (crc_mode != CRC_NONE && !done && active) {
         decide_gen();
         iters = n;
         if (crc24_bytes_dev(which, out, c.K / 8) == 0) {
@@ -1131,7 +1137,7 @@ __global__ void __launch_bounds__(kThreads) tdec_gen_kernel(const TdecLaunch a)
         }
       }
     } while (n < a.max_iter && !__all_sync(0xFFFFFFFFu, done || !active));
-    if (a.crc_mode == CRC_NONE) {
+    if (crc_mode == CRC_NONE) {
       if (active) decide_gen();
       iters = n;
     }
@@ -1157,13 +1163,13 @@ __device__ __forceinline__ uint32_t windows_of(uint32_t K)
 __global__ void __launch_bounds__(256) to_internal_kernel(const int16_t* __restrict__ src_all, uint32_t src_stride,
                                                           int16_t* __restrict__ dst_all, uint32_t dst_stride,
                                                           const uint32_t* __restrict__ cb_K, uint32_t uniform_K,
-                                                          uint32_t src_format)
+                                                          uint32_t src_format, const uint64_t* __restrict__ src_off)
 {
   extern __shared__ int16_t stage[];  // natural input of one code block (format 0 only)
   __shared__ uint32_t s_max[3];
   const uint32_t cb = blockIdx.x;
   const uint32_t K  = cb_K ? cb_K[cb] : uniform_K;
-  const int16_t* src = src_all + (size_t)cb * src_stride;
+  const int16_t* src = src_all + (src_off ? (size_t)src_off[cb] : (size_t)cb * src_stride);
   int16_t*       dst = dst_all + (size_t)cb * dst_stride;
   const uint32_t W = windows_of(K);
   if (W == 0) {
@@ -1314,9 +1320,9 @@ cudaError_t tdec_launch(int W, const TdecGeometry& g, const TdecLaunch& a, cudaS
   return cudaGetLastError();
 }
 
-cudaError_t to_internal_launch(const int16_t* src, uint32_t src_stride, int src_format, int16_t* dst,
-                               uint32_t dst_stride, const uint32_t* cb_K, uint32_t uniform_K, uint32_t n_cb,
-                               cudaStream_t s)
+cudaError_t to_internal_launch(const int16_t* src, uint32_t src_stride, const uint64_t* src_off, int src_format,
+                               int16_t* dst, uint32_t dst_stride, const uint32_t* cb_K, uint32_t uniform_K,
+                               uint32_t n_cb, cudaStream_t s)
 {
   if (n_cb == 0) return cudaSuccess;
   static bool attr_set = false;
@@ -1327,7 +1333,8 @@ cudaError_t to_internal_launch(const int16_t* src, uint32_t src_stride, int src_
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  to_internal_kernel<<<n_cb, 256, smem, s>>>(src, src_stride, dst, dst_stride, cb_K, uniform_K, (uint32_t)src_format);
+  to_internal_kernel<<<n_cb, 256, smem, s>>>(src, src_stride, dst, dst_stride, cb_K, uniform_K, (uint32_t)src_format,
+                                             src_off);
   return cudaGetLastError();
 }
 

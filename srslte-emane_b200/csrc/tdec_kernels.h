@@ -32,6 +32,7 @@ struct TdecLaunch {
   uint32_t*       counter;     // device work counter, zeroed by the launcher
   uint32_t        max_iter;    // half-iteration cap
   uint32_t        crc_mode;
+  const uint8_t*  crc_mode_cb; // [n_cb] per-block CrcMode overriding crc_mode (device, nullable)
   int16_t*        ws_ae;       // extrinsic work arrays, sized by tdec_geometry()
   uint32_t*       ws_chk;      // beta checkpoints, sized by tdec_geometry()
   uint32_t        force_exact; // 1: always run the exact saturating variant (tests)
@@ -57,9 +58,10 @@ uint32_t internal_len(uint32_t K);
 
 // src_format 0: natural (3i+j, tails last); 1: the reference's sub-block soft-buffer layout.
 // One code block per CTA; also records max |sys|, |par0|, |par1| per block for the fast-path proof.
-cudaError_t to_internal_launch(const int16_t* src, uint32_t src_stride, int src_format, int16_t* dst,
-                               uint32_t dst_stride, const uint32_t* cb_K /* device, nullable */, uint32_t uniform_K,
-                               uint32_t n_cb, cudaStream_t s);
+// The source of block i is src + src_off[i] when src_off (device, int16 elements) is given, else src + i*src_stride.
+cudaError_t to_internal_launch(const int16_t* src, uint32_t src_stride, const uint64_t* src_off, int src_format,
+                               int16_t* dst, uint32_t dst_stride, const uint32_t* cb_K /* device, nullable */,
+                               uint32_t uniform_K, uint32_t n_cb, cudaStream_t s);
 
 // rate de-matching: work[tab[i mod N]] += e[i], i < E, wrapping int16.
 struct RmItem {

@@ -1,0 +1,105 @@
+"""Transport-block path on the GPU (rate de-matching -> decode -> CRC -> TB assembly, HARQ) against the
+golden vectors produced by the reference's srslte_dlsch_decode2 and against the oracle.  B200 only."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_libs as ol
+
+pytestmark = pytest.mark.gpu
+
+
+def _cases(g, prefix):
+    return sorted({k.split("_")[0] for k in g if k.startswith(prefix)}, key=lambda s: int(s[1:]))
+
+
+def test_transport_block_golden_with_harq(ctx, golden):
+    """BASELINE config 2 (TBS 75376 = 13 x K=5824, 64QAM) and smaller TBs, rv 0 then rv 2 on the same
+    soft buffer: return code, bytes, iteration count and per-block CRC flags equal the reference's."""
+    g = golden["tb_vectors"]
+    cases = _cases(g, "t")
+    pool = ctx.harq_pool(len(cases), 13)
+    for sbi, c in enumerate(cases):
+        tbs, qm, G, max_it = (int(x) for x in g[f"{c}_par"])
+        seg = ol.PortCbsegm()
+        ol.port().port_cbsegm(C.byref(seg), tbs)
+        pool.reset(sbi)
+        for rv in (0, 2):
+            (ret, data, avg), = ctx.decode_tb_batch(pool, [dict(tbs=tbs, qm=qm, rv=rv, e_bits=g[f"{c}_rv{rv}_llr"],
+                                                                softbuffer=sbi)], max_it)
+            want_rc, want_its = (int(x) for x in g[f"{c}_rv{rv}_res"])
+            assert ret == want_rc, (c, rv)
+            assert round(avg * seg.C) == want_its, (c, rv, avg)
+            assert np.array_equal(data[: tbs // 8 + 3], g[f"{c}_rv{rv}_out"]), (c, rv)
+            assert np.array_equal(pool.cb_crc(sbi, seg.C), g[f"{c}_rv{rv}_cbcrc"]), (c, rv)
+            if ret == 0:
+                assert np.array_equal(data[: tbs // 8], g[f"{c}_data"])
+    pool.close()
+
+
+def test_many_transport_blocks_in_one_batch_vs_oracle(ctx, vec):
+    """BASELINE config 5 shape: many UL-like TBs of different sizes in ONE call, each against port_decode_tb."""
+    P = ol.port()
+    rng = np.random.default_rng(8)
+    sizes = [(2216, 4, 4800), (6200, 4, 9600), (14112, 4, 28800), (4584, 4, 7200), (1000, 2, 2400), (36696, 6, 60000),
+             (3624, 4, 5760), (75376, 6, 90000)]
+    tbs_list, want = [], []
+    dec = P.port_tdec_new()
+    for i, (tbs, qm, G) in enumerate(sizes * 3):
+        seg = ol.PortCbsegm()
+        assert P.port_cbsegm(C.byref(seg), tbs) == 0 and seg.F == 0
+        # build the TB: payload + CRC24A, segmentation with CRC24B, encode + rate match per block (36.212 5.1-5.3)
+        payload = rng.integers(0, 2, tbs, dtype=np.uint8)
+        tb = vec.attach_crc(vec.CRC24A, payload[None, :])[0]
+        e_parts, pos = [], 0
+        Gp, gamma = G // qm, (G // qm) % seg.C
+        for cb in range(seg.C):
+            K = seg.K1 if cb < seg.C1 else seg.K2
+            rlen = K if seg.C == 1 else K - 24
+            blk = tb[pos:pos + rlen]
+            pos += rlen
+            if seg.C > 1:
+                blk = vec.attach_crc(vec.CRC24B, blk[None, :])[0]
+            E = qm * (Gp // seg.C) if cb <= seg.C - gamma - 1 else qm * ((Gp + seg.C - 1) // seg.C)   # encoder's rule
+            e_parts.append(vec.rate_match(vec.turbo_encode(blk[None, :]), E, 0)[0])
+        e = np.concatenate(e_parts)
+        assert e.size == G
+        sigma = (0.0, 0.5, 0.8)[i % 3]
+        llr = vec.awgn_llr(e, sigma, 100, rng)
+        sb = ol.PortSoftbuffer()
+        P.port_softbuffer_init(C.byref(sb), seg.C)
+        out = np.zeros(tbs // 8 + 8, np.uint8)
+        avg = C.c_float()
+        noi = np.zeros(seg.C, np.uint32)
+        rc = P.port_decode_tb(dec, C.byref(sb), tbs, qm, 0, G, llr, out, 8, C.byref(avg), noi)
+        want.append((rc, out[: tbs // 8 + 3].copy(), avg.value, np.packbits(payload)))
+        P.port_softbuffer_free(C.byref(sb))
+        tbs_list.append(dict(tbs=tbs, qm=qm, rv=0, e_bits=llr, softbuffer=i))
+    P.port_tdec_free(dec)
+    pool = ctx.harq_pool(len(tbs_list), 13)
+    got = ctx.decode_tb_batch(pool, tbs_list, 8)
+    n_ok = 0
+    for i, ((ret, data, avg), (rc, out, wavg, payload)) in enumerate(zip(got, want)):
+        tbs = tbs_list[i]["tbs"]
+        assert ret == rc, i
+        assert abs(avg - wavg) < 1e-6, (i, avg, wavg)
+        assert np.array_equal(data[: tbs // 8 + 3], out), i
+        if ret == 0:
+            n_ok += 1
+            assert np.array_equal(data[: tbs // 8], payload)
+    assert n_ok >= len(want) // 2     # the clean and the moderate-noise thirds decode
+    pool.close()
+
+
+def test_tb_argument_errors(ctx):
+    pool = ctx.harq_pool(1, 2)
+    e = np.zeros(1000, np.int16)
+    # more code blocks than the soft buffer holds -> -2; tbs 0 -> 0 (decode_tb returns SUCCESS for empty TBs)
+    (ret, _, _), = ctx.decode_tb_batch(pool, [dict(tbs=36696, qm=6, rv=0, e_bits=np.zeros(60000, np.int16), softbuffer=0)], 4)
+    assert ret == -2
+    (ret, _, _), = ctx.decode_tb_batch(pool, [dict(tbs=0, qm=2, rv=0, e_bits=e, softbuffer=0)], 4)
+    assert ret == 0
+    (ret, _, _), = ctx.decode_tb_batch(pool, [dict(tbs=1000, qm=2, rv=0, e_bits=e, softbuffer=5)], 4)
+    assert ret == -2
+    pool.close()
