@@ -1,0 +1,143 @@
+/*
+ * srslte_b200_compat.h -- the reference's own entry points for this path, exported unchanged by
+ * libsrslte_b200.so so that code written against srsLTE's headers relinks without source changes.
+ *
+ * Every function below keeps the reference's name, argument meaning, return convention and struct
+ * layout; each is a thin batch-of-one wrapper over the batched C ABI in srslte_b200.h and runs on the GPU
+ * (device chosen by the environment variable SRSLTE_B200_DEVICE, default 0).  There is no CPU path:
+ * *_init fails with -1 and prints to stderr when no CUDA device is usable.
+ *
+ * Struct layouts are restated here (not copied) and are checked against the compiled reference by
+ * tests/test_compat_abi.py (sizeof / offsetof through oracle/_ref).
+ *
+ * Reference declarations mirrored (paths under the reference tree, lib/include/srslte/phy/...):
+ *   fec/turbodecoder.h:63-135      srslte_tdec_t and the srslte_tdec_* functions
+ *   fec/turbodecoder_impl.h:28-40  srslte_tdec_impl_type_t
+ *   fec/tc_interl.h:36-40          srslte_tc_interl_t
+ *   fec/rm_turbo.h:55-93           srslte_rm_turbo_gentables / free_tables / rx_lut / rx_lut_
+ *   fec/softbuffer.h:37-43         srslte_softbuffer_rx_t
+ *   phch/sch.c:429-500             decode_tb (static in the reference; exported here as
+ *                                  srslte_b200_sch_decode_tb for the 10-line patch in INTEGRATION.md)
+ *
+ * Not provided (out of scope): the experimental 8-bit decoders.  srslte_tdec_*_8bit and
+ * srslte_rm_turbo_rx_lut_8bit exist so that callers link, print an error and fail.
+ */
+#ifndef SRSLTE_B200_COMPAT_H
+#define SRSLTE_B200_COMPAT_H
+
+#include <stdbool.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef SRSLTE_API
+#define SRSLTE_API __attribute__((visibility("default")))
+#endif
+
+#ifndef SRSLTE_SUCCESS
+#define SRSLTE_SUCCESS 0
+#define SRSLTE_ERROR -1
+#define SRSLTE_ERROR_INVALID_INPUTS -2
+#endif
+
+#define SRSLTE_NOF_TC_CB_SIZES 188
+#define SRSLTE_TCOD_MAX_LEN_CB 6144
+#define SRSLTE_TDEC_NOF_AUTO_MODES_8 2
+#define SRSLTE_TDEC_NOF_AUTO_MODES_16 3
+#define SOFTBUFFER_SIZE 18600
+
+typedef enum {
+  SRSLTE_TDEC_AUTO = 0,
+  SRSLTE_TDEC_GENERIC,
+  SRSLTE_TDEC_SSE,
+  SRSLTE_TDEC_SSE_WINDOW,
+  SRSLTE_TDEC_NEON_WINDOW,
+  SRSLTE_TDEC_AVX_WINDOW,
+  SRSLTE_TDEC_SSE8_WINDOW,
+  SRSLTE_TDEC_AVX8_WINDOW,
+  SRSLTE_TDEC_NOF_IMP
+} srslte_tdec_impl_type_t;
+
+typedef enum { SRSLTE_TDEC_8, SRSLTE_TDEC_16 } srslte_tdec_llr_type_t;
+
+typedef struct {
+  uint16_t* forward;
+  uint16_t* reverse;
+  uint32_t  max_long_cb;
+} srslte_tc_interl_t;
+
+/* Same size and field offsets as the reference's handle (callers embed it by value inside srslte_sch_t).
+ * This library keeps its GPU context in dec16_hdlr[0] and a pinned staging buffer in input_conv; the work
+ * arrays app1..parity1 and the interleaver tables stay NULL (the GPU computes the QPP on the fly).          */
+typedef struct {
+  uint32_t max_long_cb;
+  void*    dec8_hdlr[SRSLTE_TDEC_NOF_AUTO_MODES_8];
+  void*    dec16_hdlr[SRSLTE_TDEC_NOF_AUTO_MODES_16];
+  void*    dec8[SRSLTE_TDEC_NOF_AUTO_MODES_8];
+  void*    dec16[SRSLTE_TDEC_NOF_AUTO_MODES_16];
+  int      nof_blocks8[SRSLTE_TDEC_NOF_AUTO_MODES_8];
+  int      nof_blocks16[SRSLTE_TDEC_NOF_AUTO_MODES_16];
+  void*    app1;
+  void*    app2;
+  void*    ext1;
+  void*    ext2;
+  void*    syst0;
+  void*    parity0;
+  void*    parity1;
+  void*    input_conv;
+  bool     force_not_sb;
+  srslte_tdec_impl_type_t dec_type;
+  srslte_tdec_llr_type_t  current_llr_type;
+  uint32_t current_dec;
+  uint32_t current_long_cb;
+  uint32_t current_inter_idx;
+  int      current_cbidx;
+  srslte_tc_interl_t interleaver[4][SRSLTE_NOF_TC_CB_SIZES];
+  int      n_iter;
+} srslte_tdec_t;
+
+typedef struct {
+  uint32_t  max_cb;
+  int16_t** buffer_f;
+  uint8_t** data;
+  bool*     cb_crc;
+  bool      tb_crc;
+} srslte_softbuffer_rx_t;
+
+/* ---- turbodecoder.h:97-135 ---- */
+SRSLTE_API int      srslte_tdec_init(srslte_tdec_t* h, uint32_t max_long_cb);
+SRSLTE_API int      srslte_tdec_init_manual(srslte_tdec_t* h, uint32_t max_long_cb, srslte_tdec_impl_type_t dec_type);
+SRSLTE_API void     srslte_tdec_free(srslte_tdec_t* h);
+SRSLTE_API void     srslte_tdec_force_not_sb(srslte_tdec_t* h);
+SRSLTE_API int      srslte_tdec_new_cb(srslte_tdec_t* h, uint32_t long_cb);
+SRSLTE_API int      srslte_tdec_get_nof_iterations(srslte_tdec_t* h);
+SRSLTE_API uint32_t srslte_tdec_autoimp_get_subblocks(uint32_t long_cb);
+SRSLTE_API uint32_t srslte_tdec_autoimp_get_subblocks_8bit(uint32_t long_cb);
+SRSLTE_API void     srslte_tdec_iteration(srslte_tdec_t* h, int16_t* input, uint8_t* output);
+SRSLTE_API int      srslte_tdec_run_all(srslte_tdec_t* h, int16_t* input, uint8_t* output, uint32_t nof_iterations,
+                                        uint32_t long_cb);
+SRSLTE_API void     srslte_tdec_iteration_8bit(srslte_tdec_t* h, int8_t* input, uint8_t* output);
+SRSLTE_API int      srslte_tdec_run_all_8bit(srslte_tdec_t* h, int8_t* input, uint8_t* output, uint32_t nof_iterations,
+                                             uint32_t long_cb);
+
+/* ---- rm_turbo.h:55-93 (receive side) ---- */
+SRSLTE_API void srslte_rm_turbo_gentables(void);
+SRSLTE_API void srslte_rm_turbo_free_tables(void);
+SRSLTE_API int  srslte_rm_turbo_rx_lut(int16_t* input, int16_t* output, uint32_t in_len, uint32_t cb_idx, uint32_t rv_idx);
+SRSLTE_API int  srslte_rm_turbo_rx_lut_(int16_t* input, int16_t* output, uint32_t in_len, uint32_t cb_idx,
+                                        uint32_t rv_idx, bool enable_input_tdec);
+SRSLTE_API int  srslte_rm_turbo_rx_lut_8bit(int8_t* input, int8_t* output, uint32_t in_len, uint32_t cb_idx,
+                                            uint32_t rv_idx);
+
+/* ---- sch.c:429-500 decode_tb, with the host-resident soft buffer the MAC owns ---- */
+/* Returns 0 / -1 (CRC failure) / -2 (bad arguments) like decode_tb; *avg_iterations = q->avg_iterations.   */
+SRSLTE_API int srslte_b200_sch_decode_tb(srslte_softbuffer_rx_t* softbuffer, uint32_t tbs, uint32_t Qm, uint32_t rv,
+                                         uint32_t nof_e_bits, int16_t* e_bits, uint8_t* data, uint32_t max_iterations,
+                                         float* avg_iterations);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRSLTE_B200_COMPAT_H */

@@ -106,7 +106,7 @@ struct srslte_b200_ctx {
   DevBuf<uint8_t> d_out[2], d_nit[2], d_crc[2];
   cudaEvent_t  ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   // rate-dematching tables
-  std::map<uint32_t, uint32_t> rm_tab_off;  // key = K*4+rv -> offset in the pool
+  std::map<uint32_t, uint32_t> rm_tab_off;  // key = ((K*4+rv)*2 + sb_layout) -> offset in the pool
   std::vector<uint16_t>        rm_pool_host;
   DevBuf<uint16_t>             rm_pool_dev;
   size_t                       rm_pool_uploaded = 0;
@@ -576,8 +576,8 @@ int srslte_b200_tdec_batch_host(srslte_b200_ctx_t* ctx, const srslte_b200_tdec_b
   return SRSLTE_B200_SUCCESS;
 }
 
-int srslte_b200_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_rm_block_t* blocks, uint32_t n_blocks,
-                                const int16_t* e, int16_t* work)
+static int rm_rx_enqueue(srslte_b200_ctx_t* ctx, const srslte_b200_rm_block_t* blocks, uint32_t n_blocks,
+                         const int16_t* e, int16_t* work, bool sb_layout)
 {
   if (!ctx) return SRSLTE_B200_ERROR_INVALID_INPUTS;
   if (n_blocks == 0) return SRSLTE_B200_SUCCESS;
@@ -591,11 +591,11 @@ int srslte_b200_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_rm_blo
     const srslte_b200_rm_block_t& bl = blocks[i];
     if (bl.rv > 3 || cb_index_exact(bl.long_cb) < 0)
       return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "block %u: invalid K=%u or rv=%u", i, bl.long_cb, bl.rv);
-    const uint32_t key = bl.long_cb * 4 + bl.rv;
+    const uint32_t key = (bl.long_cb * 4 + bl.rv) * 2 + (sb_layout ? 1u : 0u);
     auto           it  = ctx->rm_tab_off.find(key);
     if (it == ctx->rm_tab_off.end()) {
       std::vector<uint16_t> t;
-      rm_rx_table(bl.long_cb, bl.rv, true, t);
+      rm_rx_table(bl.long_cb, bl.rv, sb_layout, t);
       const uint32_t off = (uint32_t)ctx->rm_pool_host.size();
       ctx->rm_pool_host.insert(ctx->rm_pool_host.end(), t.begin(), t.end());
       it = ctx->rm_tab_off.emplace(key, off).first;
@@ -626,6 +626,12 @@ int srslte_b200_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_rm_blo
   }
   ctx->launches++;
   return SRSLTE_B200_SUCCESS;
+}
+
+int srslte_b200_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_rm_block_t* blocks, uint32_t n_blocks,
+                                const int16_t* e, int16_t* work)
+{
+  return rm_rx_enqueue(ctx, blocks, n_blocks, e, work, true);
 }
 
 }  // extern "C"
@@ -884,6 +890,306 @@ int srslte_b200_decode_tb_batch(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t*
     t.ret = (par_rx == par_tx && par_rx) ? SRSLTE_B200_SUCCESS : SRSLTE_B200_ERROR;  // `&& par_rx`: sch.c:481
   }
   return SRSLTE_B200_SUCCESS;
+}
+
+}  // extern "C"
+
+// =====================================================================================================
+// The reference's own entry points (include/srslte_b200_compat.h): batch-of-one wrappers.
+// =====================================================================================================
+#include "../../include/srslte_b200_compat.h"
+
+#include <mutex>
+
+namespace {
+
+int compat_device()
+{
+  const char* e = getenv("SRSLTE_B200_DEVICE");
+  return e ? atoi(e) : 0;
+}
+
+// process-wide context for the handle-less entry points (rate de-matching, decode_tb)
+std::mutex           g_mu;
+srslte_b200_ctx*     g_ctx  = nullptr;
+srslte_b200_harq_pool* g_pool = nullptr;  // one soft buffer of 13+ blocks, grown on demand
+DevBuf<int16_t>      g_d_e, g_d_work;
+
+srslte_b200_ctx* global_ctx()
+{
+  if (!g_ctx && srslte_b200_ctx_create(&g_ctx, compat_device()) != SRSLTE_B200_SUCCESS) g_ctx = nullptr;
+  return g_ctx;
+}
+
+struct TdecPriv {  // what srslte_tdec_t::dec16_hdlr[0] points to
+  srslte_b200_ctx* ctx    = nullptr;
+  int16_t*         stage  = nullptr;  // pinned: the natural-order input latched at the first iteration
+  uint8_t*         out    = nullptr;  // pinned
+};
+
+int tdec_decode(srslte_tdec_t* h, const int16_t* input, uint8_t* output, uint32_t nof_iterations)
+{
+  TdecPriv*      pv = static_cast<TdecPriv*>(h->dec16_hdlr[0]);
+  const uint32_t K  = h->current_long_cb;
+  if (!pv || cb_index_exact(K) < 0) {
+    fprintf(stderr, "srslte_b200: invalid code block length %u\n", K);
+    return SRSLTE_ERROR;
+  }
+  const bool natural = h->force_not_sb || nof_windows(K) == 0;
+  srslte_b200_tdec_batch_t b{};
+  b.n_cb            = 1;
+  b.uniform_long_cb = K;
+  b.input_format    = natural ? SRSLTE_B200_INPUT_NATURAL : SRSLTE_B200_INPUT_WORKING;
+  b.in_stride       = ((natural ? 3 * K + 12 : working_len(K)) + 1u) & ~1u;
+  b.out_stride      = K / 8;
+  b.nof_iterations  = nof_iterations;
+  b.crc_mode        = SRSLTE_B200_CRC_NONE;
+  int rc = srslte_b200_tdec_batch_host(pv->ctx, &b, input, pv->out, nullptr, nullptr);
+  if (rc) {
+    fprintf(stderr, "srslte_b200: decode failed (%d): %s\n", rc, srslte_b200_last_error(pv->ctx));
+    return SRSLTE_ERROR;
+  }
+  std::memcpy(output, pv->out, K / 8);
+  return SRSLTE_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+int srslte_tdec_init(srslte_tdec_t* h, uint32_t max_long_cb) { return srslte_tdec_init_manual(h, max_long_cb, SRSLTE_TDEC_AUTO); }
+
+int srslte_tdec_init_manual(srslte_tdec_t* h, uint32_t max_long_cb, srslte_tdec_impl_type_t dec_type)
+{
+  if (!h) return SRSLTE_ERROR;
+  std::memset(h, 0, sizeof(*h));
+  if (dec_type != SRSLTE_TDEC_AUTO) {
+    // the manual modes select one specific CPU SIMD decoder; only the AUTO 16-bit behaviour is reproduced
+    fprintf(stderr, "srslte_b200: Error decoder %d not supported (AUTO only)\n", (int)dec_type);
+    return SRSLTE_ERROR;
+  }
+  if (max_long_cb > SRSLTE_TCOD_MAX_LEN_CB) return SRSLTE_ERROR;
+  TdecPriv* pv = new TdecPriv();
+  if (srslte_b200_ctx_create(&pv->ctx, compat_device()) != SRSLTE_B200_SUCCESS) {
+    delete pv;
+    return SRSLTE_ERROR;  // loud message already printed: no CPU fallback
+  }
+  pv->stage = static_cast<int16_t*>(srslte_b200_host_alloc(sizeof(int16_t) * (3 * (SRSLTE_TCOD_MAX_LEN_CB + 32) + 16)));
+  pv->out   = static_cast<uint8_t*>(srslte_b200_host_alloc(SRSLTE_TCOD_MAX_LEN_CB / 8));
+  if (!pv->stage || !pv->out) {
+    srslte_b200_ctx_destroy(pv->ctx);
+    delete pv;
+    return SRSLTE_ERROR;
+  }
+  h->max_long_cb      = max_long_cb;
+  h->dec_type         = dec_type;
+  h->dec16_hdlr[0]    = pv;
+  h->nof_blocks16[0]  = 1;   // what the reference's three AUTO decoders report (generic, 8-window, 16-window)
+  h->nof_blocks16[1]  = 8;
+  h->nof_blocks16[2]  = 16;
+  h->current_cbidx    = -1;
+  h->current_llr_type = SRSLTE_TDEC_16;
+  return SRSLTE_SUCCESS;
+}
+
+void srslte_tdec_free(srslte_tdec_t* h)
+{
+  if (!h) return;
+  if (TdecPriv* pv = static_cast<TdecPriv*>(h->dec16_hdlr[0])) {
+    srslte_b200_ctx_destroy(pv->ctx);
+    srslte_b200_host_free(pv->stage);
+    srslte_b200_host_free(pv->out);
+    delete pv;
+  }
+  std::memset(h, 0, sizeof(*h));  // turbodecoder.c:376
+}
+
+void srslte_tdec_force_not_sb(srslte_tdec_t* h) { h->force_not_sb = true; }
+
+int srslte_tdec_new_cb(srslte_tdec_t* h, uint32_t long_cb)
+{
+  if (long_cb > h->max_long_cb) {
+    fprintf(stderr, "TDEC was initialized for max_long_cb=%d\n", h->max_long_cb);
+    return -1;
+  }
+  h->n_iter          = 0;
+  h->current_long_cb = long_cb;
+  h->current_cbidx   = cb_index_ceil(long_cb);
+  if (h->current_cbidx < 0) {
+    fprintf(stderr, "Invalid CB length %d\n", long_cb);
+    return -1;
+  }
+  return 0;
+}
+
+int srslte_tdec_get_nof_iterations(srslte_tdec_t* h) { return h->n_iter; }
+
+uint32_t srslte_tdec_autoimp_get_subblocks(uint32_t long_cb) { return (uint32_t)nof_windows(long_cb); }
+
+uint32_t srslte_tdec_autoimp_get_subblocks_8bit(uint32_t long_cb)
+{
+  if (!(long_cb % 32) && long_cb > 2048) return 32;
+  if (!(long_cb % 16) && long_cb > 800) return 16;
+  if (!(long_cb % 8) && long_cb > 400) return 8;
+  return 0;
+}
+
+// One more half iteration + hard decision.  The GPU kernel decodes a block in one launch, so the n-th call
+// re-runs n half iterations from the unchanged input (deterministic, therefore identical to iterating).
+void srslte_tdec_iteration(srslte_tdec_t* h, int16_t* input, uint8_t* output)
+{
+  if (h->current_cbidx < 0) return;  // turbodecoder.c:541
+  TdecPriv* pv = static_cast<TdecPriv*>(h->dec16_hdlr[0]);
+  if (!pv) return;
+  const uint32_t K  = h->current_long_cb;
+  const int      W  = nof_windows(K);
+  const bool natural = h->force_not_sb || W == 0;
+  h->current_dec     = W == 16 ? 2 : W == 8 ? 1 : 0;
+  const int16_t* src = input;
+  if (natural) {
+    // the reference latches the input at the first iteration (extract_input) and ignores it afterwards
+    if (h->n_iter == 0) std::memcpy(pv->stage, input, sizeof(int16_t) * (3 * K + 12));
+    src = pv->stage;
+  } else if (h->n_iter == 0) {
+    // sub-block mode: the reference copies the tail samples into the caller's pads (turbodecoder_iter.h:56-65)
+    for (uint32_t i = K; i < K + 3; i++) {
+      input[i]                = input[3 * (K + 32) + 2 * (i - K)];
+      input[(K + 32) + i]     = input[3 * (K + 32) + 2 * (i - K) + 1];
+      input[2 * (K + 32) + i] = input[3 * (K + 32) + 6 + 2 * (i - K) + 1];
+    }
+  }
+  h->n_iter++;
+  tdec_decode(h, src, output, (uint32_t)h->n_iter);
+}
+
+int srslte_tdec_run_all(srslte_tdec_t* h, int16_t* input, uint8_t* output, uint32_t nof_iterations, uint32_t long_cb)
+{
+  if (srslte_tdec_new_cb(h, long_cb)) return SRSLTE_ERROR;
+  const int W    = nof_windows(long_cb);
+  h->current_dec = W == 16 ? 2 : W == 8 ? 1 : 0;
+  const uint32_t n = nof_iterations ? nof_iterations : 1;  // do { } while (n_iter < nof_iterations)
+  if (tdec_decode(h, input, output, n)) return SRSLTE_ERROR;
+  h->n_iter = (int)n;
+  return SRSLTE_SUCCESS;
+}
+
+void srslte_tdec_iteration_8bit(srslte_tdec_t*, int8_t*, uint8_t*)
+{
+  fprintf(stderr, "srslte_b200: the experimental 8-bit turbo decoder is not provided\n");
+}
+
+int srslte_tdec_run_all_8bit(srslte_tdec_t*, int8_t*, uint8_t*, uint32_t, uint32_t)
+{
+  fprintf(stderr, "srslte_b200: the experimental 8-bit turbo decoder is not provided\n");
+  return SRSLTE_ERROR;
+}
+
+void srslte_rm_turbo_gentables(void) {}   // index tables are built per (K, rv) on first use
+void srslte_rm_turbo_free_tables(void) {}
+
+int srslte_rm_turbo_rx_lut_(int16_t* input, int16_t* output, uint32_t in_len, uint32_t cb_idx, uint32_t rv_idx,
+                            bool enable_input_tdec)
+{
+  if (rv_idx >= 4 || cb_idx >= (uint32_t)kNofCbSizes) {
+    printf("Invalid inputs rv_idx=%d, cb_idx=%d\n", rv_idx, cb_idx);
+    return SRSLTE_ERROR_INVALID_INPUTS;
+  }
+  if (!input || !output) return SRSLTE_ERROR_INVALID_INPUTS;
+  std::lock_guard<std::mutex> lk(g_mu);
+  srslte_b200_ctx* ctx = global_ctx();
+  if (!ctx) return SRSLTE_ERROR;
+  const uint32_t K   = kQpp[cb_idx].K;
+  const uint32_t len = enable_input_tdec ? working_len(K) : 3 * K + 12;
+  if (g_d_e.reserve(in_len + 8) != cudaSuccess || g_d_work.reserve(len + 8) != cudaSuccess) return SRSLTE_ERROR;
+  cudaStream_t st = ctx->stream;
+  if (cudaMemcpyAsync(g_d_e.p, input, in_len * sizeof(int16_t), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(g_d_work.p, output, len * sizeof(int16_t), cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return SRSLTE_ERROR;
+  srslte_b200_rm_block_t bl{K, rv_idx, 0, in_len, 0};
+  if (rm_rx_enqueue(ctx, &bl, 1, g_d_e.p, g_d_work.p, enable_input_tdec)) return SRSLTE_ERROR;
+  if (cudaMemcpyAsync(output, g_d_work.p, len * sizeof(int16_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess)
+    return SRSLTE_ERROR;
+  return SRSLTE_SUCCESS;
+}
+
+int srslte_rm_turbo_rx_lut(int16_t* input, int16_t* output, uint32_t in_len, uint32_t cb_idx, uint32_t rv_idx)
+{
+  return srslte_rm_turbo_rx_lut_(input, output, in_len, cb_idx, rv_idx, true);
+}
+
+int srslte_rm_turbo_rx_lut_8bit(int8_t*, int8_t*, uint32_t, uint32_t, uint32_t)
+{
+  fprintf(stderr, "srslte_b200: the experimental 8-bit path is not provided\n");
+  return SRSLTE_ERROR;
+}
+
+int srslte_b200_sch_decode_tb(srslte_softbuffer_rx_t* sb, uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits,
+                              int16_t* e_bits, uint8_t* data, uint32_t max_iterations, float* avg_iterations)
+{
+  if (!sb || !e_bits || !data) {
+    fprintf(stderr, "Missing inputs: data=%d, softbuffer=%d, e_bits=%d\n", data != 0, sb != 0, e_bits != 0);
+    return SRSLTE_ERROR_INVALID_INPUTS;
+  }
+  CbSegm seg;
+  if (cbsegm(&seg, tbs)) return SRSLTE_ERROR;
+  if (seg.tbs == 0 || seg.C == 0) return SRSLTE_SUCCESS;
+  if (seg.F) {
+    fprintf(stderr, "Error filler bits are not supported. Use standard TBS\n");
+    return SRSLTE_ERROR_INVALID_INPUTS;
+  }
+  if (seg.C > sb->max_cb) {
+    fprintf(stderr, "Error number of CB to decode (%d) exceeds soft buffer size (%d CBs)\n", seg.C, sb->max_cb);
+    return SRSLTE_ERROR_INVALID_INPUTS;
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  srslte_b200_ctx* ctx = global_ctx();
+  if (!ctx) return SRSLTE_ERROR;
+  if (!g_pool || g_pool->max_cb < seg.C) {
+    if (g_pool) srslte_b200_harq_pool_destroy(ctx, g_pool);
+    g_pool = nullptr;
+    if (srslte_b200_harq_pool_create(ctx, 1, std::max(seg.C, 13u), &g_pool)) return SRSLTE_ERROR;
+  }
+  constexpr uint32_t kStride = srslte_b200_harq_pool::kStride;
+  cudaStream_t       st      = ctx->stream;
+  // mirror the MAC-owned soft buffer into the device pool: LLRs of the blocks that will be decoded,
+  // CRC flags and saved payloads of the ones that will be skipped
+  for (uint32_t cb = 0; cb < seg.C; cb++) {
+    g_pool->cb_crc[cb] = sb->cb_crc[cb] ? 1 : 0;
+    if (sb->cb_crc[cb]) {
+      std::memcpy(&g_pool->saved[(size_t)cb * 768], sb->data[cb], 768);
+    } else if (cudaMemcpyAsync(g_pool->llr.p + (size_t)cb * kStride, sb->buffer_f[cb], SOFTBUFFER_SIZE * sizeof(int16_t),
+                               cudaMemcpyHostToDevice, st) != cudaSuccess) {
+      return SRSLTE_ERROR;
+    }
+  }
+  srslte_b200_tb_t t{};
+  t.tbs        = tbs;
+  t.qm         = Qm;
+  t.rv         = rv;
+  t.nof_e_bits = nof_e_bits;
+  t.softbuffer = 0;
+  t.e_bits     = e_bits;
+  t.data       = data;
+  std::vector<uint8_t> was_ok(seg.C);
+  for (uint32_t cb = 0; cb < seg.C; cb++) was_ok[cb] = g_pool->cb_crc[cb];
+  if (srslte_b200_decode_tb_batch(ctx, g_pool, &t, 1, max_iterations)) {
+    fprintf(stderr, "srslte_b200: %s\n", srslte_b200_last_error(ctx));
+    return SRSLTE_ERROR;
+  }
+  // write the HARQ state back where the unchanged callers keep it
+  for (uint32_t cb = 0; cb < seg.C; cb++) {
+    if (!was_ok[cb] &&
+        cudaMemcpyAsync(sb->buffer_f[cb], g_pool->llr.p + (size_t)cb * kStride, SOFTBUFFER_SIZE * sizeof(int16_t),
+                        cudaMemcpyDeviceToHost, st) != cudaSuccess)
+      return SRSLTE_ERROR;
+    sb->cb_crc[cb] = g_pool->cb_crc[cb] != 0;
+    if (!g_pool->tb_crc[0] && g_pool->cb_crc[cb]) std::memcpy(sb->data[cb], &g_pool->saved[(size_t)cb * 768], 768);
+  }
+  if (cudaStreamSynchronize(st) != cudaSuccess) return SRSLTE_ERROR;
+  sb->tb_crc = g_pool->tb_crc[0] != 0;
+  if (avg_iterations) *avg_iterations = t.avg_iterations;
+  return t.ret;
 }
 
 }  // extern "C"

@@ -1,0 +1,55 @@
+"""The struct layouts restated in include/srslte_b200_compat.h equal the reference's (CPU only).
+
+A tiny C program is compiled against OUR header and prints sizeof/offsetof; the numbers are compared with
+the ones the compiled reference reports through oracle/_ref (refh_sizeof_*), or -- when oracle/_ref is not
+available -- with the values recorded from the reference's AVX2 build (SURVEY.md section 7 "ABI")."""
+import os
+import subprocess
+
+import pytest
+
+import oracle_libs as ol
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+PROBE = r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "srslte_b200_compat.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu\n", sizeof(srslte_tdec_t), offsetof(srslte_tdec_t, n_iter),
+         sizeof(srslte_softbuffer_rx_t), offsetof(srslte_tdec_t, interleaver), sizeof(srslte_tc_interl_t));
+  return 0;
+}
+"""
+
+
+def test_struct_layouts_match_reference(tmp_path):
+    src = tmp_path / "probe.c"
+    src.write_text(PROBE)
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    R = ol.ref()
+    if R is not None:
+        want_tdec, want_niter, want_sb = R.refh_sizeof_tdec(), R.refh_offsetof_tdec_n_iter(), R.refh_sizeof_softbuffer_rx()
+    else:
+        want_tdec, want_niter, want_sb = 18264, 18256, 40
+    assert got[0] == want_tdec == 18264
+    assert got[1] == want_niter
+    assert got[2] == want_sb
+    assert got[4] == 24
+
+
+def test_compat_symbols_are_exported(pkg):
+    L = pkg.lib()
+    for name in ("srslte_tdec_init", "srslte_tdec_init_manual", "srslte_tdec_free", "srslte_tdec_force_not_sb",
+                 "srslte_tdec_new_cb", "srslte_tdec_get_nof_iterations", "srslte_tdec_autoimp_get_subblocks",
+                 "srslte_tdec_autoimp_get_subblocks_8bit", "srslte_tdec_iteration", "srslte_tdec_run_all",
+                 "srslte_tdec_iteration_8bit", "srslte_tdec_run_all_8bit", "srslte_rm_turbo_gentables",
+                 "srslte_rm_turbo_free_tables", "srslte_rm_turbo_rx_lut", "srslte_rm_turbo_rx_lut_",
+                 "srslte_rm_turbo_rx_lut_8bit", "srslte_b200_sch_decode_tb"):
+        assert hasattr(L, name), name
+    # host-only entry points work without a GPU
+    assert [L.srslte_tdec_autoimp_get_subblocks(k) for k in (40, 408, 816, 6144)] == [0, 8, 16, 16]
+    assert [L.srslte_tdec_autoimp_get_subblocks_8bit(k) for k in (40, 408, 816, 2112, 6144)] == [0, 8, 16, 32, 32]
