@@ -336,7 +336,7 @@ def main():
         "checksum": chk,
     }
 
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         cores = os.cpu_count() or 1
         sample = min(ne, max(1024, cores * 256))
         llr_np = pin_in.array[:sample].copy()
