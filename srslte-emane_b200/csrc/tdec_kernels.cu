@@ -40,16 +40,17 @@ namespace b200 {
 namespace {
 
 constexpr int      kWarm      = 40;  // win_overlap_len
-constexpr int      kChunk     = 16;  // rows of beta rebuilt at a time (multiple of 4)
+constexpr int      kChunk     = 12;  // rows of beta rebuilt at a time (multiple of 4)
 constexpr int      kThreads   = 128;
-constexpr int      kMaxChunks = 24;  // ceil(384 / 16)
+constexpr int      kBlocksPerSm = 3;
+constexpr int      kMaxChunks = 32;  // ceil(384 / 12)
 // per-warp-slot strides are odd multiples of 128 bytes: warps run in near lock step, and power-of-two
 // strides would send all of them to the same L2 slices / HBM channels at once
 constexpr int      kChkSlotWords = kMaxChunks * 8 * 32 + 32;
 constexpr uint32_t kAeStride16 = 6144 + 64, kAeStride8 = 800 + 32;  // int16 per A or E array
 constexpr int      kMaxL      = 384;
-constexpr int      kPrefetchGroups = 4;  // L2 prefetch distance in row groups
 constexpr int      kExactRows = 4;   // rows next to a known-state boundary always use exact arithmetic
+constexpr int      kStaticFastG = 2978; // 11 * G <= 32767: the fast variant needs no bookkeeping at all
 constexpr int      kMaxFastG  = 5461; // largest per-step metric change the fast variant accepts (6 * G <= 32767)
 constexpr int      kNegInf    = -10000;
 constexpr uint32_t kNegInf2   = 0xD8F0D8F0u;  // (-10000, -10000)
@@ -156,7 +157,7 @@ __device__ __forceinline__ void alpha_step(uint32_t a[8], uint32_t x, uint32_t y
 }
 
 // alpha recursion + a-posteriori output (max over bit-1 branches minus max over bit-0 branches)
-template <bool FAST>
+template <bool FAST, bool TRACK = true>
 __device__ __forceinline__ uint32_t alpha_out_step(uint32_t a[8], const uint32_t bb[8], uint32_t x, uint32_t y,
                                                    uint32_t xy, Range& rm)
 {
@@ -173,7 +174,7 @@ __device__ __forceinline__ uint32_t alpha_out_step(uint32_t a[8], const uint32_t
       M0 = addmax2(bb[i], m[i], M0);
       M1 = addmax2(bb[i], n[i], M1);
     }
-    rm.add2v(M0, M1);
+    if (TRACK) rm.add2v(M0, M1);
     o = wsub2(M1, M0);
   } else {
     m[0] = a[0];            m[1] = sadd2(a[3], y);  m[2] = sadd2(a[4], y);  m[3] = a[7];
@@ -259,24 +260,6 @@ struct RawGroup {
   uint4 a, b, c;  // DEC1: sys, parity, a-priori.  DEC2: b = parity, a / c = gathered low / high halves
 };
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// pull the streaming inputs of row group kg (one 128-byte line per stream and code block) into L2 well
-// ahead of the register prefetch; one lane per code block issues it
-template <int W, bool DEC2>
-__device__ __forceinline__ void prefetch_group_l2(const WinCtx<W>& c, bool apriori, int kg)
-{
-  constexpr int WH = W / 2;
-  if (c.t != 0 || kg < 0 || kg * 4 >= (int)c.L) return;
-  if (!DEC2) {
-    prefetch_l2(c.sys4 + kg * WH);
-    prefetch_l2(c.par04 + kg * WH);
-    if (apriori) prefetch_l2(c.A32 + (kg * 4) * WH);
-  } else {
-    prefetch_l2(c.par14 + kg * WH);
-  }
-}
-
 template <int W, bool DEC2>
 __device__ __forceinline__ void issue_group(const WinCtx<W>& c, bool apriori, int kg, RawGroup& q)
 {
@@ -327,26 +310,38 @@ __device__ __forceinline__ void finish_group(bool apriori, const RawGroup& q, Gr
   }
 }
 
-// one row with the reference's saturating a-priori add (exact rows)
+// one row for the exact helpers: loads issued one row ahead, the reference's saturating a-priori add
+struct RawRow {
+  uint32_t a, b, c;
+};
+
 template <int W>
-__device__ __forceinline__ void load_row_exact(const WinCtx<W>& c, bool dec2, bool apriori, uint32_t k, uint32_t& x,
-                                               uint32_t& y, uint32_t& aux)
+__device__ __forceinline__ void issue_row(const WinCtx<W>& c, bool dec2, bool apriori, uint32_t k, RawRow& q)
 {
   const uint32_t w = pm_word<W>(k, (uint32_t)c.t);
   if (!dec2) {
-    x   = __ldg(reinterpret_cast<const uint32_t*>(c.sys4) + w);
-    y   = __ldg(reinterpret_cast<const uint32_t*>(c.par04) + w);
-    aux = 0;
-    if (apriori) {
-      aux = c.A32[k * (W / 2) + c.t];
-      x   = sadd2(aux, x);
-    }
+    q.a = __ldg(reinterpret_cast<const uint32_t*>(c.sys4) + w);
+    q.b = __ldg(reinterpret_cast<const uint32_t*>(c.par04) + w);
+    q.c = apriori ? c.A32[k * (W / 2) + c.t] : 0u;
   } else {
     uint32_t i_lo, i_hi;
     qpp_pair<W>(c, k, i_lo, i_hi);
     const uint16_t* E16 = reinterpret_cast<const uint16_t*>(c.E32);
-    x   = (uint32_t)E16[i_lo] | ((uint32_t)E16[i_hi] << 16);
-    y   = __ldg(reinterpret_cast<const uint32_t*>(c.par14) + w);
+    q.a = E16[i_lo];
+    q.c = E16[i_hi];
+    q.b = __ldg(reinterpret_cast<const uint32_t*>(c.par14) + w);
+  }
+}
+
+__device__ __forceinline__ void finish_row_exact(bool dec2, bool apriori, const RawRow& q, uint32_t& x, uint32_t& y,
+                                                 uint32_t& aux)
+{
+  y = q.b;
+  if (!dec2) {
+    aux = q.c;
+    x   = apriori ? sadd2(aux, q.a) : q.a;
+  } else {
+    x   = q.a | (q.c << 16);
     aux = x;
   }
 }
@@ -408,10 +403,13 @@ __device__ __noinline__ void beta_rows_exact(const WinCtx<W> c, uint32_t flags, 
 #pragma unroll
   for (int i = 0; i < 8; i++) s[i] = st->s[i];
   Range trk = st->trk;
+  RawRow q;
+  if (k_hi >= k_lo) issue_row<W>(c, dec2, apriori, (uint32_t)k_hi, q);
 #pragma unroll 1
   for (int k = k_hi; k >= k_lo; k--) {
     uint32_t x, y, aux;
-    load_row_exact<W>(c, dec2, apriori, (uint32_t)k, x, y, aux);
+    finish_row_exact(dec2, apriori, q, x, y, aux);
+    if (k > k_lo) issue_row<W>(c, dec2, apriori, (uint32_t)(k - 1), q);
     beta_step<false>(s, x, y, sadd2(x, y));
     if (mode == 1 && (k % kChunk) == 0 && k != 0) {
 #pragma unroll
@@ -443,10 +441,13 @@ __device__ __noinline__ void alpha_rows_exact(const WinCtx<W> c, uint32_t flags,
   for (int i = 0; i < 8; i++) a[i] = st->s[i];
   Range trk = st->trk, rd = st->rd, unused;
   unused.reset();
+  RawRow q;
+  if (k_lo <= k_hi) issue_row<W>(c, dec2, apriori, (uint32_t)k_lo, q);
 #pragma unroll 1
   for (int k = k_lo; k <= k_hi; k++) {
     uint32_t x, y, aux;
-    load_row_exact<W>(c, dec2, apriori, (uint32_t)k, x, y, aux);
+    finish_row_exact(dec2, apriori, q, x, y, aux);
+    if (k < k_hi) issue_row<W>(c, dec2, apriori, (uint32_t)(k + 1), q);
     const int j = mode == 0 ? k_norm0 + (k - k_lo) : k;
     if (mode == 0) {
       alpha_step<false>(a, x, y, sadd2(x, y));
@@ -557,7 +558,7 @@ __device__ __noinline__ HalfResult half_iteration_exact(const WinCtx<W> c, bool 
 
 // ---- FAST variant: wrapping adds fused with max, plus the bookkeeping that proves it equals the exact one
 // G bounds |x|, |y| and |x + y| of every row of this code block in this half iteration.
-template <int W, bool DEC2>
+template <int W, bool DEC2, bool TRACK>
 __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bool apriori, int G)
 {
   constexpr int  WH = W / 2;
@@ -589,7 +590,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
       beta_step<true>(s, g.x[r], g.y[r], wadd2(g.x[r], g.y[r]));
       if ((r & 1) == 0 && (kg | r) != 0) {
         normalize<true>(s);
-        rb.add8(s);
+        if (TRACK) rb.add8(s);
       }
     }
   }
@@ -605,22 +606,36 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
 #pragma unroll
   for (int i = 0; i < 8; i++) s[i] = st.s[i];
   rb = st.trk;
+  {
+    RawGroup q2;
+    if (gtop >= 1) issue_group<W, DEC2>(c, apriori, gtop - 1, q2);
+    auto rows = [&](int kg) {
+#pragma unroll
+      for (int r = 3; r >= 0; r--) {
+        beta_step<true>(s, g.x[r], g.y[r], wadd2(g.x[r], g.y[r]));
+        if (r == 0 && (kg % (kChunk / 4)) == 0 && kg != 0) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) c.chk[((kg / (kChunk / 4) - 1) * 8 + i) * 32] = s[i];
+        }
+        if ((r & 1) == 0 && (kg | r) != 0) {
+          normalize<true>(s);
+          if (TRACK) rb.add8(s);
+        }
+      }
+    };
+    int kg = gtop;
 #pragma unroll 1
-  for (int kg = gtop; kg >= 0; kg--) {
-    finish_group<DEC2>(apriori, q, g);
-    if (kg > 0) issue_group<W, DEC2>(c, apriori, kg - 1, q);
-    prefetch_group_l2<W, DEC2>(c, apriori, kg - kPrefetchGroups);
-#pragma unroll
-    for (int r = 3; r >= 0; r--) {
-      beta_step<true>(s, g.x[r], g.y[r], wadd2(g.x[r], g.y[r]));
-      if (r == 0 && (kg & (kChunk / 4 - 1)) == 0 && kg != 0) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) c.chk[((kg / (kChunk / 4) - 1) * 8 + i) * 32] = s[i];
-      }
-      if ((r & 1) == 0 && (kg | r) != 0) {
-        normalize<true>(s);
-        rb.add8(s);
-      }
+    for (; kg >= 1; kg -= 2) {  // q holds group kg, q2 group kg - 1: every load is issued two groups ahead
+      finish_group<DEC2>(apriori, q, g);
+      if (kg >= 2) issue_group<W, DEC2>(c, apriori, kg - 2, q);
+      rows(kg);
+      finish_group<DEC2>(apriori, q2, g);
+      if (kg >= 3) issue_group<W, DEC2>(c, apriori, kg - 3, q2);
+      rows(kg - 1);
+    }
+    if (kg == 0) {
+      finish_group<DEC2>(apriori, q, g);
+      rows(0);
     }
   }
 
@@ -648,7 +663,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
         alpha_step<true>(a, g.x[r], g.y[r], wadd2(g.x[r], g.y[r]));
         if ((j & 1) == 0 && j != 0) {
           normalize<true>(a);
-          ra.add8(a);
+          if (TRACK) ra.add8(a);
         }
       }
     }
@@ -726,19 +741,18 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
         issue_group<W, DEC2>(c, apriori, kg + 1, q);
       else if (ch + 1 < nchunks)
         issue_group<W, DEC2>(c, apriori, min((min(hi + kChunk, L) - 1) >> 2, gtop), q);  // top fast group of the next chunk
-      prefetch_group_l2<W, DEC2>(c, apriori, kg + kChunk / 4 + kPrefetchGroups);  // rows of the chunks ahead
 #pragma unroll
       for (int r = 0; r < 4; r++) {
         const int      k  = kg * 4 + r;
         const uint4    b0 = c.sm[((k - lo) * 2 + 0) * kThreads];
         const uint4    b1 = c.sm[((k - lo) * 2 + 1) * kThreads];
         const uint32_t bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        uint32_t       o = alpha_out_step<true>(a, bb, g.x[r], g.y[r], wadd2(g.x[r], g.y[r]), rm);
+        uint32_t       o = alpha_out_step<true, TRACK>(a, bb, g.x[r], g.y[r], wadd2(g.x[r], g.y[r]), rm);
         if (W == 8) o = sra1_2(o);  // the 8-window (sse16) decoder halves its output
         store_out<W, DEC2>(c, (uint32_t)k, o, g.aux[r], rd);
         if ((r & 1) == 0) {
           normalize<true>(a);
-          ra.add8(a);
+          if (TRACK) ra.add8(a);
         }
       }
     }
@@ -762,18 +776,26 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
   // away from a normalisation point whose post-normalisation metrics lie in [lo, hi]; one step moves a
   // metric by at most G.
   bool ok = true;
+  if (TRACK) {
 #pragma unroll
-  for (int h = 0; h < 2; h++) {
-    const int bh = h ? hi16(rb.hi) : lo16(rb.hi), bl = h ? hi16(rb.lo) : lo16(rb.lo);
-    const int ah = h ? hi16(ra.hi) : lo16(ra.hi), al = h ? hi16(ra.lo) : lo16(ra.lo);
-    const int mh = h ? hi16(rm.hi) : lo16(rm.hi), ml = h ? hi16(rm.lo) : lo16(rm.lo);
-    ok = ok && (bh + 2 * G <= 32767) && (bl - 2 * G >= -32768) && (bh - bl + 4 * G <= 32767);
-    ok = ok && (ah + 2 * G <= 32767) && (al - 2 * G >= -32768) && (ah - al + 4 * G <= 32767);
-    ok = ok && (bh + ah + 5 * G <= 32767) && (bl + al - 5 * G >= -32768);
-    ok = ok && (mh < ml || mh - ml <= 32767);
+    for (int h = 0; h < 2; h++) {
+      const int bh = h ? hi16(rb.hi) : lo16(rb.hi), bl = h ? hi16(rb.lo) : lo16(rb.lo);
+      const int ah = h ? hi16(ra.hi) : lo16(ra.hi), al = h ? hi16(ra.lo) : lo16(ra.lo);
+      const int mh = h ? hi16(rm.hi) : lo16(rm.hi), ml = h ? hi16(rm.lo) : lo16(rm.lo);
+      ok = ok && (bh + 2 * G <= 32767) && (bl - 2 * G >= -32768) && (bh - bl + 4 * G <= 32767);
+      ok = ok && (ah + 2 * G <= 32767) && (al - 2 * G >= -32768) && (ah - al + 4 * G <= 32767);
+      ok = ok && (bh + ah + 5 * G <= 32767) && (bl + al - 5 * G >= -32768);
+      ok = ok && (mh < ml || mh - ml <= 32767);
+    }
+    // warm-up starts from 8 equal metrics of -10000 and runs at most 3 steps before normalising
+    ok = ok && (G <= kMaxFastG);
+  } else {
+    // Static proof, no bookkeeping: 3 steps after ANY state vector the spread of the 8 metrics is at most
+    // the sum over those steps of (|x| + |y|) <= 3G (every state reaches every state in 3 steps), so after a
+    // normalisation all metrics lie in [-3G, 3G], before it in [-5G, 5G]; beta + alpha + branch <= 11G and the
+    // output magnitude <= 7G.  G <= kStaticFastG = 32767 / 11 makes all of that fit int16.
+    ok = G <= kStaticFastG;
   }
-  // warm-up starts from 8 equal metrics of -10000 and runs at most 3 steps before normalising
-  ok         = ok && (G <= kMaxFastG);
   res.proven = ok;
   return res;
 }
@@ -788,12 +810,15 @@ __device__ void decide(const WinCtx<W>& c, uint8_t* out, bool write)
   constexpr int  WH = W / 2;
   constexpr int  NW = (kMaxL + 31) / 32;  // words per window
   const uint32_t L  = c.L;
-  // bit-string word f (= window * NW + word) of this code block lives in the .x component of beta-chunk
-  // slot f / WH of the group's thread f % WH: only this group's own shared-memory slots are touched
+  // bit-string word f (= window * NW + word) of this code block lives in component f % 4 of beta-chunk
+  // slot f / (4 WH) of the group's thread (f / 4) % WH: only this group's own shared-memory slots are touched
+  static_assert((W * NW + 4 * WH - 1) / (4 * WH) <= 2 * kChunk, "bit strings must fit the beta chunk slots");
   uint32_t* grp_base = reinterpret_cast<uint32_t*>(c.sm - c.t);
-  auto      word     = [&](uint32_t f) -> uint32_t& { return grp_base[((f / WH) * kThreads + (f % WH)) * 4]; };
+  auto      word     = [&](uint32_t f) -> uint32_t& {
+    return grp_base[(((f >> 2) / WH) * kThreads + ((f >> 2) % WH)) * 4 + (f & 3)];
+  };
   uint32_t  acc_lo = 0, acc_hi = 0;
-#pragma unroll 2
+#pragma unroll 4
   for (uint32_t kg = 0; kg * 4 < L; kg++) {
     uint32_t v[4];
 #pragma unroll
@@ -866,7 +891,7 @@ __device__ __forceinline__ uint32_t group_max(uint32_t v)
 }
 
 template <int W>
-__global__ void __launch_bounds__(kThreads, 3) tdec_win_kernel(const TdecLaunch a)
+__global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const TdecLaunch a)
 {
   constexpr int WH  = W / 2;
   constexpr int CBW = 32 / WH;
@@ -926,10 +951,12 @@ __global__ void __launch_bounds__(kThreads, 3) tdec_win_kernel(const TdecLaunch 
     c.tail  = in + 3 * S;
     const uint16_t* meta = reinterpret_cast<const uint16_t*>(in + 3 * S + 16);
     const int smax = meta[0], p0max = meta[1], p1max = meta[2];
-    int16_t* ae = a.ws_ae + ((size_t)slot * CBW + grp) * 2 * KMAX;
+    // development probe (force_exact bit 1): every warp of a CTA row shares workspace slot -> always cache resident
+    const uint32_t ws_slot = (a.force_exact & 2u) ? (slot & 3u) : slot;
+    int16_t* ae = a.ws_ae + ((size_t)ws_slot * CBW + grp) * 2 * KMAX;
     c.A32 = reinterpret_cast<uint32_t*>(ae);
     c.E32 = reinterpret_cast<uint32_t*>(ae + KMAX);
-    c.chk = a.ws_chk + (size_t)slot * kChkSlotWords + lane;
+    c.chk = a.ws_chk + (size_t)ws_slot * kChkSlotWords + lane;
     c.sm  = smem + tid;
 
     for (uint32_t k = 0; k < c.L; k++) c.A32[k * WH + t] = 0;
@@ -950,8 +977,11 @@ __global__ void __launch_bounds__(kThreads, 3) tdec_win_kernel(const TdecLaunch 
       HalfResult r;
       bool       fast_ok = false;
       // the decision must be warp-uniform: the passes below use full-warp shuffles and votes
-      if (__all_sync(0xFFFFFFFFu, a.force_exact == 0 && G <= kMaxFastG)) {
-        r       = dec2 ? half_iteration_fast<W, true>(c, apriori, G) : half_iteration_fast<W, false>(c, apriori, G);
+      if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kStaticFastG)) {
+        r = dec2 ? half_iteration_fast<W, true, false>(c, apriori, G) : half_iteration_fast<W, false, false>(c, apriori, G);
+        fast_ok = true;
+      } else if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kMaxFastG)) {
+        r = dec2 ? half_iteration_fast<W, true, true>(c, apriori, G) : half_iteration_fast<W, false, true>(c, apriori, G);
         fast_ok = __all_sync(0xFFFFFFFFu, r.proven);
       }
       if (!fast_ok) {
