@@ -40,15 +40,17 @@ namespace b200 {
 namespace {
 
 constexpr int      kWarm      = 40;  // win_overlap_len
-constexpr int      kChunk     = 12;  // rows of beta rebuilt at a time (multiple of 4)
+constexpr int      kChunk     = 8;   // rows of beta rebuilt at a time (multiple of 4)
 constexpr int      kThreads   = 128;
 constexpr int      kBlocksPerSm = 3;
-constexpr int      kMaxChunks = 32;  // ceil(384 / 12)
+constexpr int      kMaxChunks = 48;  // ceil(384 / 8)
 // per-warp-slot strides are odd multiples of 128 bytes: warps run in near lock step, and power-of-two
 // strides would send all of them to the same L2 slices / HBM channels at once
 constexpr int      kChkSlotWords = kMaxChunks * 8 * 32 + 32;
 constexpr uint32_t kAeStride16 = 6144 + 64, kAeStride8 = 800 + 32;  // int16 per A or E array
 constexpr int      kMaxL      = 384;
+constexpr int      kRingDepth = 6;   // row groups kept in flight per warp by cp.async (prefetch distance kRingDepth-1)
+constexpr int      kSeqMax    = 384; // entries of a half iteration's fetch sequence (10 + 96 + 11 + 32 + 2*96 at most)
 constexpr int      kExactRows = 4;   // rows next to a known-state boundary always use exact arithmetic
 constexpr int      kStaticFastG = 2978; // 11 * G <= 32767: the fast variant needs no bookkeeping at all
 constexpr int      kMaxFastG  = 5461; // largest per-step metric change the fast variant accepts (6 * G <= 32767)
@@ -225,7 +227,11 @@ struct WinCtx {
                           //  gather / scatter of DEC2)
   uint32_t*       chk;    // checkpoints: [(c*8 + i)*32], already offset by lane
   uint4*          sm;     // chunk of beta: [(s*2 + h)*kThreads], already offset by tid
-  const uint32_t* qtab;   // per-warp table in shared memory: pi(k) as row | window << 16, k < L
+  const uint16_t* qtab;   // per-warp table in shared memory: pi(k) as row | window << 9, k < L
+  uint4*          ring;   // per-warp cp.async ring: [kRingDepth][3 planes][32 lanes], already offset by lane
+  const uint8_t*  seq;    // per-warp fetch sequence of a half iteration: row-group index, or 0x80 | chunk (checkpoint)
+  uint32_t        n_seq;
+  int             lane;
 };
 
 // pair-major layout: int16 index of (row k, window d) and 32-bit word index of (row k, thread t)
@@ -245,7 +251,7 @@ __device__ __forceinline__ uint32_t pm_word(uint32_t k, uint32_t t)
 template <int W>
 __device__ __forceinline__ void qpp_pair(const WinCtx<W>& c, uint32_t k, uint32_t& i_lo, uint32_t& i_hi)
 {
-  const uint32_t q = c.qtab[k], row = q & 0xFFFFu, w0 = q >> 16;
+  const uint32_t q = c.qtab[k], row = q & 0x1FFu, w0 = q >> 9;
   i_lo = row * W + ((w0 + c.base_lo + c.inc_lo * k) & (W - 1));
   i_hi = row * W + ((w0 + c.base_hi + c.inc_hi * k) & (W - 1));
 }
@@ -255,47 +261,102 @@ struct Group {
   uint32_t x[4], y[4], aux[4];
 };
 
-// the loads of one row group, issued one group ahead of their use (software prefetch)
-struct RawGroup {
-  uint4 a, b, c;  // DEC1: sys, parity, a-priori.  DEC2: b = parity, a / c = gathered low / high halves
+// ---- cp.async ring: the inputs of the next kRingDepth-1 row groups are always in flight -------------------
+// Register prefetch cannot go deeper than one group (all loads of a loop share one scoreboard slot, so waiting
+// for the oldest also waits for the newest); cp.async groups are counted separately and cost no registers.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void* s, const void* g)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* s, const void* g)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct RingPos {
+  uint32_t head, head_slot;  // next sequence entry to issue and the slot it goes to
+  uint32_t tail_slot;        // slot of the next entry to consume
 };
 
-template <int W, bool DEC2>
-__device__ __forceinline__ void issue_group(const WinCtx<W>& c, bool apriori, int kg, RawGroup& q)
+// issue the copies of sequence entry pos.head (nothing when the sequence is exhausted) and close the group
+template <int W>
+__device__ __forceinline__ void ring_issue(const WinCtx<W>& c, bool dec2, bool apriori, RingPos& pos)
 {
   constexpr int WH = W / 2;
-  if (!DEC2) {
-    q.a = __ldg(c.sys4 + kg * WH + c.t);
-    q.b = __ldg(c.par04 + kg * WH + c.t);
-    if (apriori) {
-      const uint32_t* ap = c.A32 + (kg * 4) * WH + c.t;
-      q.c = make_uint4(ap[0], ap[WH], ap[2 * WH], ap[3 * WH]);
-    }
-  } else {
-    q.b = __ldg(c.par14 + kg * WH + c.t);
-    const uint16_t* E16 = reinterpret_cast<const uint16_t*>(c.E32);
-    uint32_t        lo[4], hi[4];
+  if (pos.head < c.n_seq) {
+    const uint32_t e    = c.seq[pos.head];
+    uint4*         slot = c.ring + pos.head_slot * 96;
+    if (e & 0x80u) {  // beta checkpoint of chunk (e & 0x7f): 8 words per lane
+      const uint32_t* src = c.chk + ((e & 0x7Fu) * 8) * 32;
+      uint32_t*       dst = reinterpret_cast<uint32_t*>(slot - c.lane) + c.lane;
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-      uint32_t i_lo, i_hi;
-      qpp_pair<W>(c, (uint32_t)(kg * 4 + r), i_lo, i_hi);  // only called for groups that are entirely < L
-      lo[r] = E16[i_lo];
-      hi[r] = E16[i_hi];
+      for (int i = 0; i < 8; i++) cp_async4(dst + i * 32, src + i * 32);
+    } else if (!dec2) {
+      const int kg = (int)e;
+      cp_async16(slot, c.sys4 + kg * WH + c.t);
+      cp_async16(slot + 32, c.par04 + kg * WH + c.t);
+      if (apriori) {
+        const uint32_t* ap = c.A32 + (kg * 4) * WH + c.t;
+        uint32_t*       d  = reinterpret_cast<uint32_t*>(slot + 64);
+#pragma unroll
+        for (int r = 0; r < 4; r++) cp_async4(d + r, ap + r * WH);
+      }
+    } else {
+      const int kg = (int)e;
+      cp_async16(slot, c.par14 + kg * WH + c.t);
+      // plane 1 as [4 rows][32 lanes] words: the W/2 lanes of a code block fetch one whole row pi(k) mod L of E
+      uint32_t* d = reinterpret_cast<uint32_t*>(slot + 32 - c.lane) + c.lane;
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const uint32_t row = c.qtab[kg * 4 + r] & 0x1FFu;
+        cp_async4(d + r * 32, c.E32 + row * WH + c.t);
+      }
     }
-    q.a = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    q.c = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   }
+  cp_async_commit();
+  pos.head++;
+  pos.head_slot = pos.head_slot + 1 == kRingDepth ? 0 : pos.head_slot + 1;
 }
 
-// FAST rows only: x = sys + a-priori with a wrapping add
-template <bool DEC2>
-__device__ __forceinline__ void finish_group(bool apriori, const RawGroup& q, Group& g)
+// wait for the oldest entry, refill the slot that was consumed before it, return the oldest entry's slot
+template <int W>
+__device__ __forceinline__ const uint4* ring_next(const WinCtx<W>& c, bool dec2, bool apriori, RingPos& pos)
 {
-  g.y[0] = q.b.x; g.y[1] = q.b.y; g.y[2] = q.b.z; g.y[3] = q.b.w;
-  if (!DEC2) {
-    g.x[0] = q.a.x; g.x[1] = q.a.y; g.x[2] = q.a.z; g.x[3] = q.a.w;
+  cp_async_wait<kRingDepth - 2>();
+  __syncwarp();  // every lane's copies of this entry have landed and every lane is done reading the previous slot
+  ring_issue<W>(c, dec2, apriori, pos);
+  const uint4* slot = c.ring + pos.tail_slot * 96;
+  pos.tail_slot     = pos.tail_slot + 1 == kRingDepth ? 0 : pos.tail_slot + 1;
+  return slot;
+}
+
+template <int W>
+__device__ __forceinline__ void ring_start(const WinCtx<W>& c, bool dec2, bool apriori, RingPos& pos)
+{
+  pos.head = 0;
+  pos.head_slot = 0;
+  pos.tail_slot = 0;
+#pragma unroll
+  for (int i = 0; i < kRingDepth - 1; i++) ring_issue<W>(c, dec2, apriori, pos);
+}
+
+// FAST rows only: the next row group of the sequence (must be group kg); x = sys + a-priori with a wrapping add
+template <int W>
+__device__ __forceinline__ void fetch_group(const WinCtx<W>& c, bool dec2, bool apriori, int kg, RingPos& pos, Group& g)
+{
+  const uint4* slot = ring_next<W>(c, dec2, apriori, pos);
+  const uint4  ys   = slot[dec2 ? 0 : 32];
+  g.y[0] = ys.x; g.y[1] = ys.y; g.y[2] = ys.z; g.y[3] = ys.w;
+  if (!dec2) {
+    const uint4 xs = slot[0];
+    g.x[0] = xs.x; g.x[1] = xs.y; g.x[2] = xs.z; g.x[3] = xs.w;
     if (apriori) {
-      g.aux[0] = q.c.x; g.aux[1] = q.c.y; g.aux[2] = q.c.z; g.aux[3] = q.c.w;
+      const uint4 as = slot[64];
+      g.aux[0] = as.x; g.aux[1] = as.y; g.aux[2] = as.z; g.aux[3] = as.w;
 #pragma unroll
       for (int r = 0; r < 4; r++) g.x[r] = wadd2(g.aux[r], g.x[r]);
     } else {
@@ -303,11 +364,28 @@ __device__ __forceinline__ void finish_group(bool apriori, const RawGroup& q, Gr
       for (int r = 0; r < 4; r++) g.aux[r] = 0;
     }
   } else {
-    g.x[0] = q.a.x | (q.c.x << 16); g.x[1] = q.a.y | (q.c.y << 16);
-    g.x[2] = q.a.z | (q.c.z << 16); g.x[3] = q.a.w | (q.c.w << 16);
+    // the row of E fetched for trellis row k sits in plane 1 at [r][first lane of this code block ..]
+    const uint16_t* rows = reinterpret_cast<const uint16_t*>(slot + 32 - c.lane) + 2 * (c.lane - c.t);
 #pragma unroll
-    for (int r = 0; r < 4; r++) g.aux[r] = g.x[r];
+    for (int r = 0; r < 4; r++) {
+      const uint32_t k  = (uint32_t)(kg * 4 + r);
+      const uint32_t w0 = c.qtab[k] >> 9;
+      const uint32_t lo = rows[r * 64 + ((w0 + c.base_lo + c.inc_lo * k) & (W - 1))];
+      const uint32_t hi = rows[r * 64 + ((w0 + c.base_hi + c.inc_hi * k) & (W - 1))];
+      g.x[r]   = lo | (hi << 16);
+      g.aux[r] = g.x[r];
+    }
   }
+}
+
+// the beta checkpoint that comes next in the sequence
+template <int W>
+__device__ __forceinline__ void fetch_checkpoint(const WinCtx<W>& c, bool dec2, bool apriori, RingPos& pos, uint32_t s[8])
+{
+  const uint4*    slot = ring_next<W>(c, dec2, apriori, pos);
+  const uint32_t* w    = reinterpret_cast<const uint32_t*>(slot - c.lane) + c.lane;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s[i] = w[i * 32];
 }
 
 // one row for the exact helpers: loads issued one row ahead, the reference's saturating a-priori add
@@ -347,12 +425,12 @@ __device__ __forceinline__ void finish_row_exact(bool dec2, bool apriori, const 
 }
 
 // store the differenced output of row k (see file header) and remember its extremes
-template <int W, bool DEC2>
-__device__ __forceinline__ void store_out(const WinCtx<W>& c, uint32_t k, uint32_t o, uint32_t aux, Range& rd)
+template <int W>
+__device__ __forceinline__ void store_out(const WinCtx<W>& c, bool dec2, uint32_t k, uint32_t o, uint32_t aux, Range& rd)
 {
   const uint32_t d = wsub2(o, aux);
   rd.add1(d);
-  if (!DEC2) {
+  if (!dec2) {
     c.E32[k * (W / 2) + c.t] = d;
   } else {
     uint32_t i_lo, i_hi;
@@ -457,10 +535,7 @@ __device__ __noinline__ void alpha_rows_exact(const WinCtx<W> c, uint32_t flags,
       const uint32_t bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       uint32_t       o = alpha_out_step<false>(a, bb, x, y, sadd2(x, y), unused);
       if (W == 8) o = sra1_2(o);  // the 8-window (sse16) decoder halves its output
-      if (dec2)
-        store_out<W, true>(c, (uint32_t)k, o, aux, rd);
-      else
-        store_out<W, false>(c, (uint32_t)k, o, aux, rd);
+      store_out<W>(c, dec2, (uint32_t)k, o, aux, rd);
     }
     if ((j & 1) == 0 && j != 0) {
       normalize<false>(a);
@@ -556,64 +631,46 @@ __device__ __noinline__ HalfResult half_iteration_exact(const WinCtx<W> c, bool 
   return res;
 }
 
-// ---- FAST variant: wrapping adds fused with max, plus the bookkeeping that proves it equals the exact one
+// ---- FAST variant: wrapping adds fused with max, plus (TRACK) the bookkeeping that proves it equals the exact one
 // G bounds |x|, |y| and |x + y| of every row of this code block in this half iteration.
-template <int W, bool DEC2, bool TRACK>
-__device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bool apriori, int G)
+// The row groups are consumed in exactly the order build_sequence() lists them.
+// Code size matters here: in steady state the warps of an SM are in different phases, and the instruction
+// cache has to hold all of them.  DEC1 / DEC2 therefore share one instantiation (they differ only in how a
+// row group is fetched and stored) and the two backward loops (boundary warm-up, window) are one loop.
+template <int W, bool TRACK>
+__device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bool dec2, bool apriori, int G)
 {
   constexpr int  WH = W / 2;
   const int      L  = (int)c.L;
   const int      nchunks = (L + kChunk - 1) / kChunk;
-  const uint32_t flags = (DEC2 ? 1u : 0u) | (apriori ? 2u : 0u);
+  const uint32_t flags = (dec2 ? 1u : 0u) | (apriori ? 2u : 0u);
   // rows [4, kf] are covered by full row groups of fast arithmetic; rows above kf (next to the terminated
   // tail) and rows 0..3 of the forward pass (next to the known start state) always use exact arithmetic
   const int gtop = (L - kExactRows) / 4 - 1;  // last fully fast group
   const int kf   = gtop * 4 + 3;              // last fast row (kf <= L - kExactRows - 1)
   uint32_t  s[8];
   Group     g;
-  RawGroup  q;
+  RingPos   pos;
   Range     rb, ra, rm, rd;
   rb.reset(); ra.reset(); rd.reset();
   rm.hi = kMin2; rm.lo = kMax2;
   RowState st;
+  ring_start<W>(c, dec2, apriori, pos);
 
-  // ---------------- backward pass: boundary metrics from the next window's first 40 rows ----------------
+  // ---------------- backward pass ----------------
+  // phase 0: boundary metrics from the next window's first 40 rows; phase 1: the window itself with a
+  // checkpoint every kChunk rows
 #pragma unroll
   for (int i = 0; i < 8; i++) s[i] = kNegInf2;
-  issue_group<W, DEC2>(c, apriori, kWarm / 4 - 1, q);
 #pragma unroll 1
-  for (int kg = kWarm / 4 - 1; kg >= 0; kg--) {
-    finish_group<DEC2>(apriori, q, g);
-    issue_group<W, DEC2>(c, apriori, kg > 0 ? kg - 1 : gtop, q);  // last: top fast group of the main pass
-#pragma unroll
-    for (int r = 3; r >= 0; r--) {
-      beta_step<true>(s, g.x[r], g.y[r], wadd2(g.x[r], g.y[r]));
-      if ((r & 1) == 0 && (kg | r) != 0) {
-        normalize<true>(s);
-        if (TRACK) rb.add8(s);
-      }
-    }
-  }
-  exchange_beta_boundary<WH>(s, c.t, c.tail + (DEC2 ? 6 : 0));
-#pragma unroll
-  for (int i = 0; i < 8; i++) c.chk[((nchunks - 1) * 8 + i) * 32] = s[i];
-
-  // ---------------- backward pass over the window: checkpoints every kChunk rows ----------------
-#pragma unroll
-  for (int i = 0; i < 8; i++) st.s[i] = s[i];
-  st.trk = rb;
-  beta_rows_exact<W>(c, flags, L - 1, kf + 1, 1, 0, &st);
-#pragma unroll
-  for (int i = 0; i < 8; i++) s[i] = st.s[i];
-  rb = st.trk;
-  {
-    RawGroup q2;
-    if (gtop >= 1) issue_group<W, DEC2>(c, apriori, gtop - 1, q2);
-    auto rows = [&](int kg) {
+  for (int phase = 0; phase < 2; phase++) {
+#pragma unroll 1
+    for (int kg = phase ? gtop : kWarm / 4 - 1; kg >= 0; kg--) {
+      fetch_group<W>(c, dec2, apriori, kg, pos, g);
 #pragma unroll
       for (int r = 3; r >= 0; r--) {
         beta_step<true>(s, g.x[r], g.y[r], wadd2(g.x[r], g.y[r]));
-        if (r == 0 && (kg % (kChunk / 4)) == 0 && kg != 0) {
+        if (r == 0 && phase && (kg % (kChunk / 4)) == 0 && kg != 0) {
 #pragma unroll
           for (int i = 0; i < 8; i++) c.chk[((kg / (kChunk / 4) - 1) * 8 + i) * 32] = s[i];
         }
@@ -622,30 +679,28 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
           if (TRACK) rb.add8(s);
         }
       }
-    };
-    int kg = gtop;
-#pragma unroll 1
-    for (; kg >= 1; kg -= 2) {  // q holds group kg, q2 group kg - 1: every load is issued two groups ahead
-      finish_group<DEC2>(apriori, q, g);
-      if (kg >= 2) issue_group<W, DEC2>(c, apriori, kg - 2, q);
-      rows(kg);
-      finish_group<DEC2>(apriori, q2, g);
-      if (kg >= 3) issue_group<W, DEC2>(c, apriori, kg - 3, q2);
-      rows(kg - 1);
     }
-    if (kg == 0) {
-      finish_group<DEC2>(apriori, q, g);
-      rows(0);
+    if (phase == 0) {
+      exchange_beta_boundary<WH>(s, c.t, c.tail + (dec2 ? 6 : 0));
+#pragma unroll
+      for (int i = 0; i < 8; i++) c.chk[((nchunks - 1) * 8 + i) * 32] = s[i];
+      // the rows next to the terminated tail: exact
+#pragma unroll
+      for (int i = 0; i < 8; i++) st.s[i] = s[i];
+      st.trk = rb;
+      beta_rows_exact<W>(c, flags, L - 1, kf + 1, 1, 0, &st);
+#pragma unroll
+      for (int i = 0; i < 8; i++) s[i] = st.s[i];
+      rb = st.trk;
     }
   }
 
   // ---------------- forward pass: boundary metrics from the previous window's last 40 rows ----------------
   uint32_t a[8];
   {
-    const int a0 = L - kWarm;                 // first warm-up row
-    const int ga = (a0 + 3) >> 2;             // first full group
-    const int gb = (L >> 2) - 1;              // last full group
-    issue_group<W, DEC2>(c, apriori, ga, q);
+    const int a0 = L - kWarm;      // first warm-up row
+    const int ga = (a0 + 3) >> 2;  // first full group
+    const int gb = (L >> 2) - 1;   // last full group
 #pragma unroll
     for (int i = 0; i < 8; i++) st.s[i] = kNegInf2;
     st.trk = ra;
@@ -655,8 +710,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
     ra = st.trk;
 #pragma unroll 1
     for (int kg = ga; kg <= gb; kg++) {
-      finish_group<DEC2>(apriori, q, g);
-      if (kg < gb) issue_group<W, DEC2>(c, apriori, kg + 1, q);
+      fetch_group<W>(c, dec2, apriori, kg, pos, g);
 #pragma unroll
       for (int r = 0; r < 4; r++) {
         const int j = kg * 4 + r - a0;  // the reference normalises on the warm-up counter
@@ -680,15 +734,13 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
   exchange_alpha_boundary<WH>(a, c.t);
 
   // ---------------- forward pass over the window, chunk by chunk ----------------
-  issue_group<W, DEC2>(c, apriori, min((kChunk - 1) >> 2, gtop), q);  // top fast group of chunk 0
 #pragma unroll 1
   for (int ch = 0; ch < nchunks; ch++) {
     const int lo = ch * kChunk;
     const int hi = min(lo + kChunk, L);
     const int g_lo = lo >> 2, g_hi = min((hi - 1) >> 2, gtop);  // fast groups of this chunk (may be empty)
     // rebuild B[lo+1 .. hi] into shared memory, slot (k - lo - 1) holds B[k]
-#pragma unroll
-    for (int i = 0; i < 8; i++) s[i] = c.chk[(ch * 8 + i) * 32];
+    fetch_checkpoint<W>(c, dec2, apriori, pos, s);
     c.sm[((hi - lo - 1) * 2 + 0) * kThreads] = make_uint4(s[0], s[1], s[2], s[3]);
     c.sm[((hi - lo - 1) * 2 + 1) * kThreads] = make_uint4(s[4], s[5], s[6], s[7]);
     if (hi != L) {  // hi is even and non-zero: the backward pass normalised after storing
@@ -707,9 +759,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
     }
 #pragma unroll 1
     for (int kg = g_hi; kg >= g_lo; kg--) {
-      finish_group<DEC2>(apriori, q, g);
-      // next: the group below, or (when done) the first fast group of the alpha rows of this chunk
-      issue_group<W, DEC2>(c, apriori, kg > g_lo ? kg - 1 : max(g_lo, 1), q);
+      fetch_group<W>(c, dec2, apriori, kg, pos, g);
 #pragma unroll
       for (int r = 3; r >= 0; r--) {
         const int k = kg * 4 + r;
@@ -736,11 +786,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
     }
 #pragma unroll 1
     for (int kg = ga; kg <= g_hi; kg++) {
-      finish_group<DEC2>(apriori, q, g);
-      if (kg < g_hi)
-        issue_group<W, DEC2>(c, apriori, kg + 1, q);
-      else if (ch + 1 < nchunks)
-        issue_group<W, DEC2>(c, apriori, min((min(hi + kChunk, L) - 1) >> 2, gtop), q);  // top fast group of the next chunk
+      fetch_group<W>(c, dec2, apriori, kg, pos, g);
 #pragma unroll
       for (int r = 0; r < 4; r++) {
         const int      k  = kg * 4 + r;
@@ -749,7 +795,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
         const uint32_t bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         uint32_t       o = alpha_out_step<true, TRACK>(a, bb, g.x[r], g.y[r], wadd2(g.x[r], g.y[r]), rm);
         if (W == 8) o = sra1_2(o);  // the 8-window (sse16) decoder halves its output
-        store_out<W, DEC2>(c, (uint32_t)k, o, g.aux[r], rd);
+        store_out<W>(c, dec2, (uint32_t)k, o, g.aux[r], rd);
         if ((r & 1) == 0) {
           normalize<true>(a);
           if (TRACK) ra.add8(a);
@@ -768,6 +814,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
       rd = st.rd;
     }
   }
+  cp_async_wait<0>();
   __syncwarp();
 
   HalfResult res;
@@ -798,6 +845,26 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
   }
   res.proven = ok;
   return res;
+}
+
+// the order in which a fast half iteration consumes row groups and checkpoints (depends only on L)
+template <int W>
+__device__ uint32_t build_sequence(uint32_t L32, uint8_t* seq)
+{
+  const int L = (int)L32, nchunks = (L + kChunk - 1) / kChunk;
+  const int gtop = (L - kExactRows) / 4 - 1;
+  int       n = 0;
+  for (int kg = kWarm / 4 - 1; kg >= 0; kg--) seq[n++] = (uint8_t)kg;
+  for (int kg = gtop; kg >= 0; kg--) seq[n++] = (uint8_t)kg;
+  for (int kg = (L - kWarm + 3) >> 2; kg <= (L >> 2) - 1; kg++) seq[n++] = (uint8_t)kg;
+  for (int ch = 0; ch < nchunks; ch++) {
+    const int lo = ch * kChunk, hi = min(lo + kChunk, L);
+    const int g_lo = lo >> 2, g_hi = min((hi - 1) >> 2, gtop);
+    seq[n++] = (uint8_t)(0x80 | ch);
+    for (int kg = g_hi; kg >= g_lo; kg--) seq[n++] = (uint8_t)kg;
+    for (int kg = ch == 0 ? 1 : g_lo; kg <= g_hi; kg++) seq[n++] = (uint8_t)kg;
+  }
+  return (uint32_t)n;
 }
 
 // hard decision of this code block: bit n = (A[n] + E[n] > 0), MSB first.
@@ -897,12 +964,15 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
   constexpr int CBW = 32 / WH;
   constexpr uint32_t KMAX = (W == 16) ? kAeStride16 : kAeStride8;
   extern __shared__ uint4 smem[];
-  uint32_t* qtab_all = reinterpret_cast<uint32_t*>(smem + kChunk * 2 * kThreads);
+  uint4*    ring_all = smem + kChunk * 2 * kThreads;                                  // [warps][kRingDepth][3][32]
+  uint16_t* qtab_all = reinterpret_cast<uint16_t*>(ring_all + (kThreads / 32) * kRingDepth * 96);
+  uint8_t*  seq_all  = reinterpret_cast<uint8_t*>(qtab_all + (kThreads / 32) * kMaxL);
 
   const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int      grp = lane / WH, t = lane % WH;
   const uint32_t slot = blockIdx.x * (kThreads / 32) + warp;
-  uint32_t*      qtab = qtab_all + warp * kMaxL;
+  uint16_t*      qtab = qtab_all + warp * kMaxL;
+  uint8_t*       seq  = seq_all + warp * kSeqMax;
   uint32_t       fallbacks = 0;
 
   for (;;) {
@@ -937,11 +1007,17 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
         if (p >= c.K) p -= c.K;
         if (p >= c.K) p -= c.K;
         const uint32_t w0 = __umulhi(p, mL);
-        qtab[k]           = (p - w0 * c.L) | (w0 << 16);
+        qtab[k]           = (uint16_t)((p - w0 * c.L) | (w0 << 9));
       }
+      uint32_t n_seq = 0;
+      if (lane == 0) n_seq = build_sequence<W>(c.L, seq);
+      c.n_seq = __shfl_sync(0xFFFFFFFFu, n_seq, 0);
       __syncwarp();
     }
     c.qtab = qtab;
+    c.seq  = seq;
+    c.lane = lane;
+    c.ring = ring_all + warp * kRingDepth * 96 + lane;
     const uint32_t Lp = (c.L + 3) & ~3u;
     const uint32_t S  = Lp * W;  // int16 per stream
     const int16_t* in = a.in + (size_t)cb * a.in_stride;
@@ -978,10 +1054,10 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
       bool       fast_ok = false;
       // the decision must be warp-uniform: the passes below use full-warp shuffles and votes
       if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kStaticFastG)) {
-        r = dec2 ? half_iteration_fast<W, true, false>(c, apriori, G) : half_iteration_fast<W, false, false>(c, apriori, G);
+        r       = half_iteration_fast<W, false>(c, dec2, apriori, G);
         fast_ok = true;
       } else if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kMaxFastG)) {
-        r = dec2 ? half_iteration_fast<W, true, true>(c, apriori, G) : half_iteration_fast<W, false, true>(c, apriori, G);
+        r       = half_iteration_fast<W, true>(c, dec2, apriori, G);
         fast_ok = __all_sync(0xFFFFFFFFu, r.proven);
       }
       if (!fast_ok) {
@@ -1311,7 +1387,8 @@ cudaError_t tdec_geometry(int W, int device, TdecGeometry* g)
     g->ws_chk_bytes = slots * (400 + 4) * 32 * sizeof(uint4);
     return cudaSuccess;
   }
-  g->smem = (size_t)kChunk * 2 * kThreads * sizeof(uint4) + warps_per_block * kMaxL * sizeof(uint32_t);
+  g->smem = (size_t)kChunk * 2 * kThreads * sizeof(uint4) + warps_per_block * kRingDepth * 96 * sizeof(uint4) +
+            warps_per_block * kMaxL * sizeof(uint16_t) + warps_per_block * kSeqMax;
   int per_sm = 0;
   if (W == 16) {
     e = cudaFuncSetAttribute(tdec_win_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
