@@ -33,6 +33,7 @@ NOF_ITERATIONS = 4          # srsLTE HALF iterations
 EBNO_HARNESS = 1.5          # turbodecoder_test "-e 1.5" (sigma = 1.457 on +-1; never converges, F7)
 LLR_SCALE = 100.0
 IN_LEN = 3 * K + 12
+NCU_DRAM_BYTES_PER_BLOCK = 453.7e3        # profiles/r01_final_ncu_raw.csv: (22.25 + 7.49) GB / 65536 blocks
 INT_PEAK_THREAD_INSTR_PER_CLK_SM = 64.0   # measured: profiles/r01_int_peak*.txt (VIADD.16x2 / VIMNMX.S16x2)
 
 
@@ -177,7 +178,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--blocks", type=int, default=65536, help="code blocks per GPU per step")
-    ap.add_argument("--e2e-blocks", type=int, default=16384, help="code blocks per GPU for the host-pointer leg")
+    ap.add_argument("--e2e-blocks", type=int, default=32768, help="code blocks per GPU for the host-pointer leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
 
@@ -323,11 +324,20 @@ def main():
             "ops_per_block": int_ops_per_block(), "ms_per_launch": dec_ms_per_launch,
             "peak_source": f"measured {INT_PEAK_THREAD_INSTR_PER_CLK_SM:g} packed-int16x2 thread-instr/clk/SM "
                            f"(tools/int_peak.cu, profiles/r01_int_peak*.txt) x 2 lanes x {sms} SMs x {sm_max:g} MHz",
-            "sm_mhz_during_run": sm_mhz, "traffic": None,
+            "sm_mhz_during_run": sm_mhz,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture in
+            # profiles/ (29.73 GB for the 65536-block launch = 453.7 KB per block), scaled to this launch
+            "traffic": NCU_DRAM_BYTES_PER_BLOCK * n,
+            "two_pipe_peak": 2 * peak_tops,
+            "note": "peak = ONE integer pipe (64 packed thread-instr/clk/SM, what every single packed op reaches); "
+                    "VIADD.16x2 (FMA pipe) and VIMNMX/VIADDMNMX (ALU pipe) can overlap up to ~1.9x that "
+                    "(profiles/r01_pipe_mix.txt), and a fused add-max counts as two algorithmic ops",
         },
         "roofline_hbm": {
             "bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
-            "bytes_per_block": algo_bytes_per_block(), "peak_source": f"MEASURED_PEAKS.json ({hbm_src})", "traffic": None,
+            "bytes_per_block": algo_bytes_per_block(), "peak_source": f"MEASURED_PEAKS.json ({hbm_src})",
+            "traffic": NCU_DRAM_BYTES_PER_BLOCK * n,
+            "traffic_gbs": NCU_DRAM_BYTES_PER_BLOCK * n / (dec_ms_per_launch * 1e-3) / 1e9,
         },
         "kernel_share": {"decode_ms_per_step": dec_ms / args.steps, "layout_ms_per_step": lay_ms / args.steps,
                          "decode_launches": dec_n, "layout_launches": lay_n},

@@ -538,7 +538,7 @@ int srslte_b200_tdec_batch_host(srslte_b200_ctx_t* ctx, const srslte_b200_tdec_b
 
   // Pieces of up to `piece` blocks: H2D of piece p+1 overlaps the kernels of piece p and the D2H of
   // piece p-1.  Uniform-K batches reuse one cached schedule for every full piece.
-  const uint32_t piece = 8192;
+  const uint32_t piece = 4096;
   cudaStream_t   cs    = ctx->stream;
   const uint32_t n_pieces = (b->n_cb + piece - 1) / piece;
   for (uint32_t p = 0; p < n_pieces; p++) {
