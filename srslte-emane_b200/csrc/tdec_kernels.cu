@@ -41,8 +41,8 @@ namespace {
 
 constexpr int      kWarm      = 40;  // win_overlap_len
 constexpr int      kChunk     = 8;   // rows of beta rebuilt at a time (multiple of 4)
-constexpr int      kThreads   = 128;
-constexpr int      kBlocksPerSm = 3;
+constexpr int      kThreads   = 384;  // one CTA per SM: its warps take their work items in step (see the item loop)
+constexpr int      kBlocksPerSm = 1;
 constexpr int      kMaxChunks = 48;  // ceil(384 / 8)
 // per-warp-slot strides are odd multiples of 128 bytes: warps run in near lock step, and power-of-two
 // strides would send all of them to the same L2 slices / HBM channels at once
@@ -979,7 +979,10 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
     uint32_t it = 0;
     if (lane == 0) it = atomicAdd(a.counter, 1u);
     it = __shfl_sync(0xFFFFFFFFu, it, 0);
-    if (it >= a.n_items) break;
+    // The warps of the CTA start their items together: work items of equal K take equal time, so the warps
+    // stay in the same phase of the half iteration and share the instruction cache instead of thrashing it.
+    if (!__syncthreads_or(it < a.n_items)) break;
+    if (it >= a.n_items) continue;
     const WorkItem wi     = a.items[it];
     const bool     active = grp < (int)wi.count;
     const uint32_t cb     = a.order[wi.first + (active ? grp : 0)];
