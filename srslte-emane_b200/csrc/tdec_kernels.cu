@@ -51,6 +51,7 @@ constexpr uint32_t kAeStride16 = 6144 + 64, kAeStride8 = 800 + 32;  // int16 per
 constexpr int      kMaxL      = 384;
 constexpr int      kRingDepth = 6;   // row groups kept in flight per warp by cp.async (prefetch distance kRingDepth-1)
 constexpr int      kSeqMax    = 384; // entries of a half iteration's fetch sequence (10 + 96 + 11 + 32 + 2*96 at most)
+constexpr int      kStagePad  = 2;   // int16 of padding per window in to_internal_kernel's staged copy
 constexpr int      kExactRows = 4;   // rows next to a known-state boundary always use exact arithmetic
 constexpr int      kStaticFastG = 2978; // 11 * G <= 32767: the fast variant needs no bookkeeping at all
 constexpr int      kMaxFastG  = 5461; // largest per-step metric change the fast variant accepts (6 * G <= 32767)
@@ -1286,11 +1287,23 @@ __global__ void __launch_bounds__(256) to_internal_kernel(const int16_t* __restr
     return;
   }
   const uint32_t L = K / W, Lp = (L + 3) & ~3u, WH = W / 2, S = Lp * W;
+  // the staged copy gives every window 2 extra int16 so that the W/2 threads that later read the same row of
+  // different windows fall into different shared-memory banks (3L int16 per window is a multiple of 64 words
+  // for L = 384: an 8-way conflict without the padding)
+  const uint32_t wstride = 3 * L + kStagePad;
   if (threadIdx.x < 3) s_max[threadIdx.x] = 0;
   if (src_format == 0) {
-    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
-    uint32_t*       t32 = reinterpret_cast<uint32_t*>(stage);
-    for (uint32_t i = threadIdx.x; i < (3 * K + 12) / 2; i += blockDim.x) t32[i] = s32[i];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    if (((3 * L) & 1) == 0) {  // window starts are word aligned: 32-bit copies
+      const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+      uint32_t*       t32 = reinterpret_cast<uint32_t*>(stage);
+      for (uint32_t d = warp; d < W; d += nwarps)
+        for (uint32_t p = lane; p < 3 * L / 2; p += 32) t32[d * (wstride / 2) + p] = s32[d * (3 * L / 2) + p];
+    } else {
+      for (uint32_t d = warp; d < W; d += nwarps)
+        for (uint32_t p = lane; p < 3 * L; p += 32) stage[d * wstride + p] = src[d * 3 * L + p];
+    }
+    if (threadIdx.x < 12) stage[W * wstride + threadIdx.x] = src[3 * K + threadIdx.x];
   }
   __syncthreads();
   const uint32_t groups = Lp / 4;
@@ -1305,8 +1318,8 @@ __global__ void __launch_bounds__(256) to_internal_kernel(const int16_t* __restr
       int            lo = 0, hi = 0;
       if (k < L) {
         if (src_format == 0) {
-          lo = stage[3 * ((2 * t) * L + k) + j];
-          hi = stage[3 * ((2 * t + 1) * L + k) + j];
+          lo = stage[(2 * t) * wstride + 3 * k + j];
+          hi = stage[(2 * t + 1) * wstride + 3 * k + j];
         } else {
           const uint32_t v = reinterpret_cast<const uint32_t*>(src + j * (K + 32))[k * WH + t];
           lo = (int16_t)(v & 0xFFFFu);
@@ -1318,7 +1331,7 @@ __global__ void __launch_bounds__(256) to_internal_kernel(const int16_t* __restr
     }
     reinterpret_cast<uint4*>(dst + j * S)[kg * WH + t] = make_uint4(w[0], w[1], w[2], w[3]);
   }
-  const int16_t* tl = src_format == 0 ? stage + 3 * K : src + 3 * (K + 32);
+  const int16_t* tl = src_format == 0 ? stage + W * wstride : src + 3 * (K + 32);
   if (threadIdx.x < 16) dst[3 * S + threadIdx.x] = threadIdx.x < 12 ? tl[threadIdx.x] : (int16_t)0;
 #pragma unroll
   for (int j = 0; j < 3; j++) {
@@ -1436,10 +1449,10 @@ cudaError_t to_internal_launch(const int16_t* src, uint32_t src_stride, const ui
 {
   if (n_cb == 0) return cudaSuccess;
   static bool attr_set = false;
-  const size_t smem = src_format == 0 ? (3 * 6144 + 12) * sizeof(int16_t) : 0;
+  const size_t smem = src_format == 0 ? (3 * 6144 + 16 * kStagePad + 16) * sizeof(int16_t) : 0;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(to_internal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)((3 * 6144 + 12) * sizeof(int16_t)));
+                                         (int)((3 * 6144 + 16 * kStagePad + 16) * sizeof(int16_t)));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
