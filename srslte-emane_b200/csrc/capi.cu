@@ -73,6 +73,7 @@ struct Regime {  // one per decoder kind: index 0 -> W=16, 1 -> W=8, 2 -> generi
 
 struct Schedule {  // how the code blocks of one launch map onto warps
   std::vector<uint32_t> order;
+  std::vector<uint2>    place;  // per code block: (first position of its work item, count << 8 | index in the item)
   std::vector<WorkItem> items[3];
   uint32_t              item_base[3] = {0, 0, 0};
 };
@@ -92,6 +93,8 @@ struct srslte_b200_ctx {
   DevBuf<uint32_t> d_order;
   DevBuf<WorkItem> d_items;
   DevBuf<uint32_t> d_cbK;
+  DevBuf<uint2>    d_place;
+  PinBuf<uint2>    h_place;
   PinBuf<uint32_t> h_order;
   PinBuf<WorkItem> h_items;
   PinBuf<uint32_t> h_cbK;
@@ -180,25 +183,35 @@ int ensure_regime(srslte_b200_ctx* ctx, int ri)
 }
 
 // Group the blocks [0, n) by K (largest first, so the longest work starts first) and cut each
-// group into warp-sized items.
+// group into warp-sized items.  The window kernels take tdec_items_per_cta() consecutive items per CTA round
+// and need them to share K: every K group is padded to a multiple of that with empty items.
 int build_schedule(srslte_b200_ctx* ctx, const uint32_t* K, uint32_t uniform_K, uint32_t n, Schedule& s)
 {
   s.order.resize(n);
+  const bool with_place = K != nullptr;  // a uniform-K schedule is the identity: to_internal_kernel derives it
+  s.place.resize(with_place ? n : 0);
   for (auto& v : s.items) v.clear();
   auto emit = [&](uint32_t Kv, uint32_t first, uint32_t count) {
     const int idx = cb_index_exact(Kv);
     const int W   = nof_windows(Kv);
     const int ri  = regime_index(W);
     const uint32_t per = (uint32_t)tdec_blocks_per_warp(W);
+    WorkItem       wi;
+    wi.K  = (uint16_t)Kv;
+    wi.f1 = kQpp[idx].f1;
+    wi.f2 = kQpp[idx].f2;
     for (uint32_t o = 0; o < count; o += per) {
-      WorkItem wi;
       wi.first = first + o;
       wi.count = (uint16_t)std::min(per, count - o);
-      wi.K     = (uint16_t)Kv;
-      wi.f1    = kQpp[idx].f1;
-      wi.f2    = kQpp[idx].f2;
       s.items[ri].push_back(wi);
+      if (with_place)
+        for (uint32_t j = 0; j < wi.count; j++)
+          s.place[s.order[wi.first + j]] = make_uint2(wi.first, ((uint32_t)wi.count << 8) | j);
     }
+    const size_t round = (size_t)tdec_items_per_cta(W);
+    wi.first = first;
+    wi.count = 0;
+    while (s.items[ri].size() % round) s.items[ri].push_back(wi);
   };
   if (!K) {
     if (cb_index_exact(uniform_K) < 0)
@@ -260,6 +273,10 @@ int ensure_schedule(srslte_b200_ctx* ctx, const uint32_t* K, uint32_t uniform_K,
     CU(ctx->d_cbK.reserve(n));
     std::memcpy(ctx->h_cbK.p, K, n * sizeof(uint32_t));
     CU(cudaMemcpyAsync(ctx->d_cbK.p, ctx->h_cbK.p, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CU(ctx->h_place.reserve(n));
+    CU(ctx->d_place.reserve(n));
+    std::memcpy(ctx->h_place.p, s.place.data(), n * sizeof(uint2));
+    CU(cudaMemcpyAsync(ctx->d_place.p, ctx->h_place.p, n * sizeof(uint2), cudaMemcpyHostToDevice, st));
     ctx->sched_K.assign(K, K + n);
   } else {
     ctx->sched_K.clear();
@@ -307,14 +324,12 @@ int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint
   {
     KernelTimer kt(ctx, 3, st);
     CU(to_internal_launch(d_llr, b->in_stride, d_src_off, b->input_format == SRSLTE_B200_INPUT_NATURAL ? 0 : 1,
-                          ctx->d_work.p, work_len, b->long_cb ? ctx->d_cbK.p : nullptr, b->uniform_long_cb, b->n_cb,
-                          st));
+                          ctx->d_work.p, work_len, b->long_cb ? ctx->d_cbK.p : nullptr, b->uniform_long_cb,
+                          b->long_cb ? ctx->d_place.p : nullptr, b->n_cb, st));
   }
   ctx->launches++;
   const int16_t* win    = ctx->d_work.p;
-  // development probe: B200_ALIAS_INPUT=1 makes every block read block 0's input (memory-stall experiment)
-  static const bool alias_input = getenv("B200_ALIAS_INPUT") != nullptr;
-  const uint32_t stride = alias_input ? 0u : work_len;
+  const uint32_t stride = work_len;
   if (ctx->counters.cap == 0) {
     CU(ctx->counters.reserve(4));
     CU(cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(uint32_t), st));
@@ -341,8 +356,7 @@ int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint
     a.crc_mode_cb = d_crc_mode_cb;
     a.ws_ae      = reinterpret_cast<int16_t*>(R.ws_ae.p);
     a.ws_chk     = reinterpret_cast<uint32_t*>(R.ws_chk.p);
-    static const bool alias_ws = getenv("B200_ALIAS_WS") != nullptr;  // development probe
-    a.force_exact = (ctx->force_exact ? 1u : 0u) | (alias_ws ? 2u : 0u);
+    a.force_exact = ctx->force_exact ? 1u : 0u;
     a.stats      = ctx->counters.p + 3;
     {
       KernelTimer kt(ctx, r, st);
@@ -401,6 +415,8 @@ void srslte_b200_ctx_destroy(srslte_b200_ctx_t* ctx)
   ctx->d_order.release();
   ctx->d_items.release();
   ctx->d_cbK.release();
+  ctx->d_place.release();
+  ctx->h_place.release();
   ctx->h_order.release();
   ctx->h_items.release();
   ctx->h_cbK.release();

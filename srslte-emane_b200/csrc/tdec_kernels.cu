@@ -13,8 +13,9 @@
 //   * a code block is W independent trellis windows; one thread owns TWO adjacent windows as the
 //     two int16 halves of every 32-bit register.  W/2 threads per block, 4 (W=16) or 8 (W=8) code
 //     blocks per warp, the 8 state metrics live in registers.
-//   * inputs are held in a "pair-major" layout: the words a thread needs for 4 consecutive trellis
-//     rows are contiguous, so one 128-bit load feeds 4 steps.
+//   * inputs are held in an item-interleaved "pair-major" layout: the words a thread needs for 4 consecutive
+//     trellis rows are contiguous (one 128-bit shared-memory load feeds 4 steps), and the row groups of all the
+//     code blocks of a warp are adjacent, so ONE TMA bulk copy per stream stages an 8-row chunk for the warp.
 //   * the reference keeps all beta metrics of a half iteration (98 KB per K=6144 block).  Here the
 //     backward pass keeps one checkpoint per 16 trellis rows; the forward pass rebuilds the 16 rows
 //     of beta it needs in shared memory (the recursion and its normalisation points depend only on
@@ -23,7 +24,9 @@
 //     srslte_vec_sub_sss at the start of the next half iteration), so the a-posteriori value of
 //     every bit is always A + E (wrapping) and no third array is needed.
 //   * QPP addresses are computed in the kernel from (f1, f2): pi(d*L + k) shares its row
-//     pi(k) mod L across all windows (contention-free property), only the window index differs.
+//     pi(k) mod L across all windows (contention-free property), only the window index differs.  Each
+//     extrinsic array is stored in the order its CONSUMER reads it: the producer scatters on its single
+//     write (pi for DEC2's output, pi^-1 for DEC1's), every read is linear and goes through TMA.
 //   * saturating int16x2 adds are 6 instructions on sm_100a, wrapping adds and fused add-max are 1.
 //     Every half iteration first runs a FAST variant (wrapping VIADD.16x2 on the FMA pipe, fused
 //     VIADDMNMX.S16x2 / VIMNMX.S16x2 on the ALU pipe) that also records the extremes of its state
@@ -40,17 +43,19 @@ namespace b200 {
 namespace {
 
 constexpr int      kWarm      = 40;  // win_overlap_len
-constexpr int      kChunk     = 8;   // rows of beta rebuilt at a time (multiple of 4)
-constexpr int      kThreads   = 384;  // one CTA per SM: its warps take their work items in step (see the item loop)
+constexpr int      kChunk     = 8;   // rows of beta rebuilt at a time = rows per staged chunk (two row groups of 4)
+constexpr int      kThreads   = 384; // one CTA per SM; its warps decode the work items of one CTA round in step
+constexpr int      kWarps     = kThreads / 32;
 constexpr int      kBlocksPerSm = 1;
 constexpr int      kMaxChunks = 48;  // ceil(384 / 8)
-// per-warp-slot strides are odd multiples of 128 bytes: warps run in near lock step, and power-of-two
-// strides would send all of them to the same L2 slices / HBM channels at once
-constexpr int      kChkSlotWords = kMaxChunks * 8 * 32 + 32;
-constexpr uint32_t kAeStride16 = 6144 + 64, kAeStride8 = 800 + 32;  // int16 per A or E array
 constexpr int      kMaxL      = 384;
-constexpr int      kRingDepth = 6;   // row groups kept in flight per warp by cp.async (prefetch distance kRingDepth-1)
-constexpr int      kSeqMax    = 384; // entries of a half iteration's fetch sequence (10 + 96 + 11 + 32 + 2*96 at most)
+constexpr int      kStages    = 3;   // chunks in flight per warp (TMA bulk copies, one mbarrier per stage)
+constexpr int      kStageBytes = 3072;  // [sys | par | A or E] x 1 KB: 8 rows of all the code blocks of a warp
+// per-warp-slot workspace strides are not powers of two: warps run in near lock step, and power-of-two
+// strides would send all of them to the same L2 slices / HBM channels at once
+constexpr size_t   kXArrayBytes16 = (size_t)(kMaxL + 1) * 128;  // one A or E array: rows of 32 words (all blocks of a warp)
+constexpr size_t   kXArrayBytes8  = (size_t)(100 + 1) * 128;    // W = 8: K <= 800, L <= 100
+constexpr size_t   kChkSlotBytes  = (size_t)kMaxChunks * 1024 + 128;
 constexpr int      kStagePad  = 2;   // int16 of padding per window in to_internal_kernel's staged copy
 constexpr int      kExactRows = 4;   // rows next to a known-state boundary always use exact arithmetic
 constexpr int      kStaticFastG = 2978; // 11 * G <= 32767: the fast variant needs no bookkeeping at all
@@ -213,233 +218,222 @@ __device__ __forceinline__ void normalize(uint32_t s[8])
 }
 
 // ---- per-thread decode context ---------------------------------------------------------------------
+// A work item is up to 32/(W/2) code blocks of equal K decoded by one warp.  Its inputs sit in HBM in an
+// item-interleaved layout (to_internal_kernel): [stream][row group of 4][block][thread][4 rows x 2 windows],
+// so the inputs of one 8-row chunk of ALL the warp's blocks are one contiguous piece per stream: one bulk copy.
 template <int W>
 struct WinCtx {
   uint32_t K, L;
-  int      t;  // 0..W/2-1: owns windows 2t (low half) and 2t+1 (high half)
-  uint32_t base_lo, base_hi, inc_lo, inc_hi;  // QPP window offsets of the two windows (mod W)
-  const uint4*    sys4;   // pair-major: [row/4][W/2] uint4 = 4 rows of this thread's window pair
-  const uint4*    par04;
-  const uint4*    par14;
-  const int16_t*  tail;   // 12 tail samples
-  uint32_t*       A32;    // row-major [L][W/2]: extrinsic of DEC2 minus E (= a-priori of DEC1)
-  uint32_t*       E32;    // row-major [L][W/2]: a-posteriori of DEC1 minus A (= systematic of DEC2)
-                          // (row-major keeps the 16 windows of a row in one 32-byte sector for the QPP
-                          //  gather / scatter of DEC2)
-  uint32_t*       chk;    // checkpoints: [(c*8 + i)*32], already offset by lane
-  uint4*          sm;     // chunk of beta: [(s*2 + h)*kThreads], already offset by tid
-  const uint16_t* qtab;   // per-warp table in shared memory: pi(k) as row | window << 9, k < L
-  uint4*          ring;   // per-warp cp.async ring: [kRingDepth][3 planes][32 lanes], already offset by lane
-  const uint8_t*  seq;    // per-warp fetch sequence of a half iteration: row-group index, or 0x80 | chunk (checkpoint)
-  uint32_t        n_seq;
-  int             lane;
+  int      t;         // 0..W/2-1: owns windows 2t (low half) and 2t+1 (high half)
+  int      lane, grp;
+  uint32_t g_stride;  // bytes of one row group of all the item's blocks (count * 8W)
+  uint32_t sp_off;    // byte offset of this thread's 16 bytes inside a row group
+  uint32_t s_bytes;   // bytes per input stream of the item
+  uint32_t ngroups;   // row groups per stream (L rounded up to 4, / 4)
+  const char*     in_item;  // the item's sys | par0 | par1 streams
+  const int16_t*  tail;     // this block's 12 tail samples
+  uint32_t*       A32;  // [row][32 lanes] words: extrinsic of DEC2 minus E, natural order (= a-priori of DEC1)
+  uint32_t*       E32;  // [row][32 lanes] words: a-posteriori of DEC1 minus A, in DEC2's interleaved order
+                        // (each array is written scattered by its producer and read linearly by its consumer)
+  uint4*          chk;  // beta checkpoints [chunk][half][32 lanes], already offset by lane
+  uint4*          sm;   // chunk of beta: [(s*2 + h)*kThreads], already offset by tid
+  char*           stages;  // the warp's kStages staging buffers: [sys 1 KB | par 1 KB | A or E rows 1 KB]
+  uint64_t*       mbar;    // the warp's kStages mbarriers
+  const uint16_t* rowtab;  // [2][kMaxL]    destination row of row k: dir 0 = pi (DEC2 writes A), 1 = pi^-1 (DEC1 writes E)
+  const uint8_t*  wtab;    // [2][kMaxL][8] destination windows of row k: one nibble per source window
 };
-
-// pair-major layout: int16 index of (row k, window d) and 32-bit word index of (row k, thread t)
-template <int W>
-__device__ __forceinline__ uint32_t pm_index(uint32_t k, uint32_t d)
-{
-  return (((k >> 2) * (W / 2) + (d >> 1)) << 3) + ((k & 3) << 1) + (d & 1);
-}
-template <int W>
-__device__ __forceinline__ uint32_t pm_word(uint32_t k, uint32_t t)
-{
-  return (((k >> 2) * (W / 2) + t) << 2) + (k & 3);
-}
-
-// where row k of DEC2's trellis reads its systematic input / writes its extrinsic (QPP on the fly):
-// int16 indices into the row-major A / E arrays
-template <int W>
-__device__ __forceinline__ void qpp_pair(const WinCtx<W>& c, uint32_t k, uint32_t& i_lo, uint32_t& i_hi)
-{
-  const uint32_t q = c.qtab[k], row = q & 0x1FFu, w0 = q >> 9;
-  i_lo = row * W + ((w0 + c.base_lo + c.inc_lo * k) & (W - 1));
-  i_hi = row * W + ((w0 + c.base_hi + c.inc_hi * k) & (W - 1));
-}
 
 // the inputs of 4 consecutive trellis rows (one row group) for this thread's window pair
 struct Group {
   uint32_t x[4], y[4], aux[4];
 };
 
-// ---- cp.async ring: the inputs of the next kRingDepth-1 row groups are always in flight -------------------
-// Register prefetch cannot go deeper than one group (all loads of a loop share one scoreboard slot, so waiting
-// for the oldest also waits for the newest); cp.async groups are counted separately and cost no registers.
+// ---- TMA bulk copies + mbarriers: the inputs of the next kStages-1 chunks are always in flight ---------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(void* s, const void* g)
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count)
 {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s)), "l"(g) : "memory");
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async4(void* s, const void* g)
+__device__ __forceinline__ void mbar_expect_tx(uint32_t b, uint32_t bytes)
 {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s)), "l"(g) : "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t b, uint32_t parity)
+{
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(b), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+// generic-proxy writes (st.global / st.shared) before, async-proxy (TMA) accesses after
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-struct RingPos {
-  uint32_t head, head_slot;  // next sequence entry to issue and the slot it goes to
-  uint32_t tail_slot;        // slot of the next entry to consume
+// The chunks a half iteration consumes, in order (depends only on L):
+//   phase 0: 4..0        beta over rows 39..0 (boundary metrics for the previous window)
+//   phase 1: ctop..0     beta over the window, checkpoint every kChunk rows
+//   phase 2: a0/8..ctop  alpha over rows L-40..L-1 (boundary metrics for the next window)
+//   phase 3: 0..ctop     beta rebuild + alpha + output, chunk by chunk
+struct Pipe {
+  uint32_t phase;
+  int      ch;    // next chunk to fetch
+  uint32_t slot;  // next stage to consume; it is refilled right after (the ring is always full)
+  uint32_t par;   // phase parity of every stage's mbarrier (survives across half iterations)
 };
 
-// issue the copies of sequence entry pos.head (nothing when the sequence is exhausted) and close the group
 template <int W>
-__device__ __forceinline__ void ring_issue(const WinCtx<W>& c, bool dec2, bool apriori, RingPos& pos)
+__device__ __forceinline__ void pipe_issue(const WinCtx<W>& c, bool dec2, Pipe& p, uint32_t slot)
 {
-  constexpr int WH = W / 2;
-  if (pos.head < c.n_seq) {
-    const uint32_t e    = c.seq[pos.head];
-    uint4*         slot = c.ring + pos.head_slot * 96;
-    if (e & 0x80u) {  // beta checkpoint of chunk (e & 0x7f): 8 words per lane
-      const uint32_t* src = c.chk + ((e & 0x7Fu) * 8) * 32;
-      uint32_t*       dst = reinterpret_cast<uint32_t*>(slot - c.lane) + c.lane;
-#pragma unroll
-      for (int i = 0; i < 8; i++) cp_async4(dst + i * 32, src + i * 32);
-    } else if (!dec2) {
-      const int kg = (int)e;
-      cp_async16(slot, c.sys4 + kg * WH + c.t);
-      cp_async16(slot + 32, c.par04 + kg * WH + c.t);
-      if (apriori) {
-        const uint32_t* ap = c.A32 + (kg * 4) * WH + c.t;
-        uint32_t*       d  = reinterpret_cast<uint32_t*>(slot + 64);
-#pragma unroll
-        for (int r = 0; r < 4; r++) cp_async4(d + r, ap + r * WH);
-      }
+  if (p.phase > 3) return;
+  const int ctop = (int)(c.L - 1) >> 3;
+  if (c.lane == 0) {
+    const uint32_t ch     = (uint32_t)p.ch;
+    const uint32_t gbytes = min(2u, c.ngroups - 2 * ch) * c.g_stride;
+    const uint32_t xbytes = min(8u, c.L - 8 * ch) * 128u;
+    const uint32_t mb     = smem_u32(c.mbar + slot);
+    const uint32_t dst    = smem_u32(c.stages + slot * kStageBytes);
+    const char*    g0     = c.in_item + (size_t)ch * 2 * c.g_stride;
+    mbar_expect_tx(mb, (dec2 ? gbytes : 2 * gbytes) + xbytes);
+    if (!dec2) {
+      bulk_g2s(dst, g0, gbytes, mb);
+      bulk_g2s(dst + 1024, g0 + c.s_bytes, gbytes, mb);
+      bulk_g2s(dst + 2048, reinterpret_cast<const char*>(c.A32) + (size_t)ch * 1024, xbytes, mb);
     } else {
-      const int kg = (int)e;
-      cp_async16(slot, c.par14 + kg * WH + c.t);
-      // plane 1 as [4 rows][32 lanes] words: the W/2 lanes of a code block fetch one whole row pi(k) mod L of E
-      uint32_t* d = reinterpret_cast<uint32_t*>(slot + 32 - c.lane) + c.lane;
-#pragma unroll
-      for (int r = 0; r < 4; r++) {
-        const uint32_t row = c.qtab[kg * 4 + r] & 0x1FFu;
-        cp_async4(d + r * 32, c.E32 + row * WH + c.t);
-      }
+      bulk_g2s(dst + 1024, g0 + 2 * (size_t)c.s_bytes, gbytes, mb);
+      bulk_g2s(dst + 2048, reinterpret_cast<const char*>(c.E32) + (size_t)ch * 1024, xbytes, mb);
     }
   }
-  cp_async_commit();
-  pos.head++;
-  pos.head_slot = pos.head_slot + 1 == kRingDepth ? 0 : pos.head_slot + 1;
-}
-
-// wait for the oldest entry, refill the slot that was consumed before it, return the oldest entry's slot
-template <int W>
-__device__ __forceinline__ const uint4* ring_next(const WinCtx<W>& c, bool dec2, bool apriori, RingPos& pos)
-{
-  cp_async_wait<kRingDepth - 2>();
-  __syncwarp();  // every lane's copies of this entry have landed and every lane is done reading the previous slot
-  ring_issue<W>(c, dec2, apriori, pos);
-  const uint4* slot = c.ring + pos.tail_slot * 96;
-  pos.tail_slot     = pos.tail_slot + 1 == kRingDepth ? 0 : pos.tail_slot + 1;
-  return slot;
-}
-
-template <int W>
-__device__ __forceinline__ void ring_start(const WinCtx<W>& c, bool dec2, bool apriori, RingPos& pos)
-{
-  pos.head = 0;
-  pos.head_slot = 0;
-  pos.tail_slot = 0;
-#pragma unroll
-  for (int i = 0; i < kRingDepth - 1; i++) ring_issue<W>(c, dec2, apriori, pos);
-}
-
-// FAST rows only: the next row group of the sequence (must be group kg); x = sys + a-priori with a wrapping add
-template <int W>
-__device__ __forceinline__ void fetch_group(const WinCtx<W>& c, bool dec2, bool apriori, int kg, RingPos& pos, Group& g)
-{
-  const uint4* slot = ring_next<W>(c, dec2, apriori, pos);
-  const uint4  ys   = slot[dec2 ? 0 : 32];
-  g.y[0] = ys.x; g.y[1] = ys.y; g.y[2] = ys.z; g.y[3] = ys.w;
-  if (!dec2) {
-    const uint4 xs = slot[0];
-    g.x[0] = xs.x; g.x[1] = xs.y; g.x[2] = xs.z; g.x[3] = xs.w;
-    if (apriori) {
-      const uint4 as = slot[64];
-      g.aux[0] = as.x; g.aux[1] = as.y; g.aux[2] = as.z; g.aux[3] = as.w;
-#pragma unroll
-      for (int r = 0; r < 4; r++) g.x[r] = wadd2(g.aux[r], g.x[r]);
+  if (p.phase == 0 || p.phase == 1) {
+    if (p.ch == 0) {
+      p.ch = p.phase == 0 ? ctop : (int)(c.L - kWarm) >> 3;
+      p.phase++;
     } else {
-#pragma unroll
-      for (int r = 0; r < 4; r++) g.aux[r] = 0;
+      p.ch--;
     }
   } else {
-    // the row of E fetched for trellis row k sits in plane 1 at [r][first lane of this code block ..]
-    const uint16_t* rows = reinterpret_cast<const uint16_t*>(slot + 32 - c.lane) + 2 * (c.lane - c.t);
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      const uint32_t k  = (uint32_t)(kg * 4 + r);
-      const uint32_t w0 = c.qtab[k] >> 9;
-      const uint32_t lo = rows[r * 64 + ((w0 + c.base_lo + c.inc_lo * k) & (W - 1))];
-      const uint32_t hi = rows[r * 64 + ((w0 + c.base_hi + c.inc_hi * k) & (W - 1))];
-      g.x[r]   = lo | (hi << 16);
-      g.aux[r] = g.x[r];
+    if (p.ch == ctop) {
+      p.ch = 0;
+      p.phase++;
+    } else {
+      p.ch++;
     }
   }
 }
 
-// the beta checkpoint that comes next in the sequence
 template <int W>
-__device__ __forceinline__ void fetch_checkpoint(const WinCtx<W>& c, bool dec2, bool apriori, RingPos& pos, uint32_t s[8])
+__device__ __forceinline__ void pipe_start(const WinCtx<W>& c, bool dec2, Pipe& p)
 {
-  const uint4*    slot = ring_next<W>(c, dec2, apriori, pos);
-  const uint32_t* w    = reinterpret_cast<const uint32_t*>(slot - c.lane) + c.lane;
+  p.phase = 0;
+  p.ch    = kWarm / kChunk - 1;
+  p.slot  = 0;
 #pragma unroll
-  for (int i = 0; i < 8; i++) s[i] = w[i * 32];
+  for (uint32_t s = 0; s < (uint32_t)kStages; s++) pipe_issue<W>(c, dec2, p, s);
 }
 
-// one row for the exact helpers: loads issued one row ahead, the reference's saturating a-priori add
+// wait for the oldest chunk in flight; returns its staging buffer
+template <int W>
+__device__ __forceinline__ const char* pipe_wait(const WinCtx<W>& c, Pipe& p)
+{
+  const uint32_t mb = smem_u32(c.mbar + p.slot), parity = (p.par >> p.slot) & 1u;
+  uint32_t       spins = 0;
+  while (!mbar_try_wait(mb, parity)) {
+    if (++spins > (1u << 24)) __trap();  // a lost copy must not hang the GPU
+  }
+  p.par ^= 1u << p.slot;
+  return c.stages + p.slot * kStageBytes;
+}
+
+// every lane is done reading the stage: refill it with the next chunk of the sequence
+template <int W>
+__device__ __forceinline__ void pipe_release(const WinCtx<W>& c, bool dec2, Pipe& p)
+{
+  __syncwarp();
+  pipe_issue<W>(c, dec2, p, p.slot);
+  p.slot = p.slot + 1 == (uint32_t)kStages ? 0u : p.slot + 1;
+}
+
+// FAST rows only: row group g (0 / 1) of a staged chunk; x = sys + a-priori with a wrapping add
+template <int W>
+__device__ __forceinline__ void load_group(const WinCtx<W>& c, bool dec2, const char* st, int g, Group& q)
+{
+  const uint4     ys = *reinterpret_cast<const uint4*>(st + 1024 + g * c.g_stride + c.sp_off);
+  const uint32_t* xr = reinterpret_cast<const uint32_t*>(st + 2048 + g * 512) + c.lane;
+  q.y[0] = ys.x; q.y[1] = ys.y; q.y[2] = ys.z; q.y[3] = ys.w;
+#pragma unroll
+  for (int r = 0; r < 4; r++) q.aux[r] = xr[r * 32];
+  if (!dec2) {
+    const uint4 xs = *reinterpret_cast<const uint4*>(st + g * c.g_stride + c.sp_off);
+    q.x[0] = wadd2(q.aux[0], xs.x); q.x[1] = wadd2(q.aux[1], xs.y);
+    q.x[2] = wadd2(q.aux[2], xs.z); q.x[3] = wadd2(q.aux[3], xs.w);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; r++) q.x[r] = q.aux[r];
+  }
+}
+
+template <int W>
+__device__ __forceinline__ void chk_store(const WinCtx<W>& c, int ch, const uint32_t s[8])
+{
+  c.chk[(ch * 2 + 0) * 32] = make_uint4(s[0], s[1], s[2], s[3]);
+  c.chk[(ch * 2 + 1) * 32] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+template <int W>
+__device__ __forceinline__ void chk_load(const WinCtx<W>& c, int ch, uint32_t s[8])
+{
+  const uint4 v0 = c.chk[(ch * 2 + 0) * 32], v1 = c.chk[(ch * 2 + 1) * 32];
+  s[0] = v0.x; s[1] = v0.y; s[2] = v0.z; s[3] = v0.w;
+  s[4] = v1.x; s[5] = v1.y; s[6] = v1.z; s[7] = v1.w;
+}
+
+// one row for the exact helpers: plain loads issued one row ahead, the reference's saturating a-priori add
 struct RawRow {
   uint32_t a, b, c;
 };
 
 template <int W>
-__device__ __forceinline__ void issue_row(const WinCtx<W>& c, bool dec2, bool apriori, uint32_t k, RawRow& q)
+__device__ __forceinline__ void issue_row(const WinCtx<W>& c, bool dec2, uint32_t k, RawRow& q)
 {
-  const uint32_t w = pm_word<W>(k, (uint32_t)c.t);
+  const char* gp = c.in_item + (size_t)(k >> 2) * c.g_stride + c.sp_off + (k & 3) * 4;
   if (!dec2) {
-    q.a = __ldg(reinterpret_cast<const uint32_t*>(c.sys4) + w);
-    q.b = __ldg(reinterpret_cast<const uint32_t*>(c.par04) + w);
-    q.c = apriori ? c.A32[k * (W / 2) + c.t] : 0u;
+    q.a = __ldg(reinterpret_cast<const uint32_t*>(gp));
+    q.b = __ldg(reinterpret_cast<const uint32_t*>(gp + c.s_bytes));
+    q.c = c.A32[k * 32 + c.lane];
   } else {
-    uint32_t i_lo, i_hi;
-    qpp_pair<W>(c, k, i_lo, i_hi);
-    const uint16_t* E16 = reinterpret_cast<const uint16_t*>(c.E32);
-    q.a = E16[i_lo];
-    q.c = E16[i_hi];
-    q.b = __ldg(reinterpret_cast<const uint32_t*>(c.par14) + w);
+    q.a = 0;
+    q.b = __ldg(reinterpret_cast<const uint32_t*>(gp + 2 * (size_t)c.s_bytes));
+    q.c = c.E32[k * 32 + c.lane];
   }
 }
 
-__device__ __forceinline__ void finish_row_exact(bool dec2, bool apriori, const RawRow& q, uint32_t& x, uint32_t& y,
-                                                 uint32_t& aux)
+__device__ __forceinline__ void finish_row_exact(bool dec2, const RawRow& q, uint32_t& x, uint32_t& y, uint32_t& aux)
 {
-  y = q.b;
-  if (!dec2) {
-    aux = q.c;
-    x   = apriori ? sadd2(aux, q.a) : q.a;
-  } else {
-    x   = q.a | (q.c << 16);
-    aux = x;
-  }
+  y   = q.b;
+  aux = q.c;
+  x   = dec2 ? aux : sadd2(aux, q.a);  // the a-priori array is all zero in the first half iteration
 }
 
-// store the differenced output of row k (see file header) and remember its extremes
+// store the differenced output of row k (see file header) where its consumer will read it linearly, and
+// remember its extremes.  DEC1 (natural position) -> E in DEC2's order: pi^-1;  DEC2 -> A in natural order: pi.
+// The QPP is contention free: all windows of row k go to ONE destination row, permuted among the windows.
 template <int W>
 __device__ __forceinline__ void store_out(const WinCtx<W>& c, bool dec2, uint32_t k, uint32_t o, uint32_t aux, Range& rd)
 {
   const uint32_t d = wsub2(o, aux);
   rd.add1(d);
-  if (!dec2) {
-    c.E32[k * (W / 2) + c.t] = d;
-  } else {
-    uint32_t i_lo, i_hi;
-    qpp_pair<W>(c, k, i_lo, i_hi);
-    uint16_t* A16 = reinterpret_cast<uint16_t*>(c.A32);
-    A16[i_lo]     = (uint16_t)(d & 0xFFFFu);
-    A16[i_hi]     = (uint16_t)(d >> 16);
-  }
+  const uint32_t e   = (dec2 ? 0u : (uint32_t)kMaxL) + k;
+  const uint32_t row = c.rowtab[e];
+  const uint32_t wb  = c.wtab[e * 8 + c.t];
+  uint16_t*      Y   = reinterpret_cast<uint16_t*>(dec2 ? c.A32 : c.E32) + row * 64 + c.grp * W;
+  Y[wb & 15u] = (uint16_t)(d & 0xFFFFu);
+  Y[wb >> 4]  = (uint16_t)(d >> 16);
 }
 
 // beta of the terminated last window from the 3 tail rows: plain (wrapping) int16 arithmetic.
@@ -474,26 +468,22 @@ struct RowState {
 // beta recursion over rows k_hi .. k_lo (descending).  mode 0: warm-up (nothing stored), 1: main pass
 // (checkpoint when k % kChunk == 0), 2: rebuild (B[k] -> shared memory slot k - sm_lo - 1).
 template <int W>
-__device__ __noinline__ void beta_rows_exact(const WinCtx<W> c, uint32_t flags, int k_hi, int k_lo, int mode, int sm_lo,
+__device__ __noinline__ void beta_rows_exact(const WinCtx<W> c, bool dec2, int k_hi, int k_lo, int mode, int sm_lo,
                                              RowState* st)
 {
-  const bool dec2 = flags & 1, apriori = (flags & 2) != 0;
   uint32_t   s[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) s[i] = st->s[i];
   Range trk = st->trk;
   RawRow q;
-  if (k_hi >= k_lo) issue_row<W>(c, dec2, apriori, (uint32_t)k_hi, q);
+  if (k_hi >= k_lo) issue_row<W>(c, dec2, (uint32_t)k_hi, q);
 #pragma unroll 1
   for (int k = k_hi; k >= k_lo; k--) {
     uint32_t x, y, aux;
-    finish_row_exact(dec2, apriori, q, x, y, aux);
-    if (k > k_lo) issue_row<W>(c, dec2, apriori, (uint32_t)(k - 1), q);
+    finish_row_exact(dec2, q, x, y, aux);
+    if (k > k_lo) issue_row<W>(c, dec2, (uint32_t)(k - 1), q);
     beta_step<false>(s, x, y, sadd2(x, y));
-    if (mode == 1 && (k % kChunk) == 0 && k != 0) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) c.chk[((k / kChunk - 1) * 8 + i) * 32] = s[i];
-    }
+    if (mode == 1 && (k % kChunk) == 0 && k != 0) chk_store<W>(c, k / kChunk - 1, s);
     if (mode == 2) {
       c.sm[((k - sm_lo - 1) * 2 + 0) * kThreads] = make_uint4(s[0], s[1], s[2], s[3]);
       c.sm[((k - sm_lo - 1) * 2 + 1) * kThreads] = make_uint4(s[4], s[5], s[6], s[7]);
@@ -511,22 +501,21 @@ __device__ __noinline__ void beta_rows_exact(const WinCtx<W> c, uint32_t flags, 
 // alpha recursion over rows k_lo .. k_hi (ascending).  mode 0: warm-up (normalisation counter starts at
 // k_norm0 for row k_lo, no output), 1: with a-posteriori output from the beta chunk whose base row is sm_lo.
 template <int W>
-__device__ __noinline__ void alpha_rows_exact(const WinCtx<W> c, uint32_t flags, int k_lo, int k_hi, int mode, int sm_lo,
+__device__ __noinline__ void alpha_rows_exact(const WinCtx<W> c, bool dec2, int k_lo, int k_hi, int mode, int sm_lo,
                                               int k_norm0, RowState* st)
 {
-  const bool dec2 = flags & 1, apriori = (flags & 2) != 0;
   uint32_t   a[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) a[i] = st->s[i];
   Range trk = st->trk, rd = st->rd, unused;
   unused.reset();
   RawRow q;
-  if (k_lo <= k_hi) issue_row<W>(c, dec2, apriori, (uint32_t)k_lo, q);
+  if (k_lo <= k_hi) issue_row<W>(c, dec2, (uint32_t)k_lo, q);
 #pragma unroll 1
   for (int k = k_lo; k <= k_hi; k++) {
     uint32_t x, y, aux;
-    finish_row_exact(dec2, apriori, q, x, y, aux);
-    if (k < k_hi) issue_row<W>(c, dec2, apriori, (uint32_t)(k + 1), q);
+    finish_row_exact(dec2, q, x, y, aux);
+    if (k < k_hi) issue_row<W>(c, dec2, (uint32_t)(k + 1), q);
     const int j = mode == 0 ? k_norm0 + (k - k_lo) : k;
     if (mode == 0) {
       alpha_step<false>(a, x, y, sadd2(x, y));
@@ -591,39 +580,36 @@ __device__ __forceinline__ uint32_t range_absmax(const Range& r)
 
 // ---- EXACT variant of one half iteration: the reference's saturating arithmetic on every row -------
 template <int W>
-__device__ __noinline__ HalfResult half_iteration_exact(const WinCtx<W> c, bool dec2, bool apriori)
+__device__ __noinline__ HalfResult half_iteration_exact(const WinCtx<W> c, bool dec2)
 {
   constexpr int  WH = W / 2;
   const int      L  = (int)c.L;
   const int      nchunks = (L + kChunk - 1) / kChunk;
-  const uint32_t flags = (dec2 ? 1u : 0u) | (apriori ? 2u : 0u);
   RowState       st;
   st.trk.reset();
   st.rd.reset();
 #pragma unroll
   for (int i = 0; i < 8; i++) st.s[i] = kNegInf2;
-  beta_rows_exact<W>(c, flags, kWarm - 1, 0, 0, 0, &st);
+  beta_rows_exact<W>(c, dec2, kWarm - 1, 0, 0, 0, &st);
   exchange_beta_boundary<WH>(st.s, c.t, c.tail + (dec2 ? 6 : 0));
-#pragma unroll
-  for (int i = 0; i < 8; i++) c.chk[((nchunks - 1) * 8 + i) * 32] = st.s[i];
-  beta_rows_exact<W>(c, flags, L - 1, 0, 1, 0, &st);
+  chk_store<W>(c, nchunks - 1, st.s);
+  beta_rows_exact<W>(c, dec2, L - 1, 0, 1, 0, &st);
 
   RowState al;
   al.trk.reset();
   al.rd.reset();
 #pragma unroll
   for (int i = 0; i < 8; i++) al.s[i] = kNegInf2;
-  alpha_rows_exact<W>(c, flags, L - kWarm, L - 1, 0, 0, 0, &al);
+  alpha_rows_exact<W>(c, dec2, L - kWarm, L - 1, 0, 0, 0, &al);
   exchange_alpha_boundary<WH>(al.s, c.t);
   for (int ch = 0; ch < nchunks; ch++) {
     const int lo = ch * kChunk, hi = min(lo + kChunk, L);
-#pragma unroll
-    for (int i = 0; i < 8; i++) st.s[i] = c.chk[(ch * 8 + i) * 32];
+    chk_load<W>(c, ch, st.s);
     c.sm[((hi - lo - 1) * 2 + 0) * kThreads] = make_uint4(st.s[0], st.s[1], st.s[2], st.s[3]);
     c.sm[((hi - lo - 1) * 2 + 1) * kThreads] = make_uint4(st.s[4], st.s[5], st.s[6], st.s[7]);
     if (hi != L) normalize<false>(st.s);  // hi is even and non-zero: the backward pass normalised after storing
-    beta_rows_exact<W>(c, flags, hi - 1, lo + 1, 2, lo, &st);
-    alpha_rows_exact<W>(c, flags, lo, hi - 1, 1, lo, 0, &al);
+    beta_rows_exact<W>(c, dec2, hi - 1, lo + 1, 2, lo, &st);
+    alpha_rows_exact<W>(c, dec2, lo, hi - 1, 1, lo, 0, &al);
   }
   __syncwarp();
   HalfResult res;
@@ -634,29 +620,26 @@ __device__ __noinline__ HalfResult half_iteration_exact(const WinCtx<W> c, bool 
 
 // ---- FAST variant: wrapping adds fused with max, plus (TRACK) the bookkeeping that proves it equals the exact one
 // G bounds |x|, |y| and |x + y| of every row of this code block in this half iteration.
-// The row groups are consumed in exactly the order build_sequence() lists them.
-// Code size matters here: in steady state the warps of an SM are in different phases, and the instruction
-// cache has to hold all of them.  DEC1 / DEC2 therefore share one instantiation (they differ only in how a
-// row group is fetched and stored) and the two backward loops (boundary warm-up, window) are one loop.
+// DEC1 and DEC2 share one instantiation (they differ only in which streams a chunk holds): in steady state the
+// 12 warps of an SM run the same code, and the hot loops (backward 4 rows, rebuild + forward 8 rows) fit the
+// instruction cache.
 template <int W, bool TRACK>
-__device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bool dec2, bool apriori, int G)
+__device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bool dec2, int G, Pipe& p)
 {
-  constexpr int  WH = W / 2;
-  const int      L  = (int)c.L;
-  const int      nchunks = (L + kChunk - 1) / kChunk;
-  const uint32_t flags = (dec2 ? 1u : 0u) | (apriori ? 2u : 0u);
-  // rows [4, kf] are covered by full row groups of fast arithmetic; rows above kf (next to the terminated
-  // tail) and rows 0..3 of the forward pass (next to the known start state) always use exact arithmetic
-  const int gtop = (L - kExactRows) / 4 - 1;  // last fully fast group
-  const int kf   = gtop * 4 + 3;              // last fast row (kf <= L - kExactRows - 1)
+  constexpr int WH = W / 2;
+  const int     L  = (int)c.L;
+  const int     ctop = (L - 1) >> 3;
+  // rows [kExactRows, kf] use fast arithmetic in the forward pass, rows [0, kf] in the backward pass; the rows
+  // next to the terminated tail (above kf: 4 to 7 rows, so that a row group is either all fast or all exact) and
+  // next to the known start state (0..3, forward) are always exact
+  const int kf = ((L - kExactRows) & ~3) - 1;
+  const int a0 = L - kWarm;  // first row of the alpha warm-up
   uint32_t  s[8];
-  Group     g;
-  RingPos   pos;
   Range     rb, ra, rm, rd;
   rb.reset(); ra.reset(); rd.reset();
   rm.hi = kMin2; rm.lo = kMax2;
   RowState st;
-  ring_start<W>(c, dec2, apriori, pos);
+  pipe_start<W>(c, dec2, p);
 
   // ---------------- backward pass ----------------
   // phase 0: boundary metrics from the next window's first 40 rows; phase 1: the window itself with a
@@ -666,30 +649,34 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
 #pragma unroll 1
   for (int phase = 0; phase < 2; phase++) {
 #pragma unroll 1
-    for (int kg = phase ? gtop : kWarm / 4 - 1; kg >= 0; kg--) {
-      fetch_group<W>(c, dec2, apriori, kg, pos, g);
+    for (int ch = phase ? ctop : kWarm / kChunk - 1; ch >= 0; ch--) {
+      const char* stg = pipe_wait<W>(c, p);
+#pragma unroll 1
+      for (int g = 1; g >= 0; g--) {
+        const int k0 = ch * kChunk + g * 4;
+        if (k0 > kf) continue;
+        Group q;
+        load_group<W>(c, dec2, stg, g, q);
 #pragma unroll
-      for (int r = 3; r >= 0; r--) {
-        beta_step<true>(s, g.x[r], g.y[r], wadd2(g.x[r], g.y[r]));
-        if (r == 0 && phase && (kg % (kChunk / 4)) == 0 && kg != 0) {
-#pragma unroll
-          for (int i = 0; i < 8; i++) c.chk[((kg / (kChunk / 4) - 1) * 8 + i) * 32] = s[i];
-        }
-        if ((r & 1) == 0 && (kg | r) != 0) {
-          normalize<true>(s);
-          if (TRACK) rb.add8(s);
+        for (int r = 3; r >= 0; r--) {
+          beta_step<true>(s, q.x[r], q.y[r], wadd2(q.x[r], q.y[r]));
+          if (r == 0 && g == 0 && phase && ch != 0) chk_store<W>(c, ch - 1, s);
+          if ((r & 1) == 0 && (k0 | r) != 0) {
+            normalize<true>(s);
+            if (TRACK) rb.add8(s);
+          }
         }
       }
+      pipe_release<W>(c, dec2, p);
     }
     if (phase == 0) {
       exchange_beta_boundary<WH>(s, c.t, c.tail + (dec2 ? 6 : 0));
-#pragma unroll
-      for (int i = 0; i < 8; i++) c.chk[((nchunks - 1) * 8 + i) * 32] = s[i];
+      chk_store<W>(c, ctop, s);
       // the rows next to the terminated tail: exact
 #pragma unroll
       for (int i = 0; i < 8; i++) st.s[i] = s[i];
       st.trk = rb;
-      beta_rows_exact<W>(c, flags, L - 1, kf + 1, 1, 0, &st);
+      beta_rows_exact<W>(c, dec2, L - 1, kf + 1, 1, 0, &st);
 #pragma unroll
       for (int i = 0; i < 8; i++) s[i] = st.s[i];
       rb = st.trk;
@@ -698,50 +685,44 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
 
   // ---------------- forward pass: boundary metrics from the previous window's last 40 rows ----------------
   uint32_t a[8];
-  {
-    const int a0 = L - kWarm;      // first warm-up row
-    const int ga = (a0 + 3) >> 2;  // first full group
-    const int gb = (L >> 2) - 1;   // last full group
 #pragma unroll
-    for (int i = 0; i < 8; i++) st.s[i] = kNegInf2;
-    st.trk = ra;
-    if (ga * 4 > a0) alpha_rows_exact<W>(c, flags, a0, ga * 4 - 1, 0, 0, 0, &st);
-#pragma unroll
-    for (int i = 0; i < 8; i++) a[i] = st.s[i];
-    ra = st.trk;
+  for (int i = 0; i < 8; i++) a[i] = kNegInf2;
 #pragma unroll 1
-    for (int kg = ga; kg <= gb; kg++) {
-      fetch_group<W>(c, dec2, apriori, kg, pos, g);
+  for (int ch = a0 >> 3; ch <= ctop; ch++) {
+    const char* stg = pipe_wait<W>(c, p);
+#pragma unroll 1
+    for (int g = 0; g < 2; g++) {
+      const int k0 = ch * kChunk + g * 4;
+      if (k0 + 3 < a0 || k0 >= L) continue;
+      Group q;
+      load_group<W>(c, dec2, stg, g, q);
 #pragma unroll
       for (int r = 0; r < 4; r++) {
-        const int j = kg * 4 + r - a0;  // the reference normalises on the warm-up counter
-        alpha_step<true>(a, g.x[r], g.y[r], wadd2(g.x[r], g.y[r]));
+        const int j = k0 + r - a0;  // the reference normalises on the warm-up counter
+        if (j < 0 || k0 + r >= L) continue;
+        alpha_step<true>(a, q.x[r], q.y[r], wadd2(q.x[r], q.y[r]));
         if ((j & 1) == 0 && j != 0) {
           normalize<true>(a);
           if (TRACK) ra.add8(a);
         }
       }
     }
-    if ((gb + 1) * 4 < L) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) st.s[i] = a[i];
-      st.trk = ra;
-      alpha_rows_exact<W>(c, flags, (gb + 1) * 4, L - 1, 0, 0, (gb + 1) * 4 - a0, &st);
-#pragma unroll
-      for (int i = 0; i < 8; i++) a[i] = st.s[i];
-      ra = st.trk;
-    }
+    pipe_release<W>(c, dec2, p);
   }
   exchange_alpha_boundary<WH>(a, c.t);
 
   // ---------------- forward pass over the window, chunk by chunk ----------------
+  uint32_t nxt[8];  // checkpoint of the next chunk, loaded one chunk ahead
+  chk_load<W>(c, 0, nxt);
 #pragma unroll 1
-  for (int ch = 0; ch < nchunks; ch++) {
+  for (int ch = 0; ch <= ctop; ch++) {
     const int lo = ch * kChunk;
     const int hi = min(lo + kChunk, L);
-    const int g_lo = lo >> 2, g_hi = min((hi - 1) >> 2, gtop);  // fast groups of this chunk (may be empty)
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = nxt[i];
+    if (ch < ctop) chk_load<W>(c, ch + 1, nxt);
+    const char* stg = pipe_wait<W>(c, p);
     // rebuild B[lo+1 .. hi] into shared memory, slot (k - lo - 1) holds B[k]
-    fetch_checkpoint<W>(c, dec2, apriori, pos, s);
     c.sm[((hi - lo - 1) * 2 + 0) * kThreads] = make_uint4(s[0], s[1], s[2], s[3]);
     c.sm[((hi - lo - 1) * 2 + 1) * kThreads] = make_uint4(s[4], s[5], s[6], s[7]);
     if (hi != L) {  // hi is even and non-zero: the backward pass normalised after storing
@@ -754,68 +735,70 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
 #pragma unroll
       for (int i = 0; i < 8; i++) st.s[i] = s[i];
       st.trk.reset();
-      beta_rows_exact<W>(c, flags, hi - 1, max(kf, lo) + 1, 2, lo, &st);
+      beta_rows_exact<W>(c, dec2, hi - 1, max(kf, lo) + 1, 2, lo, &st);
 #pragma unroll
       for (int i = 0; i < 8; i++) s[i] = st.s[i];
     }
 #pragma unroll 1
-    for (int kg = g_hi; kg >= g_lo; kg--) {
-      fetch_group<W>(c, dec2, apriori, kg, pos, g);
+    for (int g = 1; g >= 0; g--) {
+      if (lo + g * 4 > kf) continue;
+      Group q;
+      load_group<W>(c, dec2, stg, g, q);
+      uint4* bs = c.sm + (g * 4 - 1) * 2 * kThreads;
 #pragma unroll
       for (int r = 3; r >= 0; r--) {
-        const int k = kg * 4 + r;
-        if (r == 0 && kg == g_lo) continue;  // B[lo] belongs to the chunk below
-        beta_step<true>(s, g.x[r], g.y[r], wadd2(g.x[r], g.y[r]));
-        c.sm[((k - lo - 1) * 2 + 0) * kThreads] = make_uint4(s[0], s[1], s[2], s[3]);
-        c.sm[((k - lo - 1) * 2 + 1) * kThreads] = make_uint4(s[4], s[5], s[6], s[7]);
+        if (r == 0 && g == 0) continue;  // B[lo] belongs to the chunk below
+        beta_step<true>(s, q.x[r], q.y[r], wadd2(q.x[r], q.y[r]));
+        bs[(r * 2 + 0) * kThreads] = make_uint4(s[0], s[1], s[2], s[3]);
+        bs[(r * 2 + 1) * kThreads] = make_uint4(s[4], s[5], s[6], s[7]);
         if ((r & 1) == 0) normalize<true>(s);
       }
     }
     // alpha recursion + a-posteriori output over the chunk
-    int ga = g_lo;
     if (ch == 0) {  // rows 0..3 next to the known start state: exact
 #pragma unroll
       for (int i = 0; i < 8; i++) st.s[i] = a[i];
       st.trk = ra;
       st.rd  = rd;
-      alpha_rows_exact<W>(c, flags, 0, min(kExactRows, hi) - 1, 1, lo, 0, &st);
+      alpha_rows_exact<W>(c, dec2, 0, kExactRows - 1, 1, lo, 0, &st);
 #pragma unroll
       for (int i = 0; i < 8; i++) a[i] = st.s[i];
       ra = st.trk;
       rd = st.rd;
-      ga = 1;
     }
 #pragma unroll 1
-    for (int kg = ga; kg <= g_hi; kg++) {
-      fetch_group<W>(c, dec2, apriori, kg, pos, g);
+    for (int g = ch == 0 ? 1 : 0; g < 2; g++) {
+      if (lo + g * 4 > kf) continue;
+      Group q;
+      load_group<W>(c, dec2, stg, g, q);
+      const uint4* bs = c.sm + g * 4 * 2 * kThreads;
 #pragma unroll
       for (int r = 0; r < 4; r++) {
-        const int      k  = kg * 4 + r;
-        const uint4    b0 = c.sm[((k - lo) * 2 + 0) * kThreads];
-        const uint4    b1 = c.sm[((k - lo) * 2 + 1) * kThreads];
+        const uint4    b0 = bs[(r * 2 + 0) * kThreads];
+        const uint4    b1 = bs[(r * 2 + 1) * kThreads];
         const uint32_t bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        uint32_t       o = alpha_out_step<true, TRACK>(a, bb, g.x[r], g.y[r], wadd2(g.x[r], g.y[r]), rm);
+        uint32_t       o = alpha_out_step<true, TRACK>(a, bb, q.x[r], q.y[r], wadd2(q.x[r], q.y[r]), rm);
         if (W == 8) o = sra1_2(o);  // the 8-window (sse16) decoder halves its output
-        store_out<W>(c, dec2, (uint32_t)k, o, g.aux[r], rd);
+        store_out<W>(c, dec2, (uint32_t)(lo + g * 4 + r), o, q.aux[r], rd);
         if ((r & 1) == 0) {
           normalize<true>(a);
           if (TRACK) ra.add8(a);
         }
       }
     }
+    pipe_release<W>(c, dec2, p);
     if (hi - 1 > kf) {  // rows next to the tail: exact
 #pragma unroll
       for (int i = 0; i < 8; i++) st.s[i] = a[i];
       st.trk = ra;
       st.rd  = rd;
-      alpha_rows_exact<W>(c, flags, max(max(kf, lo - 1) + 1, ch == 0 ? kExactRows : 0), hi - 1, 1, lo, 0, &st);
+      alpha_rows_exact<W>(c, dec2, max(kf + 1, lo), hi - 1, 1, lo, 0, &st);
 #pragma unroll
       for (int i = 0; i < 8; i++) a[i] = st.s[i];
       ra = st.trk;
       rd = st.rd;
     }
   }
-  cp_async_wait<0>();
   __syncwarp();
 
   HalfResult res;
@@ -848,30 +831,41 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
   return res;
 }
 
-// the order in which a fast half iteration consumes row groups and checkpoints (depends only on L)
+// QPP of this K as destination tables, computed from (f1, f2) by the whole CTA:
+//   pi(d*L + k) = pi(k) + L * d * (f1 + f2*d*L + 2*f2*k)  (mod K = W*L), so with pi(k) = w0*L + r every window
+//   d of row k lands in row r, window (w0 + d*(f1 + f2*d*L) + 2*f2*d*k) mod W.
+// dir 0 holds pi (where DEC2's row k goes in natural order), dir 1 its inverse (where natural row r goes in
+// DEC2's order).
 template <int W>
-__device__ uint32_t build_sequence(uint32_t L32, uint8_t* seq)
+__device__ void build_tables(uint32_t K, uint32_t f1, uint32_t f2, uint16_t* rowtab, uint8_t* wtab)
 {
-  const int L = (int)L32, nchunks = (L + kChunk - 1) / kChunk;
-  const int gtop = (L - kExactRows) / 4 - 1;
-  int       n = 0;
-  for (int kg = kWarm / 4 - 1; kg >= 0; kg--) seq[n++] = (uint8_t)kg;
-  for (int kg = gtop; kg >= 0; kg--) seq[n++] = (uint8_t)kg;
-  for (int kg = (L - kWarm + 3) >> 2; kg <= (L >> 2) - 1; kg++) seq[n++] = (uint8_t)kg;
-  for (int ch = 0; ch < nchunks; ch++) {
-    const int lo = ch * kChunk, hi = min(lo + kChunk, L);
-    const int g_lo = lo >> 2, g_hi = min((hi - 1) >> 2, gtop);
-    seq[n++] = (uint8_t)(0x80 | ch);
-    for (int kg = g_hi; kg >= g_lo; kg--) seq[n++] = (uint8_t)kg;
-    for (int kg = ch == 0 ? 1 : g_lo; kg <= g_hi; kg++) seq[n++] = (uint8_t)kg;
+  const uint32_t L  = K / W;
+  const uint32_t mK = (uint32_t)(0x100000000ull / K);
+  const uint32_t mL = (uint32_t)((0x100000000ull + L - 1) / L);
+  for (uint32_t k = threadIdx.x; k < L; k += blockDim.x) {
+    const uint32_t v = (f1 + f2 * k) * k;  // k < L <= 384 keeps it below 2^32
+    uint32_t       p = v - __umulhi(v, mK) * K;
+    if (p >= K) p -= K;
+    if (p >= K) p -= K;
+    const uint32_t w0 = __umulhi(p, mL), r = p - w0 * L;
+    uint64_t       fw = 0, iv = 0;
+#pragma unroll
+    for (uint32_t d = 0; d < (uint32_t)W; d++) {
+      const uint32_t w = (w0 + d * (f1 + f2 * d * L) + 2 * f2 * d * k) & (uint32_t)(W - 1);
+      fw |= (uint64_t)w << (4 * d);
+      iv |= (uint64_t)d << (4 * w);
+    }
+    rowtab[k]         = (uint16_t)r;
+    rowtab[kMaxL + r] = (uint16_t)k;
+    *reinterpret_cast<uint64_t*>(wtab + 8 * k)           = fw;
+    *reinterpret_cast<uint64_t*>(wtab + 8 * (kMaxL + r)) = iv;
   }
-  return (uint32_t)n;
 }
 
-// hard decision of this code block: bit n = (A[n] + E[n] > 0), MSB first.
+// hard decision of this code block: bit n = (A[n] + E[pi^-1(n)] > 0), MSB first.
 // Phase 1: every thread turns its two windows into bit strings (32 rows per word) in shared memory;
-// phase 2: bytes are cut out of the concatenated window strings.  `bits` is per-warp scratch (the beta
-// chunk area, free between half iterations): [group][window][word].
+// phase 2: bytes are cut out of the concatenated window strings.  The bit strings live in the group's own beta
+// chunk slots (free between half iterations).
 template <int W>
 __device__ void decide(const WinCtx<W>& c, uint8_t* out, bool write)
 {
@@ -885,31 +879,24 @@ __device__ void decide(const WinCtx<W>& c, uint8_t* out, bool write)
   auto      word     = [&](uint32_t f) -> uint32_t& {
     return grp_base[(((f >> 2) / WH) * kThreads + ((f >> 2) % WH)) * 4 + (f & 3)];
   };
+  const uint16_t* E16 = reinterpret_cast<const uint16_t*>(c.E32) + c.grp * W;
   uint32_t  acc_lo = 0, acc_hi = 0;
 #pragma unroll 4
-  for (uint32_t kg = 0; kg * 4 < L; kg++) {
-    uint32_t v[4];
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      const uint32_t k = min(kg * 4 + r, L - 1);
-      v[r] = wadd2(c.A32[k * WH + c.t], c.E32[k * WH + c.t]);
-    }
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      const uint32_t k = kg * 4 + r;
-      if (k < L) {
-        // sign bit of -(max(v, -1)) is set exactly when v > 0 (no overflow: max(v,-1) >= -1)
-        const uint32_t m = wneg2(max2(v[r], 0xFFFFFFFFu));
-        acc_lo = (acc_lo << 1) | ((m >> 15) & 1u);
-        acc_hi = (acc_hi << 1) | (m >> 31);
-        if ((k & 31) == 31 || k == L - 1) {
-          const uint32_t sh = 31 - (k & 31);  // left-align a partial last word
-          word((2 * c.t) * NW + (k >> 5))     = acc_lo << sh;
-          word((2 * c.t + 1) * NW + (k >> 5)) = acc_hi << sh;
-          acc_lo = 0;
-          acc_hi = 0;
-        }
-      }
+  for (uint32_t k = 0; k < L; k++) {
+    const uint32_t row = c.rowtab[kMaxL + k];
+    const uint32_t wb  = c.wtab[(kMaxL + k) * 8 + c.t];
+    const uint32_t e   = (uint32_t)E16[row * 64 + (wb & 15u)] | ((uint32_t)E16[row * 64 + (wb >> 4)] << 16);
+    const uint32_t v   = wadd2(c.A32[k * 32 + c.lane], e);
+    // sign bit of -(max(v, -1)) is set exactly when v > 0 (no overflow: max(v,-1) >= -1)
+    const uint32_t m = wneg2(max2(v, 0xFFFFFFFFu));
+    acc_lo = (acc_lo << 1) | ((m >> 15) & 1u);
+    acc_hi = (acc_hi << 1) | (m >> 31);
+    if ((k & 31) == 31 || k == L - 1) {
+      const uint32_t sh = 31 - (k & 31);  // left-align a partial last word
+      word((2 * c.t) * NW + (k >> 5))     = acc_lo << sh;
+      word((2 * c.t + 1) * NW + (k >> 5)) = acc_hi << sh;
+      acc_lo = 0;
+      acc_hi = 0;
     }
   }
   __syncwarp();
@@ -958,145 +945,139 @@ __device__ __forceinline__ uint32_t group_max(uint32_t v)
   return v;
 }
 
+// One CTA per SM.  The CTA takes kWarps consecutive work items at a time; the host pads the item list so that
+// they all have the same K (items with count 0 are fillers): the QPP tables are built once per CTA round, and the
+// warps run the same phase of the same code at the same time (one copy of the hot loops in the instruction cache).
 template <int W>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const TdecLaunch a)
 {
   constexpr int WH  = W / 2;
   constexpr int CBW = 32 / WH;
-  constexpr uint32_t KMAX = (W == 16) ? kAeStride16 : kAeStride8;
   extern __shared__ uint4 smem[];
-  uint4*    ring_all = smem + kChunk * 2 * kThreads;                                  // [warps][kRingDepth][3][32]
-  uint16_t* qtab_all = reinterpret_cast<uint16_t*>(ring_all + (kThreads / 32) * kRingDepth * 96);
-  uint8_t*  seq_all  = reinterpret_cast<uint8_t*>(qtab_all + (kThreads / 32) * kMaxL);
+  char*     stages_all = reinterpret_cast<char*>(smem + kChunk * 2 * kThreads);  // [warps][kStages][kStageBytes]
+  uint16_t* rowtab     = reinterpret_cast<uint16_t*>(stages_all + kWarps * kStages * kStageBytes);
+  uint8_t*  wtab       = reinterpret_cast<uint8_t*>(rowtab + 2 * kMaxL);
+  uint64_t* mbar_all   = reinterpret_cast<uint64_t*>(wtab + 2 * kMaxL * 8);
+  __shared__ uint32_t s_item;
 
   const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int      grp = lane / WH, t = lane % WH;
-  const uint32_t slot = blockIdx.x * (kThreads / 32) + warp;
-  uint16_t*      qtab = qtab_all + warp * kMaxL;
-  uint8_t*       seq  = seq_all + warp * kSeqMax;
+  const uint32_t slot = blockIdx.x * kWarps + warp;
   uint32_t       fallbacks = 0;
+  Pipe           pipe;
+  pipe.par = 0;
+  if (lane == 0) {
+    for (int s = 0; s < kStages; s++) mbar_init(mbar_all + warp * kStages + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_proxy_async();
+  __syncthreads();
 
   for (;;) {
-    uint32_t it = 0;
-    if (lane == 0) it = atomicAdd(a.counter, 1u);
-    it = __shfl_sync(0xFFFFFFFFu, it, 0);
-    // The warps of the CTA start their items together: work items of equal K take equal time, so the warps
-    // stay in the same phase of the half iteration and share the instruction cache instead of thrashing it.
-    if (!__syncthreads_or(it < a.n_items)) break;
-    if (it >= a.n_items) continue;
-    const WorkItem wi     = a.items[it];
-    const bool     active = grp < (int)wi.count;
-    const uint32_t cb     = a.order[wi.first + (active ? grp : 0)];
-
-    WinCtx<W> c;
-    c.K = wi.K;
-    c.L = c.K / W;
-    c.t = t;
-    const uint32_t f1 = wi.f1, f2 = wi.f2;
+    if (tid == 0) s_item = atomicAdd(a.counter, (uint32_t)kWarps);
+    __syncthreads();
+    const uint32_t it0 = s_item;
+    if (it0 >= a.n_items) break;
     {
-      const uint32_t d0 = 2 * (uint32_t)t, d1 = d0 + 1;
-      c.base_lo = (d0 * (f1 + f2 * d0 * c.L)) & (W - 1);
-      c.base_hi = (d1 * (f1 + f2 * d1 * c.L)) & (W - 1);
-      c.inc_lo  = (2 * f2 * d0) & (W - 1);
-      c.inc_hi  = (2 * f2 * d1) & (W - 1);
+      const WorkItem w0 = a.items[it0];
+      build_tables<W>(w0.K, w0.f1, w0.f2, rowtab, wtab);
     }
-    // pi(k) for k < L, computed here from (f1, f2): row = pi(k) mod L, window = pi(k) / L
-    {
-      const uint32_t mK = (uint32_t)(0x100000000ull / c.K);
-      const uint32_t mL = (uint32_t)((0x100000000ull + c.L - 1) / c.L);
-      __syncwarp();
-      for (uint32_t k = (uint32_t)lane; k < c.L; k += 32) {
-        const uint32_t v = (f1 + f2 * k) * k;  // k < L <= 384 keeps it below 2^32
-        uint32_t       p = v - __umulhi(v, mK) * c.K;
-        if (p >= c.K) p -= c.K;
-        if (p >= c.K) p -= c.K;
-        const uint32_t w0 = __umulhi(p, mL);
-        qtab[k]           = (uint16_t)((p - w0 * c.L) | (w0 << 9));
-      }
-      uint32_t n_seq = 0;
-      if (lane == 0) n_seq = build_sequence<W>(c.L, seq);
-      c.n_seq = __shfl_sync(0xFFFFFFFFu, n_seq, 0);
-      __syncwarp();
-    }
-    c.qtab = qtab;
-    c.seq  = seq;
-    c.lane = lane;
-    c.ring = ring_all + warp * kRingDepth * 96 + lane;
-    const uint32_t Lp = (c.L + 3) & ~3u;
-    const uint32_t S  = Lp * W;  // int16 per stream
-    const int16_t* in = a.in + (size_t)cb * a.in_stride;
-    c.sys4  = reinterpret_cast<const uint4*>(in);
-    c.par04 = reinterpret_cast<const uint4*>(in + S);
-    c.par14 = reinterpret_cast<const uint4*>(in + 2 * S);
-    c.tail  = in + 3 * S;
-    const uint16_t* meta = reinterpret_cast<const uint16_t*>(in + 3 * S + 16);
-    const int smax = meta[0], p0max = meta[1], p1max = meta[2];
-    // development probe (force_exact bit 1): every warp of a CTA row shares workspace slot -> always cache resident
-    const uint32_t ws_slot = (a.force_exact & 2u) ? (slot & 3u) : slot;
-    int16_t* ae = a.ws_ae + ((size_t)ws_slot * CBW + grp) * 2 * KMAX;
-    c.A32 = reinterpret_cast<uint32_t*>(ae);
-    c.E32 = reinterpret_cast<uint32_t*>(ae + KMAX);
-    c.chk = a.ws_chk + (size_t)ws_slot * kChkSlotWords + lane;
-    c.sm  = smem + tid;
+    __syncthreads();
+    const uint32_t it = it0 + (uint32_t)warp;
+    WorkItem       wi;
+    wi.count = 0;
+    if (it < a.n_items) wi = a.items[it];
+    if (wi.count != 0) {
+      const bool     active = grp < (int)wi.count;
+      const uint32_t b_eff  = active ? (uint32_t)grp : 0u;  // idle groups of a partial item shadow block 0
+      const uint32_t cb     = a.order[wi.first + b_eff];
 
-    for (uint32_t k = 0; k < c.L; k++) c.A32[k * WH + t] = 0;
-    __syncwarp();
+      WinCtx<W> c;
+      c.K = wi.K;
+      c.L = c.K / W;
+      c.t = t;
+      c.lane = lane;
+      c.grp  = grp;
+      c.ngroups  = (c.L + 3) >> 2;
+      c.g_stride = (uint32_t)wi.count * 8u * W;
+      c.sp_off   = b_eff * 8u * W + (uint32_t)t * 16u;
+      c.s_bytes  = c.ngroups * c.g_stride;
+      c.in_item  = reinterpret_cast<const char*>(a.in + (size_t)wi.first * a.in_stride);
+      c.tail     = reinterpret_cast<const int16_t*>(c.in_item + 3 * (size_t)c.s_bytes) + b_eff * 32;
+      c.rowtab = rowtab;
+      c.wtab   = wtab;
+      c.stages = stages_all + warp * kStages * kStageBytes;
+      c.mbar   = mbar_all + warp * kStages;
+      const uint16_t* meta = reinterpret_cast<const uint16_t*>(c.tail + 16);
+      const int smax = meta[0], p0max = meta[1], p1max = meta[2];
+      constexpr size_t XB = (W == 16) ? kXArrayBytes16 : kXArrayBytes8;
+      char* ae = reinterpret_cast<char*>(a.ws_ae) + (size_t)slot * 2 * XB;
+      c.A32 = reinterpret_cast<uint32_t*>(ae);
+      c.E32 = reinterpret_cast<uint32_t*>(ae + XB);
+      c.chk = reinterpret_cast<uint4*>(reinterpret_cast<char*>(a.ws_chk) + (size_t)slot * kChkSlotBytes) + lane;
+      c.sm  = smem + tid;
 
-    uint8_t* out  = a.out + (size_t)cb * a.out_stride;
-    uint32_t n    = 0, iters = 0;
-    bool     done = false, ok = false;
-    int      amax = 0, emax = 0;  // max |A|, max |E| over the code block
-    const uint32_t crc_mode = a.crc_mode_cb ? a.crc_mode_cb[cb] : a.crc_mode;
-    const int      which    = crc_mode == CRC_24A ? 0 : 1;
-    const bool     any_crc  = __any_sync(0xFFFFFFFFu, crc_mode != CRC_NONE);
-    do {
-      const bool dec2 = (n & 1) != 0, apriori = n > 0;
-      // bound on |x|, |y|, |x + y| of this half iteration
-      const int Gx = dec2 ? emax : (apriori ? smax + amax : smax);
-      const int G  = Gx + (dec2 ? p1max : p0max);
-      HalfResult r;
-      bool       fast_ok = false;
-      // the decision must be warp-uniform: the passes below use full-warp shuffles and votes
-      if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kStaticFastG)) {
-        r       = half_iteration_fast<W, false>(c, dec2, apriori, G);
-        fast_ok = true;
-      } else if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kMaxFastG)) {
-        r       = half_iteration_fast<W, true>(c, dec2, apriori, G);
-        fast_ok = __all_sync(0xFFFFFFFFu, r.proven);
-      }
-      if (!fast_ok) {
-        r = half_iteration_exact<W>(c, dec2, apriori);
-        fallbacks++;
-      }
-      const int dm = (int)group_max<WH>(r.dmax);
-      if (dec2) amax = dm; else emax = dm;
-      n++;
-      if (any_crc) {
-        const bool check = crc_mode != CRC_NONE && !done && active;
-        decide<W>(c, out, check);
-        uint32_t crc = 1;
-        if (check && t == 0) crc = crc24_bytes_dev(which, out, c.K / 8);
-        crc = __shfl_sync(0xFFFFFFFFu, crc, grp * WH);
-        if (check) {
-          iters = n;
-          if (crc == 0) {
-            ok   = true;
-            done = true;
+      for (uint32_t k = 0; k < c.L; k++) c.A32[k * 32 + lane] = 0;
+
+      uint8_t* out  = a.out + (size_t)cb * a.out_stride;
+      uint32_t n    = 0, iters = 0;
+      bool     done = false, ok = false;
+      int      amax = 0, emax = 0;  // max |A|, max |E| over the code block
+      const uint32_t crc_mode = a.crc_mode_cb ? a.crc_mode_cb[cb] : a.crc_mode;
+      const int      which    = crc_mode == CRC_24A ? 0 : 1;
+      const bool     any_crc  = __any_sync(0xFFFFFFFFu, crc_mode != CRC_NONE);
+      do {
+        const bool dec2 = (n & 1) != 0;
+        // what the previous half iteration (or the clearing above) stored must be visible to the bulk copies
+        fence_proxy_async();
+        __syncwarp();
+        // bound on |x|, |y|, |x + y| of this half iteration
+        const int Gx = dec2 ? emax : smax + amax;
+        const int G  = Gx + (dec2 ? p1max : p0max);
+        HalfResult r;
+        bool       fast_ok = false;
+        // the decision must be warp-uniform: the passes below use full-warp shuffles and votes
+        if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kStaticFastG)) {
+          r       = half_iteration_fast<W, false>(c, dec2, G, pipe);
+          fast_ok = true;
+        } else if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kMaxFastG)) {
+          r       = half_iteration_fast<W, true>(c, dec2, G, pipe);
+          fast_ok = __all_sync(0xFFFFFFFFu, r.proven);
+        }
+        if (!fast_ok) {
+          r = half_iteration_exact<W>(c, dec2);
+          fallbacks++;
+        }
+        const int dm = (int)group_max<WH>(r.dmax);
+        if (dec2) amax = dm; else emax = dm;
+        n++;
+        if (any_crc) {
+          const bool check = crc_mode != CRC_NONE && !done && active;
+          decide<W>(c, out, check);
+          uint32_t crc = 1;
+          if (check && t == 0) crc = crc24_bytes_dev(which, out, c.K / 8);
+          crc = __shfl_sync(0xFFFFFFFFu, crc, grp * WH);
+          if (check) {
+            iters = n;
+            if (crc == 0) {
+              ok   = true;
+              done = true;
+            }
           }
         }
+      } while (n < a.max_iter && !__all_sync(0xFFFFFFFFu, done || !active));
+      if (crc_mode == CRC_NONE) {
+        decide<W>(c, out, active);
+        iters = n;
+      } else if (!any_crc) {
+        iters = n;
       }
-    } while (n < a.max_iter && !__all_sync(0xFFFFFFFFu, done || !active));
-    if (crc_mode == CRC_NONE) {
-      decide<W>(c, out, active);
-      iters = n;
-    } else if (!any_crc) {
-      iters = n;
+      if (active && t == 0) {
+        if (a.n_iter) a.n_iter[cb] = (uint8_t)iters;
+        if (a.crc_ok) a.crc_ok[cb] = ok ? 1 : 0;
+      }
     }
-    if (active && t == 0) {
-      if (a.n_iter) a.n_iter[cb] = (uint8_t)iters;
-      if (a.crc_ok) a.crc_ok[cb] = ok ? 1 : 0;
-    }
-    __syncwarp();
+    __syncthreads();  // every warp is done with the tables (and with s_item)
   }
   if (lane == 0 && fallbacks && a.stats) atomicAdd(a.stats, fallbacks);
 }
@@ -1217,7 +1198,7 @@ __global__ void __launch_bounds__(kThreads) tdec_gen_kernel(const TdecLaunch a)
     c.K    = wi.K;
     c.f1   = wi.f1;
     c.f2   = wi.f2;
-    c.in   = a.in + (size_t)cb * a.in_stride;
+    c.in   = a.in + (size_t)(wi.first + (active ? lane : 0)) * a.in_stride;  // blocks are stored by schedule position
     c.A    = a.ws_ae + ((size_t)slot * 32 + lane) * 2 * KMAX;
     c.E    = c.A + KMAX;
     c.beta = reinterpret_cast<uint4*>(a.ws_chk) + (size_t)slot * (KMAX + 4) * 32 + lane;
@@ -1260,10 +1241,14 @@ __global__ void __launch_bounds__(kThreads) tdec_gen_kernel(const TdecLaunch a)
 }
 
 // ---- layout conversion into the decoder's internal layout -----------------------------------------
-// window decoders: [sys | par0 | par1] pair-major streams of Lp*W int16 each (Lp = L rounded up to 4),
-//                  then 16 int16 holding the 12 tail samples, then 16 int16 of meta data:
+// Every code block is stored at its position in the decode schedule (dst_stride int16 per block); the blocks
+// of one work item (`count` blocks of equal K starting at position `first`) are interleaved:
+// window decoders: [sys | par0 | par1] streams; a stream is [row group of 4][block of the item][thread][4 rows]
+//                  32-bit words (two windows each), Lp = L rounded up to 4 rows;
+//                  then per block 16 int16 holding the 12 tail samples and 16 int16 of meta data:
 //                  max |sys|, max |par0|, max |par1| (uint16) -- the inputs of the fast-path proof.
-// generic decoder: the natural 3i+j order unchanged.
+// generic decoder: the natural 3i+j order unchanged, one block after the other.
+// place[cb] = (first, count << 8 | index in the item); without it the schedule is the identity (uniform K).
 __device__ __forceinline__ uint32_t windows_of(uint32_t K)
 {
   return (K % 16 == 0 && K > 800) ? 16u : (K % 8 == 0 && K > 400) ? 8u : 0u;
@@ -1273,20 +1258,35 @@ __device__ __forceinline__ uint32_t windows_of(uint32_t K)
 __global__ void __launch_bounds__(256) to_internal_kernel(const int16_t* __restrict__ src_all, uint32_t src_stride,
                                                           int16_t* __restrict__ dst_all, uint32_t dst_stride,
                                                           const uint32_t* __restrict__ cb_K, uint32_t uniform_K,
-                                                          uint32_t src_format, const uint64_t* __restrict__ src_off)
+                                                          uint32_t src_format, const uint64_t* __restrict__ src_off,
+                                                          const uint2* __restrict__ place)
 {
   extern __shared__ int16_t stage[];  // natural input of one code block (format 0 only)
   __shared__ uint32_t s_max[3];
   const uint32_t cb = blockIdx.x;
   const uint32_t K  = cb_K ? cb_K[cb] : uniform_K;
   const int16_t* src = src_all + (src_off ? (size_t)src_off[cb] : (size_t)cb * src_stride);
-  int16_t*       dst = dst_all + (size_t)cb * dst_stride;
   const uint32_t W = windows_of(K);
+  uint32_t       first, cnt, b;
+  if (place) {
+    const uint2 pl = place[cb];
+    first = pl.x;
+    cnt   = pl.y >> 8;
+    b     = pl.y & 0xFFu;
+  } else {
+    const uint32_t per = W ? 64u / W : 32u;  // code blocks per work item
+    first = cb / per * per;
+    cnt   = min(per, gridDim.x - first);
+    b     = cb - first;
+  }
   if (W == 0) {
+    int16_t* dst = dst_all + (size_t)(first + b) * dst_stride;
     for (uint32_t i = threadIdx.x; i < 3 * K + 12; i += blockDim.x) dst[i] = src[i];
     return;
   }
   const uint32_t L = K / W, Lp = (L + 3) & ~3u, WH = W / 2, S = Lp * W;
+  int16_t*       item = dst_all + (size_t)first * dst_stride;  // the work item's interleaved storage
+  int16_t*       tailp = item + 3 * (size_t)cnt * S + b * 32;
   // the staged copy gives every window 2 extra int16 so that the W/2 threads that later read the same row of
   // different windows fall into different shared-memory banks (3L int16 per window is a multiple of 64 words
   // for L = 384: an 8-way conflict without the padding)
@@ -1329,10 +1329,10 @@ __global__ void __launch_bounds__(256) to_internal_kernel(const int16_t* __restr
       mx[j] = max(mx[j], (uint32_t)max(abs(lo), abs(hi)));
       w[r]  = (uint32_t)(uint16_t)lo | ((uint32_t)(uint16_t)hi << 16);
     }
-    reinterpret_cast<uint4*>(dst + j * S)[kg * WH + t] = make_uint4(w[0], w[1], w[2], w[3]);
+    reinterpret_cast<uint4*>(item + (size_t)j * cnt * S)[(kg * cnt + b) * WH + t] = make_uint4(w[0], w[1], w[2], w[3]);
   }
   const int16_t* tl = src_format == 0 ? stage + W * wstride : src + 3 * (K + 32);
-  if (threadIdx.x < 16) dst[3 * S + threadIdx.x] = threadIdx.x < 12 ? tl[threadIdx.x] : (int16_t)0;
+  if (threadIdx.x < 16) tailp[threadIdx.x] = threadIdx.x < 12 ? tl[threadIdx.x] : (int16_t)0;
 #pragma unroll
   for (int j = 0; j < 3; j++) {
     uint32_t v = mx[j];
@@ -1341,7 +1341,7 @@ __global__ void __launch_bounds__(256) to_internal_kernel(const int16_t* __restr
   }
   __syncthreads();
   if (threadIdx.x < 16) {
-    uint16_t* meta = reinterpret_cast<uint16_t*>(dst + 3 * S + 16);
+    uint16_t* meta = reinterpret_cast<uint16_t*>(tailp + 16);
     meta[threadIdx.x] = threadIdx.x < 3 ? (uint16_t)s_max[threadIdx.x] : (uint16_t)0;
   }
 }
@@ -1380,6 +1380,10 @@ void upload_crc_tables()
 
 int tdec_blocks_per_warp(int W) { return W == 16 ? 4 : W == 8 ? 8 : 32; }
 
+// the window kernels take this many consecutive work items per CTA round; they must share K (host pads with
+// count-0 items).  1 for the generic kernel.
+int tdec_items_per_cta(int W) { return W ? kWarps : 1; }
+
 uint32_t internal_len(uint32_t K)
 {
   const uint32_t W = (K % 16 == 0 && K > 800) ? 16u : (K % 8 == 0 && K > 400) ? 8u : 0u;
@@ -1403,8 +1407,8 @@ cudaError_t tdec_geometry(int W, int device, TdecGeometry* g)
     g->ws_chk_bytes = slots * (400 + 4) * 32 * sizeof(uint4);
     return cudaSuccess;
   }
-  g->smem = (size_t)kChunk * 2 * kThreads * sizeof(uint4) + warps_per_block * kRingDepth * 96 * sizeof(uint4) +
-            warps_per_block * kMaxL * sizeof(uint16_t) + warps_per_block * kSeqMax;
+  g->smem = (size_t)kChunk * 2 * kThreads * sizeof(uint4) + warps_per_block * kStages * kStageBytes +
+            2 * kMaxL * sizeof(uint16_t) + 2 * kMaxL * 8 + warps_per_block * kStages * sizeof(uint64_t);
   int per_sm = 0;
   if (W == 16) {
     e = cudaFuncSetAttribute(tdec_win_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
@@ -1421,9 +1425,8 @@ cudaError_t tdec_geometry(int W, int device, TdecGeometry* g)
   }
   g->blocks = sms * per_sm;
   const size_t slots = (size_t)g->blocks * warps_per_block;
-  const size_t kmax  = W == 16 ? kAeStride16 : kAeStride8;
-  g->ws_ae_bytes  = slots * (size_t)tdec_blocks_per_warp(W) * 2 * kmax * sizeof(int16_t);
-  g->ws_chk_bytes = slots * kChkSlotWords * sizeof(uint32_t);
+  g->ws_ae_bytes  = slots * 2 * (W == 16 ? kXArrayBytes16 : kXArrayBytes8);
+  g->ws_chk_bytes = slots * kChkSlotBytes;
   return cudaSuccess;
 }
 
@@ -1432,7 +1435,7 @@ cudaError_t tdec_launch(int W, const TdecGeometry& g, const TdecLaunch& a, cudaS
   if (a.n_items == 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
-  const int want   = (int)((a.n_items + (kThreads / 32) - 1) / (kThreads / 32));
+  const int want   = (int)((a.n_items + (kThreads / 32) - 1) / (kThreads / 32));  // CTA rounds (window kernels)
   const int blocks = want < g.blocks ? want : g.blocks;
   if (W == 16)
     tdec_win_kernel<16><<<blocks, g.threads, g.smem, s>>>(a);
@@ -1445,7 +1448,7 @@ cudaError_t tdec_launch(int W, const TdecGeometry& g, const TdecLaunch& a, cudaS
 
 cudaError_t to_internal_launch(const int16_t* src, uint32_t src_stride, const uint64_t* src_off, int src_format,
                                int16_t* dst, uint32_t dst_stride, const uint32_t* cb_K, uint32_t uniform_K,
-                               uint32_t n_cb, cudaStream_t s)
+                               const uint2* place, uint32_t n_cb, cudaStream_t s)
 {
   if (n_cb == 0) return cudaSuccess;
   static bool attr_set = false;
@@ -1457,7 +1460,7 @@ cudaError_t to_internal_launch(const int16_t* src, uint32_t src_stride, const ui
     attr_set = true;
   }
   to_internal_kernel<<<n_cb, 256, smem, s>>>(src, src_stride, dst, dst_stride, cb_K, uniform_K, (uint32_t)src_format,
-                                             src_off);
+                                             src_off, place);
   return cudaGetLastError();
 }
 
@@ -1470,3 +1473,4 @@ cudaError_t rm_rx_launch(const int16_t* e, int16_t* work, const uint16_t* tab_po
 }
 
 }  // namespace b200
+

@@ -20,8 +20,8 @@ enum CrcMode : uint32_t {
 };
 
 struct TdecLaunch {
-  const int16_t*  in;          // internal-layout input of every code block (device), see to_internal_launch
-  uint32_t        in_stride;   // int16 elements between code blocks (even)
+  const int16_t*  in;          // internal-layout input (device), indexed by schedule position, see to_internal_launch
+  uint32_t        in_stride;   // int16 elements per code block (multiple of 64)
   uint8_t*        out;         // decoded bytes (device)
   uint32_t        out_stride;  // bytes between code blocks
   uint8_t*        n_iter;      // [n_cb] half iterations run (device, nullable)
@@ -51,6 +51,7 @@ struct TdecGeometry {
 cudaError_t tdec_geometry(int W, int device, TdecGeometry* g);
 cudaError_t tdec_launch(int W, const TdecGeometry& g, const TdecLaunch& a, cudaStream_t s);
 int         tdec_blocks_per_warp(int W);
+int         tdec_items_per_cta(int W);  // consecutive work items a CTA takes per round; they must share K
 
 // int16 elements of one code block in the decoder's internal layout (pair-major streams + tail + meta
 // for window decoders, natural order for the generic decoder).
@@ -59,9 +60,12 @@ uint32_t internal_len(uint32_t K);
 // src_format 0: natural (3i+j, tails last); 1: the reference's sub-block soft-buffer layout.
 // One code block per CTA; also records max |sys|, |par0|, |par1| per block for the fast-path proof.
 // The source of block i is src + src_off[i] when src_off (device, int16 elements) is given, else src + i*src_stride.
+// Blocks are written at their position in the decode schedule, the blocks of one work item interleaved:
+// place[i] = (first position of i's work item, count << 8 | index in the item) (device); nullptr = the identity
+// schedule of a uniform-K batch.
 cudaError_t to_internal_launch(const int16_t* src, uint32_t src_stride, const uint64_t* src_off, int src_format,
                                int16_t* dst, uint32_t dst_stride, const uint32_t* cb_K /* device, nullable */,
-                               uint32_t uniform_K, uint32_t n_cb, cudaStream_t s);
+                               uint32_t uniform_K, const uint2* place, uint32_t n_cb, cudaStream_t s);
 
 // rate de-matching: work[tab[i mod N]] += e[i], i < E, wrapping int16.
 struct RmItem {
