@@ -49,6 +49,7 @@ constexpr int      kWarps     = kThreads / 32;
 constexpr int      kBlocksPerSm = 1;
 constexpr int      kMaxChunks = 48;  // ceil(384 / 8)
 constexpr int      kMaxL      = 384;
+constexpr int      kChkAhead  = 4;   // forward pass: checkpoints are prefetched into L2 this many chunks ahead
 constexpr int      kStages    = 3;   // chunks in flight per warp (TMA bulk copies, one mbarrier per stage)
 constexpr int      kStageBytes = 3072;  // [sys | par | A or E] x 1 KB: 8 rows of all the code blocks of a warp
 // per-warp-slot workspace strides are not powers of two: warps run in near lock step, and power-of-two
@@ -385,6 +386,13 @@ __device__ __forceinline__ void chk_store(const WinCtx<W>& c, int ch, const uint
   c.chk[(ch * 2 + 0) * 32] = make_uint4(s[0], s[1], s[2], s[3]);
   c.chk[(ch * 2 + 1) * 32] = make_uint4(s[4], s[5], s[6], s[7]);
 }
+// checkpoints come back from HBM in the forward pass: pull them into L2 a few chunks before they are loaded
+template <int W>
+__device__ __forceinline__ void chk_prefetch_l2(const WinCtx<W>& c, int ch)
+{
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(c.chk + (ch * 2 + 0) * 32));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(c.chk + (ch * 2 + 1) * 32));
+}
 template <int W>
 __device__ __forceinline__ void chk_load(const WinCtx<W>& c, int ch, uint32_t s[8])
 {
@@ -712,8 +720,11 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
   exchange_alpha_boundary<WH>(a, c.t);
 
   // ---------------- forward pass over the window, chunk by chunk ----------------
-  uint32_t nxt[8];  // checkpoint of the next chunk, loaded one chunk ahead
+  uint32_t nxt[8];  // checkpoint of the next chunk, loaded one chunk ahead (and prefetched into L2 kChkAhead ahead)
   chk_load<W>(c, 0, nxt);
+#pragma unroll
+  for (int i = 1; i < kChkAhead; i++)
+    if (i <= ctop) chk_prefetch_l2<W>(c, i);
 #pragma unroll 1
   for (int ch = 0; ch <= ctop; ch++) {
     const int lo = ch * kChunk;
@@ -721,6 +732,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
 #pragma unroll
     for (int i = 0; i < 8; i++) s[i] = nxt[i];
     if (ch < ctop) chk_load<W>(c, ch + 1, nxt);
+    if (ch + kChkAhead <= ctop) chk_prefetch_l2<W>(c, ch + kChkAhead);
     const char* stg = pipe_wait<W>(c, p);
     // rebuild B[lo+1 .. hi] into shared memory, slot (k - lo - 1) holds B[k]
     c.sm[((hi - lo - 1) * 2 + 0) * kThreads] = make_uint4(s[0], s[1], s[2], s[3]);
@@ -881,22 +893,36 @@ __device__ void decide(const WinCtx<W>& c, uint8_t* out, bool write)
   };
   const uint16_t* E16 = reinterpret_cast<const uint16_t*>(c.E32) + c.grp * W;
   uint32_t  acc_lo = 0, acc_hi = 0;
-#pragma unroll 4
-  for (uint32_t k = 0; k < L; k++) {
-    const uint32_t row = c.rowtab[kMaxL + k];
-    const uint32_t wb  = c.wtab[(kMaxL + k) * 8 + c.t];
-    const uint32_t e   = (uint32_t)E16[row * 64 + (wb & 15u)] | ((uint32_t)E16[row * 64 + (wb >> 4)] << 16);
-    const uint32_t v   = wadd2(c.A32[k * 32 + c.lane], e);
-    // sign bit of -(max(v, -1)) is set exactly when v > 0 (no overflow: max(v,-1) >= -1)
-    const uint32_t m = wneg2(max2(v, 0xFFFFFFFFu));
-    acc_lo = (acc_lo << 1) | ((m >> 15) & 1u);
-    acc_hi = (acc_hi << 1) | (m >> 31);
-    if ((k & 31) == 31 || k == L - 1) {
-      const uint32_t sh = 31 - (k & 31);  // left-align a partial last word
-      word((2 * c.t) * NW + (k >> 5))     = acc_lo << sh;
-      word((2 * c.t + 1) * NW + (k >> 5)) = acc_hi << sh;
-      acc_lo = 0;
-      acc_hi = 0;
+  constexpr int NB = 16;  // rows gathered per batch: the E gather is latency bound, keep many loads in flight
+#pragma unroll 1
+  for (uint32_t k0 = 0; k0 < L; k0 += NB) {
+    uint32_t av[NB], el[NB], eh[NB];
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      const uint32_t k   = min(k0 + j, L - 1);
+      const uint32_t row = c.rowtab[kMaxL + k];
+      const uint32_t wb  = c.wtab[(kMaxL + k) * 8 + c.t];
+      el[j] = E16[row * 64 + (wb & 15u)];
+      eh[j] = E16[row * 64 + (wb >> 4)];
+      av[j] = c.A32[k * 32 + c.lane];
+    }
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      const uint32_t k = k0 + j;
+      if (k < L) {
+        const uint32_t v = wadd2(av[j], el[j] | (eh[j] << 16));
+        // sign bit of -(max(v, -1)) is set exactly when v > 0 (no overflow: max(v,-1) >= -1)
+        const uint32_t m = wneg2(max2(v, 0xFFFFFFFFu));
+        acc_lo = (acc_lo << 1) | ((m >> 15) & 1u);
+        acc_hi = (acc_hi << 1) | (m >> 31);
+        if ((k & 31) == 31 || k == L - 1) {
+          const uint32_t sh = 31 - (k & 31);  // left-align a partial last word
+          word((2 * c.t) * NW + (k >> 5))     = acc_lo << sh;
+          word((2 * c.t + 1) * NW + (k >> 5)) = acc_hi << sh;
+          acc_lo = 0;
+          acc_hi = 0;
+        }
+      }
     }
   }
   __syncwarp();
