@@ -76,12 +76,16 @@ struct Schedule {  // how the code blocks of one launch map onto warps
   std::vector<uint2>    place;  // per code block: (first position of its work item, count << 8 | index in the item)
   std::vector<WorkItem> items[3];
   uint32_t              item_base[3] = {0, 0, 0};
+  // window regimes: the CTA rounds (first item, number of items <= tdec_items_per_cta) in launch order
+  std::vector<uint2>    rounds[2];
+  uint32_t              round_base[2] = {0, 0};
 };
 
 }  // namespace
 
 struct srslte_b200_ctx {
   int          device      = 0;
+  int          sm_count    = 1;
   cudaStream_t own_stream  = nullptr;
   cudaStream_t stream      = nullptr;  // where *_dev work goes
   cudaStream_t h2d_stream  = nullptr;
@@ -93,8 +97,8 @@ struct srslte_b200_ctx {
   DevBuf<uint32_t> d_order;
   DevBuf<WorkItem> d_items;
   DevBuf<uint32_t> d_cbK;
-  DevBuf<uint2>    d_place;
-  PinBuf<uint2>    h_place;
+  DevBuf<uint2>    d_place, d_rounds;
+  PinBuf<uint2>    h_place, h_rounds;
   PinBuf<uint32_t> h_order;
   PinBuf<WorkItem> h_items;
   PinBuf<uint32_t> h_cbK;
@@ -182,6 +186,34 @@ int ensure_regime(srslte_b200_ctx* ctx, int ri)
   return 0;
 }
 
+// Cut the (padded) item lists of the window regimes into CTA rounds.  Rounds of equal K take equal time, so the
+// launch runs in waves of one round per SM; the rounds of the last, partial wave are split into up to 4 smaller
+// rounds each so that they spread over the idle SMs (a warp that shares its SM with fewer warps runs faster).
+void build_rounds(srslte_b200_ctx* ctx, Schedule& s)
+{
+  for (int ri = 0; ri < 2; ri++) {
+    auto&          R   = s.rounds[ri];
+    const uint32_t per = (uint32_t)tdec_items_per_cta(ri == 0 ? 16 : 8);
+    R.clear();
+    const auto& items = s.items[ri];
+    for (uint32_t i = 0; i < items.size(); i += per) R.push_back(make_uint2(i, per));
+    const uint32_t G = (uint32_t)std::max(1, ctx->sm_count);
+    const uint32_t last = (uint32_t)(R.size() % G);
+    const uint32_t q = last ? std::min(4u, G / last) : 1u;
+    if (q >= 2) {
+      std::vector<uint2> tail(R.end() - last, R.end());
+      R.resize(R.size() - last);
+      for (const uint2& r : tail)
+        for (uint32_t j = 0; j < q; j++) {
+          const uint2 sub = make_uint2(r.x + j * (per / q), per / q);
+          bool any = false;
+          for (uint32_t k = 0; k < sub.y; k++) any = any || items[sub.x + k].count != 0;
+          if (any) R.push_back(sub);
+        }
+    }
+  }
+}
+
 // Group the blocks [0, n) by K (largest first, so the longest work starts first) and cut each
 // group into warp-sized items.  The window kernels take tdec_items_per_cta() consecutive items per CTA round
 // and need them to share K: every K group is padded to a multiple of that with empty items.
@@ -218,6 +250,7 @@ int build_schedule(srslte_b200_ctx* ctx, const uint32_t* K, uint32_t uniform_K, 
       return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "invalid code block size %u", uniform_K);
     for (uint32_t i = 0; i < n; i++) s.order[i] = i;
     emit(uniform_K, 0, n);
+    build_rounds(ctx, s);
     return 0;
   }
   std::vector<uint32_t> cnt(kNofCbSizes + 1, 0);
@@ -233,6 +266,7 @@ int build_schedule(srslte_b200_ctx* ctx, const uint32_t* K, uint32_t uniform_K, 
   for (uint32_t i = 0; i < n; i++) s.order[fill[kNofCbSizes - 1 - idx[i]]++] = i;
   for (int b = 0; b < kNofCbSizes; b++)
     if (cnt[b]) emit(kQpp[kNofCbSizes - 1 - b].K, start[b], cnt[b]);
+  build_rounds(ctx, s);
   return 0;
 }
 
@@ -256,8 +290,20 @@ int ensure_schedule(srslte_b200_ctx* ctx, const uint32_t* K, uint32_t uniform_K,
     s.item_base[r] = (uint32_t)n_items;
     n_items += s.items[r].size();
   }
+  size_t n_rounds = 0;
+  for (int r = 0; r < 2; r++) {
+    s.round_base[r] = (uint32_t)n_rounds;
+    n_rounds += s.rounds[r].size();
+  }
   // the pinned staging may still be in flight from a previous upload
   CU(cudaStreamSynchronize(st));
+  CU(ctx->h_rounds.reserve(n_rounds + 1));
+  CU(ctx->d_rounds.reserve(n_rounds + 1));
+  for (int r = 0; r < 2; r++)
+    if (!s.rounds[r].empty())
+      std::memcpy(ctx->h_rounds.p + s.round_base[r], s.rounds[r].data(), s.rounds[r].size() * sizeof(uint2));
+  if (n_rounds)
+    CU(cudaMemcpyAsync(ctx->d_rounds.p, ctx->h_rounds.p, n_rounds * sizeof(uint2), cudaMemcpyHostToDevice, st));
   CU(ctx->h_order.reserve(n));
   CU(ctx->h_items.reserve(n_items));
   CU(ctx->d_order.reserve(n));
@@ -350,6 +396,8 @@ int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint
     a.order      = ctx->d_order.p;
     a.items      = ctx->d_items.p + ctx->sched.item_base[r];
     a.n_items    = (uint32_t)items.size();
+    a.rounds     = r < 2 ? ctx->d_rounds.p + ctx->sched.round_base[r] : nullptr;
+    a.n_rounds   = r < 2 ? (uint32_t)ctx->sched.rounds[r].size() : 0u;
     a.counter    = ctx->counters.p + r;
     a.max_iter   = b->nof_iterations;
     a.crc_mode   = b->crc_mode;
@@ -383,6 +431,7 @@ int srslte_b200_ctx_create(srslte_b200_ctx_t** out, int cuda_device)
   }
   srslte_b200_ctx* ctx = new srslte_b200_ctx();
   ctx->device          = cuda_device;
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, cuda_device);
   if (cudaSetDevice(cuda_device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -417,6 +466,8 @@ void srslte_b200_ctx_destroy(srslte_b200_ctx_t* ctx)
   ctx->d_cbK.release();
   ctx->d_place.release();
   ctx->h_place.release();
+  ctx->d_rounds.release();
+  ctx->h_rounds.release();
   ctx->h_order.release();
   ctx->h_items.release();
   ctx->h_cbK.release();

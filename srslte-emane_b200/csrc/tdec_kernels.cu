@@ -1000,19 +1000,19 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
   __syncthreads();
 
   for (;;) {
-    if (tid == 0) s_item = atomicAdd(a.counter, (uint32_t)kWarps);
+    if (tid == 0) s_item = atomicAdd(a.counter, 1u);
     __syncthreads();
-    const uint32_t it0 = s_item;
-    if (it0 >= a.n_items) break;
+    const uint32_t rnd = s_item;
+    if (rnd >= a.n_rounds) break;
+    const uint2 round = a.rounds[rnd];  // (first item, number of items): one item per warp, all of the same K
     {
-      const WorkItem w0 = a.items[it0];
+      const WorkItem w0 = a.items[round.x];
       build_tables<W>(w0.K, w0.f1, w0.f2, rowtab, wtab);
     }
     __syncthreads();
-    const uint32_t it = it0 + (uint32_t)warp;
-    WorkItem       wi;
+    WorkItem wi;
     wi.count = 0;
-    if (it < a.n_items) wi = a.items[it];
+    if ((uint32_t)warp < round.y) wi = a.items[round.x + (uint32_t)warp];
     if (wi.count != 0) {
       const bool     active = grp < (int)wi.count;
       const uint32_t b_eff  = active ? (uint32_t)grp : 0u;  // idle groups of a partial item shadow block 0
@@ -1458,10 +1458,10 @@ cudaError_t tdec_geometry(int W, int device, TdecGeometry* g)
 
 cudaError_t tdec_launch(int W, const TdecGeometry& g, const TdecLaunch& a, cudaStream_t s)
 {
-  if (a.n_items == 0) return cudaSuccess;
+  if (a.n_items == 0 || (W && a.n_rounds == 0)) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
-  const int want   = (int)((a.n_items + (kThreads / 32) - 1) / (kThreads / 32));  // CTA rounds (window kernels)
+  const int want   = W ? (int)a.n_rounds : (int)((a.n_items + (kThreads / 32) - 1) / (kThreads / 32));
   const int blocks = want < g.blocks ? want : g.blocks;
   if (W == 16)
     tdec_win_kernel<16><<<blocks, g.threads, g.smem, s>>>(a);

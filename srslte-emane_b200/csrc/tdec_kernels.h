@@ -29,6 +29,8 @@ struct TdecLaunch {
   const uint32_t* order;       // code-block indices grouped by K (device)
   const WorkItem* items;       // device
   uint32_t        n_items;
+  const uint2*    rounds;      // window kernels: CTA rounds (first item, items <= tdec_items_per_cta(), same K) (device)
+  uint32_t        n_rounds;
   uint32_t*       counter;     // device work counter, zeroed by the launcher
   uint32_t        max_iter;    // half-iteration cap
   uint32_t        crc_mode;
