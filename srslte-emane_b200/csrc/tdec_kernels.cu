@@ -57,7 +57,7 @@ constexpr int      kStageBytes = 3072;  // [sys | par | A or E] x 1 KB: 8 rows o
 constexpr size_t   kXArrayBytes16 = (size_t)(kMaxL + 1) * 128;  // one A or E array: rows of 32 words (all blocks of a warp)
 constexpr size_t   kXArrayBytes8  = (size_t)(100 + 1) * 128;    // W = 8: K <= 800, L <= 100
 constexpr size_t   kChkSlotBytes  = (size_t)kMaxChunks * 1024 + 128;
-constexpr int      kStagePad  = 2;   // int16 of padding per window in to_internal_kernel's staged copy
+constexpr int      kStagePad  = 4;   // int16 of padding per window in to_internal_kernel's staged copy
 constexpr int      kExactRows = 4;   // rows next to a known-state boundary always use exact arithmetic
 constexpr int      kStaticFastG = 2978; // 11 * G <= 32767: the fast variant needs no bookkeeping at all
 constexpr int      kMaxFastG  = 5461; // largest per-step metric change the fast variant accepts (6 * G <= 32767)
@@ -1313,14 +1313,23 @@ __global__ void __launch_bounds__(256) to_internal_kernel(const int16_t* __restr
   const uint32_t L = K / W, Lp = (L + 3) & ~3u, WH = W / 2, S = Lp * W;
   int16_t*       item = dst_all + (size_t)first * dst_stride;  // the work item's interleaved storage
   int16_t*       tailp = item + 3 * (size_t)cnt * S + b * 32;
-  // the staged copy gives every window 2 extra int16 so that the W/2 threads that later read the same row of
-  // different windows fall into different shared-memory banks (3L int16 per window is a multiple of 64 words
-  // for L = 384: an 8-way conflict without the padding)
+  // the staged copy gives every window kStagePad extra int16 so that the W/2 threads that later read the same
+  // row of different windows fall into different shared-memory banks (3L int16 per window is a multiple of 64
+  // words for L = 384: an 8-way conflict without the padding)
   const uint32_t wstride = 3 * L + kStagePad;
   if (threadIdx.x < 3) s_max[threadIdx.x] = 0;
   if (src_format == 0) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    if (((3 * L) & 1) == 0) {  // window starts are word aligned: 32-bit copies
+    if (((3 * L) & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 7) == 0) {  // 8-byte aligned window starts
+      const uint2* s64 = reinterpret_cast<const uint2*>(src);
+      uint2*       t64 = reinterpret_cast<uint2*>(stage);
+      for (uint32_t d = warp; d < W; d += nwarps) {
+        const uint2* sp = s64 + d * (3 * L / 4);
+        uint2*       tp = t64 + d * (wstride / 4);
+#pragma unroll 4
+        for (uint32_t p = lane; p < 3 * L / 4; p += 32) tp[p] = __ldg(sp + p);
+      }
+    } else if (((3 * L) & 1) == 0) {  // window starts are word aligned: 32-bit copies
       const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
       uint32_t*       t32 = reinterpret_cast<uint32_t*>(stage);
       for (uint32_t d = warp; d < W; d += nwarps)
@@ -1333,30 +1342,38 @@ __global__ void __launch_bounds__(256) to_internal_kernel(const int16_t* __restr
   }
   __syncthreads();
   const uint32_t groups = Lp / 4;
-  uint32_t       mx[3]  = {0, 0, 0};
-  for (uint32_t o = threadIdx.x; o < 3 * groups * WH; o += blockDim.x) {
-    const uint32_t j = o / (groups * WH), rem = o - j * groups * WH;
-    const uint32_t kg = rem / WH, t = rem - kg * WH;
-    uint32_t       w[4];
+  // one thread = one window pair t of one row group kg: 4 rows x 3 streams in, three 128-bit words out
+  const uint32_t t = threadIdx.x % WH, ng = blockDim.x / WH;
+  uint32_t       mx2[3] = {0, 0, 0};  // packed unsigned max of |.| per stream
+  for (uint32_t kg = threadIdx.x / WH; kg < groups; kg += ng) {
+    uint32_t w[3][4];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       const uint32_t k = kg * 4 + r;
-      int            lo = 0, hi = 0;
+#pragma unroll
+      for (int j = 0; j < 3; j++) w[j][r] = 0;
       if (k < L) {
         if (src_format == 0) {
-          lo = stage[(2 * t) * wstride + 3 * k + j];
-          hi = stage[(2 * t + 1) * wstride + 3 * k + j];
+          const int16_t* pl = stage + (2 * t) * wstride + 3 * k;
+          const int16_t* ph = pl + wstride;
+#pragma unroll
+          for (int j = 0; j < 3; j++) w[j][r] = (uint32_t)(uint16_t)pl[j] | ((uint32_t)(uint16_t)ph[j] << 16);
         } else {
-          const uint32_t v = reinterpret_cast<const uint32_t*>(src + j * (K + 32))[k * WH + t];
-          lo = (int16_t)(v & 0xFFFFu);
-          hi = (int16_t)(v >> 16);
+#pragma unroll
+          for (int j = 0; j < 3; j++) w[j][r] = reinterpret_cast<const uint32_t*>(src + j * (K + 32))[k * WH + t];
         }
       }
-      mx[j] = max(mx[j], (uint32_t)max(abs(lo), abs(hi)));
-      w[r]  = (uint32_t)(uint16_t)lo | ((uint32_t)(uint16_t)hi << 16);
+#pragma unroll
+      for (int j = 0; j < 3; j++) mx2[j] = __vmaxu2(mx2[j], __vabs2(w[j][r]));
     }
-    reinterpret_cast<uint4*>(item + (size_t)j * cnt * S)[(kg * cnt + b) * WH + t] = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+      reinterpret_cast<uint4*>(item + (size_t)j * cnt * S)[(kg * cnt + b) * WH + t] =
+          make_uint4(w[j][0], w[j][1], w[j][2], w[j][3]);
   }
+  uint32_t mx[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) mx[j] = max(mx2[j] & 0xFFFFu, mx2[j] >> 16);
   const int16_t* tl = src_format == 0 ? stage + W * wstride : src + 3 * (K + 32);
   if (threadIdx.x < 16) tailp[threadIdx.x] = threadIdx.x < 12 ? tl[threadIdx.x] : (int16_t)0;
 #pragma unroll
