@@ -178,7 +178,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--blocks", type=int, default=65536, help="code blocks per GPU per step")
-    ap.add_argument("--e2e-blocks", type=int, default=32768, help="code blocks per GPU for the host-pointer leg")
+    ap.add_argument("--e2e-blocks", type=int, default=65536, help="code blocks per GPU for the host-pointer leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
 
