@@ -166,9 +166,10 @@ __device__ __forceinline__ void alpha_step(uint32_t a[8], uint32_t x, uint32_t y
 }
 
 // alpha recursion + a-posteriori output (max over bit-1 branches minus max over bit-0 branches)
+// aux: FAST only -- returns out - aux (the differenced value that is stored), saving one packed subtraction
 template <bool FAST, bool TRACK = true>
 __device__ __forceinline__ uint32_t alpha_out_step(uint32_t a[8], const uint32_t bb[8], uint32_t x, uint32_t y,
-                                                   uint32_t xy, Range& rm)
+                                                   uint32_t xy, Range& rm, uint32_t aux = 0)
 {
   uint32_t m[8], n[8], M0, M1, o;
   if (FAST) {
@@ -184,7 +185,7 @@ __device__ __forceinline__ uint32_t alpha_out_step(uint32_t a[8], const uint32_t
       M1 = addmax2(bb[i], n[i], M1);
     }
     if (TRACK) rm.add2v(M0, M1);
-    o = wsub2(M1, M0);
+    o = wsub2(M1, wadd2(M0, aux));
   } else {
     m[0] = a[0];            m[1] = sadd2(a[3], y);  m[2] = sadd2(a[4], y);  m[3] = a[7];
     m[4] = a[1];            m[5] = sadd2(a[2], y);  m[6] = sadd2(a[5], y);  m[7] = a[6];
@@ -432,9 +433,8 @@ __device__ __forceinline__ void finish_row_exact(bool dec2, const RawRow& q, uin
 // remember its extremes.  DEC1 (natural position) -> E in DEC2's order: pi^-1;  DEC2 -> A in natural order: pi.
 // The QPP is contention free: all windows of row k go to ONE destination row, permuted among the windows.
 template <int W>
-__device__ __forceinline__ void store_out(const WinCtx<W>& c, bool dec2, uint32_t k, uint32_t o, uint32_t aux, Range& rd)
+__device__ __forceinline__ void store_diff(const WinCtx<W>& c, bool dec2, uint32_t k, uint32_t d, Range& rd)
 {
-  const uint32_t d = wsub2(o, aux);
   rd.add1(d);
   const uint32_t e   = (dec2 ? 0u : (uint32_t)kMaxL) + k;
   const uint32_t row = c.rowtab[e];
@@ -442,6 +442,11 @@ __device__ __forceinline__ void store_out(const WinCtx<W>& c, bool dec2, uint32_
   uint16_t*      Y   = reinterpret_cast<uint16_t*>(dec2 ? c.A32 : c.E32) + row * 64 + c.grp * W;
   Y[wb & 15u] = (uint16_t)(d & 0xFFFFu);
   Y[wb >> 4]  = (uint16_t)(d >> 16);
+}
+template <int W>
+__device__ __forceinline__ void store_out(const WinCtx<W>& c, bool dec2, uint32_t k, uint32_t o, uint32_t aux, Range& rd)
+{
+  store_diff<W>(c, dec2, k, wsub2(o, aux), rd);
 }
 
 // beta of the terminated last window from the 3 tail rows: plain (wrapping) int16 arithmetic.
@@ -659,7 +664,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
 #pragma unroll 1
     for (int ch = phase ? ctop : kWarm / kChunk - 1; ch >= 0; ch--) {
       const char* stg = pipe_wait<W>(c, p);
-#pragma unroll 1
+#pragma unroll
       for (int g = 1; g >= 0; g--) {
         const int k0 = ch * kChunk + g * 4;
         if (k0 > kf) continue;
@@ -789,9 +794,13 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
         const uint4    b0 = bs[(r * 2 + 0) * kThreads];
         const uint4    b1 = bs[(r * 2 + 1) * kThreads];
         const uint32_t bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        uint32_t       o = alpha_out_step<true, TRACK>(a, bb, q.x[r], q.y[r], wadd2(q.x[r], q.y[r]), rm);
-        if (W == 8) o = sra1_2(o);  // the 8-window (sse16) decoder halves its output
-        store_out<W>(c, dec2, (uint32_t)(lo + g * 4 + r), o, q.aux[r], rd);
+        if (W == 8) {  // the 8-window (sse16) decoder halves its output before the extrinsic subtraction
+          const uint32_t o = sra1_2(alpha_out_step<true, TRACK>(a, bb, q.x[r], q.y[r], wadd2(q.x[r], q.y[r]), rm));
+          store_out<W>(c, dec2, (uint32_t)(lo + g * 4 + r), o, q.aux[r], rd);
+        } else {  // out - aux comes straight out of the step
+          const uint32_t d = alpha_out_step<true, TRACK>(a, bb, q.x[r], q.y[r], wadd2(q.x[r], q.y[r]), rm, q.aux[r]);
+          store_diff<W>(c, dec2, (uint32_t)(lo + g * 4 + r), d, rd);
+        }
         if ((r & 1) == 0) {
           normalize<true>(a);
           if (TRACK) ra.add8(a);
