@@ -756,7 +756,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
 #pragma unroll
       for (int i = 0; i < 8; i++) s[i] = st.s[i];
     }
-#pragma unroll 1
+#pragma unroll
     for (int g = 1; g >= 0; g--) {
       if (lo + g * 4 > kf) continue;
       Group q;
