@@ -59,6 +59,7 @@ constexpr size_t   kXArrayBytes8  = (size_t)(100 + 1) * 128;    // W = 8: K <= 8
 constexpr size_t   kChkSlotBytes  = (size_t)kMaxChunks * 1024 + 128;
 constexpr int      kStagePad  = 4;   // int16 of padding per window in to_internal_kernel's staged copy
 constexpr int      kExactRows = 4;   // rows next to a known-state boundary always use exact arithmetic
+constexpr int      kPureFastG = 2529;   // 10000 + 9 * G <= 32768: fast arithmetic is exact even next to the known start state
 constexpr int      kStaticFastG = 2978; // 11 * G <= 32767: the fast variant needs no bookkeeping at all
 constexpr int      kMaxFastG  = 5461; // largest per-step metric change the fast variant accepts (6 * G <= 32767)
 constexpr int      kNegInf    = -10000;
@@ -636,7 +637,14 @@ __device__ __noinline__ HalfResult half_iteration_exact(const WinCtx<W> c, bool 
 // DEC1 and DEC2 share one instantiation (they differ only in which streams a chunk holds): in steady state the
 // 12 warps of an SM run the same code, and the hot loops (backward 4 rows, rebuild + forward 8 rows) fit the
 // instruction cache.
-template <int W, bool TRACK>
+// EDGE = false (G <= kPureFastG, L a multiple of 4): no exact rows at all.  Proof on top of the static one below:
+// the tail samples are part of G (to_internal_kernel), so the last window's start metrics -- 3 tail steps from
+// the known end state -- already lie in [-3G, 3G] like any other beta; the first window's alpha starts from
+// (0, -10000 x 7), so for rows 0..2 alpha + branch lies in [-10000 - 3G, 3G], plus beta in [-5G, 5G] that is
+// [-10000 - 8G, 8G]: inside int16 for G <= kPureFastG; from row 3 on alpha has gone through 3 steps and a
+// normalisation and is in general position.  |out| <= 5G there too: the best bit-1 and bit-0 candidates can be
+// chosen from the same predecessor state, so they differ by at most spread(beta) + 2G.
+template <int W, bool TRACK, bool EDGE>
 __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bool dec2, int G, Pipe& p)
 {
   constexpr int WH = W / 2;
@@ -645,7 +653,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
   // rows [kExactRows, kf] use fast arithmetic in the forward pass, rows [0, kf] in the backward pass; the rows
   // next to the terminated tail (above kf: 4 to 7 rows, so that a row group is either all fast or all exact) and
   // next to the known start state (0..3, forward) are always exact
-  const int kf = ((L - kExactRows) & ~3) - 1;
+  const int kf = EDGE ? ((L - kExactRows) & ~3) - 1 : L - 1;
   const int a0 = L - kWarm;  // first row of the alpha warm-up
   uint32_t  s[8];
   Range     rb, ra, rm, rd;
@@ -685,14 +693,15 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
     if (phase == 0) {
       exchange_beta_boundary<WH>(s, c.t, c.tail + (dec2 ? 6 : 0));
       chk_store<W>(c, ctop, s);
-      // the rows next to the terminated tail: exact
+      if (EDGE) {  // the rows next to the terminated tail: exact
 #pragma unroll
-      for (int i = 0; i < 8; i++) st.s[i] = s[i];
-      st.trk = rb;
-      beta_rows_exact<W>(c, dec2, L - 1, kf + 1, 1, 0, &st);
+        for (int i = 0; i < 8; i++) st.s[i] = s[i];
+        st.trk = rb;
+        beta_rows_exact<W>(c, dec2, L - 1, kf + 1, 1, 0, &st);
 #pragma unroll
-      for (int i = 0; i < 8; i++) s[i] = st.s[i];
-      rb = st.trk;
+        for (int i = 0; i < 8; i++) s[i] = st.s[i];
+        rb = st.trk;
+      }
     }
   }
 
@@ -743,12 +752,12 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
     c.sm[((hi - lo - 1) * 2 + 0) * kThreads] = make_uint4(s[0], s[1], s[2], s[3]);
     c.sm[((hi - lo - 1) * 2 + 1) * kThreads] = make_uint4(s[4], s[5], s[6], s[7]);
     if (hi != L) {  // hi is even and non-zero: the backward pass normalised after storing
-      if (hi <= kf)
+      if (!EDGE || hi <= kf)
         normalize<true>(s);
       else
         normalize<false>(s);
     }
-    if (hi - 1 > kf) {  // rows next to the tail: exact
+    if (EDGE && hi - 1 > kf) {  // rows next to the tail: exact
 #pragma unroll
       for (int i = 0; i < 8; i++) st.s[i] = s[i];
       st.trk.reset();
@@ -772,7 +781,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
       }
     }
     // alpha recursion + a-posteriori output over the chunk
-    if (ch == 0) {  // rows 0..3 next to the known start state: exact
+    if (EDGE && ch == 0) {  // rows 0..3 next to the known start state: exact
 #pragma unroll
       for (int i = 0; i < 8; i++) st.s[i] = a[i];
       st.trk = ra;
@@ -784,7 +793,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
       rd = st.rd;
     }
 #pragma unroll 1
-    for (int g = ch == 0 ? 1 : 0; g < 2; g++) {
+    for (int g = (EDGE && ch == 0) ? 1 : 0; g < 2; g++) {
       if (lo + g * 4 > kf) continue;
       Group q;
       load_group<W>(c, dec2, stg, g, q);
@@ -801,14 +810,14 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
           const uint32_t d = alpha_out_step<true, TRACK>(a, bb, q.x[r], q.y[r], wadd2(q.x[r], q.y[r]), rm, q.aux[r]);
           store_diff<W>(c, dec2, (uint32_t)(lo + g * 4 + r), d, rd);
         }
-        if ((r & 1) == 0) {
+        if ((r & 1) == 0 && (EDGE || r != 0 || (lo | g) != 0)) {  // never after row 0
           normalize<true>(a);
           if (TRACK) ra.add8(a);
         }
       }
     }
     pipe_release<W>(c, dec2, p);
-    if (hi - 1 > kf) {  // rows next to the tail: exact
+    if (EDGE && hi - 1 > kf) {  // rows next to the tail: exact
 #pragma unroll
       for (int i = 0; i < 8; i++) st.s[i] = a[i];
       st.trk = ra;
@@ -1072,11 +1081,14 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
         HalfResult r;
         bool       fast_ok = false;
         // the decision must be warp-uniform: the passes below use full-warp shuffles and votes
-        if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kStaticFastG)) {
-          r       = half_iteration_fast<W, false>(c, dec2, G, pipe);
+        if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kPureFastG && (c.L & 3u) == 0)) {
+          r       = half_iteration_fast<W, false, false>(c, dec2, G, pipe);
+          fast_ok = true;
+        } else if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kStaticFastG)) {
+          r       = half_iteration_fast<W, false, true>(c, dec2, G, pipe);
           fast_ok = true;
         } else if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kMaxFastG)) {
-          r       = half_iteration_fast<W, true>(c, dec2, G, pipe);
+          r       = half_iteration_fast<W, true, true>(c, dec2, G, pipe);
           fast_ok = __all_sync(0xFFFFFFFFu, r.proven);
         }
         if (!fast_ok) {
@@ -1383,6 +1395,13 @@ __global__ void __launch_bounds__(256) to_internal_kernel(const int16_t* __restr
   uint32_t mx[3];
 #pragma unroll
   for (int j = 0; j < 3; j++) mx[j] = max(mx2[j] & 0xFFFFu, mx2[j] >> 16);
+  {  // the 12 tail samples count for every stream: the decoder's bound G must cover the tail steps too
+    const int16_t* tq = src_format == 0 ? stage + W * wstride : src + 3 * (K + 32);
+    uint32_t       tm = 0;
+    if (threadIdx.x < 12) tm = (uint32_t)abs((int)tq[threadIdx.x]);
+#pragma unroll
+    for (int j = 0; j < 3; j++) mx[j] = max(mx[j], tm);
+  }
   const int16_t* tl = src_format == 0 ? stage + W * wstride : src + 3 * (K + 32);
   if (threadIdx.x < 16) tailp[threadIdx.x] = threadIdx.x < 12 ? tl[threadIdx.x] : (int16_t)0;
 #pragma unroll
