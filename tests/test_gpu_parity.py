@@ -246,3 +246,35 @@ def test_near_saturation_boundary(ctx, vec):
         for nit in (2, 5, 9):
             got, _, _ = ctx.tdec_batch_host(llr, K, nit)
             assert np.array_equal(got, ol.port_run_all(llr, K, nit)), (scale, nit)
+
+
+def test_pure_fast_tier_edges(ctx, vec):
+    """The tier without exact edge rows (G <= 2529, L % 4 == 0) next to its limits: inputs whose bound G sits just
+    below / above the tier thresholds, adversarial sign patterns in the rows next to the known start state and
+    in the tail, and tail samples that dominate the bound.  Bit-exact with the oracle in every case."""
+    rng = np.random.default_rng(2529)
+    for K in (6144, 1024, 512):
+        base_bits, base = vec.make_blocks(6, K, 0.9, 100, seed=K + 5)
+        cases = []
+        # (a) body magnitudes clipped so that max|sys| + max|par| is just below / above 2529 and 2978
+        for lim in (1200, 1264, 1265, 1400, 1489, 1490, 1600):
+            x = np.clip(base.astype(np.int32) * 12, -lim, lim).astype(np.int16)
+            cases.append(("clip%d" % lim, x))
+        # (b) constant-magnitude inputs with random / all-equal signs: the worst case of the bound on every row
+        for mag in (1260, 1264):
+            s = rng.integers(0, 2, base.shape) * 2 - 1
+            cases.append(("pm%d" % mag, (s * mag).astype(np.int16)))
+            cases.append(("pos%d" % mag, np.full(base.shape, mag, np.int16)))
+            cases.append(("neg%d" % mag, np.full(base.shape, -mag, np.int16)))
+        # (c) small body, huge tail samples (the tail must count for G), and the other way round
+        x = (base // 4).astype(np.int16)
+        x[:, 3 * K:] = (rng.integers(0, 2, (base.shape[0], 12)) * 2 - 1) * 9000
+        cases.append(("bigtail", x))
+        x = np.clip(base.astype(np.int32) * 12, -1264, 1264).astype(np.int16)
+        x[:, 3 * K:] = 0
+        x[:, :24] = 1264  # rows 0..7 of window 0 all at the bound
+        cases.append(("start", x))
+        for name, llr in cases:
+            for nit in (1, 2, 4):
+                got, _, _ = ctx.tdec_batch_host(llr, K, nit)
+                assert np.array_equal(got, ol.port_run_all(llr, K, nit)), (K, name, nit)
