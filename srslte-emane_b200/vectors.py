@@ -153,8 +153,11 @@ def sb_layout_from_natural(nat, K):
 
 
 def harness_sigma(ebno_db):
-    """sigma used by turbodecoder_test for its -e argument (turbodecoder_test.c:207-220)."""
-    return float(np.sqrt(1.0 / 10.0 ** (ebno_db / 10.0)))
+    """sigma used by turbodecoder_test for its -e argument (turbodecoder_test.c:207-220): the harness turns
+    "Eb/N0" into Es/N0 with the code rate 1/3 and then uses sqrt(1 / EsN0) as the STANDARD DEVIATION of the
+    noise added to the +-1 symbols: -e 1.5 -> 1.457, -e 4.0 -> 1.092."""
+    esno_db = ebno_db + 10.0 * np.log10(1.0 / 3.0)
+    return float(np.sqrt(1.0 / 10.0 ** (esno_db / 10.0)))
 
 
 def awgn_llr(coded_bits, sigma, scale=100.0, rng=None):
