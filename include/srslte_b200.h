@@ -136,6 +136,41 @@ typedef struct {
 SRSLTE_B200_API int srslte_b200_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_rm_block_t* blocks,
                                                 uint32_t n_blocks, const int16_t* e, int16_t* work);
 
+/* ---- front end: soft demodulation + descrambling --------------------------- */
+/* Replaces, for many codewords per call, the two steps in front of srslte_dlsch_decode2 / srslte_ulsch_decode:
+ *   srslte_demod_soft_demodulate_s(mod, symbols, e, nof_re)          lib/src/phy/modem/demod_soft.c:503-525
+ *   srslte_scrambling_s_offset(seq, e, 0, nof_bits)                  lib/src/phy/scrambling/scrambling.c:44-47
+ * (call sites lib/src/phy/phch/pdsch.c:760-779, pusch.c:482-500), seq = srslte_sequence_LTE_pr(len, c_init)
+ * (lib/src/phy/common/sequence.c:123-136).  Bit-exact with the reference's AVX2/SSE build while
+ * |scale * x| < 32768 (the reference's out-of-range float -> short conversions are undefined behaviour).      */
+typedef struct {
+  uint32_t qm;          /* bits per symbol: 2 QPSK, 4 16QAM, 6 64QAM, 8 256QAM (srslte_mod_t 1..4)                 */
+  uint32_t nof_symbols; /* cfg->grant.nof_re                                                                        */
+  uint32_t c_init;      /* scrambling seed: (rnti << 14) + (q << 13) + ((nslot / 2) << 9) + cell_id for PDSCH       */
+  uint32_t nof_bits;    /* LLRs that are descrambled: grant.tb[].nof_bits, <= qm * nof_symbols, <= 262144          */
+  uint64_t sym_offset;  /* first symbol of the codeword in `symbols` (complex floats: re, im)                       */
+  uint64_t llr_offset;  /* first LLR of the codeword in `e` (int16); unused by the fused entry                      */
+} srslte_b200_codeword_t;
+
+/* e[cw.llr_offset + j] = descrambled LLR j of codeword cw, j < qm * nof_symbols.  symbols, e: device memory. */
+SRSLTE_B200_API int srslte_b200_demod_descramble_dev(srslte_b200_ctx_t* ctx, const srslte_b200_codeword_t* cws,
+                                                     uint32_t n_cw, const float* symbols, int16_t* e);
+
+/* Fused with rate de-matching (srslte_rm_turbo_rx_lut semantics, HARQ combining in place): the e array of the
+ * reference is never written.  work[blk.work_offset + table(K, rv)[i mod (3K+12)]] += LLR(blk.codeword,
+ * blk.e_offset + i) for i < e_len.  symbols, work: device memory. */
+typedef struct {
+  uint32_t long_cb;     /* K */
+  uint32_t rv;
+  uint32_t codeword;    /* index into cws[] */
+  uint32_t e_offset;    /* first rate-matched LLR of this block inside its codeword (rp of sch.c:324-334) */
+  uint32_t e_len;       /* E */
+  uint32_t work_offset; /* int16 offset of the block's working buffer in `work` */
+} srslte_b200_rm_sym_block_t;
+SRSLTE_B200_API int srslte_b200_demod_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_codeword_t* cws,
+                                                      uint32_t n_cw, const srslte_b200_rm_sym_block_t* blocks,
+                                                      uint32_t n_blocks, const float* symbols, int16_t* work);
+
 /* ---- batched transport-block decode (the sch.c decode_tb loop over many TBs) ----------------- */
 /* HARQ state lives on the device: one "soft buffer" = max_cb code-block LLR buffers + CRC flags +
  * saved payloads, the counterpart of srslte_softbuffer_rx_t (softbuffer.h:37-43, softbuffer.c:41-150). */

@@ -248,3 +248,30 @@ uint32_t refh_crc_bits(uint32_t poly, const uint8_t* bits, uint32_t nbits)
   srslte_crc_init(&c, poly, 24);
   return srslte_crc_checksum(&c, (uint8_t*)bits, (int)nbits);
 }
+
+/* ---- front end: the reference's own soft demodulator + descrambler, pdsch.c:760-779 order ---- */
+#include "srslte/phy/common/sequence.h"
+#include "srslte/phy/modem/demod_soft.h"
+#include "srslte/phy/scrambling/scrambling.h"
+/* mod: srslte_mod_t (1 QPSK, 2 16QAM, 3 64QAM, 4 256QAM); buffers are copied into SIMD-aligned memory because the
+ * reference's SSE demodulators use aligned loads/stores (demod_soft.c:104-119) */
+int refh_demod_descramble(int mod, const float* sym, uint32_t nsym, uint32_t c_init, uint32_t nof_bits, int16_t* llr,
+                          uint32_t nof_llr)
+{
+  cf_t*  s = srslte_vec_malloc(sizeof(cf_t) * (nsym + 16));
+  short* l = srslte_vec_malloc(sizeof(short) * (nof_llr + 64));
+  if (!s || !l) return -1;
+  memcpy(s, sym, sizeof(cf_t) * nsym);
+  int rc = srslte_demod_soft_demodulate_s((srslte_mod_t)mod, s, l, (int)nsym);
+  if (rc == 0 && nof_bits) {
+    srslte_sequence_t seq;
+    memset(&seq, 0, sizeof(seq));
+    if (srslte_sequence_LTE_pr(&seq, nof_bits, c_init)) rc = -1;
+    if (rc == 0) srslte_scrambling_s_offset(&seq, l, 0, (int)nof_bits);
+    srslte_sequence_free(&seq);
+  }
+  memcpy(llr, l, sizeof(short) * nof_llr);
+  free(s);
+  free(l);
+  return rc;
+}

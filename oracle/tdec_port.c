@@ -856,3 +856,140 @@ int port_batch_run_all(const int16_t* in, uint32_t in_stride, int natural, uint8
   free(jobs);
   return rc;
 }
+
+/* =====================================================================================================
+ * Front end of the path: soft demodulation to int16 LLRs + descrambling.
+ * TEST INFRASTRUCTURE like the rest of this file.
+ *
+ * Reference (AVX2/SSE build, as compiled by oracle/Makefile):
+ *   srslte_demod_soft_demodulate_s      lib/src/phy/modem/demod_soft.c:503-525
+ *     QPSK    demod_qpsk_lte_s          :68-70  -> srslte_vec_convert_fi_simd, lib/src/phy/utils/vector_simd.c:392-427
+ *     16QAM   demod_16qam_lte_s(_sse)   :90-133 (groups of 4 symbols), scalar remainder :121-131
+ *     64QAM   demod_64qam_lte_s(_sse)   :240-302, scalar remainder :290-300
+ *     256QAM  demod_256qam_lte_s        :457-477 (scalar float)
+ *   srslte_sequence_set_LTE_pr          lib/src/phy/common/sequence.c:46-75 (36.211 7.2 Gold sequence, Nc = 1600)
+ *   srslte_scrambling_s_offset          lib/src/phy/scrambling/scrambling.c:44-47 -> srslte_vec_neg_sss (sign flip)
+ * The SSE bodies of 16QAM / 64QAM round to nearest even (cvtps2dq) and saturate (packssdw); QPSK's AVX2 body
+ * truncates (cvttps2dq) and saturates; the scalar remainders truncate and wrap (out-of-range conversions are
+ * undefined behaviour in the reference: parity is claimed for |scale * x| < 32768 only).
+ * ===================================================================================================== */
+#include <math.h>
+
+static int16_t sat16_i32(int32_t v) { return (int16_t)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v)); }
+static int16_t rint_sat16(float v)
+{ /* cvtps2dq + packssdw */
+  if (!(v > -2147483648.0f && v < 2147483648.0f)) return (int16_t)-32768; /* integer indefinite */
+  return sat16_i32((int32_t)lrintf(v));
+}
+static int16_t trunc16_f(float v) { return (int16_t)(int32_t)v; }
+static int16_t trunc16_d(double v) { return (int16_t)(int32_t)v; }
+
+void port_gold_sequence(uint32_t seed, uint32_t len, uint8_t* c)
+{
+  const uint32_t n_tot = 1600 + len;
+  uint8_t* x1 = (uint8_t*)calloc(n_tot + 31, 1);
+  uint8_t* x2 = (uint8_t*)calloc(n_tot + 31, 1);
+  for (uint32_t n = 0; n < 31; n++) x2[n] = (uint8_t)((seed >> n) & 1u);
+  x1[0] = 1;
+  for (uint32_t n = 0; n < n_tot; n++) {
+    x1[n + 31] = (uint8_t)((x1[n + 3] + x1[n]) & 1);
+    x2[n + 31] = (uint8_t)((x2[n + 3] + x2[n + 2] + x2[n + 1] + x2[n]) & 1);
+  }
+  for (uint32_t n = 0; n < len; n++) c[n] = (uint8_t)((x1[n + 1600] + x2[n + 1600]) & 1);
+  free(x1);
+  free(x2);
+}
+
+/* qm = bits per symbol: 2 (QPSK), 4 (16QAM), 6 (64QAM), 8 (256QAM); sym = nsym complex floats (re, im) */
+int port_demod_s(int qm, const float* sym, int16_t* llr, uint32_t nsym)
+{
+  if (qm == 2) {
+    const float    scale = (float)(-100 * sqrt(2));
+    const uint32_t len = 2 * nsym, simd = len & ~15u; /* 16 int16 per AVX2 iteration */
+    for (uint32_t i = 0; i < simd; i++) { /* cvttps2dq + packssdw: truncate, then saturate (simd.h:1681-1686) */
+      const float v = sym[i] * scale;
+      llr[i] = (v > -2147483648.0f && v < 2147483648.0f) ? sat16_i32((int32_t)v) : (int16_t)-32768;
+    }
+    for (uint32_t i = simd; i < len; i++) llr[i] = trunc16_f(sym[i] * scale);
+    return 0;
+  }
+  if (qm == 4) {
+    const int16_t  off  = (int16_t)(2 * 400 / sqrt(10));
+    const uint32_t simd = nsym & ~3u;
+    for (uint32_t i = 0; i < simd; i++) {
+      const int16_t re = rint_sat16(sym[2 * i] * -400.0f), im = rint_sat16(sym[2 * i + 1] * -400.0f);
+      const int16_t are = (int16_t)(re < 0 ? -re : re), aim = (int16_t)(im < 0 ? -im : im); /* pabsw: -32768 stays */
+      llr[4 * i + 0] = re;
+      llr[4 * i + 1] = im;
+      llr[4 * i + 2] = (int16_t)(are - off);
+      llr[4 * i + 3] = (int16_t)(aim - off);
+    }
+    for (uint32_t i = simd; i < nsym; i++) {
+      const int16_t yre = trunc16_f(400 * sym[2 * i]), yim = trunc16_f(400 * sym[2 * i + 1]);
+      llr[4 * i + 0] = (int16_t)-yre;
+      llr[4 * i + 1] = (int16_t)-yim;
+      llr[4 * i + 2] = trunc16_d(abs(yre) - 2 * 400 / sqrt(10));
+      llr[4 * i + 3] = trunc16_d(abs(yim) - 2 * 400 / sqrt(10));
+    }
+    return 0;
+  }
+  if (qm == 6) {
+    const int16_t  off1 = (int16_t)(4 * 700 / sqrt(42)), off2 = (int16_t)(2 * 700 / sqrt(42));
+    const uint32_t simd = nsym & ~3u;
+    for (uint32_t i = 0; i < simd; i++) {
+      for (int c = 0; c < 2; c++) {
+        const int16_t v  = rint_sat16(sym[2 * i + c] * -700.0f);
+        const int16_t a1 = (int16_t)((int16_t)(v < 0 ? -v : v) - off1);
+        const int16_t a2 = (int16_t)((int16_t)(a1 < 0 ? -a1 : a1) - off2);
+        llr[6 * i + c]     = v;
+        llr[6 * i + 2 + c] = a1;
+        llr[6 * i + 4 + c] = a2;
+      }
+    }
+    for (uint32_t i = simd; i < nsym; i++) {
+      for (int c = 0; c < 2; c++) {
+        const float y = (float)trunc16_f(700 * sym[2 * i + c]);
+        llr[6 * i + c]     = trunc16_f(-y);
+        llr[6 * i + 2 + c] = trunc16_d(abs((int)y) - 4 * 700 / sqrt(42));
+        llr[6 * i + 4 + c] = trunc16_d(abs(llr[6 * i + 2 + c]) - 2 * 700 / sqrt(42));
+      }
+    }
+    return 0;
+  }
+  if (qm == 8) {
+    const float c8 = 8.0f / sqrtf(170.0f), c4 = 4.0f / sqrtf(170.0f), c2 = 2.0f / sqrtf(170.0f);
+    for (uint32_t i = 0; i < nsym; i++) {
+      for (int c = 0; c < 2; c++) {
+        float v = -sym[2 * i + c];
+        llr[8 * i + c] = trunc16_f(1000 * v);
+        v = fabsf(v) - c8;
+        llr[8 * i + 2 + c] = trunc16_f(1000 * v);
+        v = fabsf(v) - c4;
+        llr[8 * i + 4 + c] = trunc16_f(1000 * v);
+        v = fabsf(v) - c2;
+        llr[8 * i + 6 + c] = trunc16_f(1000 * v);
+      }
+    }
+    return 0;
+  }
+  return -1;
+}
+
+/* llr[i] = c[i] ? -llr[i] : llr[i] (wrapping negation: -(-32768) = -32768) */
+void port_descramble_s(int16_t* llr, const uint8_t* c, uint32_t len)
+{
+  for (uint32_t i = 0; i < len; i++)
+    if (c[i]) llr[i] = (int16_t)(0u - (uint16_t)llr[i]);
+}
+
+/* pdsch.c:760-779 / pusch.c:482-500: demodulate nsym symbols, descramble the first nof_bits LLRs with seed c_init */
+int port_demod_descramble(int qm, const float* sym, uint32_t nsym, uint32_t c_init, uint32_t nof_bits, int16_t* llr)
+{
+  if (port_demod_s(qm, sym, llr, nsym)) return -1;
+  if (nof_bits > (uint32_t)qm * nsym) return -1;
+  uint8_t* c = (uint8_t*)malloc(nof_bits + 1);
+  port_gold_sequence(c_init, nof_bits, c);
+  port_descramble_s(llr, c, nof_bits);
+  free(c);
+  return 0;
+}

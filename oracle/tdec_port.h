@@ -104,6 +104,16 @@ int port_batch_run_all(const int16_t* in, uint32_t in_stride, int natural, uint8
                        uint32_t out_stride, uint32_t n, uint32_t K, uint32_t nof_iterations,
                        uint32_t threads);
 
+/* ---- front end: soft demodulation + descrambling ---------------------- */
+/* 36.211 7.2 Gold sequence (sequence.c:46-75) */
+void port_gold_sequence(uint32_t seed, uint32_t len, uint8_t* c);
+/* srslte_demod_soft_demodulate_s of the AVX2/SSE build (demod_soft.c:503-525); qm = 2, 4, 6, 8 */
+int  port_demod_s(int qm, const float* sym, int16_t* llr, uint32_t nsym);
+/* srslte_scrambling_s_offset (scrambling.c:44-47) */
+void port_descramble_s(int16_t* llr, const uint8_t* c, uint32_t len);
+/* the two in the order of pdsch.c:760-779 / pusch.c:482-500 */
+int  port_demod_descramble(int qm, const float* sym, uint32_t nsym, uint32_t c_init, uint32_t nof_bits, int16_t* llr);
+
 #ifdef __cplusplus
 }
 #endif

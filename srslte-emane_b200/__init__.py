@@ -34,6 +34,16 @@ class RmBlock(C.Structure):
                 ("work_offset", C.c_uint32)]
 
 
+class Codeword(C.Structure):
+    _fields_ = [("qm", C.c_uint32), ("nof_symbols", C.c_uint32), ("c_init", C.c_uint32), ("nof_bits", C.c_uint32),
+                ("sym_offset", C.c_uint64), ("llr_offset", C.c_uint64)]
+
+
+class RmSymBlock(C.Structure):
+    _fields_ = [("long_cb", C.c_uint32), ("rv", C.c_uint32), ("codeword", C.c_uint32), ("e_offset", C.c_uint32),
+                ("e_len", C.c_uint32), ("work_offset", C.c_uint32)]
+
+
 class TbDesc(C.Structure):
     _fields_ = [("tbs", C.c_uint32), ("qm", C.c_uint32), ("rv", C.c_uint32), ("nof_e_bits", C.c_uint32),
                 ("softbuffer", C.c_uint32), ("e_bits", C.c_void_p), ("data", C.c_void_p), ("ret", C.c_int32),
@@ -47,6 +57,7 @@ EXPORTS = [
     "srslte_b200_ctx_fallback_count", "srslte_b200_host_alloc", "srslte_b200_host_free", "srslte_b200_cb_index", "srslte_b200_cb_size",
     "srslte_b200_nof_windows", "srslte_b200_working_len", "srslte_b200_rm_rx_table",
     "srslte_b200_tdec_batch_dev", "srslte_b200_tdec_batch_host", "srslte_b200_rm_rx_batch_dev",
+    "srslte_b200_demod_descramble_dev", "srslte_b200_demod_rm_rx_batch_dev",
     "srslte_b200_harq_pool_create", "srslte_b200_harq_pool_destroy", "srslte_b200_harq_reset",
     "srslte_b200_harq_cb_crc", "srslte_b200_decode_tb_batch",
 ]
@@ -91,6 +102,8 @@ def lib():
     L.srslte_b200_tdec_batch_dev.argtypes = [vp, C.POINTER(TdecBatch), vp, vp, vp, vp]
     L.srslte_b200_tdec_batch_host.argtypes = [vp, C.POINTER(TdecBatch), vp, vp, vp, vp]
     L.srslte_b200_rm_rx_batch_dev.argtypes = [vp, C.POINTER(RmBlock), u32, vp, vp]
+    L.srslte_b200_demod_descramble_dev.argtypes = [vp, C.POINTER(Codeword), u32, vp, vp]
+    L.srslte_b200_demod_rm_rx_batch_dev.argtypes = [vp, C.POINTER(Codeword), u32, C.POINTER(RmSymBlock), u32, vp, vp]
     L.srslte_b200_harq_pool_create.argtypes = [vp, u32, u32, C.POINTER(vp)]
     L.srslte_b200_harq_pool_destroy.argtypes = [vp, vp]
     L.srslte_b200_harq_pool_destroy.restype = None
@@ -270,6 +283,32 @@ class Context:
             arr[i] = RmBlock(K, rv, eo, el, wo)
         rc = self._L.srslte_b200_rm_rx_batch_dev(self._h, arr, len(blocks), C.c_void_p(e_ptr), C.c_void_p(work_ptr))
         self._check(rc, "srslte_b200_rm_rx_batch_dev")
+
+
+    # ---- front end: soft demodulation + descrambling (device pointers) ---------------------------
+    @staticmethod
+    def _codewords(cws):
+        arr = (Codeword * len(cws))()
+        for i, c in enumerate(cws):
+            arr[i] = Codeword(c["qm"], c["nof_symbols"], c["c_init"], c.get("nof_bits", c["qm"] * c["nof_symbols"]),
+                              c.get("sym_offset", 0), c.get("llr_offset", 0))
+        return arr
+
+    def demod_descramble_dev(self, cws, symbols_ptr, e_ptr):
+        """cws: list of dicts(qm, nof_symbols, c_init[, nof_bits, sym_offset, llr_offset])."""
+        arr = self._codewords(cws)
+        rc = self._L.srslte_b200_demod_descramble_dev(self._h, arr, len(cws), C.c_void_p(symbols_ptr), C.c_void_p(e_ptr))
+        self._check(rc, "srslte_b200_demod_descramble_dev")
+
+    def demod_rm_rx_batch_dev(self, cws, blocks, symbols_ptr, work_ptr):
+        """blocks: list of (K, rv, codeword, e_offset, e_len, work_offset)."""
+        arr = self._codewords(cws)
+        bl = (RmSymBlock * len(blocks))()
+        for i, b in enumerate(blocks):
+            bl[i] = RmSymBlock(*b)
+        rc = self._L.srslte_b200_demod_rm_rx_batch_dev(self._h, arr, len(cws), bl, len(blocks), C.c_void_p(symbols_ptr),
+                                                       C.c_void_p(work_ptr))
+        self._check(rc, "srslte_b200_demod_rm_rx_batch_dev")
 
 
 class HarqPool:

@@ -119,6 +119,13 @@ struct srslte_b200_ctx {
   size_t                       rm_pool_uploaded = 0;
   DevBuf<RmItem>               d_rm_items;
   PinBuf<RmItem>               h_rm_items;
+  // front end (soft demodulation + descrambling)
+  DevBuf<uint32_t>             gold_x1, gold_x2;   // scrambling-sequence tables (lte_tables.cpp:gold_tables)
+  bool                         gold_ready = false;
+  DevBuf<FeCodeword>           d_cws;
+  PinBuf<FeCodeword>           h_cws;
+  DevBuf<RmSymItem>            d_rm_sym;
+  PinBuf<RmSymItem>            h_rm_sym;
   uint64_t     launches = 0;
   // optional per-kernel event timing (bench.py's roofline): kind 0..4 = W16, W8, generic, layout, rate-dematch
   bool         timing = false;
@@ -489,6 +496,12 @@ void srslte_b200_ctx_destroy(srslte_b200_ctx_t* ctx)
   ctx->rm_pool_dev.release();
   ctx->d_rm_items.release();
   ctx->h_rm_items.release();
+  ctx->gold_x1.release();
+  ctx->gold_x2.release();
+  ctx->d_cws.release();
+  ctx->h_cws.release();
+  ctx->d_rm_sym.release();
+  ctx->h_rm_sym.release();
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
   if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
@@ -708,6 +721,114 @@ int srslte_b200_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_rm_blo
                                 const int16_t* e, int16_t* work)
 {
   return rm_rx_enqueue(ctx, blocks, n_blocks, e, work, true);
+}
+
+// ---- front end: soft demodulation + descrambling ---------------------------------------------------
+static int fe_prepare(srslte_b200_ctx_t* ctx, const srslte_b200_codeword_t* cws, uint32_t n_cw, uint32_t* max_llr)
+{
+  cudaStream_t st = ctx->stream;
+  if (!ctx->gold_ready) {
+    std::vector<uint32_t> x1, x2;
+    gold_tables(kGoldMaxLen, x1, x2);
+    CU(ctx->gold_x1.reserve(x1.size()));
+    CU(ctx->gold_x2.reserve(x2.size()));
+    CU(cudaMemcpyAsync(ctx->gold_x1.p, x1.data(), x1.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->gold_x2.p, x2.data(), x2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));  // the sources are pageable std::vector memory
+    ctx->gold_ready = true;
+  }
+  CU(cudaStreamSynchronize(st));  // pinned staging reuse
+  CU(ctx->h_cws.reserve(n_cw));
+  CU(ctx->d_cws.reserve(n_cw));
+  uint32_t mx = 0;
+  for (uint32_t i = 0; i < n_cw; i++) {
+    const srslte_b200_codeword_t& c = cws[i];
+    if (c.qm != 2 && c.qm != 4 && c.qm != 6 && c.qm != 8)
+      return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "codeword %u: qm %u is not 2, 4, 6 or 8", i, c.qm);
+    const uint64_t n = (uint64_t)c.qm * c.nof_symbols;
+    if (c.nof_bits > n || c.nof_bits > kGoldMaxLen || n > 0xFFFFFFFFull)
+      return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "codeword %u: nof_bits %u out of range", i, c.nof_bits);
+    FeCodeword f;
+    f.qm = c.qm; f.nsym = c.nof_symbols; f.c_init = c.c_init; f.nof_bits = c.nof_bits;
+    f.sym_off = c.sym_offset; f.llr_off = c.llr_offset;
+    ctx->h_cws.p[i] = f;
+    mx = std::max(mx, (uint32_t)n);
+  }
+  CU(cudaMemcpyAsync(ctx->d_cws.p, ctx->h_cws.p, n_cw * sizeof(FeCodeword), cudaMemcpyHostToDevice, st));
+  *max_llr = mx;
+  return 0;
+}
+
+int srslte_b200_demod_descramble_dev(srslte_b200_ctx_t* ctx, const srslte_b200_codeword_t* cws, uint32_t n_cw,
+                                     const float* symbols, int16_t* e)
+{
+  if (!ctx) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  if (n_cw == 0) return SRSLTE_B200_SUCCESS;
+  if (!cws || !symbols || !e) return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "NULL argument");
+  CU(cudaSetDevice(ctx->device));
+  uint32_t max_llr = 0;
+  int      rc      = fe_prepare(ctx, cws, n_cw, &max_llr);
+  if (rc) return rc;
+  CU(demod_descramble_launch(ctx->d_cws.p, n_cw, max_llr, symbols, e, ctx->gold_x1.p, ctx->gold_x2.p, ctx->stream));
+  ctx->launches++;
+  return SRSLTE_B200_SUCCESS;
+}
+
+int srslte_b200_demod_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_codeword_t* cws, uint32_t n_cw,
+                                      const srslte_b200_rm_sym_block_t* blocks, uint32_t n_blocks,
+                                      const float* symbols, int16_t* work)
+{
+  if (!ctx) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  if (n_blocks == 0) return SRSLTE_B200_SUCCESS;
+  if (!cws || !blocks || !symbols || !work || n_cw == 0)
+    return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "NULL argument");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  uint32_t     max_llr = 0;
+  int          rc      = fe_prepare(ctx, cws, n_cw, &max_llr);
+  if (rc) return rc;
+  CU(ctx->h_rm_sym.reserve(n_blocks));
+  CU(ctx->d_rm_sym.reserve(n_blocks));
+  for (uint32_t i = 0; i < n_blocks; i++) {
+    const srslte_b200_rm_sym_block_t& bl = blocks[i];
+    if (bl.rv > 3 || cb_index_exact(bl.long_cb) < 0 || bl.codeword >= n_cw)
+      return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "block %u: invalid K=%u, rv=%u or codeword=%u", i, bl.long_cb,
+                  bl.rv, bl.codeword);
+    const srslte_b200_codeword_t& c = cws[bl.codeword];
+    if ((uint64_t)bl.e_offset + bl.e_len > (uint64_t)c.qm * c.nof_symbols)
+      return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "block %u reads past the end of codeword %u", i, bl.codeword);
+    const uint32_t key = (bl.long_cb * 4 + bl.rv) * 2 + 1u;
+    auto           it  = ctx->rm_tab_off.find(key);
+    if (it == ctx->rm_tab_off.end()) {
+      std::vector<uint16_t> t;
+      rm_rx_table(bl.long_cb, bl.rv, true, t);
+      const uint32_t off = (uint32_t)ctx->rm_pool_host.size();
+      ctx->rm_pool_host.insert(ctx->rm_pool_host.end(), t.begin(), t.end());
+      it = ctx->rm_tab_off.emplace(key, off).first;
+    }
+    RmSymItem ri;
+    ri.E = bl.e_len; ri.work_off = bl.work_offset; ri.tab_off = it->second; ri.N = 3 * bl.long_cb + 12;
+    ri.cw = bl.codeword; ri.e_off = bl.e_offset;
+    ctx->h_rm_sym.p[i] = ri;
+  }
+  if (ctx->rm_pool_uploaded != ctx->rm_pool_host.size()) {
+    if (ctx->rm_pool_host.size() > ctx->rm_pool_dev.cap) {
+      CU(ctx->rm_pool_dev.reserve(ctx->rm_pool_host.size() * 2));
+      ctx->rm_pool_uploaded = 0;
+    }
+    CU(cudaMemcpyAsync(ctx->rm_pool_dev.p + ctx->rm_pool_uploaded, ctx->rm_pool_host.data() + ctx->rm_pool_uploaded,
+                       (ctx->rm_pool_host.size() - ctx->rm_pool_uploaded) * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->rm_pool_uploaded = ctx->rm_pool_host.size();
+  }
+  CU(cudaMemcpyAsync(ctx->d_rm_sym.p, ctx->h_rm_sym.p, n_blocks * sizeof(RmSymItem), cudaMemcpyHostToDevice, st));
+  {
+    KernelTimer kt(ctx, 4, st);
+    CU(rm_rx_sym_launch(ctx->d_cws.p, symbols, work, ctx->rm_pool_dev.p, ctx->d_rm_sym.p, n_blocks, ctx->gold_x1.p,
+                        ctx->gold_x2.p, st));
+  }
+  ctx->launches++;
+  return SRSLTE_B200_SUCCESS;
 }
 
 }  // extern "C"

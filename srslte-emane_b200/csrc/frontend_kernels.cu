@@ -1,0 +1,124 @@
+// frontend_kernels.cu -- the stage in front of rate de-matching: equalised symbols ->
+// int16 LLRs (soft demodulation) -> descrambling, alone or fused into the rate-dematching scatter-add so that the
+// e_bits array of the reference (pdsch.c:760-779, pusch.c:482-500) is never written to HBM.
+//
+// What is computed (bit-exact with the reference's AVX2/SSE build for |scale * x| < 32768):
+//   srslte_demod_soft_demodulate_s   lib/src/phy/modem/demod_soft.c:503-525
+//       QPSK   :68-70 -> srslte_vec_convert_fi_simd (vector_simd.c:392-427): x * (float)(-100 sqrt 2), truncated;
+//              saturating in the 16-wide AVX2 body, plain cast in the remainder
+//       16QAM  :90-133   groups of 4 symbols: round-to-nearest-even of x * -400, saturate, |.| - 252 (wrapping);
+//              remainder :121-131: truncation and a double-precision offset
+//       64QAM  :240-302  the same with -700 and offsets 432 / 216; remainder :290-300
+//       256QAM :457-477  scalar float chain, truncation
+//   srslte_scrambling_s_offset       lib/src/phy/scrambling/scrambling.c:44-47 (sign flip where c(n) = 1)
+//   the scrambling sequence c(n)     lib/src/phy/common/sequence.c:46-75 (36.211 7.2, Nc = 1600); here
+//       c(n) = x1(n + 1600) xor parity(mask[n] & c_init): x2 is linear in its seed, so one table of 31-bit masks
+//       (lte_tables.cpp:gold_tables) serves every seed and every LLR is computed independently.
+#include "tdec_kernels.h"
+
+namespace b200 {
+
+namespace {
+
+__device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v)); }
+__device__ __forceinline__ int wrap16(int v) { return (int)(int16_t)v; }
+
+// LLR number j of a codeword (before rate de-matching), descrambled
+__device__ __forceinline__ int fe_llr(const FeCodeword& cw, const float* __restrict__ sym, uint32_t j,
+                                      const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x2mask)
+{
+  const uint32_t qm = cw.qm, s = j / qm, r = j - s * qm, lvl = r >> 1;
+  const float    x  = __ldg(sym + 2 * (size_t)s + (r & 1u));
+  int            v;
+  if (qm == 2) {
+    constexpr float kScale = (float)(-100.0 * 1.4142135623730951);
+    const int       t = __float2int_rz(__fmul_rn(x, kScale));
+    v = j < ((2 * cw.nsym) & ~15u) ? sat16(t) : wrap16(t);
+  } else if (qm == 4) {
+    if (s < (cw.nsym & ~3u)) {
+      const int v0 = sat16(__float2int_rn(__fmul_rn(x, -400.0f)));
+      v = lvl == 0 ? v0 : wrap16(abs(v0) - 252);
+    } else {
+      const int y = wrap16(__float2int_rz(__fmul_rn(400.0f, x)));
+      v = lvl == 0 ? wrap16(-y) : wrap16(__double2int_rz((double)abs(y) - 800.0 / 3.1622776601683795));
+    }
+  } else if (qm == 6) {
+    if (s < (cw.nsym & ~3u)) {
+      const int v0 = sat16(__float2int_rn(__fmul_rn(x, -700.0f)));
+      const int a1 = wrap16(abs(v0) - 432);
+      v = lvl == 0 ? v0 : lvl == 1 ? a1 : wrap16(abs(a1) - 216);
+    } else {
+      const int y  = wrap16(__float2int_rz(__fmul_rn(700.0f, x)));
+      const int l2 = wrap16(__double2int_rz((double)abs(y) - 2800.0 / 6.48074069840786));
+      v = lvl == 0 ? wrap16(-y) : lvl == 1 ? l2 : wrap16(__double2int_rz((double)abs(l2) - 1400.0 / 6.48074069840786));
+    }
+  } else {
+    const float s170 = __fsqrt_rn(170.0f);
+    float       f = -x;
+    if (lvl >= 1) f = __fsub_rn(fabsf(f), __fdiv_rn(8.0f, s170));
+    if (lvl >= 2) f = __fsub_rn(fabsf(f), __fdiv_rn(4.0f, s170));
+    if (lvl >= 3) f = __fsub_rn(fabsf(f), __fdiv_rn(2.0f, s170));
+    v = wrap16(__float2int_rz(__fmul_rn(1000.0f, f)));
+  }
+  if (j < cw.nof_bits) {
+    const uint32_t c = ((__ldg(x1 + (j >> 5)) >> (j & 31u)) ^ (uint32_t)__popc(__ldg(x2mask + j) & cw.c_init)) & 1u;
+    if (c) v = wrap16(-v);
+  }
+  return v;
+}
+
+// grid: (chunks of 256 LLRs, codewords)
+__global__ void __launch_bounds__(256) demod_descramble_kernel(const FeCodeword* __restrict__ cws,
+                                                               const float* __restrict__ symbols,
+                                                               int16_t* __restrict__ e, const uint32_t* __restrict__ x1,
+                                                               const uint32_t* __restrict__ x2mask)
+{
+  const FeCodeword cw = cws[blockIdx.y];
+  const float*     sym = symbols + 2 * cw.sym_off;
+  int16_t*         out = e + cw.llr_off;
+  const uint32_t   n = cw.qm * cw.nsym;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+    out[j] = (int16_t)fe_llr(cw, sym, j, x1, x2mask);
+}
+
+// rate de-matching straight from the symbols: work[tab[i]] += sum over the wrap-around repeats of LLR(e_off + p)
+__global__ void rm_rx_sym_kernel(const FeCodeword* __restrict__ cws, const float* __restrict__ symbols,
+                                 int16_t* __restrict__ work, const uint16_t* __restrict__ tab_pool,
+                                 const RmSymItem* __restrict__ items, const uint32_t* __restrict__ x1,
+                                 const uint32_t* __restrict__ x2mask)
+{
+  const RmSymItem  it  = items[blockIdx.x];
+  const FeCodeword cw  = cws[it.cw];
+  const float*     sym = symbols + 2 * cw.sym_off;
+  int16_t*         dst = work + it.work_off;
+  const uint16_t*  tab = tab_pool + it.tab_off;
+  for (uint32_t i = threadIdx.x; i < it.N && i < it.E; i += blockDim.x) {
+    int acc = 0;
+    for (uint32_t p = i; p < it.E; p += it.N) acc += fe_llr(cw, sym, it.e_off + p, x1, x2mask);
+    const uint32_t o = tab[i];
+    dst[o] = (int16_t)(dst[o] + acc);  // wrapping int16, like the reference's `+=`
+  }
+}
+
+}  // namespace
+
+cudaError_t demod_descramble_launch(const FeCodeword* cws, uint32_t n_cw, uint32_t max_llr, const float* symbols,
+                                    int16_t* e, const uint32_t* x1, const uint32_t* x2mask, cudaStream_t s)
+{
+  if (n_cw == 0 || max_llr == 0) return cudaSuccess;
+  const uint32_t chunks = (max_llr + 255) / 256;
+  dim3           grid(chunks < 1024 ? chunks : 1024, n_cw);
+  demod_descramble_kernel<<<grid, 256, 0, s>>>(cws, symbols, e, x1, x2mask);
+  return cudaGetLastError();
+}
+
+cudaError_t rm_rx_sym_launch(const FeCodeword* cws, const float* symbols, int16_t* work, const uint16_t* tab_pool,
+                             const RmSymItem* items, uint32_t n_items, const uint32_t* x1, const uint32_t* x2mask,
+                             cudaStream_t s)
+{
+  if (n_items == 0) return cudaSuccess;
+  rm_rx_sym_kernel<<<n_items, 256, 0, s>>>(cws, symbols, work, tab_pool, items, x1, x2mask);
+  return cudaGetLastError();
+}
+
+}  // namespace b200

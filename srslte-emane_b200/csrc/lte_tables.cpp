@@ -333,4 +333,23 @@ uint32_t crc24_bytes(uint32_t poly, const uint8_t* data, uint32_t nbytes)
   return crc;
 }
 
+void gold_tables(uint32_t len, std::vector<uint32_t>& x1_packed, std::vector<uint32_t>& x2_mask)
+{
+  const uint32_t Nc = 1600, n_tot = Nc + len;
+  std::vector<uint8_t>  x1(n_tot + 31, 0);
+  std::vector<uint32_t> m2(n_tot + 31, 0);
+  x1[0] = 1;
+  for (uint32_t n = 0; n < 31; n++) m2[n] = 1u << n;
+  for (uint32_t n = 0; n < n_tot; n++) {
+    x1[n + 31] = (uint8_t)(x1[n + 3] ^ x1[n]);
+    m2[n + 31] = m2[n + 3] ^ m2[n + 2] ^ m2[n + 1] ^ m2[n];
+  }
+  x1_packed.assign((len + 31) / 32, 0);
+  x2_mask.resize(len);
+  for (uint32_t n = 0; n < len; n++) {
+    x1_packed[n >> 5] |= (uint32_t)x1[n + Nc] << (n & 31);
+    x2_mask[n] = m2[n + Nc];
+  }
+}
+
 }  // namespace b200

@@ -42,6 +42,11 @@ int cbsegm(CbSegm* s, uint32_t tbs);
 // sb_layout=false gives natural 3i+j indices for every K.
 void rm_rx_table(uint32_t K, uint32_t rv, bool sb_layout, std::vector<uint16_t>& table);
 
+// 36.211 7.2 scrambling sequence c(n) = x1(n + 1600) xor x2(n + 1600) for n < len (sequence.c:46-75):
+// x1_packed bit (n & 31) of word n / 32 = x1(n + 1600); x2(n + 1600) = parity(x2_mask[n] & c_init), because x2 is a
+// linear function of its 31 seed bits.
+void gold_tables(uint32_t len, std::vector<uint32_t>& x1_packed, std::vector<uint32_t>& x2_mask);
+
 void crc24_table(uint32_t poly, uint32_t table[256]);
 uint32_t crc24_bytes(uint32_t poly, const uint8_t* data, uint32_t nbytes);
 

@@ -80,6 +80,28 @@ struct RmItem {
 cudaError_t rm_rx_launch(const int16_t* e, int16_t* work, const uint16_t* tab_pool, const RmItem* items,
                          uint32_t n_items, cudaStream_t s);
 
+// ---- front end: soft demodulation + descrambling (frontend_kernels.cu) ------------------------------
+struct FeCodeword {
+  uint32_t qm;        // bits per symbol: 2, 4, 6, 8
+  uint32_t nsym;      // symbols of the codeword
+  uint32_t c_init;    // seed of the scrambling sequence
+  uint32_t nof_bits;  // LLRs that are descrambled (<= qm * nsym)
+  uint64_t sym_off;   // first symbol in the symbol buffer (complex floats)
+  uint64_t llr_off;   // first LLR in the output (demod_descramble only)
+};
+struct RmSymItem {
+  uint32_t E, work_off, tab_off, N;  // as RmItem
+  uint32_t cw;                       // codeword the block belongs to
+  uint32_t e_off;                    // first LLR of the block inside the codeword
+};
+constexpr uint32_t kGoldMaxLen = 256 * 1024;  // MAX_SEQ_LEN of the reference (sequence.c:34)
+// x1: kGoldMaxLen / 32 packed words of x1(n + 1600); x2mask: kGoldMaxLen masks, x2(n + 1600) = parity(mask & seed)
+cudaError_t demod_descramble_launch(const FeCodeword* cws, uint32_t n_cw, uint32_t max_llr, const float* symbols,
+                                    int16_t* e, const uint32_t* x1, const uint32_t* x2mask, cudaStream_t s);
+cudaError_t rm_rx_sym_launch(const FeCodeword* cws, const float* symbols, int16_t* work, const uint16_t* tab_pool,
+                             const RmSymItem* items, uint32_t n_items, const uint32_t* x1, const uint32_t* x2mask,
+                             cudaStream_t s);
+
 void upload_crc_tables();  // fills the __constant__ CRC tables (once per process/device)
 
 }  // namespace b200

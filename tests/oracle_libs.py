@@ -25,6 +25,7 @@ _i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
 _u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 _u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
 _u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 
 _port = None
 _ref = None
@@ -89,6 +90,10 @@ def port():
                                  C.POINTER(C.c_float), _u32p]
     L.port_batch_run_all.argtypes = [_i16p, C.c_uint32, C.c_int, _u8p, C.c_uint32, C.c_uint32,
                                      C.c_uint32, C.c_uint32, C.c_uint32]
+    L.port_gold_sequence.argtypes = [C.c_uint32, C.c_uint32, _u8p]
+    L.port_demod_s.argtypes = [C.c_int, _f32p, _i16p, C.c_uint32]
+    L.port_descramble_s.argtypes = [_i16p, _u8p, C.c_uint32]
+    L.port_demod_descramble.argtypes = [C.c_int, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _i16p]
     _port = L
     return L
 
@@ -128,6 +133,7 @@ def ref():
     L.srslte_cbsegm_cbindex.argtypes = [C.c_uint32]
     L.srslte_tdec_autoimp_get_subblocks.argtypes = [C.c_uint32]
     L.srslte_tdec_autoimp_get_subblocks.restype = C.c_uint32
+    L.refh_demod_descramble.argtypes = [C.c_int, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _i16p, C.c_uint32]
     L.srslte_rm_turbo_gentables()
     _ref = L
     return L
@@ -193,3 +199,29 @@ def ref_trace(llr1, K, nit, natural=True):
         n = np.arange(K)
         so = so[:, (n % L) * W + n // L]
     return by, so
+
+
+# ---- front end (soft demodulation + descrambling) ---------------------------------
+REF_MOD = {2: 1, 4: 2, 6: 3, 8: 4}   # bits per symbol -> srslte_mod_t
+
+
+def port_demod_descramble(qm, sym, c_init, nof_bits=None):
+    """sym: complex64 [n] -> int16 [qm * n] through the port (nof_bits defaults to all of them)."""
+    sym = np.ascontiguousarray(sym, dtype=np.complex64)
+    n = sym.shape[0]
+    nb = qm * n if nof_bits is None else nof_bits
+    llr = np.zeros(qm * n, np.int16)
+    rc = port().port_demod_descramble(qm, sym.view(np.float32), n, c_init, nb, llr)
+    assert rc == 0
+    return llr
+
+
+def ref_demod_descramble(qm, sym, c_init, nof_bits=None):
+    """the same through the reference's own srslte_demod_soft_demodulate_s + srslte_scrambling_s_offset."""
+    sym = np.ascontiguousarray(sym, dtype=np.complex64)
+    n = sym.shape[0]
+    nb = qm * n if nof_bits is None else nof_bits
+    llr = np.zeros(qm * n, np.int16)
+    rc = ref().refh_demod_descramble(REF_MOD[qm], sym.view(np.float32), n, c_init, nb, llr, qm * n)
+    assert rc == 0
+    return llr
