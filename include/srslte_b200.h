@@ -202,6 +202,25 @@ typedef struct {
 SRSLTE_B200_API int srslte_b200_decode_tb_batch(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
                                                 srslte_b200_tb_t* tbs, uint32_t n_tb, uint32_t max_iterations);
 
+/* The same fed with equalised symbols instead of LLRs: soft demodulation, descrambling and rate de-matching run
+ * fused on the device (pdsch.c:760-781: srslte_demod_soft_demodulate_s, srslte_scrambling_s_offset,
+ * srslte_dlsch_decode2), and 8 bytes per resource element cross PCIe instead of 2 * Qm. */
+typedef struct {
+  uint32_t     tbs;            /* transport block size in bits                                        */
+  uint32_t     qm;             /* modulation bits per symbol: 2, 4, 6, 8 (one layer)                  */
+  uint32_t     rv;
+  uint32_t     nof_e_bits;     /* G = grant.tb[].nof_bits (<= qm * nof_symbols): descrambled + decoded */
+  uint32_t     softbuffer;
+  uint32_t     nof_symbols;    /* grant.nof_re                                                        */
+  uint32_t     c_init;         /* scrambling seed of (rnti, codeword, subframe, cell)                 */
+  const float* symbols;        /* host: nof_symbols complex floats (re, im)                           */
+  uint8_t*     data;           /* host: decoded TB, at least tbs/8 + 6 bytes                          */
+  int32_t      ret;            /* out: as srslte_b200_tb_t                                            */
+  float        avg_iterations; /* out                                                                 */
+} srslte_b200_tb_sym_t;
+SRSLTE_B200_API int srslte_b200_decode_tb_sym_batch(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
+                                                    srslte_b200_tb_sym_t* tbs, uint32_t n_tb, uint32_t max_iterations);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,12 @@ class TbDesc(C.Structure):
                 ("avg_iterations", C.c_float)]
 
 
+class TbSymDesc(C.Structure):
+    _fields_ = [("tbs", C.c_uint32), ("qm", C.c_uint32), ("rv", C.c_uint32), ("nof_e_bits", C.c_uint32),
+                ("softbuffer", C.c_uint32), ("nof_symbols", C.c_uint32), ("c_init", C.c_uint32),
+                ("symbols", C.c_void_p), ("data", C.c_void_p), ("ret", C.c_int32), ("avg_iterations", C.c_float)]
+
+
 EXPORTS = [
     "srslte_b200_ctx_create", "srslte_b200_ctx_destroy", "srslte_b200_ctx_set_stream",
     "srslte_b200_ctx_synchronize", "srslte_b200_last_error", "srslte_b200_launch_count",
@@ -59,7 +65,7 @@ EXPORTS = [
     "srslte_b200_tdec_batch_dev", "srslte_b200_tdec_batch_host", "srslte_b200_rm_rx_batch_dev",
     "srslte_b200_demod_descramble_dev", "srslte_b200_demod_rm_rx_batch_dev",
     "srslte_b200_harq_pool_create", "srslte_b200_harq_pool_destroy", "srslte_b200_harq_reset",
-    "srslte_b200_harq_cb_crc", "srslte_b200_decode_tb_batch",
+    "srslte_b200_harq_cb_crc", "srslte_b200_decode_tb_batch", "srslte_b200_decode_tb_sym_batch",
 ]
 
 _lib = None
@@ -110,6 +116,7 @@ def lib():
     L.srslte_b200_harq_reset.argtypes = [vp, vp, u32]
     L.srslte_b200_harq_cb_crc.argtypes = [vp, u32, vp, u32]
     L.srslte_b200_decode_tb_batch.argtypes = [vp, vp, C.POINTER(TbDesc), u32, u32]
+    L.srslte_b200_decode_tb_sym_batch.argtypes = [vp, vp, C.POINTER(TbSymDesc), u32, u32]
     _lib = L
     return L
 
@@ -274,6 +281,23 @@ class Context:
             arr[i] = TbDesc(t["tbs"], t["qm"], t["rv"], e.size, t["softbuffer"], e.ctypes.data, o.ctypes.data, 0, 0.0)
         rc = self._L.srslte_b200_decode_tb_batch(self._h, pool._p, arr, n, max_iterations)
         self._check(rc, "srslte_b200_decode_tb_batch")
+        return [(int(arr[i].ret), outs[i], float(arr[i].avg_iterations)) for i in range(n)]
+
+    def decode_tb_sym_batch(self, pool, tbs, max_iterations):
+        """tbs: list of dicts(tbs, qm, rv, nof_e_bits, softbuffer, c_init, symbols=complex64 array).
+        Returns [(ret, data bytes, avg_iterations)] like decode_tb_batch."""
+        n = len(tbs)
+        arr = (TbSymDesc * n)()
+        keep, outs = [], []
+        for i, d in enumerate(tbs):
+            sym = np.ascontiguousarray(d["symbols"], dtype=np.complex64)
+            out = np.zeros(d["tbs"] // 8 + 8, np.uint8)
+            keep.append(sym)
+            outs.append(out)
+            arr[i] = TbSymDesc(d["tbs"], d["qm"], d["rv"], d["nof_e_bits"], d["softbuffer"], sym.shape[0], d["c_init"],
+                               sym.ctypes.data, out.ctypes.data, 0, 0.0)
+        rc = self._L.srslte_b200_decode_tb_sym_batch(self._h, pool._p, arr, n, max_iterations)
+        self._check(rc, "srslte_b200_decode_tb_sym_batch")
         return [(int(arr[i].ret), outs[i], float(arr[i].avg_iterations)) for i in range(n)]
 
     def rm_rx_batch_dev(self, blocks, e_ptr, work_ptr):

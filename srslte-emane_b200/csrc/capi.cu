@@ -927,8 +927,18 @@ int srslte_b200_harq_cb_crc(srslte_b200_harq_pool_t* p, uint32_t softbuffer, uin
   return SRSLTE_B200_SUCCESS;
 }
 
-int srslte_b200_decode_tb_batch(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool, srslte_b200_tb_t* tbs,
-                                uint32_t n_tb, uint32_t max_iterations)
+}  // extern "C"
+
+namespace {
+struct TbSymSrc {  // where a transport block's LLRs come from when the caller hands over equalised symbols
+  const float* symbols;  // host: nof_symbols complex floats
+  uint32_t     nof_symbols, mod_bits, c_init;
+};
+}  // namespace
+
+// sym == nullptr: tbs[i].e_bits are int16 LLRs (decode_tb); else LLRs are demodulated + descrambled on the device
+static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool, srslte_b200_tb_t* tbs, uint32_t n_tb,
+                          uint32_t max_iterations, const TbSymSrc* sym)
 {
   if (!ctx) return SRSLTE_B200_ERROR_INVALID_INPUTS;
   if (n_tb == 0) return SRSLTE_B200_SUCCESS;
@@ -949,7 +959,11 @@ int srslte_b200_decode_tb_batch(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t*
     srslte_b200_tb_t& t = tbs[i];
     t.ret            = SRSLTE_B200_ERROR_INVALID_INPUTS;
     t.avg_iterations = 0;
-    if (!t.e_bits || !t.data || t.softbuffer >= pool->n_sb || t.rv > 3 || t.qm == 0) continue;
+    if ((!sym && !t.e_bits) || !t.data || t.softbuffer >= pool->n_sb || t.rv > 3 || t.qm == 0) continue;
+    if (sym && (!sym[i].symbols || (uint64_t)sym[i].mod_bits * sym[i].nof_symbols < t.nof_e_bits ||
+                (sym[i].mod_bits != 2 && sym[i].mod_bits != 4 && sym[i].mod_bits != 6 && sym[i].mod_bits != 8) ||
+                t.nof_e_bits > kGoldMaxLen))
+      continue;
     if (cbsegm(&seg[i], t.tbs)) {
       t.ret = SRSLTE_B200_ERROR;  // srslte_dlsch_decode2: "Error computing Codeword segmentation"
       continue;
@@ -964,7 +978,7 @@ int srslte_b200_decode_tb_batch(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t*
     t.data[t.tbs / 8 + 1] = 0;
     t.data[t.tbs / 8 + 2] = 0;
     e_base[i] = e_total;
-    e_total += (t.nof_e_bits + 1u) & ~1u;
+    e_total += sym ? (size_t)sym[i].nof_symbols : (size_t)((t.nof_e_bits + 1u) & ~1u);  // symbols or int16 LLRs
     const CbSegm& s   = seg[i];
     uint8_t*      crc = pool->cb_crc.data() + (size_t)t.softbuffer * pool->max_cb;
     for (uint32_t cb = 0; cb < s.C; cb++) {
@@ -990,11 +1004,19 @@ int srslte_b200_decode_tb_batch(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t*
   if (n_cb) {
     // ---- upload the rate-matched LLRs of every TB that has work ----
     CU(cudaStreamSynchronize(st));  // staging reuse
-    CU(pool->h_e.reserve(e_total));
-    CU(pool->d_e.reserve(e_total));
-    for (uint32_t i = 0; i < n_tb; i++)
-      if (run[i]) std::memcpy(pool->h_e.p + e_base[i], tbs[i].e_bits, (size_t)tbs[i].nof_e_bits * sizeof(int16_t));
-    CU(cudaMemcpyAsync(pool->d_e.p, pool->h_e.p, e_total * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    // (symbols: 8 bytes per resource element instead of 2 * Qm bytes of LLRs cross PCIe)
+    const size_t e_units = sym ? e_total * 4 : e_total;  // int16 units of the staging buffers
+    CU(pool->h_e.reserve(e_units));
+    CU(pool->d_e.reserve(e_units));
+    for (uint32_t i = 0; i < n_tb; i++) {
+      if (!run[i]) continue;
+      if (sym)
+        std::memcpy(reinterpret_cast<float*>(pool->h_e.p) + 2 * e_base[i], sym[i].symbols,
+                    (size_t)sym[i].nof_symbols * 2 * sizeof(float));
+      else
+        std::memcpy(pool->h_e.p + e_base[i], tbs[i].e_bits, (size_t)tbs[i].nof_e_bits * sizeof(int16_t));
+    }
+    CU(cudaMemcpyAsync(pool->d_e.p, pool->h_e.p, e_units * sizeof(int16_t), cudaMemcpyHostToDevice, st));
 
     // ---- rate de-matching with HARQ combining, in place in the pool ----
     std::vector<srslte_b200_rm_block_t> rm(n_cb);
@@ -1015,7 +1037,28 @@ int srslte_b200_decode_tb_batch(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t*
       pool->h_off.p[j]  = off;
       pool->h_mode.p[j] = seg[jb.tb].C > 1 ? (uint8_t)CRC_24B : (uint8_t)CRC_24A;
     }
-    int rc = srslte_b200_rm_rx_batch_dev(ctx, rm.data(), n_cb, pool->d_e.p, pool->llr.p);
+    int rc;
+    if (!sym) {
+      rc = srslte_b200_rm_rx_batch_dev(ctx, rm.data(), n_cb, pool->d_e.p, pool->llr.p);
+    } else {  // demodulate + descramble + rate de-match in one kernel: the e array never exists
+      std::vector<srslte_b200_codeword_t>     cws;
+      std::vector<uint32_t>                   cw_of(n_tb, 0);
+      std::vector<srslte_b200_rm_sym_block_t> bl(n_cb);
+      for (uint32_t i = 0; i < n_tb; i++) {
+        if (!run[i]) continue;
+        srslte_b200_codeword_t c{};
+        c.qm = sym[i].mod_bits; c.nof_symbols = sym[i].nof_symbols; c.c_init = sym[i].c_init;
+        c.nof_bits = tbs[i].nof_e_bits; c.sym_offset = e_base[i]; c.llr_offset = 0;
+        cw_of[i] = (uint32_t)cws.size();
+        cws.push_back(c);
+      }
+      for (uint32_t j = 0; j < n_cb; j++) {
+        bl[j].long_cb = rm[j].long_cb; bl[j].rv = rm[j].rv; bl[j].codeword = cw_of[jobs[j].tb];
+        bl[j].e_offset = jobs[j].rp; bl[j].e_len = rm[j].e_len; bl[j].work_offset = rm[j].work_offset;
+      }
+      rc = srslte_b200_demod_rm_rx_batch_dev(ctx, cws.data(), (uint32_t)cws.size(), bl.data(), n_cb,
+                                             reinterpret_cast<const float*>(pool->d_e.p), pool->llr.p);
+    }
     if (rc) return rc;
 
     // ---- decode all blocks of all TBs in one batch, CRC after every half iteration ----
@@ -1087,6 +1130,37 @@ int srslte_b200_decode_tb_batch(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t*
     t.ret = (par_rx == par_tx && par_rx) ? SRSLTE_B200_SUCCESS : SRSLTE_B200_ERROR;  // `&& par_rx`: sch.c:481
   }
   return SRSLTE_B200_SUCCESS;
+}
+
+extern "C" {
+
+int srslte_b200_decode_tb_batch(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool, srslte_b200_tb_t* tbs,
+                                uint32_t n_tb, uint32_t max_iterations)
+{
+  return decode_tb_core(ctx, pool, tbs, n_tb, max_iterations, nullptr);
+}
+
+int srslte_b200_decode_tb_sym_batch(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool, srslte_b200_tb_sym_t* tbs,
+                                    uint32_t n_tb, uint32_t max_iterations)
+{
+  if (!ctx) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  if (n_tb == 0) return SRSLTE_B200_SUCCESS;
+  if (!tbs) return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "NULL argument");
+  std::vector<srslte_b200_tb_t> tb(n_tb);
+  std::vector<TbSymSrc>         src(n_tb);
+  for (uint32_t i = 0; i < n_tb; i++) {
+    tb[i] = srslte_b200_tb_t{};
+    tb[i].tbs = tbs[i].tbs; tb[i].qm = tbs[i].qm; tb[i].rv = tbs[i].rv; tb[i].nof_e_bits = tbs[i].nof_e_bits;
+    tb[i].softbuffer = tbs[i].softbuffer; tb[i].e_bits = nullptr; tb[i].data = tbs[i].data;
+    src[i].symbols = tbs[i].symbols; src[i].nof_symbols = tbs[i].nof_symbols; src[i].mod_bits = tbs[i].qm;
+    src[i].c_init = tbs[i].c_init;
+  }
+  const int rc = decode_tb_core(ctx, pool, tb.data(), n_tb, max_iterations, src.data());
+  for (uint32_t i = 0; i < n_tb; i++) {
+    tbs[i].ret            = tb[i].ret;
+    tbs[i].avg_iterations = tb[i].avg_iterations;
+  }
+  return rc;
 }
 
 }  // extern "C"

@@ -96,3 +96,75 @@ def test_argument_errors(ctx):
         ctx.demod_descramble_dev([dict(qm=3, nof_symbols=4, c_init=1)], s.data_ptr(), e.data_ptr())
     with pytest.raises(Exception):
         ctx.demod_descramble_dev([dict(qm=2, nof_symbols=4, c_init=1, nof_bits=9)], s.data_ptr(), e.data_ptr())
+
+
+def _modulate(bits, qm):
+    """36.211 7.1 mapping (QPSK, 16QAM, 64QAM): bits [n * qm] -> complex64 [n]."""
+    b = 1.0 - 2.0 * bits.reshape(-1, qm).astype(np.float64)
+    if qm == 2:
+        i, q, nrm = b[:, 0], b[:, 1], np.sqrt(2)
+    elif qm == 4:
+        i, q, nrm = b[:, 0] * (2 - b[:, 2]), b[:, 1] * (2 - b[:, 3]), np.sqrt(10)
+    else:
+        i, q, nrm = b[:, 0] * (4 - b[:, 2] * (2 - b[:, 4])), b[:, 1] * (4 - b[:, 3] * (2 - b[:, 5])), np.sqrt(42)
+    return ((i + 1j * q) / nrm).astype(np.complex64)
+
+
+def test_transport_blocks_from_symbols_vs_oracle(ctx, vec):
+    """Whole chain from equalised symbols to transport-block bytes in one call (pdsch.c:760-796): TBs are built
+    with the numpy TX mirror (CRC, segmentation, turbo encoder, rate matching, scrambling, modulation, AWGN) and
+    decoded by the oracle (port_demod_descramble -> port_decode_tb) and by srslte_b200_decode_tb_sym_batch."""
+    import ctypes as C
+    P = ol.port()
+    rng = np.random.default_rng(21)
+    cases = [(2216, 2, 4800), (6200, 4, 9600), (14112, 4, 28800), (36696, 6, 60000), (75376, 6, 90000), (1000, 2, 2400)]
+    descs, want = [], []
+    dec = P.port_tdec_new()
+    for i, (tbs, qm, G) in enumerate(cases * 2):
+        seg = ol.PortCbsegm()
+        assert P.port_cbsegm(C.byref(seg), tbs) == 0 and seg.F == 0
+        payload = rng.integers(0, 2, tbs, dtype=np.uint8)
+        tb = vec.attach_crc(vec.CRC24A, payload[None, :])[0]
+        e_parts, pos = [], 0
+        Gp, gamma = G // qm, (G // qm) % seg.C
+        for cb in range(seg.C):
+            K = seg.K1 if cb < seg.C1 else seg.K2
+            rlen = K if seg.C == 1 else K - 24
+            blk = tb[pos:pos + rlen]
+            pos += rlen
+            if seg.C > 1:
+                blk = vec.attach_crc(vec.CRC24B, blk[None, :])[0]
+            E = qm * (Gp // seg.C) if cb <= seg.C - gamma - 1 else qm * ((Gp + seg.C - 1) // seg.C)
+            e_parts.append(vec.rate_match(vec.turbo_encode(blk[None, :]), E, 0)[0])
+        e = np.concatenate(e_parts).astype(np.uint8)
+        assert e.size == G
+        c_init = int(rng.integers(1, 2 ** 31 - 1))
+        c = np.zeros(G, np.uint8)
+        P.port_gold_sequence(c_init, G, c)
+        sigma = (0.0, 0.08, 0.25)[i % 3]
+        sym = _modulate(e ^ c, qm)
+        sym = (sym + sigma * (rng.standard_normal(sym.size) + 1j * rng.standard_normal(sym.size))).astype(np.complex64)
+        llr = ol.port_demod_descramble(qm, sym, c_init, G)
+        sb = ol.PortSoftbuffer()
+        P.port_softbuffer_init(C.byref(sb), seg.C)
+        out = np.zeros(tbs // 8 + 8, np.uint8)
+        avg = C.c_float()
+        noi = np.zeros(seg.C, np.uint32)
+        rc = P.port_decode_tb(dec, C.byref(sb), tbs, qm, 0, G, llr, out, 8, C.byref(avg), noi)
+        want.append((rc, out[: tbs // 8 + 3].copy(), avg.value, np.packbits(payload)))
+        P.port_softbuffer_free(C.byref(sb))
+        descs.append(dict(tbs=tbs, qm=qm, rv=0, nof_e_bits=G, softbuffer=i, c_init=c_init, symbols=sym))
+    P.port_tdec_free(dec)
+    pool = ctx.harq_pool(len(descs), 13)
+    got = ctx.decode_tb_sym_batch(pool, descs, 8)
+    n_ok = 0
+    for i, ((ret, data, avg), (rc, out, wavg, payload)) in enumerate(zip(got, want)):
+        tbs = descs[i]["tbs"]
+        assert ret == rc, i
+        assert abs(avg - wavg) < 1e-6, (i, avg, wavg)
+        assert np.array_equal(data[: tbs // 8 + 3], out), i
+        if ret == 0:
+            n_ok += 1
+            assert np.array_equal(data[: tbs // 8], payload)
+    assert n_ok >= 8
+    pool.close()
