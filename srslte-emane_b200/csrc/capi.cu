@@ -127,7 +127,7 @@ struct srslte_b200_ctx {
   DevBuf<RmSymItem>            d_rm_sym;
   PinBuf<RmSymItem>            h_rm_sym;
   uint64_t     launches = 0;
-  // optional per-kernel event timing (bench.py's roofline): kind 0..4 = W16, W8, generic, layout, rate-dematch
+  // optional per-kernel event timing (bench.py's roofline): kind 0..4 = W16, W8, generic, layout, front end (demod / rate-dematch)
   bool         timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev[5];
   size_t       tev_used[5] = {0, 0, 0, 0, 0};
@@ -769,7 +769,10 @@ int srslte_b200_demod_descramble_dev(srslte_b200_ctx_t* ctx, const srslte_b200_c
   uint32_t max_llr = 0;
   int      rc      = fe_prepare(ctx, cws, n_cw, &max_llr);
   if (rc) return rc;
-  CU(demod_descramble_launch(ctx->d_cws.p, n_cw, max_llr, symbols, e, ctx->gold_x1.p, ctx->gold_x2.p, ctx->stream));
+  {
+    KernelTimer kt(ctx, 4, ctx->stream);
+    CU(demod_descramble_launch(ctx->d_cws.p, n_cw, max_llr, symbols, e, ctx->gold_x1.p, ctx->gold_x2.p, ctx->stream));
+  }
   ctx->launches++;
   return SRSLTE_B200_SUCCESS;
 }

@@ -84,3 +84,42 @@ def run4():
 ms = timed(run4)
 print(f"config4 mixed batch: {len(Ks)} blocks = 188 sizes x {per}, 4 half-its: {ms:.3f} ms/step, "
       f"{float(Ks.sum()) / ms / 1e6:.2f} Gbit/s")
+
+# ---- front end: soft demodulation + descrambling, alone and fused into rate de-matching ----------
+n_cw, nsym, qm = 1024, 15000, 6        # config 2's codeword: 100 PRB, 64QAM, 90000 bits, 13 blocks of K = 5824
+sym = torch.randn((n_cw, nsym, 2), device=dev, dtype=torch.float32) * 0.7
+e = torch.zeros((n_cw, qm * nsym), dtype=torch.int16, device=dev)
+cws = [dict(qm=qm, nof_symbols=nsym, c_init=1 + 7919 * i, sym_offset=i * nsym, llr_offset=i * qm * nsym) for i in range(n_cw)]
+def ktimed(fn, reps=3):
+    """device time of the front-end kernels only (the library's own CUDA events, kind 4)"""
+    fn(); ctx.synchronize()
+    ctx.enable_timing(True)
+    for _ in range(reps): fn()
+    ctx.synchronize()
+    ms, n = ctx.kernel_time(4)
+    ctx.enable_timing(False)
+    return ms / reps
+
+
+ms = ktimed(lambda: ctx.demod_descramble_dev(cws, sym.data_ptr(), e.data_ptr()))
+byt = n_cw * nsym * (8 + 2 * qm)
+print(f"front end: {n_cw} codewords x {nsym} symbols 64QAM -> {n_cw * nsym * qm / 1e6:.1f} M LLRs: {ms:.3f} ms kernel time, "
+      f"{byt / ms / 1e6:.0f} GB/s of symbol + LLR traffic ({byt / ms / 1e6 / 6536.7 * 100:.0f}% of the measured HBM copy rate), "
+      f"{n_cw * nsym * qm / ms / 1e6:.1f} G LLR/s")
+wl = 18624
+work = torch.zeros((n_cw * 13, wl), dtype=torch.int16, device=dev)
+blocks = []
+for i in range(n_cw):
+    rp = 0
+    for cb in range(13):
+        E = 6918 if cb <= 2 else 6924     # sch.c:324-334 for G = 90000, C = 13
+        blocks.append((5824, 0, i, rp, E, (i * 13 + cb) * wl))
+        rp += E
+ms = ktimed(lambda: ctx.demod_rm_rx_batch_dev(cws, blocks, sym.data_ptr(), work.data_ptr()))
+print(f"front end fused with rate de-matching: {len(blocks)} blocks K=5824: {ms:.3f} ms kernel time, "
+      f"{n_cw * 90000 / ms / 1e6:.1f} G LLR/s")
+e2 = e.clone()
+rmb = [(5824, 0, b[2] * 90000 + b[3], b[4], b[5]) for b in blocks]
+ms2 = ktimed(lambda: (ctx.demod_descramble_dev(cws, sym.data_ptr(), e2.data_ptr()),
+                      ctx.rm_rx_batch_dev(rmb, e2.data_ptr(), work.data_ptr())))
+print(f"front end unfused (demod kernel + rm kernel through the e array): {ms2:.3f} ms kernel time")
