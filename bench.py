@@ -33,7 +33,7 @@ NOF_ITERATIONS = 4          # srsLTE HALF iterations
 EBNO_HARNESS = 1.5          # turbodecoder_test "-e 1.5" (sigma = 1.457 on +-1; never converges, F7)
 LLR_SCALE = 100.0
 IN_LEN = 3 * K + 12
-NCU_DRAM_BYTES_PER_BLOCK = 425.8e3        # profiles/r01b_ncu_raw.csv: (20.46 + 7.45) GB / 65536 blocks
+NCU_DRAM_BYTES_PER_BLOCK = 421.0e3        # profiles/r01c_ncu_raw.csv: (20.35 + 7.24) GB / 65536 blocks
 INT_PEAK_THREAD_INSTR_PER_CLK_SM = 64.0   # measured: profiles/r01_int_peak*.txt (VIADD.16x2 / VIMNMX.S16x2)
 
 
@@ -326,7 +326,7 @@ def main():
                            f"(tools/int_peak.cu, profiles/r01_int_peak*.txt) x 2 lanes x {sms} SMs x {sm_max:g} MHz",
             "sm_mhz_during_run": sm_mhz,
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture in
-            # profiles/ (27.91 GB for the 65536-block launch = 425.8 KB per block), scaled to this launch
+            # profiles/ (27.59 GB for the 65536-block launch = 421.0 KB per block), scaled to this launch
             "traffic": NCU_DRAM_BYTES_PER_BLOCK * n,
             "two_pipe_peak": 2 * peak_tops,
             "note": "peak = ONE integer pipe (64 packed thread-instr/clk/SM, what every single packed op reaches); "
