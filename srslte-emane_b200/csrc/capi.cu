@@ -111,6 +111,8 @@ struct srslte_b200_ctx {
   // host-pipeline buffers (double buffered)
   DevBuf<int16_t> d_in[2];
   DevBuf<uint8_t> d_out[2], d_nit[2], d_crc[2];
+  PinBuf<uint8_t> h_nit_all, h_crc_all;  // n_iter / crc_ok of a whole host call: the caller's arrays may be pageable,
+                                         // and an async copy into pageable memory would block the enqueueing thread
   cudaEvent_t  ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   // rate-dematching tables
   std::map<uint32_t, uint32_t> rm_tab_off;  // key = ((K*4+rv)*2 + sb_layout) -> offset in the pool
@@ -484,6 +486,8 @@ void srslte_b200_ctx_destroy(srslte_b200_ctx_t* ctx)
     ctx->d_out[i].release();
     ctx->d_nit[i].release();
     ctx->d_crc[i].release();
+    ctx->h_nit_all.release();
+    ctx->h_crc_all.release();
     if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
     if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
     if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
@@ -618,17 +622,28 @@ int srslte_b200_tdec_batch_host(srslte_b200_ctx_t* ctx, const srslte_b200_tdec_b
 
   // Pieces of up to `piece` blocks: H2D of piece p+1 overlaps the kernels of piece p and the D2H of
   // piece p-1.  Uniform-K batches reuse one cached schedule for every full piece.
-  // Large copies run closer to the PCIe rate than small ones and the decode kernels slow a concurrent copy
-  // down, so big batches use big pieces (measured on B200: 16384-block pieces 7.45 Gbit/s, 4096-block pieces
-  // 6.87 Gbit/s at 32768 blocks of K = 6144); small batches keep 4096 so that they still pipeline.
+  // Pieces of 4096 blocks (151 MB of LLRs at K = 6144) keep the copy engine at the PCIe rate and leave only one
+  // small piece of compute + D2H exposed at the end.
   static const uint32_t piece_env = [] {
     const char* e = getenv("SRSLTE_B200_PIECE");  // tuning knob: code blocks per pipeline piece
     const long  v = e ? atol(e) : 0;
     return v >= 64 && v <= (1 << 20) ? (uint32_t)v : 0u;
   }();
-  const uint32_t piece = piece_env ? piece_env : b->n_cb >= 32768 ? 16384u : b->n_cb >= 16384 ? 8192u : 4096u;
+  const uint32_t piece = piece_env ? piece_env : 4096u;
   cudaStream_t   cs    = ctx->stream;
   const uint32_t n_pieces = (b->n_cb + piece - 1) / piece;
+  if (n_iter) CU(ctx->h_nit_all.reserve(b->n_cb));
+  if (crc_ok) CU(ctx->h_crc_all.reserve(b->n_cb));
+  static const bool trace = getenv("SRSLTE_B200_TRACE") != nullptr;  // development probe: per-piece timeline
+  std::vector<cudaEvent_t> tr;
+  auto mark = [&](cudaStream_t s) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    tr.push_back(e);
+  };
+  mark(cs);
   for (uint32_t p = 0; p < n_pieces; p++) {
     const int      s     = (int)(p & 1);
     const uint32_t first = p * piece;
@@ -643,25 +658,42 @@ int srslte_b200_tdec_batch_host(srslte_b200_ctx_t* ctx, const srslte_b200_tdec_b
       CU(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_comp[s], 0));
       CU(cudaStreamWaitEvent(cs, ctx->ev_d2h[s], 0));
     }
+    mark(ctx->h2d_stream);
     CU(cudaMemcpyAsync(ctx->d_in[s].p, llr + (size_t)first * b->in_stride, in_elems * sizeof(int16_t),
                        cudaMemcpyHostToDevice, ctx->h2d_stream));
+    mark(ctx->h2d_stream);
     CU(cudaEventRecord(ctx->ev_h2d[s], ctx->h2d_stream));
     CU(cudaStreamWaitEvent(cs, ctx->ev_h2d[s], 0));
     srslte_b200_tdec_batch_t pb = *b;
     pb.n_cb                     = n;
     pb.long_cb                  = b->long_cb ? b->long_cb + first : nullptr;
+    mark(cs);
     rc = enqueue_decode(ctx, &pb, work_len, ctx->d_in[s].p, ctx->d_out[s].p, ctx->d_nit[s].p, ctx->d_crc[s].p, cs);
     if (rc) return rc;
+    mark(cs);
     CU(cudaEventRecord(ctx->ev_comp[s], cs));
     CU(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_comp[s], 0));
     CU(cudaMemcpyAsync(out + (size_t)first * b->out_stride, ctx->d_out[s].p, (size_t)n * b->out_stride,
                        cudaMemcpyDeviceToHost, ctx->d2h_stream));
-    if (n_iter) CU(cudaMemcpyAsync(n_iter + first, ctx->d_nit[s].p, n, cudaMemcpyDeviceToHost, ctx->d2h_stream));
-    if (crc_ok) CU(cudaMemcpyAsync(crc_ok + first, ctx->d_crc[s].p, n, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    if (n_iter) CU(cudaMemcpyAsync(ctx->h_nit_all.p + first, ctx->d_nit[s].p, n, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    if (crc_ok) CU(cudaMemcpyAsync(ctx->h_crc_all.p + first, ctx->d_crc[s].p, n, cudaMemcpyDeviceToHost, ctx->d2h_stream));
     CU(cudaEventRecord(ctx->ev_d2h[s], ctx->d2h_stream));
   }
   CU(cudaStreamSynchronize(ctx->d2h_stream));
   CU(cudaStreamSynchronize(cs));
+  if (n_iter) std::memcpy(n_iter, ctx->h_nit_all.p, b->n_cb);
+  if (crc_ok) std::memcpy(crc_ok, ctx->h_crc_all.p, b->n_cb);
+  if (trace && !tr.empty()) {
+    for (size_t i = 1; i + 3 < tr.size() + 1 && i + 3 <= tr.size(); i += 4) {
+      float a, b2, c2, d2;
+      cudaEventElapsedTime(&a, tr[0], tr[i]);
+      cudaEventElapsedTime(&b2, tr[0], tr[i + 1]);
+      cudaEventElapsedTime(&c2, tr[0], tr[i + 2]);
+      cudaEventElapsedTime(&d2, tr[0], tr[i + 3]);
+      fprintf(stderr, "piece %zu: H2D %.2f..%.2f ms, decode %.2f..%.2f ms\n", (i - 1) / 4, a, b2, c2, d2);
+    }
+    for (auto e : tr) cudaEventDestroy(e);
+  }
   return SRSLTE_B200_SUCCESS;
 }
 
