@@ -121,6 +121,10 @@ struct srslte_b200_ctx {
   size_t                       rm_pool_uploaded = 0;
   DevBuf<RmItem>               d_rm_items;
   PinBuf<RmItem>               h_rm_items;
+  // per-bit CRC contributions of the window decoders (CRC modes), built per K on first use
+  std::vector<uint32_t>        crc_pos_host, crc_pos_off_host;
+  DevBuf<uint32_t>             crc_pos_dev, crc_pos_off_dev;
+  size_t                       crc_pos_uploaded = 0;
   // front end (soft demodulation + descrambling)
   DevBuf<uint32_t>             gold_x1, gold_x2;   // scrambling-sequence tables (lte_tables.cpp:gold_tables)
   bool                         gold_ready = false;
@@ -238,9 +242,11 @@ int build_schedule(srslte_b200_ctx* ctx, const uint32_t* K, uint32_t uniform_K, 
     const int ri  = regime_index(W);
     const uint32_t per = (uint32_t)tdec_blocks_per_warp(W);
     WorkItem       wi;
-    wi.K  = (uint16_t)Kv;
-    wi.f1 = kQpp[idx].f1;
-    wi.f2 = kQpp[idx].f2;
+    wi.K    = (uint16_t)Kv;
+    wi.f1   = kQpp[idx].f1;
+    wi.f2   = kQpp[idx].f2;
+    wi.kidx = (uint16_t)idx;
+    wi.pad  = 0;
     for (uint32_t o = 0; o < count; o += per) {
       wi.first = first + o;
       wi.count = (uint16_t)std::min(per, count - o);
@@ -389,6 +395,38 @@ int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint
     CU(ctx->counters.reserve(4));
     CU(cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(uint32_t), st));
   }
+  if (b->crc_mode != SRSLTE_B200_CRC_NONE || d_crc_mode_cb) {
+    // the window decoders check CRCs through per-bit contribution tables: make sure every K of this launch has one
+    if (ctx->crc_pos_off_host.empty()) ctx->crc_pos_off_host.assign(kNofCbSizes, 0xFFFFFFFFu);
+    bool grew = false;
+    for (int r = 0; r < 2; r++) {
+      uint32_t lastK = 0;
+      for (const WorkItem& wi : ctx->sched.items[r]) {
+        if (wi.K == lastK) continue;
+        lastK = wi.K;
+        if (ctx->crc_pos_off_host[wi.kidx] != 0xFFFFFFFFu) continue;
+        std::vector<uint32_t> tab;
+        crc_pos_tables(wi.K, tab);
+        ctx->crc_pos_off_host[wi.kidx] = (uint32_t)ctx->crc_pos_host.size();
+        ctx->crc_pos_host.insert(ctx->crc_pos_host.end(), tab.begin(), tab.end());
+        grew = true;
+      }
+    }
+    if (grew) {
+      if (ctx->crc_pos_host.size() > ctx->crc_pos_dev.cap) {
+        CU(cudaStreamSynchronize(st));  // kernels in flight may still read the old pool
+        CU(ctx->crc_pos_dev.reserve(ctx->crc_pos_host.size() * 2));
+        ctx->crc_pos_uploaded = 0;
+      }
+      CU(ctx->crc_pos_off_dev.reserve(kNofCbSizes));
+      CU(cudaMemcpyAsync(ctx->crc_pos_dev.p + ctx->crc_pos_uploaded, ctx->crc_pos_host.data() + ctx->crc_pos_uploaded,
+                         (ctx->crc_pos_host.size() - ctx->crc_pos_uploaded) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(ctx->crc_pos_off_dev.p, ctx->crc_pos_off_host.data(), kNofCbSizes * sizeof(uint32_t),
+                         cudaMemcpyHostToDevice, st));
+      CU(cudaStreamSynchronize(st));  // the sources are pageable std::vector memory
+      ctx->crc_pos_uploaded = ctx->crc_pos_host.size();
+    }
+  }
   for (int r = 0; r < 3; r++) {
     const auto& items = ctx->sched.items[r];
     if (items.empty()) continue;
@@ -413,6 +451,8 @@ int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint
     a.crc_mode_cb = d_crc_mode_cb;
     a.ws_ae      = reinterpret_cast<int16_t*>(R.ws_ae.p);
     a.ws_chk     = reinterpret_cast<uint32_t*>(R.ws_chk.p);
+    a.crc_pos     = ctx->crc_pos_dev.p;
+    a.crc_pos_off = ctx->crc_pos_off_dev.p;
     a.force_exact = ctx->force_exact ? 1u : 0u;
     a.stats      = ctx->counters.p + 3;
     {
@@ -500,6 +540,8 @@ void srslte_b200_ctx_destroy(srslte_b200_ctx_t* ctx)
   ctx->rm_pool_dev.release();
   ctx->d_rm_items.release();
   ctx->h_rm_items.release();
+  ctx->crc_pos_dev.release();
+  ctx->crc_pos_off_dev.release();
   ctx->gold_x1.release();
   ctx->gold_x2.release();
   ctx->d_cws.release();

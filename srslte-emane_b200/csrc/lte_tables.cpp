@@ -333,6 +333,33 @@ uint32_t crc24_bytes(uint32_t poly, const uint8_t* data, uint32_t nbytes)
   return crc;
 }
 
+void crc_pos_tables(uint32_t K, std::vector<uint32_t>& out)
+{
+  const int      ki = cb_index_exact(K);
+  const uint32_t W = (uint32_t)nof_windows(K), L = W ? K / W : 0;
+  out.clear();
+  if (ki < 0 || W == 0) return;
+  const uint64_t f1 = kQpp[ki].f1, f2 = kQpp[ki].f2;
+  out.resize(4 * (size_t)K);
+  const uint32_t polys[2] = {kCrc24A, kCrc24B};
+  std::vector<uint32_t> pw(K + 24);
+  for (uint32_t which = 0; which < 2; which++) {
+    uint32_t v = 1;
+    for (uint32_t n = 0; n < K + 24; n++) {  // pw[n] = x^n mod P
+      pw[n] = v;
+      v <<= 1;
+      if (v & 0x1000000u) v ^= polys[which];
+    }
+    for (uint32_t k = 0; k < L; k++)
+      for (uint32_t d = 0; d < W; d++) {
+        const uint64_t i = (uint64_t)d * L + k;
+        const uint32_t pi = (uint32_t)((f1 * i + f2 * i * i) % K);
+        out[((which * 2 + 0) * (size_t)L + k) * W + d] = pw[K + 23 - (uint32_t)i];
+        out[((which * 2 + 1) * (size_t)L + k) * W + d] = pw[K + 23 - pi];
+      }
+  }
+}
+
 void gold_tables(uint32_t len, std::vector<uint32_t>& x1_packed, std::vector<uint32_t>& x2_mask)
 {
   const uint32_t Nc = 1600, n_tot = Nc + len;

@@ -48,6 +48,12 @@ void rm_rx_table(uint32_t K, uint32_t rv, bool sb_layout, std::vector<uint16_t>&
 void gold_tables(uint32_t len, std::vector<uint32_t>& x1_packed, std::vector<uint32_t>& x2_mask);
 
 void crc24_table(uint32_t poly, uint32_t table[256]);
+// What bit p of a K-bit block contributes to its CRC24 register (init 0): x^(K + 23 - p) mod P.  The CRC is linear,
+// so the register is the xor of the contributions of the set bits IN ANY ORDER: the window decoders accumulate it
+// while they produce the hard decisions, without assembling the bit string.
+// out[((which * 2 + dir) * L + k) * W + d], which: 0 = CRC24A, 1 = CRC24B; dir 0: trellis position d*L + k of DEC1
+// (natural order), dir 1: of DEC2 (bit pi(d*L + k)).  Window decoders only (W = 16 or 8).
+void crc_pos_tables(uint32_t K, std::vector<uint32_t>& out);
 uint32_t crc24_bytes(uint32_t poly, const uint8_t* data, uint32_t nbytes);
 
 }  // namespace b200

@@ -238,6 +238,9 @@ struct WinCtx {
   uint32_t*       A32;  // [row][32 lanes] words: extrinsic of DEC2 minus E, natural order (= a-priori of DEC1)
   uint32_t*       E32;  // [row][32 lanes] words: a-posteriori of DEC1 minus A, in DEC2's interleaved order
                         // (each array is written scattered by its producer and read linearly by its consumer)
+  const uint32_t* R;    // CRC modes: per-bit CRC contributions of this half iteration's trellis positions,
+                        // [row][window] (lte_tables.h:crc_pos_tables), offset to this thread's window pair;
+                        // nullptr when no block of the warp checks a CRC
   uint4*          chk;  // beta checkpoints [chunk][half][32 lanes], already offset by lane
   uint4*          sm;   // chunk of beta: [(s*2 + h)*kThreads], already offset by tid
   char*           stages;  // the warp's kStages staging buffers: [sys 1 KB | par 1 KB | A or E rows 1 KB]
@@ -433,10 +436,19 @@ __device__ __forceinline__ void finish_row_exact(bool dec2, const RawRow& q, uin
 // store the differenced output of row k (see file header) where its consumer will read it linearly, and
 // remember its extremes.  DEC1 (natural position) -> E in DEC2's order: pi^-1;  DEC2 -> A in natural order: pi.
 // The QPP is contention free: all windows of row k go to ONE destination row, permuted among the windows.
-template <int W>
-__device__ __forceinline__ void store_diff(const WinCtx<W>& c, bool dec2, uint32_t k, uint32_t d, Range& rd)
+// HARD (CRC modes): the hard decisions (out = d + aux > 0) of the two windows are folded into the running CRC of
+// the block: the CRC is linear, every set bit xors in its precomputed contribution, in whatever order they come.
+template <int W, bool HARD>
+__device__ __forceinline__ void store_diff(const WinCtx<W>& c, bool dec2, uint32_t k, uint32_t d, uint32_t aux, Range& rd,
+                                           uint32_t& crc)
 {
   rd.add1(d);
+  if (HARD) {
+    // sign bit of -(max(v, -1)) is set exactly when v > 0 (no overflow: max(v,-1) >= -1)
+    const uint32_t m  = wneg2(max2(wadd2(d, aux), 0xFFFFFFFFu));
+    const uint2    rr = *reinterpret_cast<const uint2*>(c.R + k * W);
+    crc ^= (rr.x & (uint32_t)((int32_t)(m << 16) >> 31)) ^ (rr.y & (uint32_t)((int32_t)m >> 31));
+  }
   const uint32_t e   = (dec2 ? 0u : (uint32_t)kMaxL) + k;
   const uint32_t row = c.rowtab[e];
   const uint32_t wb  = c.wtab[e * 8 + c.t];
@@ -445,9 +457,13 @@ __device__ __forceinline__ void store_diff(const WinCtx<W>& c, bool dec2, uint32
   Y[wb >> 4]  = (uint16_t)(d >> 16);
 }
 template <int W>
-__device__ __forceinline__ void store_out(const WinCtx<W>& c, bool dec2, uint32_t k, uint32_t o, uint32_t aux, Range& rd)
+__device__ __forceinline__ void store_out(const WinCtx<W>& c, bool dec2, uint32_t k, uint32_t o, uint32_t aux, Range& rd,
+                                          uint32_t& crc)
 {
-  store_diff<W>(c, dec2, k, wsub2(o, aux), rd);
+  if (c.R)
+    store_diff<W, true>(c, dec2, k, wsub2(o, aux), aux, rd, crc);
+  else
+    store_diff<W, false>(c, dec2, k, wsub2(o, aux), aux, rd, crc);
 }
 
 // beta of the terminated last window from the 3 tail rows: plain (wrapping) int16 arithmetic.
@@ -475,6 +491,7 @@ struct RowState {
   uint32_t s[8];       // beta or alpha metrics
   Range    trk;        // post-normalisation extremes
   Range    rd;         // extremes of the stored outputs
+  uint32_t crc;        // running CRC of the hard decisions (CRC modes)
 };
 
 // ---- exact rows (reference arithmetic), one row at a time, shared by the exact variant and by the
@@ -522,6 +539,7 @@ __device__ __noinline__ void alpha_rows_exact(const WinCtx<W> c, bool dec2, int 
 #pragma unroll
   for (int i = 0; i < 8; i++) a[i] = st->s[i];
   Range trk = st->trk, rd = st->rd, unused;
+  uint32_t crc = st->crc;
   unused.reset();
   RawRow q;
   if (k_lo <= k_hi) issue_row<W>(c, dec2, (uint32_t)k_lo, q);
@@ -539,7 +557,7 @@ __device__ __noinline__ void alpha_rows_exact(const WinCtx<W> c, bool dec2, int 
       const uint32_t bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       uint32_t       o = alpha_out_step<false>(a, bb, x, y, sadd2(x, y), unused);
       if (W == 8) o = sra1_2(o);  // the 8-window (sse16) decoder halves its output
-      store_out<W>(c, dec2, (uint32_t)k, o, aux, rd);
+      store_out<W>(c, dec2, (uint32_t)k, o, aux, rd, crc);
     }
     if ((j & 1) == 0 && j != 0) {
       normalize<false>(a);
@@ -550,12 +568,14 @@ __device__ __noinline__ void alpha_rows_exact(const WinCtx<W> c, bool dec2, int 
   for (int i = 0; i < 8; i++) st->s[i] = a[i];
   st->trk = trk;
   st->rd  = rd;
+  st->crc = crc;
 }
 
 // what one half iteration reports back
 struct HalfResult {
   bool     proven;  // fast variant only: no saturating op of the reference can have clamped
   uint32_t dmax;    // max |stored differenced output| over this thread's rows and lanes
+  uint32_t crc;     // CRC modes: xor of the CRC contributions of this thread's set bits
 };
 
 template <int WH>
@@ -612,6 +632,7 @@ __device__ __noinline__ HalfResult half_iteration_exact(const WinCtx<W> c, bool 
   RowState al;
   al.trk.reset();
   al.rd.reset();
+  al.crc = 0;
 #pragma unroll
   for (int i = 0; i < 8; i++) al.s[i] = kNegInf2;
   alpha_rows_exact<W>(c, dec2, L - kWarm, L - 1, 0, 0, 0, &al);
@@ -629,6 +650,7 @@ __device__ __noinline__ HalfResult half_iteration_exact(const WinCtx<W> c, bool 
   HalfResult res;
   res.proven = true;
   res.dmax   = range_absmax(al.rd);
+  res.crc    = al.crc;
   return res;
 }
 
@@ -644,7 +666,8 @@ __device__ __noinline__ HalfResult half_iteration_exact(const WinCtx<W> c, bool 
 // [-10000 - 8G, 8G]: inside int16 for G <= kPureFastG; from row 3 on alpha has gone through 3 steps and a
 // normalisation and is in general position.  |out| <= 5G there too: the best bit-1 and bit-0 candidates can be
 // chosen from the same predecessor state, so they differ by at most spread(beta) + 2G.
-template <int W, bool TRACK, bool EDGE>
+// HARD (CRC modes): the forward pass also accumulates the CRC of the hard decisions (c.R).
+template <int W, bool TRACK, bool EDGE, bool HARD>
 __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bool dec2, int G, Pipe& p)
 {
   constexpr int WH = W / 2;
@@ -660,6 +683,8 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
   rb.reset(); ra.reset(); rd.reset();
   rm.hi = kMin2; rm.lo = kMax2;
   RowState st;
+  uint32_t crc = 0;
+  st.crc = 0;
   pipe_start<W>(c, dec2, p);
 
   // ---------------- backward pass ----------------
@@ -786,11 +811,13 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
       for (int i = 0; i < 8; i++) st.s[i] = a[i];
       st.trk = ra;
       st.rd  = rd;
+      st.crc = crc;
       alpha_rows_exact<W>(c, dec2, 0, kExactRows - 1, 1, lo, 0, &st);
 #pragma unroll
       for (int i = 0; i < 8; i++) a[i] = st.s[i];
-      ra = st.trk;
-      rd = st.rd;
+      ra  = st.trk;
+      rd  = st.rd;
+      crc = st.crc;
     }
 #pragma unroll 1
     for (int g = (EDGE && ch == 0) ? 1 : 0; g < 2; g++) {
@@ -805,10 +832,10 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
         const uint32_t bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         if (W == 8) {  // the 8-window (sse16) decoder halves its output before the extrinsic subtraction
           const uint32_t o = sra1_2(alpha_out_step<true, TRACK>(a, bb, q.x[r], q.y[r], wadd2(q.x[r], q.y[r]), rm));
-          store_out<W>(c, dec2, (uint32_t)(lo + g * 4 + r), o, q.aux[r], rd);
+          store_diff<W, HARD>(c, dec2, (uint32_t)(lo + g * 4 + r), wsub2(o, q.aux[r]), q.aux[r], rd, crc);
         } else {  // out - aux comes straight out of the step
           const uint32_t d = alpha_out_step<true, TRACK>(a, bb, q.x[r], q.y[r], wadd2(q.x[r], q.y[r]), rm, q.aux[r]);
-          store_diff<W>(c, dec2, (uint32_t)(lo + g * 4 + r), d, rd);
+          store_diff<W, HARD>(c, dec2, (uint32_t)(lo + g * 4 + r), d, q.aux[r], rd, crc);
         }
         if ((r & 1) == 0 && (EDGE || r != 0 || (lo | g) != 0)) {  // never after row 0
           normalize<true>(a);
@@ -822,17 +849,20 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
       for (int i = 0; i < 8; i++) st.s[i] = a[i];
       st.trk = ra;
       st.rd  = rd;
+      st.crc = crc;
       alpha_rows_exact<W>(c, dec2, max(kf + 1, lo), hi - 1, 1, lo, 0, &st);
 #pragma unroll
       for (int i = 0; i < 8; i++) a[i] = st.s[i];
-      ra = st.trk;
-      rd = st.rd;
+      ra  = st.trk;
+      rd  = st.rd;
+      crc = st.crc;
     }
   }
   __syncwarp();
 
   HalfResult res;
   res.dmax = range_absmax(rd);
+  res.crc  = crc;
   // Proof obligations, per int16 lane (see DESIGN.md "fast path"): every fast row is at most 2 steps
   // away from a normalisation point whose post-normalisation metrics lie in [lo, hi]; one step moves a
   // metric by at most G.
@@ -1059,6 +1089,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
       c.A32 = reinterpret_cast<uint32_t*>(ae);
       c.E32 = reinterpret_cast<uint32_t*>(ae + XB);
       c.chk = reinterpret_cast<uint4*>(reinterpret_cast<char*>(a.ws_chk) + (size_t)slot * kChkSlotBytes) + lane;
+      c.R   = nullptr;
       c.sm  = smem + tid;
 
       for (uint32_t k = 0; k < c.L; k++) c.A32[k * 32 + lane] = 0;
@@ -1070,8 +1101,11 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
       const uint32_t crc_mode = a.crc_mode_cb ? a.crc_mode_cb[cb] : a.crc_mode;
       const int      which    = crc_mode == CRC_24A ? 0 : 1;
       const bool     any_crc  = __any_sync(0xFFFFFFFFu, crc_mode != CRC_NONE);
+      // CRC modes: this thread's window pair in the tables of the block's polynomial ([dir][row][window])
+      const uint32_t* Rblk = any_crc ? a.crc_pos + a.crc_pos_off[wi.kidx] + (size_t)which * 2 * c.K + 2 * t : nullptr;
       do {
         const bool dec2 = (n & 1) != 0;
+        if (any_crc) c.R = Rblk + (dec2 ? c.K : 0u);
         // what the previous half iteration (or the clearing above) stored must be visible to the bulk copies
         fence_proxy_async();
         __syncwarp();
@@ -1082,13 +1116,16 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
         bool       fast_ok = false;
         // the decision must be warp-uniform: the passes below use full-warp shuffles and votes
         if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kPureFastG && (c.L & 3u) == 0)) {
-          r       = half_iteration_fast<W, false, false>(c, dec2, G, pipe);
+          r       = any_crc ? half_iteration_fast<W, false, false, true>(c, dec2, G, pipe)
+                            : half_iteration_fast<W, false, false, false>(c, dec2, G, pipe);
           fast_ok = true;
         } else if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kStaticFastG)) {
-          r       = half_iteration_fast<W, false, true>(c, dec2, G, pipe);
+          r       = any_crc ? half_iteration_fast<W, false, true, true>(c, dec2, G, pipe)
+                            : half_iteration_fast<W, false, true, false>(c, dec2, G, pipe);
           fast_ok = true;
         } else if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kMaxFastG)) {
-          r       = half_iteration_fast<W, true, true>(c, dec2, G, pipe);
+          r       = any_crc ? half_iteration_fast<W, true, true, true>(c, dec2, G, pipe)
+                            : half_iteration_fast<W, true, true, false>(c, dec2, G, pipe);
           fast_ok = __all_sync(0xFFFFFFFFu, r.proven);
         }
         if (!fast_ok) {
@@ -1099,26 +1136,24 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
         if (dec2) amax = dm; else emax = dm;
         n++;
         if (any_crc) {
+          // the block's CRC = xor of its threads' partial CRCs; a block that passes freezes its output now (the
+          // arrays of its warp slot keep changing while the other blocks of the item go on)
+          uint32_t crc = r.crc;
+#pragma unroll
+          for (int o = WH / 2; o > 0; o >>= 1) crc ^= __shfl_xor_sync(0xFFFFFFFFu, crc, o);
           const bool check = crc_mode != CRC_NONE && !done && active;
-          decide<W>(c, out, check);
-          uint32_t crc = 1;
-          if (check && t == 0) crc = crc24_bytes_dev(which, out, c.K / 8);
-          crc = __shfl_sync(0xFFFFFFFFu, crc, grp * WH);
-          if (check) {
-            iters = n;
-            if (crc == 0) {
-              ok   = true;
-              done = true;
-            }
+          const bool pass  = check && crc == 0;
+          if (check) iters = n;
+          if (__any_sync(0xFFFFFFFFu, pass)) decide<W>(c, out, pass);
+          if (pass) {
+            ok   = true;
+            done = true;
           }
         }
       } while (n < a.max_iter && !__all_sync(0xFFFFFFFFu, done || !active));
-      if (crc_mode == CRC_NONE) {
-        decide<W>(c, out, active);
-        iters = n;
-      } else if (!any_crc) {
-        iters = n;
-      }
+      // blocks that never passed (or do not check a CRC): the decision after the last half iteration
+      if (__any_sync(0xFFFFFFFFu, active && !done)) decide<W>(c, out, active && !done);
+      if (crc_mode == CRC_NONE) iters = n;
       if (active && t == 0) {
         if (a.n_iter) a.n_iter[cb] = (uint8_t)iters;
         if (a.crc_ok) a.crc_ok[cb] = ok ? 1 : 0;

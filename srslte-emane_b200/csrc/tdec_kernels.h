@@ -11,6 +11,8 @@ struct WorkItem {
   uint16_t count;   // code blocks in this item (<= blocks-per-warp of the kernel that runs it)
   uint16_t K;
   uint16_t f1, f2;  // QPP coefficients of K
+  uint16_t kidx;    // index of K in the table of the 188 code-block sizes
+  uint16_t pad;
 };
 
 enum CrcMode : uint32_t {
@@ -37,6 +39,8 @@ struct TdecLaunch {
   const uint8_t*  crc_mode_cb; // [n_cb] per-block CrcMode overriding crc_mode (device, nullable)
   int16_t*        ws_ae;       // extrinsic work arrays, sized by tdec_geometry()
   uint32_t*       ws_chk;      // beta checkpoints, sized by tdec_geometry()
+  const uint32_t* crc_pos;     // window kernels, CRC modes: per-bit CRC contributions (lte_tables.h:crc_pos_tables)
+  const uint32_t* crc_pos_off; // [188] offset of each K's tables in crc_pos (uint32 units)
   uint32_t        force_exact; // 1: always run the exact saturating variant (tests)
   uint32_t*       stats;       // device counter: half iterations (per warp) that fell back to the exact variant
 };
