@@ -769,6 +769,7 @@ static int rm_rx_enqueue(srslte_b200_ctx_t* ctx, const srslte_b200_rm_block_t* b
     ri.work_off = bl.work_offset;
     ri.tab_off  = it->second;
     ri.N        = 3 * bl.long_cb + 12;
+    ri.wl       = sb_layout ? working_len(bl.long_cb) : 3 * bl.long_cb + 12;
     ctx->h_rm_items.p[i] = ri;
   }
   if (ctx->rm_pool_uploaded != ctx->rm_pool_host.size()) {
@@ -885,6 +886,7 @@ int srslte_b200_demod_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_
     }
     RmSymItem ri;
     ri.E = bl.e_len; ri.work_off = bl.work_offset; ri.tab_off = it->second; ri.N = 3 * bl.long_cb + 12;
+    ri.wl = working_len(bl.long_cb);
     ri.cw = bl.codeword; ri.e_off = bl.e_offset;
     ctx->h_rm_sym.p[i] = ri;
   }

@@ -87,17 +87,13 @@ __global__ void rm_rx_sym_kernel(const FeCodeword* __restrict__ cws, const float
                                  const RmSymItem* __restrict__ items, const uint32_t* __restrict__ x1,
                                  const uint32_t* __restrict__ x2mask)
 {
+  extern __shared__ int16_t rm_img[];
   const RmSymItem  it  = items[blockIdx.x];
   const FeCodeword cw  = cws[it.cw];
   const float*     sym = symbols + 2 * cw.sym_off;
-  int16_t*         dst = work + it.work_off;
-  const uint16_t*  tab = tab_pool + it.tab_off;
-  for (uint32_t i = threadIdx.x; i < it.N && i < it.E; i += blockDim.x) {
-    int acc = 0;
-    for (uint32_t p = i; p < it.E; p += it.N) acc += fe_llr(cw, sym, it.e_off + p, x1, x2mask);
-    const uint32_t o = tab[i];
-    dst[o] = (int16_t)(dst[o] + acc);  // wrapping int16, like the reference's `+=`
-  }
+  const uint32_t   e0  = it.e_off;
+  rm_rx_body([&](uint32_t p) { return fe_llr(cw, sym, e0 + p, x1, x2mask); }, it.E, it.N, it.wl, tab_pool + it.tab_off,
+             work + it.work_off, rm_img);
 }
 
 }  // namespace
@@ -117,7 +113,8 @@ cudaError_t rm_rx_sym_launch(const FeCodeword* cws, const float* symbols, int16_
                              cudaStream_t s)
 {
   if (n_items == 0) return cudaSuccess;
-  rm_rx_sym_kernel<<<n_items, 256, 0, s>>>(cws, symbols, work, tab_pool, items, x1, x2mask);
+  rm_rx_sym_kernel<<<n_items, 256, (kRmMaxWorkLen + 8) * sizeof(int16_t), s>>>(cws, symbols, work, tab_pool, items, x1,
+                                                                               x2mask);
   return cudaGetLastError();
 }
 

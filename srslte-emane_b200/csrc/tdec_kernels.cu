@@ -1456,16 +1456,11 @@ __global__ void __launch_bounds__(256) to_internal_kernel(const int16_t* __restr
 __global__ void rm_rx_kernel(const int16_t* __restrict__ e, int16_t* __restrict__ work,
                              const uint16_t* __restrict__ tab_pool, const RmItem* __restrict__ items)
 {
-  const RmItem    it  = items[blockIdx.x];
-  const int16_t*  src = e + it.e_off;
-  int16_t*        dst = work + it.work_off;
-  const uint16_t* tab = tab_pool + it.tab_off;
-  for (uint32_t i = threadIdx.x; i < it.N && i < it.E; i += blockDim.x) {
-    int acc = 0;
-    for (uint32_t p = i; p < it.E; p += it.N) acc += src[p];  // wrap-around repeats hit the same cell
-    const uint32_t o = tab[i];
-    dst[o] = (int16_t)(dst[o] + acc);  // wrapping int16, like the reference's `+=`
-  }
+  extern __shared__ int16_t rm_img[];
+  const RmItem   it  = items[blockIdx.x];
+  const int16_t* src = e + it.e_off;
+  rm_rx_body([src](uint32_t p) { return (int)src[p]; }, it.E, it.N, it.wl, tab_pool + it.tab_off, work + it.work_off,
+             rm_img);
 }
 
 }  // namespace
@@ -1574,7 +1569,7 @@ cudaError_t rm_rx_launch(const int16_t* e, int16_t* work, const uint16_t* tab_po
                          uint32_t n_items, cudaStream_t s)
 {
   if (n_items == 0) return cudaSuccess;
-  rm_rx_kernel<<<n_items, 256, 0, s>>>(e, work, tab_pool, items);
+  rm_rx_kernel<<<n_items, 256, (kRmMaxWorkLen + 8) * sizeof(int16_t), s>>>(e, work, tab_pool, items);
   return cudaGetLastError();
 }
 

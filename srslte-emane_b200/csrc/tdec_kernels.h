@@ -80,7 +80,41 @@ struct RmItem {
   uint32_t work_off;  // offset of the block's working buffer (int16 elements)
   uint32_t tab_off;   // offset of its (K, rv) index table in the table pool (uint16 elements)
   uint32_t N;         // 3K+12
+  uint32_t wl;        // int16 elements of the block's working buffer that the table can address (working_len(K))
 };
+constexpr uint32_t kRmMaxWorkLen = 18600;  // SOFTBUFFER_SIZE of the reference (softbuffer.h:50) >= working_len(6144)
+
+// Shared by the two rate-dematching kernels: sum the wrap-around repeats of every rate-matched position, scatter the
+// sums into a shared-memory image of the working buffer (table order), then add the image to the working buffer
+// with coalesced 128-bit read-modify-writes (wrapping int16, like the reference's `+=`).
+template <class Src>
+__device__ __forceinline__ void rm_rx_body(const Src& src, uint32_t E, uint32_t N, uint32_t wl, const uint16_t* tab,
+                                           int16_t* dst, int16_t* img /* shared, wl rounded up to 8 */)
+{
+  const uint32_t wl8 = (wl + 7) & ~7u;
+  for (uint32_t j = threadIdx.x; j < wl8 / 2; j += blockDim.x) reinterpret_cast<uint32_t*>(img)[j] = 0;
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < N && i < E; i += blockDim.x) {
+    int acc = 0;
+    for (uint32_t p = i; p < E; p += N) acc += src(p);  // wrap-around repeats hit the same cell
+    img[tab[i]] = (int16_t)acc;                         // the table is one-to-one
+  }
+  __syncthreads();
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const uint32_t nv = wl / 8;
+    uint4*         d4 = reinterpret_cast<uint4*>(dst);
+    const uint4*   s4 = reinterpret_cast<const uint4*>(img);
+    for (uint32_t j = threadIdx.x; j < nv; j += blockDim.x) {
+      uint4       v = d4[j];
+      const uint4 a = s4[j];
+      v.x = __vadd2(v.x, a.x); v.y = __vadd2(v.y, a.y); v.z = __vadd2(v.z, a.z); v.w = __vadd2(v.w, a.w);
+      d4[j] = v;
+    }
+    for (uint32_t j = nv * 8 + threadIdx.x; j < wl; j += blockDim.x) dst[j] = (int16_t)(dst[j] + img[j]);
+  } else {
+    for (uint32_t j = threadIdx.x; j < wl; j += blockDim.x) dst[j] = (int16_t)(dst[j] + img[j]);
+  }
+}
 cudaError_t rm_rx_launch(const int16_t* e, int16_t* work, const uint16_t* tab_pool, const RmItem* items,
                          uint32_t n_items, cudaStream_t s);
 
@@ -94,7 +128,7 @@ struct FeCodeword {
   uint64_t llr_off;   // first LLR in the output (demod_descramble only)
 };
 struct RmSymItem {
-  uint32_t E, work_off, tab_off, N;  // as RmItem
+  uint32_t E, work_off, tab_off, N, wl;  // as RmItem
   uint32_t cw;                       // codeword the block belongs to
   uint32_t e_off;                    // first LLR of the block inside the codeword
 };
