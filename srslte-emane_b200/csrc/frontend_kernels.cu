@@ -20,14 +20,19 @@ namespace b200 {
 
 namespace {
 
+constexpr uint32_t kLlrPerThread = 8;
+
 __device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v)); }
 __device__ __forceinline__ int wrap16(int v) { return (int)(int16_t)v; }
 
-// LLR number j of a codeword (before rate de-matching), descrambled
+// LLR number j of a codeword (before rate de-matching), descrambled.  QM = bits per symbol, a compile-time constant:
+// the kernels branch once per CTA on the codeword's modulation (no division by a run-time Qm, no per-LLR dispatch).
+template <uint32_t QM>
 __device__ __forceinline__ int fe_llr(const FeCodeword& cw, const float* __restrict__ sym, uint32_t j,
                                       const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x2mask)
 {
-  const uint32_t qm = cw.qm, s = j / qm, r = j - s * qm, lvl = r >> 1;
+  constexpr uint32_t qm = QM;
+  const uint32_t     s = j / qm, r = j - s * qm, lvl = r >> 1;
   const float    x  = __ldg(sym + 2 * (size_t)s + (r & 1u));
   int            v;
   if (qm == 2) {
@@ -67,7 +72,8 @@ __device__ __forceinline__ int fe_llr(const FeCodeword& cw, const float* __restr
   return v;
 }
 
-// grid: (chunks of 256 LLRs, codewords)
+// grid: (chunks of 256 * kLlrPerThread LLRs, codewords): a thread amortises the codeword descriptor and pointer
+// set-up over several LLRs, consecutive threads write consecutive LLRs
 __global__ void __launch_bounds__(256) demod_descramble_kernel(const FeCodeword* __restrict__ cws,
                                                                const float* __restrict__ symbols,
                                                                int16_t* __restrict__ e, const uint32_t* __restrict__ x1,
@@ -76,9 +82,17 @@ __global__ void __launch_bounds__(256) demod_descramble_kernel(const FeCodeword*
   const FeCodeword cw = cws[blockIdx.y];
   const float*     sym = symbols + 2 * cw.sym_off;
   int16_t*         out = e + cw.llr_off;
-  const uint32_t   n = cw.qm * cw.nsym;
-  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
-    out[j] = (int16_t)fe_llr(cw, sym, j, x1, x2mask);
+  const uint32_t   n = cw.qm * cw.nsym, st = blockDim.x;
+  const uint32_t   per = blockDim.x * kLlrPerThread;
+  for (uint32_t base = blockIdx.x * per; base < n; base += gridDim.x * per) {
+    const uint32_t j0 = base + threadIdx.x, j1 = min(n, base + per);
+    switch (cw.qm) {
+      case 2: for (uint32_t j = j0; j < j1; j += st) out[j] = (int16_t)fe_llr<2>(cw, sym, j, x1, x2mask); break;
+      case 4: for (uint32_t j = j0; j < j1; j += st) out[j] = (int16_t)fe_llr<4>(cw, sym, j, x1, x2mask); break;
+      case 6: for (uint32_t j = j0; j < j1; j += st) out[j] = (int16_t)fe_llr<6>(cw, sym, j, x1, x2mask); break;
+      default: for (uint32_t j = j0; j < j1; j += st) out[j] = (int16_t)fe_llr<8>(cw, sym, j, x1, x2mask); break;
+    }
+  }
 }
 
 // rate de-matching straight from the symbols: work[tab[i]] += sum over the wrap-around repeats of LLR(e_off + p)
@@ -92,8 +106,14 @@ __global__ void rm_rx_sym_kernel(const FeCodeword* __restrict__ cws, const float
   const FeCodeword cw  = cws[it.cw];
   const float*     sym = symbols + 2 * cw.sym_off;
   const uint32_t   e0  = it.e_off;
-  rm_rx_body([&](uint32_t p) { return fe_llr(cw, sym, e0 + p, x1, x2mask); }, it.E, it.N, it.wl, tab_pool + it.tab_off,
-             work + it.work_off, rm_img);
+  const uint16_t*  tab = tab_pool + it.tab_off;
+  int16_t*         dst = work + it.work_off;
+  switch (cw.qm) {
+    case 2: rm_rx_body([&](uint32_t p) { return fe_llr<2>(cw, sym, e0 + p, x1, x2mask); }, it.E, it.N, it.wl, tab, dst, rm_img); break;
+    case 4: rm_rx_body([&](uint32_t p) { return fe_llr<4>(cw, sym, e0 + p, x1, x2mask); }, it.E, it.N, it.wl, tab, dst, rm_img); break;
+    case 6: rm_rx_body([&](uint32_t p) { return fe_llr<6>(cw, sym, e0 + p, x1, x2mask); }, it.E, it.N, it.wl, tab, dst, rm_img); break;
+    default: rm_rx_body([&](uint32_t p) { return fe_llr<8>(cw, sym, e0 + p, x1, x2mask); }, it.E, it.N, it.wl, tab, dst, rm_img); break;
+  }
 }
 
 }  // namespace
@@ -102,7 +122,7 @@ cudaError_t demod_descramble_launch(const FeCodeword* cws, uint32_t n_cw, uint32
                                     int16_t* e, const uint32_t* x1, const uint32_t* x2mask, cudaStream_t s)
 {
   if (n_cw == 0 || max_llr == 0) return cudaSuccess;
-  const uint32_t chunks = (max_llr + 255) / 256;
+  const uint32_t chunks = (max_llr + 256 * kLlrPerThread - 1) / (256 * kLlrPerThread);
   dim3           grid(chunks < 1024 ? chunks : 1024, n_cw);
   demod_descramble_kernel<<<grid, 256, 0, s>>>(cws, symbols, e, x1, x2mask);
   return cudaGetLastError();
