@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <map>
 #include <string>
 #include <vector>
@@ -114,6 +115,8 @@ struct srslte_b200_ctx {
   PinBuf<uint8_t> h_nit_all, h_crc_all;  // n_iter / crc_ok of a whole host call: the caller's arrays may be pageable,
                                          // and an async copy into pageable memory would block the enqueueing thread
   cudaEvent_t  ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  cudaEvent_t  ev_sched   = nullptr;   // last upload of the schedule staging
+  cudaEvent_t  ev_staging = nullptr;   // last copy that read the rate-dematching / front-end descriptor staging
   // rate-dematching tables
   std::map<uint32_t, uint32_t> rm_tab_off;  // key = ((K*4+rv)*2 + sb_layout) -> offset in the pool
   std::vector<uint16_t>        rm_pool_host;
@@ -310,8 +313,10 @@ int ensure_schedule(srslte_b200_ctx* ctx, const uint32_t* K, uint32_t uniform_K,
     s.round_base[r] = (uint32_t)n_rounds;
     n_rounds += s.rounds[r].size();
   }
-  // the pinned staging may still be in flight from a previous upload
-  CU(cudaStreamSynchronize(st));
+  // the pinned staging may still be in flight from the previous upload (wait for that copy only; the device
+  // arrays are overwritten in stream order, after the kernels that read them)
+  if (!ctx->ev_sched) CU(cudaEventCreateWithFlags(&ctx->ev_sched, cudaEventDisableTiming));
+  else CU(cudaEventSynchronize(ctx->ev_sched));
   CU(ctx->h_rounds.reserve(n_rounds + 1));
   CU(ctx->d_rounds.reserve(n_rounds + 1));
   for (int r = 0; r < 2; r++)
@@ -342,6 +347,7 @@ int ensure_schedule(srslte_b200_ctx* ctx, const uint32_t* K, uint32_t uniform_K,
   } else {
     ctx->sched_K.clear();
   }
+  CU(cudaEventRecord(ctx->ev_sched, st));
   ctx->sched_n         = n;
   ctx->sched_uniform_K = uniform_K;
   ctx->sched_valid     = true;
@@ -739,15 +745,25 @@ int srslte_b200_tdec_batch_host(srslte_b200_ctx_t* ctx, const srslte_b200_tdec_b
   return SRSLTE_B200_SUCCESS;
 }
 
+// the pinned descriptor staging of the rate-dematching / front-end entries is reused by the next call: wait for the
+// copy that read it last (an event), not for everything that has been queued on the stream since
+static int staging_wait(srslte_b200_ctx_t* ctx)
+{
+  if (!ctx->ev_staging) CU(cudaEventCreateWithFlags(&ctx->ev_staging, cudaEventDisableTiming));
+  else CU(cudaEventSynchronize(ctx->ev_staging));
+  return 0;
+}
+
+// overwrite (nullable): per block, 1 = the working buffer counts as all zero (fresh HARQ buffer): store, don't add
 static int rm_rx_enqueue(srslte_b200_ctx_t* ctx, const srslte_b200_rm_block_t* blocks, uint32_t n_blocks,
-                         const int16_t* e, int16_t* work, bool sb_layout)
+                         const int16_t* e, int16_t* work, bool sb_layout, const uint8_t* overwrite = nullptr)
 {
   if (!ctx) return SRSLTE_B200_ERROR_INVALID_INPUTS;
   if (n_blocks == 0) return SRSLTE_B200_SUCCESS;
   if (!blocks || !e || !work) return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "NULL argument");
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  CU(cudaStreamSynchronize(st));  // pinned staging reuse
+  if (int rc = staging_wait(ctx)) return rc;
   CU(ctx->h_rm_items.reserve(n_blocks));
   CU(ctx->d_rm_items.reserve(n_blocks));
   for (uint32_t i = 0; i < n_blocks; i++) {
@@ -770,6 +786,7 @@ static int rm_rx_enqueue(srslte_b200_ctx_t* ctx, const srslte_b200_rm_block_t* b
     ri.tab_off  = it->second;
     ri.N        = 3 * bl.long_cb + 12;
     ri.wl       = sb_layout ? working_len(bl.long_cb) : 3 * bl.long_cb + 12;
+    ri.overwrite = overwrite ? overwrite[i] : 0u;
     ctx->h_rm_items.p[i] = ri;
   }
   if (ctx->rm_pool_uploaded != ctx->rm_pool_host.size()) {
@@ -784,6 +801,7 @@ static int rm_rx_enqueue(srslte_b200_ctx_t* ctx, const srslte_b200_rm_block_t* b
     ctx->rm_pool_uploaded = ctx->rm_pool_host.size();
   }
   CU(cudaMemcpyAsync(ctx->d_rm_items.p, ctx->h_rm_items.p, n_blocks * sizeof(RmItem), cudaMemcpyHostToDevice, st));
+  CU(cudaEventRecord(ctx->ev_staging, st));
   {
     KernelTimer kt(ctx, 4, st);
     CU(rm_rx_launch(e, work, ctx->rm_pool_dev.p, ctx->d_rm_items.p, n_blocks, st));
@@ -812,7 +830,7 @@ static int fe_prepare(srslte_b200_ctx_t* ctx, const srslte_b200_codeword_t* cws,
     CU(cudaStreamSynchronize(st));  // the sources are pageable std::vector memory
     ctx->gold_ready = true;
   }
-  CU(cudaStreamSynchronize(st));  // pinned staging reuse
+  if (int rc = staging_wait(ctx)) return rc;
   CU(ctx->h_cws.reserve(n_cw));
   CU(ctx->d_cws.reserve(n_cw));
   uint32_t mx = 0;
@@ -830,6 +848,7 @@ static int fe_prepare(srslte_b200_ctx_t* ctx, const srslte_b200_codeword_t* cws,
     mx = std::max(mx, (uint32_t)n);
   }
   CU(cudaMemcpyAsync(ctx->d_cws.p, ctx->h_cws.p, n_cw * sizeof(FeCodeword), cudaMemcpyHostToDevice, st));
+  CU(cudaEventRecord(ctx->ev_staging, st));
   *max_llr = mx;
   return 0;
 }
@@ -852,9 +871,9 @@ int srslte_b200_demod_descramble_dev(srslte_b200_ctx_t* ctx, const srslte_b200_c
   return SRSLTE_B200_SUCCESS;
 }
 
-int srslte_b200_demod_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_codeword_t* cws, uint32_t n_cw,
-                                      const srslte_b200_rm_sym_block_t* blocks, uint32_t n_blocks,
-                                      const float* symbols, int16_t* work)
+static int demod_rm_rx_enqueue(srslte_b200_ctx_t* ctx, const srslte_b200_codeword_t* cws, uint32_t n_cw,
+                               const srslte_b200_rm_sym_block_t* blocks, uint32_t n_blocks, const float* symbols,
+                               int16_t* work, const uint8_t* overwrite)
 {
   if (!ctx) return SRSLTE_B200_ERROR_INVALID_INPUTS;
   if (n_blocks == 0) return SRSLTE_B200_SUCCESS;
@@ -887,6 +906,7 @@ int srslte_b200_demod_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_
     RmSymItem ri;
     ri.E = bl.e_len; ri.work_off = bl.work_offset; ri.tab_off = it->second; ri.N = 3 * bl.long_cb + 12;
     ri.wl = working_len(bl.long_cb);
+    ri.overwrite = overwrite ? overwrite[i] : 0u;
     ri.cw = bl.codeword; ri.e_off = bl.e_offset;
     ctx->h_rm_sym.p[i] = ri;
   }
@@ -901,6 +921,7 @@ int srslte_b200_demod_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_
     ctx->rm_pool_uploaded = ctx->rm_pool_host.size();
   }
   CU(cudaMemcpyAsync(ctx->d_rm_sym.p, ctx->h_rm_sym.p, n_blocks * sizeof(RmSymItem), cudaMemcpyHostToDevice, st));
+  CU(cudaEventRecord(ctx->ev_staging, st));
   {
     KernelTimer kt(ctx, 4, st);
     CU(rm_rx_sym_launch(ctx->d_cws.p, symbols, work, ctx->rm_pool_dev.p, ctx->d_rm_sym.p, n_blocks, ctx->gold_x1.p,
@@ -908,6 +929,13 @@ int srslte_b200_demod_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_
   }
   ctx->launches++;
   return SRSLTE_B200_SUCCESS;
+}
+
+int srslte_b200_demod_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_codeword_t* cws, uint32_t n_cw,
+                                      const srslte_b200_rm_sym_block_t* blocks, uint32_t n_blocks,
+                                      const float* symbols, int16_t* work)
+{
+  return demod_rm_rx_enqueue(ctx, cws, n_cw, blocks, n_blocks, symbols, work, nullptr);
 }
 
 }  // extern "C"
@@ -921,6 +949,8 @@ struct srslte_b200_harq_pool {
   static constexpr uint32_t kStride = 18624;  // int16 per code block (>= SOFTBUFFER_SIZE 18600, multiple of 64)
   DevBuf<int16_t>      llr;                   // [n_sb][max_cb][kStride]
   std::vector<uint8_t> cb_crc;                // [n_sb][max_cb]
+  std::vector<uint8_t> fresh;                 // [n_sb][max_cb] 1 = reset since the last rate de-matching into the block:
+                                              // its LLR buffer counts as all zero (the kernel stores instead of adding)
   std::vector<uint8_t> tb_crc;                // [n_sb]
   std::vector<uint8_t> saved;                 // [n_sb][max_cb][768] payloads of good blocks of a failed TB
   // staging of the batch entry
@@ -958,6 +988,7 @@ int srslte_b200_harq_pool_create(srslte_b200_ctx_t* ctx, uint32_t n_softbuffers,
     return fail(ctx, SRSLTE_B200_ERROR, "HARQ pool allocation failed: %s", cudaGetErrorString(e));
   }
   p->cb_crc.assign(n, 0);
+  p->fresh.assign(n, 0);  // the allocation is zeroed for real
   p->tb_crc.assign(n_softbuffers, 0);
   p->saved.assign(n * 768, 0);
   *pool = p;
@@ -991,8 +1022,8 @@ int srslte_b200_harq_reset(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* p, u
 {
   if (!ctx || !p || softbuffer >= p->n_sb) return SRSLTE_B200_ERROR_INVALID_INPUTS;
   CU(cudaSetDevice(ctx->device));
-  const size_t per = (size_t)p->max_cb * srslte_b200_harq_pool::kStride;
-  CU(cudaMemsetAsync(p->llr.p + softbuffer * per, 0, per * sizeof(int16_t), ctx->stream));
+  // no memset: the next rate de-matching into each block of this soft buffer overwrites instead of accumulating
+  std::fill(p->fresh.begin() + (size_t)softbuffer * p->max_cb, p->fresh.begin() + (size_t)(softbuffer + 1) * p->max_cb, 1);
   std::fill(p->cb_crc.begin() + (size_t)softbuffer * p->max_cb, p->cb_crc.begin() + (size_t)(softbuffer + 1) * p->max_cb, 0);
   std::fill(p->saved.begin() + (size_t)softbuffer * p->max_cb * 768, p->saved.begin() + (size_t)(softbuffer + 1) * p->max_cb * 768, 0);
   p->tb_crc[softbuffer] = 0;
@@ -1027,6 +1058,16 @@ static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
   cudaStream_t st = ctx->stream;
   constexpr uint32_t kStride = srslte_b200_harq_pool::kStride;
 
+  static const bool tb_trace = getenv("SRSLTE_B200_TRACE") != nullptr;  // development probe: host phase times
+  auto              now = [] { return std::chrono::steady_clock::now(); };
+  auto              t_start = now();
+  std::vector<std::pair<const char*, double>> phases;
+  auto lap = [&](const char* name) {
+    if (!tb_trace) return;
+    const auto t1 = now();
+    phases.emplace_back(name, std::chrono::duration<double, std::milli>(t1 - t_start).count());
+    t_start = t1;
+  };
   // ---- plan: segmentation, per-block rate-matching sizes (sch.c:315-334), blocks to skip ----
   std::vector<CbSegm>   seg(n_tb);
   std::vector<uint8_t>  run(n_tb, 0);
@@ -1078,6 +1119,7 @@ static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
     }
   }
 
+  lap("plan");
   const uint32_t n_cb = (uint32_t)jobs.size();
   std::vector<uint32_t> noi(n_cb, 0);
   if (n_cb) {
@@ -1096,9 +1138,11 @@ static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
         std::memcpy(pool->h_e.p + e_base[i], tbs[i].e_bits, (size_t)tbs[i].nof_e_bits * sizeof(int16_t));
     }
     CU(cudaMemcpyAsync(pool->d_e.p, pool->h_e.p, e_units * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    lap("stage + H2D enqueue");
 
     // ---- rate de-matching with HARQ combining, in place in the pool ----
     std::vector<srslte_b200_rm_block_t> rm(n_cb);
+    std::vector<uint8_t>                over(n_cb, 0);
     CU(pool->h_off.reserve(n_cb));
     CU(pool->d_off.reserve(n_cb));
     CU(pool->h_mode.reserve(n_cb));
@@ -1114,11 +1158,14 @@ static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
       rm[j].e_len       = jb.E;
       rm[j].work_offset = (uint32_t)off;
       pool->h_off.p[j]  = off;
+      uint8_t& fr = pool->fresh[(size_t)tbs[jb.tb].softbuffer * pool->max_cb + jb.cb];
+      over[j] = fr;
+      fr      = 0;
       pool->h_mode.p[j] = seg[jb.tb].C > 1 ? (uint8_t)CRC_24B : (uint8_t)CRC_24A;
     }
     int rc;
     if (!sym) {
-      rc = srslte_b200_rm_rx_batch_dev(ctx, rm.data(), n_cb, pool->d_e.p, pool->llr.p);
+      rc = rm_rx_enqueue(ctx, rm.data(), n_cb, pool->d_e.p, pool->llr.p, true, over.data());
     } else {  // demodulate + descramble + rate de-match in one kernel: the e array never exists
       std::vector<srslte_b200_codeword_t>     cws;
       std::vector<uint32_t>                   cw_of(n_tb, 0);
@@ -1135,10 +1182,11 @@ static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
         bl[j].long_cb = rm[j].long_cb; bl[j].rv = rm[j].rv; bl[j].codeword = cw_of[jobs[j].tb];
         bl[j].e_offset = jobs[j].rp; bl[j].e_len = rm[j].e_len; bl[j].work_offset = rm[j].work_offset;
       }
-      rc = srslte_b200_demod_rm_rx_batch_dev(ctx, cws.data(), (uint32_t)cws.size(), bl.data(), n_cb,
-                                             reinterpret_cast<const float*>(pool->d_e.p), pool->llr.p);
+      rc = demod_rm_rx_enqueue(ctx, cws.data(), (uint32_t)cws.size(), bl.data(), n_cb,
+                               reinterpret_cast<const float*>(pool->d_e.p), pool->llr.p, over.data());
     }
     if (rc) return rc;
+    lap("rate-dematch enqueue");
 
     // ---- decode all blocks of all TBs in one batch, CRC after every half iteration ----
     CU(cudaMemcpyAsync(pool->d_off.p, pool->h_off.p, n_cb * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
@@ -1166,7 +1214,9 @@ static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
     CU(cudaMemcpyAsync(pool->h_out.p, pool->d_out.p, (size_t)n_cb * 768, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(pool->h_nit.p, pool->d_nit.p, n_cb, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(pool->h_ok.p, pool->d_ok.p, n_cb, cudaMemcpyDeviceToHost, st));
+    lap("decode enqueue");
     CU(cudaStreamSynchronize(st));
+    lap("wait for the GPU");
 
     // ---- code blocks -> transport blocks.  Like the reference, every block writes its full K/8 bytes at
     // cb*rlen/8, so a block's CRC bytes are overwritten by the next block and the last block's survive. ----
@@ -1180,6 +1230,7 @@ static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
     }
   }
 
+  lap("blocks -> TBs");
   // ---- per-TB bookkeeping (sch.c:391-412, 470-488) ----
   std::vector<float> total_it(n_tb, 0.f);
   for (uint32_t j = 0; j < n_cb; j++) total_it[jobs[j].tb] += (float)noi[j];
@@ -1207,6 +1258,16 @@ static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
     const uint32_t par_tx = ((uint32_t)t.data[t.tbs / 8] << 16) | ((uint32_t)t.data[t.tbs / 8 + 1] << 8) |
                             (uint32_t)t.data[t.tbs / 8 + 2];
     t.ret = (par_rx == par_tx && par_rx) ? SRSLTE_B200_SUCCESS : SRSLTE_B200_ERROR;  // `&& par_rx`: sch.c:481
+  }
+  lap("TB CRC + bookkeeping");
+  if (tb_trace) {
+    std::string s;
+    char        buf[96];
+    for (auto& ph : phases) {
+      snprintf(buf, sizeof(buf), " %s %.3f ms;", ph.first, ph.second);
+      s += buf;
+    }
+    fprintf(stderr, "decode_tb (%u TBs, %u blocks):%s\n", n_tb, n_cb, s.c_str());
   }
   return SRSLTE_B200_SUCCESS;
 }

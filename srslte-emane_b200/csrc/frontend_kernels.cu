@@ -109,10 +109,10 @@ __global__ void rm_rx_sym_kernel(const FeCodeword* __restrict__ cws, const float
   const uint16_t*  tab = tab_pool + it.tab_off;
   int16_t*         dst = work + it.work_off;
   switch (cw.qm) {
-    case 2: rm_rx_body([&](uint32_t p) { return fe_llr<2>(cw, sym, e0 + p, x1, x2mask); }, it.E, it.N, it.wl, tab, dst, rm_img); break;
-    case 4: rm_rx_body([&](uint32_t p) { return fe_llr<4>(cw, sym, e0 + p, x1, x2mask); }, it.E, it.N, it.wl, tab, dst, rm_img); break;
-    case 6: rm_rx_body([&](uint32_t p) { return fe_llr<6>(cw, sym, e0 + p, x1, x2mask); }, it.E, it.N, it.wl, tab, dst, rm_img); break;
-    default: rm_rx_body([&](uint32_t p) { return fe_llr<8>(cw, sym, e0 + p, x1, x2mask); }, it.E, it.N, it.wl, tab, dst, rm_img); break;
+    case 2: rm_rx_body([&](uint32_t p) { return fe_llr<2>(cw, sym, e0 + p, x1, x2mask); }, it.E, it.N, it.wl, tab, dst, rm_img, it.overwrite != 0); break;
+    case 4: rm_rx_body([&](uint32_t p) { return fe_llr<4>(cw, sym, e0 + p, x1, x2mask); }, it.E, it.N, it.wl, tab, dst, rm_img, it.overwrite != 0); break;
+    case 6: rm_rx_body([&](uint32_t p) { return fe_llr<6>(cw, sym, e0 + p, x1, x2mask); }, it.E, it.N, it.wl, tab, dst, rm_img, it.overwrite != 0); break;
+    default: rm_rx_body([&](uint32_t p) { return fe_llr<8>(cw, sym, e0 + p, x1, x2mask); }, it.E, it.N, it.wl, tab, dst, rm_img, it.overwrite != 0); break;
   }
 }
 

@@ -1460,7 +1460,7 @@ __global__ void rm_rx_kernel(const int16_t* __restrict__ e, int16_t* __restrict_
   const RmItem   it  = items[blockIdx.x];
   const int16_t* src = e + it.e_off;
   rm_rx_body([src](uint32_t p) { return (int)src[p]; }, it.E, it.N, it.wl, tab_pool + it.tab_off, work + it.work_off,
-             rm_img);
+             rm_img, it.overwrite != 0);
 }
 
 }  // namespace

@@ -81,6 +81,7 @@ struct RmItem {
   uint32_t tab_off;   // offset of its (K, rv) index table in the table pool (uint16 elements)
   uint32_t N;         // 3K+12
   uint32_t wl;        // int16 elements of the block's working buffer that the table can address (working_len(K))
+  uint32_t overwrite; // 1: the working buffer is logically all zero (fresh HARQ buffer): store instead of add
 };
 constexpr uint32_t kRmMaxWorkLen = 18600;  // SOFTBUFFER_SIZE of the reference (softbuffer.h:50) >= working_len(6144)
 
@@ -89,7 +90,7 @@ constexpr uint32_t kRmMaxWorkLen = 18600;  // SOFTBUFFER_SIZE of the reference (
 // with coalesced 128-bit read-modify-writes (wrapping int16, like the reference's `+=`).
 template <class Src>
 __device__ __forceinline__ void rm_rx_body(const Src& src, uint32_t E, uint32_t N, uint32_t wl, const uint16_t* tab,
-                                           int16_t* dst, int16_t* img /* shared, wl rounded up to 8 */)
+                                           int16_t* dst, int16_t* img /* shared, wl rounded up to 8 */, bool overwrite)
 {
   const uint32_t wl8 = (wl + 7) & ~7u;
   for (uint32_t j = threadIdx.x; j < wl8 / 2; j += blockDim.x) reinterpret_cast<uint32_t*>(img)[j] = 0;
@@ -105,14 +106,19 @@ __device__ __forceinline__ void rm_rx_body(const Src& src, uint32_t E, uint32_t 
     uint4*         d4 = reinterpret_cast<uint4*>(dst);
     const uint4*   s4 = reinterpret_cast<const uint4*>(img);
     for (uint32_t j = threadIdx.x; j < nv; j += blockDim.x) {
-      uint4       v = d4[j];
       const uint4 a = s4[j];
-      v.x = __vadd2(v.x, a.x); v.y = __vadd2(v.y, a.y); v.z = __vadd2(v.z, a.z); v.w = __vadd2(v.w, a.w);
-      d4[j] = v;
+      if (overwrite) {
+        d4[j] = a;
+      } else {
+        uint4 v = d4[j];
+        v.x = __vadd2(v.x, a.x); v.y = __vadd2(v.y, a.y); v.z = __vadd2(v.z, a.z); v.w = __vadd2(v.w, a.w);
+        d4[j] = v;
+      }
     }
-    for (uint32_t j = nv * 8 + threadIdx.x; j < wl; j += blockDim.x) dst[j] = (int16_t)(dst[j] + img[j]);
+    for (uint32_t j = nv * 8 + threadIdx.x; j < wl; j += blockDim.x)
+      dst[j] = overwrite ? img[j] : (int16_t)(dst[j] + img[j]);
   } else {
-    for (uint32_t j = threadIdx.x; j < wl; j += blockDim.x) dst[j] = (int16_t)(dst[j] + img[j]);
+    for (uint32_t j = threadIdx.x; j < wl; j += blockDim.x) dst[j] = overwrite ? img[j] : (int16_t)(dst[j] + img[j]);
   }
 }
 cudaError_t rm_rx_launch(const int16_t* e, int16_t* work, const uint16_t* tab_pool, const RmItem* items,
@@ -128,7 +134,7 @@ struct FeCodeword {
   uint64_t llr_off;   // first LLR in the output (demod_descramble only)
 };
 struct RmSymItem {
-  uint32_t E, work_off, tab_off, N, wl;  // as RmItem
+  uint32_t E, work_off, tab_off, N, wl, overwrite;  // as RmItem
   uint32_t cw;                       // codeword the block belongs to
   uint32_t e_off;                    // first LLR of the block inside the codeword
 };

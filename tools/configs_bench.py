@@ -123,3 +123,84 @@ rmb = [(5824, 0, b[2] * 90000 + b[3], b[4], b[5]) for b in blocks]
 ms2 = ktimed(lambda: (ctx.demod_descramble_dev(cws, sym.data_ptr(), e2.data_ptr()),
                       ctx.rm_rx_batch_dev(rmb, e2.data_ptr(), work.data_ptr())))
 print(f"front end unfused (demod kernel + rm kernel through the e array): {ms2:.3f} ms kernel time")
+
+# ---- config 5: 200 UL transport blocks per 1 ms subframe (16QAM, mixed sizes), host LLRs in, TB bytes out ----------
+import ctypes as C
+rng5 = np.random.default_rng(5)
+sizes5 = [(2216, 4, 4800), (6200, 4, 9600), (14112, 4, 28800), (4584, 4, 7200), (3624, 4, 5760), (9144, 4, 14400),
+          (1000, 4, 2400), (20616, 4, 36000)]
+tbs5 = []
+for i in range(200):
+    tbs, qm, G = sizes5[i % len(sizes5)]
+    payload = rng5.integers(0, 2, tbs, dtype=np.uint8)
+    tb = vec.attach_crc(vec.CRC24A, payload[None, :])[0]
+    # segmentation (36.212 5.1.2) through the library's own table helper
+    from math import ceil
+    B = tbs + 24
+    Cn = 1 if B <= 6144 else ceil(B / (6144 - 24))
+    Bp = B if Cn == 1 else B + Cn * 24
+    Kp = next(k for k in vec.ALL_K if Cn * k >= Bp)
+    assert Cn * Kp == Bp, "sizes chosen without filler bits"
+    e_parts, pos = [], 0
+    Gp, gamma = G // qm, (G // qm) % Cn
+    for cb in range(Cn):
+        rlen = Kp if Cn == 1 else Kp - 24
+        blk = tb[pos:pos + rlen]; pos += rlen
+        if Cn > 1:
+            blk = vec.attach_crc(vec.CRC24B, blk[None, :])[0]
+        E = qm * (Gp // Cn) if cb <= Cn - gamma - 1 else qm * ((Gp + Cn - 1) // Cn)
+        e_parts.append(vec.rate_match(vec.turbo_encode(blk[None, :]), E, 0)[0])
+    e5 = np.concatenate(e_parts)
+    tbs5.append(dict(tbs=tbs, qm=qm, rv=0, e_bits=vec.awgn_llr(e5, 0.35, 400, rng5), softbuffer=i))
+import threading
+
+
+def subframe_rate(n_threads, seconds=1.5):
+    """Sustained subframes/s through the raw C ABI: every thread owns a context, a HARQ pool and its descriptors and
+    per subframe resets its 200 HARQ buffers and decodes its 200 TBs (ctypes releases the GIL during the calls)."""
+    Lc = pkg.lib()
+    workers = []
+    for _ in range(n_threads):
+        cx = pkg.Context(0)
+        pl = cx.harq_pool(200, 13)
+        arr = (pkg.TbDesc * 200)()
+        keep = []
+        for i, d in enumerate(tbs5):
+            e = np.ascontiguousarray(d["e_bits"], dtype=np.int16)
+            out = np.zeros(d["tbs"] // 8 + 8, np.uint8)
+            keep += [e, out]
+            arr[i] = pkg.TbDesc(d["tbs"], d["qm"], d["rv"], e.shape[0], d["softbuffer"], e.ctypes.data, out.ctypes.data, 0, 0.0)
+        workers.append((cx, pl, arr, keep))
+    counts = [0] * n_threads
+    stop = [False]
+
+    def loop(w):
+        cx, pl, arr, _ = workers[w]
+        while not stop[0]:
+            for i in range(200):
+                Lc.srslte_b200_harq_reset(cx._h, pl._p, i)
+            rc = Lc.srslte_b200_decode_tb_batch(cx._h, pl._p, arr, 200, 10)
+            assert rc == 0 and all(arr[i].ret == 0 for i in range(0, 200, 37))
+            counts[w] += 1
+    for w in range(n_threads):          # warm-up
+        cx, pl, arr, _ = workers[w]
+        for i in range(200): Lc.srslte_b200_harq_reset(cx._h, pl._p, i)
+        Lc.srslte_b200_decode_tb_batch(cx._h, pl._p, arr, 200, 10)
+    ths = [threading.Thread(target=loop, args=(w,)) for w in range(n_threads)]
+    t0 = time.perf_counter()
+    for th in ths: th.start()
+    time.sleep(seconds)
+    stop[0] = True
+    for th in ths: th.join()
+    dt = time.perf_counter() - t0
+    for cx, pl, _, _ in workers:
+        pl.close()
+    return sum(counts) / dt
+
+
+bits5 = sum(d["tbs"] for d in tbs5)
+for nt in (1, 2, 3):
+    r = subframe_rate(nt)
+    print(f"config5: 200 TBs (16QAM, {bits5} payload bits, {sum(len(d['e_bits']) for d in tbs5)} LLRs) per subframe, host LLRs in, "
+          f"TB bytes out, 200 HARQ resets per subframe, {nt} caller thread(s) on one GPU: {r:.0f} subframes/s "
+          f"({bits5 * r / 1e9:.2f} Gbit/s payload)")
