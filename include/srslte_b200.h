@@ -150,6 +150,11 @@ typedef struct {
   uint32_t nof_bits;    /* LLRs that are descrambled: grant.tb[].nof_bits, <= qm * nof_symbols, <= 262144          */
   uint64_t sym_offset;  /* first symbol of the codeword in `symbols` (complex floats: re, im)                       */
   uint64_t llr_offset;  /* first LLR of the codeword in `e` (int16); unused by the fused entry                      */
+  uint32_t ul_nof_symb; /* 0: PDSCH.  PUSCH: cfg->grant.nof_symb (N_pusch_symbs): the outputs are additionally put in
+                         * UL-SCH order by the channel de-interleaver of 36.212 5.2.2.8 (ulsch_deinterleave,
+                         * sch.c:891-918) -- data only: no RI / ACK / CQI multiplexed; nof_bits must be
+                         * qm * nof_symbols and a multiple of qm * ul_nof_symb                                       */
+  uint32_t reserved;    /* 0 */
 } srslte_b200_codeword_t;
 
 /* e[cw.llr_offset + j] = descrambled LLR j of codeword cw, j < qm * nof_symbols.  symbols, e: device memory. */
@@ -213,6 +218,7 @@ typedef struct {
   uint32_t     softbuffer;
   uint32_t     nof_symbols;    /* grant.nof_re                                                        */
   uint32_t     c_init;         /* scrambling seed of (rnti, codeword, subframe, cell)                 */
+  uint32_t     ul_nof_symb;    /* 0 for PDSCH; PUSCH: N_pusch_symbs (UL-SCH de-interleaver, no UCI)     */
   const float* symbols;        /* host: nof_symbols complex floats (re, im)                           */
   uint8_t*     data;           /* host: decoded TB, at least tbs/8 + 6 bytes                          */
   int32_t      ret;            /* out: as srslte_b200_tb_t                                            */

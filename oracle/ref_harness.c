@@ -275,3 +275,21 @@ int refh_demod_descramble(int mod, const float* sym, uint32_t nsym, uint32_t c_i
   free(l);
   return rc;
 }
+
+/* the reference's UL-SCH channel de-interleaver (sch.c:891-918; not static) with no RI bits */
+void ulsch_deinterleave(int16_t* q_bits, uint32_t Qm, uint32_t H_prime_total, uint32_t N_pusch_symbs, int16_t* g_bits,
+                        srslte_uci_bit_t* ri_bits, uint32_t nof_ri_bits, uint8_t* ri_present, uint32_t* inteleaver_lut);
+int refh_ulsch_deinterleave(const int16_t* q, uint32_t Qm, uint32_t H_prime_total, uint32_t N_pusch_symbs, int16_t* g)
+{
+  const uint32_t n = H_prime_total * Qm;
+  int16_t*  qq  = malloc(sizeof(int16_t) * (n + 8));
+  uint8_t*  pre = calloc(n + 8, 1);
+  uint32_t* lut = calloc(n + 8, sizeof(uint32_t));
+  if (!qq || !pre || !lut) return -1;
+  memcpy(qq, q, sizeof(int16_t) * n);
+  ulsch_deinterleave(qq, Qm, H_prime_total, N_pusch_symbs, g, NULL, 0, pre, lut);
+  free(qq);
+  free(pre);
+  free(lut);
+  return 0;
+}

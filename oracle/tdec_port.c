@@ -993,3 +993,15 @@ int port_demod_descramble(int qm, const float* sym, uint32_t nsym, uint32_t c_in
   free(c);
   return 0;
 }
+
+/* UL-SCH channel de-interleaver of 36.212 5.2.2.8 without multiplexed UCI (no RI / ACK / CQI):
+ * reference ulsch_deinterleave + ulsch_interleave_gen, lib/src/phy/phch/sch.c:580-598, 891-918:
+ * lut[(i*rows + j)*Qm + k] = (j*cols + i)*Qm + k,  g[lut[x]] = q[x].                                         */
+void port_ulsch_deinterleave(const int16_t* q, uint32_t Qm, uint32_t H_prime_total, uint32_t N_pusch_symbs, int16_t* g)
+{
+  const uint32_t rows = H_prime_total / N_pusch_symbs, cols = N_pusch_symbs;
+  uint32_t idx = 0;
+  for (uint32_t j = 0; j < rows; j++)
+    for (uint32_t i = 0; i < cols; i++)
+      for (uint32_t k = 0; k < Qm; k++) g[idx++] = q[j * Qm + i * rows * Qm + k];
+}

@@ -36,7 +36,8 @@ class RmBlock(C.Structure):
 
 class Codeword(C.Structure):
     _fields_ = [("qm", C.c_uint32), ("nof_symbols", C.c_uint32), ("c_init", C.c_uint32), ("nof_bits", C.c_uint32),
-                ("sym_offset", C.c_uint64), ("llr_offset", C.c_uint64)]
+                ("sym_offset", C.c_uint64), ("llr_offset", C.c_uint64), ("ul_nof_symb", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 class RmSymBlock(C.Structure):
@@ -53,7 +54,7 @@ class TbDesc(C.Structure):
 class TbSymDesc(C.Structure):
     _fields_ = [("tbs", C.c_uint32), ("qm", C.c_uint32), ("rv", C.c_uint32), ("nof_e_bits", C.c_uint32),
                 ("softbuffer", C.c_uint32), ("nof_symbols", C.c_uint32), ("c_init", C.c_uint32),
-                ("symbols", C.c_void_p), ("data", C.c_void_p), ("ret", C.c_int32), ("avg_iterations", C.c_float)]
+                ("ul_nof_symb", C.c_uint32), ("symbols", C.c_void_p), ("data", C.c_void_p), ("ret", C.c_int32), ("avg_iterations", C.c_float)]
 
 
 EXPORTS = [
@@ -295,7 +296,7 @@ class Context:
             keep.append(sym)
             outs.append(out)
             arr[i] = TbSymDesc(d["tbs"], d["qm"], d["rv"], d["nof_e_bits"], d["softbuffer"], sym.shape[0], d["c_init"],
-                               sym.ctypes.data, out.ctypes.data, 0, 0.0)
+                               d.get("ul_nof_symb", 0), sym.ctypes.data, out.ctypes.data, 0, 0.0)
         rc = self._L.srslte_b200_decode_tb_sym_batch(self._h, pool._p, arr, n, max_iterations)
         self._check(rc, "srslte_b200_decode_tb_sym_batch")
         return [(int(arr[i].ret), outs[i], float(arr[i].avg_iterations)) for i in range(n)]
@@ -315,7 +316,7 @@ class Context:
         arr = (Codeword * len(cws))()
         for i, c in enumerate(cws):
             arr[i] = Codeword(c["qm"], c["nof_symbols"], c["c_init"], c.get("nof_bits", c["qm"] * c["nof_symbols"]),
-                              c.get("sym_offset", 0), c.get("llr_offset", 0))
+                              c.get("sym_offset", 0), c.get("llr_offset", 0), c.get("ul_nof_symb", 0), 0)
         return arr
 
     def demod_descramble_dev(self, cws, symbols_ptr, e_ptr):

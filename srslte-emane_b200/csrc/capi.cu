@@ -844,6 +844,14 @@ static int fe_prepare(srslte_b200_ctx_t* ctx, const srslte_b200_codeword_t* cws,
     FeCodeword f;
     f.qm = c.qm; f.nsym = c.nof_symbols; f.c_init = c.c_init; f.nof_bits = c.nof_bits;
     f.sym_off = c.sym_offset; f.llr_off = c.llr_offset;
+    f.ul_cols = c.ul_nof_symb;
+    f.ul_rows = 0;
+    if (c.ul_nof_symb) {
+      if (c.nof_bits != n || c.nof_bits % (c.qm * c.ul_nof_symb))
+        return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS,
+                    "codeword %u: UL-SCH de-interleaving needs nof_bits = qm * nof_symbols, a multiple of qm * ul_nof_symb", i);
+      f.ul_rows = c.nof_bits / c.qm / c.ul_nof_symb;
+    }
     ctx->h_cws.p[i] = f;
     mx = std::max(mx, (uint32_t)n);
   }
@@ -1042,7 +1050,7 @@ int srslte_b200_harq_cb_crc(srslte_b200_harq_pool_t* p, uint32_t softbuffer, uin
 namespace {
 struct TbSymSrc {  // where a transport block's LLRs come from when the caller hands over equalised symbols
   const float* symbols;  // host: nof_symbols complex floats
-  uint32_t     nof_symbols, mod_bits, c_init;
+  uint32_t     nof_symbols, mod_bits, c_init, ul_nof_symb;
 };
 }  // namespace
 
@@ -1175,6 +1183,7 @@ static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
         srslte_b200_codeword_t c{};
         c.qm = sym[i].mod_bits; c.nof_symbols = sym[i].nof_symbols; c.c_init = sym[i].c_init;
         c.nof_bits = tbs[i].nof_e_bits; c.sym_offset = e_base[i]; c.llr_offset = 0;
+        c.ul_nof_symb = sym[i].ul_nof_symb;
         cw_of[i] = (uint32_t)cws.size();
         cws.push_back(c);
       }
@@ -1294,6 +1303,7 @@ int srslte_b200_decode_tb_sym_batch(srslte_b200_ctx_t* ctx, srslte_b200_harq_poo
     tb[i].softbuffer = tbs[i].softbuffer; tb[i].e_bits = nullptr; tb[i].data = tbs[i].data;
     src[i].symbols = tbs[i].symbols; src[i].nof_symbols = tbs[i].nof_symbols; src[i].mod_bits = tbs[i].qm;
     src[i].c_init = tbs[i].c_init;
+    src[i].ul_nof_symb = tbs[i].ul_nof_symb;
   }
   const int rc = decode_tb_core(ctx, pool, tb.data(), n_tb, max_iterations, src.data());
   for (uint32_t i = 0; i < n_tb; i++) {

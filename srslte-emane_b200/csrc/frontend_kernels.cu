@@ -11,6 +11,8 @@
 //       64QAM  :240-302  the same with -700 and offsets 432 / 216; remainder :290-300
 //       256QAM :457-477  scalar float chain, truncation
 //   srslte_scrambling_s_offset       lib/src/phy/scrambling/scrambling.c:44-47 (sign flip where c(n) = 1)
+//   ulsch_deinterleave (no UCI)      lib/src/phy/phch/sch.c:580-598, 891-918: g[(j*cols + i)*Qm + k] = q[(i*rows + j)*Qm + k];
+//       applied as an index map in front of the LLR computation, so the permuted array never exists
 //   the scrambling sequence c(n)     lib/src/phy/common/sequence.c:46-75 (36.211 7.2, Nc = 1600); here
 //       c(n) = x1(n + 1600) xor parity(mask[n] & c_init): x2 is linear in its seed, so one table of 31-bit masks
 //       (lte_tables.cpp:gold_tables) serves every seed and every LLR is computed independently.
@@ -32,6 +34,11 @@ __device__ __forceinline__ int fe_llr(const FeCodeword& cw, const float* __restr
                                       const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x2mask)
 {
   constexpr uint32_t qm = QM;
+  if (cw.ul_cols) {  // j counts in UL-SCH order: vector v = j / qm sits at row v / cols, column v % cols of the
+                     // interleaver matrix and was sent as vector column * rows + row
+    const uint32_t v = j / qm, k = j - v * qm, row = v / cw.ul_cols, col = v - row * cw.ul_cols;
+    j = (col * cw.ul_rows + row) * qm + k;
+  }
   const uint32_t     s = j / qm, r = j - s * qm, lvl = r >> 1;
   const float    x  = __ldg(sym + 2 * (size_t)s + (r & 1u));
   int            v;

@@ -132,6 +132,9 @@ struct FeCodeword {
   uint32_t nof_bits;  // LLRs that are descrambled (<= qm * nsym)
   uint64_t sym_off;   // first symbol in the symbol buffer (complex floats)
   uint64_t llr_off;   // first LLR in the output (demod_descramble only)
+  uint32_t ul_cols;   // 0: the LLRs are used in channel order (PDSCH); else N_pusch_symbs: the UL-SCH channel
+                      // de-interleaver of 36.212 5.2.2.8 (no UCI) sits between descrambling and rate de-matching
+  uint32_t ul_rows;   // nof_bits / qm / ul_cols
 };
 struct RmSymItem {
   uint32_t E, work_off, tab_off, N, wl, overwrite;  // as RmItem

@@ -94,6 +94,8 @@ def port():
     L.port_demod_s.argtypes = [C.c_int, _f32p, _i16p, C.c_uint32]
     L.port_descramble_s.argtypes = [_i16p, _u8p, C.c_uint32]
     L.port_demod_descramble.argtypes = [C.c_int, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _i16p]
+    L.port_ulsch_deinterleave.argtypes = [_i16p, C.c_uint32, C.c_uint32, C.c_uint32, _i16p]
+    L.port_ulsch_deinterleave.restype = None
     _port = L
     return L
 
@@ -134,6 +136,7 @@ def ref():
     L.srslte_tdec_autoimp_get_subblocks.argtypes = [C.c_uint32]
     L.srslte_tdec_autoimp_get_subblocks.restype = C.c_uint32
     L.refh_demod_descramble.argtypes = [C.c_int, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _i16p, C.c_uint32]
+    L.refh_ulsch_deinterleave.argtypes = [_i16p, C.c_uint32, C.c_uint32, C.c_uint32, _i16p]
     L.srslte_rm_turbo_gentables()
     _ref = L
     return L
@@ -225,3 +228,18 @@ def ref_demod_descramble(qm, sym, c_init, nof_bits=None):
     rc = ref().refh_demod_descramble(REF_MOD[qm], sym.view(np.float32), n, c_init, nb, llr, qm * n)
     assert rc == 0
     return llr
+
+
+def port_ulsch_deinterleave(q, qm, n_symb):
+    """q: int16 [H' * qm] in channel order -> g in UL-SCH order (no UCI), through the port."""
+    q = np.ascontiguousarray(q, dtype=np.int16)
+    g = np.zeros_like(q)
+    port().port_ulsch_deinterleave(q, qm, q.size // qm, n_symb, g)
+    return g
+
+
+def ref_ulsch_deinterleave(q, qm, n_symb):
+    q = np.ascontiguousarray(q, dtype=np.int16)
+    g = np.zeros_like(q)
+    assert ref().refh_ulsch_deinterleave(q, qm, q.size // qm, n_symb, g) == 0
+    return g

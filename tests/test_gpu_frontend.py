@@ -53,6 +53,26 @@ def test_many_codewords_vs_oracle(ctx):
     assert np.array_equal(got, np.concatenate(want))
 
 
+def test_pusch_codewords_with_ulsch_deinterleaver_vs_oracle(ctx):
+    """PUSCH order of operations (pusch.c:482-500, sch.c:1028-1036): demodulate, descramble, then the UL-SCH channel
+    de-interleaver; the kernel applies the permutation as an index map."""
+    rng = np.random.default_rng(14)
+    cws, syms, want, so, lo = [], [], [], 0, 0
+    for qm in (2, 4, 6):
+        for cols in (12, 11, 10):
+            for prb in (1, 6, 50):
+                nsym = prb * 12 * cols
+                sym = ((rng.standard_normal(nsym) + 1j * rng.standard_normal(nsym)) * 0.9).astype(np.complex64)
+                c_init = int(rng.integers(1, 2 ** 31 - 1))
+                cws.append(dict(qm=qm, nof_symbols=nsym, c_init=c_init, sym_offset=so, llr_offset=lo, ul_nof_symb=cols))
+                syms.append(sym)
+                want.append(ol.port_ulsch_deinterleave(ol.port_demod_descramble(qm, sym, c_init), qm, cols))
+                so += nsym
+                lo += qm * nsym
+    got = _run(ctx, cws, syms)
+    assert np.array_equal(got, np.concatenate(want))
+
+
 def test_fused_with_rate_dematching_vs_oracle(ctx):
     """symbols -> LLR -> descramble -> srslte_rm_turbo_rx_lut in ONE kernel (no e array), with HARQ combining of two
     transmissions, against the oracle: port_demod_descramble, then the port's receive index table applied as
@@ -117,10 +137,12 @@ def test_transport_blocks_from_symbols_vs_oracle(ctx, vec):
     import ctypes as C
     P = ol.port()
     rng = np.random.default_rng(21)
-    cases = [(2216, 2, 4800), (6200, 4, 9600), (14112, 4, 28800), (36696, 6, 60000), (75376, 6, 90000), (1000, 2, 2400)]
+    # (tbs, qm, G, N_pusch_symbs or 0 for PDSCH)
+    cases = [(2216, 2, 4800, 0), (6200, 4, 9600, 0), (14112, 4, 28800, 0), (36696, 6, 60000, 0), (75376, 6, 90000, 0),
+             (1000, 2, 2400, 0), (2216, 4, 4800, 12), (14112, 4, 28800, 12), (36696, 6, 59904, 12), (6200, 4, 9504, 11)]
     descs, want = [], []
     dec = P.port_tdec_new()
-    for i, (tbs, qm, G) in enumerate(cases * 2):
+    for i, (tbs, qm, G, ul) in enumerate(cases * 2):
         seg = ol.PortCbsegm()
         assert P.port_cbsegm(C.byref(seg), tbs) == 0 and seg.F == 0
         payload = rng.integers(0, 2, tbs, dtype=np.uint8)
@@ -142,9 +164,16 @@ def test_transport_blocks_from_symbols_vs_oracle(ctx, vec):
         c = np.zeros(G, np.uint8)
         P.port_gold_sequence(c_init, G, c)
         sigma = (0.0, 0.08, 0.25)[i % 3]
-        sym = _modulate(e ^ c, qm)
+        if ul:   # UL-SCH channel interleaver (36.212 5.2.2.8): q[(i*rows + j)*Qm + k] = g[(j*cols + i)*Qm + k]
+            rows = G // qm // ul
+            tx = e.reshape(rows, ul, qm).transpose(1, 0, 2).reshape(-1)
+        else:
+            tx = e
+        sym = _modulate(tx ^ c, qm)
         sym = (sym + sigma * (rng.standard_normal(sym.size) + 1j * rng.standard_normal(sym.size))).astype(np.complex64)
         llr = ol.port_demod_descramble(qm, sym, c_init, G)
+        if ul:
+            llr = ol.port_ulsch_deinterleave(llr, qm, ul)
         sb = ol.PortSoftbuffer()
         P.port_softbuffer_init(C.byref(sb), seg.C)
         out = np.zeros(tbs // 8 + 8, np.uint8)
@@ -153,7 +182,7 @@ def test_transport_blocks_from_symbols_vs_oracle(ctx, vec):
         rc = P.port_decode_tb(dec, C.byref(sb), tbs, qm, 0, G, llr, out, 8, C.byref(avg), noi)
         want.append((rc, out[: tbs // 8 + 3].copy(), avg.value, np.packbits(payload)))
         P.port_softbuffer_free(C.byref(sb))
-        descs.append(dict(tbs=tbs, qm=qm, rv=0, nof_e_bits=G, softbuffer=i, c_init=c_init, symbols=sym))
+        descs.append(dict(tbs=tbs, qm=qm, rv=0, nof_e_bits=G, softbuffer=i, c_init=c_init, symbols=sym, ul_nof_symb=ul))
     P.port_tdec_free(dec)
     pool = ctx.harq_pool(len(descs), 13)
     got = ctx.decode_tb_sym_batch(pool, descs, 8)
@@ -166,5 +195,5 @@ def test_transport_blocks_from_symbols_vs_oracle(ctx, vec):
         if ret == 0:
             n_ok += 1
             assert np.array_equal(data[: tbs // 8], payload)
-    assert n_ok >= 8
+    assert n_ok >= 13
     pool.close()

@@ -57,3 +57,21 @@ def test_port_matches_compiled_reference():
                 nb = qm * n if n % 2 else qm * n - (qm * n) // 3
                 assert np.array_equal(ol.port_demod_descramble(qm, sym, c_init, nb),
                                       ol.ref_demod_descramble(qm, sym, c_init, nb)), (qm, n, amp)
+
+
+def test_ulsch_deinterleaver_port_vs_reference_and_definition():
+    """36.212 5.2.2.8 without UCI: g[(j*cols + i)*Qm + k] = q[(i*rows + j)*Qm + k]; the port against that formula and,
+    when oracle/_ref is present, against the reference's own ulsch_deinterleave (sch.c:891-918)."""
+    rng = np.random.default_rng(9)
+    have_ref = ol.ref() is not None
+    for qm in (2, 4, 6):
+        for cols in (12, 11, 10, 9):
+            for prb in (1, 3, 25, 100):
+                H = prb * 12 * cols
+                rows = H // cols
+                q = rng.integers(-3000, 3000, H * qm).astype(np.int16)
+                g = ol.port_ulsch_deinterleave(q, qm, cols)
+                want = q.reshape(cols, rows, qm).transpose(1, 0, 2).reshape(-1)
+                assert np.array_equal(g, want), (qm, cols, prb)
+                if have_ref:
+                    assert np.array_equal(g, ol.ref_ulsch_deinterleave(q, qm, cols)), (qm, cols, prb)
