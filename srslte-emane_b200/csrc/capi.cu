@@ -213,7 +213,7 @@ void build_rounds(srslte_b200_ctx* ctx, Schedule& s)
     R.clear();
     const auto& items = s.items[ri];
     for (uint32_t i = 0; i < items.size(); i += per) R.push_back(make_uint2(i, per));
-    const uint32_t G = (uint32_t)std::max(1, ctx->sm_count);
+    const uint32_t G = (uint32_t)std::max(1, ctx->sm_count * tdec_ctas_per_sm());
     const uint32_t last = (uint32_t)(R.size() % G);
     const uint32_t q = last ? std::min(4u, G / last) : 1u;
     if (q >= 2) {

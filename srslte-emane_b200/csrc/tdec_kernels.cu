@@ -1484,6 +1484,7 @@ int tdec_blocks_per_warp(int W) { return W == 16 ? 4 : W == 8 ? 8 : 32; }
 // the window kernels take this many consecutive work items per CTA round; they must share K (host pads with
 // count-0 items).  1 for the generic kernel.
 int tdec_items_per_cta(int W) { return W ? kWarps : 1; }
+int tdec_ctas_per_sm() { return kBlocksPerSm; }
 
 uint32_t internal_len(uint32_t K)
 {

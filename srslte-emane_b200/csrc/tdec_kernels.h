@@ -57,6 +57,7 @@ struct TdecGeometry {
 cudaError_t tdec_geometry(int W, int device, TdecGeometry* g);
 cudaError_t tdec_launch(int W, const TdecGeometry& g, const TdecLaunch& a, cudaStream_t s);
 int         tdec_blocks_per_warp(int W);
+int         tdec_ctas_per_sm();         // resident CTAs of the window kernels per SM
 int         tdec_items_per_cta(int W);  // consecutive work items a CTA takes per round; they must share K
 
 // int16 elements of one code block in the decoder's internal layout (pair-major streams + tail + meta
