@@ -1003,13 +1003,6 @@ __device__ void decide(const WinCtx<W>& c, uint8_t* out, bool write)
   __syncwarp();
 }
 
-__device__ __forceinline__ uint32_t crc24_bytes_dev(int which, const uint8_t* p, uint32_t nbytes)
-{
-  uint32_t crc = 0;
-  for (uint32_t i = 0; i < nbytes; i++) crc = ((crc << 8) ^ c_crc_tab[which][((crc >> 16) & 0xFFu) ^ p[i]]) & 0xFFFFFFu;
-  return crc;
-}
-
 // max over the W/2 threads of a code block
 template <int WH>
 __device__ __forceinline__ uint32_t group_max(uint32_t v)
@@ -1164,108 +1157,155 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
   if (lane == 0 && fallbacks && a.stats) atomicAdd(a.stats, fallbacks);
 }
 
-// ---- generic decoder (K <= 400): one thread per code block, natural order, wrapping arithmetic ----
+// ---- generic decoder (K <= 400): one thread per code block, wrapping arithmetic -------------------------------
+// reference: lib/src/phy/fec/turbodecoder_gen.c:54-231 (no windows: beta over all K + 3 rows, normalisation every 4).
+// A work item is up to 32 code blocks of equal K, one per lane.  Everything the lanes touch is laid out [row][lane]
+// (inputs by to_internal_kernel, A / E / beta per warp slot), and every row index -- also pi(k) -- is the same for all
+// lanes, so each access is one coalesced row; the rows of the next 4 trellis steps are loaded while the current 4 are
+// computed (the recursion itself is a chain of dependent operations: latency, not bandwidth, is what this kernel
+// has to hide when a launch holds few small blocks).
 struct GenCtx {
-  uint32_t       K, f1, f2;
-  const int16_t* in;   // natural 3i+j, tails at 3K
-  int16_t*       A;    // [K]
-  int16_t*       E;    // [K]
-  uint4*         beta; // [(k)*32], offset by lane; k = 0..K+3
+  int             K;
+  uint32_t        cnt;   // code blocks of the item = lane stride of the input rows
+  const int16_t*  in;    // item input, [3k + j][block] then 12 tail rows, already offset by this lane's block
+  int16_t*        A;     // [k][32 lanes], offset by lane: extrinsic of DEC2 minus E (a-priori of DEC1), natural order
+  int16_t*        E;     // [k][32 lanes]: a-posteriori of DEC1 minus A (systematic of DEC2), natural order
+  uint4*          beta;  // [k][32 lanes], offset by lane; k = 0..K+3
+  const uint16_t* pi;    // shared: pi(k), k < K
 };
 
 __device__ __forceinline__ int16_t w16(int v) { return (int16_t)v; }
 
-__device__ void gen_half_iteration(const GenCtx& c, bool dec2, bool apriori)
+struct GenRaw {
+  int x, y, ap;
+};
+
+// the three values trellis row k needs (k >= K: tail rows, no a-priori)
+__device__ __forceinline__ GenRaw gen_load(const GenCtx& c, bool dec2, int k)
 {
-  const int K = (int)c.K;
+  GenRaw r;
+  if (k >= c.K) {
+    const int t = (dec2 ? 6 : 0) + 2 * (k - c.K);
+    r.x  = c.in[(size_t)(3 * c.K + t) * c.cnt];
+    r.y  = c.in[(size_t)(3 * c.K + t + 1) * c.cnt];
+    r.ap = 0;
+  } else if (!dec2) {
+    r.x  = c.in[(size_t)(3 * k) * c.cnt];
+    r.y  = c.in[(size_t)(3 * k + 1) * c.cnt];
+    r.ap = c.A[k * 32];
+  } else {
+    r.x  = c.E[(int)c.pi[k] * 32];
+    r.y  = c.in[(size_t)(3 * k + 2) * c.cnt];
+    r.ap = 0;
+  }
+  return r;
+}
+
+__device__ void gen_half_iteration(const GenCtx& c, bool dec2)
+{
+  const int K = c.K;
   int16_t   s[8];
   s[0] = 0;
   for (int i = 1; i < 8; i++) s[i] = (int16_t)kNegInf;
-  auto pi = [&](int k) { return (uint32_t)(((c.f1 + c.f2 * (uint32_t)k) * (uint32_t)k) % c.K); };
-  auto load = [&](int k, int& x, int& y, int& aux, uint32_t& p) {
-    p = 0;
-    if (k >= K) {  // tail rows: no a-priori
-      const int r = k - K;
-      x   = c.in[3 * K + (dec2 ? 6 : 0) + 2 * r];
-      y   = c.in[3 * K + (dec2 ? 6 : 0) + 2 * r + 1];
-      aux = 0;
-    } else if (!dec2) {
-      x   = c.in[3 * k];
-      y   = c.in[3 * k + 1];
-      aux = 0;
-      if (apriori) {
-        aux = c.A[k];
-        x   = w16(x + aux);
-      }
-    } else {
-      p   = pi(k);
-      x   = c.E[p];
-      y   = c.in[3 * k + 2];
-      aux = x;
-    }
-  };
-  for (int k = K + 2; k >= 0; k--) {
-    int      x, y, aux;
-    uint32_t p;
-    load(k, x, y, aux, p);
-    const int xy = w16(x + y);
-    int16_t   m[8], n[8];
-    m[0] = w16(s[4] + xy); m[1] = s[4];           m[2] = w16(s[5] + y);  m[3] = w16(s[5] + x);
-    m[4] = w16(s[6] + x);  m[5] = w16(s[6] + y);  m[6] = s[7];           m[7] = w16(s[7] + xy);
-    n[0] = s[0];           n[1] = w16(s[0] + xy); n[2] = w16(s[1] + x);  n[3] = w16(s[1] + y);
-    n[4] = w16(s[2] + y);  n[5] = w16(s[2] + x);  n[6] = w16(s[3] + xy); n[7] = s[3];
+  GenRaw cur[4], nxt[4];
+  // ---- beta over rows K+2 .. 0, four at a time ----
 #pragma unroll
-    for (int i = 0; i < 8; i++) s[i] = m[i] > n[i] ? m[i] : n[i];
-    uint4 v;
-    v.x = (uint16_t)s[0] | ((uint32_t)(uint16_t)s[1] << 16);
-    v.y = (uint16_t)s[2] | ((uint32_t)(uint16_t)s[3] << 16);
-    v.z = (uint16_t)s[4] | ((uint32_t)(uint16_t)s[5] << 16);
-    v.w = (uint16_t)s[6] | ((uint32_t)(uint16_t)s[7] << 16);
-    c.beta[(size_t)k * 32] = v;
-    if ((k % 4) == 0 && k < K) {
-      for (int i = 1; i < 8; i++) s[i] = w16(s[i] - s[0]);
-      s[0] = 0;
+  for (int j = 0; j < 4; j++) cur[j] = gen_load(c, dec2, max(K + 2 - j, 0));
+  for (int k0 = K + 2; k0 >= 0; k0 -= 4) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) nxt[j] = gen_load(c, dec2, max(k0 - 4 - j, 0));
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int k = k0 - j;
+      if (k < 0) break;
+      const int x  = dec2 ? cur[j].x : w16(cur[j].x + cur[j].ap);  // the a-priori array is all zero at first
+      const int y  = cur[j].y;
+      const int xy = w16(x + y);
+      int16_t   m[8], n[8];
+      m[0] = w16(s[4] + xy); m[1] = s[4];           m[2] = w16(s[5] + y);  m[3] = w16(s[5] + x);
+      m[4] = w16(s[6] + x);  m[5] = w16(s[6] + y);  m[6] = s[7];           m[7] = w16(s[7] + xy);
+      n[0] = s[0];           n[1] = w16(s[0] + xy); n[2] = w16(s[1] + x);  n[3] = w16(s[1] + y);
+      n[4] = w16(s[2] + y);  n[5] = w16(s[2] + x);  n[6] = w16(s[3] + xy); n[7] = s[3];
+#pragma unroll
+      for (int i = 0; i < 8; i++) s[i] = m[i] > n[i] ? m[i] : n[i];
+      uint4 v;
+      v.x = (uint16_t)s[0] | ((uint32_t)(uint16_t)s[1] << 16);
+      v.y = (uint16_t)s[2] | ((uint32_t)(uint16_t)s[3] << 16);
+      v.z = (uint16_t)s[4] | ((uint32_t)(uint16_t)s[5] << 16);
+      v.w = (uint16_t)s[6] | ((uint32_t)(uint16_t)s[7] << 16);
+      c.beta[(size_t)k * 32] = v;
+      if ((k % 4) == 0 && k < K) {
+#pragma unroll
+        for (int i = 1; i < 8; i++) s[i] = w16(s[i] - s[0]);
+        s[0] = 0;
+      }
     }
+#pragma unroll
+    for (int j = 0; j < 4; j++) cur[j] = nxt[j];
   }
+  // ---- alpha + output over steps 1 .. K (step k uses row k-1 and beta[k]) ----
   s[0] = 0;
   for (int i = 1; i < 8; i++) s[i] = (int16_t)kNegInf;
-  for (int k = 1; k <= K; k++) {
-    int      x, y, aux;
-    uint32_t p;
-    load(k - 1, x, y, aux, p);
-    const int xy = w16(x + y);
-    int16_t   m[8], n[8], b[8];
-    m[0] = s[0];           m[1] = w16(s[3] + y);  m[2] = w16(s[4] + y);  m[3] = s[7];
-    m[4] = s[1];           m[5] = w16(s[2] + y);  m[6] = w16(s[5] + y);  m[7] = s[6];
-    n[0] = w16(s[1] + xy); n[1] = w16(s[2] + x);  n[2] = w16(s[5] + x);  n[3] = w16(s[6] + xy);
-    n[4] = w16(s[0] + xy); n[5] = w16(s[3] + x);  n[6] = w16(s[4] + x);  n[7] = w16(s[7] + xy);
-    const uint4 v = c.beta[(size_t)k * 32];
-    b[0] = (int16_t)(v.x & 0xFFFF); b[1] = (int16_t)(v.x >> 16); b[2] = (int16_t)(v.y & 0xFFFF); b[3] = (int16_t)(v.y >> 16);
-    b[4] = (int16_t)(v.z & 0xFFFF); b[5] = (int16_t)(v.z >> 16); b[6] = (int16_t)(v.w & 0xFFFF); b[7] = (int16_t)(v.w >> 16);
-    int16_t M0 = w16(m[0] + b[0]), M1 = w16(n[0] + b[0]);
+  uint4 bcur[4], bnxt[4];
 #pragma unroll
-    for (int i = 1; i < 8; i++) {
-      const int16_t c0 = w16(m[i] + b[i]), c1 = w16(n[i] + b[i]);
-      if (c0 > M0) M0 = c0;
-      if (c1 > M1) M1 = c1;
+  for (int j = 0; j < 4; j++) {
+    cur[j]  = gen_load(c, dec2, min(j, K - 1));
+    bcur[j] = c.beta[(size_t)min(1 + j, K) * 32];
+  }
+  for (int k0 = 1; k0 <= K; k0 += 4) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      nxt[j]  = gen_load(c, dec2, min(k0 + 3 + j, K - 1));
+      bnxt[j] = c.beta[(size_t)min(k0 + 4 + j, K) * 32];
     }
 #pragma unroll
-    for (int i = 0; i < 8; i++) s[i] = m[i] > n[i] ? m[i] : n[i];
-    if ((k % 4) == 0) {
-      for (int i = 1; i < 8; i++) s[i] = w16(s[i] - s[0]);
-      s[0] = 0;
+    for (int j = 0; j < 4; j++) {
+      const int k = k0 + j;
+      if (k > K) break;
+      const int aux = dec2 ? cur[j].x : cur[j].ap;
+      const int x   = dec2 ? cur[j].x : w16(cur[j].x + cur[j].ap);
+      const int y   = cur[j].y;
+      const int xy  = w16(x + y);
+      int16_t   m[8], n[8], b[8];
+      m[0] = s[0];           m[1] = w16(s[3] + y);  m[2] = w16(s[4] + y);  m[3] = s[7];
+      m[4] = s[1];           m[5] = w16(s[2] + y);  m[6] = w16(s[5] + y);  m[7] = s[6];
+      n[0] = w16(s[1] + xy); n[1] = w16(s[2] + x);  n[2] = w16(s[5] + x);  n[3] = w16(s[6] + xy);
+      n[4] = w16(s[0] + xy); n[5] = w16(s[3] + x);  n[6] = w16(s[4] + x);  n[7] = w16(s[7] + xy);
+      const uint4 v = bcur[j];
+      b[0] = (int16_t)(v.x & 0xFFFF); b[1] = (int16_t)(v.x >> 16); b[2] = (int16_t)(v.y & 0xFFFF); b[3] = (int16_t)(v.y >> 16);
+      b[4] = (int16_t)(v.z & 0xFFFF); b[5] = (int16_t)(v.z >> 16); b[6] = (int16_t)(v.w & 0xFFFF); b[7] = (int16_t)(v.w >> 16);
+      int16_t M0 = w16(m[0] + b[0]), M1 = w16(n[0] + b[0]);
+#pragma unroll
+      for (int i = 1; i < 8; i++) {
+        const int16_t c0 = w16(m[i] + b[i]), c1 = w16(n[i] + b[i]);
+        if (c0 > M0) M0 = c0;
+        if (c1 > M1) M1 = c1;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) s[i] = m[i] > n[i] ? m[i] : n[i];
+      if ((k % 4) == 0) {
+#pragma unroll
+        for (int i = 1; i < 8; i++) s[i] = w16(s[i] - s[0]);
+        s[0] = 0;
+      }
+      const int16_t d = w16(w16(M1 - M0) - aux);
+      if (!dec2)
+        c.E[(k - 1) * 32] = d;
+      else
+        c.A[(int)c.pi[k - 1] * 32] = d;
     }
-    const int16_t o = w16(M1 - M0);
-    if (!dec2)
-      c.E[k - 1] = w16(o - aux);
-    else
-      c.A[p] = w16(o - aux);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      cur[j]  = nxt[j];
+      bcur[j] = bnxt[j];
+    }
   }
 }
 
 __global__ void __launch_bounds__(kThreads) tdec_gen_kernel(const TdecLaunch a)
 {
   constexpr uint32_t KMAX = 400;
+  __shared__ uint16_t s_pi[kThreads / 32][KMAX];
   const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t slot = blockIdx.x * (kThreads / 32) + warp;
   for (;;) {
@@ -1275,36 +1315,45 @@ __global__ void __launch_bounds__(kThreads) tdec_gen_kernel(const TdecLaunch a)
     if (it >= a.n_items) break;
     const WorkItem wi     = a.items[it];
     const bool     active = lane < (int)wi.count;
-    const uint32_t cb     = a.order[wi.first + (active ? lane : 0)];
+    const uint32_t b_eff  = active ? (uint32_t)lane : 0u;  // idle lanes shadow block 0
+    const uint32_t cb     = a.order[wi.first + b_eff];
     GenCtx c;
-    c.K    = wi.K;
-    c.f1   = wi.f1;
-    c.f2   = wi.f2;
-    c.in   = a.in + (size_t)(wi.first + (active ? lane : 0)) * a.in_stride;  // blocks are stored by schedule position
-    c.A    = a.ws_ae + ((size_t)slot * 32 + lane) * 2 * KMAX;
-    c.E    = c.A + KMAX;
+    c.K    = (int)wi.K;
+    c.cnt  = wi.count;
+    c.in   = a.in + (size_t)wi.first * a.in_stride + b_eff;  // items are stored by schedule position, lanes interleaved
+    c.A    = a.ws_ae + (size_t)slot * 2 * KMAX * 32 + lane;
+    c.E    = c.A + KMAX * 32;
     c.beta = reinterpret_cast<uint4*>(a.ws_chk) + (size_t)slot * (KMAX + 4) * 32 + lane;
-    for (uint32_t k = 0; k < c.K; k++) c.A[k] = 0;
+    c.pi   = s_pi[warp];
+    __syncwarp();
+    for (uint32_t k = (uint32_t)lane; k < wi.K; k += 32)  // pi(k) = (f1 k + f2 k^2) mod K, K <= 400: fits 32 bits
+      s_pi[warp][k] = (uint16_t)(((uint32_t)wi.f1 * k + (uint32_t)wi.f2 * k * k) % wi.K);
+    for (int k = 0; k < c.K; k++) c.A[k * 32] = 0;
+    __syncwarp();
 
     uint8_t* out  = a.out + (size_t)cb * a.out_stride;
     uint32_t n    = 0, iters = 0;
     bool     done = false, ok = false;
     const uint32_t crc_mode = a.crc_mode_cb ? a.crc_mode_cb[cb] : a.crc_mode;
     const int      which    = crc_mode == CRC_24A ? 0 : 1;
-    auto decide_gen = [&]() {
-      for (uint32_t j = 0; j < c.K / 8; j++) {
+    // hard decision (A + E > 0, MSB first) and, on the fly, the CRC of the bytes
+    auto decide_gen = [&]() -> uint32_t {
+      uint32_t crc = 0;
+      for (int j = 0; j < c.K / 8; j++) {
         uint32_t byte = 0;
-        for (int b = 0; b < 8; b++) byte = (byte << 1) | (w16(c.A[8 * j + b] + c.E[8 * j + b]) > 0 ? 1u : 0u);
+#pragma unroll
+        for (int b = 0; b < 8; b++) byte = (byte << 1) | (w16(c.A[(8 * j + b) * 32] + c.E[(8 * j + b) * 32]) > 0 ? 1u : 0u);
         out[j] = (uint8_t)byte;
+        crc    = ((crc << 8) ^ c_crc_tab[which][((crc >> 16) & 0xFFu) ^ byte]) & 0xFFFFFFu;
       }
+      return crc;
     };
     do {
-      gen_half_iteration(c, (n & 1) != 0, n > 0);
+      gen_half_iteration(c, (n & 1) != 0);
       n++;
       if (crc_mode != CRC_NONE && !done && active) {
-        decide_gen();
         iters = n;
-        if (crc24_bytes_dev(which, out, c.K / 8) == 0) {
+        if (decide_gen() == 0) {
           ok   = true;
           done = true;
         }
@@ -1329,7 +1378,7 @@ __global__ void __launch_bounds__(kThreads) tdec_gen_kernel(const TdecLaunch a)
 //                  32-bit words (two windows each), Lp = L rounded up to 4 rows;
 //                  then per block 16 int16 holding the 12 tail samples and 16 int16 of meta data:
 //                  max |sys|, max |par0|, max |par1| (uint16) -- the inputs of the fast-path proof.
-// generic decoder: the natural 3i+j order unchanged, one block after the other.
+// generic decoder: [natural index 3i+j, then the 12 tail samples][block of the item] -- one coalesced row per value.
 // place[cb] = (first, count << 8 | index in the item); without it the schedule is the identity (uniform K).
 __device__ __forceinline__ uint32_t windows_of(uint32_t K)
 {
@@ -1361,9 +1410,9 @@ __global__ void __launch_bounds__(256) to_internal_kernel(const int16_t* __restr
     cnt   = min(per, gridDim.x - first);
     b     = cb - first;
   }
-  if (W == 0) {
-    int16_t* dst = dst_all + (size_t)(first + b) * dst_stride;
-    for (uint32_t i = threadIdx.x; i < 3 * K + 12; i += blockDim.x) dst[i] = src[i];
+  if (W == 0) {  // generic decoder: value i of the block goes to row i of the item, column b
+    int16_t* dst = dst_all + (size_t)first * dst_stride + b;
+    for (uint32_t i = threadIdx.x; i < 3 * K + 12; i += blockDim.x) dst[(size_t)i * cnt] = src[i];
     return;
   }
   const uint32_t L = K / W, Lp = (L + 3) & ~3u, WH = W / 2, S = Lp * W;
