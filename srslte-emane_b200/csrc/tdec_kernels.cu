@@ -1157,45 +1157,45 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
   if (lane == 0 && fallbacks && a.stats) atomicAdd(a.stats, fallbacks);
 }
 
-// ---- generic decoder (K <= 400): one thread per code block, wrapping arithmetic -------------------------------
-// reference: lib/src/phy/fec/turbodecoder_gen.c:54-231 (no windows: beta over all K + 3 rows, normalisation every 4).
-// A work item is up to 32 code blocks of equal K, one per lane.  Everything the lanes touch is laid out [row][lane]
-// (inputs by to_internal_kernel, A / E / beta per warp slot), and every row index -- also pi(k) -- is the same for all
-// lanes, so each access is one coalesced row; the rows of the next 4 trellis steps are loaded while the current 4 are
-// computed (the recursion itself is a chain of dependent operations: latency, not bandwidth, is what this kernel
-// has to hide when a launch holds few small blocks).
+// ---- generic decoder (K <= 400): one thread per PAIR of code blocks, wrapping arithmetic ------------------------
+// reference: lib/src/phy/fec/turbodecoder_gen.c:54-231 (no windows: beta over all K + 3 rows, normalisation every 4,
+// plain wrapping int16 arithmetic -- exactly the packed VIADD.16x2 / VIADDMNMX.S16x2 steps of the window kernels'
+// fast variant, here with no proof obligations).
+// A work item is up to 64 code blocks of equal K; a lane owns two of them as the halves of its 32-bit registers.
+// Everything is laid out [row][block] (inputs by to_internal_kernel, A / E / beta per warp slot), and every row
+// index -- also pi(k) -- is the same for all lanes, so each access is one coalesced row of words; the rows of the
+// next 4 trellis steps are loaded while the current 4 are computed (the recursion is a chain of dependent
+// operations: latency, not bandwidth, is what this kernel has to hide when a launch holds few small blocks).
 struct GenCtx {
   int             K;
-  uint32_t        cnt;   // code blocks of the item = lane stride of the input rows
-  const int16_t*  in;    // item input, [3k + j][block] then 12 tail rows, already offset by this lane's block
-  int16_t*        A;     // [k][32 lanes], offset by lane: extrinsic of DEC2 minus E (a-priori of DEC1), natural order
-  int16_t*        E;     // [k][32 lanes]: a-posteriori of DEC1 minus A (systematic of DEC2), natural order
-  uint4*          beta;  // [k][32 lanes], offset by lane; k = 0..K+3
-  const uint16_t* pi;    // shared: pi(k), k < K
+  uint32_t        stride;  // 32-bit words per input row = (blocks of the item rounded up to 2) / 2
+  const uint32_t* in;      // item input, [3k + j][block pair] then 12 tail rows, already offset by this lane's pair
+  uint32_t*       A;       // [k][32 lanes], offset by lane: extrinsic of DEC2 minus E (a-priori of DEC1), natural order
+  uint32_t*       E;       // [k][32 lanes]: a-posteriori of DEC1 minus A (systematic of DEC2), natural order
+  uint4*          beta;    // [k][half][32 lanes], offset by lane; k = 0..K+3
+  const uint16_t* pi;      // shared: pi(k), k < K
 };
-
-__device__ __forceinline__ int16_t w16(int v) { return (int16_t)v; }
 
 struct GenRaw {
-  int x, y, ap;
+  uint32_t x, y, ap;
 };
 
-// the three values trellis row k needs (k >= K: tail rows, no a-priori)
+// the three words trellis row k needs (k >= K: tail rows, no a-priori)
 __device__ __forceinline__ GenRaw gen_load(const GenCtx& c, bool dec2, int k)
 {
   GenRaw r;
   if (k >= c.K) {
     const int t = (dec2 ? 6 : 0) + 2 * (k - c.K);
-    r.x  = c.in[(size_t)(3 * c.K + t) * c.cnt];
-    r.y  = c.in[(size_t)(3 * c.K + t + 1) * c.cnt];
+    r.x  = c.in[(size_t)(3 * c.K + t) * c.stride];
+    r.y  = c.in[(size_t)(3 * c.K + t + 1) * c.stride];
     r.ap = 0;
   } else if (!dec2) {
-    r.x  = c.in[(size_t)(3 * k) * c.cnt];
-    r.y  = c.in[(size_t)(3 * k + 1) * c.cnt];
+    r.x  = c.in[(size_t)(3 * k) * c.stride];
+    r.y  = c.in[(size_t)(3 * k + 1) * c.stride];
     r.ap = c.A[k * 32];
   } else {
     r.x  = c.E[(int)c.pi[k] * 32];
-    r.y  = c.in[(size_t)(3 * k + 2) * c.cnt];
+    r.y  = c.in[(size_t)(3 * k + 2) * c.stride];
     r.ap = 0;
   }
   return r;
@@ -1204,9 +1204,10 @@ __device__ __forceinline__ GenRaw gen_load(const GenCtx& c, bool dec2, int k)
 __device__ void gen_half_iteration(const GenCtx& c, bool dec2)
 {
   const int K = c.K;
-  int16_t   s[8];
+  uint32_t  s[8];
   s[0] = 0;
-  for (int i = 1; i < 8; i++) s[i] = (int16_t)kNegInf;
+#pragma unroll
+  for (int i = 1; i < 8; i++) s[i] = kNegInf2;
   GenRaw cur[4], nxt[4];
   // ---- beta over rows K+2 .. 0, four at a time ----
 #pragma unroll
@@ -1218,77 +1219,48 @@ __device__ void gen_half_iteration(const GenCtx& c, bool dec2)
     for (int j = 0; j < 4; j++) {
       const int k = k0 - j;
       if (k < 0) break;
-      const int x  = dec2 ? cur[j].x : w16(cur[j].x + cur[j].ap);  // the a-priori array is all zero at first
-      const int y  = cur[j].y;
-      const int xy = w16(x + y);
-      int16_t   m[8], n[8];
-      m[0] = w16(s[4] + xy); m[1] = s[4];           m[2] = w16(s[5] + y);  m[3] = w16(s[5] + x);
-      m[4] = w16(s[6] + x);  m[5] = w16(s[6] + y);  m[6] = s[7];           m[7] = w16(s[7] + xy);
-      n[0] = s[0];           n[1] = w16(s[0] + xy); n[2] = w16(s[1] + x);  n[3] = w16(s[1] + y);
-      n[4] = w16(s[2] + y);  n[5] = w16(s[2] + x);  n[6] = w16(s[3] + xy); n[7] = s[3];
-#pragma unroll
-      for (int i = 0; i < 8; i++) s[i] = m[i] > n[i] ? m[i] : n[i];
-      uint4 v;
-      v.x = (uint16_t)s[0] | ((uint32_t)(uint16_t)s[1] << 16);
-      v.y = (uint16_t)s[2] | ((uint32_t)(uint16_t)s[3] << 16);
-      v.z = (uint16_t)s[4] | ((uint32_t)(uint16_t)s[5] << 16);
-      v.w = (uint16_t)s[6] | ((uint32_t)(uint16_t)s[7] << 16);
-      c.beta[(size_t)k * 32] = v;
-      if ((k % 4) == 0 && k < K) {
-#pragma unroll
-        for (int i = 1; i < 8; i++) s[i] = w16(s[i] - s[0]);
-        s[0] = 0;
-      }
+      const uint32_t x = dec2 ? cur[j].x : wadd2(cur[j].x, cur[j].ap);  // the a-priori array is all zero at first
+      const uint32_t y = cur[j].y;
+      beta_step<true>(s, x, y, wadd2(x, y));
+      c.beta[((size_t)k * 2 + 0) * 32] = make_uint4(s[0], s[1], s[2], s[3]);
+      c.beta[((size_t)k * 2 + 1) * 32] = make_uint4(s[4], s[5], s[6], s[7]);
+      if ((k % 4) == 0 && k < K) normalize<true>(s);
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) cur[j] = nxt[j];
   }
   // ---- alpha + output over steps 1 .. K (step k uses row k-1 and beta[k]) ----
   s[0] = 0;
-  for (int i = 1; i < 8; i++) s[i] = (int16_t)kNegInf;
-  uint4 bcur[4], bnxt[4];
+#pragma unroll
+  for (int i = 1; i < 8; i++) s[i] = kNegInf2;
+  uint4 bcur[4][2], bnxt[4][2];
+  Range unused;
+  unused.reset();
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    cur[j]  = gen_load(c, dec2, min(j, K - 1));
-    bcur[j] = c.beta[(size_t)min(1 + j, K) * 32];
+    cur[j] = gen_load(c, dec2, min(j, K - 1));
+    bcur[j][0] = c.beta[((size_t)min(1 + j, K) * 2 + 0) * 32];
+    bcur[j][1] = c.beta[((size_t)min(1 + j, K) * 2 + 1) * 32];
   }
   for (int k0 = 1; k0 <= K; k0 += 4) {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      nxt[j]  = gen_load(c, dec2, min(k0 + 3 + j, K - 1));
-      bnxt[j] = c.beta[(size_t)min(k0 + 4 + j, K) * 32];
+      nxt[j] = gen_load(c, dec2, min(k0 + 3 + j, K - 1));
+      bnxt[j][0] = c.beta[((size_t)min(k0 + 4 + j, K) * 2 + 0) * 32];
+      bnxt[j][1] = c.beta[((size_t)min(k0 + 4 + j, K) * 2 + 1) * 32];
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int k = k0 + j;
       if (k > K) break;
-      const int aux = dec2 ? cur[j].x : cur[j].ap;
-      const int x   = dec2 ? cur[j].x : w16(cur[j].x + cur[j].ap);
-      const int y   = cur[j].y;
-      const int xy  = w16(x + y);
-      int16_t   m[8], n[8], b[8];
-      m[0] = s[0];           m[1] = w16(s[3] + y);  m[2] = w16(s[4] + y);  m[3] = s[7];
-      m[4] = s[1];           m[5] = w16(s[2] + y);  m[6] = w16(s[5] + y);  m[7] = s[6];
-      n[0] = w16(s[1] + xy); n[1] = w16(s[2] + x);  n[2] = w16(s[5] + x);  n[3] = w16(s[6] + xy);
-      n[4] = w16(s[0] + xy); n[5] = w16(s[3] + x);  n[6] = w16(s[4] + x);  n[7] = w16(s[7] + xy);
-      const uint4 v = bcur[j];
-      b[0] = (int16_t)(v.x & 0xFFFF); b[1] = (int16_t)(v.x >> 16); b[2] = (int16_t)(v.y & 0xFFFF); b[3] = (int16_t)(v.y >> 16);
-      b[4] = (int16_t)(v.z & 0xFFFF); b[5] = (int16_t)(v.z >> 16); b[6] = (int16_t)(v.w & 0xFFFF); b[7] = (int16_t)(v.w >> 16);
-      int16_t M0 = w16(m[0] + b[0]), M1 = w16(n[0] + b[0]);
-#pragma unroll
-      for (int i = 1; i < 8; i++) {
-        const int16_t c0 = w16(m[i] + b[i]), c1 = w16(n[i] + b[i]);
-        if (c0 > M0) M0 = c0;
-        if (c1 > M1) M1 = c1;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; i++) s[i] = m[i] > n[i] ? m[i] : n[i];
-      if ((k % 4) == 0) {
-#pragma unroll
-        for (int i = 1; i < 8; i++) s[i] = w16(s[i] - s[0]);
-        s[0] = 0;
-      }
-      const int16_t d = w16(w16(M1 - M0) - aux);
+      const uint32_t aux = dec2 ? cur[j].x : cur[j].ap;
+      const uint32_t x   = dec2 ? cur[j].x : wadd2(cur[j].x, cur[j].ap);
+      const uint32_t y   = cur[j].y;
+      const uint32_t bb[8] = {bcur[j][0].x, bcur[j][0].y, bcur[j][0].z, bcur[j][0].w,
+                              bcur[j][1].x, bcur[j][1].y, bcur[j][1].z, bcur[j][1].w};
+      const uint32_t o = alpha_out_step<true, false>(s, bb, x, y, wadd2(x, y), unused);
+      if ((k % 4) == 0) normalize<true>(s);
+      const uint32_t d = wsub2(o, aux);
       if (!dec2)
         c.E[(k - 1) * 32] = d;
       else
@@ -1296,8 +1268,9 @@ __device__ void gen_half_iteration(const GenCtx& c, bool dec2)
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      cur[j]  = nxt[j];
-      bcur[j] = bnxt[j];
+      cur[j]     = nxt[j];
+      bcur[j][0] = bnxt[j][0];
+      bcur[j][1] = bnxt[j][1];
     }
   }
 }
@@ -1313,60 +1286,90 @@ __global__ void __launch_bounds__(kThreads) tdec_gen_kernel(const TdecLaunch a)
     if (lane == 0) it = atomicAdd(a.counter, 1u);
     it = __shfl_sync(0xFFFFFFFFu, it, 0);
     if (it >= a.n_items) break;
-    const WorkItem wi     = a.items[it];
-    const bool     active = lane < (int)wi.count;
-    const uint32_t b_eff  = active ? (uint32_t)lane : 0u;  // idle lanes shadow block 0
-    const uint32_t cb     = a.order[wi.first + b_eff];
+    const WorkItem wi = a.items[it];
+    // this lane's two code blocks (low / high half of its registers); idle halves and lanes shadow valid storage
+    const uint32_t npair = ((uint32_t)wi.count + 1) / 2;
+    const bool     act[2] = {2 * (uint32_t)lane < wi.count, 2 * (uint32_t)lane + 1 < wi.count};
+    const uint32_t pair_eff = (uint32_t)lane < npair ? (uint32_t)lane : 0u;
+    uint32_t       cb[2];
+    cb[0] = a.order[wi.first + (act[0] ? 2 * lane : 0)];
+    cb[1] = a.order[wi.first + (act[1] ? 2 * lane + 1 : 0)];
     GenCtx c;
-    c.K    = (int)wi.K;
-    c.cnt  = wi.count;
-    c.in   = a.in + (size_t)wi.first * a.in_stride + b_eff;  // items are stored by schedule position, lanes interleaved
-    c.A    = a.ws_ae + (size_t)slot * 2 * KMAX * 32 + lane;
-    c.E    = c.A + KMAX * 32;
-    c.beta = reinterpret_cast<uint4*>(a.ws_chk) + (size_t)slot * (KMAX + 4) * 32 + lane;
-    c.pi   = s_pi[warp];
+    c.K      = (int)wi.K;
+    c.stride = npair;
+    c.in     = reinterpret_cast<const uint32_t*>(a.in + (size_t)wi.first * a.in_stride) + pair_eff;
+    c.A      = reinterpret_cast<uint32_t*>(a.ws_ae) + (size_t)slot * 2 * KMAX * 32 + lane;
+    c.E      = c.A + KMAX * 32;
+    c.beta   = reinterpret_cast<uint4*>(a.ws_chk) + (size_t)slot * (KMAX + 4) * 2 * 32 + lane;
+    c.pi     = s_pi[warp];
     __syncwarp();
     for (uint32_t k = (uint32_t)lane; k < wi.K; k += 32)  // pi(k) = (f1 k + f2 k^2) mod K, K <= 400: fits 32 bits
       s_pi[warp][k] = (uint16_t)(((uint32_t)wi.f1 * k + (uint32_t)wi.f2 * k * k) % wi.K);
     for (int k = 0; k < c.K; k++) c.A[k * 32] = 0;
     __syncwarp();
 
-    uint8_t* out  = a.out + (size_t)cb * a.out_stride;
-    uint32_t n    = 0, iters = 0;
-    bool     done = false, ok = false;
-    const uint32_t crc_mode = a.crc_mode_cb ? a.crc_mode_cb[cb] : a.crc_mode;
-    const int      which    = crc_mode == CRC_24A ? 0 : 1;
-    // hard decision (A + E > 0, MSB first) and, on the fly, the CRC of the bytes
-    auto decide_gen = [&]() -> uint32_t {
-      uint32_t crc = 0;
-      for (int j = 0; j < c.K / 8; j++) {
-        uint32_t byte = 0;
+    uint32_t n = 0;
+    uint32_t iters[2] = {0, 0};
+    bool     done[2] = {false, false}, ok[2] = {false, false};
+    uint32_t mode[2];
 #pragma unroll
-        for (int b = 0; b < 8; b++) byte = (byte << 1) | (w16(c.A[(8 * j + b) * 32] + c.E[(8 * j + b) * 32]) > 0 ? 1u : 0u);
-        out[j] = (uint8_t)byte;
-        crc    = ((crc << 8) ^ c_crc_tab[which][((crc >> 16) & 0xFFu) ^ byte]) & 0xFFFFFFu;
+    for (int h = 0; h < 2; h++) mode[h] = a.crc_mode_cb ? a.crc_mode_cb[cb[h]] : a.crc_mode;
+    // hard decision (A + E > 0, MSB first) of the blocks selected by wr, and on the fly the CRC of their bytes
+    auto decide_gen = [&](const bool wr[2], uint32_t crc[2]) {
+      crc[0] = crc[1] = 0;
+      uint8_t* out0 = a.out + (size_t)cb[0] * a.out_stride;
+      uint8_t* out1 = a.out + (size_t)cb[1] * a.out_stride;
+      const int w0 = mode[0] == CRC_24A ? 0 : 1, w1 = mode[1] == CRC_24A ? 0 : 1;
+      for (int j = 0; j < c.K / 8; j++) {
+        uint32_t b0 = 0, b1 = 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+          const uint32_t v = wadd2(c.A[(8 * j + b) * 32], c.E[(8 * j + b) * 32]);
+          b0 = (b0 << 1) | (lo16(v) > 0 ? 1u : 0u);
+          b1 = (b1 << 1) | (hi16(v) > 0 ? 1u : 0u);
+        }
+        if (wr[0]) out0[j] = (uint8_t)b0;
+        if (wr[1]) out1[j] = (uint8_t)b1;
+        crc[0] = ((crc[0] << 8) ^ c_crc_tab[w0][((crc[0] >> 16) & 0xFFu) ^ b0]) & 0xFFFFFFu;
+        crc[1] = ((crc[1] << 8) ^ c_crc_tab[w1][((crc[1] >> 16) & 0xFFu) ^ b1]) & 0xFFFFFFu;
       }
-      return crc;
     };
+    bool busy;
     do {
       gen_half_iteration(c, (n & 1) != 0);
       n++;
-      if (crc_mode != CRC_NONE && !done && active) {
-        iters = n;
-        if (decide_gen() == 0) {
-          ok   = true;
-          done = true;
-        }
+      bool chk[2];
+#pragma unroll
+      for (int h = 0; h < 2; h++) chk[h] = mode[h] != CRC_NONE && !done[h] && act[h];
+      if (chk[0] || chk[1]) {
+        uint32_t crc[2];
+        decide_gen(chk, crc);
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+          if (chk[h]) {
+            iters[h] = n;
+            if (crc[h] == 0) {
+              ok[h]   = true;
+              done[h] = true;
+            }
+          }
       }
-    } while (n < a.max_iter && !__all_sync(0xFFFFFFFFu, done || !active));
-    if (crc_mode == CRC_NONE) {
-      if (active) decide_gen();
-      iters = n;
+      busy = (act[0] && !done[0]) || (act[1] && !done[1]);
+    } while (n < a.max_iter && __any_sync(0xFFFFFFFFu, busy));
+    {
+      bool     fin[2];
+      uint32_t crc[2];
+#pragma unroll
+      for (int h = 0; h < 2; h++) fin[h] = act[h] && mode[h] == CRC_NONE;
+      if (fin[0] || fin[1]) decide_gen(fin, crc);
     }
-    if (active) {
-      if (a.n_iter) a.n_iter[cb] = (uint8_t)iters;
-      if (a.crc_ok) a.crc_ok[cb] = ok ? 1 : 0;
-    }
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+      if (act[h]) {
+        if (mode[h] == CRC_NONE) iters[h] = n;
+        if (a.n_iter) a.n_iter[cb[h]] = (uint8_t)iters[h];
+        if (a.crc_ok) a.crc_ok[cb[h]] = ok[h] ? 1 : 0;
+      }
     __syncwarp();
   }
 }
@@ -1378,7 +1381,8 @@ __global__ void __launch_bounds__(kThreads) tdec_gen_kernel(const TdecLaunch a)
 //                  32-bit words (two windows each), Lp = L rounded up to 4 rows;
 //                  then per block 16 int16 holding the 12 tail samples and 16 int16 of meta data:
 //                  max |sys|, max |par0|, max |par1| (uint16) -- the inputs of the fast-path proof.
-// generic decoder: [natural index 3i+j, then the 12 tail samples][block of the item] -- one coalesced row per value.
+// generic decoder: [natural index 3i+j, then the 12 tail samples][block of the item, count rounded up to 2] -- one
+//                  coalesced row per value, two blocks per 32-bit word.
 // place[cb] = (first, count << 8 | index in the item); without it the schedule is the identity (uniform K).
 __device__ __forceinline__ uint32_t windows_of(uint32_t K)
 {
@@ -1405,14 +1409,15 @@ __global__ void __launch_bounds__(256) to_internal_kernel(const int16_t* __restr
     cnt   = pl.y >> 8;
     b     = pl.y & 0xFFu;
   } else {
-    const uint32_t per = W ? 64u / W : 32u;  // code blocks per work item
+    const uint32_t per = W ? 64u / W : 64u;  // code blocks per work item
     first = cb / per * per;
     cnt   = min(per, gridDim.x - first);
     b     = cb - first;
   }
-  if (W == 0) {  // generic decoder: value i of the block goes to row i of the item, column b
-    int16_t* dst = dst_all + (size_t)first * dst_stride + b;
-    for (uint32_t i = threadIdx.x; i < 3 * K + 12; i += blockDim.x) dst[(size_t)i * cnt] = src[i];
+  if (W == 0) {  // generic decoder: value i of the block goes to row i of the item, column b (rows of an even length)
+    int16_t*       dst = dst_all + (size_t)first * dst_stride + b;
+    const uint32_t rs  = (cnt + 1) & ~1u;
+    for (uint32_t i = threadIdx.x; i < 3 * K + 12; i += blockDim.x) dst[(size_t)i * rs] = src[i];
     return;
   }
   const uint32_t L = K / W, Lp = (L + 3) & ~3u, WH = W / 2, S = Lp * W;
@@ -1528,7 +1533,7 @@ void upload_crc_tables()
   cudaMemcpyToSymbol(c_crc_tab, tab, sizeof(tab));
 }
 
-int tdec_blocks_per_warp(int W) { return W == 16 ? 4 : W == 8 ? 8 : 32; }
+int tdec_blocks_per_warp(int W) { return W == 16 ? 4 : W == 8 ? 8 : 64; }
 
 // the window kernels take this many consecutive work items per CTA round; they must share K (host pads with
 // count-0 items).  1 for the generic kernel.
@@ -1538,7 +1543,7 @@ int tdec_ctas_per_sm() { return kBlocksPerSm; }
 uint32_t internal_len(uint32_t K)
 {
   const uint32_t W = (K % 16 == 0 && K > 800) ? 16u : (K % 8 == 0 && K > 400) ? 8u : 0u;
-  if (W == 0) return 3 * K + 12;
+  if (W == 0) return 2 * (3 * K + 12);  // rows of an even number of blocks: an item of 1 block takes 2 columns
   const uint32_t L = K / W, Lp = (L + 3) & ~3u;
   return 3 * Lp * W + 32;
 }
@@ -1554,8 +1559,8 @@ cudaError_t tdec_geometry(int W, int device, TdecGeometry* g)
     g->smem   = 0;
     g->blocks = sms * 4;
     const size_t slots = (size_t)g->blocks * warps_per_block;
-    g->ws_ae_bytes  = slots * 32 * 2 * 400 * sizeof(int16_t);
-    g->ws_chk_bytes = slots * (400 + 4) * 32 * sizeof(uint4);
+    g->ws_ae_bytes  = slots * 32 * 2 * 400 * sizeof(uint32_t);
+    g->ws_chk_bytes = slots * (400 + 4) * 2 * 32 * sizeof(uint4);
     return cudaSuccess;
   }
   g->smem = (size_t)kChunk * 2 * kThreads * sizeof(uint4) + warps_per_block * kStages * kStageBytes +
