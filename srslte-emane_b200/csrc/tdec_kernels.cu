@@ -1183,19 +1183,20 @@ struct GenRaw {
 // the three words trellis row k needs (k >= K: tail rows, no a-priori)
 __device__ __forceinline__ GenRaw gen_load(const GenCtx& c, bool dec2, int k)
 {
-  GenRaw r;
-  if (k >= c.K) {
-    const int t = (dec2 ? 6 : 0) + 2 * (k - c.K);
-    r.x  = c.in[(size_t)(3 * c.K + t) * c.stride];
-    r.y  = c.in[(size_t)(3 * c.K + t + 1) * c.stride];
+  GenRaw         r;
+  const uint32_t uk = (uint32_t)k, K = (uint32_t)c.K;  // 32-bit index arithmetic: an item is at most 1212 x 32 words
+  if (uk >= K) {
+    const uint32_t t = (dec2 ? 6u : 0u) + 2 * (uk - K);
+    r.x  = c.in[(3 * K + t) * c.stride];
+    r.y  = c.in[(3 * K + t + 1) * c.stride];
     r.ap = 0;
   } else if (!dec2) {
-    r.x  = c.in[(size_t)(3 * k) * c.stride];
-    r.y  = c.in[(size_t)(3 * k + 1) * c.stride];
-    r.ap = c.A[k * 32];
+    r.x  = c.in[(3 * uk) * c.stride];
+    r.y  = c.in[(3 * uk + 1) * c.stride];
+    r.ap = c.A[uk * 32];
   } else {
-    r.x  = c.E[(int)c.pi[k] * 32];
-    r.y  = c.in[(size_t)(3 * k + 2) * c.stride];
+    r.x  = c.E[(uint32_t)c.pi[uk] * 32];
+    r.y  = c.in[(3 * uk + 2) * c.stride];
     r.ap = 0;
   }
   return r;
@@ -1222,8 +1223,8 @@ __device__ void gen_half_iteration(const GenCtx& c, bool dec2)
       const uint32_t x = dec2 ? cur[j].x : wadd2(cur[j].x, cur[j].ap);  // the a-priori array is all zero at first
       const uint32_t y = cur[j].y;
       beta_step<true>(s, x, y, wadd2(x, y));
-      c.beta[((size_t)k * 2 + 0) * 32] = make_uint4(s[0], s[1], s[2], s[3]);
-      c.beta[((size_t)k * 2 + 1) * 32] = make_uint4(s[4], s[5], s[6], s[7]);
+      c.beta[((uint32_t)k * 2 + 0) * 32] = make_uint4(s[0], s[1], s[2], s[3]);
+      c.beta[((uint32_t)k * 2 + 1) * 32] = make_uint4(s[4], s[5], s[6], s[7]);
       if ((k % 4) == 0 && k < K) normalize<true>(s);
     }
 #pragma unroll
@@ -1239,15 +1240,15 @@ __device__ void gen_half_iteration(const GenCtx& c, bool dec2)
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     cur[j] = gen_load(c, dec2, min(j, K - 1));
-    bcur[j][0] = c.beta[((size_t)min(1 + j, K) * 2 + 0) * 32];
-    bcur[j][1] = c.beta[((size_t)min(1 + j, K) * 2 + 1) * 32];
+    bcur[j][0] = c.beta[((uint32_t)min(1 + j, K) * 2 + 0) * 32];
+    bcur[j][1] = c.beta[((uint32_t)min(1 + j, K) * 2 + 1) * 32];
   }
   for (int k0 = 1; k0 <= K; k0 += 4) {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       nxt[j] = gen_load(c, dec2, min(k0 + 3 + j, K - 1));
-      bnxt[j][0] = c.beta[((size_t)min(k0 + 4 + j, K) * 2 + 0) * 32];
-      bnxt[j][1] = c.beta[((size_t)min(k0 + 4 + j, K) * 2 + 1) * 32];
+      bnxt[j][0] = c.beta[((uint32_t)min(k0 + 4 + j, K) * 2 + 0) * 32];
+      bnxt[j][1] = c.beta[((uint32_t)min(k0 + 4 + j, K) * 2 + 1) * 32];
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -1262,9 +1263,9 @@ __device__ void gen_half_iteration(const GenCtx& c, bool dec2)
       if ((k % 4) == 0) normalize<true>(s);
       const uint32_t d = wsub2(o, aux);
       if (!dec2)
-        c.E[(k - 1) * 32] = d;
+        c.E[(uint32_t)(k - 1) * 32] = d;
       else
-        c.A[(int)c.pi[k - 1] * 32] = d;
+        c.A[(uint32_t)c.pi[k - 1] * 32] = d;
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
