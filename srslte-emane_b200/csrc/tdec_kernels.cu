@@ -300,21 +300,23 @@ __device__ __forceinline__ void pipe_issue(const WinCtx<W>& c, bool dec2, Pipe& 
 {
   if (p.phase > 3) return;
   const int ctop = (int)(c.L - 1) >> 3;
-  if (c.lane == 0) {
+  {
+    // lane i prepares and issues copy i (DEC1: sys, par0, A; DEC2: par1, E): the operands are computed once, SIMD,
+    // and the bulk-copy instruction -- which takes uniform registers -- runs once per active lane
     const uint32_t ch     = (uint32_t)p.ch;
     const uint32_t gbytes = min(2u, c.ngroups - 2 * ch) * c.g_stride;
     const uint32_t xbytes = min(8u, c.L - 8 * ch) * 128u;
     const uint32_t mb     = smem_u32(c.mbar + slot);
-    const uint32_t dst    = smem_u32(c.stages + slot * kStageBytes);
-    const char*    g0     = c.in_item + (size_t)ch * 2 * c.g_stride;
-    mbar_expect_tx(mb, (dec2 ? gbytes : 2 * gbytes) + xbytes);
-    if (!dec2) {
-      bulk_g2s(dst, g0, gbytes, mb);
-      bulk_g2s(dst + 1024, g0 + c.s_bytes, gbytes, mb);
-      bulk_g2s(dst + 2048, reinterpret_cast<const char*>(c.A32) + (size_t)ch * 1024, xbytes, mb);
-    } else {
-      bulk_g2s(dst + 1024, g0 + 2 * (size_t)c.s_bytes, gbytes, mb);
-      bulk_g2s(dst + 2048, reinterpret_cast<const char*>(c.E32) + (size_t)ch * 1024, xbytes, mb);
+    const uint32_t nc     = dec2 ? 2u : 3u;
+    const uint32_t i      = (uint32_t)c.lane;
+    if (i == 0) mbar_expect_tx(mb, (dec2 ? gbytes : 2 * gbytes) + xbytes);
+    if (i < nc) {
+      const bool     isx    = i == nc - 1;
+      const uint32_t stream = dec2 ? 2u : i;
+      const char*    src    = isx ? reinterpret_cast<const char*>(dec2 ? c.E32 : c.A32) + (size_t)ch * 1024
+                                  : c.in_item + (size_t)ch * 2 * c.g_stride + (size_t)stream * c.s_bytes;
+      const uint32_t dst    = smem_u32(c.stages + slot * kStageBytes) + (isx ? 2048u : dec2 ? 1024u : i * 1024u);
+      bulk_g2s(dst, src, isx ? xbytes : gbytes, mb);
     }
   }
   if (p.phase == 0 || p.phase == 1) {
