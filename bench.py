@@ -139,6 +139,18 @@ def cpu_reference_rate(sample_blocks, threads, llr_np, min_wall=1.5):
     return passes * len(x) * K / dt / 1e9, dt, kind, passes
 
 
+def workload_config(n, world):
+    """The `config` object of the bench line: the same for the B200 arm and for the reference arm."""
+    return {
+        "workload": f"batched srslte_tdec_run_all: {n} code blocks per GPU, K={K}, nof_iterations={NOF_ITERATIONS} "
+                    f"(srsLTE half iterations), natural-order int16 LLR, AWGN harness -e {EBNO_HARNESS} "
+                    f"(sigma 1.457), LLR scale {LLR_SCALE:g}, 16-window int16 max-log-MAP, no CRC",
+        "blocks_per_gpu": n, "K": K, "nof_iterations": NOF_ITERATIONS,
+        "l2": f"inputs {n * IN_LEN * 2 / 1e6:.0f} MB per step > 126 MB L2, no flush needed",
+        "parallelism": f"code blocks sharded over {world} GPU(s), no collective",
+    }
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -161,10 +173,11 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "turbo_decode_info_gbps_k6144_4it", "value": value, "unit": "Gbit/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": f"srslte_tdec_run_all K={K} nof_iterations={NOF_ITERATIONS} (half iterations), "
-                               f"AWGN harness -e {EBNO_HARNESS}, scale {LLR_SCALE:g}; reference CPU arm: {n} blocks per step"},
+        # the B200 arm's workload; every step decodes a bounded sample of it on the host cores (cpu_baseline.sample)
+        "config": workload_config(args.blocks, max(args.gpus, 1)),
         "cpu_baseline": {"value": value, "unit": "Gbit/s", "cores": cores, "kind": kind,
-                         "sample": f"{n} K={K} blocks per step, {cores} pthreads, one srslte_tdec_t each"},
+                         "sample": f"{n} blocks of the workload (K={K}, nof_iterations={NOF_ITERATIONS}) per step, "
+                                   f"{cores} pthreads, one srslte_tdec_t each, the reference's AVX2 16-window decoder"},
         "e2e": {"value": value, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -305,14 +318,7 @@ def main():
         "metric": "turbo_decode_info_gbps_k6144_4it", "value": value, "unit": "Gbit/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {
-            "workload": f"batched srslte_tdec_run_all: {n} code blocks per GPU, K={K}, nof_iterations={NOF_ITERATIONS} "
-                        f"(srsLTE half iterations), natural-order int16 LLR, AWGN harness -e {EBNO_HARNESS} "
-                        f"(sigma 1.457), LLR scale {LLR_SCALE:g}, 16-window int16 max-log-MAP, no CRC",
-            "blocks_per_gpu": n, "K": K, "nof_iterations": NOF_ITERATIONS,
-            "l2": f"inputs {n * IN_LEN * 2 / 1e6:.0f} MB per step > 126 MB L2, no flush needed",
-            "parallelism": f"code blocks sharded over {world} GPU(s), no collective",
-        },
+        "config": workload_config(n, world),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Gbit/s", "h2d_bytes_per_step": ne * IN_LEN * 2,
                 "d2h_bytes_per_step": ne * (K // 8 + 2), "blocks_per_gpu": ne, "ms_per_step": e2e_dt * 1e3,
