@@ -278,3 +278,24 @@ def test_pure_fast_tier_edges(ctx, vec):
             for nit in (1, 2, 4):
                 got, _, _ = ctx.tdec_batch_host(llr, K, nit)
                 assert np.array_equal(got, ol.port_run_all(llr, K, nit)), (K, name, nit)
+
+
+def test_generic_decoder_pairs_and_ragged_items(ctx, vec, pkg):
+    """K <= 400: a thread decodes two blocks and a warp item holds up to 64 -- odd counts, single blocks, several
+    items, with and without CRC early termination (n_iter and the CRC flag per block), extreme LLR values."""
+    P = ol.port()
+    for K in (40, 104, 400):
+        for n in (1, 2, 3, 63, 64, 65, 131):
+            bits, llr = vec.make_blocks(n, K, vec.harness_sigma(4.0), 100, seed=K * 7 + n)
+            got, _, _ = ctx.tdec_batch_host(llr, K, 5)
+            assert np.array_equal(got, ol.port_run_all(llr, K, 5)), (K, n)
+        bits, llr = vec.make_blocks(67, K, 0.7, 100, seed=K + 3)
+        llr[5] = 32767
+        llr[6] = -32768
+        got, n_iter, ok = ctx.tdec_batch_host(llr, K, 8, crc_mode=pkg.CRC_24B)
+        for i in range(67):
+            by, _, _ = ol.port_trace(llr[i], K, 8)
+            crcs = [P.port_crc_bytes(ol.CRC24B, by[it].copy(), K) for it in range(8)]
+            stop = next((it + 1 for it in range(8) if crcs[it] == 0), 8)
+            assert n_iter[i] == stop and ok[i] == int(crcs[stop - 1] == 0), (K, i)
+            assert np.array_equal(got[i], by[stop - 1]), (K, i)

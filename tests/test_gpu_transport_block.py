@@ -103,3 +103,56 @@ def test_tb_argument_errors(ctx):
     (ret, _, _), = ctx.decode_tb_batch(pool, [dict(tbs=1000, qm=2, rv=0, e_bits=e, softbuffer=5)], 4)
     assert ret == -2
     pool.close()
+
+
+def test_lazy_harq_reset_equals_zero_and_accumulate(ctx, vec):
+    """srslte_b200_harq_reset only flags the soft buffer; the next rate de-matching into each of its blocks stores
+    instead of adding.  A soft buffer that held a 13-block TB is reset and reused for a 2-block TB, then -- without
+    a reset -- receives a second transmission (rv 2): results equal the oracle's zeroed-and-accumulated buffer."""
+    P = ol.port()
+    rng = np.random.default_rng(31)
+
+    def make(tbs, qm, G, rv, payload=None):
+        seg = ol.PortCbsegm()
+        assert P.port_cbsegm(C.byref(seg), tbs) == 0 and seg.F == 0
+        payload = rng.integers(0, 2, tbs, dtype=np.uint8) if payload is None else payload
+        tb = vec.attach_crc(vec.CRC24A, payload[None, :])[0]
+        parts, pos = [], 0
+        Gp, gamma = G // qm, (G // qm) % seg.C
+        for cb in range(seg.C):
+            K = seg.K1 if cb < seg.C1 else seg.K2
+            rlen = K if seg.C == 1 else K - 24
+            blk = tb[pos:pos + rlen]
+            pos += rlen
+            if seg.C > 1:
+                blk = vec.attach_crc(vec.CRC24B, blk[None, :])[0]
+            E = qm * (Gp // seg.C) if cb <= seg.C - gamma - 1 else qm * ((Gp + seg.C - 1) // seg.C)
+            parts.append(vec.rate_match(vec.turbo_encode(blk[None, :]), E, rv)[0])
+        return seg, payload, np.concatenate(parts)
+
+    pool = ctx.harq_pool(1, 13)
+    # 1. fill the soft buffer with a big, very noisy TB (fails): leaves garbage in all 13 block buffers
+    seg, _, e = make(75376, 6, 90000, 0)
+    (ret, _, _), = ctx.decode_tb_batch(pool, [dict(tbs=75376, qm=6, rv=0, e_bits=vec.awgn_llr(e, 1.5, 100, rng), softbuffer=0)], 2)
+    assert ret == -1
+    # 2. reset, then a 2-block TB in two transmissions at a noise level where one alone fails
+    pool.reset(0)
+    tbs, qm, G = 8760, 2, 10000
+    seg, payload, e0 = make(tbs, qm, G, 0)
+    _, _, e2 = make(tbs, qm, G, 2, payload)
+    llr0, llr2 = vec.awgn_llr(e0, 1.3, 100, rng), vec.awgn_llr(e2, 1.3, 100, rng)
+    dec = P.port_tdec_new()
+    sb = ol.PortSoftbuffer()
+    P.port_softbuffer_init(C.byref(sb), seg.C)
+    for rv, llr in ((0, llr0), (2, llr2)):
+        out = np.zeros(tbs // 8 + 8, np.uint8)
+        avg = C.c_float()
+        noi = np.zeros(seg.C, np.uint32)
+        rc = P.port_decode_tb(dec, C.byref(sb), tbs, qm, rv, G, llr, out, 6, C.byref(avg), noi)
+        (ret, data, gavg), = ctx.decode_tb_batch(pool, [dict(tbs=tbs, qm=qm, rv=rv, e_bits=llr, softbuffer=0)], 6)
+        assert ret == rc, rv
+        assert abs(gavg - avg.value) < 1e-6, rv
+        assert np.array_equal(data[: tbs // 8 + 3], out[: tbs // 8 + 3]), rv
+    P.port_softbuffer_free(C.byref(sb))
+    P.port_tdec_free(dec)
+    pool.close()
