@@ -1021,7 +1021,6 @@ template <int W>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const TdecLaunch a)
 {
   constexpr int WH  = W / 2;
-  constexpr int CBW = 32 / WH;
   extern __shared__ uint4 smem[];
   char*     stages_all = reinterpret_cast<char*>(smem + kChunk * 2 * kThreads);  // [warps][kStages][kStageBytes]
   uint16_t* rowtab     = reinterpret_cast<uint16_t*>(stages_all + kWarps * kStages * kStageBytes);
