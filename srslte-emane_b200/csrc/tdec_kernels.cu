@@ -96,6 +96,11 @@ struct Range {
     hi = max2(hi, s[7]);
     lo = min2(lo, s[7]);
   }
+  __device__ __forceinline__ void add8full(const uint32_t s[8])
+  {  // a state vector that has not just been normalised: s[0] counts too
+    add8(s);
+    add1(s[0]);
+  }
   __device__ __forceinline__ void add2v(uint32_t a, uint32_t b)
   {
     hi = max3(hi, a, b);
@@ -661,13 +666,17 @@ __device__ __noinline__ HalfResult half_iteration_exact(const WinCtx<W> c, bool 
 // DEC1 and DEC2 share one instantiation (they differ only in which streams a chunk holds): in steady state the
 // 12 warps of an SM run the same code, and the hot loops (backward 4 rows, rebuild + forward 8 rows) fit the
 // instruction cache.
-// EDGE = false (G <= kPureFastG, L a multiple of 4): no exact rows at all.  Proof on top of the static one below:
-// the tail samples are part of G (to_internal_kernel), so the last window's start metrics -- 3 tail steps from
-// the known end state -- already lie in [-3G, 3G] like any other beta; the first window's alpha starts from
-// (0, -10000 x 7), so for rows 0..2 alpha + branch lies in [-10000 - 3G, 3G], plus beta in [-5G, 5G] that is
-// [-10000 - 8G, 8G]: inside int16 for G <= kPureFastG; from row 3 on alpha has gone through 3 steps and a
-// normalisation and is in general position.  |out| <= 5G there too: the best bit-1 and bit-0 candidates can be
-// chosen from the same predecessor state, so they differ by at most spread(beta) + 2G.
+// Rows next to the terminated tail need no special treatment in any tier: the tail samples are part of G
+// (to_internal_kernel), so the last window's start metrics -- 3 tail steps from the known end state, every state
+// reached -- already lie in [-3G, 3G] like any other beta (the tracked tier adds that boundary vector to its
+// bookkeeping).  Only the rows above the last full row group (L % 4 of them) go through the exact helpers, because
+// the fast loops work on whole groups.
+// EDGE = true: rows 0..3 of the forward pass, next to the known start state (0, -10000 x 7) of the first window,
+// use exact arithmetic.  EDGE = false (G <= kPureFastG): not even those.  Proof: for rows 0..2 alpha + branch lies
+// in [-10000 - 3G, 3G], plus beta in [-5G, 5G] that is [-10000 - 8G, 8G]: inside int16 for G <= kPureFastG; from
+// row 3 on alpha has gone through 3 steps and a normalisation and is in general position.  |out| <= 5G there too:
+// the best bit-1 and bit-0 candidates can be chosen from the same predecessor state, so they differ by at most
+// spread(beta) + 2G.
 // HARD (CRC modes): the forward pass also accumulates the CRC of the hard decisions (c.R).
 template <int W, bool TRACK, bool EDGE, bool HARD>
 __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bool dec2, int G, Pipe& p)
@@ -675,10 +684,9 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
   constexpr int WH = W / 2;
   const int     L  = (int)c.L;
   const int     ctop = (L - 1) >> 3;
-  // rows [kExactRows, kf] use fast arithmetic in the forward pass, rows [0, kf] in the backward pass; the rows
-  // next to the terminated tail (above kf: 4 to 7 rows, so that a row group is either all fast or all exact) and
-  // next to the known start state (0..3, forward) are always exact
-  const int kf = EDGE ? ((L - kExactRows) & ~3) - 1 : L - 1;
+  // rows [0, kf] are covered by full row groups: fast arithmetic (except, EDGE, rows 0..3 of the forward pass);
+  // the L % 4 rows above kf go through the exact helpers
+  const int kf = (L & ~3) - 1;
   const int a0 = L - kWarm;  // first row of the alpha warm-up
   uint32_t  s[8];
   Range     rb, ra, rm, rd;
@@ -720,7 +728,8 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
     if (phase == 0) {
       exchange_beta_boundary<WH>(s, c.t, c.tail + (dec2 ? 6 : 0));
       chk_store<W>(c, ctop, s);
-      if (EDGE) {  // the rows next to the terminated tail: exact
+      if (TRACK) rb.add8full(s);
+      if (kf < L - 1) {  // the rows above the last full row group
 #pragma unroll
         for (int i = 0; i < 8; i++) st.s[i] = s[i];
         st.trk = rb;
@@ -779,12 +788,12 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
     c.sm[((hi - lo - 1) * 2 + 0) * kThreads] = make_uint4(s[0], s[1], s[2], s[3]);
     c.sm[((hi - lo - 1) * 2 + 1) * kThreads] = make_uint4(s[4], s[5], s[6], s[7]);
     if (hi != L) {  // hi is even and non-zero: the backward pass normalised after storing
-      if (!EDGE || hi <= kf)
+      if (hi <= kf)
         normalize<true>(s);
       else
         normalize<false>(s);
     }
-    if (EDGE && hi - 1 > kf) {  // rows next to the tail: exact
+    if (hi - 1 > kf) {  // rows above the last full row group
 #pragma unroll
       for (int i = 0; i < 8; i++) st.s[i] = s[i];
       st.trk.reset();
@@ -846,7 +855,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
       }
     }
     pipe_release<W>(c, dec2, p);
-    if (EDGE && hi - 1 > kf) {  // rows next to the tail: exact
+    if (hi - 1 > kf) {  // rows above the last full row group
 #pragma unroll
       for (int i = 0; i < 8; i++) st.s[i] = a[i];
       st.trk = ra;
@@ -1109,7 +1118,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
         HalfResult r;
         bool       fast_ok = false;
         // the decision must be warp-uniform: the passes below use full-warp shuffles and votes
-        if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kPureFastG && (c.L & 3u) == 0)) {
+        if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kPureFastG)) {
           r       = any_crc ? half_iteration_fast<W, false, false, true>(c, dec2, G, pipe)
                             : half_iteration_fast<W, false, false, false>(c, dec2, G, pipe);
           fast_ok = true;
