@@ -459,7 +459,12 @@ int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint
     a.ws_chk     = reinterpret_cast<uint32_t*>(R.ws_chk.p);
     a.crc_pos     = ctx->crc_pos_dev.p;
     a.crc_pos_off = ctx->crc_pos_off_dev.p;
-    a.force_exact = ctx->force_exact ? 1u : 0u;
+    static const uint32_t skip_tiers = [] {  // measurement probe: SRSLTE_B200_SKIP_TIERS=1 (pure), 2 (static), 3 (both)
+      const char* e = getenv("SRSLTE_B200_SKIP_TIERS");
+      const long  v = e ? atol(e) : 0;
+      return (uint32_t)(((v & 1) ? 2u : 0u) | ((v & 2) ? 4u : 0u));
+    }();
+    a.force_exact = (ctx->force_exact ? 1u : 0u) | skip_tiers;
     a.stats      = ctx->counters.p + 3;
     {
       KernelTimer kt(ctx, r, st);

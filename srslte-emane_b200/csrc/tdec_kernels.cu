@@ -1118,11 +1118,12 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
         HalfResult r;
         bool       fast_ok = false;
         // the decision must be warp-uniform: the passes below use full-warp shuffles and votes
-        if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kPureFastG)) {
+        // force_exact: bit 0 = exact variant only (tests); bits 1, 2 = skip the pure / the static tier (measurements)
+        if (__all_sync(0xFFFFFFFFu, (a.force_exact & 3u) == 0 && G <= kPureFastG)) {
           r       = any_crc ? half_iteration_fast<W, false, false, true>(c, dec2, G, pipe)
                             : half_iteration_fast<W, false, false, false>(c, dec2, G, pipe);
           fast_ok = true;
-        } else if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kStaticFastG)) {
+        } else if (__all_sync(0xFFFFFFFFu, (a.force_exact & 5u) == 0 && G <= kStaticFastG)) {
           r       = any_crc ? half_iteration_fast<W, false, true, true>(c, dec2, G, pipe)
                             : half_iteration_fast<W, false, true, false>(c, dec2, G, pipe);
           fast_ok = true;
