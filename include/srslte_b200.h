@@ -176,6 +176,22 @@ SRSLTE_B200_API int srslte_b200_demod_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, co
                                                       uint32_t n_cw, const srslte_b200_rm_sym_block_t* blocks,
                                                       uint32_t n_blocks, const float* symbols, int16_t* work);
 
+/* ---- TX mirror: turbo encoder + rate matching ---------------------------------- */
+/* For generating test / benchmark vectors on the device and as the encode half of a batched DL path:
+ *   srslte_tcod_encode(bits, d, K)                 lib/src/phy/fec/turbocoder.c:95-187   (d = 3K + 12 bits, 3i+j order)
+ *   srslte_rm_turbo_tx(..., d, 3K+12, e, E, rv)    lib/src/phy/fec/rm_turbo.c:303-372    (circular-buffer selection)
+ * bits / e: device memory, one bit per byte (0 / 1). */
+typedef struct {
+  uint32_t long_cb;      /* K: input bits of this block (its CRC already attached) */
+  uint32_t rv;
+  uint32_t e_len;        /* E */
+  uint32_t reserved;     /* 0 */
+  uint64_t bits_offset;  /* first input bit of the block in `bits` */
+  uint64_t e_offset;     /* first rate-matched bit of the block in `e` */
+} srslte_b200_tx_block_t;
+SRSLTE_B200_API int srslte_b200_tcod_rm_tx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_tx_block_t* blocks,
+                                                     uint32_t n_blocks, const uint8_t* bits, uint8_t* e);
+
 /* ---- batched transport-block decode (the sch.c decode_tb loop over many TBs) ----------------- */
 /* HARQ state lives on the device: one "soft buffer" = max_cb code-block LLR buffers + CRC flags +
  * saved payloads, the counterpart of srslte_softbuffer_rx_t (softbuffer.h:37-43, softbuffer.c:41-150). */

@@ -51,6 +51,11 @@ class TbDesc(C.Structure):
                 ("avg_iterations", C.c_float)]
 
 
+class TxBlock(C.Structure):
+    _fields_ = [("long_cb", C.c_uint32), ("rv", C.c_uint32), ("e_len", C.c_uint32), ("reserved", C.c_uint32),
+                ("bits_offset", C.c_uint64), ("e_offset", C.c_uint64)]
+
+
 class TbSymDesc(C.Structure):
     _fields_ = [("tbs", C.c_uint32), ("qm", C.c_uint32), ("rv", C.c_uint32), ("nof_e_bits", C.c_uint32),
                 ("softbuffer", C.c_uint32), ("nof_symbols", C.c_uint32), ("c_init", C.c_uint32),
@@ -64,7 +69,7 @@ EXPORTS = [
     "srslte_b200_ctx_fallback_count", "srslte_b200_host_alloc", "srslte_b200_host_free", "srslte_b200_cb_index", "srslte_b200_cb_size",
     "srslte_b200_nof_windows", "srslte_b200_working_len", "srslte_b200_rm_rx_table",
     "srslte_b200_tdec_batch_dev", "srslte_b200_tdec_batch_host", "srslte_b200_rm_rx_batch_dev",
-    "srslte_b200_demod_descramble_dev", "srslte_b200_demod_rm_rx_batch_dev",
+    "srslte_b200_demod_descramble_dev", "srslte_b200_demod_rm_rx_batch_dev", "srslte_b200_tcod_rm_tx_batch_dev",
     "srslte_b200_harq_pool_create", "srslte_b200_harq_pool_destroy", "srslte_b200_harq_reset",
     "srslte_b200_harq_cb_crc", "srslte_b200_decode_tb_batch", "srslte_b200_decode_tb_sym_batch",
 ]
@@ -111,6 +116,7 @@ def lib():
     L.srslte_b200_rm_rx_batch_dev.argtypes = [vp, C.POINTER(RmBlock), u32, vp, vp]
     L.srslte_b200_demod_descramble_dev.argtypes = [vp, C.POINTER(Codeword), u32, vp, vp]
     L.srslte_b200_demod_rm_rx_batch_dev.argtypes = [vp, C.POINTER(Codeword), u32, C.POINTER(RmSymBlock), u32, vp, vp]
+    L.srslte_b200_tcod_rm_tx_batch_dev.argtypes = [vp, C.POINTER(TxBlock), u32, vp, vp]
     L.srslte_b200_harq_pool_create.argtypes = [vp, u32, u32, C.POINTER(vp)]
     L.srslte_b200_harq_pool_destroy.argtypes = [vp, vp]
     L.srslte_b200_harq_pool_destroy.restype = None
@@ -300,6 +306,14 @@ class Context:
         rc = self._L.srslte_b200_decode_tb_sym_batch(self._h, pool._p, arr, n, max_iterations)
         self._check(rc, "srslte_b200_decode_tb_sym_batch")
         return [(int(arr[i].ret), outs[i], float(arr[i].avg_iterations)) for i in range(n)]
+
+    def tcod_rm_tx_batch_dev(self, blocks, bits_ptr, e_ptr):
+        """TX mirror: blocks = list of (K, rv, e_len, bits_offset, e_offset); bits / e: device, one bit per byte."""
+        arr = (TxBlock * len(blocks))()
+        for i, (K, rv, el, bo, eo) in enumerate(blocks):
+            arr[i] = TxBlock(K, rv, el, 0, bo, eo)
+        rc = self._L.srslte_b200_tcod_rm_tx_batch_dev(self._h, arr, len(blocks), C.c_void_p(bits_ptr), C.c_void_p(e_ptr))
+        self._check(rc, "srslte_b200_tcod_rm_tx_batch_dev")
 
     def rm_rx_batch_dev(self, blocks, e_ptr, work_ptr):
         """blocks: list of (K, rv, e_offset, e_len, work_offset)."""

@@ -135,6 +135,8 @@ struct srslte_b200_ctx {
   PinBuf<FeCodeword>           h_cws;
   DevBuf<RmSymItem>            d_rm_sym;
   PinBuf<RmSymItem>            h_rm_sym;
+  DevBuf<TxItem>               d_tx;
+  PinBuf<TxItem>               h_tx;
   uint64_t     launches = 0;
   // optional per-kernel event timing (bench.py's roofline): kind 0..4 = W16, W8, generic, layout, front end (demod / rate-dematch)
   bool         timing = false;
@@ -559,6 +561,8 @@ void srslte_b200_ctx_destroy(srslte_b200_ctx_t* ctx)
   ctx->h_cws.release();
   ctx->d_rm_sym.release();
   ctx->h_rm_sym.release();
+  ctx->d_tx.release();
+  ctx->h_tx.release();
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
   if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
@@ -949,6 +953,54 @@ int srslte_b200_demod_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_
                                       const float* symbols, int16_t* work)
 {
   return demod_rm_rx_enqueue(ctx, cws, n_cw, blocks, n_blocks, symbols, work, nullptr);
+}
+
+// ---- TX mirror: turbo encoder + rate matching --------------------------------------------------------
+int srslte_b200_tcod_rm_tx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_tx_block_t* blocks, uint32_t n_blocks,
+                                     const uint8_t* bits, uint8_t* e)
+{
+  if (!ctx) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  if (n_blocks == 0) return SRSLTE_B200_SUCCESS;
+  if (!blocks || !bits || !e) return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "NULL argument");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (int rc = staging_wait(ctx)) return rc;
+  CU(ctx->h_tx.reserve(n_blocks));
+  CU(ctx->d_tx.reserve(n_blocks));
+  for (uint32_t i = 0; i < n_blocks; i++) {
+    const srslte_b200_tx_block_t& bl = blocks[i];
+    const int                     ki = cb_index_exact(bl.long_cb);
+    if (bl.rv > 3 || ki < 0)
+      return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "block %u: invalid K=%u or rv=%u", i, bl.long_cb, bl.rv);
+    const uint32_t key = (bl.long_cb * 4 + bl.rv) * 2;  // the natural-order table: the TX selection order
+    auto           it  = ctx->rm_tab_off.find(key);
+    if (it == ctx->rm_tab_off.end()) {
+      std::vector<uint16_t> t;
+      rm_rx_table(bl.long_cb, bl.rv, false, t);
+      const uint32_t off = (uint32_t)ctx->rm_pool_host.size();
+      ctx->rm_pool_host.insert(ctx->rm_pool_host.end(), t.begin(), t.end());
+      it = ctx->rm_tab_off.emplace(key, off).first;
+    }
+    TxItem ti;
+    ti.K = bl.long_cb; ti.f1 = kQpp[ki].f1; ti.f2 = kQpp[ki].f2; ti.E = bl.e_len; ti.tab_off = it->second; ti.pad = 0;
+    ti.bits_off = bl.bits_offset; ti.e_off = bl.e_offset;
+    ctx->h_tx.p[i] = ti;
+  }
+  if (ctx->rm_pool_uploaded != ctx->rm_pool_host.size()) {
+    if (ctx->rm_pool_host.size() > ctx->rm_pool_dev.cap) {
+      CU(ctx->rm_pool_dev.reserve(ctx->rm_pool_host.size() * 2));
+      ctx->rm_pool_uploaded = 0;
+    }
+    CU(cudaMemcpyAsync(ctx->rm_pool_dev.p + ctx->rm_pool_uploaded, ctx->rm_pool_host.data() + ctx->rm_pool_uploaded,
+                       (ctx->rm_pool_host.size() - ctx->rm_pool_uploaded) * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->rm_pool_uploaded = ctx->rm_pool_host.size();
+  }
+  CU(cudaMemcpyAsync(ctx->d_tx.p, ctx->h_tx.p, n_blocks * sizeof(TxItem), cudaMemcpyHostToDevice, st));
+  CU(cudaEventRecord(ctx->ev_staging, st));
+  CU(tcod_rm_tx_launch(ctx->d_tx.p, n_blocks, bits, e, ctx->rm_pool_dev.p, st));
+  ctx->launches++;
+  return SRSLTE_B200_SUCCESS;
 }
 
 }  // extern "C"

@@ -123,7 +123,56 @@ __global__ void rm_rx_sym_kernel(const FeCodeword* __restrict__ cws, const float
   }
 }
 
+// ---- TX mirror: turbo encoder + rate matching, for vector generation on the device ----------
+// reference: srslte_tcod_encode (lib/src/phy/fec/turbocoder.c:95-187: two RSC encoders g0 = 1 + D^2 + D^3,
+// g1 = 1 + D + D^3, the second one on the QPP-interleaved bits, output 3i+j then the 12 tail bits) and
+// srslte_rm_turbo_tx (lib/src/phy/fec/rm_turbo.c:303-372: e[i] = d[table[i mod N]], the same selection table the
+// receive side scatters through).  One CTA per code block: thread 0 and thread 32 run the two shift registers
+// (a 6144-step chain each), everybody copies the systematic bits and gathers the rate-matched output.
+__global__ void __launch_bounds__(128) tcod_rm_tx_kernel(const TxItem* __restrict__ items, const uint8_t* __restrict__ bits_all,
+                                                         uint8_t* __restrict__ e_all, const uint16_t* __restrict__ tab_pool)
+{
+  extern __shared__ uint8_t tx_d[];  // the 3K + 12 coded bits
+  const TxItem   it   = items[blockIdx.x];
+  const uint32_t K    = it.K;
+  const uint8_t* bits = bits_all + it.bits_off;
+  for (uint32_t k = threadIdx.x; k < K; k += blockDim.x) tx_d[3 * k] = bits[k] & 1u;
+  if (threadIdx.x == 0 || threadIdx.x == 32) {
+    const bool second = threadIdx.x == 32;
+    uint32_t   r0 = 0, r1 = 0, r2 = 0;
+    uint32_t   p = 0, g = (it.f1 + it.f2) % K;  // pi(k) and pi(k+1) - pi(k) = f1 + f2 (2k + 1), both mod K
+    const uint32_t g2 = (2 * it.f2) % K;
+    for (uint32_t k = 0; k < K; k++) {
+      const uint32_t in = bits[second ? p : k] & 1u;
+      const uint32_t fb = in ^ r2 ^ r1;
+      tx_d[3 * k + (second ? 2 : 1)] = (uint8_t)(r2 ^ r0 ^ fb);
+      r2 = r1; r1 = r0; r0 = fb;
+      p += g; if (p >= K) p -= K;
+      g += g2; if (g >= K) g -= K;
+    }
+    uint8_t* tail = tx_d + 3 * K + (second ? 6 : 0);
+    for (int j = 0; j < 3; j++) {  // flush: the input equals the feedback, so 0 enters the register
+      tail[2 * j]     = (uint8_t)(r2 ^ r1);
+      tail[2 * j + 1] = (uint8_t)(r2 ^ r0);
+      r2 = r1; r1 = r0; r0 = 0;
+    }
+  }
+  __syncthreads();
+  const uint16_t* tab = tab_pool + it.tab_off;
+  uint8_t*        e   = e_all + it.e_off;
+  const uint32_t  N   = 3 * K + 12;
+  for (uint32_t i = threadIdx.x; i < it.E; i += blockDim.x) e[i] = tx_d[tab[i % N]];
+}
+
 }  // namespace
+
+cudaError_t tcod_rm_tx_launch(const TxItem* items, uint32_t n_items, const uint8_t* bits, uint8_t* e,
+                              const uint16_t* tab_pool, cudaStream_t s)
+{
+  if (n_items == 0) return cudaSuccess;
+  tcod_rm_tx_kernel<<<n_items, 128, 3 * 6144 + 16, s>>>(items, bits, e, tab_pool);
+  return cudaGetLastError();
+}
 
 cudaError_t demod_descramble_launch(const FeCodeword* cws, uint32_t n_cw, uint32_t max_llr, const float* symbols,
                                     int16_t* e, const uint32_t* x1, const uint32_t* x2mask, cudaStream_t s)

@@ -150,6 +150,18 @@ cudaError_t rm_rx_sym_launch(const FeCodeword* cws, const float* symbols, int16_
                              const RmSymItem* items, uint32_t n_items, const uint32_t* x1, const uint32_t* x2mask,
                              cudaStream_t s);
 
+// TX mirror: turbo encoder + rate matching of one code block per item (frontend_kernels.cu)
+struct TxItem {
+  uint32_t K, f1, f2;
+  uint32_t E;         // rate-matched bits to produce
+  uint32_t tab_off;   // offset of the natural-order (K, rv) selection table in the table pool
+  uint32_t pad;
+  uint64_t bits_off;  // first input bit (one per byte)
+  uint64_t e_off;     // first output bit (one per byte)
+};
+cudaError_t tcod_rm_tx_launch(const TxItem* items, uint32_t n_items, const uint8_t* bits, uint8_t* e,
+                              const uint16_t* tab_pool, cudaStream_t s);
+
 void upload_crc_tables();  // fills the __constant__ CRC tables (once per process/device)
 
 }  // namespace b200

@@ -197,3 +197,40 @@ def test_transport_blocks_from_symbols_vs_oracle(ctx, vec):
             assert np.array_equal(data[: tbs // 8], payload)
     assert n_ok >= 13
     pool.close()
+
+
+def test_tx_mirror_encoder_and_rate_matching(ctx, vec):
+    """Device TX mirror (turbo encoder + rate matching) against the numpy mirror, which the CPU suite pins to
+    srslte_tcod_encode / srslte_rm_turbo_tx; then the round trip through the device decoder."""
+    import torch
+    rng = np.random.default_rng(41)
+    blocks, want, bits_all, bo, eo = [], [], [], 0, 0
+    for K in (40, 104, 504, 1024, 5824, 6144):
+        for rv in range(4):
+            for E in (96, 3 * K + 12, 4 * K + 77):
+                b = rng.integers(0, 2, K, dtype=np.uint8)
+                blocks.append((K, rv, E, bo, eo))
+                bits_all.append(b)
+                want.append(vec.rate_match(vec.turbo_encode(b[None, :]), E, rv)[0])
+                bo += K
+                eo += E
+    bits_d = torch.from_numpy(np.concatenate(bits_all)).cuda()
+    e_d = torch.zeros(eo, dtype=torch.uint8, device="cuda")
+    ctx.tcod_rm_tx_batch_dev(blocks, bits_d.data_ptr(), e_d.data_ptr())
+    ctx.synchronize()
+    assert np.array_equal(e_d.cpu().numpy(), np.concatenate(want))
+    # round trip: encode 64 blocks of K = 6144 on the device (rv 0, whole circular buffer in natural order is not what
+    # the selection gives, so go through the rate de-matcher), decode, compare
+    K, n = 6144, 64
+    bits = rng.integers(0, 2, (n, K), dtype=np.uint8)
+    N = 3 * K + 12
+    bd = torch.from_numpy(bits.reshape(-1)).cuda()
+    ed = torch.zeros(n * N, dtype=torch.uint8, device="cuda")
+    ctx.tcod_rm_tx_batch_dev([(K, 0, N, i * K, i * N) for i in range(n)], bd.data_ptr(), ed.data_ptr())
+    llr = ((ed.to(torch.int16) * 2 - 1) * 100).contiguous()
+    wl = 18624
+    work = torch.zeros((n, wl), dtype=torch.int16, device="cuda")
+    ctx.rm_rx_batch_dev([(K, 0, i * N, N, i * wl) for i in range(n)], llr.data_ptr(), work.data_ptr())
+    ctx.synchronize()
+    got, _, _ = ctx.tdec_batch_host(work.cpu().numpy(), K, 2, natural=False)
+    assert np.array_equal(got, np.packbits(bits, axis=1))
