@@ -1191,55 +1191,76 @@ struct GenRaw {
   uint32_t x, y, ap;
 };
 
-// the three words trellis row k needs (k >= K: tail rows, no a-priori)
-__device__ __forceinline__ GenRaw gen_load(const GenCtx& c, bool dec2, int k)
+// the three words of trellis row k < K; r3 = 3 * stride is loop invariant, so a group of 4 rows costs one multiply
+__device__ __forceinline__ GenRaw gen_load(const GenCtx& c, bool dec2, uint32_t k, uint32_t r3)
 {
-  GenRaw         r;
-  const uint32_t uk = (uint32_t)k, K = (uint32_t)c.K;  // 32-bit index arithmetic: an item is at most 1212 x 32 words
-  if (uk >= K) {
-    const uint32_t t = (dec2 ? 6u : 0u) + 2 * (uk - K);
-    r.x  = c.in[(3 * K + t) * c.stride];
-    r.y  = c.in[(3 * K + t + 1) * c.stride];
-    r.ap = 0;
-  } else if (!dec2) {
-    r.x  = c.in[(3 * uk) * c.stride];
-    r.y  = c.in[(3 * uk + 1) * c.stride];
-    r.ap = c.A[uk * 32];
+  GenRaw r;
+  if (!dec2) {
+    r.x  = c.in[k * r3];
+    r.y  = c.in[k * r3 + c.stride];
+    r.ap = c.A[k * 32];
   } else {
-    r.x  = c.E[(uint32_t)c.pi[uk] * 32];
-    r.y  = c.in[(3 * uk + 2) * c.stride];
+    r.x  = c.E[(uint32_t)c.pi[k] * 32];
+    r.y  = c.in[k * r3 + 2 * c.stride];
     r.ap = 0;
   }
   return r;
 }
 
+// K is a multiple of 8 for every LTE block size: the K rows split into whole groups of 4, the 3 tail rows are peeled
 __device__ void gen_half_iteration(const GenCtx& c, bool dec2)
 {
-  const int K = c.K;
-  uint32_t  s[8];
+  const uint32_t K = (uint32_t)c.K, r3 = 3 * c.stride;
+  uint32_t       s[8];
   s[0] = 0;
 #pragma unroll
   for (int i = 1; i < 8; i++) s[i] = kNegInf2;
   GenRaw cur[4], nxt[4];
-  // ---- beta over rows K+2 .. 0, four at a time ----
 #pragma unroll
-  for (int j = 0; j < 4; j++) cur[j] = gen_load(c, dec2, max(K + 2 - j, 0));
-  for (int k0 = K + 2; k0 >= 0; k0 -= 4) {
+  for (int j = 0; j < 4; j++) cur[j] = gen_load(c, dec2, K - 1 - j, r3);
+  // ---- beta: the 3 tail rows K+2 .. K (no a-priori, no normalisation) ----
+  {
+    const uint32_t* tl = c.in + (3 * K + (dec2 ? 6u : 0u)) * c.stride;
+    uint32_t        tx[3], ty[3];
 #pragma unroll
-    for (int j = 0; j < 4; j++) nxt[j] = gen_load(c, dec2, max(k0 - 4 - j, 0));
+    for (int r = 0; r < 3; r++) {
+      tx[r] = tl[(2 * r) * c.stride];
+      ty[r] = tl[(2 * r + 1) * c.stride];
+    }
+#pragma unroll
+    for (int r = 2; r >= 0; r--) {
+      beta_step<true>(s, tx[r], ty[r], wadd2(tx[r], ty[r]));
+      c.beta[((K + r) * 2 + 0) * 32] = make_uint4(s[0], s[1], s[2], s[3]);
+      c.beta[((K + r) * 2 + 1) * 32] = make_uint4(s[4], s[5], s[6], s[7]);
+    }
+  }
+  // ---- beta over rows K-1 .. 0, four at a time; the rows of the next TWO groups are in flight (a beta step is
+  // short, two groups of arithmetic do not cover a trip to L2) ----
+  GenRaw nx2[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) nxt[j] = gen_load(c, dec2, K >= 8 ? K - 5 - j : (uint32_t)j, r3);
+  for (uint32_t k0 = K - 1;; k0 -= 4) {
+    const bool more = k0 >= 7;
+    if (k0 >= 11) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) nx2[j] = gen_load(c, dec2, k0 - 8 - j, r3);
+    }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const int k = k0 - j;
-      if (k < 0) break;
+      const uint32_t k = k0 - j;
       const uint32_t x = dec2 ? cur[j].x : wadd2(cur[j].x, cur[j].ap);  // the a-priori array is all zero at first
       const uint32_t y = cur[j].y;
       beta_step<true>(s, x, y, wadd2(x, y));
-      c.beta[((uint32_t)k * 2 + 0) * 32] = make_uint4(s[0], s[1], s[2], s[3]);
-      c.beta[((uint32_t)k * 2 + 1) * 32] = make_uint4(s[4], s[5], s[6], s[7]);
-      if ((k % 4) == 0 && k < K) normalize<true>(s);
+      c.beta[(k * 2 + 0) * 32] = make_uint4(s[0], s[1], s[2], s[3]);
+      c.beta[(k * 2 + 1) * 32] = make_uint4(s[4], s[5], s[6], s[7]);
+      if (j == 3) normalize<true>(s);  // k % 4 == 0 (k0 = 3 mod 4)
     }
+    if (!more) break;
 #pragma unroll
-    for (int j = 0; j < 4; j++) cur[j] = nxt[j];
+    for (int j = 0; j < 4; j++) {
+      cur[j] = nxt[j];
+      nxt[j] = nx2[j];
+    }
   }
   // ---- alpha + output over steps 1 .. K (step k uses row k-1 and beta[k]) ----
   s[0] = 0;
@@ -1250,34 +1271,37 @@ __device__ void gen_half_iteration(const GenCtx& c, bool dec2)
   unused.reset();
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    cur[j] = gen_load(c, dec2, min(j, K - 1));
-    bcur[j][0] = c.beta[((uint32_t)min(1 + j, K) * 2 + 0) * 32];
-    bcur[j][1] = c.beta[((uint32_t)min(1 + j, K) * 2 + 1) * 32];
+    cur[j]     = gen_load(c, dec2, (uint32_t)j, r3);
+    bcur[j][0] = c.beta[((1 + j) * 2 + 0) * 32];
+    bcur[j][1] = c.beta[((1 + j) * 2 + 1) * 32];
   }
-  for (int k0 = 1; k0 <= K; k0 += 4) {
+  for (uint32_t k0 = 1;; k0 += 4) {  // steps k0 .. k0+3
+    const bool more = k0 + 4 <= K;
+    if (more) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      nxt[j] = gen_load(c, dec2, min(k0 + 3 + j, K - 1));
-      bnxt[j][0] = c.beta[((uint32_t)min(k0 + 4 + j, K) * 2 + 0) * 32];
-      bnxt[j][1] = c.beta[((uint32_t)min(k0 + 4 + j, K) * 2 + 1) * 32];
+      for (int j = 0; j < 4; j++) {
+        nxt[j]     = gen_load(c, dec2, k0 + 3 + j, r3);
+        bnxt[j][0] = c.beta[((k0 + 4 + j) * 2 + 0) * 32];
+        bnxt[j][1] = c.beta[((k0 + 4 + j) * 2 + 1) * 32];
+      }
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const int k = k0 + j;
-      if (k > K) break;
+      const uint32_t k   = k0 + j;
       const uint32_t aux = dec2 ? cur[j].x : cur[j].ap;
       const uint32_t x   = dec2 ? cur[j].x : wadd2(cur[j].x, cur[j].ap);
       const uint32_t y   = cur[j].y;
       const uint32_t bb[8] = {bcur[j][0].x, bcur[j][0].y, bcur[j][0].z, bcur[j][0].w,
                               bcur[j][1].x, bcur[j][1].y, bcur[j][1].z, bcur[j][1].w};
       const uint32_t o = alpha_out_step<true, false>(s, bb, x, y, wadd2(x, y), unused);
-      if ((k % 4) == 0) normalize<true>(s);
+      if (j == 3) normalize<true>(s);  // k % 4 == 0 (k0 = 1 mod 4)
       const uint32_t d = wsub2(o, aux);
       if (!dec2)
-        c.E[(uint32_t)(k - 1) * 32] = d;
+        c.E[(k - 1) * 32] = d;
       else
         c.A[(uint32_t)c.pi[k - 1] * 32] = d;
     }
+    if (!more) break;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       cur[j]     = nxt[j];
