@@ -143,6 +143,27 @@ SRSLTE_B200_API int srslte_b200_rm_rx_batch_dev(srslte_b200_ctx_t* ctx, const sr
  * (call sites lib/src/phy/phch/pdsch.c:760-779, pusch.c:482-500), seq = srslte_sequence_LTE_pr(len, c_init)
  * (lib/src/phy/common/sequence.c:123-136).  Bit-exact with the reference's AVX2/SSE build while
  * |scale * x| < 32768 (the reference's out-of-range float -> short conversions are undefined behaviour).      */
+/* UCI multiplexed with the UL-SCH data (36.212 5.2.2.6 - 5.2.2.8), as far as it shapes the DATA path of
+ * srslte_ulsch_decode (sch.c:920-1064).  Decoding the ACK / RI / CQI values themselves (uci.c) is control-plane work
+ * and stays with the caller: it reads the LLRs of the plain call (ul_nof_symb = 0) at the positions of
+ * uci_ulsch_interleave_ack_gen / _ri_gen, and the first Q'_cqi * qm entries of the de-multiplexed output.
+ *   q_prime_ack  coded HARQ-ACK symbols: they puncture the data, their LLRs are erased (sch.c:961-964)
+ *   q_prime_ri   coded RI symbols: the de-interleaver skips them (ulsch_interleave_gen, sch.c:580-598).  The reference
+ *                scatters every RI sample to g[0] (lut = 0 through srslte_vec_lut_sis, sch.c:589-590, 910), so g[0]
+ *                ends up holding the RI sample with the highest channel position; that is reproduced
+ *   q_prime_cqi  coded CQI symbols at the head of the UL-SCH order: the data starts q_prime_cqi * qm LLRs in
+ *   ri_len       1 or 2 RI payload bits (cfg->uci_cfg.cqi.ri_len); the 1-bit RI decoder flips one LLR per RI symbol
+ *                back in place (decode_ri_ack_1bit, uci.c:627-628), which is visible through g[0] for QPSK
+ * The counts are srslte_b200_uci_q_prime_ri_ack / _cqi below (= Q_prime_ri_ack / Q_prime_cqi, uci.c:266-283, 547-571). */
+typedef struct {
+  uint32_t q_prime_ack, q_prime_ri, q_prime_cqi, ri_len;
+} srslte_b200_ul_uci_t;
+/* O payload bits, K_segm = C1*K1 + C2*K2 of the transport block (> 0), beta from 36.213 tables 8.6.3-1/2/3 */
+SRSLTE_B200_API uint32_t srslte_b200_uci_q_prime_ri_ack(uint32_t O, uint32_t K_segm, uint32_t L_prb, uint32_t nof_symb,
+                                                        float beta);
+SRSLTE_B200_API uint32_t srslte_b200_uci_q_prime_cqi(uint32_t O, uint32_t K_segm, uint32_t L_prb, uint32_t nof_symb,
+                                                     float beta, uint32_t q_prime_ri);
+
 typedef struct {
   uint32_t qm;          /* bits per symbol: 2 QPSK, 4 16QAM, 6 64QAM, 8 256QAM (srslte_mod_t 1..4)                 */
   uint32_t nof_symbols; /* cfg->grant.nof_re                                                                        */
@@ -152,12 +173,15 @@ typedef struct {
   uint64_t llr_offset;  /* first LLR of the codeword in `e` (int16); unused by the fused entry                      */
   uint32_t ul_nof_symb; /* 0: PDSCH.  PUSCH: cfg->grant.nof_symb (N_pusch_symbs): the outputs are additionally put in
                          * UL-SCH order by the channel de-interleaver of 36.212 5.2.2.8 (ulsch_deinterleave,
-                         * sch.c:891-918) -- data only: no RI / ACK / CQI multiplexed; nof_bits must be
-                         * qm * nof_symbols and a multiple of qm * ul_nof_symb                                       */
+                         * sch.c:891-918); nof_bits must be qm * nof_symbols and a multiple of qm * ul_nof_symb     */
   uint32_t reserved;    /* 0 */
+  srslte_b200_ul_uci_t uci; /* control information multiplexed into the PUSCH codeword; all 0: none                */
 } srslte_b200_codeword_t;
 
-/* e[cw.llr_offset + j] = descrambled LLR j of codeword cw, j < qm * nof_symbols.  symbols, e: device memory. */
+/* e[cw.llr_offset + j] = descrambled LLR j of codeword cw, j < qm * nof_symbols.  symbols, e: device memory.
+ * With ul_nof_symb and uci: e is the reference's g_bits array after srslte_ulsch_decode's de-multiplexing
+ * (sch.c:1028-1035): (H' - Q'_ri) * qm entries, the CQI LLRs first (Q'_cqi * qm of them, as received), then the data
+ * with the ACK positions erased; the remaining Q'_ri * qm entries (stale memory in the reference) are 0.        */
 SRSLTE_B200_API int srslte_b200_demod_descramble_dev(srslte_b200_ctx_t* ctx, const srslte_b200_codeword_t* cws,
                                                      uint32_t n_cw, const float* symbols, int16_t* e);
 
@@ -230,11 +254,13 @@ typedef struct {
   uint32_t     tbs;            /* transport block size in bits                                        */
   uint32_t     qm;             /* modulation bits per symbol: 2, 4, 6, 8 (one layer)                  */
   uint32_t     rv;
-  uint32_t     nof_e_bits;     /* G = grant.tb[].nof_bits (<= qm * nof_symbols): descrambled + decoded */
+  uint32_t     nof_e_bits;     /* grant.tb[].nof_bits (<= qm * nof_symbols): descrambled; with uci the decoded
+                                * data bits are nof_e_bits - (q_prime_ri + q_prime_cqi) * qm (sch.c:1061-1062) */
   uint32_t     softbuffer;
   uint32_t     nof_symbols;    /* grant.nof_re                                                        */
   uint32_t     c_init;         /* scrambling seed of (rnti, codeword, subframe, cell)                 */
-  uint32_t     ul_nof_symb;    /* 0 for PDSCH; PUSCH: N_pusch_symbs (UL-SCH de-interleaver, no UCI)     */
+  uint32_t     ul_nof_symb;    /* 0 for PDSCH; PUSCH: N_pusch_symbs (UL-SCH de-interleaver)           */
+  srslte_b200_ul_uci_t uci;    /* PUSCH: multiplexed control information, all 0 for none              */
   const float* symbols;        /* host: nof_symbols complex floats (re, im)                           */
   uint8_t*     data;           /* host: decoded TB, at least tbs/8 + 6 bytes                          */
   int32_t      ret;            /* out: as srslte_b200_tb_t                                            */

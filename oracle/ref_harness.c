@@ -293,3 +293,90 @@ int refh_ulsch_deinterleave(const int16_t* q, uint32_t Qm, uint32_t H_prime_tota
   free(lut);
   return 0;
 }
+
+/* ---- UL-SCH with multiplexed UCI: the reference's own srslte_ulsch_encode / srslte_ulsch_decode (sch.c:1013-1232) ----
+ * u[12] = { tbs, qm, rv, nb_q (= Qm * nof_re), L_prb, nof_symb, nof_ack, ri_len, cqi_mode (0 none, 1 wideband = 4 bits,
+ *           2 higher-layer sub-band with N = 9 = 22 bits -> the "long" CQI branch), I_offset_ack, I_offset_ri, I_offset_cqi } */
+#include "srslte/phy/phch/pusch_cfg.h"
+static void fill_ul_cfg(refh_tb_t* t, srslte_pusch_cfg_t* c, const uint32_t* u, int tx)
+{
+  memset(c, 0, sizeof(*c));
+  c->grant.tb.mod      = u[1] == 2 ? SRSLTE_MOD_QPSK : u[1] == 4 ? SRSLTE_MOD_16QAM : SRSLTE_MOD_64QAM;
+  c->grant.tb.tbs      = (int)u[0];
+  c->grant.tb.rv       = (int)u[2];
+  c->grant.tb.nof_bits = u[3];
+  c->grant.tb.enabled  = true;
+  c->grant.L_prb       = u[4];
+  c->grant.nof_symb    = u[5];
+  c->grant.nof_re      = u[3] / u[1];
+  c->uci_cfg.ack[0].nof_acks = u[6];
+  c->uci_cfg.cqi.ri_len      = u[7];
+  if (u[8]) {
+    c->uci_cfg.cqi.data_enable = true;
+    c->uci_cfg.cqi.type        = u[8] == 1 ? SRSLTE_CQI_TYPE_WIDEBAND : SRSLTE_CQI_TYPE_SUBBAND_HL;
+    c->uci_cfg.cqi.N           = 9;
+  }
+  c->uci_offset.I_offset_ack = u[9];
+  c->uci_offset.I_offset_ri  = u[10];
+  c->uci_offset.I_offset_cqi = u[11];
+  if (tx)
+    c->softbuffers.tx = &t->sb_tx;
+  else
+    c->softbuffers.rx = &t->sb_rx;
+}
+
+/* data: tbs/8 bytes; q_bits: nb_q unpacked bits out (placeholder / repetition positions of ACK and RI hold whatever
+ * the encoder left there: pusch.c resolves them while scrambling, the data path does not depend on them) */
+int refh_ulsch_encode(refh_tb_t* t, const uint32_t* u, const uint8_t* data, const uint8_t* ack, uint32_t ri, uint8_t* q_bits)
+{
+  srslte_pusch_cfg_t c;
+  srslte_uci_value_t v;
+  fill_ul_cfg(t, &c, u, 1);
+  memset(&v, 0, sizeof(v));
+  for (uint32_t i = 0; i < u[6] && i < SRSLTE_UCI_MAX_ACK_BITS; i++) v.ack.ack_value[i] = ack[i];
+  v.ri = (uint8_t)ri;
+  v.cqi.subband_hl.wideband_cqi_cw0     = 11;
+  v.cqi.subband_hl.subband_diff_cqi_cw0 = 0x2a5a5;
+  uint8_t* g = (uint8_t*)calloc(u[3] / 8 + 64, 1);
+  uint8_t* q = (uint8_t*)calloc(u[3] / 8 + 64, 1);
+  uint8_t* d = (uint8_t*)calloc(u[0] / 8 + 64, 1);
+  memcpy(d, data, u[0] / 8);
+  if (u[2] == 0) srslte_softbuffer_tx_reset_tbs(&t->sb_tx, u[0]);
+  int rc = srslte_ulsch_encode(&t->sch, &c, d, &v, g, q);
+  if (rc >= 0) srslte_bit_unpack_vector(q, q_bits, (int)u[3]); /* returns the number of ACK + RI bits */
+  free(g);
+  free(q);
+  free(d);
+  return rc;
+}
+
+/* q_llr: nb_q descrambled LLRs (copied; the reference modifies them); c_seq: the scrambling bits, one per byte;
+ * g_out: nb_q de-interleaved LLRs; out: tbs/8 + 8 bytes; uci_out[4] = { ack0, ack1, ri, cqi crc ok } */
+int refh_ulsch_decode(refh_tb_t* t, const uint32_t* u, const int16_t* q_llr, const uint8_t* c_seq, int16_t* g_out,
+                      uint8_t* out, uint32_t max_it, float* avg_it, uint8_t* uci_out)
+{
+  srslte_pusch_cfg_t c;
+  srslte_uci_value_t v;
+  fill_ul_cfg(t, &c, u, 0);
+  memset(&v, 0, sizeof(v));
+  int16_t* q = (int16_t*)srslte_vec_malloc(sizeof(int16_t) * (u[3] + 64));
+  int16_t* g = (int16_t*)srslte_vec_malloc(sizeof(int16_t) * (u[3] + 64));
+  uint8_t* s = (uint8_t*)malloc(u[3] + 64);
+  memcpy(q, q_llr, sizeof(int16_t) * u[3]);
+  memset(g, 0, sizeof(int16_t) * (u[3] + 64));
+  memcpy(s, c_seq, u[3]);
+  srslte_sch_set_max_noi(&t->sch, max_it);
+  int rc = srslte_ulsch_decode(&t->sch, &c, q, g, s, out, &v);
+  if (avg_it) *avg_it = srslte_sch_last_noi(&t->sch);
+  memcpy(g_out, g, sizeof(int16_t) * u[3]);
+  if (uci_out) {
+    uci_out[0] = v.ack.ack_value[0];
+    uci_out[1] = v.ack.ack_value[1];
+    uci_out[2] = v.ri;
+    uci_out[3] = v.cqi.data_crc;
+  }
+  free(q);
+  free(g);
+  free(s);
+  return rc;
+}

@@ -994,6 +994,92 @@ int port_demod_descramble(int qm, const float* sym, uint32_t nsym, uint32_t c_in
   return 0;
 }
 
+/* ---- UL-SCH with multiplexed UCI (36.212 5.2.2.6 - 5.2.2.8): what srslte_ulsch_decode does to the LLRs before
+ * decode_tb sees them (lib/src/phy/phch/sch.c:920-1064).  Only the DATA path is restated: the values of the ACK /
+ * RI / CQI bits themselves are control information and stay with the reference's uci.c. ---- */
+
+/* number of coded ACK or RI symbols: Q_prime_ri_ack, lib/src/phy/phch/uci.c:547-571, with K = cfg->K_segm > 0 */
+uint32_t port_uci_q_prime_ri_ack(uint32_t O, uint32_t K_segm, uint32_t L_prb, uint32_t nof_symb, float beta)
+{
+  const uint32_t x = (uint32_t)ceilf((float)O * L_prb * 12 * nof_symb * beta / K_segm);
+  const uint32_t m = 4 * L_prb * 12;
+  return x < m ? x : m;
+}
+
+/* number of coded CQI symbols: Q_prime_cqi, lib/src/phy/phch/uci.c:266-283 (L = 8 CRC bits from 11 payload bits on) */
+uint32_t port_uci_q_prime_cqi(uint32_t O, uint32_t K_segm, uint32_t L_prb, uint32_t nof_symb, float beta, uint32_t q_prime_ri)
+{
+  const uint32_t L = O < 11 ? 0 : 8;
+  uint32_t       x = 999999;
+  if (K_segm > 0) x = (uint32_t)ceilf((float)(O + L) * L_prb * 12 * nof_symb * beta / K_segm);
+  const uint32_t m = L_prb * 12 * nof_symb - q_prime_ri;
+  return x < m ? x : m;
+}
+
+/* position in q of bit k of coded ACK / RI symbol number idx: uci_ulsch_interleave_ack_gen / _ri_gen,
+ * lib/src/phy/phch/uci.c:497-545 (bottom rows of the interleaver matrix, columns next to the reference symbols).
+ * Returns -1 where the reference reports an error (more symbols than 4 per matrix row allow). */
+static int port_uci_position(int is_ri, uint32_t idx, uint32_t Qm, uint32_t H_prime_total, uint32_t N_pusch_symbs,
+                             uint32_t k, uint32_t* pos)
+{
+  static const uint32_t ack_norm[4] = {2, 3, 8, 9}, ack_ext[4] = {1, 2, 6, 7};
+  static const uint32_t ri_norm[4] = {1, 4, 7, 10}, ri_ext[4] = {0, 3, 5, 8};
+  const uint32_t rows = H_prime_total / N_pusch_symbs;
+  if (rows < 1 + idx / 4) return -1;
+  const uint32_t row = rows - 1 - idx / 4, colidx = (3 * idx) % 4;
+  const uint32_t col = N_pusch_symbs > 10 ? (is_ri ? ri_norm : ack_norm)[colidx] : (is_ri ? ri_ext : ack_ext)[colidx];
+  *pos = row * Qm + rows * col * Qm + k;
+  return 0;
+}
+
+/* q (descrambled LLRs, channel order, H' * Qm of them; NOT modified here) -> g (UL-SCH order), the sequence of
+ * lib/src/phy/phch/sch.c:940-1035:
+ *   1. the Q'_ack * Qm ACK positions are erased (q = 0, :961-964);
+ *   2. a 1-bit RI decode flips q[p1] of every RI symbol back where c[p1] = 1 (decode_ri_ack_1bit, uci.c:622-634);
+ *      the 2-bit decode does not write (uci.c:636-649);
+ *   3. ulsch_deinterleave (:891-918): lut[x] = running index over the non-RI positions in row-major order, 0 for the
+ *      RI positions (ulsch_interleave_gen :580-598), then srslte_vec_lut_sis g[lut[x]] = q[x] for x ascending -- so
+ *      every RI sample is written to g[0] and the last writer in x order wins.
+ * g has (H' - Q'_ri) * Qm defined entries; the rest is left untouched (stale in the reference).
+ * Returns 0, or -1 where the reference fails.                                                                  */
+int port_ulsch_demux(const int16_t* q_in, const uint8_t* c_seq, uint32_t Qm, uint32_t H_prime_total, uint32_t N_pusch_symbs,
+                     uint32_t q_prime_ack, uint32_t q_prime_ri, uint32_t ri_len, int16_t* g)
+{
+  const uint32_t n = H_prime_total * Qm, rows = H_prime_total / N_pusch_symbs, cols = N_pusch_symbs;
+  int16_t*       q = (int16_t*)malloc(sizeof(int16_t) * (n + 1));
+  uint8_t*       ri_present = (uint8_t*)calloc(n + 1, 1);
+  uint32_t*      lut = (uint32_t*)calloc(n + 1, sizeof(uint32_t));
+  int            rc = 0;
+  memcpy(q, q_in, sizeof(int16_t) * n);
+  for (uint32_t i = 0; i < q_prime_ack && !rc; i++)
+    for (uint32_t k = 0; k < Qm; k++) {
+      uint32_t pos;
+      if (port_uci_position(0, i, Qm, H_prime_total, N_pusch_symbs, k, &pos)) { rc = -1; break; }
+      q[pos] = 0;
+    }
+  for (uint32_t i = 0; i < q_prime_ri && !rc; i++)
+    for (uint32_t k = 0; k < Qm; k++) {
+      uint32_t pos;
+      if (port_uci_position(1, i, Qm, H_prime_total, N_pusch_symbs, k, &pos)) { rc = -1; break; }
+      ri_present[pos] = 1;
+      if (ri_len == 1 && k == 1 && c_seq[pos]) q[pos] = (int16_t)(-q[pos]);
+    }
+  if (!rc) {
+    uint32_t idx = 0;
+    for (uint32_t j = 0; j < rows; j++)
+      for (uint32_t i = 0; i < cols; i++)
+        for (uint32_t k = 0; k < Qm; k++) {
+          const uint32_t x = j * Qm + i * rows * Qm + k;
+          lut[x] = ri_present[x] ? 0 : idx++;
+        }
+    for (uint32_t x = 0; x < n; x++) g[lut[x]] = q[x];
+  }
+  free(q);
+  free(ri_present);
+  free(lut);
+  return rc;
+}
+
 /* UL-SCH channel de-interleaver of 36.212 5.2.2.8 without multiplexed UCI (no RI / ACK / CQI):
  * reference ulsch_deinterleave + ulsch_interleave_gen, lib/src/phy/phch/sch.c:580-598, 891-918:
  * lut[(i*rows + j)*Qm + k] = (j*cols + i)*Qm + k,  g[lut[x]] = q[x].                                         */

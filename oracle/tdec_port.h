@@ -112,6 +112,11 @@ int  port_demod_s(int qm, const float* sym, int16_t* llr, uint32_t nsym);
 /* srslte_scrambling_s_offset (scrambling.c:44-47) */
 void port_descramble_s(int16_t* llr, const uint8_t* c, uint32_t len);
 /* the two in the order of pdsch.c:760-779 / pusch.c:482-500 */
+/* UL-SCH with multiplexed UCI, data path only (sch.c:920-1064, uci.c:266-283, 497-571) */
+uint32_t port_uci_q_prime_ri_ack(uint32_t O, uint32_t K_segm, uint32_t L_prb, uint32_t nof_symb, float beta);
+uint32_t port_uci_q_prime_cqi(uint32_t O, uint32_t K_segm, uint32_t L_prb, uint32_t nof_symb, float beta, uint32_t q_prime_ri);
+int port_ulsch_demux(const int16_t* q, const uint8_t* c_seq, uint32_t Qm, uint32_t H_prime_total, uint32_t N_pusch_symbs,
+                     uint32_t q_prime_ack, uint32_t q_prime_ri, uint32_t ri_len, int16_t* g);
 /* ulsch_deinterleave without UCI (sch.c:580-598, 891-918) */
 void port_ulsch_deinterleave(const int16_t* q, uint32_t Qm, uint32_t H_prime_total, uint32_t N_pusch_symbs, int16_t* g);
 int  port_demod_descramble(int qm, const float* sym, uint32_t nsym, uint32_t c_init, uint32_t nof_bits, int16_t* llr);

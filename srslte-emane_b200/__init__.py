@@ -34,10 +34,21 @@ class RmBlock(C.Structure):
                 ("work_offset", C.c_uint32)]
 
 
+class UlUci(C.Structure):
+    """srslte_b200_ul_uci_t: UCI multiplexed into a PUSCH codeword (data-path view)."""
+    _fields_ = [("q_prime_ack", C.c_uint32), ("q_prime_ri", C.c_uint32), ("q_prime_cqi", C.c_uint32),
+                ("ri_len", C.c_uint32)]
+
+
+def _uci(d):
+    u = d.get("uci") or {}
+    return UlUci(u.get("q_prime_ack", 0), u.get("q_prime_ri", 0), u.get("q_prime_cqi", 0), u.get("ri_len", 0))
+
+
 class Codeword(C.Structure):
     _fields_ = [("qm", C.c_uint32), ("nof_symbols", C.c_uint32), ("c_init", C.c_uint32), ("nof_bits", C.c_uint32),
                 ("sym_offset", C.c_uint64), ("llr_offset", C.c_uint64), ("ul_nof_symb", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("reserved", C.c_uint32), ("uci", UlUci)]
 
 
 class RmSymBlock(C.Structure):
@@ -59,7 +70,8 @@ class TxBlock(C.Structure):
 class TbSymDesc(C.Structure):
     _fields_ = [("tbs", C.c_uint32), ("qm", C.c_uint32), ("rv", C.c_uint32), ("nof_e_bits", C.c_uint32),
                 ("softbuffer", C.c_uint32), ("nof_symbols", C.c_uint32), ("c_init", C.c_uint32),
-                ("ul_nof_symb", C.c_uint32), ("symbols", C.c_void_p), ("data", C.c_void_p), ("ret", C.c_int32), ("avg_iterations", C.c_float)]
+                ("ul_nof_symb", C.c_uint32), ("uci", UlUci), ("symbols", C.c_void_p), ("data", C.c_void_p),
+                ("ret", C.c_int32), ("avg_iterations", C.c_float)]
 
 
 EXPORTS = [
@@ -72,6 +84,7 @@ EXPORTS = [
     "srslte_b200_demod_descramble_dev", "srslte_b200_demod_rm_rx_batch_dev", "srslte_b200_tcod_rm_tx_batch_dev",
     "srslte_b200_harq_pool_create", "srslte_b200_harq_pool_destroy", "srslte_b200_harq_reset",
     "srslte_b200_harq_cb_crc", "srslte_b200_decode_tb_batch", "srslte_b200_decode_tb_sym_batch",
+    "srslte_b200_uci_q_prime_ri_ack", "srslte_b200_uci_q_prime_cqi",
 ]
 
 _lib = None
@@ -124,6 +137,10 @@ def lib():
     L.srslte_b200_harq_cb_crc.argtypes = [vp, u32, vp, u32]
     L.srslte_b200_decode_tb_batch.argtypes = [vp, vp, C.POINTER(TbDesc), u32, u32]
     L.srslte_b200_decode_tb_sym_batch.argtypes = [vp, vp, C.POINTER(TbSymDesc), u32, u32]
+    L.srslte_b200_uci_q_prime_ri_ack.argtypes = [u32, u32, u32, u32, C.c_float]
+    L.srslte_b200_uci_q_prime_ri_ack.restype = u32
+    L.srslte_b200_uci_q_prime_cqi.argtypes = [u32, u32, u32, u32, C.c_float, u32]
+    L.srslte_b200_uci_q_prime_cqi.restype = u32
     _lib = L
     return L
 
@@ -291,7 +308,8 @@ class Context:
         return [(int(arr[i].ret), outs[i], float(arr[i].avg_iterations)) for i in range(n)]
 
     def decode_tb_sym_batch(self, pool, tbs, max_iterations):
-        """tbs: list of dicts(tbs, qm, rv, nof_e_bits, softbuffer, c_init, symbols=complex64 array).
+        """tbs: list of dicts(tbs, qm, rv, nof_e_bits, softbuffer, c_init, symbols=complex64 array[, ul_nof_symb,
+        uci=dict(q_prime_ack, q_prime_ri, q_prime_cqi, ri_len)]).
         Returns [(ret, data bytes, avg_iterations)] like decode_tb_batch."""
         n = len(tbs)
         arr = (TbSymDesc * n)()
@@ -302,7 +320,7 @@ class Context:
             keep.append(sym)
             outs.append(out)
             arr[i] = TbSymDesc(d["tbs"], d["qm"], d["rv"], d["nof_e_bits"], d["softbuffer"], sym.shape[0], d["c_init"],
-                               d.get("ul_nof_symb", 0), sym.ctypes.data, out.ctypes.data, 0, 0.0)
+                               d.get("ul_nof_symb", 0), _uci(d), sym.ctypes.data, out.ctypes.data, 0, 0.0)
         rc = self._L.srslte_b200_decode_tb_sym_batch(self._h, pool._p, arr, n, max_iterations)
         self._check(rc, "srslte_b200_decode_tb_sym_batch")
         return [(int(arr[i].ret), outs[i], float(arr[i].avg_iterations)) for i in range(n)]
@@ -330,7 +348,7 @@ class Context:
         arr = (Codeword * len(cws))()
         for i, c in enumerate(cws):
             arr[i] = Codeword(c["qm"], c["nof_symbols"], c["c_init"], c.get("nof_bits", c["qm"] * c["nof_symbols"]),
-                              c.get("sym_offset", 0), c.get("llr_offset", 0), c.get("ul_nof_symb", 0), 0)
+                              c.get("sym_offset", 0), c.get("llr_offset", 0), c.get("ul_nof_symb", 0), 0, _uci(c))
         return arr
 
     def demod_descramble_dev(self, cws, symbols_ptr, e_ptr):

@@ -861,6 +861,33 @@ static int fe_prepare(srslte_b200_ctx_t* ctx, const srslte_b200_codeword_t* cws,
                     "codeword %u: UL-SCH de-interleaving needs nof_bits = qm * nof_symbols, a multiple of qm * ul_nof_symb", i);
       f.ul_rows = c.nof_bits / c.qm / c.ul_nof_symb;
     }
+    f.q_ack = f.q_ri = f.g0_raw = 0;
+    f.g0_src = kNoG0;
+    if (c.uci.q_prime_ack | c.uci.q_prime_ri | c.uci.q_prime_cqi) {
+      // the reference fails where a row of the matrix would need more than its 4 ACK / RI cells (uci.c:504, 529)
+      if (!c.ul_nof_symb || c.ul_nof_symb < 9 || c.uci.q_prime_ack > 4 * f.ul_rows || c.uci.q_prime_ri > 4 * f.ul_rows ||
+          c.uci.q_prime_ri + c.uci.q_prime_cqi > c.nof_symbols)
+        return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "codeword %u: UCI counts do not fit the PUSCH allocation", i);
+      f.q_ack = c.uci.q_prime_ack;
+      f.q_ri  = c.uci.q_prime_ri;
+      if (f.q_ri) {
+        // g[0]: srslte_vec_lut_sis walks the channel positions upwards, every RI position writes g[0], and so does the
+        // first cell that carries no RI; the highest of these positions wins
+        const bool     norm = c.ul_nof_symb > 10;
+        const uint32_t rows = f.ul_rows, last_ri = (uci_col(true, norm, f.q_ri >= 2 ? 3 : 0) * rows + rows - 1) * c.qm + c.qm - 1;
+        uint32_t       first = 0;  // first column of row 0 without RI (row 0 carries RI only when q_ri > 4 (rows - 1))
+        const uint32_t nri_row0 = f.q_ri > 4 * (rows - 1) ? f.q_ri - 4 * (rows - 1) : 0;
+        for (bool moved = true; moved;) {
+          moved = false;
+          for (uint32_t m = 0; m < nri_row0; m++)
+            if (uci_col(true, norm, (3 * m) % 4) == first) { first++; moved = true; }
+        }
+        if (last_ri > first * rows * c.qm) {
+          f.g0_src = last_ri;
+          f.g0_raw = (c.uci.ri_len == 1 && c.qm == 2) ? 1u : 0u;  // bit 1 of the symbol is the repetition bit the 1-bit decoder flips
+        }
+      }
+    }
     ctx->h_cws.p[i] = f;
     mx = std::max(mx, (uint32_t)n);
   }
@@ -868,6 +895,23 @@ static int fe_prepare(srslte_b200_ctx_t* ctx, const srslte_b200_codeword_t* cws,
   CU(cudaEventRecord(ctx->ev_staging, st));
   *max_llr = mx;
   return 0;
+}
+
+// Q_prime_ri_ack (lib/src/phy/phch/uci.c:547-571) and Q_prime_cqi (uci.c:266-283): single-precision like the reference
+uint32_t srslte_b200_uci_q_prime_ri_ack(uint32_t O, uint32_t K_segm, uint32_t L_prb, uint32_t nof_symb, float beta)
+{
+  if (K_segm == 0 || beta < 0) return 0;
+  const uint32_t x = (uint32_t)ceilf((float)O * L_prb * 12 * nof_symb * beta / K_segm);
+  return std::min(x, 4 * L_prb * 12);
+}
+
+uint32_t srslte_b200_uci_q_prime_cqi(uint32_t O, uint32_t K_segm, uint32_t L_prb, uint32_t nof_symb, float beta,
+                                     uint32_t q_prime_ri)
+{
+  if (beta < 0) return 0;
+  uint32_t x = 999999;
+  if (K_segm > 0) x = (uint32_t)ceilf((float)(O + (O < 11 ? 0u : 8u)) * L_prb * 12 * nof_symb * beta / K_segm);
+  return std::min(x, L_prb * 12 * nof_symb - q_prime_ri);
 }
 
 int srslte_b200_demod_descramble_dev(srslte_b200_ctx_t* ctx, const srslte_b200_codeword_t* cws, uint32_t n_cw,
@@ -1108,6 +1152,8 @@ namespace {
 struct TbSymSrc {  // where a transport block's LLRs come from when the caller hands over equalised symbols
   const float* symbols;  // host: nof_symbols complex floats
   uint32_t     nof_symbols, mod_bits, c_init, ul_nof_symb;
+  uint32_t     nof_bits;  // descrambled LLRs of the codeword (data + multiplexed UCI)
+  srslte_b200_ul_uci_t uci;
 };
 }  // namespace
 
@@ -1239,14 +1285,16 @@ static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
         if (!run[i]) continue;
         srslte_b200_codeword_t c{};
         c.qm = sym[i].mod_bits; c.nof_symbols = sym[i].nof_symbols; c.c_init = sym[i].c_init;
-        c.nof_bits = tbs[i].nof_e_bits; c.sym_offset = e_base[i]; c.llr_offset = 0;
+        c.nof_bits = sym[i].nof_bits; c.sym_offset = e_base[i]; c.llr_offset = 0;
         c.ul_nof_symb = sym[i].ul_nof_symb;
+        c.uci = sym[i].uci;
         cw_of[i] = (uint32_t)cws.size();
         cws.push_back(c);
       }
       for (uint32_t j = 0; j < n_cb; j++) {
         bl[j].long_cb = rm[j].long_cb; bl[j].rv = rm[j].rv; bl[j].codeword = cw_of[jobs[j].tb];
-        bl[j].e_offset = jobs[j].rp; bl[j].e_len = rm[j].e_len; bl[j].work_offset = rm[j].work_offset;
+        bl[j].e_offset = jobs[j].rp + sym[jobs[j].tb].uci.q_prime_cqi * sym[jobs[j].tb].mod_bits;  // data follows the CQI
+        bl[j].e_len = rm[j].e_len; bl[j].work_offset = rm[j].work_offset;
       }
       rc = demod_rm_rx_enqueue(ctx, cws.data(), (uint32_t)cws.size(), bl.data(), n_cb,
                                reinterpret_cast<const float*>(pool->d_e.p), pool->llr.p, over.data());
@@ -1356,7 +1404,12 @@ int srslte_b200_decode_tb_sym_batch(srslte_b200_ctx_t* ctx, srslte_b200_harq_poo
   std::vector<TbSymSrc>         src(n_tb);
   for (uint32_t i = 0; i < n_tb; i++) {
     tb[i] = srslte_b200_tb_t{};
-    tb[i].tbs = tbs[i].tbs; tb[i].qm = tbs[i].qm; tb[i].rv = tbs[i].rv; tb[i].nof_e_bits = tbs[i].nof_e_bits;
+    const uint64_t uci_bits = ((uint64_t)tbs[i].uci.q_prime_ri + tbs[i].uci.q_prime_cqi) * tbs[i].qm;
+    if (uci_bits > tbs[i].nof_e_bits)
+      return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "transport block %u: more RI + CQI symbols than coded bits", i);
+    // G = nb_q / Qm - Q'_ri - Q'_cqi symbols of data (sch.c:1061-1062)
+    tb[i].tbs = tbs[i].tbs; tb[i].qm = tbs[i].qm; tb[i].rv = tbs[i].rv; tb[i].nof_e_bits = tbs[i].nof_e_bits - (uint32_t)uci_bits;
+    src[i].nof_bits = tbs[i].nof_e_bits; src[i].uci = tbs[i].uci;
     tb[i].softbuffer = tbs[i].softbuffer; tb[i].e_bits = nullptr; tb[i].data = tbs[i].data;
     src[i].symbols = tbs[i].symbols; src[i].nof_symbols = tbs[i].nof_symbols; src[i].mod_bits = tbs[i].qm;
     src[i].c_init = tbs[i].c_init;

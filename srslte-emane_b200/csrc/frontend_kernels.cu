@@ -27,6 +27,54 @@ constexpr uint32_t kLlrPerThread = 8;
 __device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v)); }
 __device__ __forceinline__ int wrap16(int v) { return (int)(int16_t)v; }
 
+// UL-SCH order -> channel order for a codeword with multiplexed UCI (data path of srslte_ulsch_decode,
+// lib/src/phy/phch/sch.c:920-1064).  The reference marks the Q'_ri * Qm RI positions (uci_ulsch_interleave_ri_gen,
+// uci.c:522-545: symbol idx sits in row rows-1-idx/4, column set[(3 idx) % 4]), numbers the remaining matrix cells in
+// row-major order (ulsch_interleave_gen, sch.c:580-598) and scatters g[lut[x]] = q[x]; here the inverse is closed
+// form: rows above r0 = rows - ceil(Q'_ri / 4) are complete, row r0 misses Q'_ri - 4 (rows-1-r0) cells, the rows below
+// miss 4.  ACK symbols (uci_ulsch_interleave_ack_gen, uci.c:497-520) use the same row rule on their own column set
+// and are erased (sch.c:961-964).  Returns the channel position, kUciErased for an LLR the reference sets to 0 (or
+// never defines: j >= (H' - Q'_ri) Qm), with kUciRaw set when the sample is used without descrambling (g0_raw).
+constexpr uint32_t kUciErased = 0xFFFFFFFFu, kUciRaw = 0x80000000u;
+__device__ __noinline__ uint32_t ul_uci_map(const FeCodeword& cw, uint32_t j, uint32_t qm)
+{
+  const uint32_t rows = cw.ul_rows, cols = cw.ul_cols;
+  const bool     norm = cols > 10;
+  if (j == 0 && cw.g0_src != kNoG0) return cw.g0_src | (cw.g0_raw ? kUciRaw : 0u);
+  const uint32_t v = j / qm, k = j - v * qm;
+  if (v >= rows * cols - cw.q_ri) return kUciErased;
+  const uint32_t ri_rows = (cw.q_ri + 3) / 4, r0 = rows - ri_rows;
+  uint32_t       row, col;
+  if (v < r0 * cols) {
+    row = v / cols;
+    col = v - row * cols;
+  } else {
+    uint32_t       t = v - r0 * cols;
+    const uint32_t nri0 = cw.q_ri - 4 * (ri_rows - 1);  // 1..4 RI cells in the first RI row
+    uint32_t       nri = nri0;
+    row = r0;
+    if (t >= cols - nri0) {
+      t -= cols - nri0;
+      const uint32_t d = t / (cols - 4);
+      row = r0 + 1 + d;
+      t -= d * (cols - 4);
+      nri = 4;
+    }
+    col = t;  // t-th column of the row that carries no RI; symbol 4g + m of a row uses set[(3m) % 4]: m = 0, 1, 2, 3
+              // -> set[0], set[3], set[2], set[1]
+    if (col >= uci_col(true, norm, 0)) col++;
+    if (nri >= 4 && col >= uci_col(true, norm, 1)) col++;
+    if (nri >= 3 && col >= uci_col(true, norm, 2)) col++;
+    if (nri >= 2 && col >= uci_col(true, norm, 3)) col++;
+  }
+  if (cw.q_ack) {
+#pragma unroll
+    for (uint32_t c = 0; c < 4; c++)
+      if (col == uci_col(false, norm, c) && 4 * (rows - 1 - row) + ((4 - c) & 3u) < cw.q_ack) return kUciErased;
+  }
+  return (col * rows + row) * qm + k;
+}
+
 // LLR number j of a codeword (before rate de-matching), descrambled.  QM = bits per symbol, a compile-time constant:
 // the kernels branch once per CTA on the codeword's modulation (no division by a run-time Qm, no per-LLR dispatch).
 template <uint32_t QM>
@@ -34,10 +82,18 @@ __device__ __forceinline__ int fe_llr(const FeCodeword& cw, const float* __restr
                                       const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x2mask)
 {
   constexpr uint32_t qm = QM;
+  bool               raw = false;  // g[0] quirk with a 1-bit RI: the sample is used as demodulated (not descrambled)
   if (cw.ul_cols) {  // j counts in UL-SCH order: vector v = j / qm sits at row v / cols, column v % cols of the
                      // interleaver matrix and was sent as vector column * rows + row
-    const uint32_t v = j / qm, k = j - v * qm, row = v / cw.ul_cols, col = v - row * cw.ul_cols;
-    j = (col * cw.ul_rows + row) * qm + k;
+    if (cw.q_ack | cw.q_ri) {
+      const uint32_t x = ul_uci_map(cw, j, qm);
+      if (x == kUciErased) return 0;
+      raw = (x & kUciRaw) != 0;
+      j   = x & ~kUciRaw;
+    } else {
+      const uint32_t v = j / qm, k = j - v * qm, row = v / cw.ul_cols, col = v - row * cw.ul_cols;
+      j = (col * cw.ul_rows + row) * qm + k;
+    }
   }
   const uint32_t     s = j / qm, r = j - s * qm, lvl = r >> 1;
   const float    x  = __ldg(sym + 2 * (size_t)s + (r & 1u));
@@ -74,7 +130,7 @@ __device__ __forceinline__ int fe_llr(const FeCodeword& cw, const float* __restr
   }
   if (j < cw.nof_bits) {
     const uint32_t c = ((__ldg(x1 + (j >> 5)) >> (j & 31u)) ^ (uint32_t)__popc(__ldg(x2mask + j) & cw.c_init)) & 1u;
-    if (c) v = wrap16(-v);
+    if (c && !raw) v = wrap16(-v);
   }
   return v;
 }

@@ -136,7 +136,21 @@ struct FeCodeword {
   uint32_t ul_cols;   // 0: the LLRs are used in channel order (PDSCH); else N_pusch_symbs: the UL-SCH channel
                       // de-interleaver of 36.212 5.2.2.8 (no UCI) sits between descrambling and rate de-matching
   uint32_t ul_rows;   // nof_bits / qm / ul_cols
+  // UCI multiplexed into the PUSCH codeword (data path of srslte_ulsch_decode, sch.c:920-1064); all 0 without UCI
+  uint32_t q_ack;     // Q'_ack coded HARQ-ACK symbols: their LLRs are erased (sch.c:961-964)
+  uint32_t q_ri;      // Q'_ri coded RI symbols: skipped by the de-interleaver (ulsch_interleave_gen, sch.c:580-598)
+  uint32_t g0_src;    // kNoG0 or the channel position whose LLR the reference leaves in g[0] (every RI sample is
+                      // written to g[0], the last writer wins: srslte_vec_lut_sis over lut = 0, sch.c:589-590, 910)
+  uint32_t g0_raw;    // 1: that LLR was flipped back by the 1-bit RI decoder (decode_ri_ack_1bit, uci.c:627-628)
 };
+constexpr uint32_t kNoG0 = 0xFFFFFFFFu;
+// columns of the interleaver matrix that carry ACK / RI (uci.c:501-502, 526-527); normal CP set when N_pusch_symbs > 10
+__host__ __device__ inline uint32_t uci_col(bool ri, bool norm, uint32_t c)
+{
+  // packed nibbles, entry c at bits 4c
+  const uint32_t t = ri ? (norm ? 0xA741u : 0x8530u) : (norm ? 0x9832u : 0x7621u);
+  return (t >> (4 * c)) & 15u;
+}
 struct RmSymItem {
   uint32_t E, work_off, tab_off, N, wl, overwrite;  // as RmItem
   uint32_t cw;                       // codeword the block belongs to

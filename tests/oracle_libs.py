@@ -96,6 +96,11 @@ def port():
     L.port_demod_descramble.argtypes = [C.c_int, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _i16p]
     L.port_ulsch_deinterleave.argtypes = [_i16p, C.c_uint32, C.c_uint32, C.c_uint32, _i16p]
     L.port_ulsch_deinterleave.restype = None
+    L.port_uci_q_prime_ri_ack.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float]
+    L.port_uci_q_prime_ri_ack.restype = C.c_uint32
+    L.port_uci_q_prime_cqi.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_uint32]
+    L.port_uci_q_prime_cqi.restype = C.c_uint32
+    L.port_ulsch_demux.argtypes = [_i16p, _u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _i16p]
     _port = L
     return L
 
@@ -137,6 +142,8 @@ def ref():
     L.srslte_tdec_autoimp_get_subblocks.restype = C.c_uint32
     L.refh_demod_descramble.argtypes = [C.c_int, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _i16p, C.c_uint32]
     L.refh_ulsch_deinterleave.argtypes = [_i16p, C.c_uint32, C.c_uint32, C.c_uint32, _i16p]
+    L.refh_ulsch_encode.argtypes = [C.c_void_p, _u32p, _u8p, _u8p, C.c_uint32, _u8p]
+    L.refh_ulsch_decode.argtypes = [C.c_void_p, _u32p, _i16p, _u8p, _i16p, _u8p, C.c_uint32, C.POINTER(C.c_float), _u8p]
     L.srslte_rm_turbo_gentables()
     _ref = L
     return L
@@ -243,3 +250,62 @@ def ref_ulsch_deinterleave(q, qm, n_symb):
     g = np.zeros_like(q)
     assert ref().refh_ulsch_deinterleave(q, qm, q.size // qm, n_symb, g) == 0
     return g
+
+
+# ---- UL-SCH with multiplexed UCI (data path; sch.c:920-1064) ------------------------------------------
+# 36.213 tables 8.6.3-1/2/3 as the reference holds them (sch.c:43-52)
+BETA_HARQ = [2.0, 2.5, 3.125, 4.0, 5.0, 6.250, 8.0, 10.0, 12.625, 15.875, 20.0, 31.0, 50.0, 80.0, 126.0, -1.0]
+BETA_RI = [1.25, 1.625, 2.0, 2.5, 3.125, 4.0, 5.0, 6.25, 8.0, 10.0, 12.625, 15.875, 20.0, -1.0, -1.0, -1.0]
+BETA_CQI = [-1.0, -1.0, 1.125, 1.25, 1.375, 1.625, 1.750, 2.0, 2.25, 2.5, 2.875, 3.125, 3.5, 4.0, 5.0, 6.25]
+CQI_LEN = {0: 0, 1: 4, 2: 22}   # cqi_mode of the harness -> payload bits (srslte_cqi_size)
+
+
+def ul_cfg(tbs, qm, rv, nb_q, l_prb, nof_symb, nof_ack=0, ri_len=0, cqi_mode=0, i_ack=5, i_ri=5, i_cqi=7):
+    return np.array([tbs, qm, rv, nb_q, l_prb, nof_symb, nof_ack, ri_len, cqi_mode, i_ack, i_ri, i_cqi], np.uint32)
+
+
+def port_uci_q_primes(u):
+    """(Q'_ack, Q'_ri, Q'_cqi) of an ul_cfg through the port's restatement of uci.c:266-283, 547-571."""
+    P = port()
+    tbs, qm, rv, nb_q, l_prb, nof_symb, nof_ack, ri_len, cqi_mode, i_ack, i_ri, i_cqi = (int(x) for x in u)
+    seg = PortCbsegm()
+    assert P.port_cbsegm(C.byref(seg), tbs) == 0
+    k_segm = seg.C1 * seg.K1 + seg.C2 * seg.K2
+    o_cqi = CQI_LEN[cqi_mode]
+    q_ack = P.port_uci_q_prime_ri_ack(nof_ack, k_segm, l_prb, nof_symb, BETA_HARQ[i_ack]) if nof_ack else 0
+    q_ri = P.port_uci_q_prime_ri_ack(ri_len, k_segm, l_prb, nof_symb, BETA_RI[i_ri]) if ri_len else 0
+    q_cqi = P.port_uci_q_prime_cqi(o_cqi, k_segm, l_prb, nof_symb, BETA_CQI[i_cqi], q_ri) if o_cqi else 0
+    return q_ack, q_ri, q_cqi
+
+
+def port_ulsch_demux(q, c_seq, qm, n_symb, q_ack, q_ri, ri_len):
+    """descrambled LLRs in channel order -> UL-SCH order with ACK erasure and RI skipping (g[0] quirk included);
+    returns the (H' - Q'_ri) * qm defined entries."""
+    q = np.ascontiguousarray(q, np.int16)
+    g = np.zeros_like(q)
+    rc = port().port_ulsch_demux(q, np.ascontiguousarray(c_seq, np.uint8), qm, q.size // qm, n_symb, q_ack, q_ri, ri_len, g)
+    assert rc == 0
+    return g[: q.size - q_ri * qm]
+
+
+def port_ulsch_decode(u, q, c_seq, max_it):
+    """The data path of srslte_ulsch_decode through the port: Q' counts, de-multiplexing, decode_tb on the data part.
+    Returns (ret, bytes[tbs/8 + 3], avg half iterations, g, (Q'_ack, Q'_ri, Q'_cqi))."""
+    P = port()
+    tbs, qm, rv, nb_q, l_prb, nof_symb, nof_ack, ri_len = (int(x) for x in u[:8])
+    q_ack, q_ri, q_cqi = port_uci_q_primes(u)
+    g = port_ulsch_demux(q, c_seq, qm, nof_symb, q_ack, q_ri, ri_len)
+    seg = PortCbsegm()
+    assert P.port_cbsegm(C.byref(seg), tbs) == 0
+    sb = PortSoftbuffer()
+    P.port_softbuffer_init(C.byref(sb), seg.C)
+    dec = P.port_tdec_new()
+    out = np.zeros(tbs // 8 + 8, np.uint8)
+    avg = C.c_float()
+    noi = np.zeros(seg.C, np.uint32)
+    G = nb_q - (q_ri + q_cqi) * qm
+    rc = P.port_decode_tb(dec, C.byref(sb), tbs, qm, rv, G, np.ascontiguousarray(g[q_cqi * qm:]), out, max_it,
+                          C.byref(avg), noi)
+    P.port_softbuffer_free(C.byref(sb))
+    P.port_tdec_free(dec)
+    return rc, out[: tbs // 8 + 3].copy(), avg.value, g, (q_ack, q_ri, q_cqi)

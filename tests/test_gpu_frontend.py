@@ -234,3 +234,133 @@ def test_tx_mirror_encoder_and_rate_matching(ctx, vec):
     ctx.synchronize()
     got, _, _ = ctx.tdec_batch_host(work.cpu().numpy(), K, 2, natural=False)
     assert np.array_equal(got, np.packbits(bits, axis=1))
+
+
+# ---- PUSCH with multiplexed UCI (data path of srslte_ulsch_decode, sch.c:920-1064) ----------
+def _uci_positions(is_ri, n, qm, rows, cols):
+    """channel positions of the n coded ACK / RI symbols (uci.c:497-545), [n, qm]."""
+    sets = {(0, True): (2, 3, 8, 9), (0, False): (1, 2, 6, 7), (1, True): (1, 4, 7, 10), (1, False): (0, 3, 5, 8)}
+    s = sets[(int(is_ri), cols > 10)]
+    idx = np.arange(n)
+    row = rows - 1 - idx // 4
+    col = np.array([s[(3 * i) % 4] for i in idx], dtype=np.int64)
+    return (row[:, None] * qm + rows * col[:, None] * qm + np.arange(qm)[None, :]).astype(np.int64)
+
+
+def test_pusch_codewords_with_multiplexed_uci_vs_oracle(ctx):
+    """De-multiplexing as an index map: ACK erasure, RI skipping with the reference's g[0] behaviour, 12 / 11 / 10 / 9
+    PUSCH symbols, RI rows that reach up the matrix, against the sequential port (pinned to the compiled reference by
+    tests/test_oracle_ulsch_uci.py)."""
+    rng = np.random.default_rng(77)
+    P = ol.port()
+    cws, syms, want, so, lo = [], [], [], 0, 0
+    shapes = []
+    for qm in (2, 4, 6):
+        for cols in (12, 11, 10, 9):
+            for l_prb in (1, 3, 8):
+                rows = l_prb * 12
+                for q_ack, q_ri, ri_len in ((0, 1, 1), (3, 0, 0), (5, 2, 1), (17, 9, 2), (4 * rows, 7, 1), (2, 4 * rows, 2),
+                                            (0, 4 * rows - 3, 1), (11, 4, 1)):
+                    shapes.append((qm, cols, rows, q_ack, q_ri, ri_len))
+    for qm, cols, rows, q_ack, q_ri, ri_len in shapes:
+        nsym = rows * cols
+        sym = ((rng.standard_normal(nsym) + 1j * rng.standard_normal(nsym)) * 0.9).astype(np.complex64)
+        c_init = int(rng.integers(1, 2 ** 31 - 1))
+        cws.append(dict(qm=qm, nof_symbols=nsym, c_init=c_init, sym_offset=so, llr_offset=lo, ul_nof_symb=cols,
+                        uci=dict(q_prime_ack=q_ack, q_prime_ri=q_ri, q_prime_cqi=0, ri_len=ri_len)))
+        q = ol.port_demod_descramble(qm, sym, c_init)
+        c = np.zeros(qm * nsym, np.uint8)
+        P.port_gold_sequence(c_init, qm * nsym, c)
+        g = ol.port_ulsch_demux(q, c, qm, cols, q_ack, q_ri, ri_len)
+        syms.append(sym)
+        want.append(np.concatenate([g, np.zeros(q_ri * qm, np.int16)]))   # the undefined tail reads 0 here
+        so += nsym; lo += qm * nsym
+    got = _run(ctx, cws, syms)
+    wantc = np.concatenate(want)
+    if not np.array_equal(got, wantc):
+        lo = 0
+        for (qm, cols, rows, q_ack, q_ri, ri_len), w in zip(shapes, want):
+            bad = np.nonzero(got[lo:lo + w.size] != w)[0]
+            assert bad.size == 0, (qm, cols, rows, q_ack, q_ri, ri_len, bad[:8], got[lo + bad[:8]], w[bad[:8]])
+            lo += w.size
+    # more ACK / RI symbols than 4 per matrix row: the reference fails (uci.c:504, 529), so does the library
+    import torch
+    s = torch.zeros(2 * 144, dtype=torch.float32, device="cuda")
+    e = torch.zeros(2 * 144, dtype=torch.int16, device="cuda")
+    with pytest.raises(RuntimeError):
+        ctx.demod_descramble_dev([dict(qm=2, nof_symbols=144, c_init=1, ul_nof_symb=12, uci=dict(q_prime_ri=49))],
+                                 s.data_ptr(), e.data_ptr())
+
+
+def test_pusch_transport_blocks_with_uci_from_symbols_vs_oracle(ctx, vec):
+    """srslte_ulsch_decode's data path from equalised symbols to bytes in one call: the TX side (numpy mirror) puts CQI
+    bits in front of the rate-matched data, interleaves around the RI cells and overwrites the ACK cells; the oracle is
+    port_demod_descramble -> port_ulsch_demux -> port_decode_tb; also the committed golden cases of the compiled
+    reference, fed as QPSK-like symbols is not possible (they are LLRs), so they pin the port in the CPU suite."""
+    import ctypes as C
+    P = ol.port()
+    rng = np.random.default_rng(31)
+    # tbs, qm, L_prb, N_pusch_symbs, nof_ack, ri_len, cqi_mode
+    cases = [(2216, 4, 10, 12, 1, 1, 1), (1000, 2, 6, 12, 2, 1, 0), (14112, 4, 50, 12, 2, 2, 2), (36696, 6, 100, 12, 1, 1, 2),
+             (6200, 4, 20, 11, 4, 1, 1), (2600, 6, 6, 10, 0, 2, 1), (4008, 6, 8, 12, 2, 0, 0), (9912, 4, 25, 9, 1, 1, 0),
+             (75376, 6, 100, 12, 2, 1, 1)]
+    descs, want = [], []
+    for i, (tbs, qm, l_prb, cols, nof_ack, ri_len, cqi) in enumerate(cases * 2):
+        rows = l_prb * 12
+        nb_q = qm * rows * cols
+        u = ol.ul_cfg(tbs, qm, 0, nb_q, l_prb, cols, nof_ack, ri_len, cqi, i_ack=int(rng.integers(0, 10)),
+                      i_ri=int(rng.integers(0, 12)), i_cqi=int(rng.integers(2, 12)))
+        q_ack, q_ri, q_cqi = ol.port_uci_q_primes(u)
+        G = nb_q - (q_ri + q_cqi) * qm
+        seg = ol.PortCbsegm()
+        assert P.port_cbsegm(C.byref(seg), tbs) == 0 and seg.F == 0
+        payload = rng.integers(0, 2, tbs, dtype=np.uint8)
+        tb = vec.attach_crc(vec.CRC24A, payload[None, :])[0]
+        e_parts, pos = [], 0
+        Gp, gamma = G // qm, (G // qm) % seg.C
+        for cb in range(seg.C):
+            K = seg.K1 if cb < seg.C1 else seg.K2
+            rlen = K if seg.C == 1 else K - 24
+            blk = tb[pos:pos + rlen]
+            pos += rlen
+            if seg.C > 1:
+                blk = vec.attach_crc(vec.CRC24B, blk[None, :])[0]
+            E = qm * (Gp // seg.C) if cb <= seg.C - gamma - 1 else qm * ((Gp + seg.C - 1) // seg.C)
+            e_parts.append(vec.rate_match(vec.turbo_encode(blk[None, :]), E, 0)[0])
+        g_tx = np.concatenate([rng.integers(0, 2, q_cqi * qm, dtype=np.uint8)] + e_parts).astype(np.uint8)
+        assert g_tx.size == nb_q - q_ri * qm
+        ri_pos = _uci_positions(True, q_ri, qm, rows, cols).reshape(-1)
+        ack_pos = _uci_positions(False, q_ack, qm, rows, cols).reshape(-1)
+        is_ri = np.zeros(nb_q, bool)
+        is_ri[ri_pos] = True
+        jj, ii, kk = np.meshgrid(np.arange(rows), np.arange(cols), np.arange(qm), indexing="ij")
+        x = (jj * qm + ii * rows * qm + kk).reshape(-1)   # channel positions in UL-SCH (row-major) order
+        x = x[~is_ri[x]]
+        q_tx = rng.integers(0, 2, nb_q, dtype=np.uint8)     # RI cells: anything
+        q_tx[x] = g_tx
+        q_tx[ack_pos] = rng.integers(0, 2, ack_pos.size, dtype=np.uint8)
+        c_init = int(rng.integers(1, 2 ** 31 - 1))
+        c = np.zeros(nb_q, np.uint8)
+        P.port_gold_sequence(c_init, nb_q, c)
+        sigma = (0.0, 0.07, 0.2)[i % 3]
+        sym = _modulate(q_tx ^ c, qm)
+        sym = (sym + sigma * (rng.standard_normal(sym.size) + 1j * rng.standard_normal(sym.size))).astype(np.complex64)
+        q = ol.port_demod_descramble(qm, sym, c_init, nb_q)
+        rc, out, avg, _, qp = ol.port_ulsch_decode(u, q, c, 8)
+        assert qp == (q_ack, q_ri, q_cqi)
+        want.append((rc, out, avg, np.packbits(payload)))
+        descs.append(dict(tbs=tbs, qm=qm, rv=0, nof_e_bits=nb_q, softbuffer=i, c_init=c_init, symbols=sym, ul_nof_symb=cols,
+                          uci=dict(q_prime_ack=q_ack, q_prime_ri=q_ri, q_prime_cqi=q_cqi, ri_len=ri_len)))
+    pool = ctx.harq_pool(len(descs), 13)
+    got = ctx.decode_tb_sym_batch(pool, descs, 8)
+    n_ok = 0
+    for i, ((ret, data, avg), (rc, out, wavg, payload)) in enumerate(zip(got, want)):
+        tbs = descs[i]["tbs"]
+        assert ret == rc, i
+        assert abs(avg - wavg) < 1e-6, (i, avg, wavg)
+        assert np.array_equal(data[: tbs // 8 + 3], out), i
+        if ret == 0:
+            n_ok += 1
+            assert np.array_equal(data[: tbs // 8], payload)
+    assert n_ok >= 12
+    pool.close()
