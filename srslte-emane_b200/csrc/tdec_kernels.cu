@@ -238,6 +238,8 @@ struct WinCtx {
   uint32_t sp_off;    // byte offset of this thread's 16 bytes inside a row group
   uint32_t s_bytes;   // bytes per input stream of the item
   uint32_t ngroups;   // row groups per stream (L rounded up to 4, / 4)
+  bool     noap;      // first half iteration of a block: there is no a-priori information yet (A reads as zero and is
+                      // neither fetched nor, unless a hard decision can come before DEC2 has written it, cleared)
   const char*     in_item;  // the item's sys | par0 | par1 streams
   const int16_t*  tail;     // this block's 12 tail samples
   uint32_t*       A32;  // [row][32 lanes] words: extrinsic of DEC2 minus E, natural order (= a-priori of DEC1)
@@ -312,11 +314,11 @@ __device__ __forceinline__ void pipe_issue(const WinCtx<W>& c, bool dec2, Pipe& 
     const uint32_t gbytes = min(2u, c.ngroups - 2 * ch) * c.g_stride;
     const uint32_t xbytes = min(8u, c.L - 8 * ch) * 128u;
     const uint32_t mb     = smem_u32(c.mbar + slot);
-    const uint32_t nc     = dec2 ? 2u : 3u;
+    const uint32_t nc     = (dec2 || c.noap) ? 2u : 3u;
     const uint32_t i      = (uint32_t)c.lane;
-    if (i == 0) mbar_expect_tx(mb, (dec2 ? gbytes : 2 * gbytes) + xbytes);
+    if (i == 0) mbar_expect_tx(mb, (dec2 ? gbytes : 2 * gbytes) + (c.noap ? 0u : xbytes));
     if (i < nc) {
-      const bool     isx    = i == nc - 1;
+      const bool     isx    = i == (dec2 ? 1u : 2u);
       const uint32_t stream = dec2 ? 2u : i;
       const char*    src    = isx ? reinterpret_cast<const char*>(dec2 ? c.E32 : c.A32) + (size_t)ch * 1024
                                   : c.in_item + (size_t)ch * 2 * c.g_stride + (size_t)stream * c.s_bytes;
@@ -425,7 +427,7 @@ __device__ __forceinline__ void issue_row(const WinCtx<W>& c, bool dec2, uint32_
   if (!dec2) {
     q.a = __ldg(reinterpret_cast<const uint32_t*>(gp));
     q.b = __ldg(reinterpret_cast<const uint32_t*>(gp + c.s_bytes));
-    q.c = c.A32[k * 32 + c.lane];
+    q.c = c.noap ? 0u : c.A32[k * 32 + c.lane];
   } else {
     q.a = 0;
     q.b = __ldg(reinterpret_cast<const uint32_t*>(gp + 2 * (size_t)c.s_bytes));
@@ -1095,7 +1097,13 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
       c.R   = nullptr;
       c.sm  = smem + tid;
 
-      for (uint32_t k = 0; k < c.L; k++) c.A32[k * 32 + lane] = 0;
+      // The first half iteration has no a-priori information: its bulk copies skip A and the A part of the warp's
+      // staging buffers is cleared instead (generic-proxy stores; the fence at the top of every half iteration
+      // orders them before the next copies into the same bytes).  A itself is only cleared when a hard decision
+      // can be taken before DEC2 has written every element of it (a single half iteration, or a CRC pass after the
+      // first): 48 KB of stores per work item that the plain K = 6144 / 4 half iterations case does not need.
+      for (int i = lane; i < kStages * 64; i += 32)
+        *reinterpret_cast<uint4*>(c.stages + (i >> 6) * kStageBytes + 2048 + (i & 63) * 16) = make_uint4(0, 0, 0, 0);
 
       uint8_t* out  = a.out + (size_t)cb * a.out_stride;
       uint32_t n    = 0, iters = 0;
@@ -1106,8 +1114,11 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
       const bool     any_crc  = __any_sync(0xFFFFFFFFu, crc_mode != CRC_NONE);
       // CRC modes: this thread's window pair in the tables of the block's polynomial ([dir][row][window])
       const uint32_t* Rblk = any_crc ? a.crc_pos + a.crc_pos_off[wi.kidx] + (size_t)which * 2 * c.K + 2 * t : nullptr;
+      if (a.max_iter < 2 || any_crc)
+        for (uint32_t k = 0; k < c.L; k++) c.A32[k * 32 + lane] = 0;
       do {
         const bool dec2 = (n & 1) != 0;
+        c.noap = n == 0;
         if (any_crc) c.R = Rblk + (dec2 ? c.K : 0u);
         // what the previous half iteration (or the clearing above) stored must be visible to the bulk copies
         fence_proxy_async();
