@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsrslte_b200.so")
 
-SOURCES = ["tdec_kernels.cu", "frontend_kernels.cu", "capi.cu", "compat.cu", "lte_tables.cpp"]
+SOURCES = ["tdec_kernels.cu", "frontend_kernels.cu", "capi.cu", "lte_tables.cpp"]
 HEADERS = ["tdec_kernels.h", "lte_tables.h", os.path.join("..", "..", "include", "srslte_b200.h"),
            os.path.join("..", "..", "include", "srslte_b200_compat.h")]
 
