@@ -210,6 +210,20 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = None
+    if world > 1:
+        # one process per GPU: run on (and first-touch the pinned buffers from) the CPUs next to this rank's GPU
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:   # CUDA_VISIBLE_DEVICES may renumber the devices: go by UUID
+                h = pynvml.nvmlDeviceGetHandleByUUID(f"GPU-{torch.cuda.get_device_properties(local).uuid}")
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(local)
+            pynvml.nvmlDeviceSetCpuAffinity(h)
+            affinity = f"{len(os.sched_getaffinity(0))} gpu-local cpus per rank (nvml)"
+        except Exception as e:  # no NVML / cpuset restrictions: keep the inherited affinity
+            affinity = f"inherited ({type(e).__name__})"
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -322,7 +336,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Gbit/s", "h2d_bytes_per_step": ne * IN_LEN * 2,
                 "d2h_bytes_per_step": ne * (K // 8 + 2), "blocks_per_gpu": ne, "ms_per_step": e2e_dt * 1e3,
-                "matches_device_path": same},
+                "matches_device_path": same, "host_affinity": affinity or "inherited"},
         "gpu_launches": launches,
         "roofline": {
             "bound": "int_alu", "kernel": "tdec_win_kernel<16>", "achieved": achieved_tops, "peak": peak_tops,
