@@ -1124,8 +1124,11 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
         fence_proxy_async();
         __syncwarp();
         // bound on |x|, |y|, |x + y| of this half iteration
+        // A block whose CRC has passed has frozen its output: what its lanes compute from here on is never read (they
+        // only keep the warp's shuffles and votes complete), so it neither picks the tier for the blocks that are
+        // still being decoded nor can it send the warp to the exact variant.
         const int Gx = dec2 ? emax : smax + amax;
-        const int G  = Gx + (dec2 ? p1max : p0max);
+        const int G  = done ? 0 : Gx + (dec2 ? p1max : p0max);
         HalfResult r;
         bool       fast_ok = false;
         // the decision must be warp-uniform: the passes below use full-warp shuffles and votes
@@ -1141,7 +1144,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
         } else if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kMaxFastG)) {
           r       = any_crc ? half_iteration_fast<W, true, true, true>(c, dec2, G, pipe)
                             : half_iteration_fast<W, true, true, false>(c, dec2, G, pipe);
-          fast_ok = __all_sync(0xFFFFFFFFu, r.proven);
+          fast_ok = __all_sync(0xFFFFFFFFu, r.proven || done);
         }
         if (!fast_ok) {
           r = half_iteration_exact<W>(c, dec2);
