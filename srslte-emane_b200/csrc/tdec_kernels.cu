@@ -1481,14 +1481,16 @@ __global__ void __launch_bounds__(256) to_internal_kernel(const int16_t* __restr
   if (src_format == 0) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     if (((3 * L) & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 7) == 0) {  // 8-byte aligned window starts
-      const uint2* s64 = reinterpret_cast<const uint2*>(src);
-      uint2*       t64 = reinterpret_cast<uint2*>(stage);
+      // asynchronous 8-byte copies straight into shared memory: all of a thread's pieces are in flight at once
+      const uint2*   s64 = reinterpret_cast<const uint2*>(src);
+      const uint32_t t64 = smem_u32(stage);
       for (uint32_t d = warp; d < W; d += nwarps) {
-        const uint2* sp = s64 + d * (3 * L / 4);
-        uint2*       tp = t64 + d * (wstride / 4);
-#pragma unroll 4
-        for (uint32_t p = lane; p < 3 * L / 4; p += 32) tp[p] = __ldg(sp + p);
+        const uint2*   sp = s64 + d * (3 * L / 4);
+        const uint32_t tp = t64 + d * (wstride / 4) * 8;
+        for (uint32_t p = lane; p < 3 * L / 4; p += 32)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tp + p * 8), "l"(sp + p) : "memory");
       }
+      asm volatile("cp.async.wait_all;" ::: "memory");
     } else if (((3 * L) & 1) == 0) {  // window starts are word aligned: 32-bit copies
       const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
       uint32_t*       t32 = reinterpret_cast<uint32_t*>(stage);
@@ -1505,8 +1507,24 @@ __global__ void __launch_bounds__(256) to_internal_kernel(const int16_t* __restr
   // one thread = one window pair t of one row group kg: 4 rows x 3 streams in, three 128-bit words out
   const uint32_t t = threadIdx.x % WH, ng = blockDim.x / WH;
   uint32_t       mx2[3] = {0, 0, 0};  // packed unsigned max of |.| per stream
+  const bool wide = src_format == 0 && (L & 3) == 0;  // the 12 samples of a row group are three aligned 64-bit words
   for (uint32_t kg = threadIdx.x / WH; kg < groups; kg += ng) {
     uint32_t w[3][4];
+    if (wide) {
+      // samples 3r + j (row r, stream j) of both windows: word n / 2, half n % 2 -> one PRMT per output word
+      const uint2* pl = reinterpret_cast<const uint2*>(stage + (2 * t) * wstride + 12 * kg);
+      const uint2* ph = reinterpret_cast<const uint2*>(stage + (2 * t + 1) * wstride + 12 * kg);
+      const uint2  a0 = pl[0], a1 = pl[1], a2 = pl[2], b0 = ph[0], b1 = ph[1], b2 = ph[2];
+      const uint32_t A[6] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y}, B[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const int n = 3 * r + j;
+          w[j][r]     = __byte_perm(A[n >> 1], B[n >> 1], (n & 1) ? 0x7632u : 0x5410u);
+          mx2[j]      = __vmaxu2(mx2[j], __vabs2(w[j][r]));
+        }
+    } else
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       const uint32_t k = kg * 4 + r;
