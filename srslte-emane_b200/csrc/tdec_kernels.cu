@@ -953,41 +953,51 @@ __device__ void decide(const WinCtx<W>& c, uint8_t* out, bool write)
     return grp_base[(((f >> 2) / WH) * kThreads + ((f >> 2) % WH)) * 4 + (f & 3)];
   };
   const uint16_t* E16 = reinterpret_cast<const uint16_t*>(c.E32) + c.grp * W;
-  uint32_t  acc_lo = 0, acc_hi = 0;
+  const uint16_t* rt  = c.rowtab + kMaxL;
+  const uint8_t*  wt  = c.wtab + kMaxL * 8 + c.t;
   constexpr int NB = 16;  // rows gathered per batch: the E gather is latency bound, keep many loads in flight
+  // 32 rows = one word per window.  Rows past L repeat row L - 1: their bits land below the last valid bit of the
+  // window's last word, where phase 2 never looks.
 #pragma unroll 1
-  for (uint32_t k0 = 0; k0 < L; k0 += NB) {
-    uint32_t av[NB], el[NB], eh[NB];
+  for (uint32_t k0 = 0; k0 < L; k0 += 32) {
+    uint32_t acc_lo = 0, acc_hi = 0;
 #pragma unroll
-    for (int j = 0; j < NB; j++) {
-      const uint32_t k   = min(k0 + j, L - 1);
-      const uint32_t row = c.rowtab[kMaxL + k];
-      const uint32_t wb  = c.wtab[(kMaxL + k) * 8 + c.t];
-      el[j] = E16[row * 64 + (wb & 15u)];
-      eh[j] = E16[row * 64 + (wb >> 4)];
-      av[j] = c.A32[k * 32 + c.lane];
-    }
+    for (int h = 0; h < 32 / NB; h++) {
+      uint32_t av[NB], el[NB], eh[NB];
 #pragma unroll
-    for (int j = 0; j < NB; j++) {
-      const uint32_t k = k0 + j;
-      if (k < L) {
+      for (int j = 0; j < NB; j++) {
+        const uint32_t k   = min(k0 + h * NB + j, L - 1);
+        const uint32_t row = rt[k];
+        const uint32_t wb  = wt[k * 8];
+        el[j] = E16[row * 64 + (wb & 15u)];
+        eh[j] = E16[row * 64 + (wb >> 4)];
+        av[j] = c.A32[k * 32 + c.lane];
+      }
+#pragma unroll
+      for (int j = 0; j < NB; j++) {
         const uint32_t v = wadd2(av[j], el[j] | (eh[j] << 16));
-        // sign bit of -(max(v, -1)) is set exactly when v > 0 (no overflow: max(v,-1) >= -1)
-        const uint32_t m = wneg2(max2(v, 0xFFFFFFFFu));
-        acc_lo = (acc_lo << 1) | ((m >> 15) & 1u);
-        acc_hi = (acc_hi << 1) | (m >> 31);
-        if ((k & 31) == 31 || k == L - 1) {
-          const uint32_t sh = 31 - (k & 31);  // left-align a partial last word
-          word((2 * c.t) * NW + (k >> 5))     = acc_lo << sh;
-          word((2 * c.t + 1) * NW + (k >> 5)) = acc_hi << sh;
-          acc_lo = 0;
-          acc_hi = 0;
-        }
+        // max(v, -1) + 32767 wraps to a negative number exactly when v > 0: the sign bits are the decisions
+        const uint32_t m = wadd2(max2(v, 0xFFFFFFFFu), 0x7FFF7FFFu);
+        acc_hi = __funnelshift_l(m, acc_hi, 1);
+        acc_lo = __funnelshift_l(m << 16, acc_lo, 1);
       }
     }
+    word((2 * c.t) * NW + (k0 >> 5))     = acc_lo;
+    word((2 * c.t + 1) * NW + (k0 >> 5)) = acc_hi;
   }
   __syncwarp();
-  if (write) {
+  if (write && (L & 31) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
+    // whole words: window d's string is words d * L/32 .. of the output, first row in the top bit (big endian)
+    const uint32_t wpw = L >> 5;
+    uint32_t*      o32 = reinterpret_cast<uint32_t*>(out);
+    for (uint32_t j = (uint32_t)c.t, d = 0, i = (uint32_t)c.t; j < c.K / 32; j += WH, i += WH) {
+      while (i >= wpw) {
+        i -= wpw;
+        d++;
+      }
+      o32[j] = __byte_perm(word(d * NW + i), 0, 0x0123);
+    }
+  } else if (write) {
     const uint32_t mL = (uint32_t)((0x100000000ull + L - 1) / L);
     for (uint32_t j = (uint32_t)c.t; j < c.K / 8; j += WH) {
       const uint32_t n = 8 * j;
