@@ -252,8 +252,10 @@ struct WinCtx {
   uint4*          sm;   // chunk of beta: [(s*2 + h)*kThreads], already offset by tid
   char*           stages;  // the warp's kStages staging buffers: [sys 1 KB | par 1 KB | A or E rows 1 KB]
   uint64_t*       mbar;    // the warp's kStages mbarriers
-  const uint16_t* rowtab;  // [2][kMaxL]    destination row of row k: dir 0 = pi (DEC2 writes A), 1 = pi^-1 (DEC1 writes E)
-  const uint8_t*  wtab;    // [2][kMaxL][8] destination windows of row k: one nibble per source window
+  const uint16_t* rowtab;  // [2][kMaxL]    128 x destination row (= its byte offset in A / E) of row k: dir 0 = pi (DEC2
+                           //               writes A), 1 = pi^-1 (DEC1 writes E)
+  const uint16_t* wtab;    // [2][kMaxL][8] destination windows of row k's window pair 2t, 2t+1 as byte offsets inside the
+                           //               code block's 32 bytes of the row: low byte / high byte = 2 x window
 };
 
 // the inputs of 4 consecutive trellis rows (one row group) for this thread's window pair
@@ -447,9 +449,16 @@ __device__ __forceinline__ void finish_row_exact(bool dec2, const RawRow& q, uin
 // The QPP is contention free: all windows of row k go to ONE destination row, permuted among the windows.
 // HARD (CRC modes): the hard decisions (out = d + aux > 0) of the two windows are folded into the running CRC of
 // the block: the CRC is linear, every set bit xors in its precomputed contribution, in whatever order they come.
+// this code block's 32 bytes of row 0 of the array the half iteration writes
+template <int W>
+__device__ __forceinline__ char* out_base(const WinCtx<W>& c, bool dec2)
+{
+  return reinterpret_cast<char*>(dec2 ? c.A32 : c.E32) + c.grp * (2 * W);
+}
+
 template <int W, bool HARD>
 __device__ __forceinline__ void store_diff(const WinCtx<W>& c, bool dec2, uint32_t k, uint32_t d, uint32_t aux, Range& rd,
-                                           uint32_t& crc)
+                                           uint32_t& crc, char* Y = nullptr)
 {
   rd.add1(d);
   if (HARD) {
@@ -458,12 +467,13 @@ __device__ __forceinline__ void store_diff(const WinCtx<W>& c, bool dec2, uint32
     const uint2    rr = *reinterpret_cast<const uint2*>(c.R + k * W);
     crc ^= (rr.x & (uint32_t)((int32_t)(m << 16) >> 31)) ^ (rr.y & (uint32_t)((int32_t)m >> 31));
   }
-  const uint32_t e   = (dec2 ? 0u : (uint32_t)kMaxL) + k;
-  const uint32_t row = c.rowtab[e];
-  const uint32_t wb  = c.wtab[e * 8 + c.t];
-  uint16_t*      Y   = reinterpret_cast<uint16_t*>(dec2 ? c.A32 : c.E32) + row * 64 + c.grp * W;
-  Y[wb & 15u] = (uint16_t)(d & 0xFFFFu);
-  Y[wb >> 4]  = (uint16_t)(d >> 16);
+  // byte offsets: the row's (a multiple of 128) and the window's (< 32) OR together, the block's 32 bytes are in Y
+  const uint32_t e  = (dec2 ? 0u : (uint32_t)kMaxL) + k;
+  const uint32_t r7 = c.rowtab[e];
+  const uint32_t ww = c.wtab[e * 8 + c.t];
+  if (!Y) Y = out_base<W>(c, dec2);
+  *reinterpret_cast<uint16_t*>(Y + (r7 | (ww & 0xFFu))) = (uint16_t)(d & 0xFFFFu);
+  *reinterpret_cast<uint16_t*>(Y + (r7 | (ww >> 8)))    = (uint16_t)(d >> 16);
 }
 template <int W>
 __device__ __forceinline__ void store_out(const WinCtx<W>& c, bool dec2, uint32_t k, uint32_t o, uint32_t aux, Range& rd,
@@ -772,6 +782,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
   exchange_alpha_boundary<WH>(a, c.t);
 
   // ---------------- forward pass over the window, chunk by chunk ----------------
+  char* const Yout = out_base<W>(c, dec2);
   uint32_t nxt[8];  // checkpoint of the next chunk, loaded one chunk ahead (and prefetched into L2 kChkAhead ahead)
   chk_load<W>(c, 0, nxt);
 #pragma unroll
@@ -845,10 +856,10 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
         const uint32_t bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         if (W == 8) {  // the 8-window (sse16) decoder halves its output before the extrinsic subtraction
           const uint32_t o = sra1_2(alpha_out_step<true, TRACK>(a, bb, q.x[r], q.y[r], wadd2(q.x[r], q.y[r]), rm));
-          store_diff<W, HARD>(c, dec2, (uint32_t)(lo + g * 4 + r), wsub2(o, q.aux[r]), q.aux[r], rd, crc);
+          store_diff<W, HARD>(c, dec2, (uint32_t)(lo + g * 4 + r), wsub2(o, q.aux[r]), q.aux[r], rd, crc, Yout);
         } else {  // out - aux comes straight out of the step
           const uint32_t d = alpha_out_step<true, TRACK>(a, bb, q.x[r], q.y[r], wadd2(q.x[r], q.y[r]), rm, q.aux[r]);
-          store_diff<W, HARD>(c, dec2, (uint32_t)(lo + g * 4 + r), d, q.aux[r], rd, crc);
+          store_diff<W, HARD>(c, dec2, (uint32_t)(lo + g * 4 + r), d, q.aux[r], rd, crc, Yout);
         }
         if ((r & 1) == 0 && (EDGE || r != 0 || (lo | g) != 0)) {  // never after row 0
           normalize<true>(a);
@@ -910,7 +921,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
 // dir 0 holds pi (where DEC2's row k goes in natural order), dir 1 its inverse (where natural row r goes in
 // DEC2's order).
 template <int W>
-__device__ void build_tables(uint32_t K, uint32_t f1, uint32_t f2, uint16_t* rowtab, uint8_t* wtab)
+__device__ void build_tables(uint32_t K, uint32_t f1, uint32_t f2, uint16_t* rowtab, uint16_t* wtab)
 {
   const uint32_t L  = K / W;
   const uint32_t mK = (uint32_t)(0x100000000ull / K);
@@ -928,10 +939,14 @@ __device__ void build_tables(uint32_t K, uint32_t f1, uint32_t f2, uint16_t* row
       fw |= (uint64_t)w << (4 * d);
       iv |= (uint64_t)d << (4 * w);
     }
-    rowtab[k]         = (uint16_t)r;
-    rowtab[kMaxL + r] = (uint16_t)k;
-    *reinterpret_cast<uint64_t*>(wtab + 8 * k)           = fw;
-    *reinterpret_cast<uint64_t*>(wtab + 8 * (kMaxL + r)) = iv;
+    rowtab[k]         = (uint16_t)(r * 128);
+    rowtab[kMaxL + r] = (uint16_t)(k * 128);
+#pragma unroll
+    for (uint32_t t = 0; t < (uint32_t)W / 2; t++) {  // nibbles 2t, 2t+1 -> 2 x window in the low / high byte
+      const uint32_t f = (uint32_t)(fw >> (8 * t)) & 0xFFu, v = (uint32_t)(iv >> (8 * t)) & 0xFFu;
+      wtab[8 * k + t]           = (uint16_t)(((f & 15u) << 1) | ((f >> 4) << 9));
+      wtab[8 * (kMaxL + r) + t] = (uint16_t)(((v & 15u) << 1) | ((v >> 4) << 9));
+    }
   }
 }
 
@@ -952,9 +967,9 @@ __device__ void decide(const WinCtx<W>& c, uint8_t* out, bool write)
   auto      word     = [&](uint32_t f) -> uint32_t& {
     return grp_base[(((f >> 2) / WH) * kThreads + ((f >> 2) % WH)) * 4 + (f & 3)];
   };
-  const uint16_t* E16 = reinterpret_cast<const uint16_t*>(c.E32) + c.grp * W;
-  const uint16_t* rt  = c.rowtab + kMaxL;
-  const uint8_t*  wt  = c.wtab + kMaxL * 8 + c.t;
+  const char*     E8 = reinterpret_cast<const char*>(c.E32) + c.grp * (2 * W);
+  const uint16_t* rt = c.rowtab + kMaxL;
+  const uint16_t* wt = c.wtab + kMaxL * 8 + c.t;
   constexpr int NB = 16;  // rows gathered per batch: the E gather is latency bound, keep many loads in flight
   // 32 rows = one word per window.  Rows past L repeat row L - 1: their bits land below the last valid bit of the
   // window's last word, where phase 2 never looks.
@@ -967,10 +982,10 @@ __device__ void decide(const WinCtx<W>& c, uint8_t* out, bool write)
 #pragma unroll
       for (int j = 0; j < NB; j++) {
         const uint32_t k   = min(k0 + h * NB + j, L - 1);
-        const uint32_t row = rt[k];
-        const uint32_t wb  = wt[k * 8];
-        el[j] = E16[row * 64 + (wb & 15u)];
-        eh[j] = E16[row * 64 + (wb >> 4)];
+        const uint32_t r7 = rt[k];
+        const uint32_t ww = wt[k * 8];
+        el[j] = *reinterpret_cast<const uint16_t*>(E8 + (r7 | (ww & 0xFFu)));
+        eh[j] = *reinterpret_cast<const uint16_t*>(E8 + (r7 | (ww >> 8)));
         av[j] = c.A32[k * 32 + c.lane];
       }
 #pragma unroll
@@ -1045,7 +1060,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
   extern __shared__ uint4 smem[];
   char*     stages_all = reinterpret_cast<char*>(smem + kChunk * 2 * kThreads);  // [warps][kStages][kStageBytes]
   uint16_t* rowtab     = reinterpret_cast<uint16_t*>(stages_all + kWarps * kStages * kStageBytes);
-  uint8_t*  wtab       = reinterpret_cast<uint8_t*>(rowtab + 2 * kMaxL);
+  uint16_t* wtab       = rowtab + 2 * kMaxL;
   uint64_t* mbar_all   = reinterpret_cast<uint64_t*>(wtab + 2 * kMaxL * 8);
   __shared__ uint32_t s_item;
 
@@ -1642,7 +1657,7 @@ cudaError_t tdec_geometry(int W, int device, TdecGeometry* g)
     return cudaSuccess;
   }
   g->smem = (size_t)kChunk * 2 * kThreads * sizeof(uint4) + warps_per_block * kStages * kStageBytes +
-            2 * kMaxL * sizeof(uint16_t) + 2 * kMaxL * 8 + warps_per_block * kStages * sizeof(uint64_t);
+            2 * kMaxL * sizeof(uint16_t) + 2 * kMaxL * 8 * sizeof(uint16_t) + warps_per_block * kStages * sizeof(uint64_t);
   int per_sm = 0;
   if (W == 16) {
     e = cudaFuncSetAttribute(tdec_win_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
