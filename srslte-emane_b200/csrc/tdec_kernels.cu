@@ -377,23 +377,20 @@ __device__ __forceinline__ void pipe_release(const WinCtx<W>& c, bool dec2, Pipe
   p.slot = p.slot + 1 == (uint32_t)kStages ? 0u : p.slot + 1;
 }
 
-// FAST rows only: row group g (0 / 1) of a staged chunk; x = sys + a-priori with a wrapping add
+// FAST rows only: row group g (0 / 1) of a staged chunk; x = sys + a-priori with a wrapping add.  DEC2 has no
+// separate systematic input (x = E): its copies leave the sys part of the stages alone and the kernel clears it
+// before every DEC2 half iteration, so both decoders run the same branch-free code.
 template <int W>
 __device__ __forceinline__ void load_group(const WinCtx<W>& c, bool dec2, const char* st, int g, Group& q)
 {
   const uint4     ys = *reinterpret_cast<const uint4*>(st + 1024 + g * c.g_stride + c.sp_off);
   const uint32_t* xr = reinterpret_cast<const uint32_t*>(st + 2048 + g * 512) + c.lane;
+  const uint4     xs = *reinterpret_cast<const uint4*>(st + g * c.g_stride + c.sp_off);
   q.y[0] = ys.x; q.y[1] = ys.y; q.y[2] = ys.z; q.y[3] = ys.w;
 #pragma unroll
   for (int r = 0; r < 4; r++) q.aux[r] = xr[r * 32];
-  if (!dec2) {
-    const uint4 xs = *reinterpret_cast<const uint4*>(st + g * c.g_stride + c.sp_off);
-    q.x[0] = wadd2(q.aux[0], xs.x); q.x[1] = wadd2(q.aux[1], xs.y);
-    q.x[2] = wadd2(q.aux[2], xs.z); q.x[3] = wadd2(q.aux[3], xs.w);
-  } else {
-#pragma unroll
-    for (int r = 0; r < 4; r++) q.x[r] = q.aux[r];
-  }
+  q.x[0] = wadd2(q.aux[0], xs.x); q.x[1] = wadd2(q.aux[1], xs.y);
+  q.x[2] = wadd2(q.aux[2], xs.z); q.x[3] = wadd2(q.aux[3], xs.w);
 }
 
 template <int W>
@@ -1145,6 +1142,9 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
         const bool dec2 = (n & 1) != 0;
         c.noap = n == 0;
         if (any_crc) c.R = Rblk + (dec2 ? c.K : 0u);
+        if (dec2)  // see load_group: the sys part of the stages reads as zero in DEC2
+          for (int i = lane; i < kStages * 64; i += 32)
+            *reinterpret_cast<uint4*>(c.stages + (i >> 6) * kStageBytes + (i & 63) * 16) = make_uint4(0, 0, 0, 0);
         // what the previous half iteration (or the clearing above) stored must be visible to the bulk copies
         fence_proxy_async();
         __syncwarp();
