@@ -687,7 +687,9 @@ __device__ __noinline__ HalfResult half_iteration_exact(const WinCtx<W> c, bool 
 // the best bit-1 and bit-0 candidates can be chosen from the same predecessor state, so they differ by at most
 // spread(beta) + 2G.
 // HARD (CRC modes): the forward pass also accumulates the CRC of the hard decisions (c.R).
-template <int W, bool TRACK, bool EDGE, bool HARD>
+// FULL: L % 8 == 0, every chunk holds two complete row groups (K = 6144, 4096, 2048 ...): the partial-chunk tests
+// and the exact rows above the last full row group drop out of the loops at compile time.
+template <int W, bool TRACK, bool EDGE, bool HARD, bool FULL>
 __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bool dec2, int G, Pipe& p)
 {
   constexpr int WH = W / 2;
@@ -719,7 +721,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
 #pragma unroll
       for (int g = 1; g >= 0; g--) {
         const int k0 = ch * kChunk + g * 4;
-        if (k0 > kf) continue;
+        if (!FULL && k0 > kf) continue;
         Group q;
         load_group<W>(c, dec2, stg, g, q);
 #pragma unroll
@@ -738,7 +740,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
       exchange_beta_boundary<WH>(s, c.t, c.tail + (dec2 ? 6 : 0));
       chk_store<W>(c, ctop, s);
       if (TRACK) rb.add8full(s);
-      if (kf < L - 1) {  // the rows above the last full row group
+      if (!FULL && kf < L - 1) {  // the rows above the last full row group
 #pragma unroll
         for (int i = 0; i < 8; i++) st.s[i] = s[i];
         st.trk = rb;
@@ -788,7 +790,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
 #pragma unroll 1
   for (int ch = 0; ch <= ctop; ch++) {
     const int lo = ch * kChunk;
-    const int hi = min(lo + kChunk, L);
+    const int hi = FULL ? lo + kChunk : min(lo + kChunk, L);
 #pragma unroll
     for (int i = 0; i < 8; i++) s[i] = nxt[i];
     if (ch < ctop) chk_load<W>(c, ch + 1, nxt);
@@ -803,7 +805,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
       else
         normalize<false>(s);
     }
-    if (hi - 1 > kf) {  // rows above the last full row group
+    if (!FULL && hi - 1 > kf) {  // rows above the last full row group
 #pragma unroll
       for (int i = 0; i < 8; i++) st.s[i] = s[i];
       st.trk.reset();
@@ -813,7 +815,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
     }
 #pragma unroll
     for (int g = 1; g >= 0; g--) {
-      if (lo + g * 4 > kf) continue;
+      if (!FULL && lo + g * 4 > kf) continue;
       Group q;
       load_group<W>(c, dec2, stg, g, q);
       uint4* bs = c.sm + (g * 4 - 1) * 2 * kThreads;
@@ -842,7 +844,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
     }
 #pragma unroll 1
     for (int g = (EDGE && ch == 0) ? 1 : 0; g < 2; g++) {
-      if (lo + g * 4 > kf) continue;
+      if (!FULL && lo + g * 4 > kf) continue;
       Group q;
       load_group<W>(c, dec2, stg, g, q);
       const uint4* bs = c.sm + g * 4 * 2 * kThreads;
@@ -865,7 +867,7 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
       }
     }
     pipe_release<W>(c, dec2, p);
-    if (hi - 1 > kf) {  // rows above the last full row group
+    if (!FULL && hi - 1 > kf) {  // rows above the last full row group
 #pragma unroll
       for (int i = 0; i < 8; i++) st.s[i] = a[i];
       st.trk = ra;
@@ -910,6 +912,13 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
   }
   res.proven = ok;
   return res;
+}
+
+template <int W, bool TRACK, bool EDGE, bool HARD>
+__device__ __forceinline__ HalfResult half_fast(const WinCtx<W>& c, bool dec2, int G, Pipe& p)
+{
+  return (c.L & 7u) == 0 ? half_iteration_fast<W, TRACK, EDGE, HARD, true>(c, dec2, G, p)
+                         : half_iteration_fast<W, TRACK, EDGE, HARD, false>(c, dec2, G, p);
 }
 
 // QPP of this K as destination tables, computed from (f1, f2) by the whole CTA:
@@ -1159,16 +1168,16 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
         // the decision must be warp-uniform: the passes below use full-warp shuffles and votes
         // force_exact: bit 0 = exact variant only (tests); bits 1, 2 = skip the pure / the static tier (measurements)
         if (__all_sync(0xFFFFFFFFu, (a.force_exact & 3u) == 0 && G <= kPureFastG)) {
-          r       = any_crc ? half_iteration_fast<W, false, false, true>(c, dec2, G, pipe)
-                            : half_iteration_fast<W, false, false, false>(c, dec2, G, pipe);
+          r       = any_crc ? half_fast<W, false, false, true>(c, dec2, G, pipe)
+                            : half_fast<W, false, false, false>(c, dec2, G, pipe);
           fast_ok = true;
         } else if (__all_sync(0xFFFFFFFFu, (a.force_exact & 5u) == 0 && G <= kStaticFastG)) {
-          r       = any_crc ? half_iteration_fast<W, false, true, true>(c, dec2, G, pipe)
-                            : half_iteration_fast<W, false, true, false>(c, dec2, G, pipe);
+          r       = any_crc ? half_fast<W, false, true, true>(c, dec2, G, pipe)
+                            : half_fast<W, false, true, false>(c, dec2, G, pipe);
           fast_ok = true;
         } else if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kMaxFastG)) {
-          r       = any_crc ? half_iteration_fast<W, true, true, true>(c, dec2, G, pipe)
-                            : half_iteration_fast<W, true, true, false>(c, dec2, G, pipe);
+          r       = any_crc ? half_fast<W, true, true, true>(c, dec2, G, pipe)
+                            : half_fast<W, true, true, false>(c, dec2, G, pipe);
           fast_ok = __all_sync(0xFFFFFFFFu, r.proven || done);
         }
         if (!fast_ok) {
