@@ -33,7 +33,7 @@ NOF_ITERATIONS = 4          # srsLTE HALF iterations
 EBNO_HARNESS = 1.5          # turbodecoder_test "-e 1.5" (sigma = 1.457 on +-1; never converges, F7)
 LLR_SCALE = 100.0
 IN_LEN = 3 * K + 12
-NCU_DRAM_BYTES_PER_BLOCK = 383.9e3        # profiles/r01h_ncu_raw.csv: (18.73 + 6.43) GB / 65536 blocks (r01d: 421 KB)
+NCU_DRAM_BYTES_PER_BLOCK = 383.9e3        # profiles/r01i_ncu_raw.csv: (18.73 + 6.43) GB / 65536 blocks (r01d: 421 KB)
 INT_PEAK_THREAD_INSTR_PER_CLK_SM = 64.0   # measured: profiles/r01_int_peak*.txt (VIADD.16x2 / VIMNMX.S16x2)
 
 
