@@ -77,6 +77,7 @@ struct Schedule {  // how the code blocks of one launch map onto warps
   std::vector<uint2>    place;  // per code block: (first position of its work item, count << 8 | index in the item)
   std::vector<WorkItem> items[3];
   uint32_t              item_base[3] = {0, 0, 0};
+  uint32_t              positions = 0;  // code-block positions of the internal-layout input (K groups padded to whole items)
   // window regimes: the CTA rounds (first item, number of items <= tdec_items_per_cta) in launch order
   std::vector<uint2>    rounds[2];
   uint32_t              round_base[2] = {0, 0};
@@ -241,6 +242,7 @@ int build_schedule(srslte_b200_ctx* ctx, const uint32_t* K, uint32_t uniform_K, 
   const bool with_place = K != nullptr;  // a uniform-K schedule is the identity: to_internal_kernel derives it
   s.place.resize(with_place ? n : 0);
   for (auto& v : s.items) v.clear();
+  uint32_t in_cursor = 0;
   auto emit = [&](uint32_t Kv, uint32_t first, uint32_t count) {
     const int idx = cb_index_exact(Kv);
     const int W   = nof_windows(Kv);
@@ -253,16 +255,19 @@ int build_schedule(srslte_b200_ctx* ctx, const uint32_t* K, uint32_t uniform_K, 
     wi.kidx = (uint16_t)idx;
     wi.pad  = 0;
     for (uint32_t o = 0; o < count; o += per) {
-      wi.first = first + o;
-      wi.count = (uint16_t)std::min(per, count - o);
+      wi.first  = first + o;
+      wi.in_pos = in_cursor + o;
+      wi.count  = (uint16_t)std::min(per, count - o);
       s.items[ri].push_back(wi);
       if (with_place)
         for (uint32_t j = 0; j < wi.count; j++)
-          s.place[s.order[wi.first + j]] = make_uint2(wi.first, ((uint32_t)wi.count << 8) | j);
+          s.place[s.order[wi.first + j]] = make_uint2(wi.in_pos, ((uint32_t)wi.count << 8) | j);
     }
+    in_cursor += internal_positions(Kv, count);
     const size_t round = (size_t)tdec_items_per_cta(W);
-    wi.first = first;
-    wi.count = 0;
+    wi.first  = first;
+    wi.in_pos = 0;
+    wi.count  = 0;
     while (s.items[ri].size() % round) s.items[ri].push_back(wi);
   };
   if (!K) {
@@ -270,6 +275,7 @@ int build_schedule(srslte_b200_ctx* ctx, const uint32_t* K, uint32_t uniform_K, 
       return fail(ctx, SRSLTE_B200_ERROR_INVALID_INPUTS, "invalid code block size %u", uniform_K);
     for (uint32_t i = 0; i < n; i++) s.order[i] = i;
     emit(uniform_K, 0, n);
+    s.positions = in_cursor;
     build_rounds(ctx, s);
     return 0;
   }
@@ -286,6 +292,7 @@ int build_schedule(srslte_b200_ctx* ctx, const uint32_t* K, uint32_t uniform_K, 
   for (uint32_t i = 0; i < n; i++) s.order[fill[kNofCbSizes - 1 - idx[i]]++] = i;
   for (int b = 0; b < kNofCbSizes; b++)
     if (cnt[b]) emit(kQpp[kNofCbSizes - 1 - b].K, start[b], cnt[b]);
+  s.positions = in_cursor;
   build_rounds(ctx, s);
   return 0;
 }
@@ -389,7 +396,7 @@ int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint
   int rc = ensure_schedule(ctx, b->long_cb, b->uniform_long_cb, b->n_cb, st);
   if (rc) return rc;
   // every input format is first brought into the decoder's internal layout
-  CU(ctx->d_work.reserve((size_t)b->n_cb * work_len));
+  CU(ctx->d_work.reserve((size_t)ctx->sched.positions * work_len));
   {
     KernelTimer kt(ctx, 3, st);
     CU(to_internal_launch(d_llr, b->in_stride, d_src_off, b->input_format == SRSLTE_B200_INPUT_NATURAL ? 0 : 1,

@@ -43,19 +43,31 @@ namespace b200 {
 namespace {
 
 constexpr int      kWarm      = 40;  // win_overlap_len
-constexpr int      kChunk     = 8;   // rows of beta rebuilt at a time = rows per staged chunk (two row groups of 4)
-constexpr int      kThreads   = 384; // one CTA per SM; its warps decode the work items of one CTA round in step
+constexpr int      kThreads   = 256; // one CTA per SM; its warps decode the work items of one CTA round in step
 constexpr int      kWarps     = kThreads / 32;
+constexpr int      kGenThreads = 384; // generic decoder (K <= 400)
 constexpr int      kBlocksPerSm = 1;
-constexpr int      kMaxChunks = 48;  // ceil(384 / 8)
 constexpr int      kMaxL      = 384;
+constexpr int      kMaxGroups = kMaxL / 4;  // row groups of 4 trellis rows
+constexpr uint32_t kGroupBytes = 512;       // one row group of a warp in every stream / array: [lane][4 rows] 32-bit words
+// ---- main fast path: beta checkpoints every kCkRows rows in shared memory, an 8-row chunk of beta in registers ----
+constexpr int      kCkRows    = 16;
+constexpr int      kMaxCk     = kMaxL / kCkRows;      // 24 checkpoints of 32 B per thread
+constexpr int      kWarpSmem  = kMaxCk * 1024;        // shared memory of one warp: its checkpoints [ck][half][lane] 128-bit
+// ---- general path (L % 4 != 0, tracked tier) and exact variant: staged chunks of 8 rows (TMA ring), an 8-row chunk of
+// ---- beta in shared memory, checkpoints every 8 rows in HBM.  They live in the same per-warp shared memory (a warp runs
+// ---- one variant at a time): [ring kStages x kStageBytes | beta chunk 8 rows x 2 x 32 lanes x 16 B]
+constexpr int      kChunk     = 8;
+constexpr int      kMaxChunks = 48;  // ceil(384 / 8)
 constexpr int      kChkAhead  = 4;   // forward pass: checkpoints are prefetched into L2 this many chunks ahead
 constexpr int      kStages    = 3;   // chunks in flight per warp (TMA bulk copies, one mbarrier per stage)
 constexpr int      kStageBytes = 3072;  // [sys | par | A or E] x 1 KB: 8 rows of all the code blocks of a warp
+constexpr int      kSmLanes   = 32;     // stride (in 128-bit words) between the two halves / the rows of the beta chunk
+static_assert(kStages * kStageBytes + kChunk * 2 * 32 * 16 <= kWarpSmem, "general path must fit the warp's shared memory");
 // per-warp-slot workspace strides are not powers of two: warps run in near lock step, and power-of-two
 // strides would send all of them to the same L2 slices / HBM channels at once
-constexpr size_t   kXArrayBytes16 = (size_t)(kMaxL + 1) * 128;  // one A or E array: rows of 32 words (all blocks of a warp)
-constexpr size_t   kXArrayBytes8  = (size_t)(100 + 1) * 128;    // W = 8: K <= 800, L <= 100
+constexpr size_t   kXArrayBytes16 = (size_t)(kMaxGroups + 1) * kGroupBytes;  // one A or E array (all blocks of a warp)
+constexpr size_t   kXArrayBytes8  = (size_t)(100 / 4 + 1) * kGroupBytes;     // W = 8: K <= 800, L <= 100
 constexpr size_t   kChkSlotBytes  = (size_t)kMaxChunks * 1024 + 128;
 constexpr int      kStagePad  = 4;   // int16 of padding per window in to_internal_kernel's staged copy
 constexpr int      kExactRows = 4;   // rows next to a known-state boundary always use exact arithmetic
@@ -66,6 +78,10 @@ constexpr int      kNegInf    = -10000;
 constexpr uint32_t kNegInf2   = 0xD8F0D8F0u;  // (-10000, -10000)
 constexpr uint32_t kMax2      = 0x7FFF7FFFu;
 constexpr uint32_t kMin2      = 0x80008000u;
+
+// a page of zeros with the geometry of a stream: what a half iteration reads where it has no input (DEC2 has no
+// separate systematic stream, the first half iteration has no a-priori values) -- keeps the loops branch free
+__device__ uint4 g_zero_page[(kMaxGroups + 1) * 32];
 
 __constant__ uint32_t c_crc_tab[2][256];
 
@@ -226,37 +242,49 @@ __device__ __forceinline__ void normalize(uint32_t s[8])
 }
 
 // ---- per-thread decode context ---------------------------------------------------------------------
-// A work item is up to 32/(W/2) code blocks of equal K decoded by one warp.  Its inputs sit in HBM in an
-// item-interleaved layout (to_internal_kernel): [stream][row group of 4][block][thread][4 rows x 2 windows],
-// so the inputs of one 8-row chunk of ALL the warp's blocks are one contiguous piece per stream: one bulk copy.
+// A work item is up to 32/(W/2) code blocks of equal K decoded by one warp.  Every stream of its inputs and both
+// extrinsic arrays have ONE geometry: [row group of 4][lane of the warp][4 rows] 32-bit words (two windows each), 512
+// bytes per row group: lane = block * W/2 + thread, so the words a thread needs for 4 consecutive trellis rows are one
+// 128-bit load, and a warp reads whole 512-byte pieces.  to_internal_kernel writes the inputs that way (a partial item
+// leaves the lanes of its missing blocks unused).
 template <int W>
 struct WinCtx {
   uint32_t K, L;
   int      t;         // 0..W/2-1: owns windows 2t (low half) and 2t+1 (high half)
   int      lane, grp;
-  uint32_t g_stride;  // bytes of one row group of all the item's blocks (count * 8W)
-  uint32_t sp_off;    // byte offset of this thread's 16 bytes inside a row group
-  uint32_t s_bytes;   // bytes per input stream of the item
+  uint32_t sp_off;    // byte offset of this thread's 16 bytes inside a row group of the INPUT streams (the lanes of a
+                      // missing block of a partial item shadow block 0)
+  uint32_t s_bytes;   // bytes per input stream of the item (ngroups * 512)
   uint32_t ngroups;   // row groups per stream (L rounded up to 4, / 4)
   bool     noap;      // first half iteration of a block: there is no a-priori information yet (A reads as zero and is
                       // neither fetched nor, unless a hard decision can come before DEC2 has written it, cleared)
   const char*     in_item;  // the item's sys | par0 | par1 streams
   const int16_t*  tail;     // this block's 12 tail samples
-  uint32_t*       A32;  // [row][32 lanes] words: extrinsic of DEC2 minus E, natural order (= a-priori of DEC1)
-  uint32_t*       E32;  // [row][32 lanes] words: a-posteriori of DEC1 minus A, in DEC2's interleaved order
+  uint32_t*       A32;  // extrinsic of DEC2 minus E, natural order (= a-priori of DEC1); word of (row k, lane) = ae_word(k, lane)
+  uint32_t*       E32;  // a-posteriori of DEC1 minus A, in DEC2's interleaved order
                         // (each array is written scattered by its producer and read linearly by its consumer)
   const uint32_t* R;    // CRC modes: per-bit CRC contributions of this half iteration's trellis positions,
                         // [row][window] (lte_tables.h:crc_pos_tables), offset to this thread's window pair;
                         // nullptr when no block of the warp checks a CRC
-  uint4*          chk;  // beta checkpoints [chunk][half][32 lanes], already offset by lane
-  uint4*          sm;   // chunk of beta: [(s*2 + h)*kThreads], already offset by tid
-  char*           stages;  // the warp's kStages staging buffers: [sys 1 KB | par 1 KB | A or E rows 1 KB]
+  uint4*          ck;   // main fast path: the warp's checkpoints in shared memory [ck][half][32 lanes], offset by lane
+  uint4*          chk;  // general / exact path: beta checkpoints in HBM [chunk][half][32 lanes], already offset by lane
+  uint4*          sm;   // general / exact path: chunk of beta in the warp's shared memory [(s*2 + h)*kSmLanes], offset by lane
+  char*           stages;  // general path: the warp's kStages staging buffers: [sys 1 KB | par 1 KB | A or E rows 1 KB]
   uint64_t*       mbar;    // the warp's kStages mbarriers
-  const uint16_t* rowtab;  // [2][kMaxL]    128 x destination row (= its byte offset in A / E) of row k: dir 0 = pi (DEC2
-                           //               writes A), 1 = pi^-1 (DEC1 writes E)
-  const uint16_t* wtab;    // [2][kMaxL][8] destination windows of row k's window pair 2t, 2t+1 as byte offsets inside the
-                           //               code block's 32 bytes of the row: low byte / high byte = 2 x window
+  const uint32_t* stab;    // [2][kMaxGroups][W/2][4] scatter table, offset by t*4: where the differenced outputs of row k's
+                           // window pair go, as byte offsets inside the block's part of the array (low / high 16 bits =
+                           // window 2t / 2t+1): dir 0 = pi (DEC2 writes A), 1 = pi^-1 (DEC1 writes E)
 };
+constexpr uint32_t kStabDir = kMaxGroups * 8 * 4;  // 32-bit entries per direction (sized for W = 16)
+
+// 32-bit word of (row k, lane) in an extrinsic array
+__device__ __forceinline__ uint32_t ae_word(uint32_t k, uint32_t lane) { return (k >> 2) * 128u + lane * 4u + (k & 3u); }
+// scatter-table entry of row k for a thread whose stab pointer is already offset by t*4
+template <int W>
+__device__ __forceinline__ uint32_t stab_at(const uint32_t* stab, uint32_t dir, uint32_t k)
+{
+  return stab[dir * kStabDir + (k >> 2) * (W / 2 * 4) + (k & 3u)];
+}
 
 // the inputs of 4 consecutive trellis rows (one row group) for this thread's window pair
 struct Group {
@@ -313,8 +341,8 @@ __device__ __forceinline__ void pipe_issue(const WinCtx<W>& c, bool dec2, Pipe& 
     // lane i prepares and issues copy i (DEC1: sys, par0, A; DEC2: par1, E): the operands are computed once, SIMD,
     // and the bulk-copy instruction -- which takes uniform registers -- runs once per active lane
     const uint32_t ch     = (uint32_t)p.ch;
-    const uint32_t gbytes = min(2u, c.ngroups - 2 * ch) * c.g_stride;
-    const uint32_t xbytes = min(8u, c.L - 8 * ch) * 128u;
+    const uint32_t gbytes = min(2u, c.ngroups - 2 * ch) * kGroupBytes;
+    const uint32_t xbytes = gbytes;  // the extrinsic arrays have the geometry of a stream
     const uint32_t mb     = smem_u32(c.mbar + slot);
     const uint32_t nc     = (dec2 || c.noap) ? 2u : 3u;
     const uint32_t i      = (uint32_t)c.lane;
@@ -323,7 +351,7 @@ __device__ __forceinline__ void pipe_issue(const WinCtx<W>& c, bool dec2, Pipe& 
       const bool     isx    = i == (dec2 ? 1u : 2u);
       const uint32_t stream = dec2 ? 2u : i;
       const char*    src    = isx ? reinterpret_cast<const char*>(dec2 ? c.E32 : c.A32) + (size_t)ch * 1024
-                                  : c.in_item + (size_t)ch * 2 * c.g_stride + (size_t)stream * c.s_bytes;
+                                  : c.in_item + (size_t)ch * 2 * kGroupBytes + (size_t)stream * c.s_bytes;
       const uint32_t dst    = smem_u32(c.stages + slot * kStageBytes) + (isx ? 2048u : dec2 ? 1024u : i * 1024u);
       bulk_g2s(dst, src, isx ? xbytes : gbytes, mb);
     }
@@ -383,12 +411,11 @@ __device__ __forceinline__ void pipe_release(const WinCtx<W>& c, bool dec2, Pipe
 template <int W>
 __device__ __forceinline__ void load_group(const WinCtx<W>& c, bool dec2, const char* st, int g, Group& q)
 {
-  const uint4     ys = *reinterpret_cast<const uint4*>(st + 1024 + g * c.g_stride + c.sp_off);
-  const uint32_t* xr = reinterpret_cast<const uint32_t*>(st + 2048 + g * 512) + c.lane;
-  const uint4     xs = *reinterpret_cast<const uint4*>(st + g * c.g_stride + c.sp_off);
+  const uint4 ys = *reinterpret_cast<const uint4*>(st + 1024 + g * kGroupBytes + c.sp_off);
+  const uint4 xa = *reinterpret_cast<const uint4*>(st + 2048 + g * kGroupBytes + c.lane * 16);
+  const uint4 xs = *reinterpret_cast<const uint4*>(st + g * kGroupBytes + c.sp_off);
   q.y[0] = ys.x; q.y[1] = ys.y; q.y[2] = ys.z; q.y[3] = ys.w;
-#pragma unroll
-  for (int r = 0; r < 4; r++) q.aux[r] = xr[r * 32];
+  q.aux[0] = xa.x; q.aux[1] = xa.y; q.aux[2] = xa.z; q.aux[3] = xa.w;
   q.x[0] = wadd2(q.aux[0], xs.x); q.x[1] = wadd2(q.aux[1], xs.y);
   q.x[2] = wadd2(q.aux[2], xs.z); q.x[3] = wadd2(q.aux[3], xs.w);
 }
@@ -422,15 +449,15 @@ struct RawRow {
 template <int W>
 __device__ __forceinline__ void issue_row(const WinCtx<W>& c, bool dec2, uint32_t k, RawRow& q)
 {
-  const char* gp = c.in_item + (size_t)(k >> 2) * c.g_stride + c.sp_off + (k & 3) * 4;
+  const char* gp = c.in_item + (size_t)(k >> 2) * kGroupBytes + c.sp_off + (k & 3) * 4;
   if (!dec2) {
     q.a = __ldg(reinterpret_cast<const uint32_t*>(gp));
     q.b = __ldg(reinterpret_cast<const uint32_t*>(gp + c.s_bytes));
-    q.c = c.noap ? 0u : c.A32[k * 32 + c.lane];
+    q.c = c.noap ? 0u : c.A32[ae_word(k, c.lane)];
   } else {
     q.a = 0;
     q.b = __ldg(reinterpret_cast<const uint32_t*>(gp + 2 * (size_t)c.s_bytes));
-    q.c = c.E32[k * 32 + c.lane];
+    q.c = c.E32[ae_word(k, c.lane)];
   }
 }
 
@@ -450,7 +477,7 @@ __device__ __forceinline__ void finish_row_exact(bool dec2, const RawRow& q, uin
 template <int W>
 __device__ __forceinline__ char* out_base(const WinCtx<W>& c, bool dec2)
 {
-  return reinterpret_cast<char*>(dec2 ? c.A32 : c.E32) + c.grp * (2 * W);
+  return reinterpret_cast<char*>(dec2 ? c.A32 : c.E32) + c.grp * (W / 2 * 16);
 }
 
 template <int W, bool HARD>
@@ -464,13 +491,10 @@ __device__ __forceinline__ void store_diff(const WinCtx<W>& c, bool dec2, uint32
     const uint2    rr = *reinterpret_cast<const uint2*>(c.R + k * W);
     crc ^= (rr.x & (uint32_t)((int32_t)(m << 16) >> 31)) ^ (rr.y & (uint32_t)((int32_t)m >> 31));
   }
-  // byte offsets: the row's (a multiple of 128) and the window's (< 32) OR together, the block's 32 bytes are in Y
-  const uint32_t e  = (dec2 ? 0u : (uint32_t)kMaxL) + k;
-  const uint32_t r7 = c.rowtab[e];
-  const uint32_t ww = c.wtab[e * 8 + c.t];
+  const uint32_t e = stab_at<W>(c.stab, dec2 ? 0u : 1u, k);
   if (!Y) Y = out_base<W>(c, dec2);
-  *reinterpret_cast<uint16_t*>(Y + (r7 | (ww & 0xFFu))) = (uint16_t)(d & 0xFFFFu);
-  *reinterpret_cast<uint16_t*>(Y + (r7 | (ww >> 8)))    = (uint16_t)(d >> 16);
+  *reinterpret_cast<uint16_t*>(Y + (e & 0xFFFFu)) = (uint16_t)(d & 0xFFFFu);
+  *reinterpret_cast<uint16_t*>(Y + (e >> 16))     = (uint16_t)(d >> 16);
 }
 template <int W>
 __device__ __forceinline__ void store_out(const WinCtx<W>& c, bool dec2, uint32_t k, uint32_t o, uint32_t aux, Range& rd,
@@ -532,8 +556,8 @@ __device__ __noinline__ void beta_rows_exact(const WinCtx<W> c, bool dec2, int k
     beta_step<false>(s, x, y, sadd2(x, y));
     if (mode == 1 && (k % kChunk) == 0 && k != 0) chk_store<W>(c, k / kChunk - 1, s);
     if (mode == 2) {
-      c.sm[((k - sm_lo - 1) * 2 + 0) * kThreads] = make_uint4(s[0], s[1], s[2], s[3]);
-      c.sm[((k - sm_lo - 1) * 2 + 1) * kThreads] = make_uint4(s[4], s[5], s[6], s[7]);
+      c.sm[((k - sm_lo - 1) * 2 + 0) * kSmLanes] = make_uint4(s[0], s[1], s[2], s[3]);
+      c.sm[((k - sm_lo - 1) * 2 + 1) * kSmLanes] = make_uint4(s[4], s[5], s[6], s[7]);
     }
     if ((k & 1) == 0 && k != 0) {
       normalize<false>(s);
@@ -568,8 +592,8 @@ __device__ __noinline__ void alpha_rows_exact(const WinCtx<W> c, bool dec2, int 
     if (mode == 0) {
       alpha_step<false>(a, x, y, sadd2(x, y));
     } else {
-      const uint4    b0 = c.sm[((k - sm_lo) * 2 + 0) * kThreads];
-      const uint4    b1 = c.sm[((k - sm_lo) * 2 + 1) * kThreads];
+      const uint4    b0 = c.sm[((k - sm_lo) * 2 + 0) * kSmLanes];
+      const uint4    b1 = c.sm[((k - sm_lo) * 2 + 1) * kSmLanes];
       const uint32_t bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       uint32_t       o = alpha_out_step<false>(a, bb, x, y, sadd2(x, y), unused);
       if (W == 8) o = sra1_2(o);  // the 8-window (sse16) decoder halves its output
@@ -656,8 +680,8 @@ __device__ __noinline__ HalfResult half_iteration_exact(const WinCtx<W> c, bool 
   for (int ch = 0; ch < nchunks; ch++) {
     const int lo = ch * kChunk, hi = min(lo + kChunk, L);
     chk_load<W>(c, ch, st.s);
-    c.sm[((hi - lo - 1) * 2 + 0) * kThreads] = make_uint4(st.s[0], st.s[1], st.s[2], st.s[3]);
-    c.sm[((hi - lo - 1) * 2 + 1) * kThreads] = make_uint4(st.s[4], st.s[5], st.s[6], st.s[7]);
+    c.sm[((hi - lo - 1) * 2 + 0) * kSmLanes] = make_uint4(st.s[0], st.s[1], st.s[2], st.s[3]);
+    c.sm[((hi - lo - 1) * 2 + 1) * kSmLanes] = make_uint4(st.s[4], st.s[5], st.s[6], st.s[7]);
     if (hi != L) normalize<false>(st.s);  // hi is even and non-zero: the backward pass normalised after storing
     beta_rows_exact<W>(c, dec2, hi - 1, lo + 1, 2, lo, &st);
     alpha_rows_exact<W>(c, dec2, lo, hi - 1, 1, lo, 0, &al);
@@ -797,8 +821,8 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
     if (ch + kChkAhead <= ctop) chk_prefetch_l2<W>(c, ch + kChkAhead);
     const char* stg = pipe_wait<W>(c, p);
     // rebuild B[lo+1 .. hi] into shared memory, slot (k - lo - 1) holds B[k]
-    c.sm[((hi - lo - 1) * 2 + 0) * kThreads] = make_uint4(s[0], s[1], s[2], s[3]);
-    c.sm[((hi - lo - 1) * 2 + 1) * kThreads] = make_uint4(s[4], s[5], s[6], s[7]);
+    c.sm[((hi - lo - 1) * 2 + 0) * kSmLanes] = make_uint4(s[0], s[1], s[2], s[3]);
+    c.sm[((hi - lo - 1) * 2 + 1) * kSmLanes] = make_uint4(s[4], s[5], s[6], s[7]);
     if (hi != L) {  // hi is even and non-zero: the backward pass normalised after storing
       if (hi <= kf)
         normalize<true>(s);
@@ -818,13 +842,13 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
       if (!FULL && lo + g * 4 > kf) continue;
       Group q;
       load_group<W>(c, dec2, stg, g, q);
-      uint4* bs = c.sm + (g * 4 - 1) * 2 * kThreads;
+      uint4* bs = c.sm + (g * 4 - 1) * 2 * kSmLanes;
 #pragma unroll
       for (int r = 3; r >= 0; r--) {
         if (r == 0 && g == 0) continue;  // B[lo] belongs to the chunk below
         beta_step<true>(s, q.x[r], q.y[r], wadd2(q.x[r], q.y[r]));
-        bs[(r * 2 + 0) * kThreads] = make_uint4(s[0], s[1], s[2], s[3]);
-        bs[(r * 2 + 1) * kThreads] = make_uint4(s[4], s[5], s[6], s[7]);
+        bs[(r * 2 + 0) * kSmLanes] = make_uint4(s[0], s[1], s[2], s[3]);
+        bs[(r * 2 + 1) * kSmLanes] = make_uint4(s[4], s[5], s[6], s[7]);
         if ((r & 1) == 0) normalize<true>(s);
       }
     }
@@ -847,11 +871,11 @@ __device__ __forceinline__ HalfResult half_iteration_fast(const WinCtx<W>& c, bo
       if (!FULL && lo + g * 4 > kf) continue;
       Group q;
       load_group<W>(c, dec2, stg, g, q);
-      const uint4* bs = c.sm + g * 4 * 2 * kThreads;
+      const uint4* bs = c.sm + g * 4 * 2 * kSmLanes;
 #pragma unroll
       for (int r = 0; r < 4; r++) {
-        const uint4    b0 = bs[(r * 2 + 0) * kThreads];
-        const uint4    b1 = bs[(r * 2 + 1) * kThreads];
+        const uint4    b0 = bs[(r * 2 + 0) * kSmLanes];
+        const uint4    b1 = bs[(r * 2 + 1) * kSmLanes];
         const uint32_t bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         if (W == 8) {  // the 8-window (sse16) decoder halves its output before the extrinsic subtraction
           const uint32_t o = sra1_2(alpha_out_step<true, TRACK>(a, bb, q.x[r], q.y[r], wadd2(q.x[r], q.y[r]), rm));
@@ -921,17 +945,357 @@ __device__ __forceinline__ HalfResult half_fast(const WinCtx<W>& c, bool dec2, i
                          : half_iteration_fast<W, TRACK, EDGE, HARD, false>(c, dec2, G, p);
 }
 
-// QPP of this K as destination tables, computed from (f1, f2) by the whole CTA:
+// =====================================================================================================================
+// MAIN FAST PATH (L % 16 == 0: K = 6144, 5888, ... 1024): no staging ring, no checkpoints in HBM.
+//   * inputs come straight from HBM / L2 into registers: one 128-bit load per stream and row group, issued one to two
+//     8-row units ahead of their use (plus L2 prefetches further ahead in the backward pass);
+//   * the backward pass keeps a checkpoint every 16 rows in the warp's SHARED memory (24 x 32 B per thread);
+//   * the forward pass works on 16-row chunks: from the checkpoint it first runs beta down the upper 8 rows (stage A),
+//     then rebuilds the lower 8 rows of beta INTO REGISTERS and runs alpha + output over them (stage B), then does the
+//     same for the upper 8 rows (stage C).  1.4 beta steps per row instead of 1, but the checkpoints and the rebuilt
+//     chunk never leave the SM: DRAM sees the inputs, A / E and nothing else;
+//   * alpha + output step with the systematic term factored out: with ay = alpha + y, the bit-1 candidates are x + n',
+//     n' in {alpha, ay}, so M1 = x + max(beta + n'), alpha' = max(n' + x, m) is one fused add-max per state and the
+//     stored value out - aux = (M1' + sys) - M0 needs no x + y at all: 34 packed instructions per row instead of 39;
+//   * NORM = 4 (tiers without bookkeeping): the state metrics are normalised every FOUR rows instead of the reference's
+//     two -- beta after the rows k = 0 mod 4, alpha after the rows k = 2 mod 4.  A normalisation subtracts the same
+//     value from all eight metrics, which the outputs (differences) never see, so any schedule gives the reference's
+//     bits as long as nothing wraps: after a normalisation the metrics lie in [-3G, 3G] (every state reaches every
+//     state in 3 steps; the branch metrics of one step span at most |x| + |y| <= G), a step moves them by at most G,
+//     and with the two schedules interleaved the alpha entering row k and the beta above it have TOGETHER taken at
+//     most 4 steps since their normalisations: |alpha + branch + beta| <= (3 + 3 + 4 + 1) G = 11 G, the bound of the
+//     static tier (kStaticFastG); a single recursion stays within 7 G; next to the known start state (0, -10000 x 7)
+//     the sums stay above -10000 - 7 G.  The beta boundary vector (after the 40 warm-up rows) is normalised too.
+//     NORM = 2 follows the reference's schedule exactly and carries the tracked tier's bookkeeping.
+// =====================================================================================================================
+struct Unit {  // two consecutive row groups (8 rows) of this thread's window pair
+  uint4 s[2], p[2], a[2];  // systematic, parity, a-priori words
+};
+struct Rows4 {
+  uint32_t x[4], y[4];
+};
+
+__device__ __forceinline__ uint4 ld128(const char* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void  pf_l2(const char* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// groups at byte offsets off and off + 512 from this thread's stream pointers
+__device__ __forceinline__ void load_unit(const char* ps, const char* pp, const char* pa, int off, Unit& u)
+{
+  u.s[0] = ld128(ps + off);
+  u.p[0] = ld128(pp + off);
+  u.a[0] = ld128(pa + off);
+  u.s[1] = ld128(ps + off + (int)kGroupBytes);
+  u.p[1] = ld128(pp + off + (int)kGroupBytes);
+  u.a[1] = ld128(pa + off + (int)kGroupBytes);
+}
+__device__ __forceinline__ void prefetch_unit(const char* ps, const char* pp, const char* pa, int off)
+{
+  pf_l2(ps + off);
+  pf_l2(pp + off);
+  pf_l2(pa + off);
+  pf_l2(ps + off + (int)kGroupBytes);
+  pf_l2(pp + off + (int)kGroupBytes);
+  pf_l2(pa + off + (int)kGroupBytes);
+}
+
+__device__ __forceinline__ void rows_of(const uint4& s, const uint4& p, const uint4& a, Rows4& q)
+{
+  q.x[0] = wadd2(a.x, s.x); q.x[1] = wadd2(a.y, s.y); q.x[2] = wadd2(a.z, s.z); q.x[3] = wadd2(a.w, s.w);
+  q.y[0] = p.x; q.y[1] = p.y; q.y[2] = p.z; q.y[3] = p.w;
+}
+
+// beta over one row group, rows 4g+3 .. 4g.  skip0: no normalisation after the group's last row (row 0, NORM = 2)
+template <int NORM, bool TRACK>
+__device__ __forceinline__ void beta_group(uint32_t s[8], const Rows4& q, Range& rb, bool skip0)
+{
+#pragma unroll
+  for (int r = 3; r >= 0; r--) {
+    beta_step<true>(s, q.x[r], q.y[r], wadd2(q.x[r], q.y[r]));
+    if (NORM == 4 ? r == 0 : (r & 1) == 0) {
+      if (r != 0 || !skip0) {
+        normalize<true>(s);
+        if (TRACK) rb.add8(s);
+      }
+    }
+  }
+}
+
+// alpha over one row group without output (warm-up).  skip0: no normalisation after the group's first row (NORM = 2)
+template <int NORM, bool TRACK>
+__device__ __forceinline__ void alpha_group(uint32_t a[8], const Rows4& q, Range& ra, bool skip0)
+{
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    alpha_step<true>(a, q.x[r], q.y[r], wadd2(q.x[r], q.y[r]));
+    if (NORM == 4 ? r == 2 : (r & 1) == 0) {
+      if (r != 0 || !skip0) {
+        normalize<true>(a);
+        if (TRACK) ra.add8(a);
+      }
+    }
+  }
+}
+
+// alpha recursion + output with the systematic term factored out (see above).  Returns the a-posteriori value minus
+// the a-priori value (what is stored): (M1' + sys) - M0 with sys = x - aux.
+template <int W, bool TRACK>
+__device__ __forceinline__ uint32_t alpha_out2(uint32_t a[8], const uint32_t bb[8], uint32_t x, uint32_t y, uint32_t sys,
+                                               uint32_t aux, Range& rm)
+{
+  uint32_t ay[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) ay[i] = wadd2(a[i], y);
+  const uint32_t m[8] = {a[0], ay[3], ay[4], a[7], a[1], ay[2], ay[5], a[6]};   // bit-0 branch into state i
+  const uint32_t n[8] = {ay[1], a[2], a[5], ay[6], ay[0], a[3], a[4], ay[7]};   // bit-1 branch into state i, minus x
+  uint32_t M0 = wadd2(bb[0], m[0]), M1 = wadd2(bb[0], n[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) {
+    M0 = addmax2(bb[i], m[i], M0);
+    M1 = addmax2(bb[i], n[i], M1);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = addmax2(n[i], x, m[i]);
+  if (TRACK || W == 8) {
+    const uint32_t M1x = wadd2(M1, x);
+    if (TRACK) rm.add2v(M0, M1x);
+    uint32_t o = wsub2(M1x, M0);
+    if (W == 8) o = sra1_2(o);  // the 8-window (sse16) decoder halves its output before the extrinsic subtraction
+    return wsub2(o, aux);
+  }
+  return wsub2(wadd2(M1, sys), M0);
+}
+
+// alpha + output over one row group with the rebuilt beta in registers: B[i] is the beta above row k0 + i
+template <int W, int NORM, bool TRACK, bool HARD>
+__device__ __forceinline__ void fwd_group(const WinCtx<W>& c, const uint32_t* stab_dir, uint32_t k0, uint32_t a[8],
+                                          const uint32_t (*B)[8], const uint4& sv, const uint4& pv, const uint4& av, char* Y,
+                                          Range& ra, Range& rm, Range& rd, uint32_t& crc, bool skip0)
+{
+  const uint4    e4 = *reinterpret_cast<const uint4*>(stab_dir + (k0 >> 2) * (W / 2 * 4));
+  const uint32_t sa[4] = {sv.x, sv.y, sv.z, sv.w}, pa[4] = {pv.x, pv.y, pv.z, pv.w}, aa[4] = {av.x, av.y, av.z, av.w};
+  const uint32_t ea[4] = {e4.x, e4.y, e4.z, e4.w};
+  uint32_t       d[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const uint32_t x = wadd2(aa[r], sa[r]);
+    d[r] = alpha_out2<W, TRACK>(a, B[r], x, pa[r], sa[r], aa[r], rm);
+    if (HARD) {
+      // sign bit of -(max(v, -1)) is set exactly when v > 0 (no overflow: max(v,-1) >= -1)
+      const uint32_t m  = wneg2(max2(wadd2(d[r], aa[r]), 0xFFFFFFFFu));
+      const uint2    rr = *reinterpret_cast<const uint2*>(c.R + (k0 + r) * W);
+      crc ^= (rr.x & (uint32_t)((int32_t)(m << 16) >> 31)) ^ (rr.y & (uint32_t)((int32_t)m >> 31));
+    }
+    *reinterpret_cast<uint16_t*>(Y + (ea[r] & 0xFFFFu)) = (uint16_t)(d[r] & 0xFFFFu);
+    *reinterpret_cast<uint16_t*>(Y + (ea[r] >> 16))     = (uint16_t)(d[r] >> 16);
+    if (NORM == 4 ? r == 2 : (r & 1) == 0) {
+      if (r != 0 || !skip0) {
+        normalize<true>(a);
+        if (TRACK) ra.add8(a);
+      }
+    }
+  }
+  rd.add2v(d[0], d[1]);
+  rd.add2v(d[2], d[3]);
+}
+
+// rebuild beta over the 8 rows b .. b+7 into registers: in: s = beta above row b+7 (as the backward pass left it BEFORE
+// normalising it; top_norm: it was normalised afterwards, i.e. it is not the window's boundary vector).
+// out: B[i] = beta above row b + i, i = 0..7 (values before their normalisation, like the reference stores them).
+template <int NORM>
+__device__ __forceinline__ void rebuild8(uint32_t s[8], bool top_norm, const Unit& u, uint32_t (*B)[8])
+{
+  Range unused;
+#pragma unroll
+  for (int i = 0; i < 8; i++) B[7][i] = s[i];
+  if (top_norm) normalize<true>(s);
+#pragma unroll
+  for (int g = 1; g >= 0; g--) {
+    Rows4 q;
+    rows_of(u.s[g], u.p[g], u.a[g], q);
+#pragma unroll
+    for (int r = 3; r >= 0; r--) {
+      if (g == 0 && r == 0) continue;  // the beta above row b - 1 belongs to the chunk below
+      beta_step<true>(s, q.x[r], q.y[r], wadd2(q.x[r], q.y[r]));
+#pragma unroll
+      for (int i = 0; i < 8; i++) B[g * 4 + r - 1][i] = s[i];
+      if (NORM == 4 ? r == 0 : (r & 1) == 0) normalize<true>(s);
+    }
+  }
+  (void)unused;
+}
+
+template <int W, int NORM, bool TRACK, bool HARD>
+__device__ __forceinline__ HalfResult half_fast2(const WinCtx<W>& c, bool dec2, int G)
+{
+  constexpr int WH = W / 2;
+  const int     L  = (int)c.L;
+  const int     nc = L >> 4;      // 16-row chunks, numbered from the top of the window
+  const int     ng = L >> 2;      // row groups
+  constexpr int GB = (int)kGroupBytes;
+  // this thread's 16 bytes of row group 0 of the three streams of this half iteration
+  const char* const zp = reinterpret_cast<const char*>(g_zero_page) + c.lane * 16;
+  const char* const ps = dec2 ? zp : c.in_item + c.sp_off;
+  const char* const pp = c.in_item + (dec2 ? 2u : 1u) * (size_t)c.s_bytes + c.sp_off;
+  const char* const pa = dec2 ? reinterpret_cast<const char*>(c.E32) + c.lane * 16
+                              : c.noap ? zp : reinterpret_cast<const char*>(c.A32) + c.lane * 16;
+  Range rb, ra, rm, rd;
+  rb.reset(); ra.reset(); rd.reset();
+  rm.hi = kMin2; rm.lo = kMax2;
+  uint32_t crc = 0;
+  uint32_t s[8];
+  Unit     cur, nxt;
+
+  // ---------------- backward pass: boundary metrics from the next window's first 40 rows ----------------
+  load_unit(ps, pp, pa, 8 * GB, cur);
+#pragma unroll 1
+  for (int i = 1; i <= 6 && 2 * i <= ng; i++) prefetch_unit(ps, pp, pa, (ng - 2 * i) * GB);  // L2: the top three chunks
+#pragma unroll
+  for (int i = 0; i < 8; i++) s[i] = kNegInf2;
+#pragma unroll 1
+  for (int u = 4; u >= 0; u--) {
+    load_unit(ps, pp, pa, u > 0 ? (2 * u - 2) * GB : (ng - 2) * GB, nxt);  // next unit below, then the top of the window
+    Rows4 q;
+    rows_of(cur.s[1], cur.p[1], cur.a[1], q);
+    beta_group<NORM, TRACK>(s, q, rb, false);
+    rows_of(cur.s[0], cur.p[0], cur.a[0], q);
+    beta_group<NORM, TRACK>(s, q, rb, NORM == 2 && u == 0);
+    cur = nxt;
+  }
+  exchange_beta_boundary<WH>(s, c.t, c.tail + (dec2 ? 6 : 0));
+  if (TRACK) rb.add8full(s);
+
+  // ---------------- backward pass over the window: a checkpoint every 16 rows ----------------
+  {
+    const char *qs = ps + ng * GB, *qp = pp + ng * GB, *qa = pa + ng * GB;
+#pragma unroll 1
+    for (int j = 0; j < nc; j++) {
+      c.ck[(j * 2 + 0) * 32] = make_uint4(s[0], s[1], s[2], s[3]);
+      c.ck[(j * 2 + 1) * 32] = make_uint4(s[4], s[5], s[6], s[7]);
+      qs -= 4 * GB; qp -= 4 * GB; qa -= 4 * GB;   // the chunk's first row group
+      load_unit(qs, qp, qa, 0, nxt);                // its lower unit
+      if (j + 3 < nc) {                             // L2: two chunks further down
+        prefetch_unit(qs, qp, qa, -10 * GB);
+        prefetch_unit(qs, qp, qa, -12 * GB);
+      }
+      Rows4 q;
+      rows_of(cur.s[1], cur.p[1], cur.a[1], q);
+      beta_group<NORM, TRACK>(s, q, rb, false);
+      rows_of(cur.s[0], cur.p[0], cur.a[0], q);
+      beta_group<NORM, TRACK>(s, q, rb, false);
+      // the upper unit of the chunk below; after the last chunk the first unit of the alpha warm-up
+      if (j + 1 < nc) load_unit(qs, qp, qa, -2 * GB, cur);
+      else load_unit(ps, pp, pa, (ng - 10) * GB, cur);
+      rows_of(nxt.s[1], nxt.p[1], nxt.a[1], q);
+      beta_group<NORM, TRACK>(s, q, rb, false);
+      rows_of(nxt.s[0], nxt.p[0], nxt.a[0], q);
+      beta_group<NORM, TRACK>(s, q, rb, NORM == 2 && j + 1 == nc);
+    }
+  }
+
+  // ---------------- forward pass: boundary metrics from the previous window's last 40 rows ----------------
+  uint32_t a[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = kNegInf2;
+  Unit X, Yb, Z;  // forward chunk: upper unit (stage A), lower unit (stage B), upper unit again (stage C)
+#pragma unroll 1
+  for (int u = 0; u < 5; u++) {
+    if (u < 4) load_unit(ps, pp, pa, (ng - 10 + 2 * u + 2) * GB, nxt);
+    else {  // the first chunk of the forward pass (rows 0..15; the backward pass has just read them)
+      load_unit(ps, pp, pa, 2 * GB, X);
+      load_unit(ps, pp, pa, 0, Yb);
+    }
+    Rows4 q;
+    rows_of(cur.s[0], cur.p[0], cur.a[0], q);
+    alpha_group<NORM, TRACK>(a, q, ra, NORM == 2 && u == 0);
+    rows_of(cur.s[1], cur.p[1], cur.a[1], q);
+    alpha_group<NORM, TRACK>(a, q, ra, false);
+    if (u < 4) cur = nxt;
+  }
+  exchange_alpha_boundary<WH>(a, c.t);
+
+  // ---------------- forward pass over the window, 16 rows at a time ----------------
+  {
+    char* const           Yout = out_base<W>(c, dec2);
+    const uint32_t* const sdir = c.stab + (dec2 ? 0u : kStabDir);
+    const char *qs = ps, *qp = pp, *qa = pa;  // first row group of the chunk
+#pragma unroll 1
+    for (int j = nc - 1; j >= 0; j--) {
+      const uint32_t lo = (uint32_t)(L - 16 * (j + 1));
+      load_unit(qs, qp, qa, 2 * GB, Z);
+      uint32_t B[8][8];
+      // ---- stage A: beta from the checkpoint down the upper 8 rows ----
+      {
+        const uint4 c0 = c.ck[(j * 2 + 0) * 32], c1 = c.ck[(j * 2 + 1) * 32];
+        s[0] = c0.x; s[1] = c0.y; s[2] = c0.z; s[3] = c0.w; s[4] = c1.x; s[5] = c1.y; s[6] = c1.z; s[7] = c1.w;
+        if (j != 0) normalize<true>(s);  // every checkpoint but the boundary vector was normalised after it was stored
+        Rows4 q;
+        rows_of(X.s[1], X.p[1], X.a[1], q);
+        beta_group<NORM, false>(s, q, rb, false);
+        rows_of(X.s[0], X.p[0], X.a[0], q);
+#pragma unroll
+        for (int r = 3; r >= 1; r--) {
+          beta_step<true>(s, q.x[r], q.y[r], wadd2(q.x[r], q.y[r]));
+          if (NORM == 2 && r == 2) normalize<true>(s);
+        }
+        beta_step<true>(s, q.x[0], q.y[0], wadd2(q.x[0], q.y[0]));  // s = beta above row lo + 7, not yet normalised
+      }
+      if (j > 0) load_unit(qs, qp, qa, 6 * GB, X);
+      // ---- stage B: the lower 8 rows ----
+      rebuild8<NORM>(s, true, Yb, B);
+      fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo, a, &B[0], Yb.s[0], Yb.p[0], Yb.a[0], Yout, ra, rm, rd, crc,
+                                      NORM == 2 && lo == 0);
+      fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 4, a, &B[4], Yb.s[1], Yb.p[1], Yb.a[1], Yout, ra, rm, rd, crc, false);
+      if (j > 0) load_unit(qs, qp, qa, 4 * GB, Yb);
+      // ---- stage C: the upper 8 rows ----
+      {
+        const uint4 c0 = c.ck[(j * 2 + 0) * 32], c1 = c.ck[(j * 2 + 1) * 32];
+        s[0] = c0.x; s[1] = c0.y; s[2] = c0.z; s[3] = c0.w; s[4] = c1.x; s[5] = c1.y; s[6] = c1.z; s[7] = c1.w;
+      }
+      rebuild8<NORM>(s, j != 0, Z, B);
+      fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 8, a, &B[0], Z.s[0], Z.p[0], Z.a[0], Yout, ra, rm, rd, crc, false);
+      fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 12, a, &B[4], Z.s[1], Z.p[1], Z.a[1], Yout, ra, rm, rd, crc, false);
+      qs += 4 * GB; qp += 4 * GB; qa += 4 * GB;
+    }
+  }
+  __syncwarp();
+
+  HalfResult res;
+  res.dmax = range_absmax(rd);
+  res.crc  = crc;
+  bool ok  = true;
+  if (TRACK) {  // the proof obligations of the tracked tier (see half_iteration_fast)
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int bh = h ? hi16(rb.hi) : lo16(rb.hi), bl = h ? hi16(rb.lo) : lo16(rb.lo);
+      const int ah = h ? hi16(ra.hi) : lo16(ra.hi), al = h ? hi16(ra.lo) : lo16(ra.lo);
+      const int mh = h ? hi16(rm.hi) : lo16(rm.hi), ml = h ? hi16(rm.lo) : lo16(rm.lo);
+      ok = ok && (bh + 2 * G <= 32767) && (bl - 2 * G >= -32768) && (bh - bl + 4 * G <= 32767);
+      ok = ok && (ah + 2 * G <= 32767) && (al - 2 * G >= -32768) && (ah - al + 4 * G <= 32767);
+      ok = ok && (bh + ah + 5 * G <= 32767) && (bl + al - 5 * G >= -32768);
+      ok = ok && (mh < ml || mh - ml <= 32767);
+    }
+    ok = ok && (G <= kMaxFastG);
+  } else {
+    ok = G <= kStaticFastG;
+  }
+  res.proven = ok;
+  return res;
+}
+
+// QPP of this K as a scatter table, computed from (f1, f2) by the whole CTA:
 //   pi(d*L + k) = pi(k) + L * d * (f1 + f2*d*L + 2*f2*k)  (mod K = W*L), so with pi(k) = w0*L + r every window
 //   d of row k lands in row r, window (w0 + d*(f1 + f2*d*L) + 2*f2*d*k) mod W.
 // dir 0 holds pi (where DEC2's row k goes in natural order), dir 1 its inverse (where natural row r goes in
-// DEC2's order).
+// DEC2's order).  An entry is the pair of byte offsets (16 bits each) of the destinations of windows 2t and 2t+1
+// inside the code block's part of the array: row group * 512 + (row & 3) * 4 + (window / 2) * 16 + (window & 1) * 2.
 template <int W>
-__device__ void build_tables(uint32_t K, uint32_t f1, uint32_t f2, uint16_t* rowtab, uint16_t* wtab)
+__device__ void build_tables(uint32_t K, uint32_t f1, uint32_t f2, uint32_t* stab)
 {
+  constexpr uint32_t WH = W / 2;
   const uint32_t L  = K / W;
   const uint32_t mK = (uint32_t)(0x100000000ull / K);
   const uint32_t mL = (uint32_t)((0x100000000ull + L - 1) / L);
+  auto off = [](uint32_t row, uint32_t w) { return (row >> 2) * kGroupBytes + (row & 3u) * 4u + (w >> 1) * 16u + (w & 1u) * 2u; };
   for (uint32_t k = threadIdx.x; k < L; k += blockDim.x) {
     const uint32_t v = (f1 + f2 * k) * k;  // k < L <= 384 keeps it below 2^32
     uint32_t       p = v - __umulhi(v, mK) * K;
@@ -945,13 +1309,11 @@ __device__ void build_tables(uint32_t K, uint32_t f1, uint32_t f2, uint16_t* row
       fw |= (uint64_t)w << (4 * d);
       iv |= (uint64_t)d << (4 * w);
     }
-    rowtab[k]         = (uint16_t)(r * 128);
-    rowtab[kMaxL + r] = (uint16_t)(k * 128);
 #pragma unroll
-    for (uint32_t t = 0; t < (uint32_t)W / 2; t++) {  // nibbles 2t, 2t+1 -> 2 x window in the low / high byte
-      const uint32_t f = (uint32_t)(fw >> (8 * t)) & 0xFFu, v = (uint32_t)(iv >> (8 * t)) & 0xFFu;
-      wtab[8 * k + t]           = (uint16_t)(((f & 15u) << 1) | ((f >> 4) << 9));
-      wtab[8 * (kMaxL + r) + t] = (uint16_t)(((v & 15u) << 1) | ((v >> 4) << 9));
+    for (uint32_t t = 0; t < WH; t++) {  // nibbles 2t, 2t+1: the destination windows of this thread's pair
+      const uint32_t f = (uint32_t)(fw >> (8 * t)) & 0xFFu, u = (uint32_t)(iv >> (8 * t)) & 0xFFu;
+      stab[((k >> 2) * WH + t) * 4 + (k & 3u)]            = off(r, f & 15u) | (off(r, f >> 4) << 16);
+      stab[kStabDir + ((r >> 2) * WH + t) * 4 + (r & 3u)] = off(k, u & 15u) | (off(k, u >> 4) << 16);
     }
   }
 }
@@ -971,11 +1333,9 @@ __device__ void decide(const WinCtx<W>& c, uint8_t* out, bool write)
   static_assert((W * NW + 4 * WH - 1) / (4 * WH) <= 2 * kChunk, "bit strings must fit the beta chunk slots");
   uint32_t* grp_base = reinterpret_cast<uint32_t*>(c.sm - c.t);
   auto      word     = [&](uint32_t f) -> uint32_t& {
-    return grp_base[(((f >> 2) / WH) * kThreads + ((f >> 2) % WH)) * 4 + (f & 3)];
+    return grp_base[(((f >> 2) / WH) * kSmLanes + ((f >> 2) % WH)) * 4 + (f & 3)];
   };
-  const char*     E8 = reinterpret_cast<const char*>(c.E32) + c.grp * (2 * W);
-  const uint16_t* rt = c.rowtab + kMaxL;
-  const uint16_t* wt = c.wtab + kMaxL * 8 + c.t;
+  const char* E8 = reinterpret_cast<const char*>(c.E32) + c.grp * (WH * 16);
   constexpr int NB = 16;  // rows gathered per batch: the E gather is latency bound, keep many loads in flight
   // 32 rows = one word per window.  Rows past L repeat row L - 1: their bits land below the last valid bit of the
   // window's last word, where phase 2 never looks.
@@ -988,11 +1348,10 @@ __device__ void decide(const WinCtx<W>& c, uint8_t* out, bool write)
 #pragma unroll
       for (int j = 0; j < NB; j++) {
         const uint32_t k   = min(k0 + h * NB + j, L - 1);
-        const uint32_t r7 = rt[k];
-        const uint32_t ww = wt[k * 8];
-        el[j] = *reinterpret_cast<const uint16_t*>(E8 + (r7 | (ww & 0xFFu)));
-        eh[j] = *reinterpret_cast<const uint16_t*>(E8 + (r7 | (ww >> 8)));
-        av[j] = c.A32[k * 32 + c.lane];
+        const uint32_t e = stab_at<W>(c.stab, 1u, k);
+        el[j] = *reinterpret_cast<const uint16_t*>(E8 + (e & 0xFFFFu));
+        eh[j] = *reinterpret_cast<const uint16_t*>(E8 + (e >> 16));
+        av[j] = c.A32[ae_word(k, (uint32_t)c.lane)];
       }
 #pragma unroll
       for (int j = 0; j < NB; j++) {
@@ -1064,10 +1423,9 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
 {
   constexpr int WH  = W / 2;
   extern __shared__ uint4 smem[];
-  char*     stages_all = reinterpret_cast<char*>(smem + kChunk * 2 * kThreads);  // [warps][kStages][kStageBytes]
-  uint16_t* rowtab     = reinterpret_cast<uint16_t*>(stages_all + kWarps * kStages * kStageBytes);
-  uint16_t* wtab       = rowtab + 2 * kMaxL;
-  uint64_t* mbar_all   = reinterpret_cast<uint64_t*>(wtab + 2 * kMaxL * 8);
+  char*     warp_sm_all = reinterpret_cast<char*>(smem);                                   // [warps][kWarpSmem]
+  uint32_t* stab        = reinterpret_cast<uint32_t*>(warp_sm_all + kWarps * kWarpSmem);   // [2][kStabDir]
+  uint64_t* mbar_all    = reinterpret_cast<uint64_t*>(stab + 2 * kStabDir);
   __shared__ uint32_t s_item;
 
   const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1091,7 +1449,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
     const uint2 round = a.rounds[rnd];  // (first item, number of items): one item per warp, all of the same K
     {
       const WorkItem w0 = a.items[round.x];
-      build_tables<W>(w0.K, w0.f1, w0.f2, rowtab, wtab);
+      build_tables<W>(w0.K, w0.f1, w0.f2, stab);
     }
     __syncthreads();
     WorkItem wi;
@@ -1109,14 +1467,15 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
       c.lane = lane;
       c.grp  = grp;
       c.ngroups  = (c.L + 3) >> 2;
-      c.g_stride = (uint32_t)wi.count * 8u * W;
       c.sp_off   = b_eff * 8u * W + (uint32_t)t * 16u;
-      c.s_bytes  = c.ngroups * c.g_stride;
-      c.in_item  = reinterpret_cast<const char*>(a.in + (size_t)wi.first * a.in_stride);
+      c.s_bytes  = c.ngroups * kGroupBytes;
+      c.in_item  = reinterpret_cast<const char*>(a.in + (size_t)wi.in_pos * a.in_stride);
       c.tail     = reinterpret_cast<const int16_t*>(c.in_item + 3 * (size_t)c.s_bytes) + b_eff * 32;
-      c.rowtab = rowtab;
-      c.wtab   = wtab;
-      c.stages = stages_all + warp * kStages * kStageBytes;
+      c.stab   = stab + t * 4;
+      char* const warp_sm = warp_sm_all + warp * kWarpSmem;
+      c.ck     = reinterpret_cast<uint4*>(warp_sm) + lane;
+      c.stages = warp_sm;
+      c.sm     = reinterpret_cast<uint4*>(warp_sm + kStages * kStageBytes) + lane;
       c.mbar   = mbar_all + warp * kStages;
       const uint16_t* meta = reinterpret_cast<const uint16_t*>(c.tail + 16);
       const int smax = meta[0], p0max = meta[1], p1max = meta[2];
@@ -1126,15 +1485,6 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
       c.E32 = reinterpret_cast<uint32_t*>(ae + XB);
       c.chk = reinterpret_cast<uint4*>(reinterpret_cast<char*>(a.ws_chk) + (size_t)slot * kChkSlotBytes) + lane;
       c.R   = nullptr;
-      c.sm  = smem + tid;
-
-      // The first half iteration has no a-priori information: its bulk copies skip A and the A part of the warp's
-      // staging buffers is cleared instead (generic-proxy stores; the fence at the top of every half iteration
-      // orders them before the next copies into the same bytes).  A itself is only cleared when a hard decision
-      // can be taken before DEC2 has written every element of it (a single half iteration, or a CRC pass after the
-      // first): 48 KB of stores per work item that the plain K = 6144 / 4 half iterations case does not need.
-      for (int i = lane; i < kStages * 64; i += 32)
-        *reinterpret_cast<uint4*>(c.stages + (i >> 6) * kStageBytes + 2048 + (i & 63) * 16) = make_uint4(0, 0, 0, 0);
 
       uint8_t* out  = a.out + (size_t)cb * a.out_stride;
       uint32_t n    = 0, iters = 0;
@@ -1143,20 +1493,19 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
       const uint32_t crc_mode = a.crc_mode_cb ? a.crc_mode_cb[cb] : a.crc_mode;
       const int      which    = crc_mode == CRC_24A ? 0 : 1;
       const bool     any_crc  = __any_sync(0xFFFFFFFFu, crc_mode != CRC_NONE);
+      const bool     v2       = (c.L & 15u) == 0 && (a.force_exact & 8u) == 0;  // the main fast path takes this block size
       // CRC modes: this thread's window pair in the tables of the block's polynomial ([dir][row][window])
       const uint32_t* Rblk = any_crc ? a.crc_pos + a.crc_pos_off[wi.kidx] + (size_t)which * 2 * c.K + 2 * t : nullptr;
+      // The first half iteration has no a-priori information: it does not read A.  A itself is only cleared when a
+      // hard decision can be taken before DEC2 has written every element of it (a single half iteration, or a CRC
+      // pass after the first): 48 KB of stores per work item that the plain K = 6144 / 4 half iterations case does
+      // not need.
       if (a.max_iter < 2 || any_crc)
-        for (uint32_t k = 0; k < c.L; k++) c.A32[k * 32 + lane] = 0;
+        for (uint32_t i = lane; i < c.ngroups * 128u; i += 32) c.A32[i] = 0;
       do {
         const bool dec2 = (n & 1) != 0;
         c.noap = n == 0;
         if (any_crc) c.R = Rblk + (dec2 ? c.K : 0u);
-        if (dec2)  // see load_group: the sys part of the stages reads as zero in DEC2
-          for (int i = lane; i < kStages * 64; i += 32)
-            *reinterpret_cast<uint4*>(c.stages + (i >> 6) * kStageBytes + (i & 63) * 16) = make_uint4(0, 0, 0, 0);
-        // what the previous half iteration (or the clearing above) stored must be visible to the bulk copies
-        fence_proxy_async();
-        __syncwarp();
         // bound on |x|, |y|, |x + y| of this half iteration
         // A block whose CRC has passed has frozen its output: what its lanes compute from here on is never read (they
         // only keep the warp's shuffles and votes complete), so it neither picks the tier for the blocks that are
@@ -1165,20 +1514,46 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
         const int G  = done ? 0 : Gx + (dec2 ? p1max : p0max);
         HalfResult r;
         bool       fast_ok = false;
+        // what the previous half iteration stored must be visible to this one's loads (other lanes wrote it)
+        __syncwarp();
         // the decision must be warp-uniform: the passes below use full-warp shuffles and votes
-        // force_exact: bit 0 = exact variant only (tests); bits 1, 2 = skip the pure / the static tier (measurements)
-        if (__all_sync(0xFFFFFFFFu, (a.force_exact & 3u) == 0 && G <= kPureFastG)) {
-          r       = any_crc ? half_fast<W, false, false, true>(c, dec2, G, pipe)
-                            : half_fast<W, false, false, false>(c, dec2, G, pipe);
+        // force_exact: bit 0 = exact variant only (tests); bits 1, 2 = skip the pure / the static tier, bit 3 = general
+        // path only (measurements)
+        const bool pure = __all_sync(0xFFFFFFFFu, (a.force_exact & 3u) == 0 && G <= kPureFastG);
+        if (pure && v2) {
+          r       = any_crc ? half_fast2<W, 4, false, true>(c, dec2, G) : half_fast2<W, 4, false, false>(c, dec2, G);
           fast_ok = true;
-        } else if (__all_sync(0xFFFFFFFFu, (a.force_exact & 5u) == 0 && G <= kStaticFastG)) {
-          r       = any_crc ? half_fast<W, false, true, true>(c, dec2, G, pipe)
-                            : half_fast<W, false, true, false>(c, dec2, G, pipe);
-          fast_ok = true;
-        } else if (__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kMaxFastG)) {
-          r       = any_crc ? half_fast<W, true, true, true>(c, dec2, G, pipe)
-                            : half_fast<W, true, true, false>(c, dec2, G, pipe);
-          fast_ok = __all_sync(0xFFFFFFFFu, r.proven || done);
+        } else if (!__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kMaxFastG)) {
+          // nothing: exact variant below
+#ifndef B200_V2ONLY
+        } else {
+          // ---- general path: staged chunks through the TMA ring.  The staging buffers share the warp's shared
+          // memory with the checkpoints of the main path, so every half iteration sets them up itself: no a-priori
+          // input -> the A part reads as zero; DEC2 has no separate systematic input (x = E) -> the sys part reads as
+          // zero (its copies leave that part alone), so both decoders run the same branch-free code.
+          if (c.noap)
+            for (int i = lane; i < kStages * 64; i += 32)
+              *reinterpret_cast<uint4*>(c.stages + (i >> 6) * kStageBytes + 2048 + (i & 63) * 16) = make_uint4(0, 0, 0, 0);
+          if (dec2)
+            for (int i = lane; i < kStages * 64; i += 32)
+              *reinterpret_cast<uint4*>(c.stages + (i >> 6) * kStageBytes + (i & 63) * 16) = make_uint4(0, 0, 0, 0);
+          // generic-proxy writes (the above, the previous half iteration's outputs) before the bulk copies
+          fence_proxy_async();
+          __syncwarp();
+          if (pure) {
+            r       = any_crc ? half_fast<W, false, false, true>(c, dec2, G, pipe)
+                              : half_fast<W, false, false, false>(c, dec2, G, pipe);
+            fast_ok = true;
+          } else if (__all_sync(0xFFFFFFFFu, (a.force_exact & 5u) == 0 && G <= kStaticFastG)) {
+            r       = any_crc ? half_fast<W, false, true, true>(c, dec2, G, pipe)
+                              : half_fast<W, false, true, false>(c, dec2, G, pipe);
+            fast_ok = true;
+          } else {
+            r       = any_crc ? half_fast<W, true, true, true>(c, dec2, G, pipe)
+                              : half_fast<W, true, true, false>(c, dec2, G, pipe);
+            fast_ok = __all_sync(0xFFFFFFFFu, r.proven || done);
+          }
+#endif
         }
         if (!fast_ok) {
           r = half_iteration_exact<W>(c, dec2);
@@ -1359,12 +1734,12 @@ __device__ void gen_half_iteration(const GenCtx& c, bool dec2)
   }
 }
 
-__global__ void __launch_bounds__(kThreads) tdec_gen_kernel(const TdecLaunch a)
+__global__ void __launch_bounds__(kGenThreads) tdec_gen_kernel(const TdecLaunch a)
 {
   constexpr uint32_t KMAX = 400;
-  __shared__ uint16_t s_pi[kThreads / 32][KMAX];
+  __shared__ uint16_t s_pi[kGenThreads / 32][KMAX];
   const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t slot = blockIdx.x * (kThreads / 32) + warp;
+  const uint32_t slot = blockIdx.x * (kGenThreads / 32) + warp;
   for (;;) {
     uint32_t it = 0;
     if (lane == 0) it = atomicAdd(a.counter, 1u);
@@ -1381,7 +1756,7 @@ __global__ void __launch_bounds__(kThreads) tdec_gen_kernel(const TdecLaunch a)
     GenCtx c;
     c.K      = (int)wi.K;
     c.stride = npair;
-    c.in     = reinterpret_cast<const uint32_t*>(a.in + (size_t)wi.first * a.in_stride) + pair_eff;
+    c.in     = reinterpret_cast<const uint32_t*>(a.in + (size_t)wi.in_pos * a.in_stride) + pair_eff;
     c.A      = reinterpret_cast<uint32_t*>(a.ws_ae) + (size_t)slot * 2 * KMAX * 32 + lane;
     c.E      = c.A + KMAX * 32;
     c.beta   = reinterpret_cast<uint4*>(a.ws_chk) + (size_t)slot * (KMAX + 4) * 2 * 32 + lane;
@@ -1461,8 +1836,9 @@ __global__ void __launch_bounds__(kThreads) tdec_gen_kernel(const TdecLaunch a)
 // ---- layout conversion into the decoder's internal layout -----------------------------------------
 // Every code block is stored at its position in the decode schedule (dst_stride int16 per block); the blocks
 // of one work item (`count` blocks of equal K starting at position `first`) are interleaved:
-// window decoders: [sys | par0 | par1] streams; a stream is [row group of 4][block of the item][thread][4 rows]
-//                  32-bit words (two windows each), Lp = L rounded up to 4 rows;
+// window decoders: [sys | par0 | par1] streams; a stream is [row group of 4][lane = block of the item * W/2 + thread]
+//                  [4 rows] 32-bit words (two windows each): 512 bytes per row group whatever the number of blocks in
+//                  the item, Lp = L rounded up to 4 rows;
 //                  then per block 16 int16 holding the 12 tail samples and 16 int16 of meta data:
 //                  max |sys|, max |par0|, max |par1| (uint16) -- the inputs of the fast-path proof.
 // generic decoder: [natural index 3i+j, then the 12 tail samples][block of the item, count rounded up to 2] -- one
@@ -1493,9 +1869,9 @@ __global__ void __launch_bounds__(256) to_internal_kernel(const int16_t* __restr
     cnt   = pl.y >> 8;
     b     = pl.y & 0xFFu;
   } else {
-    const uint32_t per = W ? 64u / W : 64u;  // code blocks per work item
-    first = cb / per * per;
-    cnt   = min(per, gridDim.x - first);
+    const uint32_t ipw = W ? 64u / W : 64u;  // code blocks per work item
+    first = cb / ipw * ipw;
+    cnt   = min(ipw, gridDim.x - first);
     b     = cb - first;
   }
   if (W == 0) {  // generic decoder: value i of the block goes to row i of the item, column b (rows of an even length)
@@ -1505,8 +1881,10 @@ __global__ void __launch_bounds__(256) to_internal_kernel(const int16_t* __restr
     return;
   }
   const uint32_t L = K / W, Lp = (L + 3) & ~3u, WH = W / 2, S = Lp * W;
+  const uint32_t per = 64u / W;                                // lanes are laid out for a full item
   int16_t*       item = dst_all + (size_t)first * dst_stride;  // the work item's interleaved storage
-  int16_t*       tailp = item + 3 * (size_t)cnt * S + b * 32;
+  int16_t*       tailp = item + 3 * (size_t)per * S + b * 32;
+  (void)cnt;
   // the staged copy gives every window kStagePad extra int16 so that the W/2 threads that later read the same
   // row of different windows fall into different shared-memory banks (3L int16 per window is a multiple of 64
   // words for L = 384: an 8-way conflict without the padding)
@@ -1580,7 +1958,7 @@ __global__ void __launch_bounds__(256) to_internal_kernel(const int16_t* __restr
     }
 #pragma unroll
     for (int j = 0; j < 3; j++)
-      reinterpret_cast<uint4*>(item + (size_t)j * cnt * S)[(kg * cnt + b) * WH + t] =
+      reinterpret_cast<uint4*>(item + (size_t)j * per * S)[(kg * per + b) * WH + t] =
           make_uint4(w[j][0], w[j][1], w[j][2], w[j][3]);
   }
   uint32_t mx[3];
@@ -1650,13 +2028,21 @@ uint32_t internal_len(uint32_t K)
   return 3 * Lp * W + 32;
 }
 
+uint32_t internal_positions(uint32_t K, uint32_t n)
+{
+  const uint32_t W = (K % 16 == 0 && K > 800) ? 16u : (K % 8 == 0 && K > 400) ? 8u : 0u;
+  if (W == 0) return n;
+  const uint32_t per = 64u / W;
+  return (n + per - 1) / per * per;
+}
+
 cudaError_t tdec_geometry(int W, int device, TdecGeometry* g)
 {
   int sms = 0;
   cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (e != cudaSuccess) return e;
-  g->threads = kThreads;
-  const size_t warps_per_block = kThreads / 32;
+  g->threads = W ? kThreads : kGenThreads;
+  const size_t warps_per_block = (size_t)g->threads / 32;
   if (W == 0) {
     g->smem   = 0;
     g->blocks = sms * 4;
@@ -1665,8 +2051,7 @@ cudaError_t tdec_geometry(int W, int device, TdecGeometry* g)
     g->ws_chk_bytes = slots * (400 + 4) * 2 * 32 * sizeof(uint4);
     return cudaSuccess;
   }
-  g->smem = (size_t)kChunk * 2 * kThreads * sizeof(uint4) + warps_per_block * kStages * kStageBytes +
-            2 * kMaxL * sizeof(uint16_t) + 2 * kMaxL * 8 * sizeof(uint16_t) + warps_per_block * kStages * sizeof(uint64_t);
+  g->smem = warps_per_block * kWarpSmem + 2 * kStabDir * sizeof(uint32_t) + warps_per_block * kStages * sizeof(uint64_t);
   int per_sm = 0;
   if (W == 16) {
     e = cudaFuncSetAttribute(tdec_win_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
@@ -1693,7 +2078,7 @@ cudaError_t tdec_launch(int W, const TdecGeometry& g, const TdecLaunch& a, cudaS
   if (a.n_items == 0 || (W && a.n_rounds == 0)) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
-  const int want   = W ? (int)a.n_rounds : (int)((a.n_items + (kThreads / 32) - 1) / (kThreads / 32));
+  const int want   = W ? (int)a.n_rounds : (int)((a.n_items + (kGenThreads / 32) - 1) / (kGenThreads / 32));
   const int blocks = want < g.blocks ? want : g.blocks;
   if (W == 16)
     tdec_win_kernel<16><<<blocks, g.threads, g.smem, s>>>(a);
@@ -1709,13 +2094,16 @@ cudaError_t to_internal_launch(const int16_t* src, uint32_t src_stride, const ui
                                const uint2* place, uint32_t n_cb, cudaStream_t s)
 {
   if (n_cb == 0) return cudaSuccess;
-  static bool attr_set = false;
+  static bool attr_set[64] = {};  // per device: function attributes belong to the device's context
+  int         dev = 0;
+  cudaError_t e   = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
   const size_t smem = src_format == 0 ? (3 * 6144 + 16 * kStagePad + 16) * sizeof(int16_t) : 0;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(to_internal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)((3 * 6144 + 16 * kStagePad + 16) * sizeof(int16_t)));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    e = cudaFuncSetAttribute(to_internal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)((3 * 6144 + 16 * kStagePad + 16) * sizeof(int16_t)));
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   to_internal_kernel<<<n_cb, 256, smem, s>>>(src, src_stride, dst, dst_stride, cb_K, uniform_K, (uint32_t)src_format,
                                              src_off, place);

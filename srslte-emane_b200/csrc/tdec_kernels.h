@@ -8,6 +8,9 @@ namespace b200 {
 // One warp-load of code blocks that share K (and therefore window count, window length and QPP).
 struct WorkItem {
   uint32_t first;   // index of the first code block of this item in `order`
+  uint32_t in_pos;  // position of the item in the internal-layout input (in code blocks).  The window decoders' items
+                    // always take tdec_blocks_per_warp() positions, also when they hold fewer blocks, so the host pads
+                    // every K group of the schedule to a multiple of that
   uint16_t count;   // code blocks in this item (<= blocks-per-warp of the kernel that runs it)
   uint16_t K;
   uint16_t f1, f2;  // QPP coefficients of K
@@ -63,13 +66,15 @@ int         tdec_items_per_cta(int W);  // consecutive work items a CTA takes pe
 // int16 elements of one code block in the decoder's internal layout (pair-major streams + tail + meta
 // for window decoders, natural order for the generic decoder).
 uint32_t internal_len(uint32_t K);
+// positions the internal-layout input of n code blocks of one size takes (a partial last item is padded)
+uint32_t internal_positions(uint32_t K, uint32_t n);
 
 // src_format 0: natural (3i+j, tails last); 1: the reference's sub-block soft-buffer layout.
 // One code block per CTA; also records max |sys|, |par0|, |par1| per block for the fast-path proof.
 // The source of block i is src + src_off[i] when src_off (device, int16 elements) is given, else src + i*src_stride.
 // Blocks are written at their position in the decode schedule, the blocks of one work item interleaved:
-// place[i] = (first position of i's work item, count << 8 | index in the item) (device); nullptr = the identity
-// schedule of a uniform-K batch.
+// place[i] = (input position of i's work item, count << 8 | index in the item) (device); nullptr = the identity
+// schedule of a uniform-K batch.  dst must hold internal_positions() x dst_stride elements.
 cudaError_t to_internal_launch(const int16_t* src, uint32_t src_stride, const uint64_t* src_off, int src_format,
                                int16_t* dst, uint32_t dst_stride, const uint32_t* cb_K /* device, nullable */,
                                uint32_t uniform_K, const uint2* place, uint32_t n_cb, cudaStream_t s);
