@@ -66,8 +66,8 @@ constexpr int      kSmLanes   = 32;     // stride (in 128-bit words) between the
 static_assert(kStages * kStageBytes + kChunk * 2 * 32 * 16 <= kWarpSmem, "general path must fit the warp's shared memory");
 // per-warp-slot workspace strides are not powers of two: warps run in near lock step, and power-of-two
 // strides would send all of them to the same L2 slices / HBM channels at once
-constexpr size_t   kXArrayBytes16 = (size_t)(kMaxGroups + 1) * kGroupBytes;  // one A or E array (all blocks of a warp)
-constexpr size_t   kXArrayBytes8  = (size_t)(100 / 4 + 1) * kGroupBytes;     // W = 8: K <= 800, L <= 100
+constexpr size_t   kXArrayBytes16 = (size_t)(kMaxL + 1) * 128;  // one A or E array: rows of 32 words (all blocks of a warp)
+constexpr size_t   kXArrayBytes8  = (size_t)(100 + 1) * 128;    // W = 8: K <= 800, L <= 100
 constexpr size_t   kChkSlotBytes  = (size_t)kMaxChunks * 1024 + 128;
 constexpr int      kStagePad  = 4;   // int16 of padding per window in to_internal_kernel's staged copy
 constexpr int      kExactRows = 4;   // rows next to a known-state boundary always use exact arithmetic
@@ -81,7 +81,7 @@ constexpr uint32_t kMin2      = 0x80008000u;
 
 // a page of zeros with the geometry of a stream: what a half iteration reads where it has no input (DEC2 has no
 // separate systematic stream, the first half iteration has no a-priori values) -- keeps the loops branch free
-__device__ uint4 g_zero_page[(kMaxGroups + 1) * 32];
+__device__ uint4 g_zero_page[(kMaxGroups + 2) * 32];
 
 __constant__ uint32_t c_crc_tab[2][256];
 
@@ -242,11 +242,13 @@ __device__ __forceinline__ void normalize(uint32_t s[8])
 }
 
 // ---- per-thread decode context ---------------------------------------------------------------------
-// A work item is up to 32/(W/2) code blocks of equal K decoded by one warp.  Every stream of its inputs and both
-// extrinsic arrays have ONE geometry: [row group of 4][lane of the warp][4 rows] 32-bit words (two windows each), 512
-// bytes per row group: lane = block * W/2 + thread, so the words a thread needs for 4 consecutive trellis rows are one
-// 128-bit load, and a warp reads whole 512-byte pieces.  to_internal_kernel writes the inputs that way (a partial item
-// leaves the lanes of its missing blocks unused).
+// A work item is up to 32/(W/2) code blocks of equal K decoded by one warp.  Its input streams are laid out
+// [row group of 4][lane of the warp][4 rows] 32-bit words (two windows each), 512 bytes per row group: lane = block *
+// W/2 + thread, so the words a thread needs for 4 consecutive trellis rows are one 128-bit load, and a warp reads
+// whole 512-byte pieces.  to_internal_kernel writes them that way (a partial item leaves the lanes of its missing
+// blocks unused).  The two extrinsic arrays are [row][lane] words: the 16 windows of a row of a code block are one
+// 32-byte sector, which the producer's scatter writes completely at once (group-major arrays were tried: their
+// sectors fill up in four visits and DRAM write traffic doubled).
 template <int W>
 struct WinCtx {
   uint32_t K, L;
@@ -260,8 +262,8 @@ struct WinCtx {
                       // neither fetched nor, unless a hard decision can come before DEC2 has written it, cleared)
   const char*     in_item;  // the item's sys | par0 | par1 streams
   const int16_t*  tail;     // this block's 12 tail samples
-  uint32_t*       A32;  // extrinsic of DEC2 minus E, natural order (= a-priori of DEC1); word of (row k, lane) = ae_word(k, lane)
-  uint32_t*       E32;  // a-posteriori of DEC1 minus A, in DEC2's interleaved order
+  uint32_t*       A32;  // [row][32 lanes] words: extrinsic of DEC2 minus E, natural order (= a-priori of DEC1)
+  uint32_t*       E32;  // [row][32 lanes] words: a-posteriori of DEC1 minus A, in DEC2's interleaved order
                         // (each array is written scattered by its producer and read linearly by its consumer)
   const uint32_t* R;    // CRC modes: per-bit CRC contributions of this half iteration's trellis positions,
                         // [row][window] (lte_tables.h:crc_pos_tables), offset to this thread's window pair;
@@ -278,7 +280,7 @@ struct WinCtx {
 constexpr uint32_t kStabDir = kMaxGroups * 8 * 4;  // 32-bit entries per direction (sized for W = 16)
 
 // 32-bit word of (row k, lane) in an extrinsic array
-__device__ __forceinline__ uint32_t ae_word(uint32_t k, uint32_t lane) { return (k >> 2) * 128u + lane * 4u + (k & 3u); }
+__device__ __forceinline__ uint32_t ae_word(uint32_t k, uint32_t lane) { return k * 32u + lane; }
 // scatter-table entry of row k for a thread whose stab pointer is already offset by t*4
 template <int W>
 __device__ __forceinline__ uint32_t stab_at(const uint32_t* stab, uint32_t dir, uint32_t k)
@@ -319,6 +321,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 // generic-proxy writes (st.global / st.shared) before, async-proxy (TMA) accesses after
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void pf_l2_dyn(const char* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // The chunks a half iteration consumes, in order (depends only on L):
 //   phase 0: 4..0        beta over rows 39..0 (boundary metrics for the previous window)
@@ -342,7 +345,7 @@ __device__ __forceinline__ void pipe_issue(const WinCtx<W>& c, bool dec2, Pipe& 
     // and the bulk-copy instruction -- which takes uniform registers -- runs once per active lane
     const uint32_t ch     = (uint32_t)p.ch;
     const uint32_t gbytes = min(2u, c.ngroups - 2 * ch) * kGroupBytes;
-    const uint32_t xbytes = gbytes;  // the extrinsic arrays have the geometry of a stream
+    const uint32_t xbytes = min(8u, c.L - 8 * ch) * 128u;
     const uint32_t mb     = smem_u32(c.mbar + slot);
     const uint32_t nc     = (dec2 || c.noap) ? 2u : 3u;
     const uint32_t i      = (uint32_t)c.lane;
@@ -411,11 +414,12 @@ __device__ __forceinline__ void pipe_release(const WinCtx<W>& c, bool dec2, Pipe
 template <int W>
 __device__ __forceinline__ void load_group(const WinCtx<W>& c, bool dec2, const char* st, int g, Group& q)
 {
-  const uint4 ys = *reinterpret_cast<const uint4*>(st + 1024 + g * kGroupBytes + c.sp_off);
-  const uint4 xa = *reinterpret_cast<const uint4*>(st + 2048 + g * kGroupBytes + c.lane * 16);
-  const uint4 xs = *reinterpret_cast<const uint4*>(st + g * kGroupBytes + c.sp_off);
+  const uint4     ys = *reinterpret_cast<const uint4*>(st + 1024 + g * kGroupBytes + c.sp_off);
+  const uint32_t* xr = reinterpret_cast<const uint32_t*>(st + 2048 + g * 512) + c.lane;
+  const uint4     xs = *reinterpret_cast<const uint4*>(st + g * kGroupBytes + c.sp_off);
   q.y[0] = ys.x; q.y[1] = ys.y; q.y[2] = ys.z; q.y[3] = ys.w;
-  q.aux[0] = xa.x; q.aux[1] = xa.y; q.aux[2] = xa.z; q.aux[3] = xa.w;
+#pragma unroll
+  for (int r = 0; r < 4; r++) q.aux[r] = xr[r * 32];
   q.x[0] = wadd2(q.aux[0], xs.x); q.x[1] = wadd2(q.aux[1], xs.y);
   q.x[2] = wadd2(q.aux[2], xs.z); q.x[3] = wadd2(q.aux[3], xs.w);
 }
@@ -477,7 +481,7 @@ __device__ __forceinline__ void finish_row_exact(bool dec2, const RawRow& q, uin
 template <int W>
 __device__ __forceinline__ char* out_base(const WinCtx<W>& c, bool dec2)
 {
-  return reinterpret_cast<char*>(dec2 ? c.A32 : c.E32) + c.grp * (W / 2 * 16);
+  return reinterpret_cast<char*>(dec2 ? c.A32 : c.E32) + c.grp * (2 * W);
 }
 
 template <int W, bool HARD>
@@ -975,27 +979,61 @@ struct Rows4 {
   uint32_t x[4], y[4];
 };
 
-__device__ __forceinline__ uint4 ld128(const char* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
-__device__ __forceinline__ void  pf_l2(const char* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// groups at byte offsets off and off + 512 from this thread's stream pointers
-__device__ __forceinline__ void load_unit(const char* ps, const char* pp, const char* pa, int off, Unit& u)
+// Loads are volatile asm with a memory clobber: they stay where the source puts them relative to the stores of the
+// forward pass (the compiler otherwise sinks them next to their first use, which shortens the prefetch distance).
+template <int OFF>
+__device__ __forceinline__ uint4 ld128(const char* p)
 {
-  u.s[0] = ld128(ps + off);
-  u.p[0] = ld128(pp + off);
-  u.a[0] = ld128(pa + off);
-  u.s[1] = ld128(ps + off + (int)kGroupBytes);
-  u.p[1] = ld128(pp + off + (int)kGroupBytes);
-  u.a[1] = ld128(pa + off + (int)kGroupBytes);
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4+%5];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "n"(OFF)
+               : "memory");
+  return v;
 }
-__device__ __forceinline__ void prefetch_unit(const char* ps, const char* pp, const char* pa, int off)
+template <int OFF>
+__device__ __forceinline__ uint32_t ld32(const char* p)
 {
-  pf_l2(ps + off);
-  pf_l2(pp + off);
-  pf_l2(pa + off);
-  pf_l2(ps + off + (int)kGroupBytes);
-  pf_l2(pp + off + (int)kGroupBytes);
-  pf_l2(pa + off + (int)kGroupBytes);
+  uint32_t v;
+  asm volatile("ld.global.cg.u32 %0, [%1+%2];" : "=r"(v) : "l"(p), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ void pf_l2(const char* p)
+{
+  asm volatile("prefetch.global.L2 [%0+%1];" ::"l"(p), "n"(OFF));
+}
+
+// this thread's pointers into the three streams of a half iteration: row group g of the input streams is at
+// s / p + 512 g, its four a-priori words at a + 512 g + 128 r (the extrinsic arrays are [row][lane])
+struct Streams {
+  const char *s, *p, *a;
+  __device__ __forceinline__ Streams at(int off) const { return Streams{s + off, p + off, a + off}; }
+};
+
+// the two row groups at byte offsets OFF and OFF + 512
+template <int OFF>
+__device__ __forceinline__ void load_unit(const Streams& q, Unit& u)
+{
+  constexpr int GB = (int)kGroupBytes;
+  u.s[0] = ld128<OFF>(q.s);
+  u.p[0] = ld128<OFF>(q.p);
+  u.a[0] = make_uint4(ld32<OFF>(q.a), ld32<OFF + 128>(q.a), ld32<OFF + 256>(q.a), ld32<OFF + 384>(q.a));
+  u.s[1] = ld128<OFF + GB>(q.s);
+  u.p[1] = ld128<OFF + GB>(q.p);
+  u.a[1] = make_uint4(ld32<OFF + GB>(q.a), ld32<OFF + GB + 128>(q.a), ld32<OFF + GB + 256>(q.a), ld32<OFF + GB + 384>(q.a));
+}
+// L2 prefetch of the unit at OFF: one request per 128-byte line
+template <int OFF>
+__device__ __forceinline__ void prefetch_unit(const Streams& q)
+{
+  constexpr int GB = (int)kGroupBytes;
+  pf_l2<OFF>(q.s);
+  pf_l2<OFF>(q.p);
+  pf_l2<OFF + GB>(q.s);
+  pf_l2<OFF + GB>(q.p);
+#pragma unroll
+  for (int r = 0; r < 8; r++) pf_l2_dyn(q.a + OFF + r * 128);
 }
 
 __device__ __forceinline__ void rows_of(const uint4& s, const uint4& p, const uint4& a, Rows4& q)
@@ -1019,6 +1057,16 @@ __device__ __forceinline__ void beta_group(uint32_t s[8], const Rows4& q, Range&
     }
   }
 }
+// beta over a unit: its upper row group, then its lower one
+template <int NORM, bool TRACK>
+__device__ __forceinline__ void beta_unit(uint32_t s[8], const Unit& u, Range& rb, bool skip0)
+{
+  Rows4 q;
+  rows_of(u.s[1], u.p[1], u.a[1], q);
+  beta_group<NORM, TRACK>(s, q, rb, false);
+  rows_of(u.s[0], u.p[0], u.a[0], q);
+  beta_group<NORM, TRACK>(s, q, rb, skip0);
+}
 
 // alpha over one row group without output (warm-up).  skip0: no normalisation after the group's first row (NORM = 2)
 template <int NORM, bool TRACK>
@@ -1034,6 +1082,15 @@ __device__ __forceinline__ void alpha_group(uint32_t a[8], const Rows4& q, Range
       }
     }
   }
+}
+template <int NORM, bool TRACK>
+__device__ __forceinline__ void alpha_unit(uint32_t a[8], const Unit& u, Range& ra, bool skip0)
+{
+  Rows4 q;
+  rows_of(u.s[0], u.p[0], u.a[0], q);
+  alpha_group<NORM, TRACK>(a, q, ra, skip0);
+  rows_of(u.s[1], u.p[1], u.a[1], q);
+  alpha_group<NORM, TRACK>(a, q, ra, false);
 }
 
 // alpha recursion + output with the systematic term factored out (see above).  Returns the a-posteriori value minus
@@ -1104,7 +1161,6 @@ __device__ __forceinline__ void fwd_group(const WinCtx<W>& c, const uint32_t* st
 template <int NORM>
 __device__ __forceinline__ void rebuild8(uint32_t s[8], bool top_norm, const Unit& u, uint32_t (*B)[8])
 {
-  Range unused;
 #pragma unroll
   for (int i = 0; i < 8; i++) B[7][i] = s[i];
   if (top_norm) normalize<true>(s);
@@ -1121,141 +1177,181 @@ __device__ __forceinline__ void rebuild8(uint32_t s[8], bool top_norm, const Uni
       if (NORM == 4 ? r == 0 : (r & 1) == 0) normalize<true>(s);
     }
   }
-  (void)unused;
 }
 
-template <int W, int NORM, bool TRACK, bool HARD>
-__device__ __forceinline__ HalfResult half_fast2(const WinCtx<W>& c, bool dec2, int G)
+template <int W>
+__device__ __forceinline__ Streams half_streams(const WinCtx<W>& c, bool dec2)
+{
+  // row group 0 of this thread in the three streams of this half iteration; missing inputs read the zero page
+  const char* const zp = reinterpret_cast<const char*>(g_zero_page);
+  Streams q;
+  q.s = dec2 ? zp + c.lane * 16 : c.in_item + c.sp_off;
+  q.p = c.in_item + (dec2 ? 2u : 1u) * (size_t)c.s_bytes + c.sp_off;
+  q.a = dec2 ? reinterpret_cast<const char*>(c.E32) + c.lane * 4
+             : c.noap ? zp + c.lane * 4 : reinterpret_cast<const char*>(c.A32) + c.lane * 4;
+  return q;
+}
+
+// what the backward side hands to the forward side
+struct BackOut {
+  uint32_t a[8];  // alpha boundary vector of this thread's windows
+  Range    rb, ra;
+};
+
+// ---- backward side of a half iteration: beta warm-up (rows 39..0), alpha warm-up (rows L-40..L-1), beta over the
+// window with a checkpoint every 16 rows into the warp's shared memory.  The alpha warm-up runs BEFORE the beta pass:
+// its five 8-row units are the first five of the beta pass, which finds them in registers.  Five unit buffers;
+// every buffer is refilled right after its unit has been consumed with the unit that is due 4..5 units later.
+template <int W, int NORM, bool TRACK>
+__device__ __forceinline__ void backward_side(const WinCtx<W>& c, bool dec2, BackOut* out)
 {
   constexpr int WH = W / 2;
-  const int     L  = (int)c.L;
-  const int     nc = L >> 4;      // 16-row chunks, numbered from the top of the window
-  const int     ng = L >> 2;      // row groups
   constexpr int GB = (int)kGroupBytes;
-  // this thread's 16 bytes of row group 0 of the three streams of this half iteration
-  const char* const zp = reinterpret_cast<const char*>(g_zero_page) + c.lane * 16;
-  const char* const ps = dec2 ? zp : c.in_item + c.sp_off;
-  const char* const pp = c.in_item + (dec2 ? 2u : 1u) * (size_t)c.s_bytes + c.sp_off;
-  const char* const pa = dec2 ? reinterpret_cast<const char*>(c.E32) + c.lane * 16
-                              : c.noap ? zp : reinterpret_cast<const char*>(c.A32) + c.lane * 16;
-  Range rb, ra, rm, rd;
-  rb.reset(); ra.reset(); rd.reset();
-  rm.hi = kMin2; rm.lo = kMax2;
-  uint32_t crc = 0;
-  uint32_t s[8];
-  Unit     cur, nxt;
-
-  // ---------------- backward pass: boundary metrics from the next window's first 40 rows ----------------
-  load_unit(ps, pp, pa, 8 * GB, cur);
+  const int     ng = (int)c.L >> 2;       // row groups
+  const int     nu = ng >> 1;             // 8-row units, numbered from the top in the beta pass
+  const Streams q0  = half_streams<W>(c, dec2);
+  const Streams top = q0.at((ng - 10) * GB);  // rows L-40 ..
+  Range rb, ra;
+  rb.reset(); ra.reset();
+  Unit F0, F1, F2, F3, F4;
+  load_unit<8 * GB>(q0, F0);
+  load_unit<6 * GB>(q0, F1);
+  load_unit<4 * GB>(q0, F2);
+  load_unit<2 * GB>(q0, F3);
+  load_unit<0>(q0, F4);
+  // L2: the units of the beta pass below the top five
 #pragma unroll 1
-  for (int i = 1; i <= 6 && 2 * i <= ng; i++) prefetch_unit(ps, pp, pa, (ng - 2 * i) * GB);  // L2: the top three chunks
+  for (int u = 5; u < nu && u < 5 + 12; u++) prefetch_unit<0>(q0.at((ng - 2 - 2 * u) * GB));
+
+  uint32_t s[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) s[i] = kNegInf2;
-#pragma unroll 1
-  for (int u = 4; u >= 0; u--) {
-    load_unit(ps, pp, pa, u > 0 ? (2 * u - 2) * GB : (ng - 2) * GB, nxt);  // next unit below, then the top of the window
-    Rows4 q;
-    rows_of(cur.s[1], cur.p[1], cur.a[1], q);
-    beta_group<NORM, TRACK>(s, q, rb, false);
-    rows_of(cur.s[0], cur.p[0], cur.a[0], q);
-    beta_group<NORM, TRACK>(s, q, rb, NORM == 2 && u == 0);
-    cur = nxt;
-  }
+  beta_unit<NORM, TRACK>(s, F0, rb, false);
+  load_unit<0>(top, F0);
+  beta_unit<NORM, TRACK>(s, F1, rb, false);
+  load_unit<2 * GB>(top, F1);
+  beta_unit<NORM, TRACK>(s, F2, rb, false);
+  load_unit<4 * GB>(top, F2);
+  beta_unit<NORM, TRACK>(s, F3, rb, false);
+  load_unit<6 * GB>(top, F3);
+  beta_unit<NORM, TRACK>(s, F4, rb, NORM == 2);  // the reference does not normalise after row 0; NORM = 4 does (see above)
+  load_unit<8 * GB>(top, F4);
   exchange_beta_boundary<WH>(s, c.t, c.tail + (dec2 ? 6 : 0));
   if (TRACK) rb.add8full(s);
 
-  // ---------------- backward pass over the window: a checkpoint every 16 rows ----------------
   {
-    const char *qs = ps + ng * GB, *qp = pp + ng * GB, *qa = pa + ng * GB;
-#pragma unroll 1
-    for (int j = 0; j < nc; j++) {
-      c.ck[(j * 2 + 0) * 32] = make_uint4(s[0], s[1], s[2], s[3]);
-      c.ck[(j * 2 + 1) * 32] = make_uint4(s[4], s[5], s[6], s[7]);
-      qs -= 4 * GB; qp -= 4 * GB; qa -= 4 * GB;   // the chunk's first row group
-      load_unit(qs, qp, qa, 0, nxt);                // its lower unit
-      if (j + 3 < nc) {                             // L2: two chunks further down
-        prefetch_unit(qs, qp, qa, -10 * GB);
-        prefetch_unit(qs, qp, qa, -12 * GB);
-      }
-      Rows4 q;
-      rows_of(cur.s[1], cur.p[1], cur.a[1], q);
-      beta_group<NORM, TRACK>(s, q, rb, false);
-      rows_of(cur.s[0], cur.p[0], cur.a[0], q);
-      beta_group<NORM, TRACK>(s, q, rb, false);
-      // the upper unit of the chunk below; after the last chunk the first unit of the alpha warm-up
-      if (j + 1 < nc) load_unit(qs, qp, qa, -2 * GB, cur);
-      else load_unit(ps, pp, pa, (ng - 10) * GB, cur);
-      rows_of(nxt.s[1], nxt.p[1], nxt.a[1], q);
-      beta_group<NORM, TRACK>(s, q, rb, false);
-      rows_of(nxt.s[0], nxt.p[0], nxt.a[0], q);
-      beta_group<NORM, TRACK>(s, q, rb, NORM == 2 && j + 1 == nc);
-    }
+    uint32_t a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = kNegInf2;
+    alpha_unit<NORM, TRACK>(a, F0, ra, NORM == 2);  // the reference normalises on the warm-up counter: not after its row 0
+    alpha_unit<NORM, TRACK>(a, F1, ra, false);
+    alpha_unit<NORM, TRACK>(a, F2, ra, false);
+    alpha_unit<NORM, TRACK>(a, F3, ra, false);
+    alpha_unit<NORM, TRACK>(a, F4, ra, false);
+    exchange_alpha_boundary<WH>(a, c.t);
+#pragma unroll
+    for (int i = 0; i < 8; i++) out->a[i] = a[i];
   }
 
-  // ---------------- forward pass: boundary metrics from the previous window's last 40 rows ----------------
-  uint32_t a[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) a[i] = kNegInf2;
-  Unit X, Yb, Z;  // forward chunk: upper unit (stage A), lower unit (stage B), upper unit again (stage C)
+  // beta pass: unit k covers the row groups ng-2-2k, ng-1-2k; units 0..4 are in F4, F3, F2, F1, F0
+  auto ck_store = [&](int j) {
+    c.ck[(j * 2 + 0) * 32] = make_uint4(s[0], s[1], s[2], s[3]);
+    c.ck[(j * 2 + 1) * 32] = make_uint4(s[4], s[5], s[6], s[7]);
+  };
+  Streams q = q0.at((ng - 2) * GB);  // unit k of the current body is at q - 2 k GB
+  int     k = 0;
 #pragma unroll 1
-  for (int u = 0; u < 5; u++) {
-    if (u < 4) load_unit(ps, pp, pa, (ng - 10 + 2 * u + 2) * GB, nxt);
-    else {  // the first chunk of the forward pass (rows 0..15; the backward pass has just read them)
-      load_unit(ps, pp, pa, 2 * GB, X);
-      load_unit(ps, pp, pa, 0, Yb);
+  for (; k + 4 <= nu; k += 4) {
+    // L2: three bodies ahead
+    if (k + 16 <= nu) {
+      prefetch_unit<-24 * GB>(q);
+      prefetch_unit<-26 * GB>(q);
+      prefetch_unit<-28 * GB>(q);
+      prefetch_unit<-30 * GB>(q);
     }
-    Rows4 q;
-    rows_of(cur.s[0], cur.p[0], cur.a[0], q);
-    alpha_group<NORM, TRACK>(a, q, ra, NORM == 2 && u == 0);
-    rows_of(cur.s[1], cur.p[1], cur.a[1], q);
-    alpha_group<NORM, TRACK>(a, q, ra, false);
-    if (u < 4) cur = nxt;
+    ck_store(k >> 1);
+    beta_unit<NORM, TRACK>(s, F4, rb, false);
+    if (k == 0) F4 = F0;  // unit 4 came with the alpha warm-up
+    else if (k + 4 < nu) load_unit<-8 * GB>(q, F4);
+    beta_unit<NORM, TRACK>(s, F3, rb, false);
+    if (k + 5 < nu) load_unit<-10 * GB>(q, F3);
+    ck_store((k >> 1) + 1);
+    beta_unit<NORM, TRACK>(s, F2, rb, false);
+    if (k + 6 < nu) load_unit<-12 * GB>(q, F2);
+    beta_unit<NORM, TRACK>(s, F1, rb, NORM == 2 && k + 4 == nu);
+    if (k + 7 < nu) load_unit<-14 * GB>(q, F1);
+    q = q.at(-8 * GB);
   }
-  exchange_alpha_boundary<WH>(a, c.t);
+  if (k < nu) {  // an odd number of chunks: the last one
+    ck_store(k >> 1);
+    beta_unit<NORM, TRACK>(s, F4, rb, false);
+    beta_unit<NORM, TRACK>(s, F3, rb, NORM == 2);
+  }
+  out->rb = rb;
+  out->ra = ra;
+}
 
-  // ---------------- forward pass over the window, 16 rows at a time ----------------
-  {
-    char* const           Yout = out_base<W>(c, dec2);
-    const uint32_t* const sdir = c.stab + (dec2 ? 0u : kStabDir);
-    const char *qs = ps, *qp = pp, *qa = pa;  // first row group of the chunk
-#pragma unroll 1
-    for (int j = nc - 1; j >= 0; j--) {
-      const uint32_t lo = (uint32_t)(L - 16 * (j + 1));
-      load_unit(qs, qp, qa, 2 * GB, Z);
-      uint32_t B[8][8];
-      // ---- stage A: beta from the checkpoint down the upper 8 rows ----
-      {
-        const uint4 c0 = c.ck[(j * 2 + 0) * 32], c1 = c.ck[(j * 2 + 1) * 32];
-        s[0] = c0.x; s[1] = c0.y; s[2] = c0.z; s[3] = c0.w; s[4] = c1.x; s[5] = c1.y; s[6] = c1.z; s[7] = c1.w;
-        if (j != 0) normalize<true>(s);  // every checkpoint but the boundary vector was normalised after it was stored
-        Rows4 q;
-        rows_of(X.s[1], X.p[1], X.a[1], q);
-        beta_group<NORM, false>(s, q, rb, false);
-        rows_of(X.s[0], X.p[0], X.a[0], q);
+// ---- forward side: alpha + output over the window, 16 rows at a time (stages A, B, C above) ----
+template <int W, int NORM, bool TRACK, bool HARD>
+__device__ __forceinline__ HalfResult forward_side(const WinCtx<W>& c, bool dec2, int G, const BackOut& bo)
+{
+  constexpr int GB = (int)kGroupBytes;
+  const int     L  = (int)c.L;
+  const int     nc = L >> 4;  // 16-row chunks, numbered from the top of the window
+  Range rb = bo.rb, ra = bo.ra, rm, rd;
+  rd.reset();
+  rm.hi = kMin2; rm.lo = kMax2;
+  uint32_t crc = 0;
+  uint32_t s[8], a[8];
 #pragma unroll
-        for (int r = 3; r >= 1; r--) {
-          beta_step<true>(s, q.x[r], q.y[r], wadd2(q.x[r], q.y[r]));
-          if (NORM == 2 && r == 2) normalize<true>(s);
-        }
-        beta_step<true>(s, q.x[0], q.y[0], wadd2(q.x[0], q.y[0]));  // s = beta above row lo + 7, not yet normalised
-      }
-      if (j > 0) load_unit(qs, qp, qa, 6 * GB, X);
-      // ---- stage B: the lower 8 rows ----
-      rebuild8<NORM>(s, true, Yb, B);
-      fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo, a, &B[0], Yb.s[0], Yb.p[0], Yb.a[0], Yout, ra, rm, rd, crc,
-                                      NORM == 2 && lo == 0);
-      fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 4, a, &B[4], Yb.s[1], Yb.p[1], Yb.a[1], Yout, ra, rm, rd, crc, false);
-      if (j > 0) load_unit(qs, qp, qa, 4 * GB, Yb);
-      // ---- stage C: the upper 8 rows ----
-      {
-        const uint4 c0 = c.ck[(j * 2 + 0) * 32], c1 = c.ck[(j * 2 + 1) * 32];
-        s[0] = c0.x; s[1] = c0.y; s[2] = c0.z; s[3] = c0.w; s[4] = c1.x; s[5] = c1.y; s[6] = c1.z; s[7] = c1.w;
-      }
-      rebuild8<NORM>(s, j != 0, Z, B);
-      fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 8, a, &B[0], Z.s[0], Z.p[0], Z.a[0], Yout, ra, rm, rd, crc, false);
-      fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 12, a, &B[4], Z.s[1], Z.p[1], Z.a[1], Yout, ra, rm, rd, crc, false);
-      qs += 4 * GB; qp += 4 * GB; qa += 4 * GB;
+  for (int i = 0; i < 8; i++) a[i] = bo.a[i];
+  Streams q = half_streams<W>(c, dec2);  // first row group of the chunk
+  Unit    X, Yb, Z;  // upper unit (stage A), lower unit (stage B), upper unit again (stage C)
+  load_unit<2 * GB>(q, X);  // rows 0..15: the backward pass has just read them
+  load_unit<0>(q, Yb);
+  char* const           Yout = out_base<W>(c, dec2);
+  const uint32_t* const sdir = c.stab + (dec2 ? 0u : kStabDir);
+#pragma unroll 1
+  for (int j = nc - 1; j >= 0; j--) {
+    const uint32_t lo = (uint32_t)(L - 16 * (j + 1));
+    load_unit<2 * GB>(q, Z);
+    if (j >= 2) {  // L2: two chunks ahead
+      prefetch_unit<8 * GB>(q);
+      prefetch_unit<10 * GB>(q);
     }
+    uint32_t B[8][8];
+    // ---- stage A: beta from the checkpoint down the upper 8 rows ----
+    {
+      const uint4 c0 = c.ck[(j * 2 + 0) * 32], c1 = c.ck[(j * 2 + 1) * 32];
+      s[0] = c0.x; s[1] = c0.y; s[2] = c0.z; s[3] = c0.w; s[4] = c1.x; s[5] = c1.y; s[6] = c1.z; s[7] = c1.w;
+      if (j != 0) normalize<true>(s);  // every checkpoint but the boundary vector was normalised after it was stored
+      Rows4 r4;
+      rows_of(X.s[1], X.p[1], X.a[1], r4);
+      beta_group<NORM, false>(s, r4, rb, false);
+      rows_of(X.s[0], X.p[0], X.a[0], r4);
+#pragma unroll
+      for (int r = 3; r >= 1; r--) {
+        beta_step<true>(s, r4.x[r], r4.y[r], wadd2(r4.x[r], r4.y[r]));
+        if (NORM == 2 && r == 2) normalize<true>(s);
+      }
+      beta_step<true>(s, r4.x[0], r4.y[0], wadd2(r4.x[0], r4.y[0]));  // s = beta above row lo + 7, not yet normalised
+    }
+    if (j > 0) load_unit<6 * GB>(q, X);
+    // ---- stage B: the lower 8 rows ----
+    rebuild8<NORM>(s, true, Yb, B);
+    fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo, a, &B[0], Yb.s[0], Yb.p[0], Yb.a[0], Yout, ra, rm, rd, crc,
+                                    NORM == 2 && lo == 0);
+    fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 4, a, &B[4], Yb.s[1], Yb.p[1], Yb.a[1], Yout, ra, rm, rd, crc, false);
+    if (j > 0) load_unit<4 * GB>(q, Yb);
+    // ---- stage C: the upper 8 rows ----
+    {
+      const uint4 c0 = c.ck[(j * 2 + 0) * 32], c1 = c.ck[(j * 2 + 1) * 32];
+      s[0] = c0.x; s[1] = c0.y; s[2] = c0.z; s[3] = c0.w; s[4] = c1.x; s[5] = c1.y; s[6] = c1.z; s[7] = c1.w;
+    }
+    rebuild8<NORM>(s, j != 0, Z, B);
+    fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 8, a, &B[0], Z.s[0], Z.p[0], Z.a[0], Yout, ra, rm, rd, crc, false);
+    fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 12, a, &B[4], Z.s[1], Z.p[1], Z.a[1], Yout, ra, rm, rd, crc, false);
+    q = q.at(4 * GB);
   }
   __syncwarp();
 
@@ -1282,12 +1378,21 @@ __device__ __forceinline__ HalfResult half_fast2(const WinCtx<W>& c, bool dec2, 
   return res;
 }
 
+// one copy of the backward side serves both forward variants (hard: CRC modes)
+template <int W, int NORM, bool TRACK>
+__device__ __forceinline__ HalfResult half_fast2(const WinCtx<W>& c, bool dec2, int G, bool hard)
+{
+  BackOut bo;
+  backward_side<W, NORM, TRACK>(c, dec2, &bo);
+  return hard ? forward_side<W, NORM, TRACK, true>(c, dec2, G, bo) : forward_side<W, NORM, TRACK, false>(c, dec2, G, bo);
+}
+
 // QPP of this K as a scatter table, computed from (f1, f2) by the whole CTA:
 //   pi(d*L + k) = pi(k) + L * d * (f1 + f2*d*L + 2*f2*k)  (mod K = W*L), so with pi(k) = w0*L + r every window
 //   d of row k lands in row r, window (w0 + d*(f1 + f2*d*L) + 2*f2*d*k) mod W.
 // dir 0 holds pi (where DEC2's row k goes in natural order), dir 1 its inverse (where natural row r goes in
 // DEC2's order).  An entry is the pair of byte offsets (16 bits each) of the destinations of windows 2t and 2t+1
-// inside the code block's part of the array: row group * 512 + (row & 3) * 4 + (window / 2) * 16 + (window & 1) * 2.
+// inside the code block's part of the array: row * 128 + window * 2.
 template <int W>
 __device__ void build_tables(uint32_t K, uint32_t f1, uint32_t f2, uint32_t* stab)
 {
@@ -1295,7 +1400,7 @@ __device__ void build_tables(uint32_t K, uint32_t f1, uint32_t f2, uint32_t* sta
   const uint32_t L  = K / W;
   const uint32_t mK = (uint32_t)(0x100000000ull / K);
   const uint32_t mL = (uint32_t)((0x100000000ull + L - 1) / L);
-  auto off = [](uint32_t row, uint32_t w) { return (row >> 2) * kGroupBytes + (row & 3u) * 4u + (w >> 1) * 16u + (w & 1u) * 2u; };
+  auto off = [](uint32_t row, uint32_t w) { return row * 128u + w * 2u; };
   for (uint32_t k = threadIdx.x; k < L; k += blockDim.x) {
     const uint32_t v = (f1 + f2 * k) * k;  // k < L <= 384 keeps it below 2^32
     uint32_t       p = v - __umulhi(v, mK) * K;
@@ -1335,7 +1440,7 @@ __device__ void decide(const WinCtx<W>& c, uint8_t* out, bool write)
   auto      word     = [&](uint32_t f) -> uint32_t& {
     return grp_base[(((f >> 2) / WH) * kSmLanes + ((f >> 2) % WH)) * 4 + (f & 3)];
   };
-  const char* E8 = reinterpret_cast<const char*>(c.E32) + c.grp * (WH * 16);
+  const char* E8 = reinterpret_cast<const char*>(c.E32) + c.grp * (2 * W);
   constexpr int NB = 16;  // rows gathered per batch: the E gather is latency bound, keep many loads in flight
   // 32 rows = one word per window.  Rows past L repeat row L - 1: their bits land below the last valid bit of the
   // window's last word, where phase 2 never looks.
@@ -1501,7 +1606,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
       // pass after the first): 48 KB of stores per work item that the plain K = 6144 / 4 half iterations case does
       // not need.
       if (a.max_iter < 2 || any_crc)
-        for (uint32_t i = lane; i < c.ngroups * 128u; i += 32) c.A32[i] = 0;
+        for (uint32_t k = 0; k < c.L; k++) c.A32[k * 32 + lane] = 0;
       do {
         const bool dec2 = (n & 1) != 0;
         c.noap = n == 0;
@@ -1521,7 +1626,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
         // path only (measurements)
         const bool pure = __all_sync(0xFFFFFFFFu, (a.force_exact & 3u) == 0 && G <= kPureFastG);
         if (pure && v2) {
-          r       = any_crc ? half_fast2<W, 4, false, true>(c, dec2, G) : half_fast2<W, 4, false, false>(c, dec2, G);
+          r       = half_fast2<W, 4, false>(c, dec2, G, any_crc);
           fast_ok = true;
         } else if (!__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kMaxFastG)) {
           // nothing: exact variant below
