@@ -1004,11 +1004,25 @@ __device__ __forceinline__ void pf_l2(const char* p)
   asm volatile("prefetch.global.L2 [%0+%1];" ::"l"(p), "n"(OFF));
 }
 
+// The compiler hoists a refill above the last use of the buffer it refills; the old and the new unit then live in
+// different registers and the copies it inserts at the loop's back edge wait for loads that were issued moments
+// before.  An empty asm makes the addresses depend on a value the consumer produces last, so the refill stays behind
+// the consumption and lands in the registers that have just become free.
+__device__ __forceinline__ void pin_after(const char*& p, uint32_t dep) { asm volatile("" : "+l"(p) : "r"(dep)); }
+
 // this thread's pointers into the three streams of a half iteration: row group g of the input streams is at
 // s / p + 512 g, its four a-priori words at a + 512 g + 128 r (the extrinsic arrays are [row][lane])
 struct Streams {
   const char *s, *p, *a;
   __device__ __forceinline__ Streams at(int off) const { return Streams{s + off, p + off, a + off}; }
+  __device__ __forceinline__ Streams after(uint32_t dep) const
+  {
+    Streams r = *this;
+    pin_after(r.s, dep);
+    pin_after(r.p, dep);
+    pin_after(r.a, dep);
+    return r;
+  }
 };
 
 // the two row groups at byte offsets OFF and OFF + 512
@@ -1128,9 +1142,10 @@ __device__ __forceinline__ void fwd_group(const WinCtx<W>& c, const uint32_t* st
                                           const uint32_t (*B)[8], const uint4& sv, const uint4& pv, const uint4& av, char* Y,
                                           Range& ra, Range& rm, Range& rd, uint32_t& crc, bool skip0)
 {
-  const uint4    e4 = *reinterpret_cast<const uint4*>(stab_dir + (k0 >> 2) * (W / 2 * 4));
+  // the scatter offsets as 16-bit loads: the halves come zero-extended from the load/store unit instead of costing
+  // a mask and a shift on the ALU pipe, which the add-max instructions of this loop keep busy
+  const uint32_t e16 = smem_u32(stab_dir + (k0 >> 2) * (W / 2 * 4));
   const uint32_t sa[4] = {sv.x, sv.y, sv.z, sv.w}, pa[4] = {pv.x, pv.y, pv.z, pv.w}, aa[4] = {av.x, av.y, av.z, av.w};
-  const uint32_t ea[4] = {e4.x, e4.y, e4.z, e4.w};
   uint32_t       d[4];
 #pragma unroll
   for (int r = 0; r < 4; r++) {
@@ -1142,8 +1157,11 @@ __device__ __forceinline__ void fwd_group(const WinCtx<W>& c, const uint32_t* st
       const uint2    rr = *reinterpret_cast<const uint2*>(c.R + (k0 + r) * W);
       crc ^= (rr.x & (uint32_t)((int32_t)(m << 16) >> 31)) ^ (rr.y & (uint32_t)((int32_t)m >> 31));
     }
-    *reinterpret_cast<uint16_t*>(Y + (ea[r] & 0xFFFFu)) = (uint16_t)(d[r] & 0xFFFFu);
-    *reinterpret_cast<uint16_t*>(Y + (ea[r] >> 16))     = (uint16_t)(d[r] >> 16);
+    uint32_t o_lo, o_hi;  // (inline asm: the compiler would merge the halves into one load and take them apart again)
+    asm("ld.shared.u16 %0, [%1];" : "=r"(o_lo) : "r"(e16 + 4 * r));
+    asm("ld.shared.u16 %0, [%1];" : "=r"(o_hi) : "r"(e16 + 4 * r + 2));
+    *reinterpret_cast<uint16_t*>(Y + o_lo) = (uint16_t)(d[r] & 0xFFFFu);
+    *reinterpret_cast<uint16_t*>(Y + o_hi) = (uint16_t)(d[r] >> 16);
     if (NORM == 4 ? r == 2 : (r & 1) == 0) {
       if (r != 0 || !skip0) {
         normalize<true>(a);
@@ -1258,34 +1276,40 @@ __device__ __forceinline__ void backward_side(const WinCtx<W>& c, bool dec2, Bac
     c.ck[(j * 2 + 0) * 32] = make_uint4(s[0], s[1], s[2], s[3]);
     c.ck[(j * 2 + 1) * 32] = make_uint4(s[4], s[5], s[6], s[7]);
   };
-  Streams q = q0.at((ng - 2) * GB);  // unit k of the current body is at q - 2 k GB
-  int     k = 0;
+  // unit 0 first, so that the loop works on a ring of four buffers (F3, F2, F1, F0 = units k .. k+3) with no special
+  // case: a conditional "this buffer came with the warm-up" inside the loop makes the compiler carry a fifth buffer
+  // around and copy every refill into it at the back edge, waiting for loads it has only just issued
+  ck_store(0);
+  beta_unit<NORM, TRACK>(s, F4, rb, false);
+  Streams q = q0.at((ng - 4) * GB);  // unit k; unit k + i is at q - 2 i GB
+  int     k = 1;
 #pragma unroll 1
-  for (; k + 4 <= nu; k += 4) {
-    // L2: three bodies ahead
-    if (k + 16 <= nu) {
+  for (; k + 4 <= nu; k += 4) {  // nu is even, k odd: at least one unit is left for the tail
+    if (k + 16 <= nu) {  // L2: three bodies ahead
       prefetch_unit<-24 * GB>(q);
       prefetch_unit<-26 * GB>(q);
       prefetch_unit<-28 * GB>(q);
       prefetch_unit<-30 * GB>(q);
     }
-    ck_store(k >> 1);
-    beta_unit<NORM, TRACK>(s, F4, rb, false);
-    if (k == 0) F4 = F0;  // unit 4 came with the alpha warm-up
-    else if (k + 4 < nu) load_unit<-8 * GB>(q, F4);
     beta_unit<NORM, TRACK>(s, F3, rb, false);
-    if (k + 5 < nu) load_unit<-10 * GB>(q, F3);
-    ck_store((k >> 1) + 1);
+    if (k + 4 < nu) load_unit<-8 * GB>(q.after(s[1]), F3);
+    ck_store((k + 1) >> 1);
     beta_unit<NORM, TRACK>(s, F2, rb, false);
-    if (k + 6 < nu) load_unit<-12 * GB>(q, F2);
-    beta_unit<NORM, TRACK>(s, F1, rb, NORM == 2 && k + 4 == nu);
-    if (k + 7 < nu) load_unit<-14 * GB>(q, F1);
+    if (k + 5 < nu) load_unit<-10 * GB>(q.after(s[1]), F2);
+    beta_unit<NORM, TRACK>(s, F1, rb, false);
+    if (k + 6 < nu) load_unit<-12 * GB>(q.after(s[1]), F1);
+    ck_store((k + 3) >> 1);
+    beta_unit<NORM, TRACK>(s, F0, rb, false);
+    if (k + 7 < nu) load_unit<-14 * GB>(q.after(s[1]), F0);
     q = q.at(-8 * GB);
   }
-  if (k < nu) {  // an odd number of chunks: the last one
-    ck_store(k >> 1);
-    beta_unit<NORM, TRACK>(s, F4, rb, false);
+  if (k + 1 == nu) {  // one unit left: the lower half of the last chunk
     beta_unit<NORM, TRACK>(s, F3, rb, NORM == 2);
+  } else {            // three units left
+    beta_unit<NORM, TRACK>(s, F3, rb, false);
+    ck_store((k + 1) >> 1);
+    beta_unit<NORM, TRACK>(s, F2, rb, false);
+    beta_unit<NORM, TRACK>(s, F1, rb, NORM == 2);
   }
   out->rb = rb;
   out->ra = ra;
@@ -1306,15 +1330,31 @@ __device__ __forceinline__ HalfResult forward_side(const WinCtx<W>& c, bool dec2
 #pragma unroll
   for (int i = 0; i < 8; i++) a[i] = bo.a[i];
   Streams q = half_streams<W>(c, dec2);  // first row group of the chunk
-  Unit    X, Yb, Z;  // upper unit (stage A), lower unit (stage B), upper unit again (stage C)
+  // upper unit of the chunk (stages A and C), upper unit of the next chunk (in flight from stage A on), lower unit
+  Unit X, Xn, Yb;
   load_unit<2 * GB>(q, X);  // rows 0..15: the backward pass has just read them
   load_unit<0>(q, Yb);
+  // L2: what the NEXT half iteration reads first (the other decoder's parity and systematic streams, rows 0..39 and
+  // L-40..L-1; its a-priori values are what this pass writes)
+  {
+    const char* const ns = c.in_item + c.sp_off;                                           // systematic (DEC1 only)
+    const char* const np = c.in_item + (dec2 ? 1u : 2u) * (size_t)c.s_bytes + c.sp_off;  // the other decoder's parity
+    const int         ng = L >> 2;
+#pragma unroll 1
+    for (int g = 0; g < 10; g++) {
+      pf_l2_dyn(np + g * GB);
+      pf_l2_dyn(np + (ng - 10 + g) * GB);
+      if (dec2) {
+        pf_l2_dyn(ns + g * GB);
+        pf_l2_dyn(ns + (ng - 10 + g) * GB);
+      }
+    }
+  }
   char* const           Yout = out_base<W>(c, dec2);
   const uint32_t* const sdir = c.stab + (dec2 ? 0u : kStabDir);
 #pragma unroll 1
   for (int j = nc - 1; j >= 0; j--) {
     const uint32_t lo = (uint32_t)(L - 16 * (j + 1));
-    load_unit<2 * GB>(q, Z);
     if (j >= 2) {  // L2: two chunks ahead
       prefetch_unit<8 * GB>(q);
       prefetch_unit<10 * GB>(q);
@@ -1336,21 +1376,22 @@ __device__ __forceinline__ HalfResult forward_side(const WinCtx<W>& c, bool dec2
       }
       beta_step<true>(s, r4.x[0], r4.y[0], wadd2(r4.x[0], r4.y[0]));  // s = beta above row lo + 7, not yet normalised
     }
-    if (j > 0) load_unit<6 * GB>(q, X);
+    if (j > 0) load_unit<6 * GB>(q, Xn);
     // ---- stage B: the lower 8 rows ----
     rebuild8<NORM>(s, true, Yb, B);
     fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo, a, &B[0], Yb.s[0], Yb.p[0], Yb.a[0], Yout, ra, rm, rd, crc,
                                     NORM == 2 && lo == 0);
     fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 4, a, &B[4], Yb.s[1], Yb.p[1], Yb.a[1], Yout, ra, rm, rd, crc, false);
-    if (j > 0) load_unit<4 * GB>(q, Yb);
+    if (j > 0) load_unit<4 * GB>(q.after(a[1]), Yb);
     // ---- stage C: the upper 8 rows ----
     {
       const uint4 c0 = c.ck[(j * 2 + 0) * 32], c1 = c.ck[(j * 2 + 1) * 32];
       s[0] = c0.x; s[1] = c0.y; s[2] = c0.z; s[3] = c0.w; s[4] = c1.x; s[5] = c1.y; s[6] = c1.z; s[7] = c1.w;
     }
-    rebuild8<NORM>(s, j != 0, Z, B);
-    fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 8, a, &B[0], Z.s[0], Z.p[0], Z.a[0], Yout, ra, rm, rd, crc, false);
-    fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 12, a, &B[4], Z.s[1], Z.p[1], Z.a[1], Yout, ra, rm, rd, crc, false);
+    rebuild8<NORM>(s, j != 0, X, B);
+    fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 8, a, &B[0], X.s[0], X.p[0], X.a[0], Yout, ra, rm, rd, crc, false);
+    fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 12, a, &B[4], X.s[1], X.p[1], X.a[1], Yout, ra, rm, rd, crc, false);
+    X = Xn;
     q = q.at(4 * GB);
   }
   __syncwarp();
@@ -1546,6 +1587,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
   fence_proxy_async();
   __syncthreads();
 
+  uint32_t tab_K = 0;  // block size the scatter table was built for
   for (;;) {
     if (tid == 0) s_item = atomicAdd(a.counter, 1u);
     __syncthreads();
@@ -1554,9 +1596,12 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
     const uint2 round = a.rounds[rnd];  // (first item, number of items): one item per warp, all of the same K
     {
       const WorkItem w0 = a.items[round.x];
-      build_tables<W>(w0.K, w0.f1, w0.f2, stab);
+      if (w0.K != tab_K) {  // rounds of one block size follow each other
+        build_tables<W>(w0.K, w0.f1, w0.f2, stab);
+        tab_K = w0.K;
+        __syncthreads();
+      }
     }
-    __syncthreads();
     WorkItem wi;
     wi.count = 0;
     if ((uint32_t)warp < round.y) wi = a.items[round.x + (uint32_t)warp];
