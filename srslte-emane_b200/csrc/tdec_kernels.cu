@@ -74,6 +74,9 @@ constexpr int      kExactRows = 4;   // rows next to a known-state boundary alwa
 constexpr int      kPureFastG = 2529;   // 10000 + 9 * G <= 32768: fast arithmetic is exact even next to the known start state
 constexpr int      kStaticFastG = 2978; // 11 * G <= 32767: the fast variant needs no bookkeeping at all
 constexpr int      kMaxFastG  = 5461; // largest per-step metric change the fast variant accepts (6 * G <= 32767)
+#ifndef B200_PF
+#define B200_PF 3  // development probe: bit 0 = L2 prefetch in the backward pass, 1 = forward pass, 2 = next half iteration
+#endif
 constexpr int      kNegInf    = -10000;
 constexpr uint32_t kNegInf2   = 0xD8F0D8F0u;  // (-10000, -10000)
 constexpr uint32_t kMax2      = 0x7FFF7FFFu;
@@ -1037,6 +1040,15 @@ __device__ __forceinline__ void load_unit(const Streams& q, Unit& u)
   u.p[1] = ld128<OFF + GB>(q.p);
   u.a[1] = make_uint4(ld32<OFF + GB>(q.a), ld32<OFF + GB + 128>(q.a), ld32<OFF + GB + 256>(q.a), ld32<OFF + GB + 384>(q.a));
 }
+// A refill whose consumer sits in the NEXT loop iteration: ptxas sees no use inside the loop body and schedules the
+// loads at the very end of it, right in front of the use.  Memory instructions do not move across a warp barrier,
+// so the barrier keeps them where the source has them (the lanes are converged anyway).
+template <int OFF>
+__device__ __forceinline__ void refill_unit(const Streams& q, Unit& u)
+{
+  load_unit<OFF>(q, u);
+  __syncwarp();
+}
 // L2 prefetch of the unit at OFF: one request per 128-byte line
 template <int OFF>
 __device__ __forceinline__ void prefetch_unit(const Streams& q)
@@ -1239,7 +1251,7 @@ __device__ __forceinline__ void backward_side(const WinCtx<W>& c, bool dec2, Bac
   load_unit<0>(q0, F4);
   // L2: the units of the beta pass below the top five
 #pragma unroll 1
-  for (int u = 5; u < nu && u < 5 + 12; u++) prefetch_unit<0>(q0.at((ng - 2 - 2 * u) * GB));
+  for (int u = 5; u < nu && u < 5 + 12 && (B200_PF & 1); u++) prefetch_unit<0>(q0.at((ng - 2 - 2 * u) * GB));
 
   uint32_t s[8];
 #pragma unroll
@@ -1285,22 +1297,22 @@ __device__ __forceinline__ void backward_side(const WinCtx<W>& c, bool dec2, Bac
   int     k = 1;
 #pragma unroll 1
   for (; k + 4 <= nu; k += 4) {  // nu is even, k odd: at least one unit is left for the tail
-    if (k + 16 <= nu) {  // L2: three bodies ahead
+    if (k + 16 <= nu && (B200_PF & 1)) {  // L2: three bodies ahead
       prefetch_unit<-24 * GB>(q);
       prefetch_unit<-26 * GB>(q);
       prefetch_unit<-28 * GB>(q);
       prefetch_unit<-30 * GB>(q);
     }
     beta_unit<NORM, TRACK>(s, F3, rb, false);
-    if (k + 4 < nu) load_unit<-8 * GB>(q.after(s[1]), F3);
+    if (k + 4 < nu) refill_unit<-8 * GB>(q.after(s[1]), F3);
     ck_store((k + 1) >> 1);
     beta_unit<NORM, TRACK>(s, F2, rb, false);
-    if (k + 5 < nu) load_unit<-10 * GB>(q.after(s[1]), F2);
+    if (k + 5 < nu) refill_unit<-10 * GB>(q.after(s[1]), F2);
     beta_unit<NORM, TRACK>(s, F1, rb, false);
-    if (k + 6 < nu) load_unit<-12 * GB>(q.after(s[1]), F1);
+    if (k + 6 < nu) refill_unit<-12 * GB>(q.after(s[1]), F1);
     ck_store((k + 3) >> 1);
     beta_unit<NORM, TRACK>(s, F0, rb, false);
-    if (k + 7 < nu) load_unit<-14 * GB>(q.after(s[1]), F0);
+    if (k + 7 < nu) refill_unit<-14 * GB>(q.after(s[1]), F0);
     q = q.at(-8 * GB);
   }
   if (k + 1 == nu) {  // one unit left: the lower half of the last chunk
@@ -1341,7 +1353,7 @@ __device__ __forceinline__ HalfResult forward_side(const WinCtx<W>& c, bool dec2
     const char* const np = c.in_item + (dec2 ? 1u : 2u) * (size_t)c.s_bytes + c.sp_off;  // the other decoder's parity
     const int         ng = L >> 2;
 #pragma unroll 1
-    for (int g = 0; g < 10; g++) {
+    for (int g = 0; g < 10 && (B200_PF & 4); g++) {
       pf_l2_dyn(np + g * GB);
       pf_l2_dyn(np + (ng - 10 + g) * GB);
       if (dec2) {
@@ -1355,7 +1367,7 @@ __device__ __forceinline__ HalfResult forward_side(const WinCtx<W>& c, bool dec2
 #pragma unroll 1
   for (int j = nc - 1; j >= 0; j--) {
     const uint32_t lo = (uint32_t)(L - 16 * (j + 1));
-    if (j >= 2) {  // L2: two chunks ahead
+    if (j >= 2 && (B200_PF & 2)) {  // L2: two chunks ahead
       prefetch_unit<8 * GB>(q);
       prefetch_unit<10 * GB>(q);
     }
@@ -1382,7 +1394,7 @@ __device__ __forceinline__ HalfResult forward_side(const WinCtx<W>& c, bool dec2
     fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo, a, &B[0], Yb.s[0], Yb.p[0], Yb.a[0], Yout, ra, rm, rd, crc,
                                     NORM == 2 && lo == 0);
     fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 4, a, &B[4], Yb.s[1], Yb.p[1], Yb.a[1], Yout, ra, rm, rd, crc, false);
-    if (j > 0) load_unit<4 * GB>(q.after(a[1]), Yb);
+    if (j > 0) refill_unit<4 * GB>(q.after(a[1]), Yb);
     // ---- stage C: the upper 8 rows ----
     {
       const uint4 c0 = c.ck[(j * 2 + 0) * 32], c1 = c.ck[(j * 2 + 1) * 32];
