@@ -107,6 +107,145 @@ int refh_batch_run_all(const int16_t* in, uint32_t in_stride, int natural, uint8
   return rc;
 }
 
+/* ---- persistent pool: one srslte_tdec_t per worker thread, created ONCE (like turbodecoder_test.c:190-266, which
+ * initialises the decoder and then loops over srslte_tdec_run_all); refh_pool_run times only the decode loops ---- */
+#include <time.h>
+typedef struct refh_pool {
+  uint32_t        threads;
+  pthread_t*      th;
+  pthread_mutex_t mu;
+  pthread_cond_t  cv_go, cv_done;
+  uint64_t        epoch;     /* bumped per run */
+  uint32_t        pending;   /* workers still busy in this run */
+  uint32_t        ready;     /* workers that have created their decoder handles */
+  int             quit;
+  /* job */
+  const int16_t*  in;
+  uint8_t*        out;
+  uint32_t        in_stride, out_stride, n, K, nit;
+  int             natural, rc;
+  double*         busy_s;    /* per worker: seconds spent inside the srslte_tdec_run_all loop of the last run */
+} refh_pool_t;
+
+typedef struct {
+  refh_pool_t* p;
+  uint32_t     idx;
+} pool_arg_t;
+
+static double now_s(void)
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+static void* pool_worker(void* arg)
+{
+  pool_arg_t*    pa = (pool_arg_t*)arg;
+  refh_pool_t*   p  = pa->p;
+  const uint32_t t  = pa->idx;
+  free(pa);
+  srslte_tdec_t* h     = refh_tdec_new(6144, 0);
+  srslte_tdec_t* h_nat = refh_tdec_new(6144, 0);
+  if (h_nat) srslte_tdec_force_not_sb(h_nat);
+  int16_t* buf = (int16_t*)srslte_vec_malloc(sizeof(int16_t) * (3 * (6144 + 32) + 12 + 64));
+  uint64_t seen = 0;
+  pthread_mutex_lock(&p->mu);
+  if (++p->ready == p->threads) pthread_cond_signal(&p->cv_done);
+  pthread_mutex_unlock(&p->mu);
+  for (;;) {
+    pthread_mutex_lock(&p->mu);
+    while (!p->quit && p->epoch == seen) pthread_cond_wait(&p->cv_go, &p->mu);
+    if (p->quit) {
+      pthread_mutex_unlock(&p->mu);
+      break;
+    }
+    seen = p->epoch;
+    pthread_mutex_unlock(&p->mu);
+    int rc = (h && h_nat && buf) ? 0 : -1;
+    const uint32_t first = (uint32_t)((uint64_t)p->n * t / p->threads), last = (uint32_t)((uint64_t)p->n * (t + 1) / p->threads);
+    const uint32_t len = p->natural ? 3 * p->K + 12 : 3 * (p->K + 32) + 12;
+    srslte_tdec_t* hh = p->natural ? h_nat : h;
+    const double   t0 = now_s();
+    for (uint32_t i = first; i < last && !rc; i++) {
+      memcpy(buf, p->in + (size_t)i * p->in_stride, sizeof(int16_t) * len);
+      if (srslte_tdec_run_all(hh, buf, p->out + (size_t)i * p->out_stride, p->nit, p->K)) rc = -1;
+    }
+    p->busy_s[t] = now_s() - t0;
+    pthread_mutex_lock(&p->mu);
+    if (rc) p->rc = -1;
+    if (--p->pending == 0) pthread_cond_signal(&p->cv_done);
+    pthread_mutex_unlock(&p->mu);
+  }
+  free(buf);
+  refh_tdec_free(h);
+  refh_tdec_free(h_nat);
+  return NULL;
+}
+
+refh_pool_t* refh_pool_create(uint32_t threads)
+{
+  if (threads == 0) threads = 1;
+  refh_pool_t* p = (refh_pool_t*)calloc(1, sizeof(refh_pool_t));
+  if (!p) return NULL;
+  p->threads = threads;
+  p->th      = (pthread_t*)calloc(threads, sizeof(pthread_t));
+  p->busy_s  = (double*)calloc(threads, sizeof(double));
+  pthread_mutex_init(&p->mu, NULL);
+  pthread_cond_init(&p->cv_go, NULL);
+  pthread_cond_init(&p->cv_done, NULL);
+  for (uint32_t t = 0; t < threads; t++) {
+    pool_arg_t* pa = (pool_arg_t*)malloc(sizeof(pool_arg_t));
+    pa->p   = p;
+    pa->idx = t;
+    pthread_create(&p->th[t], NULL, pool_worker, pa);
+  }
+  pthread_mutex_lock(&p->mu);  /* handle creation (QPP tables for all 188 sizes, beta arrays) ends here */
+  while (p->ready < threads) pthread_cond_wait(&p->cv_done, &p->mu);
+  pthread_mutex_unlock(&p->mu);
+  return p;
+}
+
+/* decodes n blocks; returns 0 and the wall seconds between the release of the workers and the end of the last one
+ * (handle creation, QPP table generation and thread start are NOT in it); busy_sum = sum of the workers' loop times */
+int refh_pool_run(refh_pool_t* p, const int16_t* in, uint32_t in_stride, int natural, uint8_t* out, uint32_t out_stride,
+                  uint32_t n, uint32_t K, uint32_t nof_iterations, double* wall_s, double* busy_sum_s)
+{
+  if (!p) return -1;
+  pthread_mutex_lock(&p->mu);
+  p->in = in; p->out = out; p->in_stride = in_stride; p->out_stride = out_stride;
+  p->n = n; p->K = K; p->nit = nof_iterations; p->natural = natural; p->rc = 0;
+  p->pending = p->threads;
+  p->epoch++;
+  const double t0 = now_s();
+  pthread_cond_broadcast(&p->cv_go);
+  while (p->pending) pthread_cond_wait(&p->cv_done, &p->mu);
+  const double t1 = now_s();
+  const int    rc = p->rc;
+  double       bs = 0;
+  for (uint32_t t = 0; t < p->threads; t++) bs += p->busy_s[t];
+  pthread_mutex_unlock(&p->mu);
+  if (wall_s) *wall_s = t1 - t0;
+  if (busy_sum_s) *busy_sum_s = bs;
+  return rc;
+}
+
+void refh_pool_destroy(refh_pool_t* p)
+{
+  if (!p) return;
+  pthread_mutex_lock(&p->mu);
+  p->quit = 1;
+  pthread_cond_broadcast(&p->cv_go);
+  pthread_mutex_unlock(&p->mu);
+  for (uint32_t t = 0; t < p->threads; t++) pthread_join(p->th[t], NULL);
+  pthread_mutex_destroy(&p->mu);
+  pthread_cond_destroy(&p->cv_go);
+  pthread_cond_destroy(&p->cv_done);
+  free(p->th);
+  free(p->busy_s);
+  free(p);
+}
+
 /* ---- per-iteration trace of one block, the way sch.c drives the decoder ---- */
 int refh_tdec_trace(const int16_t* in, int natural, uint32_t K, uint32_t nof_iterations,
                     uint8_t* out_bytes /* nit * K/8 */, int16_t* out_llr /* nit * K, nullable */)

@@ -53,7 +53,8 @@ constexpr uint32_t kGroupBytes = 512;       // one row group of a warp in every 
 // ---- main fast path: beta checkpoints every kCkRows rows in shared memory, an 8-row chunk of beta in registers ----
 constexpr int      kCkRows    = 16;
 constexpr int      kMaxCk     = kMaxL / kCkRows;      // 24 checkpoints of 32 B per thread
-constexpr int      kWarpSmem  = kMaxCk * 1024;        // shared memory of one warp: its checkpoints [ck][half][lane] 128-bit
+constexpr int      kWarpSmem  = (kMaxCk + 1) * 1024;  // shared memory of one warp: its checkpoints [ck][half][lane] 128-bit
+                                                      // + one scratch vector (the beta between the two units of a chunk)
 // ---- general path (L % 4 != 0, tracked tier) and exact variant: staged chunks of 8 rows (TMA ring), an 8-row chunk of
 // ---- beta in shared memory, checkpoints every 8 rows in HBM.  They live in the same per-warp shared memory (a warp runs
 // ---- one variant at a time): [ring kStages x kStageBytes | beta chunk 8 rows x 2 x 32 lanes x 16 B]
@@ -1040,6 +1041,23 @@ __device__ __forceinline__ void load_unit(const Streams& q, Unit& u)
   u.p[1] = ld128<OFF + GB>(q.p);
   u.a[1] = make_uint4(ld32<OFF + GB>(q.a), ld32<OFF + GB + 128>(q.a), ld32<OFF + GB + 256>(q.a), ld32<OFF + GB + 384>(q.a));
 }
+// the input-stream part and the a-priori part of load_unit separately
+template <int OFF>
+__device__ __forceinline__ void load_unit_sp(const Streams& q, Unit& u)
+{
+  constexpr int GB = (int)kGroupBytes;
+  u.s[0] = ld128<OFF>(q.s);
+  u.p[0] = ld128<OFF>(q.p);
+  u.s[1] = ld128<OFF + GB>(q.s);
+  u.p[1] = ld128<OFF + GB>(q.p);
+}
+template <int OFF>
+__device__ __forceinline__ void load_unit_a(const Streams& q, Unit& u)
+{
+  constexpr int GB = (int)kGroupBytes;
+  u.a[0] = make_uint4(ld32<OFF>(q.a), ld32<OFF + 128>(q.a), ld32<OFF + 256>(q.a), ld32<OFF + 384>(q.a));
+  u.a[1] = make_uint4(ld32<OFF + GB>(q.a), ld32<OFF + GB + 128>(q.a), ld32<OFF + GB + 256>(q.a), ld32<OFF + GB + 384>(q.a));
+}
 // A refill whose consumer sits in the NEXT loop iteration: ptxas sees no use inside the loop body and schedules the
 // loads at the very end of it, right in front of the use.  Memory instructions do not move across a warp barrier,
 // so the barrier keeps them where the source has them (the lanes are converged anyway).
@@ -1149,10 +1167,12 @@ __device__ __forceinline__ uint32_t alpha_out2(uint32_t a[8], const uint32_t bb[
 }
 
 // alpha + output over one row group with the rebuilt beta in registers: B[i] is the beta above row k0 + i
+// top: nullptr, or where (shared memory, [half * 32]) the beta above the group's LAST row is to be read from
 template <int W, int NORM, bool TRACK, bool HARD>
 __device__ __forceinline__ void fwd_group(const WinCtx<W>& c, const uint32_t* stab_dir, uint32_t k0, uint32_t a[8],
                                           const uint32_t (*B)[8], const uint4& sv, const uint4& pv, const uint4& av, char* Y,
-                                          Range& ra, Range& rm, Range& rd, uint32_t& crc, bool skip0)
+                                          Range& ra, Range& rm, Range& rd, uint32_t& crc, bool skip0,
+                                          const uint4* top = nullptr)
 {
   // the scatter offsets as 16-bit loads: the halves come zero-extended from the load/store unit instead of costing
   // a mask and a shift on the ALU pipe, which the add-max instructions of this loop keep busy
@@ -1162,7 +1182,13 @@ __device__ __forceinline__ void fwd_group(const WinCtx<W>& c, const uint32_t* st
 #pragma unroll
   for (int r = 0; r < 4; r++) {
     const uint32_t x = wadd2(aa[r], sa[r]);
-    d[r] = alpha_out2<W, TRACK>(a, B[r], x, pa[r], sa[r], aa[r], rm);
+    if (r == 3 && top) {
+      const uint4    t0 = top[0], t1 = top[32];
+      const uint32_t bt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+      d[r] = alpha_out2<W, TRACK>(a, bt, x, pa[r], sa[r], aa[r], rm);
+    } else {
+      d[r] = alpha_out2<W, TRACK>(a, B[r], x, pa[r], sa[r], aa[r], rm);
+    }
     if (HARD) {
       // sign bit of -(max(v, -1)) is set exactly when v > 0 (no overflow: max(v,-1) >= -1)
       const uint32_t m  = wneg2(max2(wadd2(d[r], aa[r]), 0xFFFFFFFFu));
@@ -1174,6 +1200,7 @@ __device__ __forceinline__ void fwd_group(const WinCtx<W>& c, const uint32_t* st
     asm("ld.shared.u16 %0, [%1];" : "=r"(o_hi) : "r"(e16 + 4 * r + 2));
     *reinterpret_cast<uint16_t*>(Y + o_lo) = (uint16_t)(d[r] & 0xFFFFu);
     *reinterpret_cast<uint16_t*>(Y + o_hi) = (uint16_t)(d[r] >> 16);
+    if (r & 1) rd.add2v(d[r - 1], d[r]);
     if (NORM == 4 ? r == 2 : (r & 1) == 0) {
       if (r != 0 || !skip0) {
         normalize<true>(a);
@@ -1181,18 +1208,16 @@ __device__ __forceinline__ void fwd_group(const WinCtx<W>& c, const uint32_t* st
       }
     }
   }
-  rd.add2v(d[0], d[1]);
-  rd.add2v(d[2], d[3]);
 }
 
 // rebuild beta over the 8 rows b .. b+7 into registers: in: s = beta above row b+7 (as the backward pass left it BEFORE
 // normalising it; top_norm: it was normalised afterwards, i.e. it is not the window's boundary vector).
-// out: B[i] = beta above row b + i, i = 0..7 (values before their normalisation, like the reference stores them).
+// out: B[i] = beta above row b + i, i = 0..6 (values before their normalisation, like the reference stores them); the
+// beta above row b + 7 is the input vector itself, which the caller reads again from shared memory when row b + 7 comes
+// up (eight registers less through the whole unit).
 template <int NORM>
 __device__ __forceinline__ void rebuild8(uint32_t s[8], bool top_norm, const Unit& u, uint32_t (*B)[8])
 {
-#pragma unroll
-  for (int i = 0; i < 8; i++) B[7][i] = s[i];
   if (top_norm) normalize<true>(s);
 #pragma unroll
   for (int g = 1; g >= 0; g--) {
@@ -1222,6 +1247,28 @@ __device__ __forceinline__ Streams half_streams(const WinCtx<W>& c, bool dec2)
   return q;
 }
 
+// ---- checkpoints of the main fast path ------------------------------------------------------------------------------
+// The window is cut into 16-row chunks from the TOP: chunk j covers rows L-16(j+1) .. L-16j-1, nc = L / 16 of them, and
+// L % 16 rows (0, 4, 8 or 12) remain at the bottom.  The beta above every chunk (and above the bottom rows) is a
+// checkpoint in the warp's shared memory: ck[j], j = 0 the window's boundary vector.  They hold beta BEFORE its
+// normalisation, like the reference's beta array.
+// (Tried: the odd 8-row boundaries as additional checkpoints in HBM, which removes stage A of the forward pass and a
+// unit buffer -- 10 % fewer instructions, 48 KB more DRAM traffic per block, but 3 to 6 % slower: the loads of those
+// checkpoints, and the two unit buffers whose refills both had their consumers in the next loop iteration, could not
+// be scheduled without a wait that sits right behind freshly issued loads.)
+template <int W>
+__device__ __forceinline__ void ck_put(const WinCtx<W>& c, int j, const uint32_t s[8])
+{
+  c.ck[(j * 2 + 0) * 32] = make_uint4(s[0], s[1], s[2], s[3]);
+  c.ck[(j * 2 + 1) * 32] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+template <int W>
+__device__ __forceinline__ void ck_get(const WinCtx<W>& c, int j, uint32_t s[8])
+{
+  const uint4 v0 = c.ck[(j * 2 + 0) * 32], v1 = c.ck[(j * 2 + 1) * 32];
+  s[0] = v0.x; s[1] = v0.y; s[2] = v0.z; s[3] = v0.w; s[4] = v1.x; s[5] = v1.y; s[6] = v1.z; s[7] = v1.w;
+}
+
 // what the backward side hands to the forward side
 struct BackOut {
   uint32_t a[8];  // alpha boundary vector of this thread's windows
@@ -1229,16 +1276,17 @@ struct BackOut {
 };
 
 // ---- backward side of a half iteration: beta warm-up (rows 39..0), alpha warm-up (rows L-40..L-1), beta over the
-// window with a checkpoint every 16 rows into the warp's shared memory.  The alpha warm-up runs BEFORE the beta pass:
-// its five 8-row units are the first five of the beta pass, which finds them in registers.  Five unit buffers;
-// every buffer is refilled right after its unit has been consumed with the unit that is due 4..5 units later.
+// window with a checkpoint at every unit boundary.  The alpha warm-up runs BEFORE the beta pass: its five units are
+// the first five of the beta pass, which finds them in registers.  Every buffer is refilled right after its unit has
+// been consumed with the unit that is due four units later.
 template <int W, int NORM, bool TRACK>
 __device__ __forceinline__ void backward_side(const WinCtx<W>& c, bool dec2, BackOut* out)
 {
   constexpr int WH = W / 2;
   constexpr int GB = (int)kGroupBytes;
-  const int     ng = (int)c.L >> 2;       // row groups
-  const int     nu = ng >> 1;             // 8-row units, numbered from the top in the beta pass
+  const int     ng = (int)c.L >> 2;       // row groups (L % 4 == 0)
+  const int     nu = ng >> 1;             // 8-row units, numbered from the top
+  const bool    rem = (ng & 1) != 0;      // rows 0..3 are a group of their own
   const Streams q0  = half_streams<W>(c, dec2);
   const Streams top = q0.at((ng - 10) * GB);  // rows L-40 ..
   Range rb, ra;
@@ -1283,20 +1331,17 @@ __device__ __forceinline__ void backward_side(const WinCtx<W>& c, bool dec2, Bac
     for (int i = 0; i < 8; i++) out->a[i] = a[i];
   }
 
-  // beta pass: unit k covers the row groups ng-2-2k, ng-1-2k; units 0..4 are in F4, F3, F2, F1, F0
-  auto ck_store = [&](int j) {
-    c.ck[(j * 2 + 0) * 32] = make_uint4(s[0], s[1], s[2], s[3]);
-    c.ck[(j * 2 + 1) * 32] = make_uint4(s[4], s[5], s[6], s[7]);
-  };
-  // unit 0 first, so that the loop works on a ring of four buffers (F3, F2, F1, F0 = units k .. k+3) with no special
+  // beta pass: unit k covers the row groups ng-2-2k, ng-1-2k; units 0..4 are in F4, F3, F2, F1, F0.
+  // Unit 0 first, so that the loop works on a ring of four buffers (F3, F2, F1, F0 = units k .. k+3) with no special
   // case: a conditional "this buffer came with the warm-up" inside the loop makes the compiler carry a fifth buffer
-  // around and copy every refill into it at the back edge, waiting for loads it has only just issued
-  ck_store(0);
+  // around and copy every refill into it at the back edge, waiting for loads it has only just issued.
+  // A checkpoint at every second unit boundary (16 rows).
+  ck_put<W>(c, 0, s);
   beta_unit<NORM, TRACK>(s, F4, rb, false);
   Streams q = q0.at((ng - 4) * GB);  // unit k; unit k + i is at q - 2 i GB
   int     k = 1;
 #pragma unroll 1
-  for (; k + 4 <= nu; k += 4) {  // nu is even, k odd: at least one unit is left for the tail
+  for (; k + 4 <= nu; k += 4) {  // k is odd: the parity of the boundaries is static
     if (k + 16 <= nu && (B200_PF & 1)) {  // L2: three bodies ahead
       prefetch_unit<-24 * GB>(q);
       prefetch_unit<-26 * GB>(q);
@@ -1305,114 +1350,190 @@ __device__ __forceinline__ void backward_side(const WinCtx<W>& c, bool dec2, Bac
     }
     beta_unit<NORM, TRACK>(s, F3, rb, false);
     if (k + 4 < nu) refill_unit<-8 * GB>(q.after(s[1]), F3);
-    ck_store((k + 1) >> 1);
+    ck_put<W>(c, (k + 1) >> 1, s);
     beta_unit<NORM, TRACK>(s, F2, rb, false);
     if (k + 5 < nu) refill_unit<-10 * GB>(q.after(s[1]), F2);
     beta_unit<NORM, TRACK>(s, F1, rb, false);
     if (k + 6 < nu) refill_unit<-12 * GB>(q.after(s[1]), F1);
-    ck_store((k + 3) >> 1);
-    beta_unit<NORM, TRACK>(s, F0, rb, false);
+    ck_put<W>(c, (k + 3) >> 1, s);
+    beta_unit<NORM, TRACK>(s, F0, rb, NORM == 2 && !rem && k + 4 == nu);
     if (k + 7 < nu) refill_unit<-14 * GB>(q.after(s[1]), F0);
     q = q.at(-8 * GB);
   }
-  if (k + 1 == nu) {  // one unit left: the lower half of the last chunk
-    beta_unit<NORM, TRACK>(s, F3, rb, NORM == 2);
-  } else {            // three units left
-    beta_unit<NORM, TRACK>(s, F3, rb, false);
-    ck_store((k + 1) >> 1);
-    beta_unit<NORM, TRACK>(s, F2, rb, false);
-    beta_unit<NORM, TRACK>(s, F1, rb, NORM == 2);
+  // up to three units are left
+  if (k < nu) beta_unit<NORM, TRACK>(s, F3, rb, NORM == 2 && !rem && k + 1 == nu);  // k is odd
+  if (k + 1 < nu) {
+    ck_put<W>(c, (k + 1) >> 1, s);
+    beta_unit<NORM, TRACK>(s, F2, rb, NORM == 2 && !rem && k + 2 == nu);
+  }
+  if (k + 2 < nu) beta_unit<NORM, TRACK>(s, F1, rb, NORM == 2 && !rem);
+  if (rem) {  // rows 3..0
+    if ((nu & 1) == 0) ck_put<W>(c, nu >> 1, s);  // they are all that is left below the last chunk
+    Rows4 r4;
+    rows_of(ld128<0>(q0.s), ld128<0>(q0.p), make_uint4(ld32<0>(q0.a), ld32<128>(q0.a), ld32<256>(q0.a), ld32<384>(q0.a)), r4);
+    beta_group<NORM, TRACK>(s, r4, rb, NORM == 2);
   }
   out->rb = rb;
   out->ra = ra;
 }
 
-// ---- forward side: alpha + output over the window, 16 rows at a time (stages A, B, C above) ----
+// state of the forward pass that the out-of-line pieces update
+struct FwdState {
+  uint32_t a[8];
+  Range    ra, rm, rd;
+  uint32_t crc;
+};
+
+// alpha + output over the `nrows` (4 .. 16) rows 0 .. nrows-1 at the bottom of the window, from checkpoint j, one row at
+// a time with beta in local memory: where the window is not a whole number of chunks, and (edge) rows 0..3 next to the
+// known start state in the reference's saturating arithmetic.  Out of line: a few rows per half iteration.
 template <int W, int NORM, bool TRACK, bool HARD>
-__device__ __forceinline__ HalfResult forward_side(const WinCtx<W>& c, bool dec2, int G, const BackOut& bo)
+__device__ __noinline__ void fwd_rows_slow(const WinCtx<W> c, bool dec2, int nrows, int j, bool top_norm, bool edge,
+                                           FwdState* st)
 {
-  constexpr int GB = (int)kGroupBytes;
-  const int     L  = (int)c.L;
-  const int     nc = L >> 4;  // 16-row chunks, numbered from the top of the window
-  Range rb = bo.rb, ra = bo.ra, rm, rd;
-  rd.reset();
-  rm.hi = kMin2; rm.lo = kMax2;
-  uint32_t crc = 0;
-  uint32_t s[8], a[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) a[i] = bo.a[i];
-  Streams q = half_streams<W>(c, dec2);  // first row group of the chunk
-  // upper unit of the chunk (stages A and C), upper unit of the next chunk (in flight from stage A on), lower unit
-  Unit X, Xn, Yb;
-  load_unit<2 * GB>(q, X);  // rows 0..15: the backward pass has just read them
-  load_unit<0>(q, Yb);
-  // L2: what the NEXT half iteration reads first (the other decoder's parity and systematic streams, rows 0..39 and
-  // L-40..L-1; its a-priori values are what this pass writes)
-  {
-    const char* const ns = c.in_item + c.sp_off;                                           // systematic (DEC1 only)
-    const char* const np = c.in_item + (dec2 ? 1u : 2u) * (size_t)c.s_bytes + c.sp_off;  // the other decoder's parity
-    const int         ng = L >> 2;
-#pragma unroll 1
-    for (int g = 0; g < 10 && (B200_PF & 4); g++) {
-      pf_l2_dyn(np + g * GB);
-      pf_l2_dyn(np + (ng - 10 + g) * GB);
-      if (dec2) {
-        pf_l2_dyn(ns + g * GB);
-        pf_l2_dyn(ns + (ng - 10 + g) * GB);
+  constexpr int b = 0;
+  const Streams q = half_streams<W>(c, dec2);
+  uint32_t x[16], y[16], sy[16], ax[16];
+  for (int r = 0; r < nrows; r++) {
+    const char* g = q.s + (r >> 2) * (int)kGroupBytes + (r & 3) * 4;
+    sy[r] = __ldcg(reinterpret_cast<const uint32_t*>(g));
+    y[r]  = __ldcg(reinterpret_cast<const uint32_t*>(q.p + (r >> 2) * (int)kGroupBytes + (r & 3) * 4));
+    ax[r] = __ldcg(reinterpret_cast<const uint32_t*>(q.a + r * 128));
+    x[r]  = wadd2(ax[r], sy[r]);
+  }
+  uint32_t B[16][8], s[8];
+  ck_get<W>(c, j, s);
+  for (int i = 0; i < 8; i++) B[nrows - 1][i] = s[i];
+  if (top_norm) normalize<true>(s);
+  for (int r = nrows - 1; r >= 1; r--) {
+    beta_step<true>(s, x[r], y[r], wadd2(x[r], y[r]));
+    for (int i = 0; i < 8; i++) B[r - 1][i] = s[i];
+    if (NORM == 4 ? (r & 3) == 0 : (r & 1) == 0) normalize<true>(s);
+  }
+  uint32_t a[8];
+  for (int i = 0; i < 8; i++) a[i] = st->a[i];
+  Range ra = st->ra, rm = st->rm, rd = st->rd, unused;
+  uint32_t crc = st->crc;
+  unused.reset();
+  char* const Y = out_base<W>(c, dec2);
+  for (int r = 0; r < nrows; r++) {
+    const uint32_t k = (uint32_t)(b + r);
+    if (edge && k < (uint32_t)kExactRows) {  // exact arithmetic; the reference's schedule (after row 2) is both schedules'
+      const uint32_t xe = dec2 ? ax[r] : sadd2(ax[r], sy[r]);
+      uint32_t       o  = alpha_out_step<false>(a, B[r], xe, y[r], sadd2(xe, y[r]), unused);
+      if (W == 8) o = sra1_2(o);
+      store_out<W>(c, dec2, k, o, ax[r], rd, crc);
+      if (k == 2) {
+        normalize<false>(a);
+        if (TRACK) ra.add8(a);
+      }
+    } else {
+      const uint32_t d = alpha_out2<W, TRACK>(a, B[r], x[r], y[r], sy[r], ax[r], rm);
+      store_diff<W, HARD>(c, dec2, k, d, ax[r], rd, crc, Y);
+      if ((NORM == 4 ? (k & 3) == 2 : (k & 1) == 0) && k != 0) {
+        normalize<true>(a);
+        if (TRACK) ra.add8(a);
       }
     }
   }
-  char* const           Yout = out_base<W>(c, dec2);
-  const uint32_t* const sdir = c.stab + (dec2 ? 0u : kStabDir);
-#pragma unroll 1
-  for (int j = nc - 1; j >= 0; j--) {
-    const uint32_t lo = (uint32_t)(L - 16 * (j + 1));
-    if (j >= 2 && (B200_PF & 2)) {  // L2: two chunks ahead
-      prefetch_unit<8 * GB>(q);
-      prefetch_unit<10 * GB>(q);
-    }
-    uint32_t B[8][8];
-    // ---- stage A: beta from the checkpoint down the upper 8 rows ----
-    {
-      const uint4 c0 = c.ck[(j * 2 + 0) * 32], c1 = c.ck[(j * 2 + 1) * 32];
-      s[0] = c0.x; s[1] = c0.y; s[2] = c0.z; s[3] = c0.w; s[4] = c1.x; s[5] = c1.y; s[6] = c1.z; s[7] = c1.w;
-      if (j != 0) normalize<true>(s);  // every checkpoint but the boundary vector was normalised after it was stored
-      Rows4 r4;
-      rows_of(X.s[1], X.p[1], X.a[1], r4);
-      beta_group<NORM, false>(s, r4, rb, false);
-      rows_of(X.s[0], X.p[0], X.a[0], r4);
+  for (int i = 0; i < 8; i++) st->a[i] = a[i];
+  st->ra = ra; st->rm = rm; st->rd = rd; st->crc = crc;
+}
+
+// ---- forward side: alpha + output over the window, 16 rows at a time: from the checkpoint beta first runs down the
+// upper 8 rows (stage A), then the lower 8 rows of beta are rebuilt into registers and alpha + the outputs run over
+// them (stage B), then the same for the upper 8 rows (stage C).  edge: rows 0..3 in exact arithmetic.
+template <int W, int NORM, bool TRACK, bool HARD>
+__device__ __forceinline__ HalfResult forward_side(const WinCtx<W>& c, bool dec2, int G, bool edge, const BackOut& bo)
+{
+  constexpr int GB = (int)kGroupBytes;
+  const int     L  = (int)c.L;
+  const int     nc = L >> 4, R = L & 15;
+  Range rb = bo.rb;
+  FwdState f;
 #pragma unroll
-      for (int r = 3; r >= 1; r--) {
-        beta_step<true>(s, r4.x[r], r4.y[r], wadd2(r4.x[r], r4.y[r]));
-        if (NORM == 2 && r == 2) normalize<true>(s);
+  for (int i = 0; i < 8; i++) f.a[i] = bo.a[i];
+  f.ra = bo.ra;
+  f.rd.reset();
+  f.rm.hi = kMin2; f.rm.lo = kMax2;
+  f.crc = 0;
+  // the bottom of the window, out of line: the rows below the last chunk, or the last chunk when it has the edge rows
+  int jb = nc - 1;  // lowest chunk not done yet
+#ifndef B200_NOSLOW
+  if (R) {
+    fwd_rows_slow<W, NORM, TRACK, HARD>(c, dec2, R, nc, true, edge, &f);
+  } else if (edge) {
+    fwd_rows_slow<W, NORM, TRACK, HARD>(c, dec2, 16, jb, jb != 0, true, &f);
+    jb--;
+  }
+#endif
+  if (jb >= 0) {
+    uint32_t a[8], s[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = f.a[i];
+    Range    ra = f.ra, rm = f.rm, rd = f.rd;
+    uint32_t crc = f.crc;
+    Streams  q = half_streams<W>(c, dec2).at((L - 16 * (jb + 1)) * 128);  // first row group of the chunk
+    // upper unit of the chunk (stages A and C), upper unit of the next chunk (in flight from stage A on), lower unit
+    Unit X, Xn, Yb;
+    load_unit<2 * GB>(q, X);  // the backward pass has just read these rows
+    load_unit<0>(q, Yb);
+    char* const           Yout = out_base<W>(c, dec2);
+    const uint32_t* const sdir = c.stab + (dec2 ? 0u : kStabDir);
+#pragma unroll 1
+    for (int j = jb; j >= 0; j--) {
+      const uint32_t lo = (uint32_t)(L - 16 * (j + 1));
+      if (j >= 2 && (B200_PF & 2)) {  // L2: two chunks ahead
+        prefetch_unit<8 * GB>(q);
+        prefetch_unit<10 * GB>(q);
       }
-      beta_step<true>(s, r4.x[0], r4.y[0], wadd2(r4.x[0], r4.y[0]));  // s = beta above row lo + 7, not yet normalised
+      uint32_t B[7][8];
+      // ---- stage A: beta from the checkpoint down the upper 8 rows ----
+      {
+        ck_get<W>(c, j, s);
+        if (j != 0) normalize<true>(s);  // every checkpoint but the boundary vector was normalised after it was stored
+        Rows4 r4;
+        rows_of(X.s[1], X.p[1], X.a[1], r4);
+        beta_group<NORM, false>(s, r4, rb, false);
+        rows_of(X.s[0], X.p[0], X.a[0], r4);
+#pragma unroll
+        for (int r = 3; r >= 1; r--) {
+          beta_step<true>(s, r4.x[r], r4.y[r], wadd2(r4.x[r], r4.y[r]));
+          if (NORM == 2 && r == 2) normalize<true>(s);
+        }
+        beta_step<true>(s, r4.x[0], r4.y[0], wadd2(r4.x[0], r4.y[0]));  // s = beta above row lo + 7, not yet normalised
+        ck_put<W>(c, kMaxCk, s);  // the scratch vector: row lo + 7 reads it back
+      }
+      if (j > 0) load_unit_sp<6 * GB>(q, Xn);  // (its a-priori words follow after stage B: eight registers less here)
+      // ---- stage B: the lower 8 rows ----
+      rebuild8<NORM>(s, true, Yb, B);
+      fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo, a, &B[0], Yb.s[0], Yb.p[0], Yb.a[0], Yout, ra, rm, rd, crc,
+                                      NORM == 2 && lo == 0);
+      fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 4, a, &B[4], Yb.s[1], Yb.p[1], Yb.a[1], Yout, ra, rm, rd, crc, false,
+                                      c.ck + kMaxCk * 64);
+      if (j > 0) {
+        load_unit_a<6 * GB>(q, Xn);
+        refill_unit<4 * GB>(q.after(a[1]), Yb);
+      }
+      // ---- stage C: the upper 8 rows ----
+      ck_get<W>(c, j, s);
+      rebuild8<NORM>(s, j != 0, X, B);
+      fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 8, a, &B[0], X.s[0], X.p[0], X.a[0], Yout, ra, rm, rd, crc, false);
+      fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 12, a, &B[4], X.s[1], X.p[1], X.a[1], Yout, ra, rm, rd, crc, false,
+                                      c.ck + j * 64);
+      X = Xn;
+      q = q.at(4 * GB);
     }
-    if (j > 0) load_unit<6 * GB>(q, Xn);
-    // ---- stage B: the lower 8 rows ----
-    rebuild8<NORM>(s, true, Yb, B);
-    fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo, a, &B[0], Yb.s[0], Yb.p[0], Yb.a[0], Yout, ra, rm, rd, crc,
-                                    NORM == 2 && lo == 0);
-    fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 4, a, &B[4], Yb.s[1], Yb.p[1], Yb.a[1], Yout, ra, rm, rd, crc, false);
-    if (j > 0) refill_unit<4 * GB>(q.after(a[1]), Yb);
-    // ---- stage C: the upper 8 rows ----
-    {
-      const uint4 c0 = c.ck[(j * 2 + 0) * 32], c1 = c.ck[(j * 2 + 1) * 32];
-      s[0] = c0.x; s[1] = c0.y; s[2] = c0.z; s[3] = c0.w; s[4] = c1.x; s[5] = c1.y; s[6] = c1.z; s[7] = c1.w;
-    }
-    rebuild8<NORM>(s, j != 0, X, B);
-    fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 8, a, &B[0], X.s[0], X.p[0], X.a[0], Yout, ra, rm, rd, crc, false);
-    fwd_group<W, NORM, TRACK, HARD>(c, sdir, lo + 12, a, &B[4], X.s[1], X.p[1], X.a[1], Yout, ra, rm, rd, crc, false);
-    X = Xn;
-    q = q.at(4 * GB);
+    f.ra = ra; f.rm = rm; f.rd = rd; f.crc = crc;
   }
   __syncwarp();
 
   HalfResult res;
-  res.dmax = range_absmax(rd);
-  res.crc  = crc;
+  res.dmax = range_absmax(f.rd);
+  res.crc  = f.crc;
   bool ok  = true;
   if (TRACK) {  // the proof obligations of the tracked tier (see half_iteration_fast)
+    const Range ra = f.ra, rm = f.rm;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       const int bh = h ? hi16(rb.hi) : lo16(rb.hi), bl = h ? hi16(rb.lo) : lo16(rb.lo);
@@ -1433,12 +1554,53 @@ __device__ __forceinline__ HalfResult forward_side(const WinCtx<W>& c, bool dec2
 
 // one copy of the backward side serves both forward variants (hard: CRC modes)
 template <int W, int NORM, bool TRACK>
-__device__ __forceinline__ HalfResult half_fast2(const WinCtx<W>& c, bool dec2, int G, bool hard)
+__device__ __forceinline__ HalfResult half_fast2(const WinCtx<W>& c, bool dec2, int G, bool edge, bool hard)
 {
   BackOut bo;
   backward_side<W, NORM, TRACK>(c, dec2, &bo);
-  return hard ? forward_side<W, NORM, TRACK, true>(c, dec2, G, bo) : forward_side<W, NORM, TRACK, false>(c, dec2, G, bo);
+  return hard ? forward_side<W, NORM, TRACK, true>(c, dec2, G, edge, bo)
+              : forward_side<W, NORM, TRACK, false>(c, dec2, G, edge, bo);
 }
+
+// ---- general path (L % 4 != 0): staged chunks through the TMA ring, out of line like the tracked tier below.  The
+// staging buffers share the warp's shared memory with the checkpoints of the main path, so every half iteration sets
+// them up itself: no a-priori input -> the A part reads as zero; DEC2 has no separate systematic input (x = E) -> the
+// sys part reads as zero (its copies leave that part alone), so both decoders run the same branch-free code.
+template <int W>
+__device__ __noinline__ HalfResult half_general(const WinCtx<W> c, bool dec2, int G, int tier, bool any_crc, Pipe* pp)
+{
+  Pipe pipe = *pp;
+  if (c.noap)
+    for (int i = c.lane; i < kStages * 64; i += 32)
+      *reinterpret_cast<uint4*>(c.stages + (i >> 6) * kStageBytes + 2048 + (i & 63) * 16) = make_uint4(0, 0, 0, 0);
+  if (dec2)
+    for (int i = c.lane; i < kStages * 64; i += 32)
+      *reinterpret_cast<uint4*>(c.stages + (i >> 6) * kStageBytes + (i & 63) * 16) = make_uint4(0, 0, 0, 0);
+  // generic-proxy writes (the above, the previous half iteration's outputs) before the bulk copies
+  fence_proxy_async();
+  __syncwarp();
+  HalfResult r;
+  if (tier == 0)
+    r = any_crc ? half_fast<W, false, false, true>(c, dec2, G, pipe) : half_fast<W, false, false, false>(c, dec2, G, pipe);
+  else if (tier == 1)
+    r = any_crc ? half_fast<W, false, true, true>(c, dec2, G, pipe) : half_fast<W, false, true, false>(c, dec2, G, pipe);
+  else
+    r = any_crc ? half_fast<W, true, true, true>(c, dec2, G, pipe) : half_fast<W, true, true, false>(c, dec2, G, pipe);
+  *pp = pipe;
+  return r;
+}
+
+// The tracked tier (NORM = 2, bookkeeping) through the main path is written and bit-exact, but NOT instantiated by
+// default: with it in the kernel -- inlined or out of line -- ptxas spills eight registers of the plain tier's forward
+// loop right behind the loads that fill them (5.05 instead of 4.63 ms per 65 536 blocks).  The tracked tier runs
+// through the general path instead.
+#ifdef B200_TRK2
+template <int W>
+__device__ __noinline__ HalfResult half_tracked2(const WinCtx<W> c, bool dec2, int G, bool hard)
+{
+  return half_fast2<W, 2, true>(c, dec2, G, true, hard);
+}
+#endif
 
 // QPP of this K as a scatter table, computed from (f1, f2) by the whole CTA:
 //   pi(d*L + k) = pi(k) + L * d * (f1 + f2*d*L + 2*f2*k)  (mod K = W*L), so with pi(k) = w0*L + r every window
@@ -1655,7 +1817,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
       const uint32_t crc_mode = a.crc_mode_cb ? a.crc_mode_cb[cb] : a.crc_mode;
       const int      which    = crc_mode == CRC_24A ? 0 : 1;
       const bool     any_crc  = __any_sync(0xFFFFFFFFu, crc_mode != CRC_NONE);
-      const bool     v2       = (c.L & 15u) == 0 && (a.force_exact & 8u) == 0;  // the main fast path takes this block size
+      const bool     v2       = (c.L & 3u) == 0 && (a.force_exact & 8u) == 0;  // the main fast path takes this block size
       // CRC modes: this thread's window pair in the tables of the block's polynomial ([dir][row][window])
       const uint32_t* Rblk = any_crc ? a.crc_pos + a.crc_pos_off[wi.kidx] + (size_t)which * 2 * c.K + 2 * t : nullptr;
       // The first half iteration has no a-priori information: it does not read A.  A itself is only cleared when a
@@ -1682,39 +1844,20 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
         // force_exact: bit 0 = exact variant only (tests); bits 1, 2 = skip the pure / the static tier, bit 3 = general
         // path only (measurements)
         const bool pure = __all_sync(0xFFFFFFFFu, (a.force_exact & 3u) == 0 && G <= kPureFastG);
-        if (pure && v2) {
-          r       = half_fast2<W, 4, false>(c, dec2, G, any_crc);
+        const bool stat = !pure && __all_sync(0xFFFFFFFFu, (a.force_exact & 5u) == 0 && G <= kStaticFastG);
+        const bool trk  = !pure && !stat && __all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kMaxFastG);
+        if (v2 && (pure || stat)) {
+          r       = half_fast2<W, 4, false>(c, dec2, G, stat, any_crc);
           fast_ok = true;
-        } else if (!__all_sync(0xFFFFFFFFu, (a.force_exact & 1u) == 0 && G <= kMaxFastG)) {
-          // nothing: exact variant below
+#ifdef B200_TRK2  // development probe: the tracked tier through the main path (see half_tracked2)
+        } else if (v2 && trk) {
+          r       = half_tracked2<W>(c, dec2, G, any_crc);
+          fast_ok = __all_sync(0xFFFFFFFFu, r.proven || done);
+#endif
 #ifndef B200_V2ONLY
-        } else {
-          // ---- general path: staged chunks through the TMA ring.  The staging buffers share the warp's shared
-          // memory with the checkpoints of the main path, so every half iteration sets them up itself: no a-priori
-          // input -> the A part reads as zero; DEC2 has no separate systematic input (x = E) -> the sys part reads as
-          // zero (its copies leave that part alone), so both decoders run the same branch-free code.
-          if (c.noap)
-            for (int i = lane; i < kStages * 64; i += 32)
-              *reinterpret_cast<uint4*>(c.stages + (i >> 6) * kStageBytes + 2048 + (i & 63) * 16) = make_uint4(0, 0, 0, 0);
-          if (dec2)
-            for (int i = lane; i < kStages * 64; i += 32)
-              *reinterpret_cast<uint4*>(c.stages + (i >> 6) * kStageBytes + (i & 63) * 16) = make_uint4(0, 0, 0, 0);
-          // generic-proxy writes (the above, the previous half iteration's outputs) before the bulk copies
-          fence_proxy_async();
-          __syncwarp();
-          if (pure) {
-            r       = any_crc ? half_fast<W, false, false, true>(c, dec2, G, pipe)
-                              : half_fast<W, false, false, false>(c, dec2, G, pipe);
-            fast_ok = true;
-          } else if (__all_sync(0xFFFFFFFFu, (a.force_exact & 5u) == 0 && G <= kStaticFastG)) {
-            r       = any_crc ? half_fast<W, false, true, true>(c, dec2, G, pipe)
-                              : half_fast<W, false, true, false>(c, dec2, G, pipe);
-            fast_ok = true;
-          } else {
-            r       = any_crc ? half_fast<W, true, true, true>(c, dec2, G, pipe)
-                              : half_fast<W, true, true, false>(c, dec2, G, pipe);
-            fast_ok = __all_sync(0xFFFFFFFFu, r.proven || done);
-          }
+        } else if (pure || stat || trk) {
+          r       = half_general<W>(c, dec2, G, pure ? 0 : stat ? 1 : 2, any_crc, &pipe);
+          fast_ok = (pure || stat) ? true : __all_sync(0xFFFFFFFFu, r.proven || done);
 #endif
         }
         if (!fast_ok) {

@@ -118,6 +118,12 @@ def ref():
         getattr(L, n).restype = C.c_size_t
     L.refh_batch_run_all.argtypes = [_i16p, C.c_uint32, C.c_int, _u8p, C.c_uint32, C.c_uint32,
                                      C.c_uint32, C.c_uint32, C.c_uint32]
+    if hasattr(L, "refh_pool_create"):
+        L.refh_pool_create.argtypes = [C.c_uint32]
+        L.refh_pool_create.restype = C.c_void_p
+        L.refh_pool_run.argtypes = [C.c_void_p, _i16p, C.c_uint32, C.c_int, _u8p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                    C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.refh_pool_destroy.argtypes = [C.c_void_p]
     L.refh_tdec_trace.argtypes = [_i16p, C.c_int, C.c_uint32, C.c_uint32, _u8p, C.c_void_p]
     L.refh_tcod_encode.argtypes = [_u8p, _u8p, C.c_uint32]
     L.refh_rm_turbo_tx.argtypes = [_u8p, C.c_uint32, _u8p, C.c_uint32, C.c_uint32]
@@ -177,6 +183,33 @@ def ref_run_all(llr, K, nit, natural=True, threads=None):
                               threads or min(n, os.cpu_count() or 1))
     assert rc == 0
     return out
+
+
+class RefPool:
+    """Persistent pool of reference decoders: one srslte_tdec_t per pthread, created once (outside any timing), the
+    way the reference's own turbodecoder_test initialises once and loops.  run() returns (bytes, wall seconds of the
+    decode loops, summed per-thread loop seconds)."""
+
+    def __init__(self, threads):
+        self.R = ref()
+        self.threads = int(threads)
+        self.h = self.R.refh_pool_create(self.threads)
+        assert self.h
+
+    def run(self, llr, K, nit, natural=True):
+        llr = np.ascontiguousarray(llr, dtype=np.int16)
+        n = llr.shape[0]
+        out = np.zeros((n, K // 8), np.uint8)
+        wall, busy = C.c_double(0), C.c_double(0)
+        rc = self.R.refh_pool_run(self.h, llr.reshape(-1), llr.shape[1], int(natural), out.reshape(-1), K // 8, n, K, nit,
+                                  C.byref(wall), C.byref(busy))
+        assert rc == 0
+        return out, wall.value, busy.value
+
+    def close(self):
+        if self.h:
+            self.R.refh_pool_destroy(self.h)
+            self.h = None
 
 
 def port_trace(llr1, K, nit, natural=True):
