@@ -137,6 +137,68 @@ SRSLTE_API int srslte_b200_sch_decode_tb(srslte_softbuffer_rx_t* softbuffer, uin
                                          uint32_t nof_e_bits, int16_t* e_bits, uint8_t* data, uint32_t max_iterations,
                                          float* avg_iterations);
 
+/* ---- sch.h:98-107 / sch.c:502-532: the DL-SCH decode entry points themselves ----------------------------------
+ * srslte_dlsch_decode2 is what pdsch.c:786 (and through srslte_dlsch_decode, pmch.c:383) calls.  In the reference
+ * it shares sch.c with the encoder and with srslte_sch_init / _free / _set_max_noi / _last_noi, which stay where
+ * they are: the reference's sch.c is compiled UNCHANGED with two compile definitions
+ *     -Dsrslte_dlsch_decode2=srslte_dlsch_decode2_cpu -Dsrslte_dlsch_decode=srslte_dlsch_decode_cpu
+ * (its own two functions get out of the way) and linked with this library, whose srslte_tdec_init the unchanged
+ * srslte_sch_init then calls for q->decoder.  The structures below restate the reference layouts these two
+ * functions read (phch/ra.h:43-53, phch/pdsch_cfg.h:41-79, phch/sch.h:52-77; SRSLTE_MAX_PRB = 110,
+ * SRSLTE_MAX_CODEWORDS = 2); tests/test_compat_abi.py checks sizes and offsets against the compiled reference.   */
+typedef struct {
+  uint32_t mod; /* srslte_mod_t: BPSK = 0, QPSK, 16QAM, 64QAM, 256QAM (phy_common.h:241-247) */
+  int      tbs;
+  int      rv;
+  uint32_t nof_bits;
+  uint32_t cw_idx;
+  bool     enabled;
+  uint32_t mcs_idx;
+} srslte_ra_tb_t;
+
+typedef struct {
+  uint32_t       tx_scheme; /* srslte_tx_scheme_t */
+  uint32_t       pmi;
+  bool           prb_idx[2][110];
+  uint32_t       nof_prb;
+  uint32_t       nof_re;
+  uint32_t       nof_symb_slot[2];
+  srslte_ra_tb_t tb[2];
+  int            last_tbs[2];
+  uint32_t       nof_tb;
+  uint32_t       nof_layers;
+} srslte_pdsch_grant_t;
+
+typedef struct {
+  srslte_pdsch_grant_t grant;
+  uint16_t             rnti;
+  uint32_t             max_nof_iterations;
+  uint32_t             decoder_type; /* srslte_mimo_decoder_t */
+  float                p_a;
+  uint32_t             p_b;
+  float                rs_power;
+  bool                 power_scale;
+  bool                 csi_enable;
+  bool                 use_tbs_index_alt;
+  union {
+    void*                   tx[2];
+    srslte_softbuffer_rx_t* rx[2];
+  } softbuffers;
+  bool     meas_time_en;
+  uint32_t meas_time_value;
+} srslte_pdsch_cfg_t;
+
+/* the head of srslte_sch_t (sch.h:52-77); buffers, encoder, decoder, CRC objects follow in the reference's struct */
+typedef struct {
+  uint32_t max_iterations;
+  float    avg_iterations;
+  bool     llr_is_8bit;
+} srslte_sch_head_t;
+
+SRSLTE_API int srslte_dlsch_decode(void* q /* srslte_sch_t* */, srslte_pdsch_cfg_t* cfg, int16_t* e_bits, uint8_t* data);
+SRSLTE_API int srslte_dlsch_decode2(void* q /* srslte_sch_t* */, srslte_pdsch_cfg_t* cfg, int16_t* e_bits, uint8_t* data,
+                                    int codeword_idx, uint32_t nof_layers);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,6 +106,7 @@ struct srslte_b200_ctx {
   PinBuf<uint32_t> h_cbK;
   Schedule     sched;
   bool         sched_valid = false;
+  cudaStream_t sched_stream = nullptr;   // stream the cached schedule (and the counters' first clear) was uploaded on
   uint32_t     sched_n = 0, sched_uniform_K = 0;
   std::vector<uint32_t> sched_K;       // per-block K of the cached schedule when not uniform
   // working-layout staging for natural-order input
@@ -307,7 +308,11 @@ int ensure_schedule(srslte_b200_ctx* ctx, const uint32_t* K, uint32_t uniform_K,
     else
       same = ctx->sched_K.size() == n && std::memcmp(ctx->sched_K.data(), K, n * sizeof(uint32_t)) == 0;
   }
-  if (same) return 0;
+  if (same) {
+    // the cached arrays were uploaded on another stream: order this stream behind those copies
+    if (st != ctx->sched_stream && ctx->ev_sched) CU(cudaStreamWaitEvent(st, ctx->ev_sched, 0));
+    return 0;
+  }
   ctx->sched_valid = false;
   int rc = build_schedule(ctx, K, uniform_K, n, ctx->sched);
   if (rc) return rc;
@@ -357,6 +362,7 @@ int ensure_schedule(srslte_b200_ctx* ctx, const uint32_t* K, uint32_t uniform_K,
     ctx->sched_K.clear();
   }
   CU(cudaEventRecord(ctx->ev_sched, st));
+  ctx->sched_stream    = st;
   ctx->sched_n         = n;
   ctx->sched_uniform_K = uniform_K;
   ctx->sched_valid     = true;
@@ -409,6 +415,7 @@ int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint
   if (ctx->counters.cap == 0) {
     CU(ctx->counters.reserve(4));
     CU(cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(uint32_t), st));
+    CU(cudaStreamSynchronize(st));  // once per context: later calls may come on other streams
   }
   if (b->crc_mode != SRSLTE_B200_CRC_NONE || d_crc_mode_cb) {
     // the window decoders check CRCs through per-bit contribution tables: make sure every K of this launch has one
@@ -509,13 +516,19 @@ int srslte_b200_ctx_create(srslte_b200_ctx_t** out, int cuda_device)
     delete ctx;
     return SRSLTE_B200_ERROR;
   }
-  for (int i = 0; i < 2; i++) {
-    cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming);
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+    e = cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming);
   }
   ctx->stream = ctx->own_stream;
-  upload_crc_tables();
+  if (e == cudaSuccess) e = upload_crc_tables();  // a failed constant upload would give wrong CRC results, not an error
+  if (e != cudaSuccess) {
+    fprintf(stderr, "srslte_b200: context setup failed: %s\n", cudaGetErrorString(e));
+    srslte_b200_ctx_destroy(ctx);
+    return SRSLTE_B200_ERROR;
+  }
   *out = ctx;
   return SRSLTE_B200_SUCCESS;
 }
@@ -552,6 +565,8 @@ void srslte_b200_ctx_destroy(srslte_b200_ctx_t* ctx)
     if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
     if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
   }
+  if (ctx->ev_sched) cudaEventDestroy(ctx->ev_sched);
+  if (ctx->ev_staging) cudaEventDestroy(ctx->ev_staging);
   for (auto& v : ctx->tev)
     for (auto& pr : v) {
       cudaEventDestroy(pr.first);
@@ -1192,12 +1207,15 @@ static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
   std::vector<size_t>   e_base(n_tb, 0);
   std::vector<CbJob>    jobs;
   std::vector<uint32_t> Ks;
+  std::vector<uint8_t>  sb_used(pool->n_sb, 0);  // a soft buffer may appear once per batch (its blocks are combined
+                                                 // and its CRC / saved-data state updated by one TB only)
   size_t                e_total = 0;
   for (uint32_t i = 0; i < n_tb; i++) {
     srslte_b200_tb_t& t = tbs[i];
     t.ret            = SRSLTE_B200_ERROR_INVALID_INPUTS;
     t.avg_iterations = 0;
     if ((!sym && !t.e_bits) || !t.data || t.softbuffer >= pool->n_sb || t.rv > 3 || t.qm == 0) continue;
+    if (sb_used[t.softbuffer]) continue;  // second TB on the same soft buffer in one call: -2
     if (sym && (!sym[i].symbols || (uint64_t)sym[i].mod_bits * sym[i].nof_symbols < t.nof_e_bits ||
                 (sym[i].mod_bits != 2 && sym[i].mod_bits != 4 && sym[i].mod_bits != 6 && sym[i].mod_bits != 8) ||
                 t.nof_e_bits > kGoldMaxLen))
@@ -1212,6 +1230,7 @@ static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
     }
     if (seg[i].F || seg[i].C > pool->max_cb) continue;  // filler bits unsupported / soft buffer too small: -2
     run[i] = 1;
+    sb_used[t.softbuffer] = 1;
     t.data[t.tbs / 8 + 0] = 0;
     t.data[t.tbs / 8 + 1] = 0;
     t.data[t.tbs / 8 + 2] = 0;
@@ -1276,9 +1295,7 @@ static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
       rm[j].e_len       = jb.E;
       rm[j].work_offset = (uint32_t)off;
       pool->h_off.p[j]  = off;
-      uint8_t& fr = pool->fresh[(size_t)tbs[jb.tb].softbuffer * pool->max_cb + jb.cb];
-      over[j] = fr;
-      fr      = 0;
+      over[j] = pool->fresh[(size_t)tbs[jb.tb].softbuffer * pool->max_cb + jb.cb];  // cleared once the GPU work is done
       pool->h_mode.p[j] = seg[jb.tb].C > 1 ? (uint8_t)CRC_24B : (uint8_t)CRC_24A;
     }
     int rc;
@@ -1338,6 +1355,9 @@ static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
     lap("decode enqueue");
     CU(cudaStreamSynchronize(st));
     lap("wait for the GPU");
+    // only now is the HARQ state committed: an error return above leaves `fresh` set, so the next transmission
+    // stores into the buffer instead of adding to LLRs that were never written
+    for (uint32_t j = 0; j < n_cb; j++) pool->fresh[(size_t)tbs[jobs[j].tb].softbuffer * pool->max_cb + jobs[j].cb] = 0;
 
     // ---- code blocks -> transport blocks.  Like the reference, every block writes its full K/8 bytes at
     // cb*rlen/8, so a block's CRC bytes are overwritten by the next block and the last block's survive. ----
@@ -1728,6 +1748,40 @@ int srslte_b200_sch_decode_tb(srslte_softbuffer_rx_t* sb, uint32_t tbs, uint32_t
   sb->tb_crc = g_pool->tb_crc[0] != 0;
   if (avg_iterations) *avg_iterations = t.avg_iterations;
   return t.ret;
+}
+
+// ---- sch.h:98-107: srslte_dlsch_decode / srslte_dlsch_decode2 (sch.c:502-532) -------------------------------------
+// The unchanged pdsch.c / pmch.c call these with the reference's srslte_sch_t and srslte_pdsch_cfg_t; see
+// include/srslte_b200_compat.h for how the reference's sch.c is built next to this library.
+int srslte_dlsch_decode2(void* qv, srslte_pdsch_cfg_t* cfg, int16_t* e_bits, uint8_t* data, int tb_idx, uint32_t nof_layers)
+{
+  srslte_sch_head_t* q = static_cast<srslte_sch_head_t*>(qv);
+  if (!q || !cfg || tb_idx < 0 || tb_idx > 1) return SRSLTE_ERROR_INVALID_INPUTS;
+  if (q->llr_is_8bit) {
+    fprintf(stderr, "srslte_b200: the experimental 8-bit decoders are not provided (llr_is_8bit is set)\n");
+    return SRSLTE_ERROR;
+  }
+  const uint32_t Nl = nof_layers != cfg->grant.nof_tb ? 2u : 1u;
+  const srslte_ra_tb_t& tb = cfg->grant.tb[tb_idx];
+  static const uint32_t mod_bits[5] = {1, 2, 4, 6, 8};  // srslte_mod_bits_x_symbol (phy_common.c)
+  const uint32_t Qm = tb.mod < 5 ? mod_bits[tb.mod] : 0;
+  {  // the reference computes the segmentation first and reports its failure before anything else (sch.c:517-521)
+    CbSegm seg;
+    if (cbsegm(&seg, (uint32_t)tb.tbs)) {
+      fprintf(stderr, "Error computing Codeword (%d) segmentation for TBS=%d\n", tb_idx, tb.tbs);
+      return SRSLTE_ERROR;
+    }
+  }
+  float avg = q->avg_iterations;  // decode_tb_cb only touches it once it runs (sch.c:313, 412)
+  const int ret = srslte_b200_sch_decode_tb(cfg->softbuffers.rx[tb_idx], (uint32_t)tb.tbs, Qm * Nl, (uint32_t)tb.rv,
+                                            tb.nof_bits, e_bits, data, q->max_iterations, &avg);
+  q->avg_iterations = avg;
+  return ret;
+}
+
+int srslte_dlsch_decode(void* q, srslte_pdsch_cfg_t* cfg, int16_t* e_bits, uint8_t* data)
+{
+  return srslte_dlsch_decode2(q, cfg, e_bits, data, 0, 1);
 }
 
 }  // extern "C"

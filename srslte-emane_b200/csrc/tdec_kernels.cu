@@ -2305,7 +2305,7 @@ __global__ void rm_rx_kernel(const int16_t* __restrict__ e, int16_t* __restrict_
 }  // namespace
 
 // ---- host side -----------------------------------------------------------------------------------
-void upload_crc_tables()
+cudaError_t upload_crc_tables()
 {
   uint32_t tab[2][256];
   const uint32_t polys[2] = {0x1864CFBu, 0x1800063u};
@@ -2315,7 +2315,7 @@ void upload_crc_tables()
       for (int i = 0; i < 8; i++) r = (r & 0x800000u) ? ((r << 1) ^ polys[w]) : (r << 1);
       tab[w][b] = r & 0xFFFFFFu;
     }
-  cudaMemcpyToSymbol(c_crc_tab, tab, sizeof(tab));
+  return cudaMemcpyToSymbol(c_crc_tab, tab, sizeof(tab));
 }
 
 int tdec_blocks_per_warp(int W) { return W == 16 ? 4 : W == 8 ? 8 : 64; }

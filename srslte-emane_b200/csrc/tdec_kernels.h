@@ -181,6 +181,6 @@ struct TxItem {
 cudaError_t tcod_rm_tx_launch(const TxItem* items, uint32_t n_items, const uint8_t* bits, uint8_t* e,
                               const uint16_t* tab_pool, cudaStream_t s);
 
-void upload_crc_tables();  // fills the __constant__ CRC tables (once per process/device)
+cudaError_t upload_crc_tables();  // fills the __constant__ CRC tables (once per context)
 
 }  // namespace b200

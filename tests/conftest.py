@@ -31,6 +31,19 @@ def ctx(pkg):
     c.close()
 
 
+@pytest.fixture(autouse=True)
+def _order_torch_and_library_streams(request):
+    """GPU tests fill device buffers with torch (legacy default stream) and then hand raw pointers to the library,
+    whose own stream is non-blocking: nothing would order the fills before the kernels.  Every GPU test therefore
+    starts with the library on torch's current stream (tests that switch streams do so explicitly after this)."""
+    if request.node.get_closest_marker("gpu") is not None and "ctx" in request.fixturenames:
+        import torch
+        c = request.getfixturevalue("ctx")
+        torch.cuda.synchronize()
+        c.set_stream(torch.cuda.current_stream().cuda_stream)
+    yield
+
+
 @pytest.fixture(scope="session")
 def golden():
     import numpy as np
