@@ -27,6 +27,22 @@ size_t refh_sizeof_softbuffer_rx(void) { return sizeof(srslte_softbuffer_rx_t); 
 size_t refh_sizeof_cbsegm(void) { return sizeof(srslte_cbsegm_t); }
 size_t refh_offsetof_tdec_n_iter(void) { return offsetof(srslte_tdec_t, n_iter); }
 size_t refh_offsetof_sch_decoder(void) { return offsetof(srslte_sch_t, decoder); }
+/* layouts the DL-SCH compat entry points read: [sizeof ra_tb, sizeof pdsch_grant, sizeof pdsch_cfg, offsets of
+ * grant.tb, grant.nof_tb, tb.nof_bits, tb.rv, cfg.softbuffers, sch.max_iterations, sch.avg_iterations, sch.llr_is_8bit] */
+void refh_dlsch_layout(size_t out[11])
+{
+  out[0]  = sizeof(srslte_ra_tb_t);
+  out[1]  = sizeof(srslte_pdsch_grant_t);
+  out[2]  = sizeof(srslte_pdsch_cfg_t);
+  out[3]  = offsetof(srslte_pdsch_cfg_t, grant) + offsetof(srslte_pdsch_grant_t, tb);
+  out[4]  = offsetof(srslte_pdsch_cfg_t, grant) + offsetof(srslte_pdsch_grant_t, nof_tb);
+  out[5]  = offsetof(srslte_ra_tb_t, nof_bits);
+  out[6]  = offsetof(srslte_ra_tb_t, rv);
+  out[7]  = offsetof(srslte_pdsch_cfg_t, softbuffers);
+  out[8]  = offsetof(srslte_sch_t, max_iterations);
+  out[9]  = offsetof(srslte_sch_t, avg_iterations);
+  out[10] = offsetof(srslte_sch_t, llr_is_8bit);
+}
 
 /* ---- decoder handle ---- */
 srslte_tdec_t* refh_tdec_new(uint32_t max_k, int impl /* 0 = AUTO */)

@@ -41,6 +41,39 @@ def test_struct_layouts_match_reference(tmp_path):
     assert got[4] == 24
 
 
+PROBE_DLSCH = r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "srslte_b200_compat.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(srslte_ra_tb_t), sizeof(srslte_pdsch_grant_t),
+         sizeof(srslte_pdsch_cfg_t), offsetof(srslte_pdsch_cfg_t, grant) + offsetof(srslte_pdsch_grant_t, tb),
+         offsetof(srslte_pdsch_cfg_t, grant) + offsetof(srslte_pdsch_grant_t, nof_tb), offsetof(srslte_ra_tb_t, nof_bits),
+         offsetof(srslte_ra_tb_t, rv), offsetof(srslte_pdsch_cfg_t, softbuffers), offsetof(srslte_sch_head_t, max_iterations),
+         offsetof(srslte_sch_head_t, avg_iterations), offsetof(srslte_sch_head_t, llr_is_8bit));
+  return 0;
+}
+"""
+
+
+def test_dlsch_layouts_match_reference(tmp_path):
+    """srslte_pdsch_cfg_t / srslte_ra_tb_t / the head of srslte_sch_t as srslte_dlsch_decode2 reads them"""
+    import ctypes as C
+    src = tmp_path / "probe2.c"
+    src.write_text(PROBE_DLSCH)
+    exe = tmp_path / "probe2"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    R = ol.ref()
+    if R is not None and hasattr(R, "refh_dlsch_layout"):
+        arr = (C.c_size_t * 11)()
+        R.refh_dlsch_layout(arr)
+        want = list(arr)
+    else:   # recorded from the reference's build (oracle/ref_harness.c:refh_dlsch_layout)
+        want = [28, 316, 368, 244, 308, 12, 8, 344, 0, 4, 8]
+    assert got == want
+
+
 def test_compat_symbols_are_exported(pkg):
     L = pkg.lib()
     for name in ("srslte_tdec_init", "srslte_tdec_init_manual", "srslte_tdec_free", "srslte_tdec_force_not_sb",
@@ -48,7 +81,8 @@ def test_compat_symbols_are_exported(pkg):
                  "srslte_tdec_autoimp_get_subblocks_8bit", "srslte_tdec_iteration", "srslte_tdec_run_all",
                  "srslte_tdec_iteration_8bit", "srslte_tdec_run_all_8bit", "srslte_rm_turbo_gentables",
                  "srslte_rm_turbo_free_tables", "srslte_rm_turbo_rx_lut", "srslte_rm_turbo_rx_lut_",
-                 "srslte_rm_turbo_rx_lut_8bit", "srslte_b200_sch_decode_tb"):
+                 "srslte_rm_turbo_rx_lut_8bit", "srslte_b200_sch_decode_tb", "srslte_dlsch_decode",
+                 "srslte_dlsch_decode2"):
         assert hasattr(L, name), name
     # host-only entry points work without a GPU
     assert [L.srslte_tdec_autoimp_get_subblocks(k) for k in (40, 408, 816, 6144)] == [0, 8, 16, 16]
