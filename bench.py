@@ -33,8 +33,12 @@ NOF_ITERATIONS = 4          # srsLTE HALF iterations
 EBNO_HARNESS = 1.5          # turbodecoder_test "-e 1.5" (sigma = 1.457 on +-1; never converges, F7)
 LLR_SCALE = 100.0
 IN_LEN = 3 * K + 12
-NCU_DRAM_BYTES_PER_BLOCK = 383.9e3        # profiles/r01i_ncu_raw.csv: (18.73 + 6.43) GB / 65536 blocks (r01d: 421 KB)
-INT_PEAK_THREAD_INSTR_PER_CLK_SM = 64.0   # measured: profiles/r01_int_peak*.txt (VIADD.16x2 / VIMNMX.S16x2)
+# DRAM bytes of the decode kernel per code block, from the committed ncu capture of this workload (profiles/r02*_summary.txt:
+# dram__bytes_read.sum + dram__bytes_write.sum of one 65 536-block launch / 65 536); NOT measured by bench.py itself
+NCU_DRAM_BYTES_PER_BLOCK = 246.5e3
+NCU_DRAM_SOURCE = "profiles/r02e_summary.txt (ncu --set full, 12.88 GB read + 3.28 GB written per 65536-block launch)"
+INT_PEAK_THREAD_INSTR_PER_CLK_SM = 64.0   # measured: profiles/r01_int_peak*.txt (VIADD.16x2 / VIMNMX.S16x2), ONE pipe
+TWO_PIPE_THREAD_INSTR_PER_CLK_SM = 117.6  # measured: profiles/r01_pipe_mix.txt, "vaddmax + vadd" (both pipes busy)
 
 
 def int_ops_per_block(k=K, w=16, nit=NOF_ITERATIONS):
@@ -247,6 +251,8 @@ def main():
     ap.add_argument("--blocks", type=int, default=65536, help="code blocks per GPU per step")
     ap.add_argument("--e2e-blocks", type=int, default=65536, help="code blocks per GPU for the host-pointer leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE.json configurations (key configs)")
+    ap.add_argument("--quick-configs", action="store_true", help="smaller batches for the configs key (development)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -281,7 +287,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
-        dist_mod.init_process_group("nccl", device_id=dev)
+        # only a barrier and one max-reduce of the timing go through it: gloo (the data path has no collective)
+        dist_mod.init_process_group("gloo")
         dist = dist_mod
 
     def barrier():
@@ -330,7 +337,7 @@ def main():
     ctx.enable_timing(False)
     clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total], dtype=torch.float64)
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
@@ -353,10 +360,15 @@ def main():
     for _ in range(e2e_steps):
         got, got_nit, _ = ctx.tdec_batch_host(pin_in.array, K, NOF_ITERATIONS, out=pin_out.array)
     e2e_dt = (time.perf_counter() - t0) / e2e_steps
-    t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    t = torch.tensor([e2e_dt], dtype=torch.float64)
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * ne * K / float(t.item()) / 1e9
+    e2e_ranks = [e2e_dt * 1e3]
+    if dist:
+        allt = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(allt, torch.tensor([e2e_dt * 1e3], dtype=torch.float64))
+        e2e_ranks = [float(x.item()) for x in allt]
     same = bool(np.array_equal(pin_out.array[:64], out[:64].cpu().numpy()))
 
     if rank != 0:
@@ -379,6 +391,7 @@ def main():
     ops_launch = n * int_ops_per_block()
     achieved_tops = ops_launch / (dec_ms_per_launch * 1e-3) / 1e12
     peak_tops = INT_PEAK_THREAD_INSTR_PER_CLK_SM * 2 * sms * sm_max * 1e6 / 1e12      # int16 lane-ops/s at max clock
+    two_pipe_tops = TWO_PIPE_THREAD_INSTR_PER_CLK_SM * 2 * sms * sm_max * 1e6 / 1e12
     bytes_launch = n * algo_bytes_per_block()
     hbm_achieved = bytes_launch / (dec_ms_per_launch * 1e-3) / 1e9
 
@@ -390,7 +403,8 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Gbit/s", "h2d_bytes_per_step": ne * IN_LEN * 2,
                 "d2h_bytes_per_step": ne * (K // 8 + 2), "blocks_per_gpu": ne, "ms_per_step": e2e_dt * 1e3,
-                "matches_device_path": same, "host_affinity": affinity or "inherited"},
+                "matches_device_path": same, "host_affinity": affinity or "inherited",
+                "ms_per_step_per_rank": e2e_ranks},
         "gpu_launches": launches,
         "roofline": {
             "bound": "int_alu", "kernel": "tdec_win_kernel<16>", "achieved": achieved_tops, "peak": peak_tops,
@@ -399,19 +413,21 @@ def main():
             "peak_source": f"measured {INT_PEAK_THREAD_INSTR_PER_CLK_SM:g} packed-int16x2 thread-instr/clk/SM "
                            f"(tools/int_peak.cu, profiles/r01_int_peak*.txt) x 2 lanes x {sms} SMs x {sm_max:g} MHz",
             "sm_mhz_during_run": sm_mhz,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture in
-            # profiles/ (27.59 GB for the 65536-block launch = 421.0 KB per block), scaled to this launch
-            "traffic": NCU_DRAM_BYTES_PER_BLOCK * n,
-            "two_pipe_peak": 2 * peak_tops,
-            "note": "peak = ONE integer pipe (64 packed thread-instr/clk/SM, what every single packed op reaches); "
-                    "VIADD.16x2 (FMA pipe) and VIMNMX/VIADDMNMX (ALU pipe) can overlap up to ~1.9x that "
-                    "(profiles/r01_pipe_mix.txt), and a fused add-max counts as two algorithmic ops",
+            # NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed
+            # ncu --set full capture, per block, scaled to this launch
+            "traffic": NCU_DRAM_BYTES_PER_BLOCK * n, "traffic_from_profile": NCU_DRAM_SOURCE,
+            "two_pipe_peak": two_pipe_tops, "frac_two_pipe": achieved_tops / two_pipe_tops,
+            "note": "frac: against ONE integer pipe (64 packed thread-instr/clk/SM, what every single packed op "
+                    "reaches); frac_two_pipe: against the measured rate of the kernel's own instruction mix with both "
+                    "pipes busy (117.6 thread-instr/clk/SM for VIADDMNMX + VIADD.16x2, profiles/r01_pipe_mix.txt); a "
+                    "fused add-max counts as two algorithmic ops",
         },
         "roofline_hbm": {
             "bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
             "bytes_per_block": algo_bytes_per_block(), "peak_source": f"MEASURED_PEAKS.json ({hbm_src})",
-            "traffic": NCU_DRAM_BYTES_PER_BLOCK * n,
+            "traffic": NCU_DRAM_BYTES_PER_BLOCK * n, "traffic_from_profile": NCU_DRAM_SOURCE,
             "traffic_gbs": NCU_DRAM_BYTES_PER_BLOCK * n / (dec_ms_per_launch * 1e-3) / 1e9,
+            "traffic_frac_of_peak": NCU_DRAM_BYTES_PER_BLOCK * n / (dec_ms_per_launch * 1e-3) / 1e9 / hbm_peak,
         },
         "kernel_share": {"decode_ms_per_step": dec_ms / args.steps, "layout_ms_per_step": lay_ms / args.steps,
                          "decode_launches": dec_n, "layout_launches": lay_n},
@@ -433,6 +449,13 @@ def main():
                                 "sample": f"{r['passes']} passes over {sample} of the same K={K} blocks, "
                                           f"nof_iterations={NOF_ITERATIONS}, {threads} pthreads with one srslte_tdec_t "
                                           f"each (created before the timed region), {r['wall_s']:.2f} s of decode loops"}
+    if not args.no_configs and world == 1:
+        try:
+            import bench_configs
+            ctx.set_stream(stream.cuda_stream)
+            line["configs"] = bench_configs.run_configs(pkg, ctx, torch, dev, stream, quick=args.quick_configs)
+        except Exception as e:  # the headline line must not be lost to a side measurement
+            line["configs"] = {"error": f"{type(e).__name__}: {e}"}
     print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()

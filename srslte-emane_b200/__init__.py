@@ -397,3 +397,35 @@ class HarqPool:
             self.close()
         except Exception:
             pass
+
+
+class CompatTdec:
+    """The reference's own entry points (srslte_tdec_init / force_not_sb / run_all / free, turbodecoder.h:97-135) on a
+    raw 18 264-byte srslte_tdec_t, as turbodecoder_test.c drives them: natural-order LLRs, one block per call."""
+
+    def __init__(self, max_long_cb=6144):
+        self.L = lib()
+        i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
+        u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+        self.L.srslte_tdec_init.argtypes = [C.c_void_p, C.c_uint32]
+        self.L.srslte_tdec_free.argtypes = [C.c_void_p]
+        self.L.srslte_tdec_free.restype = None
+        self.L.srslte_tdec_force_not_sb.argtypes = [C.c_void_p]
+        self.L.srslte_tdec_force_not_sb.restype = None
+        self.L.srslte_tdec_run_all.argtypes = [C.c_void_p, i16p, u8p, C.c_uint32, C.c_uint32]
+        self.h = C.create_string_buffer(18264)
+        if self.L.srslte_tdec_init(self.h, max_long_cb) != 0:
+            raise RuntimeError("srslte_tdec_init failed (no CUDA device? this library has no CPU path)")
+        self.L.srslte_tdec_force_not_sb(self.h)
+
+    def run_all(self, llr1, nof_iterations, K):
+        out = np.zeros(K // 8, np.uint8)
+        rc = self.L.srslte_tdec_run_all(self.h, np.ascontiguousarray(llr1, np.int16).copy(), out, nof_iterations, K)
+        if rc != 0:
+            raise RuntimeError(f"srslte_tdec_run_all returned {rc}")
+        return out
+
+    def close(self):
+        if self.h is not None:
+            self.L.srslte_tdec_free(self.h)
+            self.h = None

@@ -1207,6 +1207,7 @@ static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
   std::vector<size_t>   e_base(n_tb, 0);
   std::vector<CbJob>    jobs;
   std::vector<uint32_t> Ks;
+  std::vector<std::pair<uint32_t, uint32_t>> old_blocks;  // (tb, cb) decoded in an earlier transmission
   std::vector<uint8_t>  sb_used(pool->n_sb, 0);  // a soft buffer may appear once per batch (its blocks are combined
                                                  // and its CRC / saved-data state updated by one TB only)
   size_t                e_total = 0;
@@ -1241,8 +1242,8 @@ static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
     for (uint32_t cb = 0; cb < s.C; cb++) {
       const uint32_t K    = cb < s.C1 ? s.K1 : s.K2;
       const uint32_t rlen = s.C == 1 ? K : K - 24;
-      if (crc[cb]) {  // decoded in an earlier transmission: copy what was saved then
-        std::memcpy(&t.data[cb * rlen / 8], &pool->saved[((size_t)t.softbuffer * pool->max_cb + cb) * 768], rlen / 8);
+      if (crc[cb]) {  // decoded in an earlier transmission: what was saved then is copied once the new blocks are in
+        old_blocks.push_back({i, cb});
         continue;
       }
       const uint32_t Gp = t.nof_e_bits / t.qm, gamma = Gp % s.C, n_e = t.qm * (Gp / s.C);
@@ -1371,6 +1372,15 @@ static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
     }
   }
 
+  // The reference walks the blocks of a TB in order: a newly decoded block writes K/8 bytes, i.e. its 3 CRC bytes land
+  // on the first bytes of the next block, which then overwrites them -- also when that next block was decoded in an
+  // earlier transmission and is only copied (sch.c:389-394).  So the saved blocks go in AFTER the new ones.
+  for (const auto& ob : old_blocks) {
+    srslte_b200_tb_t& t = tbs[ob.first];
+    const CbSegm&     s = seg[ob.first];
+    const uint32_t    K = ob.second < s.C1 ? s.K1 : s.K2, rlen = s.C == 1 ? K : K - 24;
+    std::memcpy(&t.data[ob.second * rlen / 8], &pool->saved[((size_t)t.softbuffer * pool->max_cb + ob.second) * 768], rlen / 8);
+  }
   lap("blocks -> TBs");
   // ---- per-TB bookkeeping (sch.c:391-412, 470-488) ----
   std::vector<float> total_it(n_tb, 0.f);
