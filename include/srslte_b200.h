@@ -67,6 +67,9 @@ SRSLTE_B200_API int srslte_b200_ctx_kernel_time(srslte_b200_ctx_t* ctx, int kind
  * iteration) pairs have taken the exact re-run so far (synchronizes the device).                 */
 SRSLTE_B200_API int srslte_b200_ctx_set_exact(srslte_b200_ctx_t* ctx, int force_exact);
 SRSLTE_B200_API int srslte_b200_ctx_fallback_count(srslte_b200_ctx_t* ctx, uint64_t* count);
+/* (warp, half iteration) pairs of the window decoders so far in the pure / static / tracked / exact variant
+ * (synchronizes the device)                                                        */
+SRSLTE_B200_API int srslte_b200_ctx_tier_counts(srslte_b200_ctx_t* ctx, uint64_t counts[4]);
 
 /* Pinned host memory for the *_host entries (plain cudaHostAlloc; any host pointer is accepted,
  * pinned ones are copied without staging).                                                      */

@@ -78,7 +78,7 @@ EXPORTS = [
     "srslte_b200_ctx_create", "srslte_b200_ctx_destroy", "srslte_b200_ctx_set_stream",
     "srslte_b200_ctx_synchronize", "srslte_b200_last_error", "srslte_b200_launch_count",
     "srslte_b200_ctx_enable_timing", "srslte_b200_ctx_kernel_time", "srslte_b200_ctx_set_exact",
-    "srslte_b200_ctx_fallback_count", "srslte_b200_host_alloc", "srslte_b200_host_free", "srslte_b200_cb_index", "srslte_b200_cb_size",
+    "srslte_b200_ctx_fallback_count", "srslte_b200_ctx_tier_counts", "srslte_b200_host_alloc", "srslte_b200_host_free", "srslte_b200_cb_index", "srslte_b200_cb_size",
     "srslte_b200_nof_windows", "srslte_b200_working_len", "srslte_b200_rm_rx_table",
     "srslte_b200_tdec_batch_dev", "srslte_b200_tdec_batch_host", "srslte_b200_rm_rx_batch_dev",
     "srslte_b200_demod_descramble_dev", "srslte_b200_demod_rm_rx_batch_dev", "srslte_b200_tcod_rm_tx_batch_dev",
@@ -113,6 +113,7 @@ def lib():
     L.srslte_b200_ctx_kernel_time.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u32)]
     L.srslte_b200_ctx_set_exact.argtypes = [vp, i32]
     L.srslte_b200_ctx_fallback_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.srslte_b200_ctx_tier_counts.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.srslte_b200_host_alloc.argtypes = [C.c_size_t]
     L.srslte_b200_host_alloc.restype = vp
     L.srslte_b200_host_free.argtypes = [vp]
@@ -231,6 +232,13 @@ class Context:
     def set_exact(self, on=True):
         """force the exact saturating variant of the window decoders (the fast variant is the default)."""
         self._check(self._L.srslte_b200_ctx_set_exact(self._h, int(on)), "set_exact")
+
+    @property
+    def tier_counts(self):
+        """(warp, half iteration) pairs so far in the pure / static / tracked / exact variant"""
+        v = (C.c_uint64 * 4)()
+        self._check(self._L.srslte_b200_ctx_tier_counts(self._h, v), "tier_counts")
+        return [int(x) for x in v]
 
     @property
     def fallback_count(self):

@@ -93,7 +93,7 @@ struct srslte_b200_ctx {
   cudaStream_t h2d_stream  = nullptr;
   cudaStream_t d2h_stream  = nullptr;
   Regime       regime[3];
-  DevBuf<uint32_t> counters;           // 3 work counters + 1 fallback counter
+  DevBuf<uint32_t> counters;           // 3 work counters + 1 fallback counter + 4 tier counters
   bool         force_exact = false;
   // schedule cache
   DevBuf<uint32_t> d_order;
@@ -413,8 +413,8 @@ int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint
   const int16_t* win    = ctx->d_work.p;
   const uint32_t stride = work_len;
   if (ctx->counters.cap == 0) {
-    CU(ctx->counters.reserve(4));
-    CU(cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(uint32_t), st));
+    CU(ctx->counters.reserve(8));
+    CU(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(uint32_t), st));
     CU(cudaStreamSynchronize(st));  // once per context: later calls may come on other streams
   }
   if (b->crc_mode != SRSLTE_B200_CRC_NONE || d_crc_mode_cb) {
@@ -475,10 +475,11 @@ int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint
     a.ws_chk     = reinterpret_cast<uint32_t*>(R.ws_chk.p);
     a.crc_pos     = ctx->crc_pos_dev.p;
     a.crc_pos_off = ctx->crc_pos_off_dev.p;
-    static const uint32_t skip_tiers = [] {  // measurement probe: SRSLTE_B200_SKIP_TIERS=1 (pure), 2 (static), 3 (both)
-      const char* e = getenv("SRSLTE_B200_SKIP_TIERS");
-      const long  v = e ? atol(e) : 0;
-      return (uint32_t)(((v & 1) ? 2u : 0u) | ((v & 2) ? 4u : 0u));
+    static const uint32_t skip_tiers = [] {  // measurement probe: SRSLTE_B200_SKIP_TIERS=1 (pure), 2 (static), 3 (both);
+      const char* e = getenv("SRSLTE_B200_SKIP_TIERS");  // SRSLTE_B200_FORCE_BITS: raw bits (8 = general path only,
+      const long  v = e ? atol(e) : 0;                   // 16 = kernel without the tracked tier of the main path)
+      const char* f = getenv("SRSLTE_B200_FORCE_BITS");
+      return (uint32_t)(((v & 1) ? 2u : 0u) | ((v & 2) ? 4u : 0u) | (f ? (uint32_t)atol(f) : 0u));
     }();
     a.force_exact = (ctx->force_exact ? 1u : 0u) | skip_tiers;
     a.stats      = ctx->counters.p + 3;
@@ -649,6 +650,19 @@ int srslte_b200_ctx_fallback_count(srslte_b200_ctx_t* ctx, uint64_t* count)
   uint32_t v = 0;
   CU(cudaMemcpy(&v, ctx->counters.p + 3, sizeof(v), cudaMemcpyDeviceToHost));
   *count = v;
+  return SRSLTE_B200_SUCCESS;
+}
+
+int srslte_b200_ctx_tier_counts(srslte_b200_ctx_t* ctx, uint64_t counts[4])
+{
+  if (!ctx || !counts) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  for (int i = 0; i < 4; i++) counts[i] = 0;
+  if (ctx->counters.cap == 0) return SRSLTE_B200_SUCCESS;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaDeviceSynchronize());
+  uint32_t v[4] = {0, 0, 0, 0};
+  CU(cudaMemcpy(v, ctx->counters.p + 4, sizeof(v), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 4; i++) counts[i] = v[i];
   return SRSLTE_B200_SUCCESS;
 }
 

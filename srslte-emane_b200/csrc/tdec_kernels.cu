@@ -101,6 +101,15 @@ __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { r
 __device__ __forceinline__ uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
 // max(a + b, c) with a wrapping add: only used where a + b is proven not to overflow
 __device__ __forceinline__ uint32_t addmax2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
+// prmt with the sign-replication bit of the selector nibbles set: every result byte is 0xFF / 0x00 by the top bit of the
+// selected byte (0x9999: byte 1, the sign of the low half; 0xBBBB: byte 3).  (__byte_perm masks that selector bit off.)
+template <uint32_t SEL>
+__device__ __forceinline__ uint32_t sign_mask(uint32_t v)
+{
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %1, %2;" : "=r"(r) : "r"(v), "n"(SEL));
+  return r;
+}
 __device__ __forceinline__ uint32_t sra1_2(uint32_t v) { return ((v >> 1) & 0x7FFF7FFFu) | (v & 0x80008000u); }
 
 // extremes of the values a thread has seen, per int16 lane
@@ -1190,10 +1199,11 @@ __device__ __forceinline__ void fwd_group(const WinCtx<W>& c, const uint32_t* st
       d[r] = alpha_out2<W, TRACK>(a, B[r], x, pa[r], sa[r], aa[r], rm);
     }
     if (HARD) {
-      // sign bit of -(max(v, -1)) is set exactly when v > 0 (no overflow: max(v,-1) >= -1)
-      const uint32_t m  = wneg2(max2(wadd2(d[r], aa[r]), 0xFFFFFFFFu));
+      // max(v, -1) + 32767 wraps to a negative number exactly when v > 0; a byte permute with sign replication turns
+      // the sign bit of each half into a 32-bit mask (7 instructions per row instead of 10)
+      const uint32_t m  = wadd2(max2(wadd2(d[r], aa[r]), 0xFFFFFFFFu), 0x7FFF7FFFu);
       const uint2    rr = *reinterpret_cast<const uint2*>(c.R + (k0 + r) * W);
-      crc ^= (rr.x & (uint32_t)((int32_t)(m << 16) >> 31)) ^ (rr.y & (uint32_t)((int32_t)m >> 31));
+      crc ^= (rr.x & sign_mask<0x9999>(m)) ^ (rr.y & sign_mask<0xBBBB>(m));
     }
     uint32_t o_lo, o_hi;  // (inline asm: the compiler would merge the halves into one load and take them apart again)
     asm("ld.shared.u16 %0, [%1];" : "=r"(o_lo) : "r"(e16 + 4 * r));
@@ -1590,17 +1600,17 @@ __device__ __noinline__ HalfResult half_general(const WinCtx<W> c, bool dec2, in
   return r;
 }
 
-// The tracked tier (NORM = 2, bookkeeping) through the main path is written and bit-exact, but NOT instantiated by
-// default: with it in the kernel -- inlined or out of line -- ptxas spills eight registers of the plain tier's forward
-// loop right behind the loads that fill them (5.05 instead of 4.63 ms per 65 536 blocks).  The tracked tier runs
-// through the general path instead.
-#ifdef B200_TRK2
+// The tracked tier (NORM = 2, bookkeeping) through the main path.  With it in the kernel -- inlined or out of line --
+// ptxas spills eight registers of the plain tier's forward loop right behind the loads that fill them (5.05 instead
+// of 4.63 ms per 65 536 blocks), so the window kernels exist twice: TRK2 = false without it (the tracked tier then
+// runs through the general path; launched when no block checks a CRC, i.e. srslte_tdec_run_all batches, whose blocks
+// stay in the plain tiers unless they converge) and TRK2 = true with it (launched for the CRC modes, where blocks
+// converge, their extrinsic values grow and the tracked tier is the common case).
 template <int W>
 __device__ __noinline__ HalfResult half_tracked2(const WinCtx<W> c, bool dec2, int G, bool hard)
 {
   return half_fast2<W, 2, true>(c, dec2, G, true, hard);
 }
-#endif
 
 // QPP of this K as a scatter table, computed from (f1, f2) by the whole CTA:
 //   pi(d*L + k) = pi(k) + L * d * (f1 + f2*d*L + 2*f2*k)  (mod K = W*L), so with pi(k) = w0*L + r every window
@@ -1738,7 +1748,7 @@ __device__ __forceinline__ uint32_t group_max(uint32_t v)
 // One CTA per SM.  The CTA takes kWarps consecutive work items at a time; the host pads the item list so that
 // they all have the same K (items with count 0 are fillers): the QPP tables are built once per CTA round, and the
 // warps run the same phase of the same code at the same time (one copy of the hot loops in the instruction cache).
-template <int W>
+template <int W, bool TRK2>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const TdecLaunch a)
 {
   constexpr int WH  = W / 2;
@@ -1752,6 +1762,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
   const int      grp = lane / WH, t = lane % WH;
   const uint32_t slot = blockIdx.x * kWarps + warp;
   uint32_t       fallbacks = 0;
+  uint32_t       tiers[4] = {0, 0, 0, 0};  // half iterations of this warp in the pure / static / tracked / exact variant
   Pipe           pipe;
   pipe.par = 0;
   if (lane == 0) {
@@ -1849,11 +1860,9 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
         if (v2 && (pure || stat)) {
           r       = half_fast2<W, 4, false>(c, dec2, G, stat, any_crc);
           fast_ok = true;
-#ifdef B200_TRK2  // development probe: the tracked tier through the main path (see half_tracked2)
-        } else if (v2 && trk) {
-          r       = half_tracked2<W>(c, dec2, G, any_crc);
+        } else if (TRK2 && v2 && trk) {
+          if constexpr (TRK2) r = half_tracked2<W>(c, dec2, G, any_crc);
           fast_ok = __all_sync(0xFFFFFFFFu, r.proven || done);
-#endif
 #ifndef B200_V2ONLY
         } else if (pure || stat || trk) {
           r       = half_general<W>(c, dec2, G, pure ? 0 : stat ? 1 : 2, any_crc, &pipe);
@@ -1863,6 +1872,9 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
         if (!fast_ok) {
           r = half_iteration_exact<W>(c, dec2);
           fallbacks++;
+          tiers[3]++;
+        } else {
+          tiers[pure ? 0 : stat ? 1 : 2]++;
         }
         const int dm = (int)group_max<WH>(r.dmax);
         if (dec2) amax = dm; else emax = dm;
@@ -1894,6 +1906,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
     __syncthreads();  // every warp is done with the tables (and with s_item)
   }
   if (lane == 0 && fallbacks && a.stats) atomicAdd(a.stats, fallbacks);
+  if (lane < 4 && a.stats && tiers[lane]) atomicAdd(a.stats + 1 + lane, tiers[lane]);
 }
 
 // ---- generic decoder (K <= 400): one thread per PAIR of code blocks, wrapping arithmetic ------------------------
@@ -2359,11 +2372,13 @@ cudaError_t tdec_geometry(int W, int device, TdecGeometry* g)
   g->smem = warps_per_block * kWarpSmem + 2 * kStabDir * sizeof(uint32_t) + warps_per_block * kStages * sizeof(uint64_t);
   int per_sm = 0;
   if (W == 16) {
-    e = cudaFuncSetAttribute(tdec_win_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tdec_win_kernel<16>, kThreads, g->smem);
+    e = cudaFuncSetAttribute(tdec_win_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tdec_win_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tdec_win_kernel<16, false>, kThreads, g->smem);
   } else {
-    e = cudaFuncSetAttribute(tdec_win_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tdec_win_kernel<8>, kThreads, g->smem);
+    e = cudaFuncSetAttribute(tdec_win_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tdec_win_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tdec_win_kernel<8, false>, kThreads, g->smem);
   }
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
@@ -2385,10 +2400,16 @@ cudaError_t tdec_launch(int W, const TdecGeometry& g, const TdecLaunch& a, cudaS
   if (e != cudaSuccess) return e;
   const int want   = W ? (int)a.n_rounds : (int)((a.n_items + (kGenThreads / 32) - 1) / (kGenThreads / 32));
   const int blocks = want < g.blocks ? want : g.blocks;
-  if (W == 16)
-    tdec_win_kernel<16><<<blocks, g.threads, g.smem, s>>>(a);
+  // CRC modes: blocks converge and their growing extrinsic values make the tracked tier the common case
+  const bool trk2 = (a.force_exact & 32u) != 0;  // measured: not worth the slower plain tiers, see half_tracked2
+  if (W == 16 && trk2)
+    tdec_win_kernel<16, true><<<blocks, g.threads, g.smem, s>>>(a);
+  else if (W == 16)
+    tdec_win_kernel<16, false><<<blocks, g.threads, g.smem, s>>>(a);
+  else if (W == 8 && trk2)
+    tdec_win_kernel<8, true><<<blocks, g.threads, g.smem, s>>>(a);
   else if (W == 8)
-    tdec_win_kernel<8><<<blocks, g.threads, g.smem, s>>>(a);
+    tdec_win_kernel<8, false><<<blocks, g.threads, g.smem, s>>>(a);
   else
     tdec_gen_kernel<<<blocks, g.threads, 0, s>>>(a);
   return cudaGetLastError();

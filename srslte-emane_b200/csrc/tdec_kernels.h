@@ -45,7 +45,8 @@ struct TdecLaunch {
   const uint32_t* crc_pos;     // window kernels, CRC modes: per-bit CRC contributions (lte_tables.h:crc_pos_tables)
   const uint32_t* crc_pos_off; // [188] offset of each K's tables in crc_pos (uint32 units)
   uint32_t        force_exact; // 1: always run the exact saturating variant (tests)
-  uint32_t*       stats;       // device counter: half iterations (per warp) that fell back to the exact variant
+  uint32_t*       stats;       // device counters: [0] half iterations (per warp) that fell back to the exact variant,
+                               // [1..4] half iterations (per warp) run in the pure / static / tracked / exact variant
 };
 
 struct TdecGeometry {
