@@ -35,8 +35,8 @@ LLR_SCALE = 100.0
 IN_LEN = 3 * K + 12
 # DRAM bytes of the decode kernel per code block, from the committed ncu capture of this workload (profiles/r02*_summary.txt:
 # dram__bytes_read.sum + dram__bytes_write.sum of one 65 536-block launch / 65 536); NOT measured by bench.py itself
-NCU_DRAM_BYTES_PER_BLOCK = 246.5e3
-NCU_DRAM_SOURCE = "profiles/r02e_summary.txt (ncu --set full, 12.88 GB read + 3.28 GB written per 65536-block launch)"
+NCU_DRAM_BYTES_PER_BLOCK = 250.0e3
+NCU_DRAM_SOURCE = "profiles/r02g_summary.txt (ncu --set full: 12.99 GB read + 3.40 GB written per 65536-block launch)"
 INT_PEAK_THREAD_INSTR_PER_CLK_SM = 64.0   # measured: profiles/r01_int_peak*.txt (VIADD.16x2 / VIMNMX.S16x2), ONE pipe
 TWO_PIPE_THREAD_INSTR_PER_CLK_SM = 117.6  # measured: profiles/r01_pipe_mix.txt, "vaddmax + vadd" (both pipes busy)
 
@@ -370,6 +370,14 @@ def main():
         dist.all_gather(allt, torch.tensor([e2e_dt * 1e3], dtype=torch.float64))
         e2e_ranks = [float(x.item()) for x in allt]
     same = bool(np.array_equal(pin_out.array[:64], out[:64].cpu().numpy()))
+    # the box's host-to-device ceiling in the same run: every rank copies the same pinned input at the same time, no kernels
+    barrier()
+    h2d_gbs = ctx.h2d_probe(pin_in.array.ctypes.data, ne * IN_LEN * 2, reps=3)
+    h2d_ranks = [h2d_gbs]
+    if dist:
+        allg = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(allg, torch.tensor([h2d_gbs], dtype=torch.float64))
+        h2d_ranks = [float(x.item()) for x in allg]
 
     if rank != 0:
         if dist:
@@ -404,7 +412,11 @@ def main():
         "e2e": {"value": e2e_value, "unit": "Gbit/s", "h2d_bytes_per_step": ne * IN_LEN * 2,
                 "d2h_bytes_per_step": ne * (K // 8 + 2), "blocks_per_gpu": ne, "ms_per_step": e2e_dt * 1e3,
                 "matches_device_path": same, "host_affinity": affinity or "inherited",
-                "ms_per_step_per_rank": e2e_ranks},
+                "ms_per_step_per_rank": e2e_ranks,
+                # H2D copies alone, all ranks at once (srslte_b200_h2d_probe): what the PCIe side of the box gives
+                "h2d_ceiling_gbs_per_rank": h2d_ranks,
+                "h2d_gbs_per_rank_in_e2e": [ne * IN_LEN * 2 / (ms * 1e-3) / 1e9 for ms in e2e_ranks],
+                "e2e_frac_of_h2d_ceiling": (ne * IN_LEN * 2 / (max(e2e_ranks) * 1e-3) / 1e9) / max(min(h2d_ranks), 1e-9)},
         "gpu_launches": launches,
         "roofline": {
             "bound": "int_alu", "kernel": "tdec_win_kernel<16>", "achieved": achieved_tops, "peak": peak_tops,

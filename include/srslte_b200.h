@@ -66,6 +66,10 @@ SRSLTE_B200_API int srslte_b200_ctx_kernel_time(srslte_b200_ctx_t* ctx, int kind
  * _set_exact(1) forces the exact variant (tests); _fallback_count returns how many (warp, half
  * iteration) pairs have taken the exact re-run so far (synchronizes the device).                 */
 SRSLTE_B200_API int srslte_b200_ctx_set_exact(srslte_b200_ctx_t* ctx, int force_exact);
+/* Tests and measurements: which of the (bit-identical) variants of the window decoders may run.  Bit 1 / 2: skip the
+ * pure / static tier; 3: general path only; 5: the kernels with the tracked tier of the main path; 6: CRC modes through
+ * the round-based kernel instead of the block-granular early-termination kernel.  0 = default.  Results never differ. */
+SRSLTE_B200_API int srslte_b200_ctx_set_variant_bits(srslte_b200_ctx_t* ctx, uint32_t bits);
 SRSLTE_B200_API int srslte_b200_ctx_fallback_count(srslte_b200_ctx_t* ctx, uint64_t* count);
 /* (warp, half iteration) pairs of the window decoders so far in the pure / static / tracked / exact variant
  * (synchronizes the device)                                                        */
@@ -123,6 +127,27 @@ SRSLTE_B200_API int srslte_b200_tdec_batch_dev(srslte_b200_ctx_t* ctx, const srs
 SRSLTE_B200_API int srslte_b200_tdec_batch_host(srslte_b200_ctx_t* ctx, const srslte_b200_tdec_batch_t* batch,
                                                 const int16_t* llr, uint8_t* out, uint8_t* n_iter,
                                                 uint8_t* crc_ok);
+
+/* ---- several GPUs of one box from ONE process ------------------------------------------------------
+ * Code blocks are independent, so a batch is cut into contiguous shards (block i -> device floor(i * n_devices / n_cb),
+ * like sharding.py) and every shard runs through srslte_b200_tdec_batch_host on its own device from its own host
+ * thread (bound to the CPUs next to that GPU): no inter-device traffic, no collective.  The reference's unit of
+ * concurrency is one worker thread per srslte_sch_t (srsenb/src/phy/sf_worker.cc:579-650); a group is what such
+ * workers -- or one caller with one large batch -- share.  devices == NULL: devices 0 .. n_devices-1.            */
+typedef struct srslte_b200_group srslte_b200_group_t;
+SRSLTE_B200_API int  srslte_b200_group_create(srslte_b200_group_t** group, const int* devices, uint32_t n_devices);
+SRSLTE_B200_API void srslte_b200_group_destroy(srslte_b200_group_t* group);
+SRSLTE_B200_API uint32_t srslte_b200_group_size(const srslte_b200_group_t* group);
+SRSLTE_B200_API srslte_b200_ctx_t* srslte_b200_group_ctx(srslte_b200_group_t* group, uint32_t index);
+SRSLTE_B200_API int  srslte_b200_group_tdec_batch_host(srslte_b200_group_t* group, const srslte_b200_tdec_batch_t* batch,
+                                                       const int16_t* llr, uint8_t* out, uint8_t* n_iter, uint8_t* crc_ok);
+/* Host-to-device ceiling of the box: every device of the group copies `bytes_per_device` from host + i * bytes_per_device
+ * at the same time, `reps` times, no kernels; gbs_per_device[i] = GB/s seen by device i while all of them copy.   */
+SRSLTE_B200_API int  srslte_b200_group_h2d_probe(srslte_b200_group_t* group, const void* host, size_t bytes_per_device,
+                                                 uint32_t reps, double* gbs_per_device);
+/* the same for one context (bench.py under torchrun: every rank probes after a barrier)                            */
+SRSLTE_B200_API int  srslte_b200_h2d_probe(srslte_b200_ctx_t* ctx, const void* host, size_t bytes, uint32_t reps, double* gbs);
+
 
 /* ---- batched rate de-matching -------------------------------------------------------------- */
 typedef struct {

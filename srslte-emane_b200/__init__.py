@@ -77,7 +77,7 @@ class TbSymDesc(C.Structure):
 EXPORTS = [
     "srslte_b200_ctx_create", "srslte_b200_ctx_destroy", "srslte_b200_ctx_set_stream",
     "srslte_b200_ctx_synchronize", "srslte_b200_last_error", "srslte_b200_launch_count",
-    "srslte_b200_ctx_enable_timing", "srslte_b200_ctx_kernel_time", "srslte_b200_ctx_set_exact",
+    "srslte_b200_ctx_enable_timing", "srslte_b200_ctx_kernel_time", "srslte_b200_ctx_set_exact", "srslte_b200_ctx_set_variant_bits",
     "srslte_b200_ctx_fallback_count", "srslte_b200_ctx_tier_counts", "srslte_b200_host_alloc", "srslte_b200_host_free", "srslte_b200_cb_index", "srslte_b200_cb_size",
     "srslte_b200_nof_windows", "srslte_b200_working_len", "srslte_b200_rm_rx_table",
     "srslte_b200_tdec_batch_dev", "srslte_b200_tdec_batch_host", "srslte_b200_rm_rx_batch_dev",
@@ -85,6 +85,8 @@ EXPORTS = [
     "srslte_b200_harq_pool_create", "srslte_b200_harq_pool_destroy", "srslte_b200_harq_reset",
     "srslte_b200_harq_cb_crc", "srslte_b200_decode_tb_batch", "srslte_b200_decode_tb_sym_batch",
     "srslte_b200_uci_q_prime_ri_ack", "srslte_b200_uci_q_prime_cqi",
+    "srslte_b200_group_create", "srslte_b200_group_destroy", "srslte_b200_group_size", "srslte_b200_group_ctx",
+    "srslte_b200_group_tdec_batch_host", "srslte_b200_group_h2d_probe", "srslte_b200_h2d_probe",
 ]
 
 _lib = None
@@ -112,6 +114,7 @@ def lib():
     L.srslte_b200_ctx_enable_timing.argtypes = [vp, i32]
     L.srslte_b200_ctx_kernel_time.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u32)]
     L.srslte_b200_ctx_set_exact.argtypes = [vp, i32]
+    L.srslte_b200_ctx_set_variant_bits.argtypes = [vp, u32]
     L.srslte_b200_ctx_fallback_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.srslte_b200_ctx_tier_counts.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.srslte_b200_host_alloc.argtypes = [C.c_size_t]
@@ -142,12 +145,74 @@ def lib():
     L.srslte_b200_uci_q_prime_ri_ack.restype = u32
     L.srslte_b200_uci_q_prime_cqi.argtypes = [u32, u32, u32, u32, C.c_float, u32]
     L.srslte_b200_uci_q_prime_cqi.restype = u32
+    L.srslte_b200_group_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), u32]
+    L.srslte_b200_group_destroy.argtypes = [vp]
+    L.srslte_b200_group_destroy.restype = None
+    L.srslte_b200_group_size.argtypes = [vp]
+    L.srslte_b200_group_size.restype = u32
+    L.srslte_b200_group_ctx.argtypes = [vp, u32]
+    L.srslte_b200_group_ctx.restype = vp
+    L.srslte_b200_group_tdec_batch_host.argtypes = [vp, C.POINTER(TdecBatch), vp, vp, vp, vp]
+    L.srslte_b200_group_h2d_probe.argtypes = [vp, vp, C.c_size_t, u32, C.POINTER(C.c_double)]
+    L.srslte_b200_h2d_probe.argtypes = [vp, vp, C.c_size_t, u32, C.POINTER(C.c_double)]
     _lib = L
     return L
 
 
 class B200Error(RuntimeError):
     pass
+
+
+class Group:
+    """Several GPUs of one box from ONE process (srslte_b200_group_t): a batch is cut into contiguous shards, one per
+    device, each run from its own host thread; no inter-device traffic."""
+
+    def __init__(self, devices):
+        self._L = lib()
+        self._h = C.c_void_p()
+        devs = list(range(devices)) if isinstance(devices, int) else list(devices)
+        arr = (C.c_int * len(devs))(*devs)
+        rc = self._L.srslte_b200_group_create(C.byref(self._h), arr, len(devs))
+        if rc:
+            raise B200Error(f"srslte_b200_group_create({devs}) failed ({rc}); there is no CPU fallback")
+
+    def close(self):
+        if self._h:
+            self._L.srslte_b200_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self._L.srslte_b200_group_size(self._h))
+
+    def tdec_batch_host(self, llr, K, nof_iterations, crc_mode=CRC_NONE, natural=True, out=None, nit=None, ok=None):
+        assert llr.dtype == np.int16 and llr.ndim == 2 and llr.flags.c_contiguous
+        n, in_stride = llr.shape
+        kmax = int(K) if np.isscalar(K) else int(np.max(K)) if n else 0
+        out_stride = kmax // 8
+        if out is None:
+            out = np.zeros((n, out_stride), np.uint8)
+        nit = np.zeros(n, np.uint8) if nit is None else nit
+        ok = np.zeros(n, np.uint8) if ok is None else ok
+        b, keep = Context._batch(n, K, natural, in_stride, out_stride, nof_iterations, crc_mode)
+        rc = self._L.srslte_b200_group_tdec_batch_host(self._h, C.byref(b), llr.ctypes.data, out.ctypes.data,
+                                                       nit.ctypes.data, ok.ctypes.data)
+        if rc:
+            raise B200Error(f"srslte_b200_group_tdec_batch_host -> {rc}")
+        return out, nit, ok
+
+    def h2d_probe(self, host_ptr, bytes_per_device, reps=4):
+        """GB/s per device while ALL devices of the group copy from pinned host memory at the same time."""
+        g = (C.c_double * len(self))()
+        rc = self._L.srslte_b200_group_h2d_probe(self._h, C.c_void_p(host_ptr), bytes_per_device, reps, g)
+        if rc:
+            raise B200Error(f"srslte_b200_group_h2d_probe -> {rc}")
+        return [float(x) for x in g]
 
 
 def rm_rx_table(K, rv, sb_layout=True):
@@ -233,6 +298,10 @@ class Context:
         """force the exact saturating variant of the window decoders (the fast variant is the default)."""
         self._check(self._L.srslte_b200_ctx_set_exact(self._h, int(on)), "set_exact")
 
+    def set_variant_bits(self, bits):
+        """tests / measurements: restrict the (bit-identical) decoder variants, see include/srslte_b200.h"""
+        self._check(self._L.srslte_b200_ctx_set_variant_bits(self._h, int(bits)), "set_variant_bits")
+
     @property
     def tier_counts(self):
         """(warp, half iteration) pairs so far in the pure / static / tracked / exact variant"""
@@ -249,6 +318,12 @@ class Context:
     @property
     def launch_count(self):
         return int(self._L.srslte_b200_launch_count(self._h))
+
+    def h2d_probe(self, host_ptr, nbytes, reps=4):
+        """GB/s of `reps` host-to-device copies of nbytes from (pinned) host_ptr on this context's copy stream."""
+        g = C.c_double()
+        self._check(self._L.srslte_b200_h2d_probe(self._h, C.c_void_p(host_ptr), nbytes, reps, C.byref(g)), "h2d_probe")
+        return g.value
 
     @staticmethod
     def _batch(n, K, natural, in_stride, out_stride, nof_iterations, crc_mode):

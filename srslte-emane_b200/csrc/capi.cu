@@ -10,6 +10,10 @@
 #include <chrono>
 #include <map>
 #include <string>
+#include <pthread.h>
+#include <sched.h>
+#include <cctype>
+#include <thread>
 #include <vector>
 
 #include "lte_tables.h"
@@ -81,6 +85,10 @@ struct Schedule {  // how the code blocks of one launch map onto warps
   // window regimes: the CTA rounds (first item, number of items <= tdec_items_per_cta) in launch order
   std::vector<uint2>    rounds[2];
   uint32_t              round_base[2] = {0, 0};
+  // window regimes, CRC modes: the work of one block size (first item, items that hold blocks), see tdec_win_dyn_kernel
+  std::vector<uint4>    epochs[2];  // (first item, items, first input position, blocks)
+  uint32_t              epoch_base[2] = {0, 0};
+  uint32_t              epoch_items[2] = {0, 0};
 };
 
 }  // namespace
@@ -95,12 +103,16 @@ struct srslte_b200_ctx {
   Regime       regime[3];
   DevBuf<uint32_t> counters;           // 3 work counters + 1 fallback counter + 4 tier counters
   bool         force_exact = false;
+  uint32_t     variant_bits = 0;       // srslte_b200_ctx_set_variant_bits
   // schedule cache
   DevBuf<uint32_t> d_order;
   DevBuf<WorkItem> d_items;
   DevBuf<uint32_t> d_cbK;
   DevBuf<uint2>    d_place, d_rounds;
   PinBuf<uint2>    h_place, h_rounds;
+  DevBuf<uint4>    d_epochs;
+  PinBuf<uint4>    h_epochs;
+  DevBuf<uint32_t> d_dyn_counters;
   PinBuf<uint32_t> h_order;
   PinBuf<WorkItem> h_items;
   PinBuf<uint32_t> h_cbK;
@@ -216,6 +228,19 @@ void build_rounds(srslte_b200_ctx* ctx, Schedule& s)
     const uint32_t per = (uint32_t)tdec_items_per_cta(ri == 0 ? 16 : 8);
     R.clear();
     const auto& items = s.items[ri];
+    auto& E = s.epochs[ri];
+    E.clear();
+    s.epoch_items[ri] = 0;
+    for (uint32_t i = 0; i < items.size(); i++) {
+      if (items[i].count == 0) continue;  // filler
+      if (!E.empty() && items[E.back().x].K == items[i].K && E.back().x + E.back().y == i) {
+        E.back().y++;
+        E.back().w += items[i].count;
+      } else {
+        E.push_back(make_uint4(i, 1, items[i].in_pos, items[i].count));
+      }
+      s.epoch_items[ri]++;
+    }
     for (uint32_t i = 0; i < items.size(); i += per) R.push_back(make_uint2(i, per));
     const uint32_t G = (uint32_t)std::max(1, ctx->sm_count * tdec_ctas_per_sm());
     const uint32_t last = (uint32_t)(R.size() % G);
@@ -338,6 +363,19 @@ int ensure_schedule(srslte_b200_ctx* ctx, const uint32_t* K, uint32_t uniform_K,
       std::memcpy(ctx->h_rounds.p + s.round_base[r], s.rounds[r].data(), s.rounds[r].size() * sizeof(uint2));
   if (n_rounds)
     CU(cudaMemcpyAsync(ctx->d_rounds.p, ctx->h_rounds.p, n_rounds * sizeof(uint2), cudaMemcpyHostToDevice, st));
+  size_t n_epochs = 0;
+  for (int r = 0; r < 2; r++) {
+    s.epoch_base[r] = (uint32_t)n_epochs;
+    n_epochs += s.epochs[r].size();
+  }
+  CU(ctx->h_epochs.reserve(n_epochs + 1));
+  CU(ctx->d_epochs.reserve(n_epochs + 1));
+  CU(ctx->d_dyn_counters.reserve(n_epochs * 8 + 8));
+  for (int r = 0; r < 2; r++)
+    if (!s.epochs[r].empty())
+      std::memcpy(ctx->h_epochs.p + s.epoch_base[r], s.epochs[r].data(), s.epochs[r].size() * sizeof(uint4));
+  if (n_epochs)
+    CU(cudaMemcpyAsync(ctx->d_epochs.p, ctx->h_epochs.p, n_epochs * sizeof(uint4), cudaMemcpyHostToDevice, st));
   CU(ctx->h_order.reserve(n));
   CU(ctx->h_items.reserve(n_items));
   CU(ctx->d_order.reserve(n));
@@ -468,6 +506,10 @@ int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint
     a.rounds     = r < 2 ? ctx->d_rounds.p + ctx->sched.round_base[r] : nullptr;
     a.n_rounds   = r < 2 ? (uint32_t)ctx->sched.rounds[r].size() : 0u;
     a.counter    = ctx->counters.p + r;
+    a.epochs       = r < 2 ? ctx->d_epochs.p + ctx->sched.epoch_base[r] : nullptr;
+    a.n_epochs     = r < 2 ? (uint32_t)ctx->sched.epochs[r].size() : 0u;
+    a.dyn_counters = r < 2 ? ctx->d_dyn_counters.p + (size_t)ctx->sched.epoch_base[r] * 8 : nullptr;
+    a.dyn_items    = r < 2 ? ctx->sched.epoch_items[r] : 0u;
     a.max_iter   = b->nof_iterations;
     a.crc_mode   = b->crc_mode;
     a.crc_mode_cb = d_crc_mode_cb;
@@ -481,7 +523,7 @@ int enqueue_decode(srslte_b200_ctx* ctx, const srslte_b200_tdec_batch_t* b, uint
       const char* f = getenv("SRSLTE_B200_FORCE_BITS");
       return (uint32_t)(((v & 1) ? 2u : 0u) | ((v & 2) ? 4u : 0u) | (f ? (uint32_t)atol(f) : 0u));
     }();
-    a.force_exact = (ctx->force_exact ? 1u : 0u) | skip_tiers;
+    a.force_exact = (ctx->force_exact ? 1u : 0u) | skip_tiers | ctx->variant_bits;
     a.stats      = ctx->counters.p + 3;
     {
       KernelTimer kt(ctx, r, st);
@@ -551,6 +593,9 @@ void srslte_b200_ctx_destroy(srslte_b200_ctx_t* ctx)
   ctx->h_place.release();
   ctx->d_rounds.release();
   ctx->h_rounds.release();
+  ctx->d_epochs.release();
+  ctx->h_epochs.release();
+  ctx->d_dyn_counters.release();
   ctx->h_order.release();
   ctx->h_items.release();
   ctx->h_cbK.release();
@@ -640,6 +685,13 @@ int srslte_b200_ctx_set_exact(srslte_b200_ctx_t* ctx, int force_exact)
   return SRSLTE_B200_SUCCESS;
 }
 
+int srslte_b200_ctx_set_variant_bits(srslte_b200_ctx_t* ctx, uint32_t bits)
+{
+  if (!ctx) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  ctx->variant_bits = bits & ~1u;
+  return SRSLTE_B200_SUCCESS;
+}
+
 int srslte_b200_ctx_fallback_count(srslte_b200_ctx_t* ctx, uint64_t* count)
 {
   if (!ctx || !count) return SRSLTE_B200_ERROR_INVALID_INPUTS;
@@ -664,6 +716,144 @@ int srslte_b200_ctx_tier_counts(srslte_b200_ctx_t* ctx, uint64_t counts[4])
   CU(cudaMemcpy(v, ctx->counters.p + 4, sizeof(v), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 4; i++) counts[i] = v[i];
   return SRSLTE_B200_SUCCESS;
+}
+
+// ---- several devices from one process -------------------------------------------------------------------------
+struct srslte_b200_group {
+  std::vector<srslte_b200_ctx*> ctx;
+};
+
+namespace {
+// run the calling thread on the CPUs next to the GPU (its PCI device's local_cpulist); best effort
+void bind_thread_near_device(int device)
+{
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return;
+  for (char* p = bus; *p; p++) *p = (char)tolower(*p);
+  char path[128];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+  FILE* f = fopen(path, "r");
+  if (!f) return;
+  char line[1024] = {0};
+  const bool got = fgets(line, sizeof(line), f) != nullptr;
+  fclose(f);
+  if (!got) return;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  int n = 0;
+  for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+    int a = 0, b = 0;
+    const int k = sscanf(tok, "%d-%d", &a, &b);
+    if (k == 1) b = a;
+    if (k >= 1)
+      for (int c = a; c <= b && c < CPU_SETSIZE; c++) {
+        CPU_SET(c, &set);
+        n++;
+      }
+  }
+  if (n) pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+}
+
+int h2d_probe_one(srslte_b200_ctx* ctx, const void* host, size_t bytes, uint32_t reps, double* gbs)
+{
+  if (!ctx || !host || !gbs || bytes == 0 || reps == 0) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->d_in[0].reserve((bytes + 1) / 2));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  CU(cudaMemcpyAsync(ctx->d_in[0].p, host, bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));  // warm
+  CU(cudaEventRecord(e0, ctx->h2d_stream));
+  for (uint32_t r = 0; r < reps; r++)
+    CU(cudaMemcpyAsync(ctx->d_in[0].p, host, bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));
+  CU(cudaEventRecord(e1, ctx->h2d_stream));
+  CU(cudaEventSynchronize(e1));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *gbs = (double)bytes * reps / (ms * 1e-3) / 1e9;
+  return SRSLTE_B200_SUCCESS;
+}
+}  // namespace
+
+int srslte_b200_group_create(srslte_b200_group_t** out, const int* devices, uint32_t n_devices)
+{
+  if (!out || n_devices == 0 || n_devices > 64) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  *out = nullptr;
+  srslte_b200_group* g = new srslte_b200_group();
+  for (uint32_t i = 0; i < n_devices; i++) {
+    srslte_b200_ctx_t* c = nullptr;
+    if (srslte_b200_ctx_create(&c, devices ? devices[i] : (int)i) != SRSLTE_B200_SUCCESS) {
+      srslte_b200_group_destroy(g);
+      return SRSLTE_B200_ERROR;
+    }
+    g->ctx.push_back(c);
+  }
+  *out = g;
+  return SRSLTE_B200_SUCCESS;
+}
+
+void srslte_b200_group_destroy(srslte_b200_group_t* g)
+{
+  if (!g) return;
+  for (auto* c : g->ctx) srslte_b200_ctx_destroy(c);
+  delete g;
+}
+
+uint32_t srslte_b200_group_size(const srslte_b200_group_t* g) { return g ? (uint32_t)g->ctx.size() : 0; }
+
+srslte_b200_ctx_t* srslte_b200_group_ctx(srslte_b200_group_t* g, uint32_t i) { return g && i < g->ctx.size() ? g->ctx[i] : nullptr; }
+
+int srslte_b200_group_tdec_batch_host(srslte_b200_group_t* g, const srslte_b200_tdec_batch_t* b, const int16_t* llr,
+                                      uint8_t* out, uint8_t* n_iter, uint8_t* crc_ok)
+{
+  if (!g || g->ctx.empty() || !b) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  const uint32_t world = (uint32_t)g->ctx.size();
+  if (b->n_cb == 0) return SRSLTE_B200_SUCCESS;
+  if (!llr || !out) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  std::vector<int>         rc(world, SRSLTE_B200_SUCCESS);
+  std::vector<std::thread> th;
+  for (uint32_t r = 0; r < world; r++) {
+    const uint32_t first = (uint32_t)((uint64_t)b->n_cb * r / world), last = (uint32_t)((uint64_t)b->n_cb * (r + 1) / world);
+    if (first == last) continue;
+    th.emplace_back([=, &rc] {
+      bind_thread_near_device(g->ctx[r]->device);
+      srslte_b200_tdec_batch_t pb = *b;
+      pb.n_cb    = last - first;
+      pb.long_cb = b->long_cb ? b->long_cb + first : nullptr;
+      rc[r] = srslte_b200_tdec_batch_host(g->ctx[r], &pb, llr + (size_t)first * b->in_stride, out + (size_t)first * b->out_stride,
+                                          n_iter ? n_iter + first : nullptr, crc_ok ? crc_ok + first : nullptr);
+    });
+  }
+  for (auto& t : th) t.join();
+  for (uint32_t r = 0; r < world; r++)
+    if (rc[r] != SRSLTE_B200_SUCCESS) return rc[r];
+  return SRSLTE_B200_SUCCESS;
+}
+
+int srslte_b200_group_h2d_probe(srslte_b200_group_t* g, const void* host, size_t bytes_per_device, uint32_t reps,
+                                double* gbs_per_device)
+{
+  if (!g || g->ctx.empty() || !host || !gbs_per_device) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  const uint32_t world = (uint32_t)g->ctx.size();
+  std::vector<int>         rc(world, SRSLTE_B200_SUCCESS);
+  std::vector<std::thread> th;
+  for (uint32_t r = 0; r < world; r++)
+    th.emplace_back([=, &rc] {
+      bind_thread_near_device(g->ctx[r]->device);
+      rc[r] = h2d_probe_one(g->ctx[r], static_cast<const char*>(host) + (size_t)r * bytes_per_device, bytes_per_device, reps,
+                            gbs_per_device + r);
+    });
+  for (auto& t : th) t.join();
+  for (uint32_t r = 0; r < world; r++)
+    if (rc[r] != SRSLTE_B200_SUCCESS) return rc[r];
+  return SRSLTE_B200_SUCCESS;
+}
+
+int srslte_b200_h2d_probe(srslte_b200_ctx_t* ctx, const void* host, size_t bytes, uint32_t reps, double* gbs)
+{
+  return h2d_probe_one(ctx, host, bytes, reps, gbs);
 }
 
 void* srslte_b200_host_alloc(size_t bytes)

@@ -1177,7 +1177,9 @@ __device__ __forceinline__ uint32_t alpha_out2(uint32_t a[8], const uint32_t bb[
 
 // alpha + output over one row group with the rebuilt beta in registers: B[i] is the beta above row k0 + i
 // top: nullptr, or where (shared memory, [half * 32]) the beta above the group's LAST row is to be read from
-template <int W, int NORM, bool TRACK, bool HARD>
+// EDGE0: this is the group of rows 0..3 next to the known start state of the first window, in the reference's saturating
+// arithmetic (alpha / output only; beta comes from the fast rebuild like everywhere else), normalised after row 2 only.
+template <int W, int NORM, bool TRACK, bool HARD, bool EDGE0 = false>
 __device__ __forceinline__ void fwd_group(const WinCtx<W>& c, const uint32_t* stab_dir, uint32_t k0, uint32_t a[8],
                                           const uint32_t (*B)[8], const uint4& sv, const uint4& pv, const uint4& av, char* Y,
                                           Range& ra, Range& rm, Range& rd, uint32_t& crc, bool skip0,
@@ -1191,7 +1193,14 @@ __device__ __forceinline__ void fwd_group(const WinCtx<W>& c, const uint32_t* st
 #pragma unroll
   for (int r = 0; r < 4; r++) {
     const uint32_t x = wadd2(aa[r], sa[r]);
-    if (r == 3 && top) {
+    if (EDGE0) {
+      Range unused;
+      unused.reset();
+      const uint32_t xe = sadd2(aa[r], sa[r]);  // (DEC2: the systematic stream reads as zero)
+      uint32_t       o  = alpha_out_step<false>(a, B[r], xe, pa[r], sadd2(xe, pa[r]), unused);
+      if (W == 8) o = sra1_2(o);
+      d[r] = wsub2(o, aa[r]);
+    } else if (r == 3 && top) {
       const uint4    t0 = top[0], t1 = top[32];
       const uint32_t bt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
       d[r] = alpha_out2<W, TRACK>(a, bt, x, pa[r], sa[r], aa[r], rm);
@@ -1211,7 +1220,12 @@ __device__ __forceinline__ void fwd_group(const WinCtx<W>& c, const uint32_t* st
     *reinterpret_cast<uint16_t*>(Y + o_lo) = (uint16_t)(d[r] & 0xFFFFu);
     *reinterpret_cast<uint16_t*>(Y + o_hi) = (uint16_t)(d[r] >> 16);
     if (r & 1) rd.add2v(d[r - 1], d[r]);
-    if (NORM == 4 ? r == 2 : (r & 1) == 0) {
+    if (EDGE0) {
+      if (r == 2) {
+        normalize<false>(a);
+        if (TRACK) ra.add8(a);
+      }
+    } else if (NORM == 4 ? r == 2 : (r & 1) == 0) {
       if (r != 0 || !skip0) {
         normalize<true>(a);
         if (TRACK) ra.add8(a);
@@ -1450,6 +1464,55 @@ __device__ __noinline__ void fwd_rows_slow(const WinCtx<W> c, bool dec2, int nro
   st->ra = ra; st->rm = rm; st->rd = rd; st->crc = crc;
 }
 
+// The chunk of rows 0..15 of a window whose length is a multiple of 16, with rows 0..3 in exact arithmetic (static and
+// tracked tiers): one pass of forward_side's loop body, out of line, with its own loads (fwd_rows_slow did this chunk row
+// by row with beta in local memory, 4 x slower per row: +12 % per half iteration).
+template <int W, int NORM, bool TRACK, bool HARD>
+__device__ __noinline__ void fwd_chunk_edge(const WinCtx<W> c, bool dec2, int j, FwdState* st)
+{
+  constexpr int GB = (int)kGroupBytes;
+  uint32_t a[8], s[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = st->a[i];
+  Range    ra = st->ra, rm = st->rm, rd = st->rd, rb;
+  uint32_t crc = st->crc;
+  rb.reset();
+  const Streams q = half_streams<W>(c, dec2);  // the chunk starts at row 0
+  Unit X, Yb;
+  load_unit<0>(q, Yb);
+  load_unit<2 * GB>(q, X);
+  char* const           Yout = out_base<W>(c, dec2);
+  const uint32_t* const sdir = c.stab + (dec2 ? 0u : kStabDir);
+  uint32_t B[7][8];
+  {
+    ck_get<W>(c, j, s);
+    if (j != 0) normalize<true>(s);
+    Rows4 r4;
+    rows_of(X.s[1], X.p[1], X.a[1], r4);
+    beta_group<NORM, false>(s, r4, rb, false);
+    rows_of(X.s[0], X.p[0], X.a[0], r4);
+#pragma unroll
+    for (int r = 3; r >= 1; r--) {
+      beta_step<true>(s, r4.x[r], r4.y[r], wadd2(r4.x[r], r4.y[r]));
+      if (NORM == 2 && r == 2) normalize<true>(s);
+    }
+    beta_step<true>(s, r4.x[0], r4.y[0], wadd2(r4.x[0], r4.y[0]));
+    ck_put<W>(c, kMaxCk, s);
+  }
+  rebuild8<NORM>(s, true, Yb, B);
+  fwd_group<W, NORM, TRACK, HARD, true>(c, sdir, 0, a, &B[0], Yb.s[0], Yb.p[0], Yb.a[0], Yout, ra, rm, rd, crc, false);
+  fwd_group<W, NORM, TRACK, HARD>(c, sdir, 4, a, &B[4], Yb.s[1], Yb.p[1], Yb.a[1], Yout, ra, rm, rd, crc, false,
+                                  c.ck + kMaxCk * 64);
+  ck_get<W>(c, j, s);
+  rebuild8<NORM>(s, j != 0, X, B);
+  fwd_group<W, NORM, TRACK, HARD>(c, sdir, 8, a, &B[0], X.s[0], X.p[0], X.a[0], Yout, ra, rm, rd, crc, false);
+  fwd_group<W, NORM, TRACK, HARD>(c, sdir, 12, a, &B[4], X.s[1], X.p[1], X.a[1], Yout, ra, rm, rd, crc, false,
+                                  c.ck + j * 64);
+#pragma unroll
+  for (int i = 0; i < 8; i++) st->a[i] = a[i];
+  st->ra = ra; st->rm = rm; st->rd = rd; st->crc = crc;
+}
+
 // ---- forward side: alpha + output over the window, 16 rows at a time: from the checkpoint beta first runs down the
 // upper 8 rows (stage A), then the lower 8 rows of beta are rebuilt into registers and alpha + the outputs run over
 // them (stage B), then the same for the upper 8 rows (stage C).  edge: rows 0..3 in exact arithmetic.
@@ -1473,7 +1536,7 @@ __device__ __forceinline__ HalfResult forward_side(const WinCtx<W>& c, bool dec2
   if (R) {
     fwd_rows_slow<W, NORM, TRACK, HARD>(c, dec2, R, nc, true, edge, &f);
   } else if (edge) {
-    fwd_rows_slow<W, NORM, TRACK, HARD>(c, dec2, 16, jb, jb != 0, true, &f);
+    fwd_chunk_edge<W, NORM, TRACK, HARD>(c, dec2, jb, &f);
     jb--;
   }
 #endif
@@ -1904,6 +1967,318 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
       }
     }
     __syncthreads();  // every warp is done with the tables (and with s_item)
+  }
+  if (lane == 0 && fallbacks && a.stats) atomicAdd(a.stats, fallbacks);
+  if (lane < 4 && a.stats && tiers[lane]) atomicAdd(a.stats + 1 + lane, tiers[lane]);
+}
+
+// Hard decision of the code blocks that finished in this half iteration, by the WHOLE CTA: a thread takes 32 consecutive
+// bits of one block (natural order: bit n = window n / L, row n % L), gathers A[n] and E[pi^-1(n)] from the extrinsic
+// arrays of the warp slot that decoded the block and stores one big-endian word.  (decide() above costs the warp that
+// calls it about a quarter of a half iteration in load latency; with the CTA's warps in step -- see the kernel below --
+// every warp would wait for it in nearly every half iteration.)
+// fin[i] = (code block index, warp << 3 | group, bit 6: finished after its first half iteration, A reads as zero).  Call between CTA barriers: the arrays must be complete and unchanged.
+template <int W>
+__device__ __noinline__ void decide_coop(const int16_t* ws_ae, uint8_t* out, uint32_t out_stride, uint32_t K, const uint32_t* stab,
+                                         const uint2* fin, uint32_t nfin)
+{
+  constexpr uint32_t WH = W / 2;
+  constexpr size_t   XB = (W == 16) ? kXArrayBytes16 : kXArrayBytes8;
+  constexpr int      NB = 16;
+  const uint32_t L  = K / W;
+  const uint32_t nw = (K + 31) >> 5;
+  const uint32_t mL = (uint32_t)((0x100000000ull + L - 1) / L);
+  if ((L & 31u) == 0 && (out_stride & 3u) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
+    // Whole words per window.  A warp takes (block, 32 rows): its lanes are (row mod RPL, window), so one load
+    // instruction reads whole 2W-byte pieces -- the W windows of a row of a block sit next to each other in A, and the
+    // QPP sends them to ONE row of E (contention free) -- instead of 32 scattered sectors: the gathers of the general
+    // form below are bound by the load/store unit (one wavefront per lane), these are 32 / W wavefronts per load.
+    constexpr uint32_t RPL = 32 / W;  // rows per load instruction
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, r = lane / W, d = lane % W;
+    const uint32_t wpw = L >> 5;      // words per window
+    // the gathers are latency bound: a warp keeps the loads of two units (2 x 32 rows) in flight
+    constexpr int NI = 32 / RPL;  // loads of each kind per lane and unit
+    const uint32_t total = nfin * wpw;
+    for (uint32_t u0 = warp; u0 < total; u0 += 2 * kWarps) {
+      uint16_t    av[2][NI], ev[2][NI];
+      uint32_t*   dst[2];
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const uint32_t u  = min(u0 + q * kWarps, total - 1);  // (an odd unit out is done twice)
+        const uint32_t bi = u / wpw, j = u - bi * wpw;
+        const uint2    f  = fin[bi];
+        const uint32_t g  = f.y & 7u;
+        const bool     noA = (f.y & 64u) != 0;
+        const char*    A8 = reinterpret_cast<const char*>(ws_ae) + (size_t)(blockIdx.x * kWarps + ((f.y >> 3) & 7u)) * 2 * XB;
+        const char*    E8 = A8 + XB + g * (2 * W);
+        dst[q] = reinterpret_cast<uint32_t*>(out + (size_t)f.x * out_stride) + d * wpw + j;
+#pragma unroll
+        for (int i = 0; i < NI; i++) {
+          const uint32_t k   = 32u * j + i * RPL + r;
+          const uint32_t e   = stab[kStabDir + (k >> 2) * (WH * 4) + (d >> 1) * 4 + (k & 3u)];
+          const uint32_t off = (d & 1u) ? e >> 16 : e & 0xFFFFu;
+          av[q][i] = noA ? (uint16_t)0 : __ldcg(reinterpret_cast<const uint16_t*>(A8 + (k * 32u + g * WH + (d >> 1)) * 4u + (d & 1u) * 2u));
+          ev[q][i] = __ldcg(reinterpret_cast<const uint16_t*>(E8 + off));
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < NI; i++)
+          acc |= ((int16_t)(uint16_t)(av[q][i] + ev[q][i]) > 0 ? 1u : 0u) << (31u - (i * RPL + r));
+#pragma unroll
+        for (uint32_t o = W; o < 32; o <<= 1) acc |= __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+        if (r == 0) *dst[q] = __byte_perm(acc, 0, 0x0123);
+      }
+    }
+    return;
+  }
+  for (uint32_t u = threadIdx.x; u < nfin * nw; u += blockDim.x) {
+    const uint32_t bi = u / nw, j = u - bi * nw;
+    const uint2    f  = fin[bi];
+    const uint32_t g  = f.y & 7u;
+    const bool     noA = (f.y & 64u) != 0;
+    const char*    A8 = reinterpret_cast<const char*>(ws_ae) + (size_t)(blockIdx.x * kWarps + ((f.y >> 3) & 7u)) * 2 * XB;
+    const char*    E8 = A8 + XB + g * (2 * W);
+    const uint32_t n0 = 32u * j, nb = min(32u, K - n0);
+    uint32_t       d = __umulhi(n0, mL), k = n0 - d * L;
+    uint32_t       word = 0;
+#pragma unroll
+    for (int h = 0; h < 32 / NB; h++) {
+      uint16_t av[NB], ev[NB];
+#pragma unroll
+      for (int i = 0; i < NB; i++) {
+        const uint32_t e   = stab[kStabDir + (k >> 2) * (WH * 4) + (d >> 1) * 4 + (k & 3u)];
+        const uint32_t off = (d & 1u) ? e >> 16 : e & 0xFFFFu;
+        av[i] = noA ? (uint16_t)0 : __ldcg(reinterpret_cast<const uint16_t*>(A8 + (k * 32u + g * WH + (d >> 1)) * 4u + (d & 1u) * 2u));
+        ev[i] = __ldcg(reinterpret_cast<const uint16_t*>(E8 + off));
+        if ((uint32_t)(h * NB + i + 1) < nb) {  // bits past the block's end repeat its last bit (never stored)
+          if (++k == L) {
+            k = 0;
+            d++;
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NB; i++) word = (word << 1) | ((int16_t)(uint16_t)(av[i] + ev[i]) > 0 ? 1u : 0u);
+    }
+    uint8_t* o = out + (size_t)f.x * out_stride + 4u * j;
+    if (nb == 32 && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {
+      *reinterpret_cast<uint32_t*>(o) = __byte_perm(word, 0, 0x0123);
+    } else {
+      for (uint32_t b = 0; b < nb / 8; b++) o[b] = (uint8_t)(word >> (24 - 8 * b));
+    }
+  }
+}
+
+// ---- CRC modes: block-granular early termination -------------------------------------------------------------------
+// reference: lib/src/phy/phch/sch.c:353-383 -- a code block leaves the loop at the half iteration its CRC passes.
+// In the kernel above a warp keeps its W/2-thread groups busy until the LAST of its blocks stops and a CTA waits for its
+// slowest warp, so blocks that converge early buy no time.  Here every thread group is its own worker: the work of one
+// block size (an "epoch": the items of one K, tables built once) is one queue PER BLOCK POSITION of a work item (a group
+// always works at its own lane position, so the item-interleaved input layout and the warp's extrinsic arrays stay as
+// they are), and a group whose block has finished -- CRC passed or iteration cap reached -- writes its result and takes
+// the next block of its queue while the other groups of the warp go on with theirs.  The groups of a warp are then at
+// different half iterations: DEC1 / DEC2 (`dec2`) and "no a-priori input yet" (`noap`) are per-thread values, which the
+// main fast path takes as they only select pointers; the tracked tier runs through the main path too (half_tracked2, out
+// of line).  The general path stages whole-warp pieces by bulk copies and needs one parity per warp: the block sizes it
+// serves (L % 4 != 0) refill a warp only as a whole (`aligned`).
+// The warps of a CTA start every half iteration together (one CTA barrier): see the loop below.
+template <int W>
+__global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_dyn_kernel(const TdecLaunch a)
+{
+  constexpr int      WH  = W / 2;
+  constexpr uint32_t PER = 32 / WH;  // block positions of an item = queues of an epoch
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
+  extern __shared__ uint4 smem[];
+  char*     warp_sm_all = reinterpret_cast<char*>(smem);
+  uint32_t* stab        = reinterpret_cast<uint32_t*>(warp_sm_all + kWarps * kWarpSmem);
+  uint64_t* mbar_all    = reinterpret_cast<uint64_t*>(stab + 2 * kStabDir);
+  __shared__ uint32_t s_epoch;
+  __shared__ uint32_t s_nfin[2];              // blocks that finished in this / the previous half iteration
+  __shared__ uint2    s_fin[2][kWarps * PER];  // (code block, warp << 3 | group)
+
+  const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int      grp = lane / WH, t = lane % WH;
+  const uint32_t slot = blockIdx.x * kWarps + warp;
+  uint32_t       fallbacks = 0;
+  uint32_t       tiers[4] = {0, 0, 0, 0};
+  Pipe           pipe;
+  pipe.par = 0;
+  if (lane == 0) {
+    for (int s = 0; s < kStages; s++) mbar_init(mbar_all + warp * kStages + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid == 0) s_nfin[0] = s_nfin[1] = 0;
+  fence_proxy_async();
+  __syncthreads();
+
+  uint32_t tab_K = 0, e_cur = 0, par = 0;  // par: which of the two lists this half iteration fills
+  for (;;) {
+    // the first epoch from e_cur on that still has blocks in one of its queues
+    if (tid == 0) s_epoch = FULL;
+    __syncthreads();
+    for (uint32_t base = e_cur; base < a.n_epochs; base += kThreads) {
+      const uint32_t e = base + (uint32_t)tid;
+      if (e < a.n_epochs) {
+        const uint32_t n = a.epochs[e].y;
+        bool left = false;
+        for (uint32_t g = 0; g < PER; g++)
+          left = left || *reinterpret_cast<volatile const uint32_t*>(a.dyn_counters + e * PER + g) < n;
+        if (left) atomicMin(&s_epoch, e);
+      }
+      __syncthreads();
+      const uint32_t found = s_epoch;
+      __syncthreads();  // nobody may update s_epoch for the next stretch before everybody has read it
+      if (found != FULL) break;
+    }
+    const uint32_t e = s_epoch;
+    if (e == FULL) break;
+    const uint4    ep = a.epochs[e];  // (first item, items with blocks in them, first input position, blocks)
+    const WorkItem w0 = a.items[ep.x];
+    if (w0.K != tab_K) {
+      build_tables<W>(w0.K, w0.f1, w0.f2, stab);
+      tab_K = w0.K;
+    }
+    __syncthreads();
+
+    WinCtx<W> c;
+    c.K = w0.K;
+    c.L = c.K / W;
+    c.t = t;
+    c.lane = lane;
+    c.grp  = grp;
+    c.ngroups  = (c.L + 3) >> 2;
+    c.sp_off   = (uint32_t)lane * 16u;
+    c.s_bytes  = c.ngroups * kGroupBytes;
+    c.stab   = stab + t * 4;
+    char* const warp_sm = warp_sm_all + warp * kWarpSmem;
+    c.ck     = reinterpret_cast<uint4*>(warp_sm) + lane;
+    c.stages = warp_sm;
+    c.sm     = reinterpret_cast<uint4*>(warp_sm + kStages * kStageBytes) + lane;
+    c.mbar   = mbar_all + warp * kStages;
+    constexpr size_t XB = (W == 16) ? kXArrayBytes16 : kXArrayBytes8;
+    char* ae = reinterpret_cast<char*>(a.ws_ae) + (size_t)slot * 2 * XB;
+    c.A32 = reinterpret_cast<uint32_t*>(ae);
+    c.E32 = reinterpret_cast<uint32_t*>(ae + XB);
+    c.chk = reinterpret_cast<uint4*>(reinterpret_cast<char*>(a.ws_chk) + (size_t)slot * kChkSlotBytes) + lane;
+    const bool v2      = (c.L & 3u) == 0 && (a.force_exact & 8u) == 0;
+    const bool aligned = !v2;  // the general path needs one parity per warp: refill the warp only as a whole
+    uint32_t* const queue = a.dyn_counters + e * PER + (uint32_t)grp;
+    const uint32_t* const Rk = a.crc_pos + a.crc_pos_off[w0.kidx] + 2 * t;
+
+    // per-group state (the same in all threads of a group).  A group without a block shadows allocated memory: the
+    // first item of the epoch until it has had a block of its own, its last block afterwards.
+    bool     have = false, dry = false;  // dry: the group's queue has run out
+    uint32_t cb = 0, n = 0, crc_mode = CRC_NONE;
+    int      amax = 0, emax = 0, smax = 0, p0max = 0, p1max = 0;
+    const uint32_t* Rblk = Rk;
+    c.in_item = reinterpret_cast<const char*>(a.in + (size_t)w0.in_pos * a.in_stride);
+    c.tail    = reinterpret_cast<const int16_t*>(c.in_item + 3 * (size_t)c.s_bytes) + grp * 32;
+    if ((uint32_t)warp * (uint32_t)gridDim.x >= a.dyn_items) dry = true;  // small launches: one warp per CTA before a second one anywhere
+    for (;;) {
+      // ONE CTA barrier per half iteration.  The warps of the CTA start every half iteration together: they then run the
+      // same loops at the same time and the instruction cache holds one of them (backward 10 KB, forward 24 KB); left to
+      // themselves they spread over all of it and starve (measured: 56 % of the stall samples "no instructions", 1.4 x
+      // the time of the round-based kernel).  The barrier also completes the list of the blocks that finished in the
+      // previous half iteration, whose hard decisions the whole CTA takes before their groups fetch new blocks.
+      const bool go = __syncthreads_or(__any_sync(FULL, have || !dry)) != 0;
+      const uint32_t nfin = s_nfin[par ^ 1u];
+      if (nfin) {
+        decide_coop<W>(a.ws_ae, a.out, a.out_stride, c.K, stab, s_fin[par ^ 1u], nfin);
+        __syncthreads();  // ... before the next blocks of these groups clear A, and before the list is reused
+        if (tid == 0) s_nfin[par ^ 1u] = 0;
+      }
+      if (!go) break;
+      const bool all_idle = __all_sync(FULL, !have);
+      const bool want = !have && !dry && (!aligned || all_idle);
+      if (__any_sync(FULL, want)) {
+        uint32_t j = FULL;
+        if (want && t == 0) j = atomicAdd(queue, 1u);
+        j = __shfl_sync(FULL, j, grp * WH);
+        bool got = false;
+        if (want) {
+          // item j of the epoch: the items of one block size are consecutive in the schedule, PER blocks and PER input
+          // positions each, only the last one may be partial (no look-up in the item list: it would be one more
+          // dependent load before the half iteration can start)
+          const uint32_t b = j * PER + (uint32_t)grp;
+          if (j < ep.y && b < ep.w) {
+            got = true;
+            cb  = a.order[w0.first + b];
+            c.in_item = reinterpret_cast<const char*>(a.in + (size_t)(ep.z + j * PER) * a.in_stride);
+            c.tail    = reinterpret_cast<const int16_t*>(c.in_item + 3 * (size_t)c.s_bytes) + grp * 32;
+            const uint16_t* meta = reinterpret_cast<const uint16_t*>(c.tail + 16);
+            smax = meta[0]; p0max = meta[1]; p1max = meta[2];
+            crc_mode = a.crc_mode_cb ? a.crc_mode_cb[cb] : a.crc_mode;
+            Rblk = Rk + (size_t)(crc_mode == CRC_24A ? 0 : 1) * 2 * c.K;
+            n = 0; amax = 0; emax = 0;
+            have = true;
+          }
+          dry = !got;
+        }
+        // (A is not cleared: the first half iteration does not read it, DEC2 writes all of it before DEC1 reads it again,
+        // and a block that finishes after its very first half iteration is flagged so in the list of finished blocks)
+      }
+      const bool warp_busy = __any_sync(FULL, have);
+      if (warp_busy) {
+        // groups without a block follow the parity of the first group that has one
+        const uint32_t hmask = __ballot_sync(FULL, have);
+        const uint32_t nlead = __shfl_sync(FULL, n, __ffs(hmask) - 1);
+        const bool     dec2  = ((have ? n : nlead) & 1u) != 0;
+        const bool     mixed = !__all_sync(FULL, dec2) && __any_sync(FULL, dec2);
+        c.noap = have && n == 0;
+        c.R    = Rblk + (dec2 ? c.K : 0u);
+        const int Gx = dec2 ? emax : smax + amax;
+        const int G  = have ? Gx + (dec2 ? p1max : p0max) : 0;
+        HalfResult r;
+        bool       fast_ok = false;
+        __syncwarp();
+        const bool pure = __all_sync(FULL, (a.force_exact & 3u) == 0 && G <= kPureFastG);
+        const bool stat = !pure && __all_sync(FULL, (a.force_exact & 5u) == 0 && G <= kStaticFastG);
+        const bool trk  = !pure && !stat && __all_sync(FULL, (a.force_exact & 1u) == 0 && G <= kMaxFastG);
+        if (v2 && (pure || stat)) {
+          r       = half_fast2<W, 4, false>(c, dec2, G, stat, true);
+          fast_ok = true;
+        } else if (v2 && trk) {
+          // the tracked tier through the main path (out of line): per-thread parities are fine there, and a warp that
+          // went through the general path alone kept the other seven waiting at the barrier for five half iterations
+          r       = half_tracked2<W>(c, dec2, G, true);
+          fast_ok = __all_sync(FULL, r.proven || !have);
+        } else if (!mixed && (pure || stat || trk)) {
+          // general path (L % 4 != 0): the groups of the warp were fetched together, so they share parity and `noap`
+          c.noap  = __any_sync(FULL, c.noap);
+          r       = half_general<W>(c, __any_sync(FULL, dec2), G, pure ? 0 : stat ? 1 : 2, true, &pipe);
+          fast_ok = (pure || stat) ? true : __all_sync(FULL, r.proven || !have);
+        }
+        if (!fast_ok) {
+          r = half_iteration_exact<W>(c, dec2);
+          fallbacks++;
+          tiers[3]++;
+        } else {
+          tiers[pure ? 0 : stat ? 1 : 2]++;
+        }
+        const int dm = (int)group_max<WH>(r.dmax);
+        if (dec2) amax = dm; else emax = dm;
+        n++;
+        uint32_t crc = r.crc;
+#pragma unroll
+        for (int o = WH / 2; o > 0; o >>= 1) crc ^= __shfl_xor_sync(FULL, crc, o);
+        const bool pass   = have && crc_mode != CRC_NONE && crc == 0;
+        const bool finish = have && (pass || n >= a.max_iter);
+        if (finish) {
+          if (t == 0) {
+            s_fin[par][atomicAdd(&s_nfin[par], 1u)] = make_uint2(cb, (uint32_t)(warp << 3 | grp) | (n == 1 ? 64u : 0u));
+            if (a.n_iter) a.n_iter[cb] = (uint8_t)n;
+            if (a.crc_ok) a.crc_ok[cb] = pass ? 1 : 0;
+          }
+          have = false;
+        }
+      }
+      par ^= 1u;
+    }
+    __syncthreads();  // every warp is done with the tables (and with s_epoch)
+    e_cur = e + 1;
   }
   if (lane == 0 && fallbacks && a.stats) atomicAdd(a.stats, fallbacks);
   if (lane < 4 && a.stats && tiers[lane]) atomicAdd(a.stats + 1 + lane, tiers[lane]);
@@ -2374,10 +2749,12 @@ cudaError_t tdec_geometry(int W, int device, TdecGeometry* g)
   if (W == 16) {
     e = cudaFuncSetAttribute(tdec_win_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tdec_win_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tdec_win_dyn_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tdec_win_kernel<16, false>, kThreads, g->smem);
   } else {
     e = cudaFuncSetAttribute(tdec_win_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tdec_win_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tdec_win_dyn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tdec_win_kernel<8, false>, kThreads, g->smem);
   }
   if (e != cudaSuccess) return e;
@@ -2402,7 +2779,18 @@ cudaError_t tdec_launch(int W, const TdecGeometry& g, const TdecLaunch& a, cudaS
   const int blocks = want < g.blocks ? want : g.blocks;
   // CRC modes: blocks converge and their growing extrinsic values make the tracked tier the common case
   const bool trk2 = (a.force_exact & 32u) != 0;  // measured: not worth the slower plain tiers, see half_tracked2
-  if (W == 16 && trk2)
+  // CRC modes: block-granular early termination (force bit 6: the round-based kernel, for measurements and tests)
+  const bool dyn = W && a.n_epochs && (a.crc_mode != CRC_NONE || a.crc_mode_cb) && (a.force_exact & 64u) == 0;
+  if (dyn) {
+    e = cudaMemsetAsync(a.dyn_counters, 0, sizeof(uint32_t) * a.n_epochs * (W == 16 ? 4 : 8), s);
+    if (e != cudaSuccess) return e;
+    // every CTA looks for work itself; a small launch spreads over the SMs instead of filling the first CTAs' warps
+    const int dblocks = (int)a.dyn_items < g.blocks ? (int)a.dyn_items : g.blocks;
+    if (W == 16)
+      tdec_win_dyn_kernel<16><<<dblocks, g.threads, g.smem, s>>>(a);
+    else
+      tdec_win_dyn_kernel<8><<<dblocks, g.threads, g.smem, s>>>(a);
+  } else if (W == 16 && trk2)
     tdec_win_kernel<16, true><<<blocks, g.threads, g.smem, s>>>(a);
   else if (W == 16)
     tdec_win_kernel<16, false><<<blocks, g.threads, g.smem, s>>>(a);

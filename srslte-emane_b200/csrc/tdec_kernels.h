@@ -37,6 +37,10 @@ struct TdecLaunch {
   const uint2*    rounds;      // window kernels: CTA rounds (first item, items <= tdec_items_per_cta(), same K) (device)
   uint32_t        n_rounds;
   uint32_t*       counter;     // device work counter, zeroed by the launcher
+  const uint4*    epochs;      // window kernels, CRC modes (block-granular early termination): per block size of the launch
+  uint32_t        n_epochs;    //   (first item, items that hold blocks, first input position, blocks), in launch order (device)
+  uint32_t*       dyn_counters;//   [n_epochs][blocks per warp] queue heads, zeroed by the launcher
+  uint32_t        dyn_items;   //   items that hold blocks, all epochs (sizes the number of warps a CTA puts to work)
   uint32_t        max_iter;    // half-iteration cap
   uint32_t        crc_mode;
   const uint8_t*  crc_mode_cb; // [n_cb] per-block CrcMode overriding crc_mode (device, nullable)

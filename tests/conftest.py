@@ -40,7 +40,9 @@ def _order_torch_and_library_streams(request):
         import torch
         c = request.getfixturevalue("ctx")
         torch.cuda.synchronize()
-        c.set_stream(torch.cuda.current_stream().cuda_stream)
+        # torch's default stream has handle 0, which the library reads as "use your own stream": name the legacy
+        # default stream explicitly (cudaStreamLegacy = 0x1), the stream torch's fills and copies run on
+        c.set_stream(torch.cuda.current_stream().cuda_stream or 1)
     yield
 
 
