@@ -109,9 +109,8 @@ def _tb_rate(pkg, descs, n_threads, seconds, max_it, resets=True):
 
     def once(w):
         cx, pl, arr, _ = workers[w]
-        if resets:
-            for i in range(n):
-                Lc.srslte_b200_harq_reset(cx._h, pl._p, i)
+        if resets:   # every TB is a new transmission: reset all soft buffers (one C call, like a MAC looping in C)
+            Lc.srslte_b200_harq_reset_many(cx._h, pl._p, None, n)
         rc = Lc.srslte_b200_decode_tb_batch(cx._h, pl._p, arr, n, max_it)
         if rc != 0 or any(arr[i].ret != 0 for i in range(0, n, max(1, n // 7))):
             bad[0] += 1
@@ -260,6 +259,7 @@ def run_configs(pkg, ctx, torch, dev, stream, quick=False):
         r5, bad5, outs5 = _tb_rate(pkg, d5, nt, 0.8 if quick else 1.5, 10)
         par5 = par5 and bad5 == 0 and all(np.array_equal(np.unpackbits(outs5[i][:d5[i]["tbs"] // 8]), pay5[i]) for i in range(200))
         c5[f"subframes_per_s_{nt}_caller_thread"] = r5
+    c5["host_threads"] = "each caller thread owns a context + HARQ pool; a pool has one helper thread (half of the staging copy and of the TB CRC24A)"
     c5["parity"] = bool(par5)
     c5["parity_sample"] = "every TB's bytes vs the transmitted payload"
     res["config5_200_ul_tbs_per_subframe"] = c5

@@ -253,6 +253,9 @@ SRSLTE_B200_API int  srslte_b200_harq_pool_create(srslte_b200_ctx_t* ctx, uint32
 SRSLTE_B200_API void srslte_b200_harq_pool_destroy(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool);
 /* srslte_softbuffer_rx_reset: zero the LLRs, clear cb_crc / tb_crc and the saved payloads of one soft buffer */
 SRSLTE_B200_API int  srslte_b200_harq_reset(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool, uint32_t softbuffer);
+/* the same for n soft buffers in one call (softbuffers == NULL and n == the pool's size: all of them) */
+SRSLTE_B200_API int  srslte_b200_harq_reset_many(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
+                                                 const uint32_t* softbuffers, uint32_t n);
 /* copy of softbuffer->cb_crc[0..n) */
 SRSLTE_B200_API int  srslte_b200_harq_cb_crc(srslte_b200_harq_pool_t* pool, uint32_t softbuffer, uint8_t* cb_crc,
                                              uint32_t n);

@@ -82,7 +82,7 @@ EXPORTS = [
     "srslte_b200_nof_windows", "srslte_b200_working_len", "srslte_b200_rm_rx_table",
     "srslte_b200_tdec_batch_dev", "srslte_b200_tdec_batch_host", "srslte_b200_rm_rx_batch_dev",
     "srslte_b200_demod_descramble_dev", "srslte_b200_demod_rm_rx_batch_dev", "srslte_b200_tcod_rm_tx_batch_dev",
-    "srslte_b200_harq_pool_create", "srslte_b200_harq_pool_destroy", "srslte_b200_harq_reset",
+    "srslte_b200_harq_pool_create", "srslte_b200_harq_pool_destroy", "srslte_b200_harq_reset", "srslte_b200_harq_reset_many",
     "srslte_b200_harq_cb_crc", "srslte_b200_decode_tb_batch", "srslte_b200_decode_tb_sym_batch",
     "srslte_b200_uci_q_prime_ri_ack", "srslte_b200_uci_q_prime_cqi",
     "srslte_b200_group_create", "srslte_b200_group_destroy", "srslte_b200_group_size", "srslte_b200_group_ctx",
@@ -138,6 +138,7 @@ def lib():
     L.srslte_b200_harq_pool_destroy.argtypes = [vp, vp]
     L.srslte_b200_harq_pool_destroy.restype = None
     L.srslte_b200_harq_reset.argtypes = [vp, vp, u32]
+    L.srslte_b200_harq_reset_many.argtypes = [vp, vp, vp, u32]
     L.srslte_b200_harq_cb_crc.argtypes = [vp, u32, vp, u32]
     L.srslte_b200_decode_tb_batch.argtypes = [vp, vp, C.POINTER(TbDesc), u32, u32]
     L.srslte_b200_decode_tb_sym_batch.argtypes = [vp, vp, C.POINTER(TbSymDesc), u32, u32]

@@ -8,7 +8,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <string>
 #include <pthread.h>
 #include <sched.h>
@@ -1279,8 +1283,74 @@ int srslte_b200_tcod_rm_tx_batch_dev(srslte_b200_ctx_t* ctx, const srslte_b200_t
 // transport blocks: rate de-matching into device-resident HARQ soft buffers, decode with CRC early
 // termination, code-block -> transport-block assembly, TB CRC24A  (reference: sch.c:299-500)
 // =====================================================================================================
+namespace {
+// One helper thread per HARQ pool: the transport-block entry hands it half of its two host-side loops (copying the
+// callers' LLRs into the pinned staging buffer, CRC24A over the decoded transport blocks) while the calling thread does
+// the other half.  The thread sleeps between calls.
+class Helper {
+ public:
+  ~Helper()
+  {
+    if (th_.joinable()) {
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        quit_ = true;
+      }
+      cv_.notify_all();
+      th_.join();
+    }
+  }
+  void run(std::function<void()> job)
+  {
+    if (!th_.joinable()) th_ = std::thread([this] { loop(); });
+    job_ = std::move(job);
+    done_.store(false, std::memory_order_relaxed);
+    pending_.store(true, std::memory_order_release);
+    if (asleep_.load(std::memory_order_acquire)) {
+      std::lock_guard<std::mutex> lk(m_);
+      cv_.notify_all();
+    }
+  }
+  void wait()  // the jobs are a fraction of a millisecond: spin
+  {
+    while (!done_.load(std::memory_order_acquire)) __builtin_ia32_pause();
+  }
+
+ private:
+  // After a job the thread polls for the next one for half a millisecond (a caller that decodes subframe after subframe
+  // finds it awake: waking a sleeping thread costs more than the work it is given), then sleeps on the condition variable.
+  void loop()
+  {
+    for (;;) {
+      const auto t0 = std::chrono::steady_clock::now();
+      unsigned   n  = 0;
+      while (!pending_.load(std::memory_order_acquire)) {
+        __builtin_ia32_pause();
+        if ((++n & 1023u) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(500)) {
+          std::unique_lock<std::mutex> lk(m_);
+          asleep_.store(true, std::memory_order_release);
+          cv_.wait(lk, [this] { return pending_.load(std::memory_order_acquire) || quit_; });
+          asleep_.store(false, std::memory_order_release);
+          if (quit_) return;
+        }
+      }
+      pending_.store(false, std::memory_order_relaxed);
+      job_();
+      done_.store(true, std::memory_order_release);
+    }
+  }
+  std::thread             th_;
+  std::mutex              m_;
+  std::condition_variable cv_;
+  std::function<void()>   job_;
+  std::atomic<bool>       pending_{false}, done_{true}, asleep_{false};
+  bool                    quit_ = false;
+};
+}  // namespace
+
 struct srslte_b200_harq_pool {
   uint32_t n_sb = 0, max_cb = 0;
+  Helper   helper;
   static constexpr uint32_t kStride = 18624;  // int16 per code block (>= SOFTBUFFER_SIZE 18600, multiple of 64)
   DevBuf<int16_t>      llr;                   // [n_sb][max_cb][kStride]
   std::vector<uint8_t> cb_crc;                // [n_sb][max_cb]
@@ -1360,8 +1430,21 @@ int srslte_b200_harq_reset(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* p, u
   // no memset: the next rate de-matching into each block of this soft buffer overwrites instead of accumulating
   std::fill(p->fresh.begin() + (size_t)softbuffer * p->max_cb, p->fresh.begin() + (size_t)(softbuffer + 1) * p->max_cb, 1);
   std::fill(p->cb_crc.begin() + (size_t)softbuffer * p->max_cb, p->cb_crc.begin() + (size_t)(softbuffer + 1) * p->max_cb, 0);
-  std::fill(p->saved.begin() + (size_t)softbuffer * p->max_cb * 768, p->saved.begin() + (size_t)(softbuffer + 1) * p->max_cb * 768, 0);
+  // (the saved payloads need no clearing: they are only read for blocks whose cb_crc flag is set, and written with it)
   p->tb_crc[softbuffer] = 0;
+  return SRSLTE_B200_SUCCESS;
+}
+
+int srslte_b200_harq_reset_many(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* p, const uint32_t* softbuffers, uint32_t n)
+{
+  if (!ctx || !p || (n && !softbuffers && n != p->n_sb)) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t sb = softbuffers ? softbuffers[i] : i;  // NULL: all of them
+    if (sb >= p->n_sb) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+    std::fill(p->fresh.begin() + (size_t)sb * p->max_cb, p->fresh.begin() + (size_t)(sb + 1) * p->max_cb, 1);
+    std::fill(p->cb_crc.begin() + (size_t)sb * p->max_cb, p->cb_crc.begin() + (size_t)(sb + 1) * p->max_cb, 0);
+    p->tb_crc[sb] = 0;
+  }
   return SRSLTE_B200_SUCCESS;
 }
 
@@ -1471,15 +1554,34 @@ static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
     const size_t e_units = sym ? e_total * 4 : e_total;  // int16 units of the staging buffers
     CU(pool->h_e.reserve(e_units));
     CU(pool->d_e.reserve(e_units));
-    for (uint32_t i = 0; i < n_tb; i++) {
-      if (!run[i]) continue;
-      if (sym)
-        std::memcpy(reinterpret_cast<float*>(pool->h_e.p) + 2 * e_base[i], sym[i].symbols,
-                    (size_t)sym[i].nof_symbols * 2 * sizeof(float));
-      else
-        std::memcpy(pool->h_e.p + e_base[i], tbs[i].e_bits, (size_t)tbs[i].nof_e_bits * sizeof(int16_t));
+    // the callers' buffers go into the pinned staging buffer in two halves: the pool's helper thread copies the second
+    // one while this thread copies the first and already starts its transfer
+    auto stage = [&](uint32_t first, uint32_t last) {
+      for (uint32_t i = first; i < last; i++) {
+        if (!run[i]) continue;
+        if (sym)
+          std::memcpy(reinterpret_cast<float*>(pool->h_e.p) + 2 * e_base[i], sym[i].symbols,
+                      (size_t)sym[i].nof_symbols * 2 * sizeof(float));
+        else
+          std::memcpy(pool->h_e.p + e_base[i], tbs[i].e_bits, (size_t)tbs[i].nof_e_bits * sizeof(int16_t));
+      }
+    };
+    uint32_t split = n_tb;  // first TB of the second half
+    if (e_units >= (256u << 10)) {
+      split = 0;
+      while (split < n_tb && (!run[split] || e_base[split] < e_total / 2)) split++;
     }
-    CU(cudaMemcpyAsync(pool->d_e.p, pool->h_e.p, e_units * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    const size_t units_per = sym ? 4 : 1;
+    const size_t cut = split < n_tb ? e_base[split] * units_per : e_units;  // int16 units of the first half
+    if (split < n_tb) pool->helper.run([&, split] { stage(split, n_tb); });
+    stage(0, split);
+    cudaError_t ce = cut ? cudaMemcpyAsync(pool->d_e.p, pool->h_e.p, cut * sizeof(int16_t), cudaMemcpyHostToDevice, st) : cudaSuccess;
+    if (split < n_tb) {
+      pool->helper.wait();  // (before any error return: the helper works on this call's locals)
+      if (ce == cudaSuccess)
+        ce = cudaMemcpyAsync(pool->d_e.p + cut, pool->h_e.p + cut, (e_units - cut) * sizeof(int16_t), cudaMemcpyHostToDevice, st);
+    }
+    CU(ce);
     lap("stage + H2D enqueue");
 
     // ---- rate de-matching with HARQ combining, in place in the pool ----
@@ -1589,30 +1691,39 @@ static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
   // ---- per-TB bookkeeping (sch.c:391-412, 470-488) ----
   std::vector<float> total_it(n_tb, 0.f);
   for (uint32_t j = 0; j < n_cb; j++) total_it[jobs[j].tb] += (float)noi[j];
-  for (uint32_t i = 0; i < n_tb; i++) {
-    if (!run[i]) continue;
-    srslte_b200_tb_t& t   = tbs[i];
-    const CbSegm&     s   = seg[i];
-    uint8_t*          crc = pool->cb_crc.data() + (size_t)t.softbuffer * pool->max_cb;
-    bool              all = true;
-    for (uint32_t cb = 0; cb < s.C && all; cb++) all = crc[cb] != 0;
-    pool->tb_crc[t.softbuffer] = all ? 1 : 0;
-    if (!all) {
-      for (uint32_t cb = 0; cb < s.C; cb++)
-        if (crc[cb]) {
-          const uint32_t K = cb < s.C1 ? s.K1 : s.K2, rlen = s.C == 1 ? K : K - 24;
-          std::memcpy(&pool->saved[((size_t)t.softbuffer * pool->max_cb + cb) * 768], &t.data[cb * rlen / 8], rlen / 8);
-        }
+  auto finish = [&](uint32_t first, uint32_t last) {  // (every TB touches its own soft buffer only)
+    for (uint32_t i = first; i < last; i++) {
+      if (!run[i]) continue;
+      srslte_b200_tb_t& t   = tbs[i];
+      const CbSegm&     s   = seg[i];
+      uint8_t*          crc = pool->cb_crc.data() + (size_t)t.softbuffer * pool->max_cb;
+      bool              all = true;
+      for (uint32_t cb = 0; cb < s.C && all; cb++) all = crc[cb] != 0;
+      pool->tb_crc[t.softbuffer] = all ? 1 : 0;
+      if (!all) {
+        for (uint32_t cb = 0; cb < s.C; cb++)
+          if (crc[cb]) {
+            const uint32_t K = cb < s.C1 ? s.K1 : s.K2, rlen = s.C == 1 ? K : K - 24;
+            std::memcpy(&pool->saved[((size_t)t.softbuffer * pool->max_cb + cb) * 768], &t.data[cb * rlen / 8], rlen / 8);
+          }
+      }
+      t.avg_iterations = total_it[i] / (float)s.C;
+      if (!all) {
+        t.ret = SRSLTE_B200_ERROR;
+        continue;
+      }
+      const uint32_t par_rx = crc24_bytes(kCrc24A, t.data, t.tbs / 8);
+      const uint32_t par_tx = ((uint32_t)t.data[t.tbs / 8] << 16) | ((uint32_t)t.data[t.tbs / 8 + 1] << 8) |
+                              (uint32_t)t.data[t.tbs / 8 + 2];
+      t.ret = (par_rx == par_tx && par_rx) ? SRSLTE_B200_SUCCESS : SRSLTE_B200_ERROR;  // `&& par_rx`: sch.c:481
     }
-    t.avg_iterations = total_it[i] / (float)s.C;
-    if (!all) {
-      t.ret = SRSLTE_B200_ERROR;
-      continue;
-    }
-    const uint32_t par_rx = crc24_bytes(kCrc24A, t.data, t.tbs / 8);
-    const uint32_t par_tx = ((uint32_t)t.data[t.tbs / 8] << 16) | ((uint32_t)t.data[t.tbs / 8 + 1] << 8) |
-                            (uint32_t)t.data[t.tbs / 8 + 2];
-    t.ret = (par_rx == par_tx && par_rx) ? SRSLTE_B200_SUCCESS : SRSLTE_B200_ERROR;  // `&& par_rx`: sch.c:481
+  };
+  if (n_tb >= 32) {  // CRC24A over the decoded transport blocks: half of them on the helper thread
+    pool->helper.run([&] { finish(n_tb / 2, n_tb); });
+    finish(0, n_tb / 2);
+    pool->helper.wait();
+  } else {
+    finish(0, n_tb);
   }
   lap("TB CRC + bookkeeping");
   if (tb_trace) {

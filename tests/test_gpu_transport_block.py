@@ -156,3 +156,37 @@ def test_lazy_harq_reset_equals_zero_and_accumulate(ctx, vec):
     P.port_softbuffer_free(C.byref(sb))
     P.port_tdec_free(dec)
     pool.close()
+
+
+def test_reset_many_and_large_batch_staging(ctx, pkg, vec):
+    """srslte_b200_harq_reset_many == one srslte_b200_harq_reset per soft buffer; a batch large enough for the two-half
+    staging (helper thread) and the split TB CRC gives the same bytes run after run, and a corrupted TB still fails."""
+    import bench_configs as bc
+    rng = np.random.default_rng(12)
+    sizes = [(2216, 4, 4800), (6200, 4, 9600), (14112, 4, 28800), (4584, 4, 7200), (20616, 4, 36000)]
+    descs, pay = [], []
+    for i in range(60):
+        tbs, qm, G = sizes[i % len(sizes)]
+        p, e = bc._make_tb(vec, rng, tbs, qm, G, 0.35, 400)
+        pay.append(p)
+        descs.append(dict(tbs=tbs, qm=qm, rv=0, e_bits=e, softbuffer=i))
+    descs[7]["e_bits"] = (-descs[7]["e_bits"]).astype(np.int16)          # all bits flipped: cannot pass its CRCs
+    pool = ctx.harq_pool(60, 13)
+    L = pkg.lib()
+    first = ctx.decode_tb_batch(pool, descs, 10)
+    for i, (ret, data, _) in enumerate(first):
+        if i == 7:
+            assert ret != 0
+        else:
+            assert ret == 0 and np.array_equal(np.unpackbits(data[: descs[i]["tbs"] // 8]), pay[i]), i
+    # without a reset the good blocks are already decoded; after reset_many everything is decoded again
+    assert L.srslte_b200_harq_reset_many(ctx._h, pool._p, None, 60) == 0
+    again = ctx.decode_tb_batch(pool, descs, 10)
+    for a, b in zip(first, again):
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and a[2] == b[2]
+    idx = np.array([3, 9, 11], dtype=np.uint32)
+    assert L.srslte_b200_harq_reset_many(ctx._h, pool._p, idx.ctypes.data_as(C.c_void_p), 3) == 0
+    assert all(pool.cb_crc(int(i), 1)[0] == 0 for i in idx) and pool.cb_crc(4, 1)[0] == 1
+    bad = np.array([60], dtype=np.uint32)
+    assert L.srslte_b200_harq_reset_many(ctx._h, pool._p, bad.ctypes.data_as(C.c_void_p), 1) != 0
+    pool.close()
