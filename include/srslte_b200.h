@@ -145,6 +145,12 @@ SRSLTE_B200_API int  srslte_b200_group_tdec_batch_host(srslte_b200_group_t* grou
  * at the same time, `reps` times, no kernels; gbs_per_device[i] = GB/s seen by device i while all of them copy.   */
 SRSLTE_B200_API int  srslte_b200_group_h2d_probe(srslte_b200_group_t* group, const void* host, size_t bytes_per_device,
                                                  uint32_t reps, double* gbs_per_device);
+/* Shares of a batch.  The host-facing entry is bound by the host-to-device copies, and the PCIe side of a box need not
+ * be symmetric (8 x B200: 24 GB/s per device on one half, 35 on the other when all copy, profiles/r02_multi_gpu.txt).
+ * set_weights: device i takes weights[i] / sum of a batch (NULL: equal shares, the default); calibrate: measure the
+ * devices' concurrent copy rates (a few ms) and use them as weights (gbs_per_device, nullable, receives them).      */
+SRSLTE_B200_API int  srslte_b200_group_set_weights(srslte_b200_group_t* group, const double* weights);
+SRSLTE_B200_API int  srslte_b200_group_calibrate(srslte_b200_group_t* group, double* gbs_per_device);
 /* the same for one context (bench.py under torchrun: every rank probes after a barrier)                            */
 SRSLTE_B200_API int  srslte_b200_h2d_probe(srslte_b200_ctx_t* ctx, const void* host, size_t bytes, uint32_t reps, double* gbs);
 

@@ -87,6 +87,7 @@ EXPORTS = [
     "srslte_b200_uci_q_prime_ri_ack", "srslte_b200_uci_q_prime_cqi",
     "srslte_b200_group_create", "srslte_b200_group_destroy", "srslte_b200_group_size", "srslte_b200_group_ctx",
     "srslte_b200_group_tdec_batch_host", "srslte_b200_group_h2d_probe", "srslte_b200_h2d_probe",
+    "srslte_b200_group_set_weights", "srslte_b200_group_calibrate",
 ]
 
 _lib = None
@@ -156,6 +157,8 @@ def lib():
     L.srslte_b200_group_tdec_batch_host.argtypes = [vp, C.POINTER(TdecBatch), vp, vp, vp, vp]
     L.srslte_b200_group_h2d_probe.argtypes = [vp, vp, C.c_size_t, u32, C.POINTER(C.c_double)]
     L.srslte_b200_h2d_probe.argtypes = [vp, vp, C.c_size_t, u32, C.POINTER(C.c_double)]
+    L.srslte_b200_group_set_weights.argtypes = [vp, C.POINTER(C.c_double)]
+    L.srslte_b200_group_calibrate.argtypes = [vp, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -206,6 +209,20 @@ class Group:
         if rc:
             raise B200Error(f"srslte_b200_group_tdec_batch_host -> {rc}")
         return out, nit, ok
+
+    def set_weights(self, weights=None):
+        """share of a batch per device (None: equal shares)"""
+        arr = None if weights is None else (C.c_double * len(self))(*weights)
+        if self._L.srslte_b200_group_set_weights(self._h, arr):
+            raise B200Error("srslte_b200_group_set_weights: bad weights")
+
+    def calibrate(self):
+        """measure the devices' concurrent host-to-device rates and use them as shares; returns GB/s per device"""
+        g = (C.c_double * len(self))()
+        rc = self._L.srslte_b200_group_calibrate(self._h, g)
+        if rc:
+            raise B200Error(f"srslte_b200_group_calibrate -> {rc}")
+        return [float(x) for x in g]
 
     def h2d_probe(self, host_ptr, bytes_per_device, reps=4):
         """GB/s per device while ALL devices of the group copy from pinned host memory at the same time."""

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <cmath>
 #include <atomic>
 #include <condition_variable>
 #include <functional>
@@ -725,6 +726,7 @@ int srslte_b200_ctx_tier_counts(srslte_b200_ctx_t* ctx, uint64_t counts[4])
 // ---- several devices from one process -------------------------------------------------------------------------
 struct srslte_b200_group {
   std::vector<srslte_b200_ctx*> ctx;
+  std::vector<double>           weight;  // share of a batch each device takes (equal unless calibrated / set)
 };
 
 namespace {
@@ -794,6 +796,7 @@ int srslte_b200_group_create(srslte_b200_group_t** out, const int* devices, uint
     }
     g->ctx.push_back(c);
   }
+  g->weight.assign(n_devices, 1.0);
   *out = g;
   return SRSLTE_B200_SUCCESS;
 }
@@ -818,8 +821,19 @@ int srslte_b200_group_tdec_batch_host(srslte_b200_group_t* g, const srslte_b200_
   if (!llr || !out) return SRSLTE_B200_ERROR_INVALID_INPUTS;
   std::vector<int>         rc(world, SRSLTE_B200_SUCCESS);
   std::vector<std::thread> th;
+  // contiguous shards in proportion to the devices' weights (equal weights: block i -> device floor(i * world / n))
+  std::vector<uint32_t> cut(world + 1, 0);
+  {
+    double total = 0, acc = 0;
+    for (double w : g->weight) total += w;
+    for (uint32_t r = 0; r < world; r++) {
+      acc += g->weight[r];
+      cut[r + 1] = r + 1 == world ? b->n_cb : (uint32_t)std::min<double>(b->n_cb, std::floor((double)b->n_cb * acc / total + 1e-9));
+      if (cut[r + 1] < cut[r]) cut[r + 1] = cut[r];
+    }
+  }
   for (uint32_t r = 0; r < world; r++) {
-    const uint32_t first = (uint32_t)((uint64_t)b->n_cb * r / world), last = (uint32_t)((uint64_t)b->n_cb * (r + 1) / world);
+    const uint32_t first = cut[r], last = cut[r + 1];
     if (first == last) continue;
     th.emplace_back([=, &rc] {
       bind_thread_near_device(g->ctx[r]->device);
@@ -852,6 +866,38 @@ int srslte_b200_group_h2d_probe(srslte_b200_group_t* g, const void* host, size_t
   for (auto& t : th) t.join();
   for (uint32_t r = 0; r < world; r++)
     if (rc[r] != SRSLTE_B200_SUCCESS) return rc[r];
+  return SRSLTE_B200_SUCCESS;
+}
+
+int srslte_b200_group_set_weights(srslte_b200_group_t* g, const double* weights)
+{
+  if (!g || g->ctx.empty()) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  if (!weights) {
+    g->weight.assign(g->ctx.size(), 1.0);
+    return SRSLTE_B200_SUCCESS;
+  }
+  double total = 0;
+  for (size_t i = 0; i < g->ctx.size(); i++) {
+    if (!(weights[i] >= 0)) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+    total += weights[i];
+  }
+  if (!(total > 0)) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  g->weight.assign(weights, weights + g->ctx.size());
+  return SRSLTE_B200_SUCCESS;
+}
+
+int srslte_b200_group_calibrate(srslte_b200_group_t* g, double* gbs_per_device)
+{
+  if (!g || g->ctx.empty()) return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  const size_t per = 32u << 20;
+  void*        host = srslte_b200_host_alloc(per * g->ctx.size());
+  if (!host) return SRSLTE_B200_ERROR;
+  std::vector<double> gbs(g->ctx.size(), 0.0);
+  const int rc = srslte_b200_group_h2d_probe(g, host, per, 3, gbs.data());
+  srslte_b200_host_free(host);
+  if (rc != SRSLTE_B200_SUCCESS) return rc;
+  g->weight = gbs;
+  if (gbs_per_device) std::copy(gbs.begin(), gbs.end(), gbs_per_device);
   return SRSLTE_B200_SUCCESS;
 }
 

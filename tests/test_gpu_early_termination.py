@@ -192,6 +192,14 @@ def test_group_entry_single_process(pkg, vec):
         got = g.tdec_batch_host(llr, K, 6, crc_mode=pkg.CRC_24B)
         for a, b_ in zip(got, want):
             assert np.array_equal(a, b_), nd
+        g.set_weights([1.0 + 2.0 * i for i in range(nd)])       # unequal shares: same results
+        got = g.tdec_batch_host(llr, K, 6, crc_mode=pkg.CRC_24B)
+        for a, b_ in zip(got, want):
+            assert np.array_equal(a, b_), nd
+        assert len(g.calibrate()) == nd
+        got = g.tdec_batch_host(llr, K, 6, crc_mode=pkg.CRC_24B)
+        for a, b_ in zip(got, want):
+            assert np.array_equal(a, b_), nd
         pin = pkg.PinnedArray((nd, 8 << 20), np.uint8)
         gbs = g.h2d_probe(pin.array.ctypes.data, 8 << 20, reps=4)
         assert len(gbs) == nd and all(x > 1.0 for x in gbs), gbs
