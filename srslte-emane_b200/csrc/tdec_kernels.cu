@@ -1639,9 +1639,10 @@ __device__ __forceinline__ HalfResult half_fast2(const WinCtx<W>& c, bool dec2, 
 // staging buffers share the warp's shared memory with the checkpoints of the main path, so every half iteration sets
 // them up itself: no a-priori input -> the A part reads as zero; DEC2 has no separate systematic input (x = E) -> the
 // sys part reads as zero (its copies leave that part alone), so both decoders run the same branch-free code.
-template <int W>
-__device__ __noinline__ HalfResult half_general(const WinCtx<W> c, bool dec2, int G, int tier, bool any_crc, Pipe* pp)
+template <int W, bool CRCOK = true>
+__device__ __noinline__ HalfResult half_general(const WinCtx<W> c, bool dec2, int G, int tier, bool any_crc_, Pipe* pp)
 {
+  const bool any_crc = CRCOK && any_crc_;  // (kernels for launches without CRC carry no copy of the CRC variants)
   Pipe pipe = *pp;
   if (c.noap)
     for (int i = c.lane; i < kStages * 64; i += 32)
@@ -1811,7 +1812,9 @@ __device__ __forceinline__ uint32_t group_max(uint32_t v)
 // One CTA per SM.  The CTA takes kWarps consecutive work items at a time; the host pads the item list so that
 // they all have the same K (items with count 0 are fillers): the QPP tables are built once per CTA round, and the
 // warps run the same phase of the same code at the same time (one copy of the hot loops in the instruction cache).
-template <int W, bool TRK2>
+// NOCRC: the launch checks no CRC (srslte_tdec_run_all batches): the kernel carries no copy of the CRC variants of its
+// loops (register allocation and the instruction cache see a smaller kernel).
+template <int W, bool TRK2, bool NOCRC = false>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const TdecLaunch a)
 {
   constexpr int WH  = W / 2;
@@ -1890,7 +1893,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
       int      amax = 0, emax = 0;  // max |A|, max |E| over the code block
       const uint32_t crc_mode = a.crc_mode_cb ? a.crc_mode_cb[cb] : a.crc_mode;
       const int      which    = crc_mode == CRC_24A ? 0 : 1;
-      const bool     any_crc  = __any_sync(0xFFFFFFFFu, crc_mode != CRC_NONE);
+      const bool     any_crc  = NOCRC ? false : __any_sync(0xFFFFFFFFu, crc_mode != CRC_NONE);
       const bool     v2       = (c.L & 3u) == 0 && (a.force_exact & 8u) == 0;  // the main fast path takes this block size
       // CRC modes: this thread's window pair in the tables of the block's polynomial ([dir][row][window])
       const uint32_t* Rblk = any_crc ? a.crc_pos + a.crc_pos_off[wi.kidx] + (size_t)which * 2 * c.K + 2 * t : nullptr;
@@ -1928,7 +1931,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
           fast_ok = __all_sync(0xFFFFFFFFu, r.proven || done);
 #ifndef B200_V2ONLY
         } else if (pure || stat || trk) {
-          r       = half_general<W>(c, dec2, G, pure ? 0 : stat ? 1 : 2, any_crc, &pipe);
+          r       = half_general<W, !NOCRC>(c, dec2, G, pure ? 0 : stat ? 1 : 2, any_crc, &pipe);
           fast_ok = (pure || stat) ? true : __all_sync(0xFFFFFFFFu, r.proven || done);
 #endif
         }
@@ -2750,11 +2753,13 @@ cudaError_t tdec_geometry(int W, int device, TdecGeometry* g)
     e = cudaFuncSetAttribute(tdec_win_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tdec_win_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tdec_win_dyn_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tdec_win_kernel<16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tdec_win_kernel<16, false>, kThreads, g->smem);
   } else {
     e = cudaFuncSetAttribute(tdec_win_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tdec_win_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tdec_win_dyn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tdec_win_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tdec_win_kernel<8, false>, kThreads, g->smem);
   }
   if (e != cudaSuccess) return e;
@@ -2790,6 +2795,10 @@ cudaError_t tdec_launch(int W, const TdecGeometry& g, const TdecLaunch& a, cudaS
       tdec_win_dyn_kernel<16><<<dblocks, g.threads, g.smem, s>>>(a);
     else
       tdec_win_dyn_kernel<8><<<dblocks, g.threads, g.smem, s>>>(a);
+  } else if (W == 16 && !trk2 && a.crc_mode == CRC_NONE && !a.crc_mode_cb && (a.force_exact & 128u) == 0) {
+    tdec_win_kernel<16, false, true><<<blocks, g.threads, g.smem, s>>>(a);
+  } else if (W == 8 && !trk2 && a.crc_mode == CRC_NONE && !a.crc_mode_cb && (a.force_exact & 128u) == 0) {
+    tdec_win_kernel<8, false, true><<<blocks, g.threads, g.smem, s>>>(a);
   } else if (W == 16 && trk2)
     tdec_win_kernel<16, true><<<blocks, g.threads, g.smem, s>>>(a);
   else if (W == 16)
