@@ -35,8 +35,8 @@ LLR_SCALE = 100.0
 IN_LEN = 3 * K + 12
 # DRAM bytes of the decode kernel per code block, from the committed ncu capture of this workload (profiles/r02*_summary.txt:
 # dram__bytes_read.sum + dram__bytes_write.sum of one 65 536-block launch / 65 536); NOT measured by bench.py itself
-NCU_DRAM_BYTES_PER_BLOCK = 250.0e3
-NCU_DRAM_SOURCE = "profiles/r02g_summary.txt (ncu --set full: 12.99 GB read + 3.40 GB written per 65536-block launch)"
+NCU_DRAM_BYTES_PER_BLOCK = 249.2e3
+NCU_DRAM_SOURCE = "profiles/r02k_summary.txt (ncu --set full: 12.94 GB read + 3.39 GB written per 65536-block launch)"
 INT_PEAK_THREAD_INSTR_PER_CLK_SM = 64.0   # measured: profiles/r01_int_peak*.txt (VIADD.16x2 / VIMNMX.S16x2), ONE pipe
 TWO_PIPE_THREAD_INSTR_PER_CLK_SM = 117.6  # measured: profiles/r01_pipe_mix.txt, "vaddmax + vadd" (both pipes busy)
 
@@ -419,7 +419,7 @@ def main():
                 "e2e_frac_of_h2d_ceiling": (ne * IN_LEN * 2 / (max(e2e_ranks) * 1e-3) / 1e9) / max(min(h2d_ranks), 1e-9)},
         "gpu_launches": launches,
         "roofline": {
-            "bound": "int_alu", "kernel": "tdec_win_kernel<16>", "achieved": achieved_tops, "peak": peak_tops,
+            "bound": "int_alu", "kernel": "tdec_win_kernel<16, false, true> (launches without CRC)", "achieved": achieved_tops, "peak": peak_tops,
             "unit": "Tops/s (int16 lane-ops)", "frac": achieved_tops / peak_tops,
             "ops_per_block": int_ops_per_block(), "ms_per_launch": dec_ms_per_launch,
             "peak_source": f"measured {INT_PEAK_THREAD_INSTR_PER_CLK_SM:g} packed-int16x2 thread-instr/clk/SM "
