@@ -133,6 +133,16 @@ SRSLTE_API int  srslte_rm_turbo_rx_lut_8bit(int8_t* input, int8_t* output, uint3
 
 /* ---- sch.c:429-500 decode_tb, with the host-resident soft buffer the MAC owns ---- */
 /* Returns 0 / -1 (CRC failure) / -2 (bad arguments) like decode_tb; *avg_iterations = q->avg_iterations.   */
+/* ---- softbuffer.h:52-66 (softbuffer.c:40-150): the receive soft buffer.  Same struct, same calls; a buffer made by
+ * srslte_softbuffer_rx_init keeps its LLRs in a device pool, a reset is a flag, and
+ * srslte_b200_sch_decode_tb / srslte_dlsch_decode2 no longer move the LLRs over PCIe.  The reference's softbuffer.c is
+ * compiled with these five names defined out of the way (its transmit-side functions stay), see oracle/Makefile.   */
+SRSLTE_API int  srslte_softbuffer_rx_init(srslte_softbuffer_rx_t* q, uint32_t nof_prb);
+SRSLTE_API void srslte_softbuffer_rx_reset(srslte_softbuffer_rx_t* q);
+SRSLTE_API void srslte_softbuffer_rx_reset_tbs(srslte_softbuffer_rx_t* q, uint32_t tbs);
+SRSLTE_API void srslte_softbuffer_rx_reset_cb(srslte_softbuffer_rx_t* q, uint32_t nof_cb);
+SRSLTE_API void srslte_softbuffer_rx_free(srslte_softbuffer_rx_t* q);
+
 SRSLTE_API int srslte_b200_sch_decode_tb(srslte_softbuffer_rx_t* softbuffer, uint32_t tbs, uint32_t Qm, uint32_t rv,
                                          uint32_t nof_e_bits, int16_t* e_bits, uint8_t* data, uint32_t max_iterations,
                                          float* avg_iterations);

@@ -247,19 +247,35 @@ void build_rounds(srslte_b200_ctx* ctx, Schedule& s)
       s.epoch_items[ri]++;
     }
     for (uint32_t i = 0; i < items.size(); i += per) R.push_back(make_uint2(i, per));
+    // The last, partial wave: its items are re-cut into one round per SM, as even as the block-size boundaries allow
+    // (rounds must share K), so that no SM idles while others decode full rounds (a warp that shares its SM with fewer
+    // warps runs faster).
     const uint32_t G = (uint32_t)std::max(1, ctx->sm_count * tdec_ctas_per_sm());
     const uint32_t last = (uint32_t)(R.size() % G);
-    const uint32_t q = last ? std::min(4u, G / last) : 1u;
-    if (q >= 2) {
-      std::vector<uint2> tail(R.end() - last, R.end());
+    if (last && last < G) {
+      const uint32_t first_item = R[R.size() - last].x;
       R.resize(R.size() - last);
-      for (const uint2& r : tail)
-        for (uint32_t j = 0; j < q; j++) {
-          const uint2 sub = make_uint2(r.x + j * (per / q), per / q);
-          bool any = false;
-          for (uint32_t k = 0; k < sub.y; k++) any = any || items[sub.x + k].count != 0;
-          if (any) R.push_back(sub);
-        }
+      std::vector<uint32_t> real;  // the items of the tail that hold blocks
+      for (uint32_t i = first_item; i < items.size(); i++)
+        if (items[i].count) real.push_back(i);
+      const uint32_t n_real = (uint32_t)real.size();
+      const uint32_t want = std::min(G, n_real);  // rounds to cut them into
+      uint32_t pos = 0;
+      for (uint32_t r = 0; r < want && pos < n_real; r++) {
+        uint32_t take = (n_real - pos + (want - r) - 1) / (want - r);  // ceil of what is left over the rounds left
+        take = std::min(take, per);
+        // consecutive items of one K only
+        uint32_t len = 1;
+        while (len < take && pos + len < n_real && real[pos + len] == real[pos] + len && items[real[pos + len]].K == items[real[pos]].K) len++;
+        R.push_back(make_uint2(real[pos], len));
+        pos += len;
+      }
+      while (pos < n_real) {  // (K boundaries can leave more pieces than SMs)
+        uint32_t len = 1;
+        while (len < per && pos + len < n_real && real[pos + len] == real[pos] + len && items[real[pos + len]].K == items[real[pos]].K) len++;
+        R.push_back(make_uint2(real[pos], len));
+        pos += len;
+      }
     }
   }
 }
@@ -1842,6 +1858,23 @@ int compat_device()
 std::mutex           g_mu;
 srslte_b200_ctx*     g_ctx  = nullptr;
 srslte_b200_harq_pool* g_pool = nullptr;  // one soft buffer of 13+ blocks, grown on demand
+// soft buffers created by srslte_softbuffer_rx_init below: host struct -> slot of a device pool (pools of kSbPerPool slots)
+struct SbSlot {
+  srslte_b200_harq_pool* pool;
+  uint32_t               idx;
+};
+constexpr uint32_t               kSbPerPool = 32, kSbMaxCb = 16;  // 97896 / 6120 + 1 blocks at 100-110 PRB
+std::map<const void*, SbSlot>    g_sb_map;
+std::vector<SbSlot>              g_sb_free;
+// 36.213 Table 7.1.7.2.1-1, row I_TBS = 33 (what srslte_ra_tbs_from_idx(33, nof_prb) returns, softbuffer.c:44), N_PRB = 1..110
+const uint32_t kTbsItbs33[110] = {
+    968, 1992, 2984, 4008, 4968, 5992, 6968, 7992, 8760, 9912, 10680, 11832, 12960, 13536, 14688, 15840, 16992, 17568, 19080,
+    19848, 20616, 21384, 22920, 23688, 24496, 25456, 26416, 27376, 28336, 29296, 30576, 31704, 32856, 34008, 35160, 35160, 36696,
+    37888, 39232, 39232, 40576, 40576, 42368, 43816, 43816, 45352, 46888, 46888, 48936, 48936, 51024, 51024, 52752, 52752, 55056,
+    55056, 57336, 57336, 59256, 59256, 59256, 61664, 61664, 63776, 63776, 63776, 66592, 66592, 68808, 68808, 71112, 71112, 71112,
+    73712, 75376, 76208, 76208, 76208, 78704, 78704, 81176, 81176, 81176, 81176, 84760, 84760, 84760, 87936, 87936, 87936, 90816,
+    90816, 90816, 93800, 93800, 93800, 93800, 97896, 97896, 97896, 97896, 97896, 97896, 97896, 97896, 97896, 97896, 97896, 97896,
+    97896};
 DevBuf<int16_t>      g_d_e, g_d_work;
 
 srslte_b200_ctx* global_ctx()
@@ -2053,6 +2086,107 @@ int srslte_rm_turbo_rx_lut_8bit(int8_t*, int8_t*, uint32_t, uint32_t, uint32_t)
   return SRSLTE_ERROR;
 }
 
+// ---- fec/softbuffer.h:52-66 (softbuffer.c:40-150): the receive soft buffer, device resident ----------------------------
+// The host struct keeps the reference's layout and host arrays (callers read max_cb, cb_crc, tb_crc, data); the LLRs live
+// in a slot of a device pool and a reset is a flag there.  The host buffer_f arrays are allocated but not maintained.
+// A struct that was not made by srslte_softbuffer_rx_init here (copied by value, hand made) is handled like the
+// reference does, and srslte_b200_sch_decode_tb mirrors it to the device per call.
+int srslte_softbuffer_rx_init(srslte_softbuffer_rx_t* q, uint32_t nof_prb)
+{
+  if (!q) return SRSLTE_ERROR_INVALID_INPUTS;
+  std::memset(q, 0, sizeof(*q));
+  if (nof_prb < 1 || nof_prb > 110) return SRSLTE_ERROR;
+  const uint32_t max_cb = kTbsItbs33[nof_prb - 1] / (SRSLTE_TCOD_MAX_LEN_CB - 24) + 1;
+  std::lock_guard<std::mutex> lk(g_mu);
+  srslte_b200_ctx* ctx = global_ctx();
+  if (!ctx) return SRSLTE_ERROR;  // no GPU, no CPU path
+  if (g_sb_free.empty()) {
+    srslte_b200_harq_pool* pool = nullptr;
+    if (srslte_b200_harq_pool_create(ctx, kSbPerPool, kSbMaxCb, &pool)) return SRSLTE_ERROR;
+    for (uint32_t i = kSbPerPool; i-- > 0;) g_sb_free.push_back({pool, i});
+  }
+  q->buffer_f = static_cast<int16_t**>(calloc(max_cb, sizeof(int16_t*)));
+  q->data     = static_cast<uint8_t**>(calloc(max_cb, sizeof(uint8_t*)));
+  q->cb_crc   = static_cast<bool*>(calloc(max_cb, sizeof(bool)));
+  bool ok = q->buffer_f && q->data && q->cb_crc;
+  for (uint32_t i = 0; ok && i < max_cb; i++) {
+    q->buffer_f[i] = static_cast<int16_t*>(calloc(SOFTBUFFER_SIZE, sizeof(int16_t)));
+    q->data[i]     = static_cast<uint8_t*>(calloc(6144 / 8, 1));
+    ok = q->buffer_f[i] && q->data[i];
+  }
+  q->max_cb = max_cb;
+  if (!ok) {
+    for (uint32_t i = 0; q->buffer_f && i < max_cb; i++) free(q->buffer_f[i]);
+    for (uint32_t i = 0; q->data && i < max_cb; i++) free(q->data[i]);
+    free(q->buffer_f); free(q->data); free(q->cb_crc);
+    std::memset(q, 0, sizeof(*q));
+    return SRSLTE_ERROR;
+  }
+  const SbSlot s = g_sb_free.back();
+  g_sb_free.pop_back();
+  g_sb_map[q] = s;
+  srslte_b200_harq_reset(ctx, s.pool, s.idx);
+  return SRSLTE_SUCCESS;
+}
+
+void srslte_softbuffer_rx_free(srslte_softbuffer_rx_t* q)
+{
+  if (!q) return;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_sb_map.find(q);
+    if (it != g_sb_map.end()) {
+      g_sb_free.push_back(it->second);
+      g_sb_map.erase(it);
+    }
+  }
+  if (q->buffer_f)
+    for (uint32_t i = 0; i < q->max_cb; i++) free(q->buffer_f[i]);
+  if (q->data)
+    for (uint32_t i = 0; i < q->max_cb; i++) free(q->data[i]);
+  free(q->buffer_f);
+  free(q->data);
+  free(q->cb_crc);
+  std::memset(q, 0, sizeof(*q));
+}
+
+void srslte_softbuffer_rx_reset_cb(srslte_softbuffer_rx_t* q, uint32_t nof_cb)
+{
+  if (!q) return;
+  if (nof_cb > q->max_cb) nof_cb = q->max_cb;
+  bool device = false;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_sb_map.find(q);
+    if (it != g_sb_map.end()) {
+      // softbuffer.c:123-141: the first nof_cb LLR buffers and payloads are cleared, ALL the CRC flags
+      srslte_b200_harq_pool* pool = it->second.pool;
+      const size_t           base = (size_t)it->second.idx * pool->max_cb;
+      for (uint32_t i = 0; i < nof_cb && i < pool->max_cb; i++) pool->fresh[base + i] = 1;
+      std::fill(pool->cb_crc.begin() + base, pool->cb_crc.begin() + base + pool->max_cb, 0);
+      pool->tb_crc[it->second.idx] = 0;
+      device = true;
+    }
+  }
+  if (q->buffer_f)
+    for (uint32_t i = 0; i < nof_cb; i++) {
+      if (!device && q->buffer_f[i]) std::memset(q->buffer_f[i], 0, SOFTBUFFER_SIZE * sizeof(int16_t));
+      if (q->data && q->data[i]) std::memset(q->data[i], 0, 6144 / 8);
+    }
+  if (q->cb_crc) std::memset(q->cb_crc, 0, sizeof(bool) * q->max_cb);
+  q->tb_crc = false;
+}
+
+void srslte_softbuffer_rx_reset_tbs(srslte_softbuffer_rx_t* q, uint32_t tbs)
+{
+  srslte_softbuffer_rx_reset_cb(q, (tbs + 24) / (SRSLTE_TCOD_MAX_LEN_CB - 24) + 1);
+}
+
+void srslte_softbuffer_rx_reset(srslte_softbuffer_rx_t* q)
+{
+  if (q) srslte_softbuffer_rx_reset_cb(q, q->max_cb);
+}
+
 int srslte_b200_sch_decode_tb(srslte_softbuffer_rx_t* sb, uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits,
                               int16_t* e_bits, uint8_t* data, uint32_t max_iterations, float* avg_iterations)
 {
@@ -2074,6 +2208,31 @@ int srslte_b200_sch_decode_tb(srslte_softbuffer_rx_t* sb, uint32_t tbs, uint32_t
   std::lock_guard<std::mutex> lk(g_mu);
   srslte_b200_ctx* ctx = global_ctx();
   if (!ctx) return SRSLTE_ERROR;
+  // A soft buffer made by this library's srslte_softbuffer_rx_init has its LLRs, flags and saved payloads in a slot of a
+  // device pool: nothing is mirrored, the host struct only receives the flags and payloads the unchanged
+  // callers read (cb_crc, tb_crc, data).
+  {
+    auto it = g_sb_map.find(sb);
+    if (it != g_sb_map.end() && seg.C <= it->second.pool->max_cb) {
+      srslte_b200_harq_pool* pool = it->second.pool;
+      const uint32_t         slot = it->second.idx;
+      srslte_b200_tb_t t{};
+      t.tbs = tbs; t.qm = Qm; t.rv = rv; t.nof_e_bits = nof_e_bits; t.softbuffer = slot; t.e_bits = e_bits; t.data = data;
+      if (srslte_b200_decode_tb_batch(ctx, pool, &t, 1, max_iterations)) {
+        fprintf(stderr, "srslte_b200: %s\n", srslte_b200_last_error(ctx));
+        return SRSLTE_ERROR;
+      }
+      const uint8_t* crc = pool->cb_crc.data() + (size_t)slot * pool->max_cb;
+      for (uint32_t cb = 0; cb < seg.C; cb++) {
+        sb->cb_crc[cb] = crc[cb] != 0;
+        if (!pool->tb_crc[slot] && crc[cb])
+          std::memcpy(sb->data[cb], &pool->saved[((size_t)slot * pool->max_cb + cb) * 768], 768);
+      }
+      sb->tb_crc = pool->tb_crc[slot] != 0;
+      if (avg_iterations) *avg_iterations = t.avg_iterations;
+      return t.ret;
+    }
+  }
   if (!g_pool || g_pool->max_cb < seg.C) {
     if (g_pool) srslte_b200_harq_pool_destroy(ctx, g_pool);
     g_pool = nullptr;

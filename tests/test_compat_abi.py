@@ -82,7 +82,8 @@ def test_compat_symbols_are_exported(pkg):
                  "srslte_tdec_iteration_8bit", "srslte_tdec_run_all_8bit", "srslte_rm_turbo_gentables",
                  "srslte_rm_turbo_free_tables", "srslte_rm_turbo_rx_lut", "srslte_rm_turbo_rx_lut_",
                  "srslte_rm_turbo_rx_lut_8bit", "srslte_b200_sch_decode_tb", "srslte_dlsch_decode",
-                 "srslte_dlsch_decode2"):
+                 "srslte_dlsch_decode2", "srslte_softbuffer_rx_init", "srslte_softbuffer_rx_free", "srslte_softbuffer_rx_reset",
+                 "srslte_softbuffer_rx_reset_tbs", "srslte_softbuffer_rx_reset_cb"):
         assert hasattr(L, name), name
     # host-only entry points work without a GPU
     assert [L.srslte_tdec_autoimp_get_subblocks(k) for k in (40, 408, 816, 6144)] == [0, 8, 16, 16]

@@ -144,3 +144,57 @@ def test_decode_tb_with_host_softbuffer(L, golden):
                     assert np.array_equal(keep[0][cb][: 3 * K + 12], want_llr[: 3 * K + 12])
         P.port_tdec_free(dec)
         P.port_softbuffer_free(C.byref(psb))
+
+
+def test_device_resident_softbuffer_api(L, golden):
+    """softbuffer.h:52-66 through this library: srslte_softbuffer_rx_init / reset_tbs / reset_cb / free keep the HARQ state
+    on the device.  rv 0 then rv 2 on the same buffer against the reference's srslte_dlsch_decode2 goldens,
+    then a reset and rv 0 again (must repeat the first result: nothing left of the combined LLRs, flags cleared)."""
+    L.srslte_b200_sch_decode_tb.argtypes = [C.POINTER(SoftbufferRx), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                            _i16p, _u8p, C.c_uint32, C.POINTER(C.c_float)]
+    for f in ("srslte_softbuffer_rx_reset", "srslte_softbuffer_rx_free"):
+        getattr(L, f).argtypes = [C.POINTER(SoftbufferRx)]
+        getattr(L, f).restype = None
+    L.srslte_softbuffer_rx_init.argtypes = [C.POINTER(SoftbufferRx), C.c_uint32]
+    L.srslte_softbuffer_rx_reset_tbs.argtypes = [C.POINTER(SoftbufferRx), C.c_uint32]
+    L.srslte_softbuffer_rx_reset_tbs.restype = None
+    L.srslte_softbuffer_rx_reset_cb.argtypes = [C.POINTER(SoftbufferRx), C.c_uint32]
+    L.srslte_softbuffer_rx_reset_cb.restype = None
+    g = golden["tb_vectors"]
+    P = ol.port()
+    sbs = []
+    for nprb in (100, 6, 110, 50):
+        sb = SoftbufferRx()
+        assert L.srslte_softbuffer_rx_init(C.byref(sb), nprb) == 0
+        assert sb.max_cb == {100: 16, 6: 1, 110: 16, 50: 8}[nprb]
+        sbs.append(sb)
+    assert L.srslte_softbuffer_rx_init(C.byref(SoftbufferRx()), 0) != 0
+    sb = sbs[0]
+    for c in sorted({k.split("_")[0] for k in g if k.startswith("t")}, key=lambda s: int(s[1:])):
+        tbs, qm, G, max_it = (int(x) for x in g[f"{c}_par"])
+        seg = ol.PortCbsegm()
+        P.port_cbsegm(C.byref(seg), tbs)
+        L.srslte_softbuffer_rx_reset_tbs(C.byref(sb), tbs)
+        first = None
+        for rv in (0, 2, -1):
+            if rv < 0:                        # new transmission of the same TB: reset, rv 0 again
+                L.srslte_softbuffer_rx_reset_cb(C.byref(sb), seg.C)
+                assert not any(sb.cb_crc[i] for i in range(sb.max_cb)) and not sb.tb_crc
+                rv = 0
+            llr = g[f"{c}_rv{rv}_llr"]
+            out = np.zeros(tbs // 8 + 8, np.uint8)
+            avg = C.c_float()
+            rc = L.srslte_b200_sch_decode_tb(C.byref(sb), tbs, qm, rv, G, llr.copy(), out, max_it, C.byref(avg))
+            if first is not None and rv == 0:
+                assert (rc, avg.value) == first[:2] and np.array_equal(out, first[2]), c
+                continue
+            want_rc, want_its = (int(x) for x in g[f"{c}_rv{rv}_res"])
+            assert rc == want_rc and round(avg.value * seg.C) == want_its, (c, rv)
+            assert np.array_equal(out[: tbs // 8 + 3], g[f"{c}_rv{rv}_out"]), (c, rv)
+            assert [bool(sb.cb_crc[i]) for i in range(seg.C)] == [bool(x) for x in g[f"{c}_rv{rv}_cbcrc"]]
+            assert bool(sb.tb_crc) == all(bool(sb.cb_crc[i]) for i in range(seg.C))      # sch.c:396-399
+            if rv == 0:
+                first = (rc, avg.value, out.copy())
+    for sb in sbs:
+        L.srslte_softbuffer_rx_free(C.byref(sb))
+        assert sb.max_cb == 0
