@@ -1628,16 +1628,46 @@ static int decode_tb_core(srslte_b200_ctx_t* ctx, srslte_b200_harq_pool_t* pool,
           std::memcpy(pool->h_e.p + e_base[i], tbs[i].e_bits, (size_t)tbs[i].nof_e_bits * sizeof(int16_t));
       }
     };
+    // Large transport blocks that already sit in pinned host memory (cudaHostAlloc / cudaHostRegister by the caller,
+    // e.g. srslte_b200_host_alloc) are copied from where they are, one transfer each: no staging copy at all.
+    bool direct = true;
+    for (uint32_t i = 0; i < n_tb && direct; i++) {
+      if (!run[i]) continue;
+      const void*  p     = sym ? static_cast<const void*>(sym[i].symbols) : static_cast<const void*>(tbs[i].e_bits);
+      const size_t bytes = sym ? (size_t)sym[i].nof_symbols * 8 : (size_t)tbs[i].nof_e_bits * 2;
+      if (bytes < (64u << 10)) {
+        direct = false;
+        break;
+      }
+      cudaPointerAttributes at{};
+      if (cudaPointerGetAttributes(&at, p) != cudaSuccess || at.type != cudaMemoryTypeHost) {
+        cudaGetLastError();  // (an unregistered pointer is not an error of ours)
+        direct = false;
+      }
+    }
+    if (direct) {
+      for (uint32_t i = 0; i < n_tb; i++) {
+        if (!run[i]) continue;
+        if (sym)
+          CU(cudaMemcpyAsync(reinterpret_cast<float*>(pool->d_e.p) + 2 * e_base[i], sym[i].symbols,
+                             (size_t)sym[i].nof_symbols * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+        else
+          CU(cudaMemcpyAsync(pool->d_e.p + e_base[i], tbs[i].e_bits, (size_t)tbs[i].nof_e_bits * sizeof(int16_t),
+                             cudaMemcpyHostToDevice, st));
+      }
+    }
     uint32_t split = n_tb;  // first TB of the second half
-    if (e_units >= (256u << 10)) {
+    if (direct) {
+      // nothing to stage
+    } else if (e_units >= (256u << 10)) {
       split = 0;
       while (split < n_tb && (!run[split] || e_base[split] < e_total / 2)) split++;
     }
     const size_t units_per = sym ? 4 : 1;
     const size_t cut = split < n_tb ? e_base[split] * units_per : e_units;  // int16 units of the first half
     if (split < n_tb) pool->helper.run([&, split] { stage(split, n_tb); });
-    stage(0, split);
-    cudaError_t ce = cut ? cudaMemcpyAsync(pool->d_e.p, pool->h_e.p, cut * sizeof(int16_t), cudaMemcpyHostToDevice, st) : cudaSuccess;
+    if (!direct) stage(0, split);
+    cudaError_t ce = (cut && !direct) ? cudaMemcpyAsync(pool->d_e.p, pool->h_e.p, cut * sizeof(int16_t), cudaMemcpyHostToDevice, st) : cudaSuccess;
     if (split < n_tb) {
       pool->helper.wait();  // (before any error return: the helper works on this call's locals)
       if (ce == cudaSuccess)

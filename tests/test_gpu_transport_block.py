@@ -190,3 +190,40 @@ def test_reset_many_and_large_batch_staging(ctx, pkg, vec):
     bad = np.array([60], dtype=np.uint32)
     assert L.srslte_b200_harq_reset_many(ctx._h, pool._p, bad.ctypes.data_as(C.c_void_p), 1) != 0
     pool.close()
+
+
+def test_pinned_caller_buffers_are_copied_without_staging(ctx, pkg, vec):
+    """large TBs whose LLRs sit in pinned host memory take the direct-copy path; the same TBs from pageable memory and a
+    mix of both (falls back to staging) give the same bytes"""
+    import bench_configs as bc
+    rng = np.random.default_rng(31)
+    descs, pay, pins = [], [], []
+    for i in range(6):
+        p, e = bc._make_tb(vec, rng, 75376, 6, 90000, 0.12, 400)
+        pay.append(p)
+        pa = pkg.PinnedArray(e.shape, np.int16)
+        pa.array[:] = e
+        pins.append(pa)
+        descs.append(dict(tbs=75376, qm=6, rv=0, e_bits=e, softbuffer=i))
+    pool = ctx.harq_pool(6, 13)
+    L = pkg.lib()
+
+    def run(bufs):
+        assert L.srslte_b200_harq_reset_many(ctx._h, pool._p, None, 6) == 0
+        arr = (pkg.TbDesc * 6)()
+        outs = [np.zeros(75376 // 8 + 8, np.uint8) for _ in range(6)]
+        for i in range(6):
+            arr[i] = pkg.TbDesc(75376, 6, 0, 90000, i, bufs[i].ctypes.data, outs[i].ctypes.data, 0, 0.0)
+        assert L.srslte_b200_decode_tb_batch(ctx._h, pool._p, arr, 6, 10) == 0
+        return [(arr[i].ret, outs[i].copy(), arr[i].avg_iterations) for i in range(6)]
+
+    pageable = run([d["e_bits"] for d in descs])
+    pinned = run([p.array for p in pins])
+    mixed = run([pins[i].array if i % 2 else descs[i]["e_bits"] for i in range(6)])
+    for i in range(6):
+        assert pageable[i][0] == 0 and np.array_equal(np.unpackbits(pageable[i][1][: 75376 // 8]), pay[i])
+        for other in (pinned, mixed):
+            assert other[i][0] == 0 and np.array_equal(other[i][1], pageable[i][1]) and other[i][2] == pageable[i][2]
+    pool.close()
+    for p in pins:
+        p.free()
