@@ -205,3 +205,21 @@ def test_group_entry_single_process(pkg, vec):
         assert len(gbs) == nd and all(x > 1.0 for x in gbs), gbs
         pin.free()
         g.close()
+
+
+@pytest.mark.parametrize("K,n", [(6144, 261), (2112, 300), (512, 203), (1008, 77)])
+def test_plain_batches_kernel_without_crc_variants(ctx, pkg, vec, K, n):
+    """launches without CRC run the kernel that carries no CRC variants (default) or the combined one (variant bit 7):
+    same bytes, and the oracle's on a sample"""
+    llr = _mixed_convergence(vec, n, K, seed=3 * K)
+    llr[: n // 3] = (llr[: n // 3].astype(np.int32) * 30).clip(-32768, 32767).astype(np.int16)   # static / tracked / exact tiers
+    for nit in (1, 4, 7):
+        a = ctx.tdec_batch_host(llr, K, nit)
+        ctx.set_variant_bits(128)
+        try:
+            b = ctx.tdec_batch_host(llr, K, nit)
+        finally:
+            ctx.set_variant_bits(0)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    idx = np.array([0, 1, n // 3 + 1, n - 1])
+    assert np.array_equal(a[0][idx], ol.port_run_all(np.ascontiguousarray(llr[idx]), K, 7))
