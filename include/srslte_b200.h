@@ -69,7 +69,8 @@ SRSLTE_B200_API int srslte_b200_ctx_set_exact(srslte_b200_ctx_t* ctx, int force_
 /* Tests and measurements: which of the (bit-identical) variants of the window decoders may run.  Bit 1 / 2: skip the
  * pure / static tier; 3: general path only; 5: the kernels with the tracked tier of the main path; 6: CRC modes through
  * the round-based kernel instead of the block-granular early-termination kernel; 7: launches without CRC through the
- * kernel that also carries the CRC variants.  0 = default.  Results never differ.                                   */
+ * kernel that also carries the CRC variants; 9: the early-termination kernel refills a thread group at once instead of
+ * waiting for its warp's next DEC1 half iteration.  0 = default.  Results never differ.                              */
 SRSLTE_B200_API int srslte_b200_ctx_set_variant_bits(srslte_b200_ctx_t* ctx, uint32_t bits);
 SRSLTE_B200_API int srslte_b200_ctx_fallback_count(srslte_b200_ctx_t* ctx, uint64_t* count);
 /* (warp, half iteration) pairs of the window decoders so far in the pure / static / tracked / exact variant

@@ -271,6 +271,7 @@ struct WinCtx {
                       // missing block of a partial item shadow block 0)
   uint32_t s_bytes;   // bytes per input stream of the item (ngroups * 512)
   uint32_t ngroups;   // row groups per stream (L rounded up to 4, / 4)
+  bool     idle;      // tdec_win_dyn_kernel: the group has no block in this half iteration: its loads go to the zero page
   bool     noap;      // first half iteration of a block: there is no a-priori information yet (A reads as zero and is
                       // neither fetched nor, unless a hard decision can come before DEC2 has written it, cleared)
   const char*     in_item;  // the item's sys | par0 | par1 streams
@@ -1264,10 +1265,10 @@ __device__ __forceinline__ Streams half_streams(const WinCtx<W>& c, bool dec2)
   // row group 0 of this thread in the three streams of this half iteration; missing inputs read the zero page
   const char* const zp = reinterpret_cast<const char*>(g_zero_page);
   Streams q;
-  q.s = dec2 ? zp + c.lane * 16 : c.in_item + c.sp_off;
-  q.p = c.in_item + (dec2 ? 2u : 1u) * (size_t)c.s_bytes + c.sp_off;
-  q.a = dec2 ? reinterpret_cast<const char*>(c.E32) + c.lane * 4
-             : c.noap ? zp + c.lane * 4 : reinterpret_cast<const char*>(c.A32) + c.lane * 4;
+  q.s = (dec2 || c.idle) ? zp + c.lane * 16 : c.in_item + c.sp_off;
+  q.p = c.idle ? zp + c.lane * 16 : c.in_item + (dec2 ? 2u : 1u) * (size_t)c.s_bytes + c.sp_off;
+  q.a = (c.noap || c.idle) ? zp + c.lane * 4
+                           : reinterpret_cast<const char*>(dec2 ? c.E32 : c.A32) + c.lane * 4;
   return q;
 }
 
@@ -1886,6 +1887,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_kernel(const 
       c.E32 = reinterpret_cast<uint32_t*>(ae + XB);
       c.chk = reinterpret_cast<uint4*>(reinterpret_cast<char*>(a.ws_chk) + (size_t)slot * kChkSlotBytes) + lane;
       c.R   = nullptr;
+      c.idle = false;
 
       uint8_t* out  = a.out + (size_t)cb * a.out_stride;
       uint32_t n    = 0, iters = 0;
@@ -2166,6 +2168,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_dyn_kernel(co
     c.A32 = reinterpret_cast<uint32_t*>(ae);
     c.E32 = reinterpret_cast<uint32_t*>(ae + XB);
     c.chk = reinterpret_cast<uint4*>(reinterpret_cast<char*>(a.ws_chk) + (size_t)slot * kChkSlotBytes) + lane;
+    c.idle = false;
     const bool v2      = (c.L & 3u) == 0 && (a.force_exact & 8u) == 0;
     const bool aligned = !v2;  // the general path needs one parity per warp: refill the warp only as a whole
     uint32_t* const queue = a.dyn_counters + e * PER + (uint32_t)grp;
@@ -2174,6 +2177,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_dyn_kernel(co
     // per-group state (the same in all threads of a group).  A group without a block shadows allocated memory: the
     // first item of the epoch until it has had a block of its own, its last block afterwards.
     bool     have = false, dry = false;  // dry: the group's queue has run out
+    uint32_t phase = 0;                  // half iterations the warp has run since it was last empty
     uint32_t cb = 0, n = 0, crc_mode = CRC_NONE;
     int      amax = 0, emax = 0, smax = 0, p0max = 0, p1max = 0;
     const uint32_t* Rblk = Rk;
@@ -2194,8 +2198,18 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_dyn_kernel(co
         if (tid == 0) s_nfin[par ^ 1u] = 0;
       }
       if (!go) break;
+      // A group takes a new block only when the blocks of the other groups of its warp are about to run DEC1 as well
+      // (or the warp is empty): the groups of a warp then share the parity, read the same array (A or E) and use whole
+      // 128-byte lines of it -- at mixed parities every line of both arrays is fetched for half its bytes (78 instead of
+      // 51 KB of DRAM reads per block and half iteration).  A block that finishes after an odd number of half iterations
+      // leaves its group idle for one half iteration (it then reads the zero page).  That pays when blocks live long
+      // (config 3 at -e 4.0, 7.2 half iterations per block: 12.8 -> 12.2 ms) and costs when they are short lived (-e 6.0,
+      // 2.8 half iterations: 5.9 -> 6.3 ms), so a group waits only if its previous block took five half iterations or more.
       const bool all_idle = __all_sync(FULL, !have);
-      const bool want = !have && !dry && (!aligned || all_idle);
+      if (all_idle) phase = 0;
+      // (n still holds the count of the group's previous block; variant bit 9: never wait -- measurements)
+      const bool in_step = (phase & 1u) == 0 || n < 5u || (a.force_exact & 512u) != 0;
+      const bool want = !have && !dry && (aligned ? all_idle : in_step);
       if (__any_sync(FULL, want)) {
         uint32_t j = FULL;
         if (want && t == 0) j = atomicAdd(queue, 1u);
@@ -2231,7 +2245,9 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSm) tdec_win_dyn_kernel(co
         const bool     dec2  = ((have ? n : nlead) & 1u) != 0;
         const bool     mixed = !__all_sync(FULL, dec2) && __any_sync(FULL, dec2);
         c.noap = have && n == 0;
+        c.idle = !have;
         c.R    = Rblk + (dec2 ? c.K : 0u);
+        phase++;
         const int Gx = dec2 ? emax : smax + amax;
         const int G  = have ? Gx + (dec2 ? p1max : p0max) : 0;
         HalfResult r;

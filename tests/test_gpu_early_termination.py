@@ -101,11 +101,12 @@ def test_dyn_kernel_mixed_sizes_and_per_block_crc_modes(ctx, pkg, vec):
 
 
 def test_dyn_kernel_forced_tiers(ctx, pkg, vec):
-    """static / tracked tier forced, general path only, exact variant forced: same results"""
+    """static / tracked tier forced, general path only, refill at once (parities mix inside a warp), exact variant forced:
+    same results"""
     K, n = 1024, 1999
     llr = _mixed_convergence(vec, n, K, seed=99)
     want = ctx.tdec_batch_host(llr, K, 8, crc_mode=pkg.CRC_24B)
-    for bits in (2, 6, 8):
+    for bits in (2, 6, 8, 512):
         ctx.set_variant_bits(bits)
         try:
             got = ctx.tdec_batch_host(llr, K, 8, crc_mode=pkg.CRC_24B)
