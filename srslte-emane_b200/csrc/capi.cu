@@ -1367,8 +1367,12 @@ class Helper {
     if (!th_.joinable()) th_ = std::thread([this] { loop(); });
     job_ = std::move(job);
     done_.store(false, std::memory_order_relaxed);
-    pending_.store(true, std::memory_order_release);
-    if (asleep_.load(std::memory_order_acquire)) {
+    // Sequentially consistent on both sides (this store / the load of asleep_ here, the store of asleep_ / the load of
+    // pending_ in loop()): with release / acquire alone the store may still sit in this core's store buffer when asleep_ is
+    // read -- both threads then see the other's flag clear, nobody notifies, and wait() spins for ever (an intermittent
+    // hang of bench.py's transport-block configurations).  The helper also wakes by itself every few milliseconds.
+    pending_.store(true, std::memory_order_seq_cst);
+    if (asleep_.load(std::memory_order_seq_cst)) {
       std::lock_guard<std::mutex> lk(m_);
       cv_.notify_all();
     }
@@ -1390,9 +1394,9 @@ class Helper {
         __builtin_ia32_pause();
         if ((++n & 1023u) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(500)) {
           std::unique_lock<std::mutex> lk(m_);
-          asleep_.store(true, std::memory_order_release);
-          cv_.wait(lk, [this] { return pending_.load(std::memory_order_acquire) || quit_; });
-          asleep_.store(false, std::memory_order_release);
+          asleep_.store(true, std::memory_order_seq_cst);
+          while (!(pending_.load(std::memory_order_seq_cst) || quit_)) cv_.wait_for(lk, std::chrono::milliseconds(5));
+          asleep_.store(false, std::memory_order_seq_cst);
           if (quit_) return;
         }
       }
