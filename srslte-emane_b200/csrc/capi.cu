@@ -2122,7 +2122,8 @@ int srslte_rm_turbo_rx_lut_8bit(int8_t*, int8_t*, uint32_t, uint32_t, uint32_t)
 
 // ---- fec/softbuffer.h:52-66 (softbuffer.c:40-150): the receive soft buffer, device resident ----------------------------
 // The host struct keeps the reference's layout and host arrays (callers read max_cb, cb_crc, tb_crc, data); the LLRs live
-// in a slot of a device pool and a reset is a flag there.  The host buffer_f arrays are allocated but not maintained.
+// in a slot of a device pool and a reset is a flag there (plus the reference's clearing of the host arrays, which the
+// paths that keep the reference's body still use).
 // A struct that was not made by srslte_softbuffer_rx_init here (copied by value, hand made) is handled like the
 // reference does, and srslte_b200_sch_decode_tb mirrors it to the device per call.
 int srslte_softbuffer_rx_init(srslte_softbuffer_rx_t* q, uint32_t nof_prb)
@@ -2188,7 +2189,6 @@ void srslte_softbuffer_rx_reset_cb(srslte_softbuffer_rx_t* q, uint32_t nof_cb)
 {
   if (!q) return;
   if (nof_cb > q->max_cb) nof_cb = q->max_cb;
-  bool device = false;
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_sb_map.find(q);
@@ -2199,12 +2199,13 @@ void srslte_softbuffer_rx_reset_cb(srslte_softbuffer_rx_t* q, uint32_t nof_cb)
       for (uint32_t i = 0; i < nof_cb && i < pool->max_cb; i++) pool->fresh[base + i] = 1;
       std::fill(pool->cb_crc.begin() + base, pool->cb_crc.begin() + base + pool->max_cb, 0);
       pool->tb_crc[it->second.idx] = 0;
-      device = true;
     }
   }
+  // the host arrays are cleared like the reference clears them: paths that keep the reference's body (srslte_ulsch_decode
+  // -> decode_tb_cb -> srslte_rm_turbo_rx_lut / srslte_tdec_iteration per block) accumulate in buffer_f on the host
   if (q->buffer_f)
     for (uint32_t i = 0; i < nof_cb; i++) {
-      if (!device && q->buffer_f[i]) std::memset(q->buffer_f[i], 0, SOFTBUFFER_SIZE * sizeof(int16_t));
+      if (q->buffer_f[i]) std::memset(q->buffer_f[i], 0, SOFTBUFFER_SIZE * sizeof(int16_t));
       if (q->data && q->data[i]) std::memset(q->data[i], 0, 6144 / 8);
     }
   if (q->cb_crc) std::memset(q->cb_crc, 0, sizeof(bool) * q->max_cb);
