@@ -209,6 +209,167 @@ SRSLTE_API int srslte_dlsch_decode(void* q /* srslte_sch_t* */, srslte_pdsch_cfg
 SRSLTE_API int srslte_dlsch_decode2(void* q /* srslte_sch_t* */, srslte_pdsch_cfg_t* cfg, int16_t* e_bits, uint8_t* data,
                                     int codeword_idx, uint32_t nof_layers);
 
+
+/* ---- sch.h:109-115 / sch.c:920-1064: the UL-SCH decode entry point ------------------------------------------------
+ * srslte_ulsch_decode is what pusch.c:503 calls.  Like the two DL entry points it shares sch.c with code that stays,
+ * so the reference's sch.c is compiled UNCHANGED with one more compile definition
+ *     -Dsrslte_ulsch_decode=srslte_ulsch_decode_cpu
+ * and linked with this library.  The transport block (decode_tb, sch.c:1058-1062: rate de-matching, HARQ combining,
+ * turbo decoding, CRCs) runs on the device through the soft buffer's device pool.  The values of the multiplexed
+ * control information (HARQ-ACK, RI, CQI) are control-plane work and stay in the reference: this entry calls the
+ * reference's own srslte_uci_decode_ack_ri, srslte_uci_decode_cqi_pusch, srslte_cqi_size, srslte_cqi_value_unpack
+ * and srslte_uci_cfg_total_ack (uci.c, cqi.c: weak references, resolved by the link with libsrslte_phy; a PUSCH with
+ * control information fails loudly when they are absent), in the reference's order and with the reference's side
+ * effects on q_bits, g_bits, cfg->K_segm and cfg->uci_cfg.cqi.rank_is_not_one.  g_bits receives the de-interleaved
+ * codeword exactly as ulsch_deinterleave leaves it (sch.c:891-918, including g[0], which ends up holding the RI
+ * sample with the highest channel position).
+ * The structures restate phch/cqi.h:121-142, phch/uci_cfg.h:27-70, phch/pusch_cfg.h:29-88, fec/turbocoder.h:46-49,
+ * fec/crc.h:38-46 and phch/sch.h:52-74 (SRSLTE_MAX_CARRIERS = 5, SRSLTE_MAX_CODEWORDS = 2);
+ * tests/test_compat_abi.py checks sizes and offsets against the compiled reference.                                */
+typedef struct {
+  bool     data_enable;
+  bool     ri_present;
+  bool     pmi_present;
+  bool     four_antenna_ports;
+  bool     rank_is_not_one;
+  bool     subband_label_2_bits;
+  uint32_t L;
+  uint32_t N;
+  uint32_t type; /* srslte_cqi_type_t: WIDEBAND = 0, SUBBAND, SUBBAND_UE, SUBBAND_HL */
+  uint32_t ri_len;
+} srslte_cqi_cfg_t;
+
+typedef struct { uint8_t wideband_cqi, spatial_diff_cqi, pmi; } srslte_cqi_format2_wideband_t;
+typedef struct { uint8_t subband_cqi, subband_label; } srslte_cqi_format2_subband_t;
+typedef struct { uint8_t wideband_cqi, subband_diff_cqi; uint32_t position_subband; } srslte_cqi_ue_subband_t;
+typedef struct {
+  uint8_t  wideband_cqi_cw0;
+  uint32_t subband_diff_cqi_cw0;
+  uint8_t  wideband_cqi_cw1;
+  uint32_t subband_diff_cqi_cw1;
+  uint32_t pmi;
+} srslte_cqi_hl_subband_t;
+
+typedef struct {
+  union {
+    srslte_cqi_format2_wideband_t wideband;
+    srslte_cqi_format2_subband_t  subband;
+    srslte_cqi_ue_subband_t       subband_ue;
+    srslte_cqi_hl_subband_t       subband_hl;
+  } u;
+  bool data_crc;
+} srslte_cqi_value_t;
+
+typedef struct {
+  bool     pending_tb[2];
+  uint32_t nof_acks;
+  uint32_t ncce[9];
+  uint32_t N_bundle;
+  uint32_t tdd_ack_M;
+  uint32_t tdd_ack_m;
+  bool     tdd_is_multiplex;
+  uint32_t tpc_for_pucch;
+  uint32_t grant_cc_idx;
+} srslte_uci_cfg_ack_t;
+
+typedef struct {
+  srslte_uci_cfg_ack_t ack[5];
+  srslte_cqi_cfg_t     cqi;
+  bool                 is_scheduling_request_tti;
+} srslte_uci_cfg_t;
+
+typedef struct {
+  uint8_t ack_value[10];
+  bool    valid;
+} srslte_uci_value_ack_t;
+
+typedef struct {
+  bool                   scheduling_request;
+  srslte_cqi_value_t     cqi;
+  srslte_uci_value_ack_t ack;
+  uint8_t                ri;
+} srslte_uci_value_t;
+
+typedef struct {
+  uint32_t position;
+  uint32_t type; /* srslte_uci_bit_type_t */
+} srslte_uci_bit_t;
+
+typedef struct {
+  uint32_t I_offset_cqi;
+  uint32_t I_offset_ri;
+  uint32_t I_offset_ack;
+} srslte_uci_offset_cfg_t;
+
+typedef struct {
+  bool           is_from_rar;
+  uint32_t       L_prb;
+  uint32_t       n_prb[2];
+  uint32_t       n_prb_tilde[2];
+  uint32_t       freq_hopping;
+  uint32_t       nof_re;
+  uint32_t       nof_symb;
+  srslte_ra_tb_t tb;
+  srslte_ra_tb_t last_tb;
+  uint32_t       n_dmrs;
+} srslte_pusch_grant_t;
+
+typedef struct {
+  uint16_t                rnti;
+  srslte_uci_cfg_t        uci_cfg;
+  srslte_uci_offset_cfg_t uci_offset;
+  srslte_pusch_grant_t    grant;
+  uint32_t                max_nof_iterations;
+  uint32_t                last_O_cqi;
+  uint32_t                K_segm;
+  uint32_t                current_tx_nb;
+  bool                    csi_enable;
+  bool                    enable_64qam;
+  union {
+    void*                   tx;
+    srslte_softbuffer_rx_t* rx;
+  } softbuffers;
+  bool     meas_time_en;
+  uint32_t meas_time_value;
+} srslte_pusch_cfg_t;
+
+typedef struct {
+  uint32_t max_long_cb;
+  uint8_t* temp;
+} srslte_tcod_t;
+
+typedef struct {
+  uint64_t table[256];
+  int      polynom;
+  int      order;
+  uint64_t crcinit;
+  uint64_t crcmask;
+  uint64_t crchighbit;
+  uint32_t srslte_crc_out;
+} srslte_crc_t;
+
+/* srslte_sch_t (sch.h:52-74) up to and including the two CRC objects; srslte_uci_cqi_pusch_t uci_cqi follows (its
+ * address is handed to the reference's CQI decoder, its content is the reference's business) */
+typedef struct {
+  uint32_t         max_iterations;
+  float            avg_iterations;
+  bool             llr_is_8bit;
+  uint8_t*         cb_in;
+  uint8_t*         parity_bits;
+  void*            e;
+  uint8_t*         temp_g_bits;
+  uint32_t*        ul_interleaver;
+  srslte_uci_bit_t ack_ri_bits[57600];
+  srslte_tcod_t    encoder;
+  srslte_tdec_t    decoder;
+  srslte_crc_t     crc_tb;
+  srslte_crc_t     crc_cb;
+  uint64_t         uci_cqi[1]; /* first word of srslte_uci_cqi_pusch_t */
+} srslte_sch_ul_t;
+
+SRSLTE_API int srslte_ulsch_decode(void* q /* srslte_sch_t* */, srslte_pusch_cfg_t* cfg, int16_t* q_bits, int16_t* g_bits,
+                                   uint8_t* c_seq, uint8_t* data, srslte_uci_value_t* uci_data);
+
 #ifdef __cplusplus
 }
 #endif

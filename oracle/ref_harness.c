@@ -44,6 +44,36 @@ void refh_dlsch_layout(size_t out[11])
   out[10] = offsetof(srslte_sch_t, llr_is_8bit);
 }
 
+/* layouts srslte_ulsch_decode reads (include/srslte_b200_compat.h restates them; tests/test_compat_abi.py) */
+#include "srslte/phy/phch/pusch_cfg.h"
+void refh_ulsch_layout(size_t out[24])
+{
+  out[0]  = sizeof(srslte_sch_t);
+  out[1]  = offsetof(srslte_sch_t, ack_ri_bits);
+  out[2]  = offsetof(srslte_sch_t, encoder);
+  out[3]  = offsetof(srslte_sch_t, decoder);
+  out[4]  = offsetof(srslte_sch_t, crc_tb);
+  out[5]  = offsetof(srslte_sch_t, uci_cqi);
+  out[6]  = sizeof(srslte_pusch_cfg_t);
+  out[7]  = offsetof(srslte_pusch_cfg_t, uci_cfg);
+  out[8]  = offsetof(srslte_pusch_cfg_t, uci_cfg) + offsetof(srslte_uci_cfg_t, cqi);
+  out[9]  = offsetof(srslte_pusch_cfg_t, uci_offset);
+  out[10] = offsetof(srslte_pusch_cfg_t, grant);
+  out[11] = offsetof(srslte_pusch_cfg_t, grant) + offsetof(srslte_pusch_grant_t, nof_symb);
+  out[12] = offsetof(srslte_pusch_cfg_t, grant) + offsetof(srslte_pusch_grant_t, tb);
+  out[13] = offsetof(srslte_pusch_cfg_t, K_segm);
+  out[14] = offsetof(srslte_pusch_cfg_t, softbuffers);
+  out[15] = sizeof(srslte_uci_cfg_ack_t);
+  out[16] = offsetof(srslte_uci_cfg_ack_t, nof_acks);
+  out[17] = sizeof(srslte_cqi_cfg_t);
+  out[18] = offsetof(srslte_cqi_cfg_t, ri_len);
+  out[19] = sizeof(srslte_uci_value_t);
+  out[20] = offsetof(srslte_uci_value_t, cqi) + offsetof(srslte_cqi_value_t, data_crc);
+  out[21] = offsetof(srslte_uci_value_t, ack);
+  out[22] = offsetof(srslte_uci_value_t, ri);
+  out[23] = sizeof(srslte_uci_bit_t);
+}
+
 /* ---- decoder handle ---- */
 srslte_tdec_t* refh_tdec_new(uint32_t max_k, int impl /* 0 = AUTO */)
 {

@@ -2350,3 +2350,168 @@ int srslte_dlsch_decode(void* q, srslte_pdsch_cfg_t* cfg, int16_t* e_bits, uint8
 }
 
 }  // extern "C"
+
+// ---- sch.h:109-115: srslte_ulsch_decode (sch.c:920-1064) -----------------------------------------------------------
+// The unchanged pusch.c:503 calls this with the reference's srslte_sch_t and srslte_pusch_cfg_t.  The transport block
+// runs on the device (srslte_b200_sch_decode_tb: the soft buffer's device pool, all code blocks in one batch).  The VALUES
+// of the multiplexed control information are control-plane work that stays in the reference: its own decoders are called
+// through weak references (uci.c:547-719, cqi.c:321-380, 529-560), resolved when this library is linked next to
+// libsrslte_phy; they also produce the RI positions the de-interleaver skips.
+extern "C" {
+#define B200_WEAK __attribute__((weak, visibility("default")))
+int      srslte_uci_decode_ack_ri(srslte_pusch_cfg_t* cfg, int16_t* q_bits, uint8_t* c_seq, float beta, uint32_t H_prime_total,
+                                  uint32_t O_cqi, srslte_uci_bit_t* ack_ri_bits, uint8_t* data, uint32_t nof_bits,
+                                  bool is_ri) B200_WEAK;
+int      srslte_uci_decode_cqi_pusch(void* q, srslte_pusch_cfg_t* cfg, int16_t* q_bits, float beta, uint32_t Q_prime_ri,
+                                     uint32_t cqi_len, uint8_t* cqi_data, bool* cqi_ack) B200_WEAK;
+uint32_t srslte_uci_cfg_total_ack(srslte_uci_cfg_t* uci_cfg) B200_WEAK;
+int      srslte_cqi_size(srslte_cqi_cfg_t* cfg) B200_WEAK;
+int      srslte_cqi_value_unpack(srslte_cqi_cfg_t* cfg, uint8_t* buff, srslte_cqi_value_t* value) B200_WEAK;
+#undef B200_WEAK
+}
+
+namespace {
+// 36.213 Tables 8.6.3-1 / -2 / -3: beta offsets by the index signalled by higher layers (-1: reserved)
+const float kBetaHarq[16] = {2.0f, 2.5f, 3.125f, 4.0f, 5.0f, 6.25f, 8.0f, 10.0f, 12.625f, 15.875f, 20.0f, 31.0f, 50.0f, 80.0f, 126.0f, -1.0f};
+const float kBetaRi[16]   = {1.25f, 1.625f, 2.0f, 2.5f, 3.125f, 4.0f, 5.0f, 6.25f, 8.0f, 10.0f, 12.625f, 15.875f, 20.0f, -1.0f, -1.0f, -1.0f};
+const float kBetaCqi[16]  = {-1.0f, -1.0f, 1.125f, 1.25f, 1.375f, 1.625f, 1.75f, 2.0f, 2.25f, 2.5f, 2.875f, 3.125f, 3.5f, 4.0f, 5.0f, 6.25f};
+
+// The UL-SCH channel de-interleaver of 36.212 5.2.2.8 as the reference leaves its output (ulsch_deinterleave,
+// sch.c:891-918): the codeword was written into a rows x cols matrix of Qm-bit vectors row by row, skipping the RI
+// positions, and sent column by column; g receives the matrix row by row without the RI samples.  The reference goes
+// through a table that maps every RI position to index 0 and fills g in channel order, so g[0] finally holds the sample
+// with the highest channel position among the RI samples and the first data sample.
+void ul_deinterleave_host(const int16_t* q, int16_t* g, uint32_t Qm, uint32_t H_total, uint32_t cols,
+                          const srslte_uci_bit_t* ri, uint32_t nof_ri, std::vector<uint8_t>& is_ri)
+{
+  if (!cols || !Qm) return;
+  const uint32_t rows = H_total / cols, n = rows * cols * Qm;
+  uint32_t       last = 0;  // highest channel position written to g[0]
+  bool           any0 = false;
+  if (nof_ri) {
+    is_ri.assign(std::max<size_t>(is_ri.size(), n), 0);
+    for (uint32_t i = 0; i < nof_ri; i++)
+      if (ri[i].position < n) {
+        is_ri[ri[i].position] = 1;
+        last = std::max(last, ri[i].position);
+        any0 = true;
+      }
+  }
+  uint32_t idx = 0;
+  if (!nof_ri) {
+    for (uint32_t j = 0; j < rows; j++)
+      for (uint32_t i = 0; i < cols; i++) {
+        const int16_t* src = q + ((size_t)i * rows + j) * Qm;
+        for (uint32_t k = 0; k < Qm; k++) g[idx++] = src[k];
+      }
+    return;
+  }
+  for (uint32_t j = 0; j < rows; j++)
+    for (uint32_t i = 0; i < cols; i++) {
+      const uint32_t p = (i * rows + j) * Qm;
+      for (uint32_t k = 0; k < Qm; k++) {
+        if (is_ri[p + k]) continue;
+        if (idx == 0) {
+          last = std::max(last, p + k);
+          any0 = true;
+        }
+        g[idx++] = q[p + k];
+      }
+    }
+  if (any0) g[0] = q[last];
+  for (uint32_t i = 0; i < nof_ri; i++)
+    if (ri[i].position < n) is_ri[ri[i].position] = 0;
+}
+}  // namespace
+
+extern "C" int srslte_ulsch_decode(void* qv, srslte_pusch_cfg_t* cfg, int16_t* q_bits, int16_t* g_bits, uint8_t* c_seq,
+                                   uint8_t* data, srslte_uci_value_t* uci_data)
+{
+  srslte_sch_ul_t* q = static_cast<srslte_sch_ul_t*>(qv);
+  if (!q || !cfg || !q_bits || !g_bits) return SRSLTE_ERROR_INVALID_INPUTS;
+  if (q->llr_is_8bit) {
+    fprintf(stderr, "srslte_b200: the experimental 8-bit decoders are not provided (llr_is_8bit is set)\n");
+    return SRSLTE_ERROR;
+  }
+  int    ret = SRSLTE_ERROR_INVALID_INPUTS;
+  CbSegm seg;
+  if (cbsegm(&seg, (uint32_t)cfg->grant.tb.tbs)) {
+    fprintf(stderr, "Error computing segmentation for TBS=%d\n", cfg->grant.tb.tbs);
+    return SRSLTE_ERROR;
+  }
+  static const uint32_t mod_bits[5] = {1, 2, 4, 6, 8};  // srslte_mod_bits_x_symbol (phy_common.c)
+  const uint32_t nb_q = cfg->grant.tb.nof_bits;
+  const uint32_t Qm   = cfg->grant.tb.mod < 5 ? mod_bits[cfg->grant.tb.mod] : 0;
+  if (!Qm) return SRSLTE_ERROR_INVALID_INPUTS;
+  cfg->K_segm = seg.C1 * seg.K1 + seg.C2 * seg.K2;
+
+  srslte_cqi_cfg_t& cqi      = cfg->uci_cfg.cqi;
+  uint32_t          nof_ack  = 0;
+  for (int i = 0; i < 5; i++) nof_ack += cfg->uci_cfg.ack[i].nof_acks;  // srslte_uci_cfg_total_ack (uci.c:790-797)
+  const bool        with_uci = nof_ack > 0 || cqi.ri_len > 0 || cqi.data_enable;
+  if (with_uci && (!srslte_uci_decode_ack_ri || !srslte_uci_decode_cqi_pusch || !srslte_cqi_size || !srslte_cqi_value_unpack)) {
+    fprintf(stderr, "srslte_b200: srslte_ulsch_decode with control information needs the reference's UCI decoders "
+                    "(srslte_uci_decode_ack_ri, srslte_uci_decode_cqi_pusch, srslte_cqi_size, srslte_cqi_value_unpack): "
+                    "link libsrslte_phy\n");
+    return SRSLTE_ERROR;
+  }
+  if (with_uci && (!uci_data || !c_seq)) return SRSLTE_ERROR_INVALID_INPUTS;
+
+  // ---- RI / HARQ-ACK (uci_decode_ri_ack, sch.c:920-1000) ----
+  uint32_t   Q_prime_ri = 0;
+  const bool hl_ri      = cqi.data_enable && cqi.type == 3 /* SRSLTE_CQI_TYPE_SUBBAND_HL */ && cqi.ri_present;
+  if (hl_ri) cqi.rank_is_not_one = false;  // RI = 1 is assumed while RI / ACK are decoded (36.212 5.2.4.1)
+  const uint32_t cqi_len = with_uci && cqi.data_enable ? (uint32_t)srslte_cqi_size(&cqi) : 0;
+  ret = 0;
+  if (nof_ack > 0) {
+    float beta = kBetaHarq[cfg->uci_offset.I_offset_ack & 15];
+    if (cfg->grant.tb.tbs == 0) beta /= kBetaCqi[cfg->uci_offset.I_offset_cqi & 15];
+    ret = srslte_uci_decode_ack_ri(cfg, q_bits, c_seq, beta, nb_q / Qm, cqi_len, q->ack_ri_bits, uci_data->ack.ack_value,
+                                   nof_ack, false);
+    if (ret < 0) {
+      fprintf(stderr, "Error decoding RI/HARQ bits\n");
+      return SRSLTE_ERROR;
+    }
+    const uint32_t Q_prime_ack = (uint32_t)ret;
+    for (uint32_t i = 0; i < Q_prime_ack * Qm; i++) q_bits[q->ack_ri_bits[i].position] = 0;  // ACK punctures the data
+  }
+  if (cqi.ri_len > 0) {
+    float beta = kBetaRi[cfg->uci_offset.I_offset_ri & 15];
+    if (cfg->grant.tb.tbs == 0) beta /= kBetaCqi[cfg->uci_offset.I_offset_cqi & 15];
+    ret = srslte_uci_decode_ack_ri(cfg, q_bits, c_seq, beta, nb_q / Qm, cqi_len, q->ack_ri_bits, &uci_data->ri, cqi.ri_len,
+                                   true);
+    if (ret < 0) {
+      fprintf(stderr, "Error decoding RI/HARQ bits\n");
+      return SRSLTE_ERROR;
+    }
+    Q_prime_ri = (uint32_t)ret;
+  }
+  if (hl_ri) cqi.rank_is_not_one = uci_data->ri > 0;
+  ret = (int)Q_prime_ri;  // what the reference's `ret` holds from here on (returned when nothing below runs)
+
+  // ---- channel de-interleaver (sch.c:1028-1037) ----
+  static thread_local std::vector<uint8_t> is_ri;
+  ul_deinterleave_host(q_bits, g_bits, Qm, nb_q / Qm, cfg->grant.nof_symb, q->ack_ri_bits, Q_prime_ri * Qm, is_ri);
+
+  // ---- CQI sits at the head of the UL-SCH order (sch.c:1039-1057) ----
+  uint32_t Q_prime_cqi = 0;
+  if (cqi.data_enable) {
+    uint8_t cqi_buff[64] = {0};  // SRSLTE_CQI_MAX_BITS
+    ret = srslte_uci_decode_cqi_pusch(q->uci_cqi, cfg, g_bits, kBetaCqi[cfg->uci_offset.I_offset_cqi & 15], Q_prime_ri,
+                                      (uint32_t)srslte_cqi_size(&cqi), cqi_buff, &uci_data->cqi.data_crc);
+    if (ret < 0) return ret;
+    srslte_cqi_value_unpack(&cqi, cqi_buff, &uci_data->cqi);
+    Q_prime_cqi = (uint32_t)ret;
+  }
+  const uint32_t e_offset = Q_prime_cqi * Qm;
+
+  // ---- the transport block (decode_tb, sch.c:1059-1062) ----
+  if (seg.tbs > 0) {
+    const uint32_t G   = nb_q / Qm - Q_prime_ri - Q_prime_cqi;
+    float          avg = q->avg_iterations;
+    ret = srslte_b200_sch_decode_tb(cfg->softbuffers.rx, (uint32_t)cfg->grant.tb.tbs, Qm, (uint32_t)cfg->grant.tb.rv, G * Qm,
+                                    &g_bits[e_offset], data, q->max_iterations, &avg);
+    q->avg_iterations = avg;
+  }
+  return ret;
+}

@@ -74,10 +74,54 @@ def test_dlsch_layouts_match_reference(tmp_path):
     assert got == want
 
 
+PROBE_ULSCH = r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "srslte_b200_compat.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu ", sizeof(srslte_sch_ul_t) - sizeof(uint64_t), offsetof(srslte_sch_ul_t, ack_ri_bits),
+         offsetof(srslte_sch_ul_t, encoder), offsetof(srslte_sch_ul_t, decoder), offsetof(srslte_sch_ul_t, crc_tb),
+         offsetof(srslte_sch_ul_t, uci_cqi));
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu ", sizeof(srslte_pusch_cfg_t), offsetof(srslte_pusch_cfg_t, uci_cfg),
+         offsetof(srslte_pusch_cfg_t, uci_cfg) + offsetof(srslte_uci_cfg_t, cqi), offsetof(srslte_pusch_cfg_t, uci_offset),
+         offsetof(srslte_pusch_cfg_t, grant), offsetof(srslte_pusch_cfg_t, grant) + offsetof(srslte_pusch_grant_t, nof_symb),
+         offsetof(srslte_pusch_cfg_t, grant) + offsetof(srslte_pusch_grant_t, tb), offsetof(srslte_pusch_cfg_t, K_segm),
+         offsetof(srslte_pusch_cfg_t, softbuffers));
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(srslte_uci_cfg_ack_t), offsetof(srslte_uci_cfg_ack_t, nof_acks),
+         sizeof(srslte_cqi_cfg_t), offsetof(srslte_cqi_cfg_t, ri_len), sizeof(srslte_uci_value_t),
+         offsetof(srslte_uci_value_t, cqi) + offsetof(srslte_cqi_value_t, data_crc), offsetof(srslte_uci_value_t, ack),
+         offsetof(srslte_uci_value_t, ri), sizeof(srslte_uci_bit_t));
+  return 0;
+}
+"""
+
+
+def test_ulsch_layouts_match_reference(tmp_path):
+    """srslte_pusch_cfg_t / srslte_uci_value_t / srslte_sch_t as srslte_ulsch_decode reads them.  srslte_sch_ul_t ends with
+    the first word of uci_cqi: its size without that word is the reference's offset of uci_cqi."""
+    import ctypes as C
+    src = tmp_path / "probe3.c"
+    src.write_text(PROBE_ULSCH)
+    exe = tmp_path / "probe3"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    R = ol.ref()
+    if R is not None and hasattr(R, "refh_ulsch_layout"):
+        arr = (C.c_size_t * 24)()
+        R.refh_ulsch_layout(arr)
+        want = list(arr)
+    else:   # recorded from the reference's build (oracle/ref_harness.c:refh_ulsch_layout)
+        want = [490792, 56, 460856, 460872, 479136, 483312, 520, 4, 344, 372, 384, 416, 420, 488, 504, 68, 4, 24, 20, 40, 24,
+                28, 39, 8]
+    assert want[5] == 483312 and want[6] == 520
+    want[0] = want[5]          # our struct stops where uci_cqi starts
+    assert got == want
+
+
 def test_compat_symbols_are_exported(pkg):
     L = pkg.lib()
     for name in ("srslte_tdec_init", "srslte_tdec_init_manual", "srslte_tdec_free", "srslte_tdec_force_not_sb",
-                 "srslte_tdec_new_cb", "srslte_tdec_get_nof_iterations", "srslte_tdec_autoimp_get_subblocks",
+                 "srslte_tdec_new_cb", "srslte_tdec_get_nof_iterations", "srslte_tdec_autoimp_get_subblocks", "srslte_ulsch_decode",
                  "srslte_tdec_autoimp_get_subblocks_8bit", "srslte_tdec_iteration", "srslte_tdec_run_all",
                  "srslte_tdec_iteration_8bit", "srslte_tdec_run_all_8bit", "srslte_rm_turbo_gentables",
                  "srslte_rm_turbo_free_tables", "srslte_rm_turbo_rx_lut", "srslte_rm_turbo_rx_lut_",

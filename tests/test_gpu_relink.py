@@ -8,6 +8,9 @@ inside oracle/_ref/):
   dlsch_harness_ref/_b200  srslte_sch_init -> srslte_dlsch_encode2 -> srslte_dlsch_decode2 with HARQ retransmissions through the
                            reference's sch.c (compiled unchanged; for _b200 its two DL decode entry points are renamed out
                            of the way by a compile definition) -> srslte_dlsch_decode2 and srslte_tdec_* from this library
+  ulsch_harness_ref/_b200  srslte_ulsch_encode -> scrambling -> srslte_ulsch_decode with multiplexed ACK / RI / CQI and HARQ
+                           retransmissions, the way pusch.c drives it -> srslte_ulsch_decode from this library (which calls
+                           the reference's UCI decoders for the control values and decodes the transport block on the device)
 """
 import os
 import re
@@ -43,6 +46,10 @@ def test_relink_binaries_take_the_hot_path_from_the_library():
     u = _undefined("dlsch_harness_b200")
     assert {"srslte_dlsch_decode2", "srslte_tdec_init", "srslte_tdec_free"} <= u
     assert "srslte_dlsch_encode2" not in u and "srslte_sch_init" not in u   # those are the reference's own objects
+    if os.path.exists(os.path.join(REFDIR, "ulsch_harness_b200")):
+        u = _undefined("ulsch_harness_b200")
+        assert {"srslte_ulsch_decode", "srslte_tdec_init", "srslte_softbuffer_rx_init"} <= u
+        assert "srslte_ulsch_encode" not in u and "srslte_uci_decode_ack_ri" not in u   # the reference's own objects
 
 
 def _tdec_test_numbers(text):
@@ -70,5 +77,16 @@ def test_reference_turbodecoder_test_relinked(args):
 def test_reference_sch_api_relinked(args):
     ref = _run("dlsch_harness_ref", *args)
     got = _run("dlsch_harness_b200", *args)
+    assert "digest" in ref and ref.count("\n") > args[0]
+    assert got == ref
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args", [(14, 0.45, 10), (14, 0.30, 4), (28, 0.60, 8)])
+def test_reference_ulsch_api_relinked(args):
+    """PUSCH transport blocks with multiplexed HARQ-ACK / RI / CQI: return codes, iterations, TB bytes, K_segm, the decoded
+    control values, the de-interleaved LLRs (g_bits) and the modified q_bits of every transmission are identical"""
+    ref = _run("ulsch_harness_ref", *args)
+    got = _run("ulsch_harness_b200", *args)
     assert "digest" in ref and ref.count("\n") > args[0]
     assert got == ref
