@@ -75,6 +75,50 @@ __device__ __noinline__ uint32_t ul_uci_map(const FeCodeword& cw, uint32_t j, ui
   return (col * rows + row) * qm + k;
 }
 
+// The modulation's level chain for channel position j (symbol j / QM, level (j % QM) / 2, x = its real or imaginary
+// part), not yet descrambled.  Which conversion rule applies depends on where the symbol sits relative to the reference's
+// SIMD bodies and scalar remainders (see the file header).
+// BODY: the caller knows that the symbol lies in the reference's SIMD body (no per-LLR test, no remainder code)
+template <uint32_t QM, bool BODY = false>
+__device__ __forceinline__ int fe_value(const FeCodeword& cw, float x, uint32_t j, uint32_t s, uint32_t lvl)
+{
+  constexpr uint32_t qm = QM;
+  int                v;
+  if (qm == 2) {
+    constexpr float kScale = (float)(-100.0 * 1.4142135623730951);
+    const int       t = __float2int_rz(__fmul_rn(x, kScale));
+    v = BODY || j < ((2 * cw.nsym) & ~15u) ? sat16(t) : wrap16(t);
+  } else if (qm == 4) {
+    if (BODY || s < (cw.nsym & ~3u)) {
+      const int v0 = sat16(__float2int_rn(__fmul_rn(x, -400.0f)));
+      v = lvl == 0 ? v0 : wrap16(abs(v0) - 252);
+    } else {
+      const int y = wrap16(__float2int_rz(__fmul_rn(400.0f, x)));
+      v = lvl == 0 ? wrap16(-y) : wrap16(__double2int_rz((double)abs(y) - 800.0 / 3.1622776601683795));
+    }
+  } else if (qm == 6) {
+    if (BODY || s < (cw.nsym & ~3u)) {
+      const int v0 = sat16(__float2int_rn(__fmul_rn(x, -700.0f)));
+      const int a1 = wrap16(abs(v0) - 432);
+      v = lvl == 0 ? v0 : lvl == 1 ? a1 : wrap16(abs(a1) - 216);
+    } else {
+      const int y  = wrap16(__float2int_rz(__fmul_rn(700.0f, x)));
+      const int l2 = wrap16(__double2int_rz((double)abs(y) - 2800.0 / 6.48074069840786));
+      v = lvl == 0 ? wrap16(-y) : lvl == 1 ? l2 : wrap16(__double2int_rz((double)abs(l2) - 1400.0 / 6.48074069840786));
+    }
+  } else {
+    // 8 / sqrtf(170), 4 / sqrtf(170), 2 / sqrtf(170) in single precision (demod_soft.c:457-477), as constants:
+    // sqrtf(170.0f) = 0x1.a13a9cp+3, the three quotients rounded to nearest differ in the exponent only
+    constexpr float k8 = 0x1.3a261cp-1f, k4 = 0x1.3a261cp-2f, k2 = 0x1.3a261cp-3f;
+    float           f = -x;
+    if (lvl >= 1) f = __fsub_rn(fabsf(f), k8);
+    if (lvl >= 2) f = __fsub_rn(fabsf(f), k4);
+    if (lvl >= 3) f = __fsub_rn(fabsf(f), k2);
+    v = wrap16(__float2int_rz(__fmul_rn(1000.0f, f)));
+  }
+  return v;
+}
+
 // LLR number j of a codeword (before rate de-matching), descrambled.  QM = bits per symbol, a compile-time constant:
 // the kernels branch once per CTA on the codeword's modulation (no division by a run-time Qm, no per-LLR dispatch).
 template <uint32_t QM>
@@ -95,39 +139,8 @@ __device__ __forceinline__ int fe_llr(const FeCodeword& cw, const float* __restr
       j = (col * cw.ul_rows + row) * qm + k;
     }
   }
-  const uint32_t     s = j / qm, r = j - s * qm, lvl = r >> 1;
-  const float    x  = __ldg(sym + 2 * (size_t)s + (r & 1u));
-  int            v;
-  if (qm == 2) {
-    constexpr float kScale = (float)(-100.0 * 1.4142135623730951);
-    const int       t = __float2int_rz(__fmul_rn(x, kScale));
-    v = j < ((2 * cw.nsym) & ~15u) ? sat16(t) : wrap16(t);
-  } else if (qm == 4) {
-    if (s < (cw.nsym & ~3u)) {
-      const int v0 = sat16(__float2int_rn(__fmul_rn(x, -400.0f)));
-      v = lvl == 0 ? v0 : wrap16(abs(v0) - 252);
-    } else {
-      const int y = wrap16(__float2int_rz(__fmul_rn(400.0f, x)));
-      v = lvl == 0 ? wrap16(-y) : wrap16(__double2int_rz((double)abs(y) - 800.0 / 3.1622776601683795));
-    }
-  } else if (qm == 6) {
-    if (s < (cw.nsym & ~3u)) {
-      const int v0 = sat16(__float2int_rn(__fmul_rn(x, -700.0f)));
-      const int a1 = wrap16(abs(v0) - 432);
-      v = lvl == 0 ? v0 : lvl == 1 ? a1 : wrap16(abs(a1) - 216);
-    } else {
-      const int y  = wrap16(__float2int_rz(__fmul_rn(700.0f, x)));
-      const int l2 = wrap16(__double2int_rz((double)abs(y) - 2800.0 / 6.48074069840786));
-      v = lvl == 0 ? wrap16(-y) : lvl == 1 ? l2 : wrap16(__double2int_rz((double)abs(l2) - 1400.0 / 6.48074069840786));
-    }
-  } else {
-    const float s170 = __fsqrt_rn(170.0f);
-    float       f = -x;
-    if (lvl >= 1) f = __fsub_rn(fabsf(f), __fdiv_rn(8.0f, s170));
-    if (lvl >= 2) f = __fsub_rn(fabsf(f), __fdiv_rn(4.0f, s170));
-    if (lvl >= 3) f = __fsub_rn(fabsf(f), __fdiv_rn(2.0f, s170));
-    v = wrap16(__float2int_rz(__fmul_rn(1000.0f, f)));
-  }
+  const uint32_t s = j / qm, r = j - s * qm;
+  int            v = fe_value<QM>(cw, __ldg(sym + 2 * (size_t)s + (r & 1u)), j, s, r >> 1);
   if (j < cw.nof_bits) {
     const uint32_t c = ((__ldg(x1 + (j >> 5)) >> (j & 31u)) ^ (uint32_t)__popc(__ldg(x2mask + j) & cw.c_init)) & 1u;
     if (c && !raw) v = wrap16(-v);
@@ -135,8 +148,97 @@ __device__ __forceinline__ int fe_llr(const FeCodeword& cw, const float* __restr
   return v;
 }
 
-// grid: (chunks of 256 * kLlrPerThread LLRs, codewords): a thread amortises the codeword descriptor and pointer
-// set-up over several LLRs, consecutive threads write consecutive LLRs
+// G consecutive LLRs of a PDSCH codeword (channel order = output order) by one thread: whole symbols in (one or two
+// 128-bit loads), whole 128-bit stores out, the x1 bits from one or two words and the x2 masks as 128-bit loads.
+// G = 8 (4 QPSK / 2 16QAM / 1 256QAM symbols) or 24 (4 64QAM symbols); j0 is a multiple of G.
+template <uint32_t QM>
+__device__ __forceinline__ void fe_group(const FeCodeword& cw, const float* __restrict__ sym, int16_t* __restrict__ out,
+                                         uint32_t j0, const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x2mask)
+{
+  constexpr uint32_t G = QM == 6 ? 24 : 8, NF = 2 * G / QM;
+  float              x[NF];
+  const float*       p = sym + 2 * (size_t)(j0 / QM);
+  if (NF == 2) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    x[0] = t.x;
+    x[1] = t.y;
+  } else {
+#pragma unroll
+    for (uint32_t i = 0; i < NF / 4; i++) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+      x[4 * i] = t.x, x[4 * i + 1] = t.y, x[4 * i + 2] = t.z, x[4 * i + 3] = t.w;
+    }
+  }
+  int v[G];
+  const uint32_t s0 = j0 / QM;  // j0 is a multiple of G, G of QM
+  // the whole group lies in the reference's SIMD body (QPSK: 16 LLRs at a time, 16QAM / 64QAM: 4 symbols at a time; the
+  // 256QAM chain has no remainder rule) or it is the one group per codeword that touches the scalar remainder
+  const bool body = QM == 8 || (QM == 2 ? j0 + G <= ((2 * cw.nsym) & ~15u) : s0 + G / QM <= (cw.nsym & ~3u));
+  if (body) {
+#pragma unroll
+    for (uint32_t i = 0; i < G; i++)
+      v[i] = fe_value<QM, true>(cw, x[2 * (i / QM) + ((i % QM) & 1u)], j0 + i, s0 + i / QM, (i % QM) >> 1);
+  } else {
+#pragma unroll
+    for (uint32_t i = 0; i < G; i++)
+      v[i] = fe_value<QM, false>(cw, x[2 * (i / QM) + ((i % QM) & 1u)], j0 + i, s0 + i / QM, (i % QM) >> 1);
+  }
+  if (j0 + G <= cw.nof_bits) {
+    const uint32_t sh = j0 & 31u, w0 = __ldg(x1 + (j0 >> 5));
+    const uint32_t w1 = sh + G > 32 ? __ldg(x1 + (j0 >> 5) + 1) : 0u;
+    const uint32_t w  = __funnelshift_r(w0, w1, sh);
+#pragma unroll
+    for (uint32_t q = 0; q < G / 4; q++) {
+      const uint4    m    = __ldg(reinterpret_cast<const uint4*>(x2mask + j0) + q);
+      const uint32_t mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+      for (uint32_t k = 0; k < 4; k++) {
+        const uint32_t i = 4 * q + k;
+        if (((w >> i) ^ (uint32_t)__popc(mm[k] & cw.c_init)) & 1u) v[i] = wrap16(-v[i]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (uint32_t i = 0; i < G; i++) {
+      const uint32_t j = j0 + i;
+      if (j < cw.nof_bits && (((__ldg(x1 + (j >> 5)) >> (j & 31u)) ^ (uint32_t)__popc(__ldg(x2mask + j) & cw.c_init)) & 1u))
+        v[i] = wrap16(-v[i]);
+    }
+  }
+#pragma unroll
+  for (uint32_t q = 0; q < G / 8; q++) {
+    uint4 o;
+    o.x = (uint32_t)(v[8 * q + 0] & 0xFFFF) | ((uint32_t)v[8 * q + 1] << 16);
+    o.y = (uint32_t)(v[8 * q + 2] & 0xFFFF) | ((uint32_t)v[8 * q + 3] << 16);
+    o.z = (uint32_t)(v[8 * q + 4] & 0xFFFF) | ((uint32_t)v[8 * q + 5] << 16);
+    o.w = (uint32_t)(v[8 * q + 6] & 0xFFFF) | ((uint32_t)v[8 * q + 7] << 16);
+    reinterpret_cast<uint4*>(out + j0)[q] = o;
+  }
+}
+
+template <uint32_t QM>
+__device__ __forceinline__ void demod_descramble_cw(const FeCodeword& cw, const float* __restrict__ sym,
+                                                    int16_t* __restrict__ out, const uint32_t* __restrict__ x1,
+                                                    const uint32_t* __restrict__ x2mask)
+{
+  constexpr uint32_t G = QM == 6 ? 24 : 8;
+  const uint32_t     n = QM * cw.nsym;
+  // PDSCH codewords whose symbols and LLRs sit on 128-bit boundaries: a thread per G LLRs
+  const bool fast = cw.ul_cols == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0 &&
+                    (reinterpret_cast<uintptr_t>(sym) & (QM == 8 ? 7u : 15u)) == 0;
+  const uint32_t groups = fast ? n / G : 0;
+  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x)
+    fe_group<QM>(cw, sym, out, g * G, x1, x2mask);
+  // what is left (fewer than G LLRs), PUSCH codewords (the de-interleaver is an index map per LLR) and unaligned
+  // buffers: one LLR at a time, consecutive threads write consecutive LLRs
+  const uint32_t first = groups * G, st = blockDim.x, per = blockDim.x * kLlrPerThread;
+  for (uint32_t base = first + blockIdx.x * per; base < n; base += gridDim.x * per) {
+    const uint32_t j1 = min(n, base + per);
+    for (uint32_t j = base + threadIdx.x; j < j1; j += st) out[j] = (int16_t)fe_llr<QM>(cw, sym, j, x1, x2mask);
+  }
+}
+
+// grid: (chunks of 256 * kLlrPerThread LLRs, codewords)
 __global__ void __launch_bounds__(256) demod_descramble_kernel(const FeCodeword* __restrict__ cws,
                                                                const float* __restrict__ symbols,
                                                                int16_t* __restrict__ e, const uint32_t* __restrict__ x1,
@@ -145,16 +247,11 @@ __global__ void __launch_bounds__(256) demod_descramble_kernel(const FeCodeword*
   const FeCodeword cw = cws[blockIdx.y];
   const float*     sym = symbols + 2 * cw.sym_off;
   int16_t*         out = e + cw.llr_off;
-  const uint32_t   n = cw.qm * cw.nsym, st = blockDim.x;
-  const uint32_t   per = blockDim.x * kLlrPerThread;
-  for (uint32_t base = blockIdx.x * per; base < n; base += gridDim.x * per) {
-    const uint32_t j0 = base + threadIdx.x, j1 = min(n, base + per);
-    switch (cw.qm) {
-      case 2: for (uint32_t j = j0; j < j1; j += st) out[j] = (int16_t)fe_llr<2>(cw, sym, j, x1, x2mask); break;
-      case 4: for (uint32_t j = j0; j < j1; j += st) out[j] = (int16_t)fe_llr<4>(cw, sym, j, x1, x2mask); break;
-      case 6: for (uint32_t j = j0; j < j1; j += st) out[j] = (int16_t)fe_llr<6>(cw, sym, j, x1, x2mask); break;
-      default: for (uint32_t j = j0; j < j1; j += st) out[j] = (int16_t)fe_llr<8>(cw, sym, j, x1, x2mask); break;
-    }
+  switch (cw.qm) {
+    case 2: demod_descramble_cw<2>(cw, sym, out, x1, x2mask); break;
+    case 4: demod_descramble_cw<4>(cw, sym, out, x1, x2mask); break;
+    case 6: demod_descramble_cw<6>(cw, sym, out, x1, x2mask); break;
+    default: demod_descramble_cw<8>(cw, sym, out, x1, x2mask); break;
   }
 }
 
@@ -234,8 +331,10 @@ cudaError_t demod_descramble_launch(const FeCodeword* cws, uint32_t n_cw, uint32
                                     int16_t* e, const uint32_t* x1, const uint32_t* x2mask, cudaStream_t s)
 {
   if (n_cw == 0 || max_llr == 0) return cudaSuccess;
+  // enough CTAs for a few waves of the 148 SMs; a CTA strides over its codeword (empty CTAs cost a launch slot each)
   const uint32_t chunks = (max_llr + 256 * kLlrPerThread - 1) / (256 * kLlrPerThread);
-  dim3           grid(chunks < 1024 ? chunks : 1024, n_cw);
+  const uint32_t cap    = n_cw >= 4736 ? 1u : 4736u / n_cw;
+  dim3           grid(chunks < cap ? chunks : cap, n_cw);
   demod_descramble_kernel<<<grid, 256, 0, s>>>(cws, symbols, e, x1, x2mask);
   return cudaGetLastError();
 }

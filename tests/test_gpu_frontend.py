@@ -53,6 +53,46 @@ def test_many_codewords_vs_oracle(ctx):
     assert np.array_equal(got, np.concatenate(want))
 
 
+def test_aligned_codewords_take_the_vector_path(ctx):
+    """Codewords whose symbols and LLRs start on 128-bit boundaries are demodulated G = 8 (24 for 64QAM) LLRs per thread;
+    every modulation with symbol counts around the reference's SIMD-body / scalar-remainder boundaries, descrambled
+    lengths that end inside a group or leave whole groups undescrambled, and one deliberately misaligned neighbour."""
+    import torch
+    rng = np.random.default_rng(23)
+    cws, want, so, lo = [], [], 0, 0
+    sizes = [1, 2, 3, 4, 5, 7, 8, 9, 12, 13, 15, 16, 17, 31, 33, 100, 255, 1001, 2998, 3000]
+    chunks = []
+    for qm in (2, 4, 6, 8):
+        for nsym in sizes:
+            for cut in (0, 1, 9, 30):
+                n = qm * nsym
+                nb = max(1, n - cut)
+                amp = float(rng.choice([0.3, 1.0, 5.0]))
+                sym = ((rng.standard_normal(nsym) + 1j * rng.standard_normal(nsym)) * amp).astype(np.complex64)
+                c_init = int(rng.integers(1, 2 ** 31 - 1))
+                mis = 1 if (nsym == 13 and cut == 1) else 0     # an odd symbol offset: the per-LLR path
+                so += mis
+                cws.append(dict(qm=qm, nof_symbols=nsym, c_init=c_init, nof_bits=nb, sym_offset=so, llr_offset=lo))
+                chunks.append((so, sym)); want.append((lo, ol.port_demod_descramble(qm, sym, c_init, nb)))
+                so = (so + nsym + 1) & ~1
+                lo = (lo + n + 7) & ~7
+    sbuf = np.zeros(so + 2, np.complex64)
+    for o, sym in chunks:
+        sbuf[o:o + len(sym)] = sym
+    st = torch.from_numpy(sbuf.view(np.float32)).cuda()
+    e = torch.full((lo + 8,), 12345, dtype=torch.int16, device="cuda")
+    ctx.demod_descramble_dev(cws, st.data_ptr(), e.data_ptr())
+    ctx.synchronize()
+    got = e.cpu().numpy()
+    for o, w in want:
+        assert np.array_equal(got[o:o + len(w)], w)
+    # nothing outside the codewords was written
+    mask = np.ones(len(got), bool)
+    for o, w in want:
+        mask[o:o + len(w)] = False
+    assert np.all(got[mask] == 12345)
+
+
 def test_pusch_codewords_with_ulsch_deinterleaver_vs_oracle(ctx):
     """PUSCH order of operations (pusch.c:482-500, sch.c:1028-1036): demodulate, descramble, then the UL-SCH channel
     de-interleaver; the kernel applies the permutation as an index map."""
