@@ -158,7 +158,7 @@ __device__ __forceinline__ void fe_group(const FeCodeword& cw, const float* __re
   constexpr uint32_t G = QM == 6 ? 24 : 8, NF = 2 * G / QM;
   float              x[NF];
   const float*       p = sym + 2 * (size_t)(j0 / QM);
-  if (NF == 2) {
+  if constexpr (NF == 2) {
     const float2 t = __ldg(reinterpret_cast<const float2*>(p));
     x[0] = t.x;
     x[1] = t.y;
@@ -280,34 +280,76 @@ __global__ void rm_rx_sym_kernel(const FeCodeword* __restrict__ cws, const float
 // reference: srslte_tcod_encode (lib/src/phy/fec/turbocoder.c:95-187: two RSC encoders g0 = 1 + D^2 + D^3,
 // g1 = 1 + D + D^3, the second one on the QPP-interleaved bits, output 3i+j then the 12 tail bits) and
 // srslte_rm_turbo_tx (lib/src/phy/fec/rm_turbo.c:303-372: e[i] = d[table[i mod N]], the same selection table the
-// receive side scatters through).  One CTA per code block: thread 0 and thread 32 run the two shift registers
-// (a 6144-step chain each), everybody copies the systematic bits and gathers the rate-matched output.
-__global__ void __launch_bounds__(128) tcod_rm_tx_kernel(const TxItem* __restrict__ items, const uint8_t* __restrict__ bits_all,
-                                                         uint8_t* __restrict__ e_all, const uint16_t* __restrict__ tab_pool)
+// receive side scatters through).  One CTA per code block.  The encoder's register is a linear function of its
+// start state and of the input bits, so the K-step chain is cut into 128 chunks per constituent encoder (threads 0-127:
+// natural order, threads 128-255: QPP order): every thread runs its chunk from the zero state, one thread per encoder
+// chains the 128 end states through the chunk's zero-input transition (an 8-entry table), and every thread runs its
+// chunk again from its true start state and writes the parity bits.  The rate-matched output is gathered by everybody.
+__device__ __forceinline__ uint32_t rsc_step(uint32_t& st, uint32_t in)
+{
+  // st = r0 | r1 << 1 | r2 << 2;  feedback g0 = 1 + D^2 + D^3, output g1 = 1 + D + D^3
+  const uint32_t r0 = st & 1u, r1 = (st >> 1) & 1u, r2 = st >> 2;
+  const uint32_t fb = in ^ r2 ^ r1;
+  st = fb | (r0 << 1) | (r1 << 2);
+  return r2 ^ r0 ^ fb;
+}
+
+constexpr uint32_t kTxThreads = 256, kTxChunks = kTxThreads / 2;
+
+__global__ void __launch_bounds__(kTxThreads) tcod_rm_tx_kernel(const TxItem* __restrict__ items,
+                                                                const uint8_t* __restrict__ bits_all,
+                                                                uint8_t* __restrict__ e_all, const uint16_t* __restrict__ tab_pool)
 {
   extern __shared__ uint8_t tx_d[];  // the 3K + 12 coded bits
+  __shared__ uint8_t s_end[2][kTxChunks], s_start[2][kTxChunks], s_zero[8];
   const TxItem   it   = items[blockIdx.x];
   const uint32_t K    = it.K;
   const uint8_t* bits = bits_all + it.bits_off;
   for (uint32_t k = threadIdx.x; k < K; k += blockDim.x) tx_d[3 * k] = bits[k] & 1u;
-  if (threadIdx.x == 0 || threadIdx.x == 32) {
-    const bool second = threadIdx.x == 32;
-    uint32_t   r0 = 0, r1 = 0, r2 = 0;
-    uint32_t   p = 0, g = (it.f1 + it.f2) % K;  // pi(k) and pi(k+1) - pi(k) = f1 + f2 (2k + 1), both mod K
+  const uint32_t L = (K + kTxChunks - 1) / kTxChunks, nch = (K + L - 1) / L;  // L <= 48 steps per chunk
+  const uint32_t second = threadIdx.x / kTxChunks, c = threadIdx.x % kTxChunks;
+  const uint32_t k0 = c * L, k1 = min(K, k0 + L);
+  uint64_t       in = 0;  // the chunk's input bits
+  if (c < nch) {
+    // pi(k) = (f1 k + f2 k^2) mod K and its increment pi(k+1) - pi(k) = f1 + f2 (2k + 1), both mod K
+    uint32_t       pk = (uint32_t)(((uint64_t)it.f1 * k0 + (uint64_t)it.f2 * k0 % K * k0) % K);
+    uint32_t       g  = (uint32_t)(((uint64_t)it.f1 + (uint64_t)it.f2 * (2 * k0 + 1)) % K);
     const uint32_t g2 = (2 * it.f2) % K;
-    for (uint32_t k = 0; k < K; k++) {
-      const uint32_t in = bits[second ? p : k] & 1u;
-      const uint32_t fb = in ^ r2 ^ r1;
-      tx_d[3 * k + (second ? 2 : 1)] = (uint8_t)(r2 ^ r0 ^ fb);
-      r2 = r1; r1 = r0; r0 = fb;
-      p += g; if (p >= K) p -= K;
+    uint32_t       st = 0;
+    for (uint32_t k = k0; k < k1; k++) {
+      const uint32_t b = bits[second ? pk : k] & 1u;
+      in |= (uint64_t)b << (k - k0);
+      rsc_step(st, b);
+      pk += g; if (pk >= K) pk -= K;
       g += g2; if (g >= K) g -= K;
     }
-    uint8_t* tail = tx_d + 3 * K + (second ? 6 : 0);
-    for (int j = 0; j < 3; j++) {  // flush: the input equals the feedback, so 0 enters the register
-      tail[2 * j]     = (uint8_t)(r2 ^ r1);
-      tail[2 * j + 1] = (uint8_t)(r2 ^ r0);
-      r2 = r1; r1 = r0; r0 = 0;
+    s_end[second][c] = (uint8_t)st;
+  }
+  if (threadIdx.x < 8) {  // where L steps without input take each of the 8 states
+    uint32_t st = threadIdx.x;
+    for (uint32_t k = 0; k < L; k++) rsc_step(st, 0);
+    s_zero[threadIdx.x] = (uint8_t)st;
+  }
+  __syncthreads();
+  if (c == 0) {  // start states of the chunks (every chunk before the last one has L steps)
+    uint32_t st = 0;
+    for (uint32_t i = 0; i < nch; i++) {
+      s_start[second][i] = (uint8_t)st;
+      st = s_zero[st] ^ s_end[second][i];
+    }
+  }
+  __syncthreads();
+  if (c < nch) {
+    uint32_t st = s_start[second][c];
+    for (uint32_t k = k0; k < k1; k++) tx_d[3 * k + 1 + second] = (uint8_t)rsc_step(st, (uint32_t)(in >> (k - k0)) & 1u);
+    if (c == nch - 1) {  // flush: the input equals the feedback, so 0 enters the register
+      uint32_t r0 = st & 1u, r1 = (st >> 1) & 1u, r2 = st >> 2;
+      uint8_t* tail = tx_d + 3 * K + (second ? 6 : 0);
+      for (int j = 0; j < 3; j++) {
+        tail[2 * j]     = (uint8_t)(r2 ^ r1);
+        tail[2 * j + 1] = (uint8_t)(r2 ^ r0);
+        r2 = r1; r1 = r0; r0 = 0;
+      }
     }
   }
   __syncthreads();
@@ -323,7 +365,7 @@ cudaError_t tcod_rm_tx_launch(const TxItem* items, uint32_t n_items, const uint8
                               const uint16_t* tab_pool, cudaStream_t s)
 {
   if (n_items == 0) return cudaSuccess;
-  tcod_rm_tx_kernel<<<n_items, 128, 3 * 6144 + 16, s>>>(items, bits, e, tab_pool);
+  tcod_rm_tx_kernel<<<n_items, kTxThreads, 3 * 6144 + 16, s>>>(items, bits, e, tab_pool);
   return cudaGetLastError();
 }
 
