@@ -216,6 +216,60 @@ __device__ __forceinline__ void fe_group(const FeCodeword& cw, const float* __re
   }
 }
 
+// The same for a PUSCH codeword without multiplexed control information: the G output LLRs are G / QM consecutive
+// vectors of the UL-SCH order; vector v sits at row v / cols, column v % cols of the channel interleaver matrix and was
+// sent as symbol column * rows + row (ulsch_deinterleave, sch.c:891-918), where it was demodulated and descrambled.
+template <uint32_t QM>
+__device__ __forceinline__ void fe_group_ul(const FeCodeword& cw, const float* __restrict__ sym, int16_t* __restrict__ out,
+                                            uint32_t j0, const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x2mask)
+{
+  constexpr uint32_t G = QM == 6 ? 24 : 8, NV = G / QM;
+  const uint32_t     v0 = j0 / QM;
+  uint32_t           row = v0 / cw.ul_cols, col = v0 - row * cw.ul_cols;
+  int                v[G];
+#pragma unroll
+  for (uint32_t u = 0; u < NV; u++) {
+    const uint32_t s = col * cw.ul_rows + row, jc = s * QM;
+    if (++col == cw.ul_cols) col = 0, row++;
+    const float2 t = __ldg(reinterpret_cast<const float2*>(sym) + s);
+    const bool   body = QM == 8 || (QM == 2 ? jc + QM <= ((2 * cw.nsym) & ~15u) : s < (cw.nsym & ~3u));
+    if (body) {
+#pragma unroll
+      for (uint32_t k = 0; k < QM; k++) v[u * QM + k] = fe_value<QM, true>(cw, (k & 1u) ? t.y : t.x, jc + k, s, k >> 1);
+    } else {
+#pragma unroll
+      for (uint32_t k = 0; k < QM; k++) v[u * QM + k] = fe_value<QM, false>(cw, (k & 1u) ? t.y : t.x, jc + k, s, k >> 1);
+    }
+    if (jc + QM <= cw.nof_bits) {
+      const uint32_t sh = jc & 31u, w0 = __ldg(x1 + (jc >> 5));
+      const uint32_t w1 = sh + QM > 32 ? __ldg(x1 + (jc >> 5) + 1) : 0u;
+      const uint32_t w  = __funnelshift_r(w0, w1, sh);
+#pragma unroll
+      for (uint32_t k = 0; k < QM; k += 2) {  // jc is a multiple of QM, QM is even: 64-bit loads are aligned
+        const uint2 m = __ldg(reinterpret_cast<const uint2*>(x2mask + jc + k));
+        if (((w >> k) ^ (uint32_t)__popc(m.x & cw.c_init)) & 1u) v[u * QM + k] = wrap16(-v[u * QM + k]);
+        if (((w >> (k + 1)) ^ (uint32_t)__popc(m.y & cw.c_init)) & 1u) v[u * QM + k + 1] = wrap16(-v[u * QM + k + 1]);
+      }
+    } else {
+#pragma unroll
+      for (uint32_t k = 0; k < QM; k++) {
+        const uint32_t j = jc + k;
+        if (j < cw.nof_bits && (((__ldg(x1 + (j >> 5)) >> (j & 31u)) ^ (uint32_t)__popc(__ldg(x2mask + j) & cw.c_init)) & 1u))
+          v[u * QM + k] = wrap16(-v[u * QM + k]);
+      }
+    }
+  }
+#pragma unroll
+  for (uint32_t q = 0; q < G / 8; q++) {
+    uint4 o;
+    o.x = (uint32_t)(v[8 * q + 0] & 0xFFFF) | ((uint32_t)v[8 * q + 1] << 16);
+    o.y = (uint32_t)(v[8 * q + 2] & 0xFFFF) | ((uint32_t)v[8 * q + 3] << 16);
+    o.z = (uint32_t)(v[8 * q + 4] & 0xFFFF) | ((uint32_t)v[8 * q + 5] << 16);
+    o.w = (uint32_t)(v[8 * q + 6] & 0xFFFF) | ((uint32_t)v[8 * q + 7] << 16);
+    reinterpret_cast<uint4*>(out + j0)[q] = o;
+  }
+}
+
 template <uint32_t QM>
 __device__ __forceinline__ void demod_descramble_cw(const FeCodeword& cw, const float* __restrict__ sym,
                                                     int16_t* __restrict__ out, const uint32_t* __restrict__ x1,
@@ -223,14 +277,22 @@ __device__ __forceinline__ void demod_descramble_cw(const FeCodeword& cw, const 
 {
   constexpr uint32_t G = QM == 6 ? 24 : 8;
   const uint32_t     n = QM * cw.nsym;
-  // PDSCH codewords whose symbols and LLRs sit on 128-bit boundaries: a thread per G LLRs
-  const bool fast = cw.ul_cols == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0 &&
-                    (reinterpret_cast<uintptr_t>(sym) & (QM == 8 ? 7u : 15u)) == 0;
+  // codewords whose LLRs (and, for PDSCH, symbols) sit on 128-bit boundaries: a thread per G LLRs.  PUSCH codewords with
+  // multiplexed control information go through the general index map (ul_uci_map) one LLR at a time.
+  const bool pusch = cw.ul_cols != 0;
+  const bool fast  = (reinterpret_cast<uintptr_t>(out) & 15u) == 0 &&
+                    (pusch ? (cw.q_ack | cw.q_ri) == 0 && cw.g0_src == kNoG0 && (reinterpret_cast<uintptr_t>(sym) & 7u) == 0
+                           : (reinterpret_cast<uintptr_t>(sym) & (QM == 8 ? 7u : 15u)) == 0);
   const uint32_t groups = fast ? n / G : 0;
-  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x)
-    fe_group<QM>(cw, sym, out, g * G, x1, x2mask);
-  // what is left (fewer than G LLRs), PUSCH codewords (the de-interleaver is an index map per LLR) and unaligned
-  // buffers: one LLR at a time, consecutive threads write consecutive LLRs
+  if (pusch) {
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x)
+      fe_group_ul<QM>(cw, sym, out, g * G, x1, x2mask);
+  } else {
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x)
+      fe_group<QM>(cw, sym, out, g * G, x1, x2mask);
+  }
+  // what is left (fewer than G LLRs) and unaligned buffers: one LLR at a time, consecutive threads write consecutive
+  // LLRs
   const uint32_t first = groups * G, st = blockDim.x, per = blockDim.x * kLlrPerThread;
   for (uint32_t base = first + blockIdx.x * per; base < n; base += gridDim.x * per) {
     const uint32_t j1 = min(n, base + per);
