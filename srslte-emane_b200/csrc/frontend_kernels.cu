@@ -152,7 +152,7 @@ __device__ __forceinline__ int fe_llr(const FeCodeword& cw, const float* __restr
 // 128-bit loads), whole 128-bit stores out, the x1 bits from one or two words and the x2 masks as 128-bit loads.
 // G = 8 (4 QPSK / 2 16QAM / 1 256QAM symbols) or 24 (4 64QAM symbols); j0 is a multiple of G.
 template <uint32_t QM>
-__device__ __forceinline__ void fe_group(const FeCodeword& cw, const float* __restrict__ sym, int16_t* __restrict__ out,
+__device__ __forceinline__ void fe_group(const FeCodeword& cw, const float* __restrict__ sym, int (&v)[QM == 6 ? 24 : 8],
                                          uint32_t j0, const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x2mask)
 {
   constexpr uint32_t G = QM == 6 ? 24 : 8, NF = 2 * G / QM;
@@ -169,7 +169,6 @@ __device__ __forceinline__ void fe_group(const FeCodeword& cw, const float* __re
       x[4 * i] = t.x, x[4 * i + 1] = t.y, x[4 * i + 2] = t.z, x[4 * i + 3] = t.w;
     }
   }
-  int v[G];
   const uint32_t s0 = j0 / QM;  // j0 is a multiple of G, G of QM
   // the whole group lies in the reference's SIMD body (QPSK: 16 LLRs at a time, 16QAM / 64QAM: 4 symbols at a time; the
   // 256QAM chain has no remainder rule) or it is the one group per codeword that touches the scalar remainder
@@ -205,28 +204,18 @@ __device__ __forceinline__ void fe_group(const FeCodeword& cw, const float* __re
         v[i] = wrap16(-v[i]);
     }
   }
-#pragma unroll
-  for (uint32_t q = 0; q < G / 8; q++) {
-    uint4 o;
-    o.x = (uint32_t)(v[8 * q + 0] & 0xFFFF) | ((uint32_t)v[8 * q + 1] << 16);
-    o.y = (uint32_t)(v[8 * q + 2] & 0xFFFF) | ((uint32_t)v[8 * q + 3] << 16);
-    o.z = (uint32_t)(v[8 * q + 4] & 0xFFFF) | ((uint32_t)v[8 * q + 5] << 16);
-    o.w = (uint32_t)(v[8 * q + 6] & 0xFFFF) | ((uint32_t)v[8 * q + 7] << 16);
-    reinterpret_cast<uint4*>(out + j0)[q] = o;
-  }
 }
 
 // The same for a PUSCH codeword without multiplexed control information: the G output LLRs are G / QM consecutive
 // vectors of the UL-SCH order; vector v sits at row v / cols, column v % cols of the channel interleaver matrix and was
 // sent as symbol column * rows + row (ulsch_deinterleave, sch.c:891-918), where it was demodulated and descrambled.
 template <uint32_t QM>
-__device__ __forceinline__ void fe_group_ul(const FeCodeword& cw, const float* __restrict__ sym, int16_t* __restrict__ out,
+__device__ __forceinline__ void fe_group_ul(const FeCodeword& cw, const float* __restrict__ sym, int (&v)[QM == 6 ? 24 : 8],
                                             uint32_t j0, const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x2mask)
 {
   constexpr uint32_t G = QM == 6 ? 24 : 8, NV = G / QM;
   const uint32_t     v0 = j0 / QM;
   uint32_t           row = v0 / cw.ul_cols, col = v0 - row * cw.ul_cols;
-  int                v[G];
 #pragma unroll
   for (uint32_t u = 0; u < NV; u++) {
     const uint32_t s = col * cw.ul_rows + row, jc = s * QM;
@@ -259,15 +248,26 @@ __device__ __forceinline__ void fe_group_ul(const FeCodeword& cw, const float* _
       }
     }
   }
-#pragma unroll
-  for (uint32_t q = 0; q < G / 8; q++) {
-    uint4 o;
-    o.x = (uint32_t)(v[8 * q + 0] & 0xFFFF) | ((uint32_t)v[8 * q + 1] << 16);
-    o.y = (uint32_t)(v[8 * q + 2] & 0xFFFF) | ((uint32_t)v[8 * q + 3] << 16);
-    o.z = (uint32_t)(v[8 * q + 4] & 0xFFFF) | ((uint32_t)v[8 * q + 5] << 16);
-    o.w = (uint32_t)(v[8 * q + 6] & 0xFFFF) | ((uint32_t)v[8 * q + 7] << 16);
-    reinterpret_cast<uint4*>(out + j0)[q] = o;
-  }
+}
+
+// G LLRs of a codeword starting at j0 (a multiple of G), PDSCH or PUSCH without control information
+template <uint32_t QM>
+__device__ __forceinline__ void fe_group_any(const FeCodeword& cw, const float* __restrict__ sym, int (&v)[QM == 6 ? 24 : 8],
+                                             uint32_t j0, const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x2mask)
+{
+  if (cw.ul_cols)
+    fe_group_ul<QM>(cw, sym, v, j0, x1, x2mask);
+  else
+    fe_group<QM>(cw, sym, v, j0, x1, x2mask);
+}
+
+// which codewords the group functions handle: PDSCH with its symbols on a 128-bit boundary (64 bits for 256QAM), PUSCH
+// without multiplexed control information (with it: the general index map ul_uci_map, one LLR at a time)
+template <uint32_t QM>
+__device__ __forceinline__ bool fe_group_ok(const FeCodeword& cw, const float* sym)
+{
+  return cw.ul_cols ? (cw.q_ack | cw.q_ri) == 0 && cw.g0_src == kNoG0 && (reinterpret_cast<uintptr_t>(sym) & 7u) == 0
+                    : (reinterpret_cast<uintptr_t>(sym) & (QM == 8 ? 7u : 15u)) == 0;
 }
 
 template <uint32_t QM>
@@ -277,19 +277,21 @@ __device__ __forceinline__ void demod_descramble_cw(const FeCodeword& cw, const 
 {
   constexpr uint32_t G = QM == 6 ? 24 : 8;
   const uint32_t     n = QM * cw.nsym;
-  // codewords whose LLRs (and, for PDSCH, symbols) sit on 128-bit boundaries: a thread per G LLRs.  PUSCH codewords with
-  // multiplexed control information go through the general index map (ul_uci_map) one LLR at a time.
-  const bool pusch = cw.ul_cols != 0;
-  const bool fast  = (reinterpret_cast<uintptr_t>(out) & 15u) == 0 &&
-                    (pusch ? (cw.q_ack | cw.q_ri) == 0 && cw.g0_src == kNoG0 && (reinterpret_cast<uintptr_t>(sym) & 7u) == 0
-                           : (reinterpret_cast<uintptr_t>(sym) & (QM == 8 ? 7u : 15u)) == 0);
+  // codewords whose LLRs (and, for PDSCH, symbols) sit on 128-bit boundaries: a thread per G LLRs, 128-bit stores
+  const bool     fast   = (reinterpret_cast<uintptr_t>(out) & 15u) == 0 && fe_group_ok<QM>(cw, sym);
   const uint32_t groups = fast ? n / G : 0;
-  if (pusch) {
-    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x)
-      fe_group_ul<QM>(cw, sym, out, g * G, x1, x2mask);
-  } else {
-    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x)
-      fe_group<QM>(cw, sym, out, g * G, x1, x2mask);
+  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+    int v[G];
+    fe_group_any<QM>(cw, sym, v, g * G, x1, x2mask);
+#pragma unroll
+    for (uint32_t q = 0; q < G / 8; q++) {
+      uint4 o;
+      o.x = (uint32_t)(v[8 * q + 0] & 0xFFFF) | ((uint32_t)v[8 * q + 1] << 16);
+      o.y = (uint32_t)(v[8 * q + 2] & 0xFFFF) | ((uint32_t)v[8 * q + 3] << 16);
+      o.z = (uint32_t)(v[8 * q + 4] & 0xFFFF) | ((uint32_t)v[8 * q + 5] << 16);
+      o.w = (uint32_t)(v[8 * q + 6] & 0xFFFF) | ((uint32_t)v[8 * q + 7] << 16);
+      reinterpret_cast<uint4*>(out + g * G)[q] = o;
+    }
   }
   // what is left (fewer than G LLRs) and unaligned buffers: one LLR at a time, consecutive threads write consecutive
   // LLRs
@@ -317,7 +319,46 @@ __global__ void __launch_bounds__(256) demod_descramble_kernel(const FeCodeword*
   }
 }
 
-// rate de-matching straight from the symbols: work[tab[i]] += sum over the wrap-around repeats of LLR(e_off + p)
+// rate de-matching straight from the symbols: work[tab[i]] += sum over the wrap-around repeats of LLR(e_off + p).
+// A block without wrap-around (E <= N, the usual case) of a codeword the group functions handle is produced G LLRs per
+// thread, in groups aligned to the codeword (the first and the last group of a block are shared with its neighbours and
+// computed by both); the table is one-to-one, so every thread owns the cells it writes.
+template <uint32_t QM>
+__device__ __forceinline__ void rm_rx_sym_cw(const RmSymItem& it, const FeCodeword& cw, const float* __restrict__ sym,
+                                             int16_t* __restrict__ dst, const uint16_t* __restrict__ tab, int16_t* img,
+                                             const uint32_t* __restrict__ x1, const uint32_t* __restrict__ x2mask)
+{
+  constexpr uint32_t G = QM == 6 ? 24 : 8;
+  const uint32_t     e0 = it.e_off;
+  if (it.E <= it.N && e0 + it.E <= QM * cw.nsym && fe_group_ok<QM>(cw, sym)) {
+    const uint32_t wl8 = (it.wl + 7) & ~7u;
+    for (uint32_t j = threadIdx.x; j < wl8 / 2; j += blockDim.x) reinterpret_cast<uint32_t*>(img)[j] = 0;
+    __syncthreads();
+    const uint32_t g0 = e0 / G, g1 = (e0 + it.E + G - 1) / G;
+    for (uint32_t g = g0 + threadIdx.x; g < g1; g += blockDim.x) {
+      if (g * G + G <= QM * cw.nsym) {
+        int v[G];
+        fe_group_any<QM>(cw, sym, v, g * G, x1, x2mask);
+#pragma unroll
+        for (uint32_t i = 0; i < G; i++) {
+          const uint32_t p = g * G + i - e0;  // wraps below e0
+          if (p < it.E) img[tab[p]] = (int16_t)v[i];
+        }
+      } else {  // the codeword ends inside this group
+        for (uint32_t i = 0; i < G; i++) {
+          const uint32_t p = g * G + i - e0;
+          if (p < it.E) img[tab[p]] = (int16_t)fe_llr<QM>(cw, sym, g * G + i, x1, x2mask);
+        }
+      }
+    }
+    __syncthreads();
+    rm_rx_add_image(img, dst, it.wl, it.overwrite != 0);
+    return;
+  }
+  rm_rx_body([&](uint32_t p) { return fe_llr<QM>(cw, sym, e0 + p, x1, x2mask); }, it.E, it.N, it.wl, tab, dst, img,
+             it.overwrite != 0);
+}
+
 __global__ void rm_rx_sym_kernel(const FeCodeword* __restrict__ cws, const float* __restrict__ symbols,
                                  int16_t* __restrict__ work, const uint16_t* __restrict__ tab_pool,
                                  const RmSymItem* __restrict__ items, const uint32_t* __restrict__ x1,
@@ -327,14 +368,13 @@ __global__ void rm_rx_sym_kernel(const FeCodeword* __restrict__ cws, const float
   const RmSymItem  it  = items[blockIdx.x];
   const FeCodeword cw  = cws[it.cw];
   const float*     sym = symbols + 2 * cw.sym_off;
-  const uint32_t   e0  = it.e_off;
   const uint16_t*  tab = tab_pool + it.tab_off;
   int16_t*         dst = work + it.work_off;
   switch (cw.qm) {
-    case 2: rm_rx_body([&](uint32_t p) { return fe_llr<2>(cw, sym, e0 + p, x1, x2mask); }, it.E, it.N, it.wl, tab, dst, rm_img, it.overwrite != 0); break;
-    case 4: rm_rx_body([&](uint32_t p) { return fe_llr<4>(cw, sym, e0 + p, x1, x2mask); }, it.E, it.N, it.wl, tab, dst, rm_img, it.overwrite != 0); break;
-    case 6: rm_rx_body([&](uint32_t p) { return fe_llr<6>(cw, sym, e0 + p, x1, x2mask); }, it.E, it.N, it.wl, tab, dst, rm_img, it.overwrite != 0); break;
-    default: rm_rx_body([&](uint32_t p) { return fe_llr<8>(cw, sym, e0 + p, x1, x2mask); }, it.E, it.N, it.wl, tab, dst, rm_img, it.overwrite != 0); break;
+    case 2: rm_rx_sym_cw<2>(it, cw, sym, dst, tab, rm_img, x1, x2mask); break;
+    case 4: rm_rx_sym_cw<4>(it, cw, sym, dst, tab, rm_img, x1, x2mask); break;
+    case 6: rm_rx_sym_cw<6>(it, cw, sym, dst, tab, rm_img, x1, x2mask); break;
+    default: rm_rx_sym_cw<8>(it, cw, sym, dst, tab, rm_img, x1, x2mask); break;
   }
 }
 

@@ -99,19 +99,9 @@ constexpr uint32_t kRmMaxWorkLen = 18600;  // SOFTBUFFER_SIZE of the reference (
 // Shared by the two rate-dematching kernels: sum the wrap-around repeats of every rate-matched position, scatter the
 // sums into a shared-memory image of the working buffer (table order), then add the image to the working buffer
 // with coalesced 128-bit read-modify-writes (wrapping int16, like the reference's `+=`).
-template <class Src>
-__device__ __forceinline__ void rm_rx_body(const Src& src, uint32_t E, uint32_t N, uint32_t wl, const uint16_t* tab,
-                                           int16_t* dst, int16_t* img /* shared, wl rounded up to 8 */, bool overwrite)
+// add (or copy) the shared-memory image to the working buffer: coalesced 128-bit read-modify-writes, wrapping int16
+__device__ __forceinline__ void rm_rx_add_image(const int16_t* img, int16_t* dst, uint32_t wl, bool overwrite)
 {
-  const uint32_t wl8 = (wl + 7) & ~7u;
-  for (uint32_t j = threadIdx.x; j < wl8 / 2; j += blockDim.x) reinterpret_cast<uint32_t*>(img)[j] = 0;
-  __syncthreads();
-  for (uint32_t i = threadIdx.x; i < N && i < E; i += blockDim.x) {
-    int acc = 0;
-    for (uint32_t p = i; p < E; p += N) acc += src(p);  // wrap-around repeats hit the same cell
-    img[tab[i]] = (int16_t)acc;                         // the table is one-to-one
-  }
-  __syncthreads();
   if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
     const uint32_t nv = wl / 8;
     uint4*         d4 = reinterpret_cast<uint4*>(dst);
@@ -131,6 +121,22 @@ __device__ __forceinline__ void rm_rx_body(const Src& src, uint32_t E, uint32_t 
   } else {
     for (uint32_t j = threadIdx.x; j < wl; j += blockDim.x) dst[j] = overwrite ? img[j] : (int16_t)(dst[j] + img[j]);
   }
+}
+
+template <class Src>
+__device__ __forceinline__ void rm_rx_body(const Src& src, uint32_t E, uint32_t N, uint32_t wl, const uint16_t* tab,
+                                           int16_t* dst, int16_t* img /* shared, wl rounded up to 8 */, bool overwrite)
+{
+  const uint32_t wl8 = (wl + 7) & ~7u;
+  for (uint32_t j = threadIdx.x; j < wl8 / 2; j += blockDim.x) reinterpret_cast<uint32_t*>(img)[j] = 0;
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < N && i < E; i += blockDim.x) {
+    int acc = 0;
+    for (uint32_t p = i; p < E; p += N) acc += src(p);  // wrap-around repeats hit the same cell
+    img[tab[i]] = (int16_t)acc;                         // the table is one-to-one
+  }
+  __syncthreads();
+  rm_rx_add_image(img, dst, wl, overwrite);
 }
 cudaError_t rm_rx_launch(const int16_t* e, int16_t* work, const uint16_t* tab_pool, const RmItem* items,
                          uint32_t n_items, cudaStream_t s);

@@ -113,18 +113,21 @@ def test_pusch_codewords_with_ulsch_deinterleaver_vs_oracle(ctx):
     assert np.array_equal(got, np.concatenate(want))
 
 
-def test_fused_with_rate_dematching_vs_oracle(ctx):
+@pytest.mark.parametrize("align", [False, True])
+def test_fused_with_rate_dematching_vs_oracle(ctx, align):
     """symbols -> LLR -> descramble -> srslte_rm_turbo_rx_lut in ONE kernel (no e array), with HARQ combining of two
     transmissions, against the oracle: port_demod_descramble, then the port's receive index table applied as
-    work[table[i mod N]] += e[i] (wrapping int16)."""
+    work[table[i mod N]] += e[i] (wrapping int16).  align: every codeword starts on a 128-bit boundary (the kernel's
+    vector path for blocks without wrap-around); packed: odd symbol offsets (one LLR at a time)."""
     import torch
     P = ol.port()
     rng = np.random.default_rng(12)
     # three codewords; each carries a few code blocks the way sch.c:324-334 cuts them (E LLRs per block)
-    plan = [(6, [5824, 5824, 5824], 6918), (4, [1024, 1056], 25000), (2, [40, 512, 6144], 1200)]
+    plan = [(6, [5824, 5824, 5824], 6918), (4, [1024, 1056], 25000), (2, [40, 512, 6144], 1200),
+            (4, [2048, 6144, 3072], 5004), (8, [4096, 1504], 4568), (6, [6144], 18438)]
     wl = 18624
-    want = np.zeros((8, wl), np.int64)
-    work = torch.zeros((8, wl), dtype=torch.int16, device="cuda")
+    want = np.zeros((14, wl), np.int64)
+    work = torch.zeros((14, wl), dtype=torch.int16, device="cuda")
     for rv in (0, 2):
         cws, syms, blocks, so, bi = [], [], [], 0, 0
         for ci, (qm, Ks, E) in enumerate(plan):
@@ -135,6 +138,9 @@ def test_fused_with_rate_dematching_vs_oracle(ctx):
             cws.append(dict(qm=qm, nof_symbols=nsym, c_init=c_init, sym_offset=so))
             syms.append(sym)
             so += nsym
+            if align and so % 2:
+                syms.append(np.zeros(1, np.complex64))
+                so += 1
             e = ol.port_demod_descramble(qm, sym, c_init).astype(np.int64)
             for j, K in enumerate(Ks):
                 blocks.append((K, rv, ci, j * E, E, bi * wl))
