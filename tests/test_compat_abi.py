@@ -132,3 +132,36 @@ def test_compat_symbols_are_exported(pkg):
     # host-only entry points work without a GPU
     assert [L.srslte_tdec_autoimp_get_subblocks(k) for k in (40, 408, 816, 6144)] == [0, 8, 16, 16]
     assert [L.srslte_tdec_autoimp_get_subblocks_8bit(k) for k in (40, 408, 816, 2112, 6144)] == [0, 8, 16, 32, 32]
+
+
+def test_ulsch_decode_without_the_reference_uci_decoders_fails_loudly(pkg, capfd):
+    """Loaded alone (ctypes, no libsrslte_phy in the process) the weak references to the reference's UCI decoders are
+    NULL: a PUSCH with multiplexed control information must be refused with a message before anything is decoded, and
+    so must the 8-bit mode and a transport block size without a segmentation (no GPU is touched on these paths)."""
+    import ctypes as C
+    L = pkg.lib()
+    L.srslte_ulsch_decode.argtypes = [C.c_void_p] * 7
+    L.srslte_ulsch_decode.restype = C.c_int
+    q = (C.c_uint8 * (490792 + 64))()          # srslte_sch_t, zeroed: max_iterations 0, llr_is_8bit false
+    cfg = (C.c_uint8 * 520)()                  # srslte_pusch_cfg_t
+    def put32(buf, off, val):
+        C.cast(C.byref(buf, off), C.POINTER(C.c_uint32))[0] = val
+    llr = (C.c_int16 * 4096)()
+    g = (C.c_int16 * 4096)()
+    seq = (C.c_uint8 * 4096)()
+    data = (C.c_uint8 * 512)()
+    uci = (C.c_uint8 * 40)()
+    put32(cfg, 420 + 0, 1)                     # grant.tb.mod = QPSK
+    put32(cfg, 420 + 4, 504)                   # grant.tb.tbs
+    put32(cfg, 420 + 12, 1728)                 # grant.tb.nof_bits
+    put32(cfg, 416, 12)                        # grant.nof_symb
+    put32(cfg, 4 + 4, 1)                       # uci_cfg.ack[0].nof_acks = 1
+    rc = L.srslte_ulsch_decode(q, cfg, llr, g, seq, data, uci)
+    assert rc == -1
+    assert "UCI decoders" in capfd.readouterr().err
+    put32(cfg, 4 + 4, 0)
+    q[8] = 1                                   # llr_is_8bit
+    assert L.srslte_ulsch_decode(q, cfg, llr, g, seq, data, uci) == -1
+    assert "8-bit" in capfd.readouterr().err
+    q[8] = 0
+    assert L.srslte_ulsch_decode(None, cfg, llr, g, seq, data, uci) == -2

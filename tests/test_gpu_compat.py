@@ -198,3 +198,58 @@ def test_device_resident_softbuffer_api(L, golden):
     for sb in sbs:
         L.srslte_softbuffer_rx_free(C.byref(sb))
         assert sb.max_cb == 0
+
+
+def test_ulsch_decode_entry_without_control_information(L, golden):
+    """srslte_ulsch_decode (sch.h:109-115) through the library alone, with the reference's srslte_pusch_cfg_t / srslte_sch_t
+    layouts built by hand: the golden transport blocks of the reference, put into channel order by the inverse of the
+    UL-SCH de-interleaver, must come back as the reference's srslte_dlsch_decode2 results (decode_tb is shared by both
+    directions, sch.c:1058-1062), g_bits must hold the de-interleaved LLRs, K_segm must be set.  (With multiplexed
+    ACK / RI / CQI the entry needs the reference's UCI decoders: tests/test_gpu_relink.py.)"""
+    L.srslte_ulsch_decode.argtypes = [C.c_void_p, C.c_void_p, _i16p, _i16p, C.c_void_p, _u8p, C.c_void_p]
+    L.srslte_ulsch_decode.restype = C.c_int
+    L.srslte_softbuffer_rx_init.argtypes = [C.POINTER(SoftbufferRx), C.c_uint32]
+    L.srslte_softbuffer_rx_reset_tbs.argtypes = [C.POINTER(SoftbufferRx), C.c_uint32]
+    L.srslte_softbuffer_rx_reset_tbs.restype = None
+    L.srslte_softbuffer_rx_free.argtypes = [C.POINTER(SoftbufferRx)]
+    L.srslte_softbuffer_rx_free.restype = None
+    g = golden["tb_vectors"]
+    P = ol.port()
+    sb = SoftbufferRx()
+    assert L.srslte_softbuffer_rx_init(C.byref(sb), 100) == 0
+    q = np.zeros(490792 + 7480, np.uint8)             # srslte_sch_t
+    ran = 0
+    for c in sorted({k.split("_")[0] for k in g if k.startswith("t")}, key=lambda s: int(s[1:])):
+        tbs, qm, G, max_it = (int(x) for x in g[f"{c}_par"])
+        cols = next((n for n in (12, 11, 10, 9) if (G // qm) % n == 0), 0)
+        if G % qm or not cols:
+            continue
+        rows = G // qm // cols
+        seg = ol.PortCbsegm()
+        P.port_cbsegm(C.byref(seg), tbs)
+        q[:4].view(np.uint32)[0] = max_it
+        L.srslte_softbuffer_rx_reset_tbs(C.byref(sb), tbs)
+        for rv in (0, 2):
+            llr = g[f"{c}_rv{rv}_llr"][:G]
+            # channel order: the matrix is sent column by column
+            chan = np.ascontiguousarray(llr.reshape(rows, cols, qm).transpose(1, 0, 2)).reshape(-1).copy()
+            cfg = np.zeros(520, np.uint8)            # srslte_pusch_cfg_t, offsets: tests/test_compat_abi.py
+            w = cfg.view(np.uint32)
+            w[416 // 4] = cols                       # grant.nof_symb
+            w[420 // 4 + 0] = {2: 1, 4: 2, 6: 3}[qm]  # grant.tb.mod
+            w[420 // 4 + 1] = tbs                    # grant.tb.tbs
+            w[420 // 4 + 2] = rv                     # grant.tb.rv
+            w[420 // 4 + 3] = G                      # grant.tb.nof_bits
+            cfg[504:512].view(np.uint64)[0] = C.addressof(sb)   # softbuffers.rx
+            out = np.zeros(tbs // 8 + 8, np.uint8)
+            gb = np.zeros(G + 8, np.int16)
+            rc = L.srslte_ulsch_decode(q.ctypes.data, cfg.ctypes.data, chan, gb, None, out, None)
+            want_rc, want_its = (int(x) for x in g[f"{c}_rv{rv}_res"])
+            assert rc == want_rc, (c, rv)
+            assert round(float(q[4:8].view(np.float32)[0]) * seg.C) == want_its, (c, rv)   # q->avg_iterations
+            assert np.array_equal(out[: tbs // 8 + 3], g[f"{c}_rv{rv}_out"]), (c, rv)
+            assert np.array_equal(gb[:G], llr), (c, rv)
+            assert int(w[488 // 4]) == seg.C1 * seg.K1 + seg.C2 * seg.K2                  # cfg->K_segm
+            ran += 1
+    assert ran >= 4
+    L.srslte_softbuffer_rx_free(C.byref(sb))
