@@ -6,6 +6,8 @@
   config 3  65 536 x K=6144, at most 8 half iterations, CRC24B early termination, at harness -e 1.5 and -e 4.0
   config 4  all 188 LTE block sizes x 64 blocks in one mixed batch, 4 half iterations
   config 5  200 UL transport blocks (16QAM, mixed sizes) per 1 ms subframe, sustained subframes per second
+  frontend  soft demodulation + descrambling alone, through the UL-SCH de-interleaver and fused with rate
+            de-matching: kernel times
 
 Every case also decodes a small sample with the oracle (tests/oracle_libs.py: the scalar port; a CHECKER here, never
 timed) and compares bit for bit: "parity" in each entry.
@@ -273,4 +275,60 @@ def run_configs(pkg, ctx, torch, dev, stream, quick=False):
     c5["parity"] = bool(par5)
     c5["parity_sample"] = "every TB's bytes vs the transmitted payload"
     res["config5_200_ul_tbs_per_subframe"] = c5
+
+    # ---- the stage in front of the path: kernel times ----
+    try:
+        res["frontend_64qam"] = _frontend(pkg, ctx, torch, dev, ol, quick)
+    except Exception as e:  # never lose the line over an auxiliary entry
+        res["frontend_64qam"] = {"error": f"{type(e).__name__}: {e}"}
     return res
+
+
+def _frontend(pkg, ctx, torch, dev, ol, quick):
+    """Soft demodulation + descrambling of 1024 codewords x 15 000 64QAM symbols (config 2's codeword), alone, through the
+    UL-SCH de-interleaver, and fused with the rate de-matching of their 13 312 code blocks; device time of the kernels
+    from the library's own CUDA events.  Parity: two codewords against the oracle port."""
+    n_cw, nsym, qm = (128 if quick else 1024), 15000, 6
+    sym = torch.randn((n_cw, nsym, 2), device=dev, dtype=torch.float32) * 0.7
+    e = torch.zeros((n_cw, qm * nsym), dtype=torch.int16, device=dev)
+    cws = [dict(qm=qm, nof_symbols=nsym, c_init=1 + 7919 * i, sym_offset=i * nsym, llr_offset=i * qm * nsym) for i in range(n_cw)]
+
+    def ktimed(fn, reps=5):
+        fn(); ctx.synchronize()
+        ctx.enable_timing(True)
+        for _ in range(reps):
+            fn()
+        ctx.synchronize()
+        ms, _n = ctx.kernel_time(4)
+        ctx.enable_timing(False)
+        return ms / reps
+
+    torch.cuda.synchronize()
+    ms_plain = ktimed(lambda: ctx.demod_descramble_dev(cws, sym.data_ptr(), e.data_ptr()))
+    got = e[:2].cpu().numpy()
+    sym_h = sym[:2].cpu().numpy()
+    ok = all(np.array_equal(got[i], ol.port_demod_descramble(qm, sym_h[i].copy().view(np.complex64).reshape(-1), cws[i]["c_init"]))
+             for i in range(2))
+    cwu = [dict(c, ul_nof_symb=12) for c in cws]
+    ms_ul = ktimed(lambda: ctx.demod_descramble_dev(cwu, sym.data_ptr(), e.data_ptr()))
+    got = e[:2].cpu().numpy()
+    ok_ul = all(np.array_equal(got[i], ol.port_ulsch_deinterleave(
+        ol.port_demod_descramble(qm, sym_h[i].copy().view(np.complex64).reshape(-1), cws[i]["c_init"]), qm, 12)) for i in range(2))
+    wl = 18624
+    work = torch.zeros((n_cw * 13, wl), dtype=torch.int16, device=dev)
+    blocks = []
+    for i in range(n_cw):
+        rp = 0
+        for cb in range(13):
+            E = 6918 if cb <= 2 else 6924     # sch.c:324-334 for G = 90000, C = 13
+            blocks.append((5824, 0, i, rp, E, (i * 13 + cb) * wl))
+            rp += E
+    ms_fused = ktimed(lambda: ctx.demod_rm_rx_batch_dev(cws, blocks, sym.data_ptr(), work.data_ptr()))
+    byt = n_cw * nsym * (8 + 2 * qm)
+    return {"codewords": n_cw, "symbols_per_codeword": nsym, "qm": qm, "llrs": n_cw * nsym * qm,
+            "demod_descramble_ms": ms_plain, "demod_descramble_gbs": byt / ms_plain / 1e6,
+            "demod_descramble_frac_of_hbm_copy_rate": byt / ms_plain / 1e6 / 6536.7,
+            "demod_descramble_pusch_deinterleaver_ms": ms_ul,
+            "fused_with_rate_dematching_ms": ms_fused, "fused_code_blocks": len(blocks),
+            "timing": "library CUDA events around the kernels, 5 back-to-back launches",
+            "parity": bool(ok and ok_ul), "parity_sample": "2 codewords, plain and through the UL-SCH de-interleaver, vs the oracle port"}
