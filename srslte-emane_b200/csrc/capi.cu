@@ -109,6 +109,10 @@ struct srslte_b200_ctx {
   DevBuf<uint32_t> counters;           // 3 work counters + 1 fallback counter + 4 tier counters
   bool         force_exact = false;
   uint32_t     variant_bits = 0;       // srslte_b200_ctx_set_variant_bits
+  uint32_t     max_ctas    = 0;        // > 0: the decode kernels of this context never use more CTAs, and the A / E and
+                                       // checkpoint workspaces (one slot per resident warp) are sized for that many: the
+                                       // context behind a compat srslte_tdec_t decodes one block per call and needs one
+                                       // CTA's worth (0.8 MB) instead of the whole GPU's (about 260 MB)
   // schedule cache
   DevBuf<uint32_t> d_order;
   DevBuf<WorkItem> d_items;
@@ -217,6 +221,11 @@ int ensure_regime(srslte_b200_ctx* ctx, int ri)
   if (r.ready) return 0;
   r.W = ri == 0 ? 16 : ri == 1 ? 8 : 0;
   CU(tdec_geometry(r.W, ctx->device, &r.geo));
+  if (ctx->max_ctas && r.geo.blocks > (int)ctx->max_ctas) {  // both sizes are (CTAs x warps per CTA) slots of fixed size
+    r.geo.ws_ae_bytes  = r.geo.ws_ae_bytes / (size_t)r.geo.blocks * ctx->max_ctas;
+    r.geo.ws_chk_bytes = r.geo.ws_chk_bytes / (size_t)r.geo.blocks * ctx->max_ctas;
+    r.geo.blocks       = (int)ctx->max_ctas;
+  }
   CU(r.ws_ae.reserve(r.geo.ws_ae_bytes));
   CU(r.ws_chk.reserve(r.geo.ws_chk_bytes));
   r.ready = true;
@@ -998,10 +1007,11 @@ int srslte_b200_tdec_batch_host(srslte_b200_ctx_t* ctx, const srslte_b200_tdec_b
     const uint32_t first = p * piece;
     const uint32_t n     = std::min(piece, b->n_cb - first);
     const size_t   in_elems = (size_t)n * b->in_stride;
-    CU(ctx->d_in[s].reserve((size_t)piece * b->in_stride));
-    CU(ctx->d_out[s].reserve((size_t)piece * b->out_stride));
-    CU(ctx->d_nit[s].reserve(piece));
-    CU(ctx->d_crc[s].reserve(piece));
+    const uint32_t cap = std::min(piece, b->n_cb);  // a one-block call (compat srslte_tdec_t) does not take 151 MB
+    CU(ctx->d_in[s].reserve((size_t)cap * b->in_stride));
+    CU(ctx->d_out[s].reserve((size_t)cap * b->out_stride));
+    CU(ctx->d_nit[s].reserve(cap));
+    CU(ctx->d_crc[s].reserve(cap));
     // the buffers of slot s were last used by piece p-2
     if (p >= 2) {
       CU(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_comp[s], 0));
@@ -1970,6 +1980,7 @@ int srslte_tdec_init_manual(srslte_tdec_t* h, uint32_t max_long_cb, srslte_tdec_
     delete pv;
     return SRSLTE_ERROR;  // loud message already printed: no CPU fallback
   }
+  pv->ctx->max_ctas = 1;  // one code block per call
   pv->stage = static_cast<int16_t*>(srslte_b200_host_alloc(sizeof(int16_t) * (3 * (SRSLTE_TCOD_MAX_LEN_CB + 32) + 16)));
   pv->out   = static_cast<uint8_t*>(srslte_b200_host_alloc(SRSLTE_TCOD_MAX_LEN_CB / 8));
   if (!pv->stage || !pv->out) {
