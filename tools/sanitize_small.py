@@ -25,6 +25,21 @@ for qm, ul in ((2, 0), (4, 12), (6, 0), (8, 0)):
     E = qm * nsym // 2
     ctx.demod_rm_rx_batch_dev([dict(qm=qm, nof_symbols=nsym, c_init=77, ul_nof_symb=ul)],
                               [(1024, 0, 0, 0, E, 0), (1056, 2, 0, E, E, 18624)], s_d.data_ptr(), work.data_ptr())
+# the vector paths at their edges: a codeword that ends inside a group, a descrambled length that ends inside one,
+# several codewords packed on 128-bit boundaries at the very end of the buffers
+for qm in (2, 4, 6, 8):
+    cws, so, lo = [], 0, 0
+    for nsym, cut in ((1441, 0), (7, 3), (1000, 50), (250, 0)):
+        cws.append(dict(qm=qm, nof_symbols=nsym, c_init=99 + nsym, nof_bits=qm * nsym - cut, sym_offset=so, llr_offset=lo))
+        so = (so + nsym + 1) & ~1
+        lo = (lo + qm * nsym + 7) & ~7
+    # the last codeword ends exactly at the end of both buffers
+    s_d = torch.randn(2 * (cws[-1]["sym_offset"] + 250), dtype=torch.float32, device="cuda")
+    e_d = torch.zeros(cws[-1]["llr_offset"] + qm * 250, dtype=torch.int16, device="cuda")
+    ctx.demod_descramble_dev(cws, s_d.data_ptr(), e_d.data_ptr())
+    work = torch.zeros((2, 18624), dtype=torch.int16, device="cuda")
+    E = (qm * 250) // 2 // qm * qm
+    ctx.demod_rm_rx_batch_dev(cws, [(512, 0, 3, 0, E, 0), (512, 1, 3, E, qm * 250 - E, 18624)], s_d.data_ptr(), work.data_ptr())
 pool = ctx.harq_pool(2, 13)
 sym = ((rng.standard_normal(15000) + 1j * rng.standard_normal(15000)) * 0.8).astype(np.complex64)
 ctx.decode_tb_sym_batch(pool, [dict(tbs=75376, qm=6, rv=0, nof_e_bits=90000, softbuffer=0, c_init=5, symbols=sym)], 2)
