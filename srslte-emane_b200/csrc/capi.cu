@@ -1969,9 +1969,13 @@ int srslte_tdec_init_manual(srslte_tdec_t* h, uint32_t max_long_cb, srslte_tdec_
 {
   if (!h) return SRSLTE_ERROR;
   std::memset(h, 0, sizeof(*h));
-  if (dec_type != SRSLTE_TDEC_AUTO) {
-    // the manual modes select one specific CPU SIMD decoder; only the AUTO 16-bit behaviour is reproduced
-    fprintf(stderr, "srslte_b200: Error decoder %d not supported (AUTO only)\n", (int)dec_type);
+  // The manual modes pin one of the reference's CPU decoders (turbodecoder.c:158-199).  The three 16-bit ones AUTO itself
+  // uses are accepted; a handle made that way decodes the block sizes for which AUTO would pick the same decoder (the
+  // result is then the same by construction) and refuses the others in srslte_tdec_new_cb.  The non-windowed SSE
+  // decoder, NEON and the 8-bit decoders are not provided.
+  if (dec_type != SRSLTE_TDEC_AUTO && dec_type != SRSLTE_TDEC_GENERIC && dec_type != SRSLTE_TDEC_SSE_WINDOW &&
+      dec_type != SRSLTE_TDEC_AVX_WINDOW) {
+    fprintf(stderr, "srslte_b200: Error decoder %d not supported (AUTO, GENERIC, SSE_WINDOW, AVX_WINDOW)\n", (int)dec_type);
     return SRSLTE_ERROR;
   }
   if (max_long_cb > SRSLTE_TCOD_MAX_LEN_CB) return SRSLTE_ERROR;
@@ -1991,9 +1995,13 @@ int srslte_tdec_init_manual(srslte_tdec_t* h, uint32_t max_long_cb, srslte_tdec_
   h->max_long_cb      = max_long_cb;
   h->dec_type         = dec_type;
   h->dec16_hdlr[0]    = pv;
-  h->nof_blocks16[0]  = 1;   // what the reference's three AUTO decoders report (generic, 8-window, 16-window)
-  h->nof_blocks16[1]  = 8;
-  h->nof_blocks16[2]  = 16;
+  if (dec_type == SRSLTE_TDEC_AUTO) {
+    h->nof_blocks16[0] = 1;  // what the reference's three AUTO decoders report (generic, 8-window, 16-window)
+    h->nof_blocks16[1] = 8;
+    h->nof_blocks16[2] = 16;
+  } else {
+    h->nof_blocks16[0] = dec_type == SRSLTE_TDEC_GENERIC ? 1 : dec_type == SRSLTE_TDEC_SSE_WINDOW ? 8 : 16;
+  }
   h->current_cbidx    = -1;
   h->current_llr_type = SRSLTE_TDEC_16;
   return SRSLTE_SUCCESS;
@@ -2026,6 +2034,16 @@ int srslte_tdec_new_cb(srslte_tdec_t* h, uint32_t long_cb)
     fprintf(stderr, "Invalid CB length %d\n", long_cb);
     return -1;
   }
+  if (h->dec_type != SRSLTE_TDEC_AUTO) {
+    // a manually selected decoder: only where AUTO selects the same one (srslte_tdec_autoimp_get_subblocks)
+    const int pinned = h->nof_blocks16[0] == 1 ? 0 : h->nof_blocks16[0];
+    if (nof_windows(long_cb) != pinned) {
+      fprintf(stderr, "srslte_b200: decoder %d (%d windows) is not provided for CB length %d (AUTO uses %d windows there)\n",
+              (int)h->dec_type, pinned, long_cb, nof_windows(long_cb));
+      h->current_cbidx = -1;
+      return -1;
+    }
+  }
   return 0;
 }
 
@@ -2051,7 +2069,7 @@ void srslte_tdec_iteration(srslte_tdec_t* h, int16_t* input, uint8_t* output)
   const uint32_t K  = h->current_long_cb;
   const int      W  = nof_windows(K);
   const bool natural = h->force_not_sb || W == 0;
-  h->current_dec     = W == 16 ? 2 : W == 8 ? 1 : 0;
+  h->current_dec     = h->dec_type != SRSLTE_TDEC_AUTO ? 0 : W == 16 ? 2 : W == 8 ? 1 : 0;
   const int16_t* src = input;
   if (natural) {
     // the reference latches the input at the first iteration (extract_input) and ignores it afterwards
@@ -2073,7 +2091,7 @@ int srslte_tdec_run_all(srslte_tdec_t* h, int16_t* input, uint8_t* output, uint3
 {
   if (srslte_tdec_new_cb(h, long_cb)) return SRSLTE_ERROR;
   const int W    = nof_windows(long_cb);
-  h->current_dec = W == 16 ? 2 : W == 8 ? 1 : 0;
+  h->current_dec = h->dec_type != SRSLTE_TDEC_AUTO ? 0 : W == 16 ? 2 : W == 8 ? 1 : 0;
   const uint32_t n = nof_iterations ? nof_iterations : 1;  // do { } while (n_iter < nof_iterations)
   if (tdec_decode(h, input, output, n)) return SRSLTE_ERROR;
   h->n_iter = (int)n;

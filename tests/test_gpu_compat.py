@@ -50,6 +50,32 @@ def test_turbodecoder_test_flow(L, vec):
     assert h.raw == b"\x00" * 18264          # srslte_tdec_free zeroes the handle like the reference
 
 
+def test_manual_decoder_selection(L, vec):
+    """srslte_tdec_init_manual (turbodecoder.c:146-260, turbodecoder_test -d): the three 16-bit decoders AUTO itself uses
+    can be pinned; a pinned handle decodes the block sizes for which AUTO picks the same decoder (same result) and
+    refuses the others; the non-windowed SSE decoder and the 8-bit decoders are refused at init."""
+    L.srslte_tdec_init_manual.argtypes = [C.c_void_p, C.c_uint32, C.c_int]
+    GENERIC, SSE, SSE_WINDOW, AVX_WINDOW, SSE8_WINDOW = 1, 2, 3, 5, 6
+    for typ, good, bad in ((GENERIC, (40, 400), (408, 6144)), (SSE_WINDOW, (408, 512, 800), (400, 816)),
+                           (AVX_WINDOW, (816, 5824, 6144), (800, 40))):
+        h = C.create_string_buffer(18264)
+        assert L.srslte_tdec_init_manual(h, 6144, typ) == 0
+        L.srslte_tdec_force_not_sb(h)
+        for K in good:
+            _bits, llr = vec.make_blocks(2, K, vec.harness_sigma(3.0), 100, seed=K + typ)
+            for i in range(2):
+                out = np.zeros(K // 8, np.uint8)
+                assert L.srslte_tdec_run_all(h, llr[i].copy(), out, 4, K) == 0
+                assert np.array_equal(out, ol.port_run_all(llr[i:i + 1], K, 4)[0]), (typ, K, i)
+        for K in bad:
+            assert L.srslte_tdec_run_all(h, np.zeros(3 * K + 12, np.int16), np.zeros(K // 8, np.uint8), 2, K) == -1
+            assert L.srslte_tdec_new_cb(h, K) == -1
+        L.srslte_tdec_free(h)
+    for typ in (SSE, SSE8_WINDOW, 99):
+        h = C.create_string_buffer(18264)
+        assert L.srslte_tdec_init_manual(h, 6144, typ) != 0
+
+
 def test_iteration_by_iteration_sub_block_input(L, vec):
     """sch.c style: srslte_tdec_new_cb, then one srslte_tdec_iteration per call on the soft-buffer layout."""
     h = C.create_string_buffer(18264)

@@ -64,7 +64,10 @@ def _tdec_test_numbers(text):
                                   ("-n", 30, "-s", 7, "-l", 1008),                               # the test's default sweep
                                   ("-n", 20, "-s", 3, "-e", "0.5", "-l", 504),
                                   ("-n", 20, "-s", 5, "-e", "1.0", "-l", 40),
-                                  ("-n", 5, "-k")])                                             # the test's known code word
+                                  ("-n", 5, "-k"),                                              # the test's known code word
+                                  ("-n", 10, "-s", 2, "-e", "1.5", "-l", 6144, "-i", 4, "-d", 5),  # pinned: 16-window AVX2
+                                  ("-n", 10, "-s", 4, "-e", "1.0", "-l", 504, "-d", 3),          # pinned: 8-window SSE
+                                  ("-n", 10, "-s", 6, "-e", "1.0", "-l", 40, "-d", 1)])         # pinned: generic
 def test_reference_turbodecoder_test_relinked(args):
     ref = _tdec_test_numbers(_run("turbodecoder_test", *args))
     got = _tdec_test_numbers(_run("turbodecoder_test_b200", *args))
