@@ -2471,7 +2471,7 @@ extern "C" int srslte_ulsch_decode(void* qv, srslte_pusch_cfg_t* cfg, int16_t* q
   static const uint32_t mod_bits[5] = {1, 2, 4, 6, 8};  // srslte_mod_bits_x_symbol (phy_common.c)
   const uint32_t nb_q = cfg->grant.tb.nof_bits;
   const uint32_t Qm   = cfg->grant.tb.mod < 5 ? mod_bits[cfg->grant.tb.mod] : 0;
-  if (!Qm) return SRSLTE_ERROR_INVALID_INPUTS;
+  if (!Qm || cfg->grant.nof_symb == 0) return SRSLTE_ERROR_INVALID_INPUTS;  // (the reference divides by nof_symb)
   cfg->K_segm = seg.C1 * seg.K1 + seg.C2 * seg.K2;
 
   srslte_cqi_cfg_t& cqi      = cfg->uci_cfg.cqi;

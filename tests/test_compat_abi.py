@@ -165,3 +165,8 @@ def test_ulsch_decode_without_the_reference_uci_decoders_fails_loudly(pkg, capfd
     assert "8-bit" in capfd.readouterr().err
     q[8] = 0
     assert L.srslte_ulsch_decode(None, cfg, llr, g, seq, data, uci) == -2
+    put32(cfg, 416, 0)                         # grant.nof_symb = 0: no interleaver matrix
+    assert L.srslte_ulsch_decode(q, cfg, llr, g, seq, data, uci) == -2
+    put32(cfg, 416, 12)
+    put32(cfg, 420 + 0, 7)                     # not a modulation
+    assert L.srslte_ulsch_decode(q, cfg, llr, g, seq, data, uci) == -2
