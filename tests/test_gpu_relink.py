@@ -93,3 +93,26 @@ def test_reference_ulsch_api_relinked(args):
     got = _run("ulsch_harness_b200", *args)
     assert "digest" in ref and ref.count("\n") > args[0]
     assert got == ref
+
+
+def test_ulsch_harness_drives_the_reference_correctly():
+    """not a GPU test: the all-reference build of oracle/ulsch_harness.c decodes what it encoded -- every transport block
+    ends with ret 0 and the transmitted bytes, the configured HARQ-ACK bits and the 1-bit RI come back, the CQI CRC holds --
+    so the comparison of the two builds above compares meaningful PUSCH decodes, not two identical failures"""
+    out = _run("ulsch_harness_ref", 14, 0.45, 10)
+    rows = [l for l in out.splitlines() if l.startswith("tb ")]
+    last = {}
+    for l in rows:
+        last[int(l.split()[1])] = l
+    assert len(last) == 14 and len(rows) > 14          # some blocks needed a retransmission
+    for t, l in last.items():
+        m = re.search(r"ack (\d) ri (\d) cqi (\d): ret\s+(-?\d+) noi [\d.]+ match (\d) .*\| ack (\d)(\d)/(\d)(\d) ri (\d+)/(\d+) cqi \d+ crc (\d)", l)
+        assert m, l
+        nof_ack, ri_len, cqi_mode, ret, match = (int(m.group(i)) for i in range(1, 6))
+        assert ret == 0 and match == 1, l
+        rx_ack, tx_ack = (int(m.group(6)), int(m.group(7))), (int(m.group(8)), int(m.group(9)))
+        assert rx_ack[:nof_ack] == tx_ack[:nof_ack], l
+        if ri_len == 1:
+            assert int(m.group(10)) == int(m.group(11)), l
+        if cqi_mode == 2:                              # the long CQI carries a CRC
+            assert int(m.group(12)) == 1, l
