@@ -170,3 +170,20 @@ def test_ulsch_decode_without_the_reference_uci_decoders_fails_loudly(pkg, capfd
     put32(cfg, 416, 12)
     put32(cfg, 420 + 0, 7)                     # not a modulation
     assert L.srslte_ulsch_decode(q, cfg, llr, g, seq, data, uci) == -2
+
+
+def test_manual_decoder_types_that_are_not_provided_are_refused(pkg, capfd):
+    """srslte_tdec_init_manual: the non-windowed SSE decoder, NEON and the 8-bit decoders are refused before any device
+    is touched; without a GPU the accepted types fail loudly too (no CPU fallback)."""
+    import ctypes as C
+    import torch
+    L = pkg.lib()
+    L.srslte_tdec_init_manual.argtypes = [C.c_void_p, C.c_uint32, C.c_int]
+    for typ in (2, 4, 6, 7, 8, 42):            # SSE, NEON_WINDOW, SSE8_WINDOW, AVX8_WINDOW, NOF_IMP, junk
+        h = C.create_string_buffer(18264)
+        assert L.srslte_tdec_init_manual(h, 6144, typ) == -1
+        assert "not supported" in capfd.readouterr().err
+    if not torch.cuda.is_available():
+        for typ in (0, 1, 3, 5):               # AUTO, GENERIC, SSE_WINDOW, AVX_WINDOW
+            h = C.create_string_buffer(18264)
+            assert L.srslte_tdec_init_manual(h, 6144, typ) == -1
